@@ -1,0 +1,178 @@
+/*
+ * k2b200.h — C ABI of libk2b200.so: the transducer-search hot path of
+ * manyeyes/K2TransducerAsr as hand-written sm_100a CUDA.
+ *
+ * Every entry point replaces one managed->native crossing (or one managed search loop) of the
+ * reference. Citations "ref:" are file:line under the reference tree (K2TransducerAsr/...).
+ *
+ * Rules of the boundary (INTEGRATION.md shows the C# P/Invoke side):
+ *   - blittable scalars and plain pointers only; no callbacks, no structs by value;
+ *   - the caller owns every in/out buffer; the library owns all device memory;
+ *   - every call returns an int status (K2B_OK == 0); k2b_last_error() gives the text;
+ *   - a handle is bound to one CUDA device and one CUDA stream and is NOT thread-safe
+ *     (the reference recognizers are unsynchronised too: ref OfflineRecognizer.cs:77-91);
+ *   - token ids cross the boundary as int64 because the reference carries them as
+ *     Int64[] / List<Int64> (ref IOfflineProj.cs:44, OfflineStream.cs:14); timestamps and
+ *     counts are int32 (ref OfflineStream.cs:15).
+ *   - entry points without a suffix take HOST pointers and are synchronous (H2D copy, kernels,
+ *     D2H copy, stream sync inside the call). Entry points ending in _dev take DEVICE pointers,
+ *     enqueue on the handle's stream and do NOT synchronise (call k2b_sync()).
+ *   - there is no CPU fallback anywhere behind this header.
+ */
+#ifndef K2B200_H_
+#define K2B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define K2B_ABI_VERSION 1
+
+#if defined(_WIN32)
+#define K2B_API __declspec(dllexport)
+#else
+#define K2B_API __attribute__((visibility("default")))
+#endif
+
+/* status codes */
+#define K2B_OK 0
+#define K2B_ERR_INVALID 1   /* bad argument / shape / capacity              */
+#define K2B_ERR_CUDA 2      /* a CUDA runtime or driver call failed (sticky) */
+#define K2B_ERR_STATE 3     /* weights not loaded, handle poisoned, ...      */
+#define K2B_ERR_UNSUPPORTED 4
+
+/* greedy_offline modes */
+#define K2B_GREEDY_SINGLE 0        /* ref OfflineRecognizer.cs:93-187 (B must be 1; 1000-symbol cap)   */
+#define K2B_GREEDY_BATCH_COMPAT 1  /* ref OfflineRecognizer.cs:189-303 incl. the whole-batch decoder   */
+                                   /* refresh on any emission                              */
+#define K2B_GREEDY_PER_STREAM 2    /* every stream behaves as SINGLE regardless of its batch neighbours */
+
+/* arithmetic of the three GEMMs (encoder_proj, decoder_proj, joiner output) */
+#define K2B_PREC_FP32 0    /* CUDA-core FMA, fp32 operands                                   */
+#define K2B_PREC_BF16X3 1  /* tcgen05, operands split hi+lo bf16, 3 MMAs, fp32 accumulate    */
+#define K2B_PREC_BF16 2    /* tcgen05, operands rounded to bf16, fp32 accumulate             */
+
+/* negative token id in the decoder context (ref OfflineRecognizer.cs:105 seeds {-1, blank}) */
+#define K2B_NEGID_MASK 0   /* embedding row is zero (zipformer exports)        */
+#define K2B_NEGID_WRAP 1   /* ONNX Gather semantics: -1 addresses row V-1      */
+
+typedef struct k2b_handle k2b_handle;
+
+/* Configuration = the ONNX custom-metadata contract the reference reads
+ * (ref OfflineModel.cs:31-46: context_size, vocab_size, joiner_dim; ids ref OfflineModel.cs:18-20). */
+typedef struct k2b_config {
+  int32_t struct_size;   /* = sizeof(k2b_config); rejects ABI drift                   */
+  int32_t device;        /* CUDA device ordinal                                       */
+  int32_t vocab_size;    /* V                                                         */
+  int32_t joiner_dim;    /* J  (the reference hard-codes 512 offline, Q8)             */
+  int32_t decoder_dim;   /* D                                                         */
+  int32_t encoder_dim;   /* E, raw encoder width fed to encoder_proj; 0 = none        */
+  int32_t context_size;  /* must be 2 (ref OfflineRecognizer.cs:105-110, Q9)          */
+  int32_t blank_id;      /* 0 */
+  int32_t sos_eos_id;    /* 1 */
+  int32_t unk_id;        /* 2 */
+  int32_t max_streams;   /* largest B of any call                                     */
+  int32_t max_frames;    /* largest T of any call                                     */
+  int32_t max_beam;      /* largest K of any call (<= 8)                              */
+  int32_t neg_id_mode;   /* K2B_NEGID_*                                               */
+  int32_t precision;     /* K2B_PREC_*                                                */
+  int32_t reserved;      /* 0                                                         */
+} k2b_config;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+K2B_API int32_t k2b_abi_version(void);
+/* replaces: new OfflineModel/OnlineModel + proj construction (ref OfflineRecognizer.cs:30-53). */
+K2B_API int32_t k2b_create(const k2b_config* cfg, k2b_handle** out);
+/* replaces: IOfflineProj.Dispose / IOnlineProj.Dispose (ref IOfflineProj.cs:47). NULL is a no-op. */
+K2B_API int32_t k2b_destroy(k2b_handle* h);
+/* UTF-8 text of the last failure on this handle (h == NULL: last k2b_create failure). */
+K2B_API const char* k2b_last_error(const k2b_handle* h);
+
+/* Host fp32 row-major weights = the tensors inside decoder.onnx / joiner.onnx / encoder_proj
+ * (ref _decoderSession/_joinerSession construction, OfflineModel.cs:84-118):
+ *   emb [V,D]; conv_w [D,4,ctx] (Conv1d groups=D/4, no bias); dec_proj_w [J,D], dec_proj_b [J];
+ *   enc_proj_w [J,E], enc_proj_b [J] (NULL when E == 0); out_w [V,J], out_b [V].            */
+K2B_API int32_t k2b_load_weights(k2b_handle* h, const float* emb, const float* conv_w,
+                         const float* dec_proj_w, const float* dec_proj_b,
+                         const float* enc_proj_w, const float* enc_proj_b,
+                         const float* out_w, const float* out_b);
+/* switch K2B_PREC_* after creation (weights keep all derived copies). */
+K2B_API int32_t k2b_set_precision(k2b_handle* h, int32_t precision);
+/* Make the handle launch on a caller-owned cudaStream_t (e.g. torch's current stream); NULL
+ * restores the handle's own stream. */
+K2B_API int32_t k2b_set_stream(k2b_handle* h, void* cuda_stream);
+K2B_API int32_t k2b_sync(k2b_handle* h);
+/* number of this library's kernels launched on the handle since creation / last reset. */
+K2B_API int64_t k2b_launch_count(const k2b_handle* h);
+K2B_API int32_t k2b_reset_launch_count(k2b_handle* h);
+/* When on, the dominant GEMM (joiner) of every step is bracketed with CUDA events on the launch
+ * stream; k2b_profile_read returns launches seen and their summed device time. */
+K2B_API int32_t k2b_profile_enable(k2b_handle* h, int32_t on);
+K2B_API int32_t k2b_profile_read(k2b_handle* h, int64_t* n_launches, double* total_ms);
+
+/* ---- fine-grained: 1:1 with the proj seam ---------------------------------------------------- */
+/* replaces: IOfflineProj/IOnlineProj.DecoderProj (ref OfflineProjOfTransducer.cs:93-123 and the
+ * four identical online copies). y [n,ctx] int64; y == NULL means n x {-1, blank}
+ * (ref OfflineProjOfTransducer.cs:97-110). out [n,J].                                          */
+K2B_API int32_t k2b_decoder_proj(k2b_handle* h, const int64_t* y, int32_t n, float* out);
+K2B_API int32_t k2b_decoder_proj_dev(k2b_handle* h, const int64_t* y, int32_t n, float* out);
+/* replaces: JoinerProj (ref OfflineProjOfTransducer.cs:125-152). enc, dec [n,J]; logits [n,V]. */
+K2B_API int32_t k2b_joiner_proj(k2b_handle* h, const float* enc, const float* dec, int32_t n, float* logits);
+K2B_API int32_t k2b_joiner_proj_dev(k2b_handle* h, const float* enc, const float* dec, int32_t n, float* logits);
+/* replaces: the encoder_proj Linear that upstream folds into encoder.onnx, i.e. the tail of
+ * EncoderProj (ref OfflineProjOfTransducer.cs:48-92). raw [n,E]; out [n,J].                    */
+K2B_API int32_t k2b_encoder_proj(k2b_handle* h, const float* raw, int32_t n, float* out);
+K2B_API int32_t k2b_encoder_proj_dev(k2b_handle* h, const float* raw, int32_t n, float* out);
+
+/* ---- fused search loops: 1:1 with the Forward* delegates ------------------------------------- */
+/* All fused calls write only the symbols APPENDED by this call (the reference's list seeds, e.g.
+ * {-1, blank} or the 2B blanks of Q5, are re-created by the host shim). tokens/ts are [B,cap]
+ * row-major, n_out [B]; cap >= T is required (at most one symbol per frame).
+ * `enc` is [B,T,J] already projected when enc_is_raw == 0, or raw [B,T,E] (then encoder_proj
+ * runs first, on device) when enc_is_raw != 0.                                                  */
+
+/* replaces: ForwardGreedySearch / ForwardBatchGreedySearch (ref OfflineRecognizer.cs:93-303).
+ * ts = frame index t (ref :164, :271).                                                          */
+K2B_API int32_t k2b_greedy_offline(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t T,
+                           int32_t mode, int64_t* tokens, int32_t* ts, int32_t* n_out, int32_t cap);
+K2B_API int32_t k2b_greedy_offline_dev(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t T,
+                               int32_t mode, int64_t* tokens, int32_t* ts, int32_t* n_out, int32_t cap);
+
+/* replaces: OnlineRecognizer.ForwardBatchGreedySearch for one chunk (ref OnlineRecognizer.cs:85-219).
+ * hyp_inout [B,ctx] = OnlineStream.Hyp in, last ctx tokens out (ref :109, :208). Emission mask is
+ * {blank, unk, 1} (ref :181); ts is chunk-local (ref :184).                                     */
+K2B_API int32_t k2b_greedy_online_chunk(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t Tc,
+                                int64_t* hyp_inout, int64_t* tokens, int32_t* ts, int32_t* n_out, int32_t cap);
+K2B_API int32_t k2b_greedy_online_chunk_dev(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t Tc,
+                                    int64_t* hyp_inout, int64_t* tokens, int32_t* ts, int32_t* n_out, int32_t cap);
+
+/* modified_beam_search: ABSENT from the reference (only the dead maxActivePaths argument,
+ * ref OnlineRecognizer.cs:19); semantics are icefall's, restated in oracle/k2_oracle.py (A.5).
+ * Output = best hypothesis per stream by log_prob/len (len counts the 2 seed entries);
+ * score [B] = its un-normalised log-prob.                                                       */
+K2B_API int32_t k2b_modified_beam_search(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t T,
+                                 int32_t K, int64_t* tokens, int32_t* ts, int32_t* n_out, float* score,
+                                 int32_t cap);
+K2B_API int32_t k2b_modified_beam_search_dev(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t T,
+                                     int32_t K, int64_t* tokens, int32_t* ts, int32_t* n_out, float* score,
+                                     int32_t cap);
+
+/* replaces: ForwardGreedySearchCTC / ForwardBatchGreedySearchCTC (ref OfflineRecognizer.cs:305-430)
+ * and the online variant (ref OnlineRecognizer.cs:220-319). logp [B,T,V]; V is an argument because
+ * the reference takes it from tokens.txt (ref :325). frame_offset [B] or NULL (= 0) is added to
+ * ts (ref :349). prev_inout [B] or NULL: previous frame's argmax carried across calls (NULL = the
+ * reference's per-call reset to -1, Q10). trailing_blank_inout [B] or NULL (ref :337-344).
+ * Needs no weights.                                                                             */
+K2B_API int32_t k2b_ctc_greedy(k2b_handle* h, const float* logp, int32_t B, int32_t T, int32_t V, int32_t blank,
+                       const int32_t* frame_offset, int64_t* prev_inout, int64_t* tokens, int32_t* ts,
+                       int32_t* n_out, int32_t* trailing_blank_inout, int32_t cap);
+K2B_API int32_t k2b_ctc_greedy_dev(k2b_handle* h, const float* logp, int32_t B, int32_t T, int32_t V, int32_t blank,
+                           const int32_t* frame_offset, int64_t* prev_inout, int64_t* tokens, int32_t* ts,
+                           int32_t* n_out, int32_t* trailing_blank_inout, int32_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* K2B200_H_ */

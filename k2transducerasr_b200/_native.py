@@ -1,0 +1,288 @@
+"""ctypes binding of libk2b200.so — the Python stand-in for the C# P/Invoke layer (`NativeMethods`, see
+INTEGRATION.md). It declares exactly the entry points of include/k2b200.h and raises if the shared
+library is missing: there is no CPU fallback and no path around the CUDA library."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from pathlib import Path
+from typing import Optional, Sequence
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libk2b200.so"
+HEADER_PATH = PKG.parent / "include" / "k2b200.h"
+
+K2B_OK, K2B_ERR_INVALID, K2B_ERR_CUDA, K2B_ERR_STATE, K2B_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
+GREEDY_SINGLE, GREEDY_BATCH_COMPAT, GREEDY_PER_STREAM = 0, 1, 2
+PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
+NEGID_MASK, NEGID_WRAP = 0, 1
+PREC_NAMES = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
+
+
+class K2bError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"libk2b200 status {status}: {message}")
+        self.status = status
+        self.message = message
+
+
+class K2bConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "struct_size", "device", "vocab_size", "joiner_dim", "decoder_dim", "encoder_dim", "context_size",
+        "blank_id", "sos_eos_id", "unk_id", "max_streams", "max_frames", "max_beam", "neg_id_mode",
+        "precision", "reserved")]
+
+
+_P = C.c_void_p
+_I = C.c_int32
+_SIGS = {
+    "k2b_abi_version": (C.c_int32, []),
+    "k2b_create": (C.c_int32, [C.POINTER(K2bConfig), C.POINTER(_P)]),
+    "k2b_destroy": (C.c_int32, [_P]),
+    "k2b_last_error": (C.c_char_p, [_P]),
+    "k2b_load_weights": (C.c_int32, [_P] + [_P] * 8),
+    "k2b_set_precision": (C.c_int32, [_P, _I]),
+    "k2b_set_stream": (C.c_int32, [_P, _P]),
+    "k2b_sync": (C.c_int32, [_P]),
+    "k2b_launch_count": (C.c_int64, [_P]),
+    "k2b_reset_launch_count": (C.c_int32, [_P]),
+    "k2b_profile_enable": (C.c_int32, [_P, _I]),
+    "k2b_profile_read": (C.c_int32, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "k2b_decoder_proj": (C.c_int32, [_P, _P, _I, _P]),
+    "k2b_decoder_proj_dev": (C.c_int32, [_P, _P, _I, _P]),
+    "k2b_joiner_proj": (C.c_int32, [_P, _P, _P, _I, _P]),
+    "k2b_joiner_proj_dev": (C.c_int32, [_P, _P, _P, _I, _P]),
+    "k2b_encoder_proj": (C.c_int32, [_P, _P, _I, _P]),
+    "k2b_encoder_proj_dev": (C.c_int32, [_P, _P, _I, _P]),
+    "k2b_greedy_offline": (C.c_int32, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _I]),
+    "k2b_greedy_offline_dev": (C.c_int32, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _I]),
+    "k2b_greedy_online_chunk": (C.c_int32, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _I]),
+    "k2b_greedy_online_chunk_dev": (C.c_int32, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _I]),
+    "k2b_modified_beam_search": (C.c_int32, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I]),
+    "k2b_modified_beam_search_dev": (C.c_int32, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I]),
+    "k2b_ctc_greedy": (C.c_int32, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I]),
+    "k2b_ctc_greedy_dev": (C.c_int32, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I]),
+}
+
+
+def header_symbols() -> list[str]:
+    """Every function include/k2b200.h declares (used by the ABI test)."""
+    text = HEADER_PATH.read_text()
+    return sorted(set(re.findall(r"K2B_API\s+[\w\s\*]+?\b(k2b_\w+)\s*\(", text)))
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libk2b200.so (built in-tree by k2transducerasr_b200.build). Raises when absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise FileNotFoundError(
+            f"{LIB_PATH} is missing: build it with `python -m k2transducerasr_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback for this path.")
+    handle = C.CDLL(os.fspath(LIB_PATH))
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(handle, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = handle
+    return _lib
+
+
+def _ptr(a) -> Optional[int]:
+    """Host numpy array -> address; int -> device/host address as is; None -> NULL."""
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return int(a)
+    if isinstance(a, np.ndarray):
+        if not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):  # torch tensor (device or pinned host memory)
+        return int(a.data_ptr())
+    raise TypeError(type(a))
+
+
+class Handle:
+    """Owns one k2b_handle (one device, one stream; not thread-safe)."""
+
+    def __init__(self, *, vocab_size: int, joiner_dim: int = 512, decoder_dim: int = 512, encoder_dim: int = 0,
+                 context_size: int = 2, blank_id: int = 0, sos_eos_id: int = 1, unk_id: int = 2, device: int = 0,
+                 max_streams: int = 0, max_frames: int = 0, max_beam: int = 4, neg_id_mode: int = NEGID_MASK,
+                 precision: int = PREC_FP32):
+        self._lib = lib()
+        self.cfg = K2bConfig(C.sizeof(K2bConfig), device, vocab_size, joiner_dim, decoder_dim, encoder_dim,
+                             context_size, blank_id, sos_eos_id, unk_id, max_streams, max_frames, max_beam,
+                             neg_id_mode, precision, 0)
+        self._h = _P()
+        st = self._lib.k2b_create(C.byref(self.cfg), C.byref(self._h))
+        if st != K2B_OK:
+            msg = self._lib.k2b_last_error(None)
+            self._h = _P()
+            raise K2bError(st, msg.decode() if msg else "k2b_create failed")
+        self._keep = []
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def _check(self, st: int):
+        if st != K2B_OK:
+            msg = self._lib.k2b_last_error(self._h)
+            raise K2bError(st, msg.decode() if msg else "")
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.k2b_destroy(self._h)
+            self._h = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def V(self): return self.cfg.vocab_size
+    @property
+    def J(self): return self.cfg.joiner_dim
+    @property
+    def E(self): return self.cfg.encoder_dim
+
+    def load_weights(self, w: dict):
+        def f(name):
+            a = w.get(name)
+            return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+        arrs = [f(k) for k in ("emb", "conv_w", "dec_proj_w", "dec_proj_b", "enc_proj_w", "enc_proj_b", "out_w", "out_b")]
+        self._check(self._lib.k2b_load_weights(self._h, *[_ptr(a) for a in arrs]))
+
+    def set_precision(self, precision):
+        if isinstance(precision, str):
+            precision = PREC_NAMES[precision]
+        self._check(self._lib.k2b_set_precision(self._h, precision))
+
+    def set_stream(self, cuda_stream: Optional[int]):
+        self._check(self._lib.k2b_set_stream(self._h, cuda_stream))
+
+    def sync(self):
+        self._check(self._lib.k2b_sync(self._h))
+
+    def launch_count(self) -> int:
+        return int(self._lib.k2b_launch_count(self._h))
+
+    def reset_launch_count(self):
+        self._check(self._lib.k2b_reset_launch_count(self._h))
+
+    def profile_enable(self, on: bool):
+        self._check(self._lib.k2b_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self):
+        n, ms = C.c_int64(0), C.c_double(0.0)
+        self._check(self._lib.k2b_profile_read(self._h, C.byref(n), C.byref(ms)))
+        return int(n.value), float(ms.value)
+
+    # -- fine-grained (host numpy in/out) ---------------------------------------------------------------
+    def decoder_proj(self, y: Optional[np.ndarray], n: Optional[int] = None) -> np.ndarray:
+        if y is not None:
+            y = np.ascontiguousarray(y, dtype=np.int64).reshape(-1, self.cfg.context_size)
+            n = y.shape[0]
+        out = np.empty((n, self.J), np.float32)
+        self._check(self._lib.k2b_decoder_proj(self._h, _ptr(y), n, _ptr(out)))
+        return out
+
+    def joiner_proj(self, enc: np.ndarray, dec: np.ndarray) -> np.ndarray:
+        enc = np.ascontiguousarray(enc, dtype=np.float32).reshape(-1, self.J)
+        dec = np.ascontiguousarray(dec, dtype=np.float32).reshape(-1, self.J)
+        if enc.shape != dec.shape:
+            raise ValueError("encoder_out and decoder_out must have the same number of rows")
+        n = enc.shape[0]
+        out = np.empty((n, self.V), np.float32)
+        self._check(self._lib.k2b_joiner_proj(self._h, _ptr(enc), _ptr(dec), n, _ptr(out)))
+        return out
+
+    def encoder_proj(self, raw: np.ndarray) -> np.ndarray:
+        raw = np.ascontiguousarray(raw, dtype=np.float32)
+        lead = raw.shape[:-1]
+        flat = raw.reshape(-1, self.E)
+        out = np.empty((flat.shape[0], self.J), np.float32)
+        self._check(self._lib.k2b_encoder_proj(self._h, _ptr(flat), flat.shape[0], _ptr(out)))
+        return out.reshape(*lead, self.J)
+
+    # -- fused (host numpy in/out) ------------------------------------------------------------------------
+    def _frames(self, enc: np.ndarray):
+        enc = np.ascontiguousarray(enc, dtype=np.float32)
+        if enc.ndim != 3:
+            raise ValueError("enc must be [B,T,width]")
+        B, T, W = enc.shape
+        if W != self.J and W != self.E:
+            raise ValueError(f"frame width {W} is neither joiner_dim {self.J} nor encoder_dim {self.E}")
+        raw = 1 if (W == self.E and W != self.J) else 0   # E == J is ambiguous: pass enc_is_raw explicitly
+        return enc, B, T, raw
+
+    @staticmethod
+    def _unpack(tokens, ts, n):
+        return [tokens[b, :n[b]].tolist() for b in range(len(n))], [ts[b, :n[b]].tolist() for b in range(len(n))]
+
+    def greedy_offline(self, enc: np.ndarray, mode: int, enc_is_raw: Optional[bool] = None):
+        enc, B, T, raw = self._frames(enc)
+        if enc_is_raw is not None:
+            raw = int(enc_is_raw)
+        cap = max(T, 1)
+        tokens = np.zeros((B, cap), np.int64); ts = np.zeros((B, cap), np.int32); n = np.zeros(B, np.int32)
+        self._check(self._lib.k2b_greedy_offline(self._h, _ptr(enc), raw, B, T, mode, _ptr(tokens), _ptr(ts), _ptr(n), cap))
+        return self._unpack(tokens, ts, n)
+
+    def greedy_online_chunk(self, enc: np.ndarray, hyp: np.ndarray, enc_is_raw: Optional[bool] = None):
+        enc, B, T, raw = self._frames(enc)
+        if enc_is_raw is not None:
+            raw = int(enc_is_raw)
+        hyp = np.ascontiguousarray(hyp, dtype=np.int64).reshape(B, self.cfg.context_size).copy()
+        cap = max(T, 1)
+        tokens = np.zeros((B, cap), np.int64); ts = np.zeros((B, cap), np.int32); n = np.zeros(B, np.int32)
+        self._check(self._lib.k2b_greedy_online_chunk(self._h, _ptr(enc), raw, B, T, _ptr(hyp), _ptr(tokens), _ptr(ts),
+                                                      _ptr(n), cap))
+        toks, tss = self._unpack(tokens, ts, n)
+        return toks, tss, hyp
+
+    def modified_beam_search(self, enc: np.ndarray, beam: int = 4, enc_is_raw: Optional[bool] = None):
+        enc, B, T, raw = self._frames(enc)
+        if enc_is_raw is not None:
+            raw = int(enc_is_raw)
+        cap = max(T, 1)
+        tokens = np.zeros((B, cap), np.int64); ts = np.zeros((B, cap), np.int32); n = np.zeros(B, np.int32)
+        score = np.zeros(B, np.float32)
+        self._check(self._lib.k2b_modified_beam_search(self._h, _ptr(enc), raw, B, T, beam, _ptr(tokens), _ptr(ts),
+                                                       _ptr(n), _ptr(score), cap))
+        toks, tss = self._unpack(tokens, ts, n)
+        return toks, tss, score
+
+    def ctc_greedy(self, logp: np.ndarray, blank: int = 0, frame_offset: Optional[Sequence[int]] = None,
+                   prev: Optional[np.ndarray] = None, trailing_blank: Optional[np.ndarray] = None):
+        logp = np.ascontiguousarray(logp, dtype=np.float32)
+        B, T, V = logp.shape
+        cap = max(T, 1)
+        tokens = np.zeros((B, cap), np.int64); ts = np.zeros((B, cap), np.int32); n = np.zeros(B, np.int32)
+        fo = None if frame_offset is None else np.ascontiguousarray(frame_offset, dtype=np.int32)
+        pv = None if prev is None else np.ascontiguousarray(prev, dtype=np.int64).copy()
+        tb = None if trailing_blank is None else np.ascontiguousarray(trailing_blank, dtype=np.int32).copy()
+        self._check(self._lib.k2b_ctc_greedy(self._h, _ptr(logp), B, T, V, blank, _ptr(fo), _ptr(pv), _ptr(tokens),
+                                             _ptr(ts), _ptr(n), _ptr(tb), cap))
+        toks, tss = self._unpack(tokens, ts, n)
+        return toks, tss, tb, pv
+
+    # -- raw pointer access for device-resident / pinned buffers (bench.py, dist.py) ---------------------------
+    def call(self, name: str, *args):
+        """Call an entry point with raw addresses (ints / torch tensors / numpy arrays / None)."""
+        fn = getattr(self._lib, name)
+        conv = [(_ptr(a) if (a is None or isinstance(a, np.ndarray) or hasattr(a, "data_ptr")) else a) for a in args]
+        self._check(fn(self._h, *conv))

@@ -1,0 +1,525 @@
+// The C ABI of libk2b200.so (include/k2b200.h): lifetime, weights, fine-grained proj calls and the host/device
+// wrappers of the fused search loops. No CPU fallback lives here: without a CUDA device k2b_create fails.
+#include <string.h>
+
+#include <mutex>
+
+#include "k2b_internal.h"
+
+namespace k2b {
+
+namespace {
+thread_local std::string g_create_error;
+
+__global__ void ctx_from_i64_kernel(const int64_t* __restrict__ y, int n, int blank, int32_t* __restrict__ ctx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (y != nullptr) {
+    ctx[2 * i] = (int32_t)y[2 * i];
+    ctx[2 * i + 1] = (int32_t)y[2 * i + 1];
+  } else {  // ref OfflineProjOfTransducer.cs:97-110: null input -> n x {-1, blank}
+    ctx[2 * i] = -1;
+    ctx[2 * i + 1] = blank;
+  }
+}
+
+void free_buf(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.bytes = 0;
+}
+
+int32_t enter(k2b_handle* h) {
+  if (h == nullptr) return K2B_ERR_INVALID;
+  if (h->poisoned) return K2B_ERR_STATE;
+  cudaError_t e = cudaSetDevice(h->cfg.device);
+  if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice", __FILE__, __LINE__);
+  return K2B_OK;
+}
+
+int32_t upload(k2b_handle* h, float** dst, const float* src, size_t n) {
+  if (*dst) { cudaFree(*dst); *dst = nullptr; }
+  K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(dst), n * sizeof(float)));
+  K2B_CUDA(h, cudaMemcpyAsync(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  return K2B_OK;
+}
+
+int32_t need_weights(k2b_handle* h) {
+  if (!h->weights_loaded) return fail(h, K2B_ERR_STATE, "weights not loaded (call k2b_load_weights first)");
+  return K2B_OK;
+}
+
+// raw [n,E] -> projected [n,J] on device (the encoder_proj Linear)
+int32_t encoder_proj_launch(k2b_handle* h, const float* raw, int n, float* out) {
+  if (h->cfg.encoder_dim <= 0 || h->enc_w == nullptr) return fail(h, K2B_ERR_STATE, "encoder_proj weights not loaded (E == 0)");
+  GemmArgs a;
+  a.M = n; a.N = h->cfg.joiner_dim; a.K = h->cfg.encoder_dim;
+  a.A = raw; a.W = h->enc_w; a.bias = h->enc_b; a.C = out;
+  return launch_gemm_simt(h, PRO_PLAIN, EPI_STORE, a);
+}
+
+// returns the device pointer of projected frames [B,T,J] for a fused call
+int32_t frames_for_search(k2b_handle* h, const float* enc_dev, int enc_is_raw, int B, int T, const float** out) {
+  if (!enc_is_raw) { *out = enc_dev; return K2B_OK; }
+  const size_t n = (size_t)B * T;
+  K2B_TRY(ensure(h, h->ws_encproj, sizeof(float) * n * h->cfg.joiner_dim));
+  K2B_TRY(encoder_proj_launch(h, enc_dev, (int)n, static_cast<float*>(h->ws_encproj.p)));
+  *out = static_cast<const float*>(h->ws_encproj.p);
+  return K2B_OK;
+}
+
+struct OutStage {
+  int64_t* tokens;
+  int32_t* ts;
+  int32_t* n;
+  float* score;
+  int64_t* hyp;
+  int32_t* aux_a;  // frame_offset / trailing
+  int32_t* aux_b;
+  int64_t* prev;
+};
+
+int32_t stage_out(k2b_handle* h, int B, int cap, OutStage* o) {
+  const size_t tok_b = (sizeof(int64_t) * (size_t)B * cap + 255) & ~size_t(255);
+  const size_t ts_b = (sizeof(int32_t) * (size_t)B * cap + 255) & ~size_t(255);
+  const size_t per_b = (sizeof(int64_t) * (size_t)B * 2 + 255) & ~size_t(255);
+  K2B_TRY(ensure(h, h->ws_out, tok_b + ts_b + 6 * per_b));
+  char* p = static_cast<char*>(h->ws_out.p);
+  o->tokens = reinterpret_cast<int64_t*>(p); p += tok_b;
+  o->ts = reinterpret_cast<int32_t*>(p); p += ts_b;
+  o->n = reinterpret_cast<int32_t*>(p); p += per_b;
+  o->score = reinterpret_cast<float*>(p); p += per_b;
+  o->hyp = reinterpret_cast<int64_t*>(p); p += per_b;
+  o->aux_a = reinterpret_cast<int32_t*>(p); p += per_b;
+  o->aux_b = reinterpret_cast<int32_t*>(p); p += per_b;
+  o->prev = reinterpret_cast<int64_t*>(p); p += per_b;
+  return K2B_OK;
+}
+
+int32_t check_search_args(k2b_handle* h, const void* enc, int B, int T, int cap, const void* tokens, const void* ts,
+                          const void* n_out, const char* who) {
+  if (B < 0 || T < 0) return fail(h, K2B_ERR_INVALID, std::string(who) + ": negative B or T");
+  if (B > 0 && T > 0 && enc == nullptr) return fail(h, K2B_ERR_INVALID, std::string(who) + ": enc is NULL");
+  if (B > 0 && (tokens == nullptr || ts == nullptr || n_out == nullptr))
+    return fail(h, K2B_ERR_INVALID, std::string(who) + ": output buffer is NULL");
+  if (cap < T) return fail(h, K2B_ERR_INVALID, std::string(who) + ": cap must be >= T (one symbol per frame at most)");
+  return K2B_OK;
+}
+
+}  // namespace
+
+int32_t fail(k2b_handle* h, int32_t code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return code;
+}
+
+int32_t cuda_fail(k2b_handle* h, cudaError_t e, const char* what, const char* file, int line) {
+  std::string m = std::string("CUDA error ") + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ") at " + what +
+                  " [" + file + ":" + std::to_string(line) + "]";
+  if (h) { h->err = m; h->poisoned = true; } else { g_create_error = m; }
+  return K2B_ERR_CUDA;
+}
+
+int32_t ensure(k2b_handle* h, DevBuf& b, size_t bytes) {
+  if (bytes <= b.bytes) return K2B_OK;
+  const size_t want = (bytes + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (b.p) { cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
+  K2B_CUDA(h, cudaMalloc(&b.p, want));
+  b.bytes = want;
+  return K2B_OK;
+}
+
+}  // namespace k2b
+
+using namespace k2b;
+
+extern "C" {
+
+int32_t k2b_abi_version(void) { return K2B_ABI_VERSION; }
+
+const char* k2b_last_error(const k2b_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int32_t k2b_create(const k2b_config* cfg, k2b_handle** out) {
+  if (out == nullptr) return fail(nullptr, K2B_ERR_INVALID, "k2b_create: out is NULL");
+  *out = nullptr;
+  if (cfg == nullptr) return fail(nullptr, K2B_ERR_INVALID, "k2b_create: cfg is NULL");
+  if (cfg->struct_size != (int32_t)sizeof(k2b_config))
+    return fail(nullptr, K2B_ERR_INVALID, "k2b_create: struct_size does not match this library's k2b_config");
+  if (cfg->context_size != 2)
+    return fail(nullptr, K2B_ERR_UNSUPPORTED, "k2b_create: context_size must be 2 (the reference only works with 2)");
+  if (cfg->vocab_size < 1 || cfg->joiner_dim < 16 || cfg->decoder_dim < 16 || cfg->joiner_dim % 16 || cfg->decoder_dim % 16 ||
+      cfg->encoder_dim < 0 || cfg->encoder_dim % 16)
+    return fail(nullptr, K2B_ERR_INVALID, "k2b_create: V >= 1 and J, D, E multiples of 16 are required");
+  if (cfg->vocab_size >= (1 << 27)) return fail(nullptr, K2B_ERR_INVALID, "k2b_create: vocab_size too large");
+  if (cfg->max_beam > kMaxBeam) return fail(nullptr, K2B_ERR_INVALID, "k2b_create: max_beam > 8");
+  if (cfg->precision < K2B_PREC_FP32 || cfg->precision > K2B_PREC_BF16)
+    return fail(nullptr, K2B_ERR_INVALID, "k2b_create: unknown precision");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0)
+    return fail(nullptr, K2B_ERR_CUDA, std::string("k2b_create: no CUDA device (") + cudaGetErrorString(e) +
+                                          "); this library has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, K2B_ERR_INVALID, "k2b_create: device ordinal out of range");
+  e = cudaSetDevice(cfg->device);
+  if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice", __FILE__, __LINE__);
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, cfg->device);
+  if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties", __FILE__, __LINE__);
+  if (prop.major != 10)
+    return fail(nullptr, K2B_ERR_UNSUPPORTED, "k2b_create: this build targets sm_100a (Blackwell B200) only");
+  k2b_handle* h = new k2b_handle();
+  h->cfg = *cfg;
+  h->sm_count = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete h; return cuda_fail(nullptr, e, "cudaStreamCreate", __FILE__, __LINE__); }
+  h->stream = h->own_stream;
+  *out = h;
+  return K2B_OK;
+}
+
+int32_t k2b_destroy(k2b_handle* h) {
+  if (h == nullptr) return K2B_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+  float** ws[] = {&h->emb, &h->conv_w, &h->dec_w, &h->dec_b, &h->enc_w, &h->enc_b, &h->out_w, &h->out_b, &h->tab0, &h->tab1};
+  for (float** p : ws) { if (*p) cudaFree(*p); *p = nullptr; }
+  DevBuf* bufs[] = {&h->ws_in, &h->ws_encproj, &h->ws_x, &h->ws_dec, &h->ws_logits, &h->ws_part, &h->ws_state, &h->ws_bp,
+                    &h->ws_out, &h->ws_misc, &h->ws_ctc};
+  for (DevBuf* b : bufs) free_buf(*b);
+  for (cudaEvent_t ev : h->prof.start) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : h->prof.stop) cudaEventDestroy(ev);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return K2B_OK;
+}
+
+int32_t k2b_load_weights(k2b_handle* h, const float* emb, const float* conv_w, const float* dec_proj_w,
+                         const float* dec_proj_b, const float* enc_proj_w, const float* enc_proj_b, const float* out_w,
+                         const float* out_b) {
+  K2B_TRY(enter(h));
+  const k2b_config& c = h->cfg;
+  if (!emb || !conv_w || !dec_proj_w || !dec_proj_b || !out_w || !out_b)
+    return fail(h, K2B_ERR_INVALID, "k2b_load_weights: a required weight pointer is NULL");
+  if (c.encoder_dim > 0 && (!enc_proj_w || !enc_proj_b))
+    return fail(h, K2B_ERR_INVALID, "k2b_load_weights: encoder_dim > 0 needs enc_proj_w and enc_proj_b");
+  const size_t V = c.vocab_size, J = c.joiner_dim, D = c.decoder_dim, E = c.encoder_dim, ctx = c.context_size;
+  h->weights_loaded = false;
+  K2B_TRY(upload(h, &h->emb, emb, V * D));
+  K2B_TRY(upload(h, &h->conv_w, conv_w, D * 4 * ctx));
+  K2B_TRY(upload(h, &h->dec_w, dec_proj_w, J * D));
+  K2B_TRY(upload(h, &h->dec_b, dec_proj_b, J));
+  K2B_TRY(upload(h, &h->out_w, out_w, V * J));
+  K2B_TRY(upload(h, &h->out_b, out_b, V));
+  if (E > 0) {
+    K2B_TRY(upload(h, &h->enc_w, enc_proj_w, J * E));
+    K2B_TRY(upload(h, &h->enc_b, enc_proj_b, J));
+  }
+  if (h->tab0) { cudaFree(h->tab0); h->tab0 = nullptr; }
+  if (h->tab1) { cudaFree(h->tab1); h->tab1 = nullptr; }
+  K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->tab0), (V + 1) * D * sizeof(float)));
+  K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->tab1), (V + 1) * D * sizeof(float)));
+  K2B_TRY(build_decoder_tables(h));
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->weights_loaded = true;
+  return K2B_OK;
+}
+
+int32_t k2b_set_precision(k2b_handle* h, int32_t precision) {
+  K2B_TRY(enter(h));
+  if (precision < K2B_PREC_FP32 || precision > K2B_PREC_BF16) return fail(h, K2B_ERR_INVALID, "unknown precision");
+  if (precision != K2B_PREC_FP32)
+    return fail(h, K2B_ERR_UNSUPPORTED, "tcgen05 precisions are not built into this library version");
+  h->cfg.precision = precision;
+  return K2B_OK;
+}
+
+int32_t k2b_set_stream(k2b_handle* h, void* cuda_stream) {
+  K2B_TRY(enter(h));
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+  return K2B_OK;
+}
+
+int32_t k2b_sync(k2b_handle* h) {
+  K2B_TRY(enter(h));
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  return K2B_OK;
+}
+
+int64_t k2b_launch_count(const k2b_handle* h) { return h ? h->launches : 0; }
+
+int32_t k2b_reset_launch_count(k2b_handle* h) {
+  if (!h) return K2B_ERR_INVALID;
+  h->launches = 0;
+  return K2B_OK;
+}
+
+int32_t k2b_profile_enable(k2b_handle* h, int32_t on) {
+  K2B_TRY(enter(h));
+  h->profile_on = on != 0;
+  return K2B_OK;
+}
+
+int32_t k2b_profile_read(k2b_handle* h, int64_t* n_launches, double* total_ms) {
+  K2B_TRY(enter(h));
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  ProfEvents& p = h->prof;
+  for (size_t i = 0; i < p.used; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.start[i], p.stop[i]) == cudaSuccess) { p.ms_total += ms; p.n_total++; }
+  }
+  p.used = 0;
+  if (n_launches) *n_launches = p.n_total;
+  if (total_ms) *total_ms = p.ms_total;
+  p.n_total = 0;
+  p.ms_total = 0.0;
+  return K2B_OK;
+}
+
+// ---- fine-grained -------------------------------------------------------------------------------
+int32_t k2b_decoder_proj_dev(k2b_handle* h, const int64_t* y, int32_t n, float* out) {
+  K2B_TRY(enter(h));
+  K2B_TRY(need_weights(h));
+  if (n < 0 || (n > 0 && out == nullptr)) return fail(h, K2B_ERR_INVALID, "k2b_decoder_proj: bad n or out");
+  if (n == 0) return K2B_OK;
+  K2B_TRY(ensure(h, h->ws_misc, sizeof(int32_t) * 2 * (size_t)n));
+  int32_t* ctx = static_cast<int32_t*>(h->ws_misc.p);
+  ctx_from_i64_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(y, n, h->cfg.blank_id, ctx);
+  K2B_LAUNCH_CHECK(h);
+  GemmArgs a;
+  a.M = n; a.N = h->cfg.joiner_dim; a.K = h->cfg.decoder_dim;
+  a.W = h->dec_w; a.bias = h->dec_b;
+  a.ctx = ctx; a.tab0 = h->tab0; a.tab1 = h->tab1; a.V = h->cfg.vocab_size;
+  a.neg_wrap = h->cfg.neg_id_mode == K2B_NEGID_WRAP; a.blank = h->cfg.blank_id;
+  a.C = out;
+  return launch_gemm_simt(h, PRO_DEC, EPI_STORE, a);
+}
+
+int32_t k2b_decoder_proj(k2b_handle* h, const int64_t* y, int32_t n, float* out) {
+  K2B_TRY(enter(h));
+  K2B_TRY(need_weights(h));
+  if (n < 0 || (n > 0 && out == nullptr)) return fail(h, K2B_ERR_INVALID, "k2b_decoder_proj: bad n or out");
+  if (n == 0) return K2B_OK;
+  const size_t J = h->cfg.joiner_dim;
+  K2B_TRY(ensure(h, h->ws_dec, sizeof(float) * (size_t)n * J));
+  const int64_t* yd = nullptr;
+  if (y != nullptr) {
+    K2B_TRY(ensure(h, h->ws_in, sizeof(int64_t) * 2 * (size_t)n));
+    K2B_CUDA(h, cudaMemcpyAsync(h->ws_in.p, y, sizeof(int64_t) * 2 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    yd = static_cast<const int64_t*>(h->ws_in.p);
+  }
+  K2B_TRY(k2b_decoder_proj_dev(h, yd, n, static_cast<float*>(h->ws_dec.p)));
+  K2B_CUDA(h, cudaMemcpyAsync(out, h->ws_dec.p, sizeof(float) * (size_t)n * J, cudaMemcpyDeviceToHost, h->stream));
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  return K2B_OK;
+}
+
+int32_t k2b_joiner_proj_dev(k2b_handle* h, const float* enc, const float* dec, int32_t n, float* logits) {
+  K2B_TRY(enter(h));
+  K2B_TRY(need_weights(h));
+  if (n < 0 || (n > 0 && (!enc || !dec || !logits))) return fail(h, K2B_ERR_INVALID, "k2b_joiner_proj: bad argument");
+  if (n == 0) return K2B_OK;
+  GemmArgs a;
+  a.M = n; a.N = h->cfg.vocab_size; a.K = h->cfg.joiner_dim;
+  a.W = h->out_w; a.bias = h->out_b;
+  a.enc = enc; a.enc_stride = h->cfg.joiner_dim; a.rows_per_stream = 1; a.dec = dec;
+  a.C = logits;
+  prof_begin(h);
+  int32_t s = launch_gemm_simt(h, PRO_JOIN, EPI_STORE, a);
+  prof_end(h);
+  return s;
+}
+
+int32_t k2b_joiner_proj(k2b_handle* h, const float* enc, const float* dec, int32_t n, float* logits) {
+  K2B_TRY(enter(h));
+  K2B_TRY(need_weights(h));
+  if (n < 0 || (n > 0 && (!enc || !dec || !logits))) return fail(h, K2B_ERR_INVALID, "k2b_joiner_proj: bad argument");
+  if (n == 0) return K2B_OK;
+  const size_t J = h->cfg.joiner_dim, V = h->cfg.vocab_size;
+  K2B_TRY(ensure(h, h->ws_in, sizeof(float) * 2 * (size_t)n * J));
+  K2B_TRY(ensure(h, h->ws_logits, sizeof(float) * (size_t)n * V));
+  float* de = static_cast<float*>(h->ws_in.p);
+  float* dd = de + (size_t)n * J;
+  K2B_CUDA(h, cudaMemcpyAsync(de, enc, sizeof(float) * (size_t)n * J, cudaMemcpyHostToDevice, h->stream));
+  K2B_CUDA(h, cudaMemcpyAsync(dd, dec, sizeof(float) * (size_t)n * J, cudaMemcpyHostToDevice, h->stream));
+  K2B_TRY(k2b_joiner_proj_dev(h, de, dd, n, static_cast<float*>(h->ws_logits.p)));
+  K2B_CUDA(h, cudaMemcpyAsync(logits, h->ws_logits.p, sizeof(float) * (size_t)n * V, cudaMemcpyDeviceToHost, h->stream));
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  return K2B_OK;
+}
+
+int32_t k2b_encoder_proj_dev(k2b_handle* h, const float* raw, int32_t n, float* out) {
+  K2B_TRY(enter(h));
+  K2B_TRY(need_weights(h));
+  if (n < 0 || (n > 0 && (!raw || !out))) return fail(h, K2B_ERR_INVALID, "k2b_encoder_proj: bad argument");
+  if (n == 0) return K2B_OK;
+  return encoder_proj_launch(h, raw, n, out);
+}
+
+int32_t k2b_encoder_proj(k2b_handle* h, const float* raw, int32_t n, float* out) {
+  K2B_TRY(enter(h));
+  K2B_TRY(need_weights(h));
+  if (n < 0 || (n > 0 && (!raw || !out))) return fail(h, K2B_ERR_INVALID, "k2b_encoder_proj: bad argument");
+  if (n == 0) return K2B_OK;
+  const size_t J = h->cfg.joiner_dim, E = h->cfg.encoder_dim;
+  K2B_TRY(ensure(h, h->ws_in, sizeof(float) * (size_t)n * E));
+  K2B_TRY(ensure(h, h->ws_encproj, sizeof(float) * (size_t)n * J));
+  K2B_CUDA(h, cudaMemcpyAsync(h->ws_in.p, raw, sizeof(float) * (size_t)n * E, cudaMemcpyHostToDevice, h->stream));
+  K2B_TRY(encoder_proj_launch(h, static_cast<const float*>(h->ws_in.p), n, static_cast<float*>(h->ws_encproj.p)));
+  K2B_CUDA(h, cudaMemcpyAsync(out, h->ws_encproj.p, sizeof(float) * (size_t)n * J, cudaMemcpyDeviceToHost, h->stream));
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  return K2B_OK;
+}
+
+// ---- fused search ---------------------------------------------------------------------------------
+int32_t k2b_greedy_offline_dev(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t T, int32_t mode,
+                               int64_t* tokens, int32_t* ts, int32_t* n_out, int32_t cap) {
+  K2B_TRY(enter(h));
+  K2B_TRY(need_weights(h));
+  K2B_TRY(check_search_args(h, enc, B, T, cap, tokens, ts, n_out, "k2b_greedy_offline"));
+  if (mode < K2B_GREEDY_SINGLE || mode > K2B_GREEDY_PER_STREAM) return fail(h, K2B_ERR_INVALID, "k2b_greedy_offline: unknown mode");
+  if (mode == K2B_GREEDY_SINGLE && B != 1) return fail(h, K2B_ERR_INVALID, "k2b_greedy_offline: SINGLE mode needs B == 1");
+  if (B == 0) return K2B_OK;
+  const float* frames = nullptr;
+  K2B_TRY(frames_for_search(h, enc, enc_is_raw, B, T, &frames));
+  return greedy_dev(h, frames, B, T, mode, false, nullptr, tokens, ts, n_out, cap);
+}
+
+int32_t k2b_greedy_offline(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t T, int32_t mode,
+                           int64_t* tokens, int32_t* ts, int32_t* n_out, int32_t cap) {
+  K2B_TRY(enter(h));
+  K2B_TRY(need_weights(h));
+  K2B_TRY(check_search_args(h, enc, B, T, cap, tokens, ts, n_out, "k2b_greedy_offline"));
+  if (B == 0) return K2B_OK;
+  const size_t width = enc_is_raw ? h->cfg.encoder_dim : h->cfg.joiner_dim;
+  const size_t in_bytes = sizeof(float) * (size_t)B * T * width;
+  K2B_TRY(ensure(h, h->ws_in, in_bytes > 0 ? in_bytes : 4));
+  OutStage o;
+  K2B_TRY(stage_out(h, B, cap > 0 ? cap : 1, &o));
+  if (in_bytes) K2B_CUDA(h, cudaMemcpyAsync(h->ws_in.p, enc, in_bytes, cudaMemcpyHostToDevice, h->stream));
+  K2B_TRY(k2b_greedy_offline_dev(h, static_cast<const float*>(h->ws_in.p), enc_is_raw, B, T, mode, o.tokens, o.ts, o.n, cap));
+  if (cap > 0) {
+    K2B_CUDA(h, cudaMemcpyAsync(tokens, o.tokens, sizeof(int64_t) * (size_t)B * cap, cudaMemcpyDeviceToHost, h->stream));
+    K2B_CUDA(h, cudaMemcpyAsync(ts, o.ts, sizeof(int32_t) * (size_t)B * cap, cudaMemcpyDeviceToHost, h->stream));
+  }
+  K2B_CUDA(h, cudaMemcpyAsync(n_out, o.n, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  return K2B_OK;
+}
+
+int32_t k2b_greedy_online_chunk_dev(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t Tc,
+                                    int64_t* hyp_inout, int64_t* tokens, int32_t* ts, int32_t* n_out, int32_t cap) {
+  K2B_TRY(enter(h));
+  K2B_TRY(need_weights(h));
+  K2B_TRY(check_search_args(h, enc, B, Tc, cap, tokens, ts, n_out, "k2b_greedy_online_chunk"));
+  if (B > 0 && hyp_inout == nullptr) return fail(h, K2B_ERR_INVALID, "k2b_greedy_online_chunk: hyp_inout is NULL");
+  if (B == 0) return K2B_OK;
+  const float* frames = nullptr;
+  K2B_TRY(frames_for_search(h, enc, enc_is_raw, B, Tc, &frames));
+  return greedy_dev(h, frames, B, Tc, K2B_GREEDY_BATCH_COMPAT, true, hyp_inout, tokens, ts, n_out, cap);
+}
+
+int32_t k2b_greedy_online_chunk(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t Tc,
+                                int64_t* hyp_inout, int64_t* tokens, int32_t* ts, int32_t* n_out, int32_t cap) {
+  K2B_TRY(enter(h));
+  K2B_TRY(need_weights(h));
+  K2B_TRY(check_search_args(h, enc, B, Tc, cap, tokens, ts, n_out, "k2b_greedy_online_chunk"));
+  if (B > 0 && hyp_inout == nullptr) return fail(h, K2B_ERR_INVALID, "k2b_greedy_online_chunk: hyp_inout is NULL");
+  if (B == 0) return K2B_OK;
+  const size_t width = enc_is_raw ? h->cfg.encoder_dim : h->cfg.joiner_dim;
+  const size_t in_bytes = sizeof(float) * (size_t)B * Tc * width;
+  K2B_TRY(ensure(h, h->ws_in, in_bytes > 0 ? in_bytes : 4));
+  OutStage o;
+  K2B_TRY(stage_out(h, B, cap > 0 ? cap : 1, &o));
+  if (in_bytes) K2B_CUDA(h, cudaMemcpyAsync(h->ws_in.p, enc, in_bytes, cudaMemcpyHostToDevice, h->stream));
+  K2B_CUDA(h, cudaMemcpyAsync(o.hyp, hyp_inout, sizeof(int64_t) * 2 * (size_t)B, cudaMemcpyHostToDevice, h->stream));
+  K2B_TRY(k2b_greedy_online_chunk_dev(h, static_cast<const float*>(h->ws_in.p), enc_is_raw, B, Tc, o.hyp, o.tokens, o.ts, o.n, cap));
+  if (cap > 0) {
+    K2B_CUDA(h, cudaMemcpyAsync(tokens, o.tokens, sizeof(int64_t) * (size_t)B * cap, cudaMemcpyDeviceToHost, h->stream));
+    K2B_CUDA(h, cudaMemcpyAsync(ts, o.ts, sizeof(int32_t) * (size_t)B * cap, cudaMemcpyDeviceToHost, h->stream));
+  }
+  K2B_CUDA(h, cudaMemcpyAsync(n_out, o.n, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+  K2B_CUDA(h, cudaMemcpyAsync(hyp_inout, o.hyp, sizeof(int64_t) * 2 * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  return K2B_OK;
+}
+
+int32_t k2b_modified_beam_search_dev(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t T, int32_t K,
+                                     int64_t* tokens, int32_t* ts, int32_t* n_out, float* score, int32_t cap) {
+  K2B_TRY(enter(h));
+  K2B_TRY(need_weights(h));
+  K2B_TRY(check_search_args(h, enc, B, T, cap, tokens, ts, n_out, "k2b_modified_beam_search"));
+  if (K < 1 || K > kMaxBeam) return fail(h, K2B_ERR_INVALID, "k2b_modified_beam_search: beam must be in 1..8");
+  if (K > h->cfg.vocab_size) return fail(h, K2B_ERR_INVALID, "k2b_modified_beam_search: beam exceeds vocab_size");
+  if (B > 0 && score == nullptr) return fail(h, K2B_ERR_INVALID, "k2b_modified_beam_search: score is NULL");
+  if (B == 0) return K2B_OK;
+  const float* frames = nullptr;
+  K2B_TRY(frames_for_search(h, enc, enc_is_raw, B, T, &frames));
+  return beam_dev(h, frames, B, T, K, tokens, ts, n_out, score, cap);
+}
+
+int32_t k2b_modified_beam_search(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t T, int32_t K,
+                                 int64_t* tokens, int32_t* ts, int32_t* n_out, float* score, int32_t cap) {
+  K2B_TRY(enter(h));
+  K2B_TRY(need_weights(h));
+  K2B_TRY(check_search_args(h, enc, B, T, cap, tokens, ts, n_out, "k2b_modified_beam_search"));
+  if (B > 0 && score == nullptr) return fail(h, K2B_ERR_INVALID, "k2b_modified_beam_search: score is NULL");
+  if (B == 0) return K2B_OK;
+  const size_t width = enc_is_raw ? h->cfg.encoder_dim : h->cfg.joiner_dim;
+  const size_t in_bytes = sizeof(float) * (size_t)B * T * width;
+  K2B_TRY(ensure(h, h->ws_in, in_bytes > 0 ? in_bytes : 4));
+  OutStage o;
+  K2B_TRY(stage_out(h, B, cap > 0 ? cap : 1, &o));
+  if (in_bytes) K2B_CUDA(h, cudaMemcpyAsync(h->ws_in.p, enc, in_bytes, cudaMemcpyHostToDevice, h->stream));
+  K2B_TRY(k2b_modified_beam_search_dev(h, static_cast<const float*>(h->ws_in.p), enc_is_raw, B, T, K, o.tokens, o.ts, o.n,
+                                       o.score, cap));
+  if (cap > 0) {
+    K2B_CUDA(h, cudaMemcpyAsync(tokens, o.tokens, sizeof(int64_t) * (size_t)B * cap, cudaMemcpyDeviceToHost, h->stream));
+    K2B_CUDA(h, cudaMemcpyAsync(ts, o.ts, sizeof(int32_t) * (size_t)B * cap, cudaMemcpyDeviceToHost, h->stream));
+  }
+  K2B_CUDA(h, cudaMemcpyAsync(n_out, o.n, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+  K2B_CUDA(h, cudaMemcpyAsync(score, o.score, sizeof(float) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  return K2B_OK;
+}
+
+int32_t k2b_ctc_greedy_dev(k2b_handle* h, const float* logp, int32_t B, int32_t T, int32_t V, int32_t blank,
+                           const int32_t* frame_offset, int64_t* prev_inout, int64_t* tokens, int32_t* ts, int32_t* n_out,
+                           int32_t* trailing_blank_inout, int32_t cap) {
+  K2B_TRY(enter(h));
+  K2B_TRY(check_search_args(h, logp, B, T, cap, tokens, ts, n_out, "k2b_ctc_greedy"));
+  if (V < 1) return fail(h, K2B_ERR_INVALID, "k2b_ctc_greedy: V must be >= 1");
+  if (B == 0) return K2B_OK;
+  return ctc_greedy_dev(h, logp, B, T, V, blank, frame_offset, prev_inout, tokens, ts, n_out, trailing_blank_inout, cap);
+}
+
+int32_t k2b_ctc_greedy(k2b_handle* h, const float* logp, int32_t B, int32_t T, int32_t V, int32_t blank,
+                       const int32_t* frame_offset, int64_t* prev_inout, int64_t* tokens, int32_t* ts, int32_t* n_out,
+                       int32_t* trailing_blank_inout, int32_t cap) {
+  K2B_TRY(enter(h));
+  K2B_TRY(check_search_args(h, logp, B, T, cap, tokens, ts, n_out, "k2b_ctc_greedy"));
+  if (V < 1) return fail(h, K2B_ERR_INVALID, "k2b_ctc_greedy: V must be >= 1");
+  if (B == 0) return K2B_OK;
+  const size_t in_bytes = sizeof(float) * (size_t)B * T * V;
+  K2B_TRY(ensure(h, h->ws_in, in_bytes > 0 ? in_bytes : 4));
+  OutStage o;
+  K2B_TRY(stage_out(h, B, cap > 0 ? cap : 1, &o));
+  if (in_bytes) K2B_CUDA(h, cudaMemcpyAsync(h->ws_in.p, logp, in_bytes, cudaMemcpyHostToDevice, h->stream));
+  if (frame_offset) K2B_CUDA(h, cudaMemcpyAsync(o.aux_a, frame_offset, sizeof(int32_t) * (size_t)B, cudaMemcpyHostToDevice, h->stream));
+  if (trailing_blank_inout) K2B_CUDA(h, cudaMemcpyAsync(o.aux_b, trailing_blank_inout, sizeof(int32_t) * (size_t)B, cudaMemcpyHostToDevice, h->stream));
+  if (prev_inout) K2B_CUDA(h, cudaMemcpyAsync(o.prev, prev_inout, sizeof(int64_t) * (size_t)B, cudaMemcpyHostToDevice, h->stream));
+  K2B_TRY(k2b_ctc_greedy_dev(h, static_cast<const float*>(h->ws_in.p), B, T, V, blank, frame_offset ? o.aux_a : nullptr,
+                             prev_inout ? o.prev : nullptr, o.tokens, o.ts, o.n, trailing_blank_inout ? o.aux_b : nullptr, cap));
+  if (cap > 0) {
+    K2B_CUDA(h, cudaMemcpyAsync(tokens, o.tokens, sizeof(int64_t) * (size_t)B * cap, cudaMemcpyDeviceToHost, h->stream));
+    K2B_CUDA(h, cudaMemcpyAsync(ts, o.ts, sizeof(int32_t) * (size_t)B * cap, cudaMemcpyDeviceToHost, h->stream));
+  }
+  K2B_CUDA(h, cudaMemcpyAsync(n_out, o.n, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+  if (trailing_blank_inout) K2B_CUDA(h, cudaMemcpyAsync(trailing_blank_inout, o.aux_b, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+  if (prev_inout) K2B_CUDA(h, cudaMemcpyAsync(prev_inout, o.prev, sizeof(int64_t) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  return K2B_OK;
+}
+
+}  // extern "C"

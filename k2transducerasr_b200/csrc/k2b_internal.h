@@ -1,0 +1,160 @@
+// Internal definitions shared by the translation units of libk2b200.so (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/k2b200.h"
+
+namespace k2b {
+
+constexpr int kMaxBeam = 8;
+
+// SIMT GEMM tile (gemm_simt.cu); the partial-result layouts of the search kernels depend on BN.
+constexpr int kBM = 64;
+constexpr int kBN = 64;
+constexpr int kBK = 16;
+
+// A device allocation that only ever grows; freed with the handle.
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct ProfEvents {
+  std::vector<cudaEvent_t> start, stop;
+  size_t used = 0;
+  int64_t n_total = 0;
+  double ms_total = 0.0;
+};
+
+}  // namespace k2b
+
+struct k2b_handle {
+  k2b_config cfg{};
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  bool poisoned = false;
+  bool weights_loaded = false;
+  int64_t launches = 0;
+  int sm_count = 148;
+
+  // fp32 weights as loaded (row-major, layouts in k2b200.h)
+  float* emb = nullptr;      // [V,D]
+  float* conv_w = nullptr;   // [D,4,ctx]
+  float* dec_w = nullptr;    // [J,D]
+  float* dec_b = nullptr;    // [J]
+  float* enc_w = nullptr;    // [J,E]
+  float* enc_b = nullptr;    // [J]
+  float* out_w = nullptr;    // [V,J]
+  float* out_b = nullptr;    // [V]
+  // grouped conv folded into per-token tables at load time: conv(e0,e1)[o] = T0[y0][o] + T1[y1][o].
+  // Row V of each table is all-zero (the "masked" negative id).
+  float* tab0 = nullptr;     // [V+1,D]
+  float* tab1 = nullptr;     // [V+1,D]
+
+  // growable workspaces
+  k2b::DevBuf ws_in;        // host-variant staging of the input frames / log-probs
+  k2b::DevBuf ws_encproj;   // [B,T,J] projected frames when the caller passes raw frames
+  k2b::DevBuf ws_x;         // [N,J] joiner A operand tanh(enc+dec)
+  k2b::DevBuf ws_dec;       // [N,J] decoder_proj output (fine-grained path)
+  k2b::DevBuf ws_logits;    // [N,V] (fine-grained path staging)
+  k2b::DevBuf ws_part;      // per-(row, vocab tile) partial argmax / softmax / top-k
+  k2b::DevBuf ws_state;     // hypothesis state (ctx, lp, len, hash, nlive), double-buffered
+  k2b::DevBuf ws_bp;        // beam back-pointers [B,T,K]
+  k2b::DevBuf ws_out;       // host-variant staging of tokens / ts / n / score
+  k2b::DevBuf ws_misc;      // int32 contexts of the fine-grained decoder call
+  k2b::DevBuf ws_ctc;       // ctc: per-frame ids [B*T] + per-stream tickets [B] (tickets stay zero between launches)
+
+  bool profile_on = false;
+  k2b::ProfEvents prof;
+};
+
+namespace k2b {
+
+int32_t fail(k2b_handle* h, int32_t code, const std::string& msg);
+int32_t cuda_fail(k2b_handle* h, cudaError_t e, const char* what, const char* file, int line);
+int32_t ensure(k2b_handle* h, DevBuf& b, size_t bytes);
+
+#define K2B_CUDA(h, expr)                                                        \
+  do {                                                                           \
+    cudaError_t _e = (expr);                                                     \
+    if (_e != cudaSuccess) return k2b::cuda_fail((h), _e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define K2B_TRY(expr)                   \
+  do {                                  \
+    int32_t _s = (expr);                \
+    if (_s != K2B_OK) return _s;        \
+  } while (0)
+
+#define K2B_LAUNCH_CHECK(h)                                                      \
+  do {                                                                           \
+    (h)->launches++;                                                             \
+    cudaError_t _e = cudaGetLastError();                                         \
+    if (_e != cudaSuccess) return k2b::cuda_fail((h), _e, "kernel launch", __FILE__, __LINE__); \
+  } while (0)
+
+// ---- gemm_simt.cu ---------------------------------------------------------------------------
+enum Pro : int { PRO_PLAIN = 0, PRO_DEC = 1, PRO_JOIN = 2 };
+enum Epi : int { EPI_STORE = 0, EPI_TANH_ADD = 1, EPI_ARGMAX = 2, EPI_TOPK = 3 };
+
+struct GemmArgs {
+  int M = 0, N = 0, K = 0;
+  const float* W = nullptr;     // [N,K]
+  const float* bias = nullptr;  // [N] or null
+  // PRO_PLAIN
+  const float* A = nullptr;     // [M,K]
+  // PRO_DEC: A(m,k) = relu(tab0[r0(m)][k] + tab1[r1(m)][k]), ids from ctx[m][2]
+  const int32_t* ctx = nullptr;
+  const float* tab0 = nullptr;
+  const float* tab1 = nullptr;
+  int V = 0;
+  int neg_wrap = 0;
+  int blank = 0;
+  const int32_t* compat_flag = nullptr;  // Q6: when *flag != 0 a negative ctx[m][0] reads as blank
+  // PRO_JOIN / EPI_TANH_ADD: encoder row of GEMM row m is enc + (m / rows_per_stream) * enc_stride
+  const float* enc = nullptr;
+  long long enc_stride = 0;
+  int rows_per_stream = 1;
+  const float* dec = nullptr;   // PRO_JOIN: [M,K]
+  // EPI_STORE / EPI_TANH_ADD
+  float* C = nullptr;           // [M,N]
+  // EPI_ARGMAX: [M,nt] each
+  float* part_val = nullptr;
+  int32_t* part_idx = nullptr;
+  int32_t* part_nan = nullptr;
+  // EPI_TOPK: part_m/part_s [M,nt]; part_tv/part_ti [M,nt,topk]
+  float* part_m = nullptr;
+  float* part_s = nullptr;
+  float* part_tv = nullptr;
+  int32_t* part_ti = nullptr;
+  int topk = 0;
+};
+
+int32_t launch_gemm_simt(k2b_handle* h, Pro pro, Epi epi, const GemmArgs& a);
+inline int num_vocab_tiles(int V) { return (V + kBN - 1) / kBN; }
+
+// ---- decoder_tables.cu -----------------------------------------------------------------------
+int32_t build_decoder_tables(k2b_handle* h);
+
+// ---- ctc.cu ------------------------------------------------------------------------------------
+int32_t ctc_greedy_dev(k2b_handle* h, const float* logp, int B, int T, int V, int blank,
+                       const int32_t* frame_offset, int64_t* prev_inout, int64_t* tokens, int32_t* ts,
+                       int32_t* n_out, int32_t* trailing_inout, int cap);
+
+// ---- search.cu ---------------------------------------------------------------------------------
+int32_t greedy_dev(k2b_handle* h, const float* enc, int B, int T, int mode, bool online,
+                   int64_t* hyp_inout, int64_t* tokens, int32_t* ts, int32_t* n_out, int cap);
+int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* tokens, int32_t* ts,
+                 int32_t* n_out, float* score, int cap);
+
+// profiling bracket around the dominant GEMM
+void prof_begin(k2b_handle* h);
+void prof_end(k2b_handle* h);
+
+}  // namespace k2b

@@ -1,0 +1,456 @@
+// Transducer search loops on the device: greedy_search (offline single / batch / online chunk) and
+// modified_beam_search. The time loop is a sequence of launches on the handle's stream, three per frame:
+//   1. decoder GEMM   x = tanh(enc[s,t] + dec_proj(relu(tab0[y0] + tab1[y1])))          (gemm_*.cu)
+//   2. joiner GEMM    logits tile = x * out_w^T + out_b  -> per-(row, vocab tile) partials only
+//   3. select         greedy: fold argmax partials, append, shift context
+//                     beam:   log_softmax constants, per-stream top-K over K*V, hypothesis merge
+// Nothing crosses PCIe inside the loop and the logits are never written to HBM.
+#include <math.h>
+
+#include "k2b_internal.h"
+
+namespace k2b {
+
+namespace {
+
+constexpr uint64_t kHashSeed = 0x9E3779B97F4A7C15ull;
+
+__device__ __forceinline__ uint64_t hash_push(uint64_t h, int tok) {
+  h = (h ^ (uint64_t)(uint32_t)(tok + 1)) * 0x100000001B3ull;
+  h ^= h >> 29;
+  h *= 0xBF58476D1CE4E5B9ull;
+  h ^= h >> 32;
+  return h;
+}
+
+__device__ __forceinline__ float logaddexp_f(float a, float b) {
+  const float mx = fmaxf(a, b), mn = fminf(a, b);
+  if (mx == -INFINITY) return -INFINITY;
+  return mx + log1pf(expf(mn - mx));
+}
+
+// ------------------------------------------------------------------------------------------------
+// greedy
+// ------------------------------------------------------------------------------------------------
+__global__ void greedy_init_kernel(int B, int blank, const int64_t* __restrict__ hyp_in, int32_t* __restrict__ ctx,
+                                   int32_t* __restrict__ n_out, int32_t* __restrict__ flag) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) *flag = 0;
+  if (b >= B) return;
+  if (hyp_in != nullptr) {           // online: context = OnlineStream.Hyp (ref OnlineRecognizer.cs:109,125)
+    ctx[2 * b] = (int32_t)hyp_in[2 * b];
+    ctx[2 * b + 1] = (int32_t)hyp_in[2 * b + 1];
+  } else {                           // offline: {-1, blank} (ref OfflineRecognizer.cs:105, :202)
+    ctx[2 * b] = -1;
+    ctx[2 * b + 1] = blank;
+  }
+  n_out[b] = 0;
+}
+
+// One thread per stream: fold the per-tile argmax partials in index order (ties / NaN -> larger index,
+// ref OfflineRecognizer.cs:153), then the emission test (ref :161 offline, OnlineRecognizer.cs:181 online).
+__global__ void greedy_select_kernel(int B, int nt, const float* __restrict__ pval, const int32_t* __restrict__ pidx,
+                                     const int32_t* __restrict__ pnan, int32_t* __restrict__ ctx,
+                                     int64_t* __restrict__ tokens, int32_t* __restrict__ ts, int32_t* __restrict__ n_out,
+                                     int cap, int t, int blank, int unk, int extra_mask, int max_sym,
+                                     int32_t* __restrict__ flag) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float bv = 0.f;
+  int bi = -1, bn = 0;
+  for (int i = 0; i < nt; ++i) {
+    const size_t o = (size_t)b * nt + i;
+    const float v = pval[o];
+    const int idx = pidx[o], nn = pnan[o];
+    if (idx < 0) continue;
+    if (bi < 0 || nn) { bv = v; bi = idx; bn = nn | bn; continue; }
+    if (!(bv > v)) { bv = v; bi = idx; }
+  }
+  (void)bn;
+  const int n = n_out[b];
+  if (n >= max_sym) return;          // single-stream loop stops at 1000 symbols (ref OfflineRecognizer.cs:122,127)
+  const int y = bi;
+  if (y != blank && y != unk && y != extra_mask) {
+    if (n < cap) {
+      tokens[(size_t)b * cap + n] = y;
+      ts[(size_t)b * cap + n] = t;
+    }
+    n_out[b] = n + 1;
+    ctx[2 * b] = ctx[2 * b + 1];
+    ctx[2 * b + 1] = y;
+    *flag = 1;                       // Q6: somebody in the batch emitted
+  }
+}
+
+__global__ void greedy_finish_online_kernel(int B, const int32_t* __restrict__ ctx, int64_t* __restrict__ hyp_out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  hyp_out[2 * b] = ctx[2 * b];       // ref OnlineRecognizer.cs:208
+  hyp_out[2 * b + 1] = ctx[2 * b + 1];
+}
+
+// ------------------------------------------------------------------------------------------------
+// modified_beam_search
+// ------------------------------------------------------------------------------------------------
+struct BeamState {
+  int32_t* ctx;    // [N,2]
+  float* lp;       // [N]
+  int32_t* len;    // [N]
+  uint64_t* hash;  // [N]
+  int32_t* nlive;  // [B]
+};
+
+__global__ void beam_init_kernel(int B, int K, int blank, BeamState s0, BeamState s1) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= B * K) return;
+  const int slot = n % K;
+  s0.ctx[2 * n] = -1; s0.ctx[2 * n + 1] = blank;
+  s1.ctx[2 * n] = -1; s1.ctx[2 * n + 1] = blank;
+  s0.lp[n] = slot == 0 ? 0.f : -INFINITY;
+  s0.len[n] = 2;
+  s0.hash[n] = kHashSeed;
+  if (slot == 0) s0.nlive[n / K] = 1;
+}
+
+__device__ __forceinline__ bool better(float v, int i, float ev, int ei) {
+  return v > ev || (v == ev && i > ei);
+}
+
+// One warp per stream ("hyp_merge"): log_softmax constants per live hypothesis from the tile partials,
+// per-stream top-K over the K*V extensions (value desc, flat index desc), extension, dedupe by
+// token-sequence hash with log-add, compaction in insertion order, back-pointer record.
+__global__ void __launch_bounds__(128)
+beam_select_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
+                   const float* __restrict__ part_m, const float* __restrict__ part_s,
+                   const float* __restrict__ part_tv, const int32_t* __restrict__ part_ti,
+                   BeamState in, BeamState out, int32_t* __restrict__ bp) {
+  __shared__ float s_mx[4][kMaxBeam], s_ls[4][kMaxBeam], s_lp[4][kMaxBeam];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * 4 + wib;
+  if (s >= B) return;
+  const int nl = in.nlive[s];
+
+  for (int h = 0; h < nl; ++h) {
+    const size_t row = (size_t)s * K + h;
+    float mx = -INFINITY, sum = 0.f;
+    for (int tile = lane; tile < nt; tile += 32) {
+      const float pm = part_m[row * nt + tile], ps = part_s[row * nt + tile];
+      const float nm = fmaxf(mx, pm);
+      if (nm != -INFINITY) sum = sum * expf(mx - nm) + ps * expf(pm - nm);
+      mx = nm;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      const float omx = __shfl_xor_sync(0xffffffffu, mx, o), osum = __shfl_xor_sync(0xffffffffu, sum, o);
+      const float nm = fmaxf(mx, omx);
+      sum = (nm == -INFINITY) ? 0.f : sum * expf(mx - nm) + osum * expf(omx - nm);
+      mx = nm;
+    }
+    if (lane == 0) {
+      s_mx[wib][h] = mx;
+      s_ls[wib][h] = logf(sum);
+      s_lp[wib][h] = in.lp[row];
+    }
+  }
+  __syncwarp();
+
+  // lane-local top-K of this lane's share of the candidates
+  float tv[kMaxBeam];
+  int tf[kMaxBeam];
+#pragma unroll
+  for (int i = 0; i < kMaxBeam; ++i) { tv[i] = -INFINITY; tf[i] = -1; }
+  const int per_h = nt * K;
+  const int total = nl * per_h;
+  const size_t base = (size_t)s * K * per_h;
+  for (int c = lane; c < total; c += 32) {
+    const int idx = part_ti[base + c];
+    if (idx < 0) continue;
+    const int h = c / per_h;
+    // same operation order as log_softmax(x) + lp : ((x - max) - log(sum)) + lp
+    float v = ((part_tv[base + c] - s_mx[wib][h]) - s_ls[wib][h]) + s_lp[wib][h];
+    int f = h * V + idx;
+    if (!(v == v)) continue;
+#pragma unroll
+    for (int i = 0; i < kMaxBeam; ++i) {
+      if (i < K && better(v, f, tv[i], tf[i])) {
+        const float fv = tv[i]; const int ff = tf[i];
+        tv[i] = v; tf[i] = f; v = fv; f = ff;
+      }
+    }
+  }
+
+  // K rounds of warp arg-best; lane r (< K) keeps winner r
+  float my_v = -INFINITY;
+  int my_f = -1;
+#pragma unroll
+  for (int r = 0; r < kMaxBeam; ++r) {
+    if (r < K) {
+      float bv = tv[0];
+      int bf = tf[0];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int of = __shfl_xor_sync(0xffffffffu, bf, o);
+        if (of >= 0 && (bf < 0 || better(ov, of, bv, bf))) { bv = ov; bf = of; }
+      }
+      if (bf >= 0 && tf[0] == bf) {   // flat indices are unique: exactly one lane pops
+#pragma unroll
+        for (int i = 0; i + 1 < kMaxBeam; ++i) { tv[i] = tv[i + 1]; tf[i] = tf[i + 1]; }
+        tv[kMaxBeam - 1] = -INFINITY; tf[kMaxBeam - 1] = -1;
+      }
+      if (lane == r) { my_v = bv; my_f = bf; }
+    }
+  }
+
+  // lane r < K: the r-th extension in rank order
+  const bool cand = lane < K && my_f >= 0;
+  int par = 0, tok = -1, c0 = -1, c1 = blank, ln = 2;
+  uint64_t hs = kHashSeed;
+  if (cand) {
+    par = my_f / V;
+    const int y = my_f - par * V;
+    const size_t prow = (size_t)s * K + par;
+    hs = in.hash[prow];
+    ln = in.len[prow];
+    c0 = in.ctx[2 * prow];
+    c1 = in.ctx[2 * prow + 1];
+    if (y != blank && y != unk) {      // ys unchanged for blank / unk
+      tok = y;
+      hs = hash_push(hs, y);
+      ln += 1;
+      c0 = c1;
+      c1 = y;
+    }
+  }
+  // dedupe: first earlier lane holding the same token sequence
+  int root = lane;
+  for (int q = 0; q < K; ++q) {
+    const uint64_t qh = __shfl_sync(0xffffffffu, hs, q);
+    const int ql = __shfl_sync(0xffffffffu, ln, q);
+    const int q0 = __shfl_sync(0xffffffffu, c0, q);
+    const int q1 = __shfl_sync(0xffffffffu, c1, q);
+    const int qc = __shfl_sync(0xffffffffu, (int)cand, q);
+    if (cand && qc && q < lane && root == lane && qh == hs && ql == ln && q0 == c0 && q1 == c1) root = q;
+  }
+  // log-add the merged scores into their root, in insertion (rank) order
+  float lp = my_v;
+  for (int q = 0; q < K; ++q) {
+    const int qroot = __shfl_sync(0xffffffffu, root, q);
+    const float qv = __shfl_sync(0xffffffffu, my_v, q);
+    const int qc = __shfl_sync(0xffffffffu, (int)cand, q);
+    if (cand && qc && q != lane && qroot == lane) lp = logaddexp_f(lp, qv);
+  }
+  const bool is_root = cand && root == lane;
+  const unsigned roots = __ballot_sync(0xffffffffu, is_root);
+  const int nnew = __popc(roots);
+  if (is_root) {
+    const int slot = __popc(roots & ((1u << lane) - 1u));
+    const size_t o = (size_t)s * K + slot;
+    out.ctx[2 * o] = c0;
+    out.ctx[2 * o + 1] = c1;
+    out.lp[o] = lp;
+    out.len[o] = ln;
+    out.hash[o] = hs;
+    bp[((size_t)s * T + t) * K + slot] = (par << 28) | (tok + 1);
+  }
+  if (lane >= nnew && lane < K) {      // dead slots keep a valid context for the next decoder GEMM
+    const size_t o = (size_t)s * K + lane;
+    out.ctx[2 * o] = -1;
+    out.ctx[2 * o + 1] = blank;
+    out.lp[o] = -INFINITY;
+    out.len[o] = 2;
+    out.hash[o] = kHashSeed;
+    bp[((size_t)s * T + t) * K + lane] = 0;
+  }
+  if (lane == 0) out.nlive[s] = nnew;
+}
+
+// One warp per stream: pick argmax lp/len (first maximum in slot order), walk the back-pointers in
+// shared memory, write tokens / timestamps in forward order.
+__global__ void __launch_bounds__(32)
+beam_backtrace_kernel(int B, int K, int T, BeamState fin, const int32_t* __restrict__ bp, int64_t* __restrict__ tokens,
+                      int32_t* __restrict__ ts, int32_t* __restrict__ n_out, float* __restrict__ score, int cap) {
+  extern __shared__ int32_t sm[];
+  int32_t* trel = sm;                 // [T*K]
+  int32_t* rtok = sm + (size_t)T * K; // [T]
+  int32_t* rts = rtok + T;            // [T]
+  const int s = blockIdx.x, lane = threadIdx.x;
+  const int32_t* src = bp + (size_t)s * T * K;
+  for (int i = lane; i < T * K; i += 32) trel[i] = src[i];
+  __syncwarp();
+  int n = 0;
+  if (lane == 0) {
+    const int nl = fin.nlive[s];
+    int best = 0;
+    float bn = -INFINITY;
+    for (int q = 0; q < nl; ++q) {
+      const float norm = __fdiv_rn(fin.lp[(size_t)s * K + q], (float)fin.len[(size_t)s * K + q]);
+      if (q == 0 || norm > bn) { bn = norm; best = q; }
+    }
+    score[s] = fin.lp[(size_t)s * K + best];
+    int slot = best;
+    for (int t = T - 1; t >= 0; --t) {
+      const int e = trel[t * K + slot];
+      const int tok = (e & 0x0fffffff) - 1;
+      if (tok >= 0) { rtok[n] = tok; rts[n] = t; ++n; }
+      slot = (e >> 28) & 0xf;
+    }
+    n_out[s] = n;
+  }
+  n = __shfl_sync(0xffffffffu, n, 0);
+  __syncwarp();
+  for (int i = lane; i < n && i < cap; i += 32) {
+    tokens[(size_t)s * cap + i] = rtok[n - 1 - i];
+    ts[(size_t)s * cap + i] = rts[n - 1 - i];
+  }
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+BeamState carve_state(char*& p, int B, int K) {
+  const size_t N = (size_t)B * K;
+  BeamState s;
+  s.ctx = reinterpret_cast<int32_t*>(p);  p += align256(N * 2 * sizeof(int32_t));
+  s.lp = reinterpret_cast<float*>(p);     p += align256(N * sizeof(float));
+  s.len = reinterpret_cast<int32_t*>(p);  p += align256(N * sizeof(int32_t));
+  s.hash = reinterpret_cast<uint64_t*>(p); p += align256(N * sizeof(uint64_t));
+  s.nlive = reinterpret_cast<int32_t*>(p); p += align256((size_t)B * sizeof(int32_t));
+  return s;
+}
+
+size_t state_bytes(int B, int K) {
+  const size_t N = (size_t)B * K;
+  return align256(N * 8) + align256(N * 4) + align256(N * 4) + align256(N * 8) + align256((size_t)B * 4);
+}
+
+}  // namespace
+
+void prof_begin(k2b_handle* h) {
+  if (!h->profile_on) return;
+  ProfEvents& p = h->prof;
+  if (p.used == p.start.size()) {
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { h->profile_on = false; return; }
+    p.start.push_back(a);
+    p.stop.push_back(b);
+  }
+  cudaEventRecord(p.start[p.used], h->stream);
+}
+
+void prof_end(k2b_handle* h) {
+  if (!h->profile_on) return;
+  ProfEvents& p = h->prof;
+  cudaEventRecord(p.stop[p.used], h->stream);
+  p.used++;
+}
+
+int32_t greedy_dev(k2b_handle* h, const float* enc, int B, int T, int mode, bool online, int64_t* hyp_inout,
+                   int64_t* tokens, int32_t* ts, int32_t* n_out, int cap) {
+  const k2b_config& c = h->cfg;
+  const int J = c.joiner_dim, V = c.vocab_size, D = c.decoder_dim;
+  const int nt = num_vocab_tiles(V);
+  K2B_TRY(ensure(h, h->ws_x, sizeof(float) * (size_t)B * J));
+  K2B_TRY(ensure(h, h->ws_part, (size_t)B * nt * 12));
+  K2B_TRY(ensure(h, h->ws_state, align256((size_t)B * 8) + 256));
+  int32_t* ctx = static_cast<int32_t*>(h->ws_state.p);
+  int32_t* flag = reinterpret_cast<int32_t*>(static_cast<char*>(h->ws_state.p) + align256((size_t)B * 8));
+  float* pval = static_cast<float*>(h->ws_part.p);
+  int32_t* pidx = reinterpret_cast<int32_t*>(pval + (size_t)B * nt);
+  int32_t* pnan = pidx + (size_t)B * nt;
+  float* x = static_cast<float*>(h->ws_x.p);
+
+  const int tb = 128, gb = (B + tb - 1) / tb;
+  greedy_init_kernel<<<gb, tb, 0, h->stream>>>(B, c.blank_id, online ? hyp_inout : nullptr, ctx, n_out, flag);
+  K2B_LAUNCH_CHECK(h);
+
+  const int max_sym = (mode == K2B_GREEDY_SINGLE && !online) ? 1000 : 0x7fffffff;
+  const int extra_mask = online ? 1 : -1;   // the literal `y != 1` of ref OnlineRecognizer.cs:181
+  for (int t = 0; t < T; ++t) {
+    GemmArgs d;
+    d.M = B; d.N = J; d.K = D;
+    d.W = h->dec_w; d.bias = h->dec_b;
+    d.ctx = ctx; d.tab0 = h->tab0; d.tab1 = h->tab1; d.V = V; d.neg_wrap = c.neg_id_mode == K2B_NEGID_WRAP;
+    d.blank = c.blank_id;
+    d.compat_flag = (mode == K2B_GREEDY_BATCH_COMPAT && !online) ? flag : nullptr;
+    d.enc = enc + (size_t)t * J; d.enc_stride = (long long)T * J; d.rows_per_stream = 1;
+    d.C = x;
+    K2B_TRY(launch_gemm_simt(h, PRO_DEC, EPI_TANH_ADD, d));
+
+    GemmArgs j;
+    j.M = B; j.N = V; j.K = J;
+    j.W = h->out_w; j.bias = h->out_b; j.A = x;
+    j.part_val = pval; j.part_idx = pidx; j.part_nan = pnan;
+    prof_begin(h);
+    K2B_TRY(launch_gemm_simt(h, PRO_PLAIN, EPI_ARGMAX, j));
+    prof_end(h);
+
+    greedy_select_kernel<<<gb, tb, 0, h->stream>>>(B, nt, pval, pidx, pnan, ctx, tokens, ts, n_out, cap, t, c.blank_id,
+                                                   c.unk_id, extra_mask, max_sym, flag);
+    K2B_LAUNCH_CHECK(h);
+  }
+  if (online) {
+    greedy_finish_online_kernel<<<gb, tb, 0, h->stream>>>(B, ctx, hyp_inout);
+    K2B_LAUNCH_CHECK(h);
+  }
+  return K2B_OK;
+}
+
+int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* tokens, int32_t* ts, int32_t* n_out,
+                 float* score, int cap) {
+  const k2b_config& c = h->cfg;
+  const int J = c.joiner_dim, V = c.vocab_size, D = c.decoder_dim;
+  const int nt = num_vocab_tiles(V);
+  const int N = B * K;
+  K2B_TRY(ensure(h, h->ws_x, sizeof(float) * (size_t)N * J));
+  K2B_TRY(ensure(h, h->ws_part, (size_t)N * nt * (8 + 8 * (size_t)K)));
+  K2B_TRY(ensure(h, h->ws_state, 2 * state_bytes(B, K)));
+  K2B_TRY(ensure(h, h->ws_bp, sizeof(int32_t) * (size_t)B * (T > 0 ? T : 1) * K));
+  char* p = static_cast<char*>(h->ws_state.p);
+  BeamState st[2];
+  st[0] = carve_state(p, B, K);
+  st[1] = carve_state(p, B, K);
+  float* part_m = static_cast<float*>(h->ws_part.p);
+  float* part_s = part_m + (size_t)N * nt;
+  float* part_tv = part_s + (size_t)N * nt;
+  int32_t* part_ti = reinterpret_cast<int32_t*>(part_tv + (size_t)N * nt * K);
+  int32_t* bp = static_cast<int32_t*>(h->ws_bp.p);
+  float* x = static_cast<float*>(h->ws_x.p);
+
+  beam_init_kernel<<<(N + 127) / 128, 128, 0, h->stream>>>(B, K, c.blank_id, st[0], st[1]);
+  K2B_LAUNCH_CHECK(h);
+
+  int cur = 0;
+  for (int t = 0; t < T; ++t) {
+    GemmArgs d;
+    d.M = N; d.N = J; d.K = D;
+    d.W = h->dec_w; d.bias = h->dec_b;
+    d.ctx = st[cur].ctx; d.tab0 = h->tab0; d.tab1 = h->tab1; d.V = V; d.neg_wrap = c.neg_id_mode == K2B_NEGID_WRAP;
+    d.blank = c.blank_id;
+    d.enc = enc + (size_t)t * J; d.enc_stride = (long long)T * J; d.rows_per_stream = K;
+    d.C = x;
+    K2B_TRY(launch_gemm_simt(h, PRO_DEC, EPI_TANH_ADD, d));
+
+    GemmArgs j;
+    j.M = N; j.N = V; j.K = J;
+    j.W = h->out_w; j.bias = h->out_b; j.A = x;
+    j.part_m = part_m; j.part_s = part_s; j.part_tv = part_tv; j.part_ti = part_ti; j.topk = K;
+    prof_begin(h);
+    K2B_TRY(launch_gemm_simt(h, PRO_PLAIN, EPI_TOPK, j));
+    prof_end(h);
+
+    beam_select_kernel<<<(B + 3) / 4, 128, 0, h->stream>>>(B, K, V, nt, T, t, c.blank_id, c.unk_id, part_m, part_s,
+                                                          part_tv, part_ti, st[cur], st[cur ^ 1], bp);
+    K2B_LAUNCH_CHECK(h);
+    cur ^= 1;
+  }
+
+  const size_t smem = sizeof(int32_t) * ((size_t)T * K + 2 * (size_t)T);
+  if (smem > 200 * 1024) return fail(h, K2B_ERR_UNSUPPORTED, "modified_beam_search: T*K too large for the back-trace");
+  if (smem > 48 * 1024)
+    K2B_CUDA(h, cudaFuncSetAttribute(beam_backtrace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  beam_backtrace_kernel<<<B, 32, smem, h->stream>>>(B, K, T, st[cur], bp, tokens, ts, n_out, score, cap);
+  K2B_LAUNCH_CHECK(h);
+  return K2B_OK;
+}
+
+}  // namespace k2b
