@@ -172,6 +172,18 @@ K2B_API int32_t k2b_ctc_greedy_dev(k2b_handle* h, const float* logp, int32_t B, 
                            const int32_t* frame_offset, int64_t* prev_inout, int64_t* tokens, int32_t* ts,
                            int32_t* n_out, int32_t* trailing_blank_inout, int32_t cap);
 
+/* ---- diagnostics ---------------------------------------------------------------------------- */
+/* Hardware self-tests of the tcgen05 / TMEM / bulk-TMA / cluster building blocks (HOST pointers).
+ * k2b_selftest_umma: D[128,N] = A[128,K] * B[N,K]^T through tcgen05.mma; mode 0 = bf16 operands in
+ * shared memory, 1 = split-bf16 x3 all in shared memory, 2 = x3 with the low part of A resident in
+ * TMEM, 3 = bf16 with A resident in TMEM; use_tma != 0 stages A through one bulk TMA copy.          */
+K2B_API int32_t k2b_selftest_umma(k2b_handle* h, const float* A, const float* B, int32_t N, int32_t K,
+                                  int32_t mode, int32_t use_tma, float* D);
+/* k2b_selftest_cluster: nclusters clusters of csize CTAs exchange data through distributed shared
+ * memory; *bad = mismatching words, *ctas_done = CTAs that ran.                                     */
+K2B_API int32_t k2b_selftest_cluster(k2b_handle* h, int32_t csize, int32_t nclusters, int32_t* bad,
+                                     int32_t* ctas_done);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,8 @@ _SIGS = {
     "k2b_modified_beam_search_dev": (C.c_int32, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I]),
     "k2b_ctc_greedy": (C.c_int32, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I]),
     "k2b_ctc_greedy_dev": (C.c_int32, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I]),
+    "k2b_selftest_umma": (C.c_int32, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "k2b_selftest_cluster": (C.c_int32, [_P, _I, _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
 }
 
 
@@ -279,6 +281,19 @@ class Handle:
                                              _ptr(ts), _ptr(n), _ptr(tb), cap))
         toks, tss = self._unpack(tokens, ts, n)
         return toks, tss, tb, pv
+
+    # -- diagnostics ------------------------------------------------------------------------------------------
+    def selftest_umma(self, A: np.ndarray, B: np.ndarray, mode: int, use_tma: bool = False) -> np.ndarray:
+        A = np.ascontiguousarray(A, np.float32); B = np.ascontiguousarray(B, np.float32)
+        N, K = B.shape
+        D = np.zeros((128, N), np.float32)
+        self._check(self._lib.k2b_selftest_umma(self._h, _ptr(A), _ptr(B), N, K, mode, int(use_tma), _ptr(D)))
+        return D
+
+    def selftest_cluster(self, csize: int, nclusters: int):
+        bad, done = C.c_int32(-1), C.c_int32(-1)
+        self._check(self._lib.k2b_selftest_cluster(self._h, csize, nclusters, C.byref(bad), C.byref(done)))
+        return int(bad.value), int(done.value)
 
     # -- raw pointer access for device-resident / pinned buffers (bench.py, dist.py) ---------------------------
     def call(self, name: str, *args):

@@ -1,0 +1,233 @@
+// Hardware self-test of the tcgen05 building blocks the persistent search kernel relies on. It pins, on a real
+// B200, the encodings written out in sm100_ptx.cuh: K-major SWIZZLE_128B shared-memory operand layout and
+// descriptor, instruction descriptor, TMEM accumulator layout as seen by tcgen05.ld, the TMEM-resident A operand
+// (tcgen05.st packed bf16 pairs + tcgen05.mma with A in TMEM), bulk TMA copy + mbarrier transaction count, and a
+// cluster round trip through distributed shared memory.
+#include <string.h>
+
+#include "k2b_internal.h"
+#include "sm100_ptx.cuh"
+
+namespace k2b {
+
+namespace {
+
+using namespace ptx;
+
+constexpr int kM = 128;
+
+// mode 0: D = bf16(A) * bf16(B)^T                          (SS)
+// mode 1: D = Ah*Bh + Ah*Bl + Al*Bh, all operands in smem  (SS x3)
+// mode 2: same, with Al resident in TMEM                   (SS, SS, TS)
+// mode 3: D = bf16(A) * bf16(B)^T with A resident in TMEM  (TS)
+// `Apk` (optional): A_hi pre-packed by the host in the exact swizzled smem image, fetched with one bulk TMA copy.
+__global__ void __launch_bounds__(128)
+umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, const uint8_t* __restrict__ Apk, int N, int K,
+                     int mode, float* __restrict__ D, int* __restrict__ status) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int nkb = K / 64;
+  uint8_t* a_hi = smem;                                  // nkb tiles of 128 x 128 B
+  uint8_t* a_lo = a_hi + (size_t)nkb * 16384;
+  uint8_t* b_hi = a_lo + (size_t)nkb * 16384;            // nkb tiles of N x 128 B
+  uint8_t* b_lo = b_hi + (size_t)nkb * N * 128;
+  __shared__ uint64_t bar_mma, bar_tma;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(&bar_mma, 1);
+    mbar_init(&bar_tma, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  const uint32_t t_d = tbase;            // 32 columns of accumulator
+  const uint32_t t_a = tbase + 64;       // up to 256 columns of packed A
+  const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
+
+  if (Apk != nullptr && tid == 0) {
+    mbar_expect_tx(&bar_tma, (uint32_t)(nkb * 16384));
+    tma_bulk_g2s(a_hi, Apk, (uint32_t)(nkb * 16384), &bar_tma);
+  }
+  // A: thread = row
+  {
+    const float* row = A + (size_t)tid * K;
+    for (int k0 = 0; k0 < K; k0 += 64) {
+      uint32_t pk_hi[32], pk_lo[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float x0 = row[k0 + 2 * j], x1 = row[k0 + 2 * j + 1];
+        const float h0 = bf16_round(x0), h1 = bf16_round(x1);
+        pk_hi[j] = pack_bf16x2(h0, h1);
+        pk_lo[j] = pack_bf16x2(x0 - h0, x1 - h1);
+      }
+      uint8_t* th = a_hi + (size_t)(k0 / 64) * 16384;
+      uint8_t* tl = a_lo + (size_t)(k0 / 64) * 16384;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (Apk == nullptr) *reinterpret_cast<uint32_t*>(th + sw128_offset(tid, 2 * j)) = pk_hi[j];
+        *reinterpret_cast<uint32_t*>(tl + sw128_offset(tid, 2 * j)) = pk_lo[j];
+      }
+      if (mode == 2) tmem_st32(t_a + lane_base + (uint32_t)(k0 / 2), pk_lo);
+      if (mode == 3) tmem_st32(t_a + lane_base + (uint32_t)(k0 / 2), pk_hi);
+    }
+    if (mode >= 2) tmem_st_wait();
+  }
+  if (tid < N) {
+    const float* row = B + (size_t)tid * K;
+    for (int k = 0; k < K; k += 2) {
+      const float x0 = row[k], x1 = row[k + 1];
+      const float h0 = bf16_round(x0), h1 = bf16_round(x1);
+      const size_t tile = (size_t)(k / 64) * N * 128;
+      *reinterpret_cast<uint32_t*>(b_hi + tile + sw128_offset(tid, k & 63)) = pack_bf16x2(h0, h1);
+      *reinterpret_cast<uint32_t*>(b_lo + tile + sw128_offset(tid, k & 63)) = pack_bf16x2(x0 - h0, x1 - h1);
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  bool ok = true;
+  if (tid == 0) {
+    if (Apk != nullptr) ok = mbar_wait(&bar_tma, 0);
+    const uint32_t idesc = umma_idesc_bf16_f32(kM, N);
+    uint32_t acc = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t dah = umma_desc_k_sw128(smem_u32(a_hi + (size_t)kb * 16384) + k * 32);
+        const uint64_t dal = umma_desc_k_sw128(smem_u32(a_lo + (size_t)kb * 16384) + k * 32);
+        const uint64_t dbh = umma_desc_k_sw128(smem_u32(b_hi + (size_t)kb * N * 128) + k * 32);
+        const uint64_t dbl = umma_desc_k_sw128(smem_u32(b_lo + (size_t)kb * N * 128) + k * 32);
+        const uint32_t ta = t_a + (uint32_t)((kb * 4 + k) * 8);
+        if (mode == 3) {
+          umma_ts(t_d, ta, dbh, idesc, acc); acc = 1;
+        } else {
+          umma_ss(t_d, dah, dbh, idesc, acc); acc = 1;
+          if (mode >= 1) {
+            umma_ss(t_d, dah, dbl, idesc, 1);
+            if (mode == 1) umma_ss(t_d, dal, dbh, idesc, 1);
+            else umma_ts(t_d, ta, dbh, idesc, 1);
+          }
+        }
+      }
+    }
+    umma_commit(&bar_mma);
+  }
+  if (!mbar_wait(&bar_mma, 0)) ok = false;
+  tc_fence_after();
+  if (!ok) atomicExch(status, 1);
+  uint32_t v[32];
+  tmem_ld32(t_d + lane_base, v);
+  tmem_ld_wait();
+  for (int n = 0; n < N && n < 32; ++n) D[(size_t)tid * N + n] = __uint_as_float(v[n]);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
+// every CTA writes (rank+1)*1000 + its own tid into slot [rank] of every CTA of the cluster, then checks its slots
+__global__ void __launch_bounds__(64) cluster_selftest_kernel(int* __restrict__ out) {
+  __shared__ uint32_t slots[16][64];
+  const uint32_t rank = cluster_ctarank(), n = cluster_nctarank();
+  cluster_sync();                      // all CTAs of the cluster have started: remote smem is valid
+  for (uint32_t r = 0; r < n; ++r)
+    dsmem_st_u32(dsmem_map(smem_u32(&slots[rank][threadIdx.x]), r), (rank + 1) * 1000 + threadIdx.x);
+  cluster_sync();
+  int bad = 0;
+  for (uint32_t r = 0; r < n; ++r) bad += slots[r][threadIdx.x] != (r + 1) * 1000 + threadIdx.x;
+  if (bad) atomicAdd(out, bad);
+  if (threadIdx.x == 0) atomicAdd(out + 1, 1);
+  cluster_sync();                      // nobody exits while a peer may still write into it
+}
+
+}  // namespace
+
+}  // namespace k2b
+
+using namespace k2b;
+
+extern "C" {
+
+// Diagnostic entry point (HOST pointers). A [128,K], B [N,K] fp32; D [128,N]. K multiple of 64, <= 256; N multiple
+// of 16, <= 32. mode: see umma_selftest_kernel. use_tma != 0: A_hi arrives pre-swizzled through one bulk TMA copy.
+K2B_API int32_t k2b_selftest_umma(k2b_handle* h, const float* A, const float* B, int32_t N, int32_t K, int32_t mode,
+                                  int32_t use_tma, float* D) {
+  if (h == nullptr) return K2B_ERR_INVALID;
+  if (K % 64 || K > 256 || K <= 0 || N % 16 || N > 32 || N <= 0 || mode < 0 || mode > 3)
+    return fail(h, K2B_ERR_INVALID, "k2b_selftest_umma: bad shape");
+  K2B_CUDA(h, cudaSetDevice(h->cfg.device));
+  float *dA, *dB, *dD;
+  int* dS;
+  uint8_t* dP = nullptr;
+  K2B_CUDA(h, cudaMalloc(&dA, sizeof(float) * 128 * K));
+  K2B_CUDA(h, cudaMalloc(&dB, sizeof(float) * N * K));
+  K2B_CUDA(h, cudaMalloc(&dD, sizeof(float) * 128 * N));
+  K2B_CUDA(h, cudaMalloc(&dS, sizeof(int)));
+  K2B_CUDA(h, cudaMemcpy(dA, A, sizeof(float) * 128 * K, cudaMemcpyHostToDevice));
+  K2B_CUDA(h, cudaMemcpy(dB, B, sizeof(float) * N * K, cudaMemcpyHostToDevice));
+  K2B_CUDA(h, cudaMemset(dS, 0, sizeof(int)));
+  K2B_CUDA(h, cudaMemset(dD, 0, sizeof(float) * 128 * N));
+  const int nkb = K / 64;
+  if (use_tma) {
+    // host-side pre-pack of A_hi into the swizzled image (same function the kernel uses: row*128 + ((k/8)^(row&7))*16)
+    std::vector<uint8_t> img((size_t)nkb * 16384);
+    for (int m = 0; m < 128; ++m)
+      for (int k = 0; k < K; ++k) {
+        const float x = A[(size_t)m * K + k];
+        uint32_t u;
+        memcpy(&u, &x, 4);
+        const uint32_t r = ((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);
+        const uint16_t b = (uint16_t)r;
+        const int kk = k & 63;
+        const size_t off = (size_t)(k / 64) * 16384 + (size_t)m * 128 + (size_t)(((kk >> 3) ^ (m & 7)) * 16) + (kk & 7) * 2;
+        memcpy(&img[off], &b, 2);
+      }
+    K2B_CUDA(h, cudaMalloc(&dP, img.size()));
+    K2B_CUDA(h, cudaMemcpy(dP, img.data(), img.size(), cudaMemcpyHostToDevice));
+  }
+  const size_t smem = (size_t)nkb * (2 * 16384 + 2 * (size_t)N * 128);
+  K2B_CUDA(h, cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_selftest_kernel<<<1, 128, smem, h->stream>>>(dA, dB, dP, N, K, mode, dD, dS);
+  K2B_LAUNCH_CHECK(h);
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  int st = 0;
+  K2B_CUDA(h, cudaMemcpy(&st, dS, sizeof(int), cudaMemcpyDeviceToHost));
+  K2B_CUDA(h, cudaMemcpy(D, dD, sizeof(float) * 128 * N, cudaMemcpyDeviceToHost));
+  cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dS);
+  if (dP) cudaFree(dP);
+  if (st != 0) return fail(h, K2B_ERR_STATE, "k2b_selftest_umma: an mbarrier wait timed out");
+  return K2B_OK;
+}
+
+// Launches `nclusters` clusters of `csize` CTAs; returns the number of mismatching DSMEM slots in *bad.
+K2B_API int32_t k2b_selftest_cluster(k2b_handle* h, int32_t csize, int32_t nclusters, int32_t* bad, int32_t* ctas_done) {
+  if (h == nullptr || csize < 1 || csize > 16 || nclusters < 1) return K2B_ERR_INVALID;
+  K2B_CUDA(h, cudaSetDevice(h->cfg.device));
+  int* d;
+  K2B_CUDA(h, cudaMalloc(&d, 2 * sizeof(int)));
+  K2B_CUDA(h, cudaMemset(d, 0, 2 * sizeof(int)));
+  if (csize > 8) K2B_CUDA(h, cudaFuncSetAttribute(cluster_selftest_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(csize * nclusters);
+  cfg.blockDim = dim3(64);
+  cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  K2B_CUDA(h, cudaLaunchKernelEx(&cfg, cluster_selftest_kernel, d));
+  h->launches++;
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  int r[2];
+  K2B_CUDA(h, cudaMemcpy(r, d, sizeof(r), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  if (bad) *bad = r[0];
+  if (ctas_done) *ctas_done = r[1];
+  return K2B_OK;
+}
+
+}  // extern "C"
