@@ -29,6 +29,15 @@ void free_buf(DevBuf& b) {
   b.bytes = 0;
 }
 
+void free_cluster_assets(k2b_handle* h) {
+  if (h->wo_hi_img) cudaFree(h->wo_hi_img);
+  if (h->wo_lo) cudaFree(h->wo_lo);
+  if (h->bias_pad) cudaFree(h->bias_pad);
+  if (h->dec_tab) cudaFree(h->dec_tab);
+  h->wo_hi_img = nullptr; h->wo_lo = nullptr; h->bias_pad = nullptr; h->dec_tab = nullptr;
+  h->tc_ready = false;
+}
+
 int32_t enter(k2b_handle* h) {
   if (h == nullptr) return K2B_ERR_INVALID;
   if (h->poisoned) return K2B_ERR_STATE;
@@ -66,6 +75,36 @@ int32_t frames_for_search(k2b_handle* h, const float* enc_dev, int enc_is_raw, i
   K2B_TRY(encoder_proj_launch(h, enc_dev, (int)n, static_cast<float*>(h->ws_encproj.p)));
   *out = static_cast<const float*>(h->ws_encproj.p);
   return K2B_OK;
+}
+
+// modified_beam_search on the persistent cluster kernel (tcgen05 precisions): frames -> exp(2x) (fused into the
+// encoder_proj epilogue when the frames are raw), one launch for the whole time loop, then the back-trace.
+int32_t beam_cluster_path(k2b_handle* h, const float* enc, int enc_is_raw, int B, int T, int K, int64_t* tokens, int32_t* ts,
+                          int32_t* n_out, float* score, int cap) {
+  K2B_TRY(ensure_cluster_assets(h));
+  const size_t n = (size_t)B * T, J = h->cfg.joiner_dim;
+  K2B_TRY(ensure(h, h->ws_encproj, sizeof(float) * n * J));
+  float* encE = static_cast<float*>(h->ws_encproj.p);
+  if (enc_is_raw) {
+    if (h->cfg.encoder_dim <= 0 || h->enc_w == nullptr) return fail(h, K2B_ERR_STATE, "encoder_proj weights not loaded (E == 0)");
+    GemmArgs g;
+    g.M = (int)n; g.N = (int)J; g.K = h->cfg.encoder_dim;
+    g.A = enc; g.W = h->enc_w; g.bias = h->enc_b; g.C = encE;
+    K2B_TRY(launch_gemm_simt(h, PRO_PLAIN, EPI_EXP2X, g));
+  } else {
+    K2B_TRY(exp2x_frames(h, enc, encE, n * J));
+  }
+  const size_t NK = (size_t)B * K;
+  const size_t bytes = ((NK * 4 + 255) & ~size_t(255)) * 2 + (((size_t)B * 4 + 255) & ~size_t(255));
+  K2B_TRY(ensure(h, h->ws_state, bytes));
+  K2B_TRY(ensure(h, h->ws_bp, sizeof(int32_t) * (size_t)B * T * K));
+  char* p = static_cast<char*>(h->ws_state.p);
+  float* fin_lp = reinterpret_cast<float*>(p); p += (NK * 4 + 255) & ~size_t(255);
+  int32_t* fin_len = reinterpret_cast<int32_t*>(p); p += (NK * 4 + 255) & ~size_t(255);
+  int32_t* fin_nlive = reinterpret_cast<int32_t*>(p);
+  int32_t* bp = static_cast<int32_t*>(h->ws_bp.p);
+  K2B_TRY(beam_cluster_dev(h, encE, B, T, K, bp, fin_lp, fin_len, fin_nlive));
+  return beam_backtrace_dev(h, B, K, T, fin_lp, fin_len, fin_nlive, bp, tokens, ts, n_out, score, cap);
 }
 
 struct OutStage {
@@ -184,6 +223,7 @@ int32_t k2b_destroy(k2b_handle* h) {
   cudaStreamSynchronize(h->stream);
   float** ws[] = {&h->emb, &h->conv_w, &h->dec_w, &h->dec_b, &h->enc_w, &h->enc_b, &h->out_w, &h->out_b, &h->tab0, &h->tab1};
   for (float** p : ws) { if (*p) cudaFree(*p); *p = nullptr; }
+  free_cluster_assets(h);
   DevBuf* bufs[] = {&h->ws_in, &h->ws_encproj, &h->ws_x, &h->ws_dec, &h->ws_logits, &h->ws_part, &h->ws_state, &h->ws_bp,
                     &h->ws_out, &h->ws_misc, &h->ws_ctc};
   for (DevBuf* b : bufs) free_buf(*b);
@@ -205,6 +245,8 @@ int32_t k2b_load_weights(k2b_handle* h, const float* emb, const float* conv_w, c
     return fail(h, K2B_ERR_INVALID, "k2b_load_weights: encoder_dim > 0 needs enc_proj_w and enc_proj_b");
   const size_t V = c.vocab_size, J = c.joiner_dim, D = c.decoder_dim, E = c.encoder_dim, ctx = c.context_size;
   h->weights_loaded = false;
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  free_cluster_assets(h);
   K2B_TRY(upload(h, &h->emb, emb, V * D));
   K2B_TRY(upload(h, &h->conv_w, conv_w, D * 4 * ctx));
   K2B_TRY(upload(h, &h->dec_w, dec_proj_w, J * D));
@@ -228,8 +270,8 @@ int32_t k2b_load_weights(k2b_handle* h, const float* emb, const float* conv_w, c
 int32_t k2b_set_precision(k2b_handle* h, int32_t precision) {
   K2B_TRY(enter(h));
   if (precision < K2B_PREC_FP32 || precision > K2B_PREC_BF16) return fail(h, K2B_ERR_INVALID, "unknown precision");
-  if (precision != K2B_PREC_FP32)
-    return fail(h, K2B_ERR_UNSUPPORTED, "tcgen05 precisions are not built into this library version");
+  if (precision != K2B_PREC_FP32 && !cluster_path_supported(h, 4))
+    return fail(h, K2B_ERR_UNSUPPORTED, "tcgen05 precisions need V <= 1024, J <= 512 (multiple of 64) in this library version");
   h->cfg.precision = precision;
   return K2B_OK;
 }
@@ -454,6 +496,8 @@ int32_t k2b_modified_beam_search_dev(k2b_handle* h, const float* enc, int32_t en
   if (K > h->cfg.vocab_size) return fail(h, K2B_ERR_INVALID, "k2b_modified_beam_search: beam exceeds vocab_size");
   if (B > 0 && score == nullptr) return fail(h, K2B_ERR_INVALID, "k2b_modified_beam_search: score is NULL");
   if (B == 0) return K2B_OK;
+  if (h->cfg.precision != K2B_PREC_FP32 && cluster_path_supported(h, K) && T > 0)
+    return beam_cluster_path(h, enc, enc_is_raw, B, T, K, tokens, ts, n_out, score, cap);
   const float* frames = nullptr;
   K2B_TRY(frames_for_search(h, enc, enc_is_raw, B, T, &frames));
   return beam_dev(h, frames, B, T, K, tokens, ts, n_out, score, cap);
@@ -481,6 +525,7 @@ int32_t k2b_modified_beam_search(k2b_handle* h, const float* enc, int32_t enc_is
   K2B_CUDA(h, cudaMemcpyAsync(n_out, o.n, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
   K2B_CUDA(h, cudaMemcpyAsync(score, o.score, sizeof(float) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
   K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->cfg.precision != K2B_PREC_FP32 && cluster_path_supported(h, K) && T > 0) K2B_TRY(cluster_status(h));
   return K2B_OK;
 }
 

@@ -6,6 +6,7 @@
 //                                                                  decoder_proj      (ref OfflineProjOfTransducer.cs:116)
 //   PRO_JOIN  A(m,k) = tanh(enc[s(m)][k] + dec[m][k])              joiner prologue   (ref OfflineProjOfTransducer.cs:146)
 //   EPI_TANH_ADD  C = tanh(acc + bias + enc[s(m)][n])              decoder_proj fused with the joiner prologue
+//   EPI_EXP2X     C = exp(2*clamp(acc + bias, +-40))                  feeds the cluster kernel's tanh-from-exp prologue
 //   EPI_ARGMAX    per (row, 64-column vocab tile) argmax, ties and NaN -> larger index
 //                                                                  (ref OfflineRecognizer.cs:150-154)
 //   EPI_TOPK      per (row, tile) max, sum-exp and top-k           (log_softmax + top-k of modified_beam_search)
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(kThreads) gemm_simt_kernel(const GemmArgs a) {
     bv[j] = (a.bias != nullptr && n < a.N) ? __ldg(a.bias + n) : 0.f;
   }
 
-  if (EPI == EPI_STORE || EPI == EPI_TANH_ADD) {
+  if (EPI == EPI_STORE || EPI == EPI_TANH_ADD || EPI == EPI_EXP2X) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int m = m0 + ty * 4 + i;
@@ -168,6 +169,7 @@ __global__ void __launch_bounds__(kThreads) gemm_simt_kernel(const GemmArgs a) {
         if (n >= a.N) continue;
         float v = acc[i][j] + bv[j];
         if (EPI == EPI_TANH_ADD) v = tanhf(v + __ldg(e + n));
+        if (EPI == EPI_EXP2X) v = expf(2.f * fminf(fmaxf(v, -40.f), 40.f));
         a.C[(size_t)m * a.N + n] = v;
       }
     }
@@ -302,6 +304,8 @@ int32_t launch_gemm_simt(k2b_handle* h, Pro pro, Epi epi, const GemmArgs& a) {
   K2B_CASE(PRO_DEC, EPI_TANH_ADD)
   K2B_CASE(PRO_PLAIN, EPI_ARGMAX)
   K2B_CASE(PRO_PLAIN, EPI_TOPK)
+  K2B_CASE(PRO_PLAIN, EPI_EXP2X)
+  K2B_CASE(PRO_DEC, EPI_EXP2X)
 #undef K2B_CASE
   return fail(h, K2B_ERR_UNSUPPORTED, "GEMM prologue/epilogue combination not instantiated");
 }

@@ -70,6 +70,13 @@ struct k2b_handle {
   k2b::DevBuf ws_misc;      // int32 contexts of the fine-grained decoder call
   k2b::DevBuf ws_ctc;       // ctc: per-frame ids [B*T] + per-stream tickets [B] (tickets stay zero between launches)
 
+  // tensor-core (cluster) path assets, built on first use after a weight load (search_cluster.cu)
+  bool tc_ready = false;
+  uint8_t* wo_hi_img = nullptr;   // [CS][J/64][16 KB] bf16 hi of out_w in the swizzled shared-memory image
+  uint32_t* wo_lo = nullptr;      // [CS*128][J/2] bf16 lo of out_w, packed pairs (TMEM source)
+  float* bias_pad = nullptr;      // [CS*128] out_b, -inf beyond V
+  float* dec_tab = nullptr;       // [(V+1)*V, J] exp(2*decoder(y0,y1)): the memoised stateless decoder
+
   bool profile_on = false;
   k2b::ProfEvents prof;
 };
@@ -101,7 +108,7 @@ int32_t ensure(k2b_handle* h, DevBuf& b, size_t bytes);
 
 // ---- gemm_simt.cu ---------------------------------------------------------------------------
 enum Pro : int { PRO_PLAIN = 0, PRO_DEC = 1, PRO_JOIN = 2 };
-enum Epi : int { EPI_STORE = 0, EPI_TANH_ADD = 1, EPI_ARGMAX = 2, EPI_TOPK = 3 };
+enum Epi : int { EPI_STORE = 0, EPI_TANH_ADD = 1, EPI_ARGMAX = 2, EPI_TOPK = 3, EPI_EXP2X = 4 };
 
 struct GemmArgs {
   int M = 0, N = 0, K = 0;
@@ -152,6 +159,17 @@ int32_t greedy_dev(k2b_handle* h, const float* enc, int B, int T, int mode, bool
                    int64_t* hyp_inout, int64_t* tokens, int32_t* ts, int32_t* n_out, int cap);
 int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* tokens, int32_t* ts,
                  int32_t* n_out, float* score, int cap);
+
+int32_t beam_backtrace_dev(k2b_handle* h, int B, int K, int T, const float* lp, const int32_t* len, const int32_t* nlive,
+                           const int32_t* bp, int64_t* tokens, int32_t* ts, int32_t* n_out, float* score, int cap);
+
+// ---- search_cluster.cu -------------------------------------------------------------------------
+bool cluster_path_supported(const k2b_handle* h, int K);
+int32_t ensure_cluster_assets(k2b_handle* h);
+int32_t exp2x_frames(k2b_handle* h, const float* in, float* out, size_t n);
+int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, int32_t* bp, float* fin_lp, int32_t* fin_len,
+                         int32_t* fin_nlive);
+int32_t cluster_status(k2b_handle* h);
 
 // profiling bracket around the dominant GEMM
 void prof_begin(k2b_handle* h);

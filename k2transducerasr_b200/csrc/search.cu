@@ -444,11 +444,20 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
     cur ^= 1;
   }
 
+  return beam_backtrace_dev(h, B, K, T, st[cur].lp, st[cur].len, st[cur].nlive, bp, tokens, ts, n_out, score, cap);
+}
+
+int32_t beam_backtrace_dev(k2b_handle* h, int B, int K, int T, const float* lp, const int32_t* len, const int32_t* nlive,
+                           const int32_t* bp, int64_t* tokens, int32_t* ts, int32_t* n_out, float* score, int cap) {
+  BeamState fin{};
+  fin.lp = const_cast<float*>(lp);
+  fin.len = const_cast<int32_t*>(len);
+  fin.nlive = const_cast<int32_t*>(nlive);
   const size_t smem = sizeof(int32_t) * ((size_t)T * K + 2 * (size_t)T);
   if (smem > 200 * 1024) return fail(h, K2B_ERR_UNSUPPORTED, "modified_beam_search: T*K too large for the back-trace");
   if (smem > 48 * 1024)
     K2B_CUDA(h, cudaFuncSetAttribute(beam_backtrace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  beam_backtrace_kernel<<<B, 32, smem, h->stream>>>(B, K, T, st[cur], bp, tokens, ts, n_out, score, cap);
+  beam_backtrace_kernel<<<B, 32, smem, h->stream>>>(B, K, T, fin, bp, tokens, ts, n_out, score, cap);
   K2B_LAUNCH_CHECK(h);
   return K2B_OK;
 }

@@ -88,6 +88,8 @@ class Model:
     context_size: int = 2    # ref Model/OfflineCustomMetadata.cs:21
     neg_id_wrap: bool = False
     prec: str = "fp32"
+    prec_joiner: Optional[str] = None   # arithmetic of the joiner output GEMM only (None = prec): restates the
+                                        # library's tensor-core modes, whose decoder / encoder_proj stay fp32
 
     @property
     def V(self) -> int:
@@ -134,7 +136,7 @@ def joiner(m: Model, enc: np.ndarray, dec: np.ndarray) -> np.ndarray:
     """JoinerProj (ref OfflineProjOfTransducer.cs:125-152): logits = out_linear(tanh(enc + dec)),
     no softmax. [EXT] for the math."""
     x = np.tanh((np.asarray(enc, F32).reshape(-1, m.J) + np.asarray(dec, F32).reshape(-1, m.J)).astype(F32)).astype(F32)
-    return (_gemm_nt(x, m.out_w, m.prec) + m.out_b).astype(F32)
+    return (_gemm_nt(x, m.out_w, m.prec_joiner or m.prec) + m.out_b).astype(F32)
 
 
 def encoder_proj(m: Model, raw: np.ndarray) -> np.ndarray:

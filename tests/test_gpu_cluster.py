@@ -1,0 +1,112 @@
+"""GPU (-m gpu): the persistent cluster kernel (tcgen05 precisions) of modified_beam_search against the oracle.
+
+bf16x3 (split-bf16, three MMAs, fp32 accumulate) is the parity-grade tensor-core mode: token sequences must
+match the fp32 oracle except on near ties, scores within 1e-3. bf16 is the fast mode: it is compared against
+the oracle restated with bf16-rounded joiner operands (same tie rule), and its distance from fp32 is reported
+with a stated tolerance."""
+import numpy as np
+import pytest
+
+from k2transducerasr_b200 import _native, synth
+from oracle import k2_oracle as O
+from tests.helpers import MID, SCORE_TOL, compare_streams, model_and_weights
+
+pytestmark = pytest.mark.gpu
+
+BF16_SCORE_TOL = 0.25     # stated bf16 tolerance on the un-normalised hypothesis log-prob after 40 frames
+
+
+def make(dims, w, prec):
+    h = _native.Handle(vocab_size=dims.vocab_size, joiner_dim=dims.joiner_dim, decoder_dim=dims.decoder_dim,
+                       encoder_dim=dims.encoder_dim, precision=_native.PREC_NAMES[prec])
+    h.load_weights(w)
+    return h
+
+
+@pytest.fixture(scope="module")
+def setup(built_lib):
+    m, w = model_and_weights(MID, blank_bias=0.99)
+    raw = synth.make_frames(19, 40, MID.encoder_dim, 34)
+    enc = O.encoder_proj(m, raw)
+    return m, w, raw, enc
+
+
+@pytest.mark.parametrize("beam", [4, 1, 2, 8, 3])
+def test_cluster_bf16x3_matches_fp32_oracle(setup, beam):
+    m, w, raw, enc = setup
+    h = make(MID, w, "bf16x3")
+    want = O.modified_beam_search(m, enc, beam)
+    t, s, sc = h.modified_beam_search(raw, beam)
+    ex = compare_streams(t, s, want, f"cluster bf16x3 beam={beam}", allow_frac=0.12)
+    for b, r in enumerate(want):
+        if b not in ex:
+            assert abs(float(sc[b]) - r.score) < SCORE_TOL
+    # projected frames in (no encoder_proj on device) give the same answer
+    t2, s2, sc2 = h.modified_beam_search(enc, beam, enc_is_raw=False)
+    assert sum(a != b for a, b in zip(t, t2)) <= len(ex) + 1
+    h.close()
+
+
+def test_cluster_bf16_matches_bf16_oracle_and_is_near_fp32(setup):
+    m, w, raw, enc = setup
+    h = make(MID, w, "bf16")
+    mb = O.Model.from_dict(w, prec_joiner="bf16")
+    want = O.modified_beam_search(mb, enc, 4)
+    t, s, sc = h.modified_beam_search(raw, 4)
+    ex = compare_streams(t, s, want, "cluster bf16 vs bf16 oracle", allow_frac=0.3)
+    for b, r in enumerate(want):
+        if b not in ex:
+            assert abs(float(sc[b]) - r.score) < 5e-3
+    ref = O.modified_beam_search(m, enc, 4)
+    same = sum(a == r.appended for a, r in zip(t, ref))
+    print(f"bf16 vs fp32 oracle: {same}/{len(ref)} streams identical; max |score diff| "
+          f"{max(abs(float(a) - r.score) for a, r in zip(sc, ref)):.4f}")
+    assert max(abs(float(a) - r.score) for a, r in zip(sc, ref)) < BF16_SCORE_TOL
+    h.close()
+
+
+def test_cluster_equals_per_step_path(setup):
+    """Same library, two engines: per-step fp32 CUDA-core kernels vs the persistent tcgen05 cluster kernel."""
+    m, w, raw, enc = setup
+    hf = make(MID, w, "fp32")
+    hx = make(MID, w, "bf16x3")
+    tf, sf, scf = hf.modified_beam_search(raw, 4)
+    tx, sx, scx = hx.modified_beam_search(raw, 4)
+    diff = [b for b in range(len(tf)) if tf[b] != tx[b] or sf[b] != sx[b]]
+    want = O.modified_beam_search(m, enc, 4)
+    assert all(want[b].min_gap < 1e-4 for b in diff), diff
+    np.testing.assert_allclose(np.delete(scf, diff), np.delete(scx, diff), atol=SCORE_TOL)
+    hf.close(); hx.close()
+
+
+def test_cluster_ragged_stream_count_and_switching(setup):
+    """B not a multiple of the streams-per-cluster; precision switched on a live handle."""
+    m, w, raw, enc = setup
+    h = make(MID, w, "fp32")
+    t0, s0, _ = h.modified_beam_search(raw[:5], 4)
+    h.set_precision("bf16x3")
+    t1, s1, _ = h.modified_beam_search(raw[:5], 4)
+    want = O.modified_beam_search(m, enc[:5], 4)
+    compare_streams(t1, s1, want, "cluster B=5", allow_frac=0.5)
+    t2, s2, _ = h.modified_beam_search(raw[:1, :3], 4)
+    compare_streams(t2, s2, O.modified_beam_search(m, enc[:1, :3], 4), "cluster B=1 T=3", allow_frac=1.0)
+    h.close()
+
+
+def test_cluster_full_size_cfg2(built_lib):
+    cfg = synth.CONFIGS["cfg2"]
+    m, w = model_and_weights(cfg.dims, blank_bias=cfg.blank_bias)
+    h = make(cfg.dims, w, "bf16x3")
+    raw = synth.make_frames(cfg.streams, cfg.frames, cfg.dims.encoder_dim, cfg.seed)
+    t1, s1, sc1 = h.modified_beam_search(raw, 4)
+    t2, s2, sc2 = h.modified_beam_search(raw, 4)
+    assert t1 == t2 and s1 == s2 and sc1.tolist() == sc2.tolist()          # deterministic
+    ta, sa, sca = h.modified_beam_search(np.ascontiguousarray(raw[64:128]), 4)
+    assert ta == t1[64:128] and sa == s1[64:128]                            # independent of batch neighbours
+    enc = O.encoder_proj(m, raw[:8])
+    want = O.modified_beam_search(m, enc, 4)
+    ex = compare_streams(t1[:8], s1[:8], want, "cluster cfg2 spot", allow_frac=0.5)
+    for b in range(8):
+        if b not in ex:
+            assert abs(float(sc1[b]) - want[b].score) < SCORE_TOL
+    h.close()
