@@ -181,7 +181,11 @@ def run_ours(args, cfg):
     h.load_weights(synth.make_weights(d, blank_bias=cfg.blank_bias))
     if prec != _native.PREC_FP32:
         h.set_precision(prec)
-    stream = torch.cuda.current_stream()
+    # a real (non-legacy) stream shared by torch's events and the library's launches: the legacy default stream has
+    # handle 0, which k2b_set_stream reads as "use the handle's own stream" and torch events would then see nothing
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     h.set_stream(stream.cuda_stream)
 
     # two distinct batches per rank, alternated, each 196 MB > the 126 MB L2

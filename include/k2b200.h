@@ -179,10 +179,22 @@ K2B_API int32_t k2b_ctc_greedy_dev(k2b_handle* h, const float* logp, int32_t B, 
  * TMEM, 3 = bf16 with A resident in TMEM; use_tma != 0 stages A through one bulk TMA copy.          */
 K2B_API int32_t k2b_selftest_umma(k2b_handle* h, const float* A, const float* B, int32_t N, int32_t K,
                                   int32_t mode, int32_t use_tma, float* D);
+/* k2b_selftest_umma_bench: cycles to issue / complete reps*nkb*4 tcgen05.mma of one flavour
+ * (0 SS N=32, 1 SS N=64, 2 TS N=32, 3 TS N=64, 4 SS M=64 N=32, 5 SS N=128, 6 TS N=128).             */
+K2B_API int32_t k2b_selftest_umma_bench(k2b_handle* h, int32_t flavour, int32_t nkb, int32_t reps,
+                                        int64_t* cycles2);
+/* k2b_selftest_collectives: dependent-chain latency (cycles) of REDUX, a 5-level SHFL butterfly and BALLOT,
+ * for one warp alone [0..2] and with 16 warps running the chain concurrently [3..5].                  */
+K2B_API int32_t k2b_selftest_collectives(k2b_handle* h, int64_t* out6);
 /* k2b_selftest_cluster: nclusters clusters of csize CTAs exchange data through distributed shared
  * memory; *bad = mismatching words, *ctas_done = CTAs that ran.                                     */
 K2B_API int32_t k2b_selftest_cluster(k2b_handle* h, int32_t csize, int32_t nclusters, int32_t* bad,
                                      int32_t* ctas_done);
+
+/* Cycle totals of the eight phases of one frame step (build, sync, MMA issue, MMA wait, TMEM read-out,
+ * reductions + DSMEM, cluster barrier, merge) summed over the last cluster-kernel launch, CTA 0. The first
+ * call switches the collection on.                                                                    */
+K2B_API int32_t k2b_cluster_phase_cycles(k2b_handle* h, int64_t* out8);
 
 #ifdef __cplusplus
 }

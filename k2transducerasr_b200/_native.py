@@ -66,6 +66,9 @@ _SIGS = {
     "k2b_ctc_greedy": (C.c_int32, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I]),
     "k2b_ctc_greedy_dev": (C.c_int32, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I]),
     "k2b_selftest_umma": (C.c_int32, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "k2b_cluster_phase_cycles": (C.c_int32, [_P, _P]),
+    "k2b_selftest_umma_bench": (C.c_int32, [_P, _I, _I, _I, _P]),
+    "k2b_selftest_collectives": (C.c_int32, [_P, _P]),
     "k2b_selftest_cluster": (C.c_int32, [_P, _I, _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
 }
 
@@ -289,6 +292,21 @@ class Handle:
         D = np.zeros((128, N), np.float32)
         self._check(self._lib.k2b_selftest_umma(self._h, _ptr(A), _ptr(B), N, K, mode, int(use_tma), _ptr(D)))
         return D
+
+    def cluster_phase_cycles(self):
+        out = np.zeros(8, np.int64)
+        self._check(self._lib.k2b_cluster_phase_cycles(self._h, _ptr(out)))
+        return out
+
+    def selftest_umma_bench(self, flavour: int, nkb: int = 4, reps: int = 8):
+        out = np.zeros(2, np.int64)
+        self._check(self._lib.k2b_selftest_umma_bench(self._h, flavour, nkb, reps, _ptr(out)))
+        return out
+
+    def selftest_collectives(self):
+        out = np.zeros(6, np.int64)
+        self._check(self._lib.k2b_selftest_collectives(self._h, _ptr(out)))
+        return out
 
     def selftest_cluster(self, csize: int, nclusters: int):
         bad, done = C.c_int32(-1), C.c_int32(-1)

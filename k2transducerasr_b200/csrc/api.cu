@@ -224,6 +224,7 @@ int32_t k2b_destroy(k2b_handle* h) {
   float** ws[] = {&h->emb, &h->conv_w, &h->dec_w, &h->dec_b, &h->enc_w, &h->enc_b, &h->out_w, &h->out_b, &h->tab0, &h->tab1};
   for (float** p : ws) { if (*p) cudaFree(*p); *p = nullptr; }
   free_cluster_assets(h);
+  if (h->cluster_timing) cudaFree(h->cluster_timing);
   DevBuf* bufs[] = {&h->ws_in, &h->ws_encproj, &h->ws_x, &h->ws_dec, &h->ws_logits, &h->ws_part, &h->ws_state, &h->ws_bp,
                     &h->ws_out, &h->ws_misc, &h->ws_ctc};
   for (DevBuf* b : bufs) free_buf(*b);
@@ -316,6 +317,20 @@ int32_t k2b_profile_read(k2b_handle* h, int64_t* n_launches, double* total_ms) {
   if (total_ms) *total_ms = p.ms_total;
   p.n_total = 0;
   p.ms_total = 0.0;
+  return K2B_OK;
+}
+
+// diagnostic: per-phase cycle totals of the last cluster-kernel launch (8 values); enables collection on first call
+K2B_API int32_t k2b_cluster_phase_cycles(k2b_handle* h, int64_t* out8) {
+  K2B_TRY(enter(h));
+  if (h->cluster_timing == nullptr) {
+    K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->cluster_timing), 8 * sizeof(long long)));
+    K2B_CUDA(h, cudaMemset(h->cluster_timing, 0, 8 * sizeof(long long)));
+  }
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  long long v[8];
+  K2B_CUDA(h, cudaMemcpy(v, h->cluster_timing, sizeof(v), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 8; ++i) out8[i] = v[i];
   return K2B_OK;
 }
 

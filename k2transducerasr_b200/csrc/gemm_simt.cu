@@ -6,7 +6,7 @@
 //                                                                  decoder_proj      (ref OfflineProjOfTransducer.cs:116)
 //   PRO_JOIN  A(m,k) = tanh(enc[s(m)][k] + dec[m][k])              joiner prologue   (ref OfflineProjOfTransducer.cs:146)
 //   EPI_TANH_ADD  C = tanh(acc + bias + enc[s(m)][n])              decoder_proj fused with the joiner prologue
-//   EPI_EXP2X     C = exp(2*clamp(acc + bias, +-40))                  feeds the cluster kernel's tanh-from-exp prologue
+//   EPI_EXP2X     C = exp(2*clamp(acc + bias, +-21))                  feeds the cluster kernel's tanh-from-exp prologue
 //   EPI_ARGMAX    per (row, 64-column vocab tile) argmax, ties and NaN -> larger index
 //                                                                  (ref OfflineRecognizer.cs:150-154)
 //   EPI_TOPK      per (row, tile) max, sum-exp and top-k           (log_softmax + top-k of modified_beam_search)
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(kThreads) gemm_simt_kernel(const GemmArgs a) {
         if (n >= a.N) continue;
         float v = acc[i][j] + bv[j];
         if (EPI == EPI_TANH_ADD) v = tanhf(v + __ldg(e + n));
-        if (EPI == EPI_EXP2X) v = expf(2.f * fminf(fmaxf(v, -40.f), 40.f));
+        if (EPI == EPI_EXP2X) v = expf(2.f * fminf(fmaxf(v, -21.f), 21.f));
         a.C[(size_t)m * a.N + n] = v;
       }
     }

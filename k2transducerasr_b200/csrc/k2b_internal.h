@@ -77,6 +77,8 @@ struct k2b_handle {
   float* bias_pad = nullptr;      // [CS*128] out_b, -inf beyond V
   float* dec_tab = nullptr;       // [(V+1)*V, J] exp(2*decoder(y0,y1)): the memoised stateless decoder
 
+  long long* cluster_timing = nullptr;   // device [8]: per-phase cycle totals of the cluster kernel (diagnostic)
+
   bool profile_on = false;
   k2b::ProfEvents prof;
 };

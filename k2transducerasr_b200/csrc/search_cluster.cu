@@ -53,11 +53,12 @@ struct ClusterArgs {
   int32_t* fin_len;         // [B*K]
   int32_t* fin_nlive;       // [B]
   int* status;
+  long long* timing;        // optional [8] cycle totals of the step phases (cluster 0, CTA 0, thread 0)
 };
 
-__device__ __forceinline__ int fkey(float f) { const int k = __float_as_int(f); return k >= 0 ? k : (k ^ 0x7fffffff); }
-__device__ __forceinline__ float funkey(int k) { return __int_as_float(k >= 0 ? k : (k ^ 0x7fffffff)); }
 __device__ __forceinline__ bool better_c(float v, int i, float ev, int ei) { return v > ev || (v == ev && i > ei); }
+
+__host__ __device__ constexpr int xw_padded(int K) { return ((2 + 2 * K + 3) / 4) * 4; }   // words per partial, 16 B multiple
 
 __device__ __forceinline__ uint64_t hash_push_c(uint64_t h, int tok) {
   h = (h ^ (uint64_t)(uint32_t)(tok + 1)) * 0x100000001B3ull;
@@ -72,19 +73,24 @@ __device__ __forceinline__ float logaddexp_c(float a, float b) {
   return mx + log1pf(expf(mn - mx));
 }
 
-// tanh(e + d) from Ee = exp(2e), Ed = exp(2d)
+// tanh(e + d) from Ee = exp(2e), Ed = exp(2d). e and d are clamped to +-21 when the tables are built, so the
+// product stays finite (e^84 < FLT_MAX) and tanh is already saturated to 1 ulp far inside that range.
 __device__ __forceinline__ float tanh_from_exp(float ee, float ed) {
   const float y = fmaf(ee, ed, 1.0f);
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));
-  r = r * fmaf(-y, r, 2.0f);                 // one Newton step: full fp32 accuracy, inf -> handled below
-  const float x = fmaf(-2.0f, r, 1.0f);
-  return (y > 3.0e38f) ? 1.0f : x;           // y = inf: r = 0 * (2 - inf*0 = NaN) -> select the limit
+  return fmaf(-2.0f, r, 1.0f);
 }
 
-// One warp: hypothesis merge of local stream s (see beam_select_kernel in search.cu for the global-memory twin).
-__device__ void select_stream(int s, int K, int V, int CS, int XW, const float* __restrict__ xb, const HypState& in,
-                              HypState& out, int blank, int unk, int32_t* __restrict__ bp_row, int lane) {
+__device__ __forceinline__ int fkey(float f) { const int k = __float_as_int(f); return k >= 0 ? k : (k ^ 0x7fffffff); }
+__device__ __forceinline__ float funkey(int k) { return __int_as_float(k >= 0 ? k : (k ^ 0x7fffffff)); }
+constexpr int kKeyNone = (int)0x80000000;
+
+// One warp: hypothesis merge of local stream s (beam_select_kernel in search.cu is the global-memory twin).
+template <int K>
+__device__ __forceinline__ void select_stream(int s, int V, int CS, const float* __restrict__ xb, const HypState& in,
+                                              HypState& out, int blank, int unk, int32_t* __restrict__ bp_row, int lane) {
+  constexpr int XWP = xw_padded(K);
   const unsigned full = 0xffffffffu;
   const int nl = in.nlive[s];
   if (nl == 0) {
@@ -95,75 +101,83 @@ __device__ void select_stream(int s, int K, int V, int CS, int XW, const float* 
     if (lane == 0) out.nlive[s] = 0;
     return;
   }
-  float M = -INFINITY, L = 0.f, LP = 0.f;
-  if (lane < nl) {
-    const int n = s * K + lane;
-    for (int c = 0; c < CS; ++c) M = fmaxf(M, xb[(c * kNH + n) * XW]);
-    float sum = 0.f;
-    for (int c = 0; c < CS; ++c) {
-      const float pm = xb[(c * kNH + n) * XW], ps = xb[(c * kNH + n) * XW + 1];
-      if (pm != -INFINITY) sum += ps * expf(pm - M);
-    }
-    L = logf(sum);
-    LP = in.lp[n];
+  // log_softmax constants: lane = (hyp h, slice c), 8 lanes per hypothesis, 4 hypotheses per pass
+  constexpr int kPass = (K + 3) / 4;
+  float Mp[kPass], Lp[kPass];
+#pragma unroll
+  for (int p = 0; p < kPass; ++p) {
+    const int h = p * 4 + (lane >> 3), c = lane & 7;
+    const bool valid = h < nl && c < CS;
+    const float* e = xb + ((size_t)c * kNH + s * K + h) * XWP;
+    const float pm = valid ? e[0] : -INFINITY, ps = valid ? e[1] : 0.f;
+    float M = pm;
+#pragma unroll
+    for (int off = 4; off >= 1; off >>= 1) M = fmaxf(M, __shfl_xor_sync(full, M, off));
+    float term = (pm > -INFINITY) ? ps * __expf(pm - M) : 0.f;
+#pragma unroll
+    for (int off = 4; off >= 1; off >>= 1) term += __shfl_xor_sync(full, term, off);
+    Mp[p] = M;
+    Lp[p] = __logf(term);
   }
-  float tv[kMaxBeam];
-  int tf[kMaxBeam];
+  // score this lane's share of the nl*CS*K candidates; lane = (slice, j), CPL candidates per lane in registers
+  constexpr int kSlots = (8 * K + 31) / 32;          // (slice, j) pairs per lane when CS = 8
+  constexpr int CPL = kSlots * K;                    // x up to K live hypotheses
+  int ckey[CPL], cflat[CPL];
 #pragma unroll
-  for (int i = 0; i < kMaxBeam; ++i) { tv[i] = -INFINITY; tf[i] = -1; }
-  const int per_h = CS * K, total = nl * per_h;
-  for (int base = 0; base < total; base += 32) {
-    const int c = base + lane;
-    const bool valid = c < total;
-    const int h = valid ? c / per_h : 0;
-    const float Mh = __shfl_sync(full, M, h), Lh = __shfl_sync(full, L, h), LPh = __shfl_sync(full, LP, h);
-    if (valid) {
-      const int r = c - h * per_h, slice = r / K, j = r - slice * K;
-      const float* e = xb + (slice * kNH + s * K + h) * XW;
-      const int idx = __float_as_int(e[2 + K + j]);
-      if (idx >= 0 && idx < V) {
-        float v = ((e[2 + j] - Mh) - Lh) + LPh;   // same operation order as log_softmax(x) + lp
-        int f = h * V + idx;
-        if (v == v) {
+  for (int i = 0; i < CPL; ++i) { ckey[i] = kKeyNone; cflat[i] = -1; }
+  const int per_h = CS * K;
 #pragma unroll
-          for (int i = 0; i < kMaxBeam; ++i) {
-            if (i < K && better_c(v, f, tv[i], tf[i])) {
-              const float fv = tv[i]; const int ff = tf[i];
-              tv[i] = v; tf[i] = f; v = fv; f = ff;
-            }
-          }
+  for (int h = 0; h < K; ++h) {
+    if (h < nl) {
+      const int src = (h & 3) * 8;
+      const float Mh = __shfl_sync(full, (h < 4) ? Mp[0] : Mp[kPass - 1], src);
+      const float Lh = __shfl_sync(full, (h < 4) ? Lp[0] : Lp[kPass - 1], src);
+      const float LPh = in.lp[s * K + h];
+#pragma unroll
+      for (int q = 0; q < kSlots; ++q) {
+        const int L = lane + 32 * q;
+        if (L < per_h) {
+          const int slice = L / K, j = L % K;
+          const float* e = xb + ((size_t)slice * kNH + s * K + h) * XWP;
+          const int idx = __float_as_int(e[2 + K + j]);
+          const float v = ((e[2 + j] - Mh) - Lh) + LPh;   // same operation order as log_softmax(x) + lp
+          if (idx >= 0 && v == v) { ckey[h * kSlots + q] = fkey(v); cflat[h * kSlots + q] = h * V + idx; }
         }
       }
     }
   }
+  // K rounds: warp max of the score key (REDUX), ties -> larger flat index (second REDUX), winner is retired
   float my_v = -INFINITY;
   int my_f = -1;
 #pragma unroll
-  for (int r = 0; r < kMaxBeam; ++r) {
-    if (r < K) {
-      const int hk = tf[0] >= 0 ? fkey(tv[0]) : (int)0x80000000;
-      const int wk = __reduce_max_sync(full, hk);
-      const int cf = (tf[0] >= 0 && hk == wk) ? tf[0] : -1;
-      const int wf = __reduce_max_sync(full, cf);
-      if (wf >= 0 && tf[0] == wf) {
+  for (int r = 0; r < K; ++r) {
+    int bk = kKeyNone, bf = -1;
 #pragma unroll
-        for (int i = 0; i + 1 < kMaxBeam; ++i) { tv[i] = tv[i + 1]; tf[i] = tf[i + 1]; }
-        tv[kMaxBeam - 1] = -INFINITY; tf[kMaxBeam - 1] = -1;
-      }
-      if (lane == r) { my_v = funkey(wk); my_f = wf; }
+    for (int i = 0; i < CPL; ++i)
+      if (cflat[i] >= 0 && (ckey[i] > bk || (ckey[i] == bk && cflat[i] > bf))) { bk = ckey[i]; bf = cflat[i]; }
+    const int wk = __reduce_max_sync(full, bk);
+    const int wf = __reduce_max_sync(full, (bf >= 0 && bk == wk) ? bf : -1);
+    if (wf >= 0) {
+#pragma unroll
+      for (int i = 0; i < CPL; ++i)
+        if (cflat[i] == wf) cflat[i] = -1;
     }
+    if (lane == r) { my_v = funkey(wk); my_f = wf; }
   }
+
   const bool cand = lane < K && my_f >= 0;
   int par = 0, tok = -1, c0 = -1, c1 = blank, ln = 2;
   uint64_t hs = kHashSeedC;
   if (cand) {
-    par = my_f / V;
+#pragma unroll
+    for (int hh = 1; hh < K; ++hh) par += (my_f >= hh * V) ? 1 : 0;
     const int y = my_f - par * V;
     const int prow = s * K + par;
     hs = in.hash[prow]; ln = in.len[prow]; c0 = in.ctx0[prow]; c1 = in.ctx1[prow];
     if (y != blank && y != unk) { tok = y; hs = hash_push_c(hs, y); ln += 1; c0 = c1; c1 = y; }
   }
   int root = lane;
+#pragma unroll
   for (int q = 0; q < K; ++q) {
     const uint64_t qh = __shfl_sync(full, hs, q);
     const int ql = __shfl_sync(full, ln, q), q0 = __shfl_sync(full, c0, q), q1 = __shfl_sync(full, c1, q);
@@ -171,11 +185,15 @@ __device__ void select_stream(int s, int K, int V, int CS, int XW, const float* 
     if (cand && qc && q < lane && root == lane && qh == hs && ql == ln && q0 == c0 && q1 == c1) root = q;
   }
   float lp = my_v;
-  for (int q = 0; q < K; ++q) {
-    const int qroot = __shfl_sync(full, root, q);
-    const float qv = __shfl_sync(full, my_v, q);
-    const int qc = __shfl_sync(full, (int)cand, q);
-    if (cand && qc && q != lane && qroot == lane) lp = logaddexp_c(lp, qv);
+  const unsigned merged = __ballot_sync(full, cand && root != lane);
+  if (merged) {                      // log-add merged scores into their root, in insertion (rank) order
+#pragma unroll
+    for (int q = 0; q < K; ++q) {
+      const int qroot = __shfl_sync(full, root, q);
+      const float qv = __shfl_sync(full, my_v, q);
+      const int qc = __shfl_sync(full, (int)cand, q);
+      if (cand && qc && q != lane && qroot == lane) lp = logaddexp_c(lp, qv);
+    }
   }
   const bool is_root = cand && root == lane;
   const unsigned roots = __ballot_sync(full, is_root);
@@ -194,7 +212,11 @@ __device__ void select_stream(int s, int K, int V, int CS, int XW, const float* 
   if (lane == 0) out.nlive[s] = nnew;
 }
 
+template <int K>
 __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const ClusterArgs a) {
+  constexpr int XWP = xw_padded(K);
+  constexpr int S = kNH / K;
+  constexpr int kXTile = 64 * 128;       // one k-block of the stacked [x_hi (32 rows); x_lo (32 rows)] operand
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ HypState st[2];
   __shared__ float bias_s[128];
@@ -202,16 +224,16 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);     // the compiler knows this one is warp-uniform
+  const uint32_t x3u = (uint32_t)a.x3;
   const uint32_t rank = cluster_ctarank();
   const int cluster = blockIdx.x / a.CS;
-  const int J = a.J, K = a.K, V = a.V, S = a.S, CS = a.CS, T = a.T;
+  const int J = a.J, V = a.V, CS = a.CS, T = a.T;
   const int nkb = J / 64;
-  const int XW = 2 + 2 * K;
   uint8_t* w_hi = smem;
-  uint8_t* b_hi = w_hi + (size_t)nkb * 16384;
-  uint8_t* b_lo = b_hi + (size_t)nkb * kNH * 128;
-  float* Lt = reinterpret_cast<float*>(b_hi);                      // aliases the B operand between MMA and next build
-  float* xch = reinterpret_cast<float*>(b_lo + (size_t)nkb * kNH * 128);   // [2][CS][NH][XW]
+  uint8_t* xop = w_hi + (size_t)nkb * 16384;                          // nkb tiles of 64 rows x 128 B
+  float* Lt = reinterpret_cast<float*>(xop);                          // aliases the operand between MMA and next build
+  float* xch = reinterpret_cast<float*>(xop + (size_t)nkb * kXTile);  // [2][CS][NH][XWP]
 
   if (tid == 0) {
     mbar_init(&bar_w, 1);
@@ -248,10 +270,9 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
   if (tid < 128) bias_s[tid] = a.bias[rank * 128 + tid];
   if (tid < kNH) {
     const int n = tid, h = n % K;
-    const bool used = n < S * K;
     for (int b = 0; b < 2; ++b) {
       st[b].ctx0[n] = -1; st[b].ctx1[n] = a.blank;
-      st[b].lp[n] = (used && h == 0) ? 0.f : -INFINITY;
+      st[b].lp[n] = (h == 0) ? 0.f : -INFINITY;
       st[b].len[n] = 2; st[b].hash[n] = kHashSeedC;
       st[b].nlive[n] = 0;
     }
@@ -264,143 +285,210 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
   tc_fence_after();
   cluster_sync();            // every CTA of the cluster is resident: remote shared memory may be written
 
-  const uint32_t idesc = umma_idesc_bf16_f32(128, kNH);
-  const uint32_t w_hi_u = smem_u32(w_hi), b_hi_u = smem_u32(b_hi), b_lo_u = smem_u32(b_lo);
+  long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const bool timed = a.timing != nullptr && blockIdx.x == 0 && tid == 0;
+  long long tlast = timed ? clock64() : 0;
+#define K2B_PHASE(i) do { if (timed) { const long long now = clock64(); tph[i] += now - tlast; tlast = now; } } while (0)
+
+  // UMMA descriptors: constant high word (SBO = 1024 B, version 1, SWIZZLE_128B), low word = address >> 4 | LBO
+  const uint32_t idesc64 = umma_idesc_bf16_f32(128, 64), idesc32 = umma_idesc_bf16_f32(128, 32);
+  const uint32_t desc_hi = 64u | (1u << 14) | (2u << 29);
+  const uint32_t w_lo0 = ((smem_u32(w_hi) & 0x3FFFFu) >> 4) | (1u << 16);
+  const uint32_t x_lo0 = ((smem_u32(xop) & 0x3FFFFu) >> 4) | (1u << 16);
   const int nq = J / 4;
   int cur = 0;
+
+  // the two hypothesis rows of this warp belong to one stream (K is even): its frame is prefetched one step ahead
+  const int n0 = warp * 2;
+  int g_w = cluster * S + n0 / K;
+  if (g_w >= a.B) g_w = a.B - 1;
+  const float4* enc_row = reinterpret_cast<const float4*>(a.encE + (size_t)g_w * T * J);
+  float4 ecur[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = lane + 32 * i;
+    if (q < nq) ecur[i] = __ldg(enc_row + q);
+  }
 
   for (int t = 0; t < T; ++t) {
     // ---- (a) joiner prologue: x[n,:] = tanh(enc[stream(n),t,:] + dec(ctx(n))) as bf16 hi/lo, K-major swizzled --
     {
       const HypState& sc = st[cur];
+      const float4* pd0 = reinterpret_cast<const float4*>(a.dec_tab + ((size_t)(sc.ctx0[n0] + 1) * V + sc.ctx1[n0]) * J);
+      const float4* pd1 = reinterpret_cast<const float4*>(a.dec_tab + ((size_t)(sc.ctx0[n0 + 1] + 1) * V + sc.ctx1[n0 + 1]) * J);
+      float4 d0[4], d1[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int q = lane + 32 * i;
+        if (q < nq) { d0[i] = __ldg(pd0 + q); d1[i] = __ldg(pd1 + q); }
+      }
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
-        const int n = warp * 2 + r;
-        int s = n / K;
-        if (s >= S) s = S - 1;
-        int g = cluster * S + s;
-        if (g >= a.B) g = a.B - 1;
-        const float4* pe = reinterpret_cast<const float4*>(a.encE + ((size_t)g * T + t) * J);
-        const float4* pd = reinterpret_cast<const float4*>(a.dec_tab + ((size_t)(sc.ctx0[n] + 1) * V + sc.ctx1[n]) * J);
-        float4 e[4], d[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int q = lane + 32 * i;
-          if (q < nq) { e[i] = __ldg(pe + q); d[i] = __ldg(pd + q); }
-        }
+        const int n = n0 + r;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int q = lane + 32 * i;
           if (q < nq) {
-            const float x0 = tanh_from_exp(e[i].x, d[i].x), x1 = tanh_from_exp(e[i].y, d[i].y);
-            const float x2 = tanh_from_exp(e[i].z, d[i].z), x3 = tanh_from_exp(e[i].w, d[i].w);
+            const float4 d = r ? d1[i] : d0[i];
+            const float x0 = tanh_from_exp(ecur[i].x, d.x), x1 = tanh_from_exp(ecur[i].y, d.y);
+            const float x2 = tanh_from_exp(ecur[i].z, d.z), x3 = tanh_from_exp(ecur[i].w, d.w);
             const int k = 4 * q;
-            const uint32_t off = (uint32_t)(k >> 6) * (kNH * 128) + sw128_offset(n, k & 63);
+            uint8_t* tile = xop + (size_t)(k >> 6) * kXTile;
             const float h0 = bf16_round(x0), h1 = bf16_round(x1), h2 = bf16_round(x2), h3 = bf16_round(x3);
-            *reinterpret_cast<uint2*>(b_hi + off) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+            *reinterpret_cast<uint2*>(tile + sw128_offset(n, k & 63)) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
             if (a.x3)
-              *reinterpret_cast<uint2*>(b_lo + off) = make_uint2(pack_bf16x2(x0 - h0, x1 - h1), pack_bf16x2(x2 - h2, x3 - h3));
+              *reinterpret_cast<uint2*>(tile + sw128_offset(32 + n, k & 63)) =
+                  make_uint2(pack_bf16x2(x0 - h0, x1 - h1), pack_bf16x2(x2 - h2, x3 - h3));
           }
         }
       }
+      if (t + 1 < T) {
+        const float4* pe = enc_row + (size_t)(t + 1) * nq;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int q = lane + 32 * i;
+          if (q < nq) ecur[i] = __ldg(pe + q);
+        }
+      }
     }
+    K2B_PHASE(0);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    K2B_PHASE(1);
 
-    // ---- (b) D[128 vocab, 32 hyps] = W_slice * x^T on the tensor core (one thread issues) --------------------
-    if (tid == 0) {
+    // ---- (b) D[128 vocab, hyps] = W_slice * x^T on the tensor core; the top warp issues, nobody spins on it -------
+    //      x3: one SS MMA with the stacked operand (N = 64: cols 0-31 = Wh*xh, 32-63 = Wh*xl) + one TS MMA
+    //      (A = Wl resident in TMEM, N = 32) accumulating Wl*xh into cols 0-31.
+    if (warp_u == kCThreads / 32 - 1) {      // warp-uniform loop: descriptors stay in uniform registers, one lane issues
+      const uint32_t el = elect_one();
       uint32_t acc = 0;
       for (int kb = 0; kb < nkb; ++kb) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint64_t dw = umma_desc_k_sw128(w_hi_u + kb * 16384 + k * 32);
-          const uint64_t dxh = umma_desc_k_sw128(b_hi_u + kb * (kNH * 128) + k * 32);
-          umma_ss(t_d, dw, dxh, idesc, acc);
+          const uint64_t dw = ((uint64_t)desc_hi << 32) | (uint64_t)(w_lo0 + (uint32_t)(kb * (16384 >> 4) + k * 2));
+          const uint64_t dx = ((uint64_t)desc_hi << 32) | (uint64_t)(x_lo0 + (uint32_t)(kb * (kXTile >> 4) + k * 2));
+          umma_ss_e(t_d, dw, dx, x3u ? idesc64 : idesc32, acc, el);
           acc = 1;
-          if (a.x3) {
-            const uint64_t dxl = umma_desc_k_sw128(b_lo_u + kb * (kNH * 128) + k * 32);
-            umma_ss(t_d, dw, dxl, idesc, 1);
-            umma_ts(t_d, t_wlo + (uint32_t)((kb * 4 + k) * 8), dxh, idesc, 1);
-          }
+          if (x3u) umma_ts_e(t_d, t_wlo + (uint32_t)((kb * 4 + k) * 8), dx, idesc32, 1, el);
         }
       }
-      umma_commit(&bar_mma);
+      umma_commit_e(&bar_mma, el);
     }
-    if (!mbar_wait(&bar_mma, (uint32_t)(t & 1))) ok = false;
-    tc_fence_after();
+    K2B_PHASE(2);
 
-    // ---- (c) accumulator -> registers (+bias) -> transposed shared tile ------------------------------------------
+    // ---- (c) accumulator -> registers (+bias) -> transposed shared tile (warps 0-3 own the 128 TMEM lanes) ----------
     if (warp < 4) {
-      uint32_t v[32];
-      tmem_ld32(t_d + lane_base, v);
-      tmem_ld_wait();
+      if (!mbar_wait(&bar_mma, (uint32_t)(t & 1))) ok = false;
+      tc_fence_after();
+      K2B_PHASE(3);
       const float bsv = bias_s[tid];
 #pragma unroll
-      for (int n = 0; n < kNH; ++n) Lt[tid * kLtStride + n] = __uint_as_float(v[n]) + bsv;
-    }
-    tc_fence_before();
-    __syncthreads();
-
-    // ---- (d) per hypothesis: max, sum-exp and top-K over this slice's 128 logits (warp REDUX) ----------------------
-    float* xw = xch + (size_t)(t & 1) * CS * kNH * XW;
+      for (int half = 0; half < 2; ++half) {
+        uint32_t va[16], vb[16];
+        tmem_ld16(t_d + lane_base + (uint32_t)(16 * half), va);
+        if (a.x3) tmem_ld16(t_d + lane_base + (uint32_t)(32 + 16 * half), vb);
+        tmem_ld_wait();
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int n = warp * 2 + r;
-      float v[4];
-      int key[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { v[j] = Lt[(lane + 32 * j) * kLtStride + n]; key[j] = fkey(v[j]); }
-      const int kmax = max(max(key[0], key[1]), max(key[2], key[3]));
-      const float m = funkey(__reduce_max_sync(0xffffffffu, kmax));
-      float sum = 0.f;
-      if (m != -INFINITY) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) sum += expf(v[j] - m);
-      }
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      unsigned taken = 0;
-      float out_v = -INFINITY;
-      int out_i = -1;
-      for (int rr = 0; rr < K; ++rr) {
-        int bk = (int)0x80000000, bj = -1;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (!((taken >> j) & 1u) && key[j] >= bk) { bk = key[j]; bj = j; }
-        const int wk = __reduce_max_sync(0xffffffffu, bk);
-        const int ci = (bj >= 0 && bk == wk) ? (int)(rank * 128 + lane + 32 * bj) : -1;
-        const int wi = __reduce_max_sync(0xffffffffu, ci);
-        if (ci == wi && wi >= 0) taken |= 1u << bj;
-        if (lane == rr) { out_v = funkey(wk); out_i = (wi >= 0 && wi < V) ? wi : -1; }
-      }
-      // partial of (slice = rank, hypothesis n) -> every CTA of the cluster
-      const uint32_t base = smem_u32(xw + ((size_t)rank * kNH + n) * XW);
-      for (uint32_t dst = 0; dst < (uint32_t)CS; ++dst) {
-        const uint32_t rb = dsmem_map(base, dst);
-        if (lane < K) {
-          dsmem_st_f32(rb + 4u * (2 + lane), out_v);
-          dsmem_st_u32(rb + 4u * (2 + K + lane), (uint32_t)out_i);
-        } else if (lane == K) {
-          dsmem_st_f32(rb, m);
-        } else if (lane == K + 1) {
-          dsmem_st_f32(rb + 4u, sum);
+        for (int n = 0; n < 16; ++n) {
+          float v = __uint_as_float(va[n]) + bsv;
+          if (a.x3) v += __uint_as_float(vb[n]);
+          Lt[tid * kLtStride + 16 * half + n] = v;
         }
       }
+      tc_fence_before();
     }
+    __syncthreads();
+    K2B_PHASE(4);
+
+    // ---- (d) per hypothesis (two per warp, interleaved): max, sum-exp and top-K over this slice's 128 logits ---------
+    float* xw = xch + (size_t)(t & 1) * CS * kNH * XWP;
+    {
+      float v[2][4];
+      int key[2][4];
+      float m[2], sum[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int n = warp * 2 + r;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[r][j] = Lt[(lane + 32 * j) * kLtStride + n];
+          const int idx = (int)rank * 128 + lane + 32 * j;
+          key[r][j] = idx < V ? fkey(v[r][j]) : kKeyNone;
+        }
+        m[r] = funkey(__reduce_max_sync(0xffffffffu, max(max(key[r][0], key[r][1]), max(key[r][2], key[r][3]))));
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        sum[r] = 0.f;
+        if (m[r] > -INFINITY) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sum[r] += (key[r][j] != kKeyNone) ? __expf(v[r][j] - m[r]) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        sum[0] += __shfl_xor_sync(0xffffffffu, sum[0], o);
+        sum[1] += __shfl_xor_sync(0xffffffffu, sum[1], o);
+      }
+      float out_v[2] = {-INFINITY, -INFINITY};
+      int out_i[2] = {-1, -1};
+#pragma unroll
+      for (int rr = 0; rr < K; ++rr) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          // this lane's best remaining logit; equal keys -> larger j = larger vocab index
+          int bk = kKeyNone, bj = -1;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (key[r][j] != kKeyNone && key[r][j] >= bk) { bk = key[r][j]; bj = j; }
+          const int wk = __reduce_max_sync(0xffffffffu, bk);
+          const int ci = (bj >= 0 && bk == wk) ? (int)rank * 128 + lane + 32 * bj : -1;
+          const int wi = __reduce_max_sync(0xffffffffu, ci);
+          if (ci == wi && wi >= 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j == bj) key[r][j] = kKeyNone;
+          }
+          if (lane == rr) { out_v[r] = funkey(wk); out_i[r] = wi; }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float* mine = xw + ((size_t)rank * kNH + warp * 2 + r) * XWP;
+        if (lane == 0) { mine[0] = m[r]; mine[1] = sum[r]; }
+        if (lane < K) { mine[2 + lane] = out_v[r]; reinterpret_cast<int*>(mine)[2 + K + lane] = out_i[r]; }
+      }
+      __syncwarp();
+      // copy both partials (contiguous) into the same slots of every other CTA of the cluster, 16 bytes per lane
+      constexpr int kChunks = 2 * XWP / 4;
+      const uint32_t base = smem_u32(xw + ((size_t)rank * kNH + warp * 2) * XWP);
+      for (int it = lane; it < kChunks * (CS - 1); it += 32) {
+        const int dsel = it / kChunks, ch = it - dsel * kChunks;
+        uint32_t dst = rank + 1 + (uint32_t)dsel;
+        if (dst >= (uint32_t)CS) dst -= (uint32_t)CS;
+        const uint4 q = lds_v4(base + 16u * ch);
+        dsmem_st_v4(dsmem_map(base + 16u * ch, dst), q.x, q.y, q.z, q.w);
+      }
+    }
+    K2B_PHASE(5);
     cluster_arrive();
     cluster_wait();
+    K2B_PHASE(6);
 
     // ---- (e) hypothesis merge, redundantly in every CTA --------------------------------------------------------
-    for (int s = warp; s < S; s += kCThreads / 32) {
-      const int g = cluster * S + s;
+    if (warp < S) {
+      const int s = warp, g = cluster * S + s;
       int32_t* bp_row = (rank == 0 && g < a.B) ? a.bp + ((size_t)g * T + t) * K : nullptr;
-      select_stream(s, K, V, CS, XW, xw, st[cur], st[cur ^ 1], a.blank, a.unk, bp_row, lane);
+      select_stream<K>(s, V, CS, xw, st[cur], st[cur ^ 1], a.blank, a.unk, bp_row, lane);
     }
     __syncthreads();
     cur ^= 1;
+    K2B_PHASE(7);
   }
+  if (timed) for (int i = 0; i < 8; ++i) a.timing[i] = tph[i];
+#undef K2B_PHASE
 
   if (rank == 0 && tid < S * K) {
     const int s = tid / K, hslot = tid % K, g = cluster * S + s;
@@ -443,7 +531,7 @@ __global__ void enum_ctx_kernel(int V, long long first, int n, int32_t* __restri
 
 __global__ void exp2x_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = expf(2.f * fminf(fmaxf(in[i], -40.f), 40.f));
+  if (i < n) out[i] = expf(2.f * fminf(fmaxf(in[i], -21.f), 21.f));
 }
 
 }  // namespace
@@ -452,8 +540,8 @@ bool cluster_path_supported(const k2b_handle* h, int K) {
   const k2b_config& c = h->cfg;
   const int CS = (c.vocab_size + 127) / 128;
   if (c.vocab_size > 1024 || c.joiner_dim > 512 || c.joiner_dim % 64) return false;
-  if (K < 1 || K > kMaxBeam) return false;
-  const size_t dyn = (size_t)(c.joiner_dim / 64) * (16384 + 2 * kNH * 128) + 2ull * CS * kNH * (2 + 2 * K) * 4;
+  if (K != 2 && K != 4 && K != 8) return false;      // both rows of a build warp must share one stream
+  const size_t dyn = (size_t)(c.joiner_dim / 64) * (16384 + 64 * 128) + 2ull * CS * kNH * xw_padded(K) * 4;
   if (dyn + 4096 > 227 * 1024) return false;
   const size_t tab = (size_t)(c.vocab_size + 1) * c.vocab_size * c.joiner_dim * sizeof(float);
   return tab <= ((size_t)16 << 30);
@@ -513,9 +601,11 @@ int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, 
   a.encE = encE; a.dec_tab = h->dec_tab; a.wo_hi_img = h->wo_hi_img; a.wo_lo = h->wo_lo; a.bias = h->bias_pad;
   a.B = B; a.T = T; a.K = K; a.V = V; a.J = J; a.S = S; a.CS = CS; a.blank = c.blank_id; a.unk = c.unk_id;
   a.x3 = c.precision == K2B_PREC_BF16X3 ? 1 : 0;
+  a.timing = h->cluster_timing;
   a.bp = bp; a.fin_lp = fin_lp; a.fin_len = fin_len; a.fin_nlive = fin_nlive; a.status = status;
-  const size_t dyn = (size_t)(J / 64) * (16384 + 2 * kNH * 128) + 2ull * CS * kNH * (2 + 2 * K) * 4;
-  K2B_CUDA(h, cudaFuncSetAttribute(cluster_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  const size_t dyn = (size_t)(J / 64) * (16384 + 64 * 128) + 2ull * CS * kNH * xw_padded(K) * 4;
+  void (*kern)(const ClusterArgs) = K == 2 ? cluster_beam_kernel<2> : (K == 4 ? cluster_beam_kernel<4> : cluster_beam_kernel<8>);
+  K2B_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(nclusters * CS));
   cfg.blockDim = dim3(kCThreads);
@@ -526,7 +616,7 @@ int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, 
   at[0].val.clusterDim.x = (unsigned)CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   prof_begin(h);
-  K2B_CUDA(h, cudaLaunchKernelEx(&cfg, cluster_beam_kernel, a));
+  K2B_CUDA(h, cudaLaunchKernelEx(&cfg, kern, a));
   prof_end(h);
   h->launches++;
   return K2B_OK;

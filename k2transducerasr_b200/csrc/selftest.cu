@@ -129,6 +129,120 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, c
   if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
+// MMA timing microbenchmark: `reps` back-to-back k-loops (nkb*4 MMAs each) of one flavour, cycles from first issue to
+// commit completion. flavour 0: SS N=32, 1: SS N=64, 2: TS N=32, 3: TS N=64, 4: SS N=32 with M=64, 5: SS N=128, 6: TS N=128,
+// 7/8/9: SS N=32 rotating over 2/4/8 independent TMEM accumulators, 10: SS N=64 over 4 accumulators
+__global__ void __launch_bounds__(128) umma_bench_kernel(int flavour, int nkb, int reps, long long* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint8_t* a_s = smem;                       // nkb x 16 KB
+  uint8_t* b_s = smem + (size_t)nkb * 16384; // nkb x 16 KB (up to 128 rows)
+  for (int i = tid; i < nkb * 32768 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + (i & 7);
+  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_slot;
+  const int nacc = flavour == 7 ? 2 : (flavour == 8 ? 4 : (flavour == 9 ? 8 : (flavour == 10 ? 4 : 1)));
+  const int N = (flavour == 1 || flavour == 3 || flavour == 10) ? 64 : ((flavour == 5 || flavour == 6) ? 128 : 32);
+  const int M = flavour == 4 ? 64 : 128;
+  const bool ts = flavour == 2 || flavour == 3 || flavour == 6;
+  const uint32_t idesc = umma_idesc_bf16_f32(M, N);
+  const uint32_t desc_hi = 64u | (1u << 14) | (2u << 29);
+  const uint32_t a0 = ((smem_u32(a_s) & 0x3FFFFu) >> 4) | (1u << 16), b0 = ((smem_u32(b_s) & 0x3FFFFu) >> 4) | (1u << 16);
+  const int wu = __shfl_sync(0xffffffffu, warp, 0);      // warp-uniform warp index
+  if (flavour >= 11 && wu == 3) {
+    // warp-uniform issue loop (flavour 11: SS N=32, 12: TS N=32, 13: SS N=64): descriptors live in uniform registers
+    const uint32_t el = elect_one();
+    const int N2 = flavour == 13 ? 64 : 32;
+    const uint32_t idesc2 = umma_idesc_bf16_f32(128, N2);
+    long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      for (int kb = 0; kb < nkb; ++kb) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a0 + (uint32_t)(kb * 1024 + k * 2));
+          const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b0 + (uint32_t)(kb * 1024 + k * 2));
+          if (flavour == 12) umma_ts_e(tb, tb + 384 + (uint32_t)((kb * 4 + k) * 8), db, idesc2, 1, el);
+          else umma_ss_e(tb, da, db, idesc2, 1, el);
+        }
+      }
+    }
+    long long t1 = clock64();
+    umma_commit_e(&bar, el);
+    mbar_wait(&bar, 0);
+    long long t2 = clock64();
+    if (el) { out[0] = t1 - t0; out[1] = t2 - t0; }
+  }
+  if (flavour < 11 && tid == 0) {
+    long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      for (int kb = 0; kb < nkb; ++kb) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a0 + (uint32_t)(kb * 1024 + k * 2));
+          const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b0 + (uint32_t)(kb * 1024 + k * 2));
+          const uint32_t td = tb + (uint32_t)(((kb * 4 + k) % nacc) * 64);   // rotate over independent accumulators
+          if (ts) umma_ts(td, tb + 384 + (uint32_t)((kb * 4 + k) * 8), db, idesc, 1);
+          else umma_ss(td, da, db, idesc, 1);
+        }
+      }
+    }
+    long long t1 = clock64();
+    umma_commit(&bar);
+    mbar_wait(&bar, 0);
+    long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
+// latency of dependent warp collectives: out[0] = cycles per __reduce_max_sync, out[1] = per 5-level shfl_xor max,
+// out[2] = per __ballot_sync, out[3] = per __reduce_max_sync when 16 warps run the same chain concurrently (out[4]: shfl)
+__global__ void __launch_bounds__(512) collective_bench_kernel(long long* __restrict__ out, int* __restrict__ sink) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int x = lane * 7 + 3;
+  const int reps = 256;
+  __syncthreads();
+  long long t0 = clock64();
+  for (int i = 0; i < reps; ++i) x = __reduce_max_sync(0xffffffffu, x ^ i) + lane;
+  long long t1 = clock64();
+  for (int i = 0; i < reps; ++i) {
+    int y = x ^ i;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) y = max(y, __shfl_xor_sync(0xffffffffu, y, o));
+    x = y + lane;
+  }
+  long long t2 = clock64();
+  for (int i = 0; i < reps; ++i) x = (int)__ballot_sync(0xffffffffu, (x ^ i) & 1) + lane;
+  long long t3 = clock64();
+  if (threadIdx.x == 0) { out[3] = (t1 - t0) / reps; out[4] = (t2 - t1) / reps; out[5] = (t3 - t2) / reps; }
+  __syncthreads();
+  if (warp == 0) {       // alone on the SM
+    long long a0 = clock64();
+    for (int i = 0; i < reps; ++i) x = __reduce_max_sync(0xffffffffu, x ^ i) + lane;
+    long long a1 = clock64();
+    for (int i = 0; i < reps; ++i) {
+      int y = x ^ i;
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) y = max(y, __shfl_xor_sync(0xffffffffu, y, o));
+      x = y + lane;
+    }
+    long long a2 = clock64();
+    for (int i = 0; i < reps; ++i) x = (int)__ballot_sync(0xffffffffu, (x ^ i) & 1) + lane;
+    long long a3 = clock64();
+    if (lane == 0) { out[0] = (a1 - a0) / reps; out[1] = (a2 - a1) / reps; out[2] = (a3 - a2) / reps; }
+  }
+  sink[threadIdx.x] = x;
+}
+
 // every CTA writes (rank+1)*1000 + its own tid into slot [rank] of every CTA of the cluster, then checks its slots
 __global__ void __launch_bounds__(64) cluster_selftest_kernel(int* __restrict__ out) {
   __shared__ uint32_t slots[16][64];
@@ -200,6 +314,40 @@ K2B_API int32_t k2b_selftest_umma(k2b_handle* h, const float* A, const float* B,
   cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dS);
   if (dP) cudaFree(dP);
   if (st != 0) return fail(h, K2B_ERR_STATE, "k2b_selftest_umma: an mbarrier wait timed out");
+  return K2B_OK;
+}
+
+// cycles[0] = issue loop, cycles[1] = until the commit barrier flips, for reps*nkb*4 MMAs of the given flavour.
+K2B_API int32_t k2b_selftest_umma_bench(k2b_handle* h, int32_t flavour, int32_t nkb, int32_t reps, int64_t* cycles2) {
+  if (h == nullptr || nkb < 1 || nkb > 6 || reps < 1) return K2B_ERR_INVALID;
+  K2B_CUDA(h, cudaSetDevice(h->cfg.device));
+  long long* d;
+  K2B_CUDA(h, cudaMalloc(&d, 2 * sizeof(long long)));
+  const size_t smem = (size_t)nkb * 32768;
+  K2B_CUDA(h, cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_bench_kernel<<<1, 128, smem, h->stream>>>(flavour, nkb, reps, d);
+  K2B_LAUNCH_CHECK(h);
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  long long r[2];
+  K2B_CUDA(h, cudaMemcpy(r, d, sizeof(r), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  cycles2[0] = r[0]; cycles2[1] = r[1];
+  return K2B_OK;
+}
+
+K2B_API int32_t k2b_selftest_collectives(k2b_handle* h, int64_t* out6) {
+  if (h == nullptr) return K2B_ERR_INVALID;
+  K2B_CUDA(h, cudaSetDevice(h->cfg.device));
+  long long* d; int* sink;
+  K2B_CUDA(h, cudaMalloc(&d, 6 * sizeof(long long)));
+  K2B_CUDA(h, cudaMalloc(&sink, 512 * sizeof(int)));
+  collective_bench_kernel<<<1, 512, 0, h->stream>>>(d, sink);
+  K2B_LAUNCH_CHECK(h);
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  long long r[6];
+  K2B_CUDA(h, cudaMemcpy(r, d, sizeof(r), cudaMemcpyDeviceToHost));
+  cudaFree(d); cudaFree(sink);
+  for (int i = 0; i < 6; ++i) out6[i] = r[i];
   return K2B_OK;
 }
 

@@ -1,0 +1,25 @@
+"""Per-phase cycle breakdown of the persistent cluster kernel on cfg2 (run on the GPU box)."""
+import sys
+import numpy as np
+sys.path.insert(0, ".")
+from k2transducerasr_b200 import _native, synth, build
+
+build.build()
+cfg = synth.CONFIGS["cfg2"]
+d = cfg.dims
+names = ["build x (gather+tanh+split)", "sync+fence", "MMA issue", "MMA wait", "TMEM->smem transpose", "reduce+DSMEM st",
+         "cluster barrier", "merge+sync"]
+for prec in ("bf16x3", "bf16"):
+    h = _native.Handle(vocab_size=d.vocab_size, joiner_dim=d.joiner_dim, decoder_dim=d.decoder_dim, encoder_dim=d.encoder_dim,
+                       precision=_native.PREC_NAMES[prec])
+    h.load_weights(synth.make_weights(d, blank_bias=cfg.blank_bias))
+    raw = synth.make_frames(cfg.streams, cfg.frames, d.encoder_dim, cfg.seed)
+    h.modified_beam_search(raw, 4)
+    h.cluster_phase_cycles()            # switch collection on
+    h.modified_beam_search(raw, 4)
+    cyc = h.cluster_phase_cycles()
+    tot = cyc.sum()
+    print(f"== {prec}: {tot / cfg.frames:.0f} cycles per frame step (CTA 0)")
+    for n, c in zip(names, cyc):
+        print(f"   {n:32s} {c / cfg.frames:8.0f} cyc  {100.0 * c / tot:5.1f} %")
+    h.close()
