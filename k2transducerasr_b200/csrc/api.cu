@@ -36,6 +36,10 @@ void free_cluster_assets(k2b_handle* h) {
   if (h->dec_tab) cudaFree(h->dec_tab);
   h->wo_hi_img = nullptr; h->wo_lo = nullptr; h->bias_pad = nullptr; h->dec_tab = nullptr;
   h->tc_ready = false;
+  if (h->we_hi_img) cudaFree(h->we_hi_img);
+  if (h->we_lo_img) cudaFree(h->we_lo_img);
+  h->we_hi_img = nullptr; h->we_lo_img = nullptr;
+  h->enc_ready = false;
 }
 
 int32_t enter(k2b_handle* h) {
@@ -61,6 +65,7 @@ int32_t need_weights(k2b_handle* h) {
 // raw [n,E] -> projected [n,J] on device (the encoder_proj Linear)
 int32_t encoder_proj_launch(k2b_handle* h, const float* raw, int n, float* out) {
   if (h->cfg.encoder_dim <= 0 || h->enc_w == nullptr) return fail(h, K2B_ERR_STATE, "encoder_proj weights not loaded (E == 0)");
+  if (h->cfg.precision != K2B_PREC_FP32 && encproj_tc_supported(h)) return encoder_proj_tc(h, raw, n, out, false);
   GemmArgs a;
   a.M = n; a.N = h->cfg.joiner_dim; a.K = h->cfg.encoder_dim;
   a.A = raw; a.W = h->enc_w; a.bias = h->enc_b; a.C = out;
@@ -87,10 +92,14 @@ int32_t beam_cluster_path(k2b_handle* h, const float* enc, int enc_is_raw, int B
   float* encE = static_cast<float*>(h->ws_encproj.p);
   if (enc_is_raw) {
     if (h->cfg.encoder_dim <= 0 || h->enc_w == nullptr) return fail(h, K2B_ERR_STATE, "encoder_proj weights not loaded (E == 0)");
-    GemmArgs g;
-    g.M = (int)n; g.N = (int)J; g.K = h->cfg.encoder_dim;
-    g.A = enc; g.W = h->enc_w; g.bias = h->enc_b; g.C = encE;
-    K2B_TRY(launch_gemm_simt(h, PRO_PLAIN, EPI_EXP2X, g));
+    if (encproj_tc_supported(h)) {
+      K2B_TRY(encoder_proj_tc(h, enc, (int)n, encE, true));
+    } else {
+      GemmArgs g;
+      g.M = (int)n; g.N = (int)J; g.K = h->cfg.encoder_dim;
+      g.A = enc; g.W = h->enc_w; g.bias = h->enc_b; g.C = encE;
+      K2B_TRY(launch_gemm_simt(h, PRO_PLAIN, EPI_EXP2X, g));
+    }
   } else {
     K2B_TRY(exp2x_frames(h, enc, encE, n * J));
   }
@@ -213,6 +222,9 @@ int32_t k2b_create(const k2b_config* cfg, k2b_handle** out) {
   e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete h; return cuda_fail(nullptr, e, "cudaStreamCreate", __FILE__, __LINE__); }
   h->stream = h->own_stream;
+  e = cudaMalloc(reinterpret_cast<void**>(&h->dev_status), 4 * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(h->dev_status, 0, 4 * sizeof(int));
+  if (e != cudaSuccess) { cudaStreamDestroy(h->own_stream); delete h; return cuda_fail(nullptr, e, "cudaMalloc(status)", __FILE__, __LINE__); }
   *out = h;
   return K2B_OK;
 }
@@ -225,6 +237,7 @@ int32_t k2b_destroy(k2b_handle* h) {
   for (float** p : ws) { if (*p) cudaFree(*p); *p = nullptr; }
   free_cluster_assets(h);
   if (h->cluster_timing) cudaFree(h->cluster_timing);
+  if (h->dev_status) cudaFree(h->dev_status);
   DevBuf* bufs[] = {&h->ws_in, &h->ws_encproj, &h->ws_x, &h->ws_dec, &h->ws_logits, &h->ws_part, &h->ws_state, &h->ws_bp,
                     &h->ws_out, &h->ws_misc, &h->ws_ctc};
   for (DevBuf* b : bufs) free_buf(*b);
@@ -271,8 +284,8 @@ int32_t k2b_load_weights(k2b_handle* h, const float* emb, const float* conv_w, c
 int32_t k2b_set_precision(k2b_handle* h, int32_t precision) {
   K2B_TRY(enter(h));
   if (precision < K2B_PREC_FP32 || precision > K2B_PREC_BF16) return fail(h, K2B_ERR_INVALID, "unknown precision");
-  if (precision != K2B_PREC_FP32 && !cluster_path_supported(h, 4))
-    return fail(h, K2B_ERR_UNSUPPORTED, "tcgen05 precisions need V <= 1024, J <= 512 (multiple of 64) in this library version");
+  if (precision != K2B_PREC_FP32 && !cluster_path_supported(h, 4) && !encproj_tc_supported(h))
+    return fail(h, K2B_ERR_UNSUPPORTED, "tcgen05 precisions need V <= 1024, J <= 512 (multiple of 64) or an encoder_proj with E % 64 == 0, J % 256 == 0");
   h->cfg.precision = precision;
   return K2B_OK;
 }
@@ -426,6 +439,7 @@ int32_t k2b_encoder_proj(k2b_handle* h, const float* raw, int32_t n, float* out)
   K2B_TRY(encoder_proj_launch(h, static_cast<const float*>(h->ws_in.p), n, static_cast<float*>(h->ws_encproj.p)));
   K2B_CUDA(h, cudaMemcpyAsync(out, h->ws_encproj.p, sizeof(float) * (size_t)n * J, cudaMemcpyDeviceToHost, h->stream));
   K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->cfg.precision != K2B_PREC_FP32) K2B_TRY(cluster_status(h));
   return K2B_OK;
 }
 

@@ -1,0 +1,230 @@
+// encoder_proj on the tensor cores:  C[M,N] = f(A[M,K] * W[N,K]^T + b)   (M = B*T frames, K = E, N = J)
+//
+// One CTA per 128 x 256 output tile, warp-specialised, 2-stage mbarrier pipeline over 64-wide k-blocks:
+//   warp 0      weight loader: bulk TMA copies (cp.async.bulk, SASS UBLKCP) of the pre-split bf16 hi / lo weight
+//               tiles, stored at load time in the exact K-major SWIZZLE_128B shared-memory image;
+//   warp 1      MMA issuer (warp-uniform loop, one elected lane): tcgen05.mma M=128 N=256 K=16, accumulator in TMEM;
+//               split-bf16 x3 (Ah*Wh + Ah*Wl + Al*Wh) for fp32-grade results, or bf16 single pass;
+//   warps 2-5   A producers: coalesced fp32 loads of the raw encoder frames, hi/lo bf16 split in registers, swizzled
+//               shared-memory stores (the frames are fp32 in HBM, so they are converted on the way in, once);
+//               afterwards the same four warps are the epilogue: TMEM -> registers -> +bias -> optional exp(2x)
+//               (the form the cluster search kernel's tanh prologue consumes) -> global.
+// Algorithmic HBM traffic: M*K*4 (frames in) + M*N*4 (projected frames out); the weights stay in L2.
+#include "k2b_internal.h"
+#include "sm100_ptx.cuh"
+
+namespace k2b {
+
+namespace {
+
+using namespace ptx;
+
+constexpr int kEM = 128, kEN = 256, kBKc = 64, kStages = 2;
+constexpr int kATile = kEM * 128;        // 16 KB: 128 rows x 64 bf16
+constexpr int kWTile = kEN * 128;        // 32 KB
+constexpr int kStageBytes = 2 * kATile + 2 * kWTile;   // 96 KB
+constexpr int kEThreads = 192;
+
+struct EncArgs {
+  const float* A;            // [M,K] fp32
+  const uint8_t* w_hi_img;   // [N/256][K/64][32 KB]
+  const uint8_t* w_lo_img;
+  const float* bias;         // [N]
+  float* C;                  // [M,N]
+  int M, N, K, x3, exp2x;
+  int* status;
+};
+
+__global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full_w[kStages], full_a[kStages], empty[kStages], acc_full;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const int ntn = a.N / kEN;
+  const int tile_m = blockIdx.x / ntn, tile_n = blockIdx.x - tile_m * ntn;
+  const int nkb = a.K / kBKc;
+  const uint32_t x3 = (uint32_t)a.x3;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_w[s], 1);
+      mbar_init(&full_a[s], 4);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(&acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t t_d = tmem_slot;
+  bool ok = true;
+
+  if (warp_u == 0) {
+    // ---- weight loader -----------------------------------------------------------------------------------
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+        if (!mbar_wait(&empty[s], ph ^ 1u)) ok = false;
+        uint8_t* st = smem + (size_t)s * kStageBytes;
+        const size_t off = ((size_t)tile_n * nkb + kb) * kWTile;
+        mbar_expect_tx(&full_w[s], (uint32_t)(x3 ? 2 * kWTile : kWTile));
+        tma_bulk_g2s(st + 2 * kATile, a.w_hi_img + off, kWTile, &full_w[s]);
+        if (x3) tma_bulk_g2s(st + 2 * kATile + kWTile, a.w_lo_img + off, kWTile, &full_w[s]);
+      }
+    }
+  } else if (warp_u == 1) {
+    // ---- MMA issuer ------------------------------------------------------------------------------------------
+    const uint32_t el = elect_one();
+    const uint32_t idesc = umma_idesc_bf16_f32(kEM, kEN);
+    const uint32_t desc_hi = 64u | (1u << 14) | (2u << 29);
+    uint32_t acc = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kStages;
+      const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+      if (!mbar_wait(&full_w[s], ph)) ok = false;
+      if (!mbar_wait(&full_a[s], ph)) ok = false;
+      tc_fence_after();
+      const uint32_t sb = smem_u32(smem + (size_t)s * kStageBytes);
+      const uint32_t ah = (((sb) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t al = (((sb + kATile) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t wh = (((sb + 2 * kATile) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t wl = (((sb + 2 * kATile + kWTile) & 0x3FFFFu) >> 4) | (1u << 16);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t dah = ((uint64_t)desc_hi << 32) | (uint64_t)(ah + 2u * k);
+        const uint64_t dwh = ((uint64_t)desc_hi << 32) | (uint64_t)(wh + 2u * k);
+        umma_ss_e(t_d, dah, dwh, idesc, acc, el);
+        acc = 1;
+        if (x3) {
+          const uint64_t dal = ((uint64_t)desc_hi << 32) | (uint64_t)(al + 2u * k);
+          const uint64_t dwl = ((uint64_t)desc_hi << 32) | (uint64_t)(wl + 2u * k);
+          umma_ss_e(t_d, dah, dwl, idesc, 1, el);
+          umma_ss_e(t_d, dal, dwh, idesc, 1, el);
+        }
+      }
+      umma_commit_e(&empty[s], el);       // frees the stage once these MMAs have read it
+    }
+    umma_commit_e(&acc_full, el);
+  } else {
+    // ---- A producers (warps 2..5), then epilogue ------------------------------------------------------------
+    const int pw = warp - 2;              // 0..3: rows pw*32 .. pw*32+31 of the tile
+    const int half = lane >> 4, c4 = lane & 15;     // two rows per warp instruction, 16 float4 per 64-wide row
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kStages;
+      const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+      if (!mbar_wait(&empty[s], ph ^ 1u)) ok = false;
+      uint8_t* a_hi = smem + (size_t)s * kStageBytes;
+      uint8_t* a_lo = a_hi + kATile;
+      float4 v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int r = pw * 32 + 2 * i + half;
+        const int m = tile_m * kEM + r;
+        v[i] = (m < a.M) ? __ldg(reinterpret_cast<const float4*>(a.A + (size_t)m * a.K + (size_t)kb * kBKc) + c4)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int r = pw * 32 + 2 * i + half;
+        const float h0 = bf16_round(v[i].x), h1 = bf16_round(v[i].y), h2 = bf16_round(v[i].z), h3 = bf16_round(v[i].w);
+        const uint32_t off = sw128_offset(r, 4 * c4);
+        *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+        if (x3)
+          *reinterpret_cast<uint2*>(a_lo + off) =
+              make_uint2(pack_bf16x2(v[i].x - h0, v[i].y - h1), pack_bf16x2(v[i].z - h2, v[i].w - h3));
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_a[s]);
+    }
+    // epilogue: this warp owns TMEM lanes 32*(warp%4) .. +31 = tile rows of the same numbers
+    if (!mbar_wait(&acc_full, 0)) ok = false;
+    tc_fence_after();
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    const int m = tile_m * kEM + row;
+    float* crow = a.C + (size_t)m * a.N + (size_t)tile_n * kEN;
+    const float* brow = a.bias + (size_t)tile_n * kEN;
+    for (int c0 = 0; c0 < kEN; c0 += 32) {
+      uint32_t u[32];
+      tmem_ld32(t_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, u);
+      tmem_ld_wait();
+      if (m < a.M) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 o;
+          o.x = __uint_as_float(u[4 * q + 0]) + __ldg(brow + c0 + 4 * q + 0);
+          o.y = __uint_as_float(u[4 * q + 1]) + __ldg(brow + c0 + 4 * q + 1);
+          o.z = __uint_as_float(u[4 * q + 2]) + __ldg(brow + c0 + 4 * q + 2);
+          o.w = __uint_as_float(u[4 * q + 3]) + __ldg(brow + c0 + 4 * q + 3);
+          if (a.exp2x) {
+            o.x = expf(2.f * fminf(fmaxf(o.x, -21.f), 21.f));
+            o.y = expf(2.f * fminf(fmaxf(o.y, -21.f), 21.f));
+            o.z = expf(2.f * fminf(fmaxf(o.z, -21.f), 21.f));
+            o.w = expf(2.f * fminf(fmaxf(o.w, -21.f), 21.f));
+          }
+          *reinterpret_cast<float4*>(crow + c0 + 4 * q) = o;
+        }
+      }
+    }
+  }
+  if (!ok) atomicExch(a.status, 1);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(t_d, 256);
+}
+
+__global__ void pack_enc_w_kernel(const float* __restrict__ w, int N, int K, uint8_t* __restrict__ hi, uint8_t* __restrict__ lo) {
+  const int n = blockIdx.x;                 // weight row
+  const int tn = n / kEN, r = n % kEN, nkb = K / kBKc;
+  for (int k = 2 * threadIdx.x; k < K; k += 2 * blockDim.x) {
+    const float x0 = w[(size_t)n * K + k], x1 = w[(size_t)n * K + k + 1];
+    const float h0 = bf16_round(x0), h1 = bf16_round(x1);
+    const size_t off = ((size_t)tn * nkb + (k >> 6)) * kWTile + sw128_offset(r, k & 63);
+    *reinterpret_cast<uint32_t*>(hi + off) = pack_bf16x2(h0, h1);
+    *reinterpret_cast<uint32_t*>(lo + off) = pack_bf16x2(x0 - h0, x1 - h1);
+  }
+}
+
+}  // namespace
+
+bool encproj_tc_supported(const k2b_handle* h) {
+  const k2b_config& c = h->cfg;
+  return c.encoder_dim > 0 && c.encoder_dim % 64 == 0 && c.joiner_dim % kEN == 0 && h->enc_w != nullptr;
+}
+
+int32_t ensure_encproj_assets(k2b_handle* h) {
+  if (h->enc_ready) return K2B_OK;
+  const int N = h->cfg.joiner_dim, K = h->cfg.encoder_dim;
+  K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->we_hi_img), (size_t)N * K * 2));
+  K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->we_lo_img), (size_t)N * K * 2));
+  pack_enc_w_kernel<<<N, 128, 0, h->stream>>>(h->enc_w, N, K, h->we_hi_img, h->we_lo_img);
+  K2B_LAUNCH_CHECK(h);
+  h->enc_ready = true;
+  return K2B_OK;
+}
+
+// raw [n,E] -> out [n,J] = f(raw * We^T + be) on tcgen05; f = identity or exp(2*clamp(., +-21))
+int32_t encoder_proj_tc(k2b_handle* h, const float* raw, int n, float* out, bool exp2x) {
+  K2B_TRY(ensure_encproj_assets(h));
+  int* status = h->dev_status + 1;
+  EncArgs a;
+  a.A = raw; a.w_hi_img = h->we_hi_img; a.w_lo_img = h->we_lo_img; a.bias = h->enc_b; a.C = out;
+  a.M = n; a.N = h->cfg.joiner_dim; a.K = h->cfg.encoder_dim;
+  a.x3 = h->cfg.precision == K2B_PREC_BF16 ? 0 : 1;
+  a.exp2x = exp2x ? 1 : 0;
+  a.status = status;
+  const int tiles = ((n + kEM - 1) / kEM) * (a.N / kEN);
+  const size_t smem = (size_t)kStages * kStageBytes;
+  K2B_CUDA(h, cudaFuncSetAttribute(encproj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  encproj_tc_kernel<<<tiles, kEThreads, smem, h->stream>>>(a);
+  K2B_LAUNCH_CHECK(h);
+  return K2B_OK;
+}
+
+}  // namespace k2b

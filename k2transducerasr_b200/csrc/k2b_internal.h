@@ -77,6 +77,10 @@ struct k2b_handle {
   float* bias_pad = nullptr;      // [CS*128] out_b, -inf beyond V
   float* dec_tab = nullptr;       // [(V+1)*V, J] exp(2*decoder(y0,y1)): the memoised stateless decoder
 
+  bool enc_ready = false;         // encproj_tc.cu: pre-split, pre-swizzled encoder_proj weight images
+  uint8_t* we_hi_img = nullptr;
+  uint8_t* we_lo_img = nullptr;
+  int* dev_status = nullptr;      // [4] error flags written by the tcgen05 kernels (mbarrier time-outs)
   long long* cluster_timing = nullptr;   // device [8]: per-phase cycle totals of the cluster kernel (diagnostic)
 
   bool profile_on = false;
@@ -172,6 +176,10 @@ int32_t exp2x_frames(k2b_handle* h, const float* in, float* out, size_t n);
 int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, int32_t* bp, float* fin_lp, int32_t* fin_len,
                          int32_t* fin_nlive);
 int32_t cluster_status(k2b_handle* h);
+
+// ---- encproj_tc.cu -----------------------------------------------------------------------------
+bool encproj_tc_supported(const k2b_handle* h);
+int32_t encoder_proj_tc(k2b_handle* h, const float* raw, int n, float* out, bool exp2x);
 
 // profiling bracket around the dominant GEMM
 void prof_begin(k2b_handle* h);

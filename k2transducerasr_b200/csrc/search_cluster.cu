@@ -594,9 +594,7 @@ int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, 
   const int V = c.vocab_size, J = c.joiner_dim, CS = (V + 127) / 128;
   const int S = kNH / K;
   const int nclusters = (B + S - 1) / S;
-  K2B_TRY(ensure(h, h->ws_misc, 256));
-  int* status = static_cast<int*>(h->ws_misc.p);
-  K2B_CUDA(h, cudaMemsetAsync(status, 0, sizeof(int), h->stream));
+  int* status = h->dev_status;
   ClusterArgs a;
   a.encE = encE; a.dec_tab = h->dec_tab; a.wo_hi_img = h->wo_hi_img; a.wo_lo = h->wo_lo; a.bias = h->bias_pad;
   a.B = B; a.T = T; a.K = K; a.V = V; a.J = J; a.S = S; a.CS = CS; a.blank = c.blank_id; a.unk = c.unk_id;
@@ -623,10 +621,13 @@ int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, 
 }
 
 int32_t cluster_status(k2b_handle* h) {
-  int st = 0;
-  K2B_CUDA(h, cudaMemcpyAsync(&st, h->ws_misc.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  int st[4] = {0, 0, 0, 0};
+  K2B_CUDA(h, cudaMemcpyAsync(st, h->dev_status, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
   K2B_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (st != 0) return fail(h, K2B_ERR_STATE, "cluster search kernel: an mbarrier wait timed out");
+  if (st[0] != 0 || st[1] != 0) {
+    cudaMemsetAsync(h->dev_status, 0, sizeof(st), h->stream);
+    return fail(h, K2B_ERR_STATE, st[0] ? "cluster search kernel: an mbarrier wait timed out" : "encoder_proj tcgen05 kernel: an mbarrier wait timed out");
+  }
   return K2B_OK;
 }
 

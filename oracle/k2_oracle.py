@@ -88,6 +88,7 @@ class Model:
     context_size: int = 2    # ref Model/OfflineCustomMetadata.cs:21
     neg_id_wrap: bool = False
     prec: str = "fp32"
+    prec_enc: Optional[str] = None      # arithmetic of the encoder_proj GEMM only (None = prec)
     prec_joiner: Optional[str] = None   # arithmetic of the joiner output GEMM only (None = prec): restates the
                                         # library's tensor-core modes, whose decoder / encoder_proj stay fp32
 
@@ -144,7 +145,7 @@ def encoder_proj(m: Model, raw: np.ndarray) -> np.ndarray:
     output (ref OfflineProjOfTransducer.cs:83)."""
     E = m.enc_proj_w.shape[1]
     shp = raw.shape[:-1]
-    out = _gemm_nt(np.asarray(raw, F32).reshape(-1, E), m.enc_proj_w, m.prec) + m.enc_proj_b
+    out = _gemm_nt(np.asarray(raw, F32).reshape(-1, E), m.enc_proj_w, m.prec_enc or m.prec) + m.enc_proj_b
     return out.astype(F32).reshape(*shp, m.J)
 
 

@@ -50,8 +50,8 @@ def test_cluster_bf16x3_matches_fp32_oracle(setup, beam):
 def test_cluster_bf16_matches_bf16_oracle_and_is_near_fp32(setup):
     m, w, raw, enc = setup
     h = make(MID, w, "bf16")
-    mb = O.Model.from_dict(w, prec_joiner="bf16")
-    want = O.modified_beam_search(mb, enc, 4)
+    mb = O.Model.from_dict(w, prec_joiner="bf16", prec_enc="bf16")
+    want = O.modified_beam_search(mb, O.encoder_proj(mb, raw), 4)
     t, s, sc = h.modified_beam_search(raw, 4)
     ex = compare_streams(t, s, want, "cluster bf16 vs bf16 oracle", allow_frac=0.3)
     for b, r in enumerate(want):
@@ -109,4 +109,20 @@ def test_cluster_full_size_cfg2(built_lib):
     for b in range(8):
         if b not in ex:
             assert abs(float(sc1[b]) - want[b].score) < SCORE_TOL
+    h.close()
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 700])
+def test_encoder_proj_tcgen05(setup, n):
+    """TMA-fed tcgen05 encoder_proj: split-bf16 x3 is fp32-grade; bf16 matches the bf16-restated oracle."""
+    m, w, raw, enc = setup
+    x = synth.make_frames(1, n, MID.encoder_dim, 77 + n)[0]
+    want = O.encoder_proj(m, x)
+    h = make(MID, w, "bf16x3")
+    np.testing.assert_allclose(h.encoder_proj(x), want, rtol=0, atol=3e-5)
+    h.set_precision("bf16")
+    mb = O.Model.from_dict(w, prec_enc="bf16")
+    got = h.encoder_proj(x)
+    np.testing.assert_allclose(got, O.encoder_proj(mb, x), rtol=0, atol=3e-5)
+    assert np.abs(got - want).max() > 1e-4
     h.close()
