@@ -1,0 +1,55 @@
+// P/Invoke surface of libk2b200.so (include/k2b200.h). Blittable arguments only.
+// NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no .NET toolchain. The same entry points are
+// exercised through ctypes by k2transducerasr_b200/_native.py and tests/.
+using System;
+using System.Runtime.InteropServices;
+
+namespace K2TransducerAsr.B200
+{
+    [StructLayout(LayoutKind.Sequential)]
+    internal struct K2bConfig
+    {
+        public int struct_size, device, vocab_size, joiner_dim, decoder_dim, encoder_dim, context_size;
+        public int blank_id, sos_eos_id, unk_id, max_streams, max_frames, max_beam, neg_id_mode, precision, reserved;
+    }
+
+    internal static class NativeMethods
+    {
+        private const string Lib = "k2b200";   // libk2b200.so / k2b200.dll next to the assembly
+
+        public const int K2B_OK = 0;
+        public const int GREEDY_SINGLE = 0, GREEDY_BATCH_COMPAT = 1, GREEDY_PER_STREAM = 2;
+        public const int PREC_FP32 = 0, PREC_BF16X3 = 1, PREC_BF16 = 2;
+
+        [DllImport(Lib)] public static extern int k2b_abi_version();
+        [DllImport(Lib)] public static extern int k2b_create(ref K2bConfig cfg, out IntPtr handle);
+        [DllImport(Lib)] public static extern int k2b_destroy(IntPtr h);
+        [DllImport(Lib)] public static extern IntPtr k2b_last_error(IntPtr h);
+        [DllImport(Lib)] public static extern int k2b_load_weights(IntPtr h, float[] emb, float[] conv_w, float[] dec_proj_w,
+            float[] dec_proj_b, float[]? enc_proj_w, float[]? enc_proj_b, float[] out_w, float[] out_b);
+        [DllImport(Lib)] public static extern int k2b_set_precision(IntPtr h, int precision);
+
+        // fine-grained: 1:1 with IOfflineProj / IOnlineProj
+        [DllImport(Lib)] public static extern int k2b_decoder_proj(IntPtr h, long[]? y, int n, [Out] float[] outp);
+        [DllImport(Lib)] public static extern int k2b_joiner_proj(IntPtr h, float[] enc, float[] dec, int n, [Out] float[] logits);
+        [DllImport(Lib)] public static extern int k2b_encoder_proj(IntPtr h, float[] raw, int n, [Out] float[] outp);
+
+        // fused: 1:1 with the Forward* delegates
+        [DllImport(Lib)] public static extern int k2b_greedy_offline(IntPtr h, float[] enc, int enc_is_raw, int B, int T, int mode,
+            [Out] long[] tokens, [Out] int[] ts, [Out] int[] n_out, int cap);
+        [DllImport(Lib)] public static extern int k2b_greedy_online_chunk(IntPtr h, float[] enc, int enc_is_raw, int B, int Tc,
+            [In, Out] long[] hyp_inout, [Out] long[] tokens, [Out] int[] ts, [Out] int[] n_out, int cap);
+        [DllImport(Lib)] public static extern int k2b_modified_beam_search(IntPtr h, float[] enc, int enc_is_raw, int B, int T, int K,
+            [Out] long[] tokens, [Out] int[] ts, [Out] int[] n_out, [Out] float[] score, int cap);
+        [DllImport(Lib)] public static extern int k2b_ctc_greedy(IntPtr h, float[] logp, int B, int T, int V, int blank,
+            int[]? frame_offset, [In, Out] long[]? prev_inout, [Out] long[] tokens, [Out] int[] ts, [Out] int[] n_out,
+            [In, Out] int[]? trailing_blank_inout, int cap);
+
+        internal static void Check(IntPtr h, int status, string what)
+        {
+            if (status == K2B_OK) return;
+            string msg = Marshal.PtrToStringUTF8(k2b_last_error(h)) ?? "";
+            throw new Exception($"{what} failed (libk2b200 status {status}): {msg}");
+        }
+    }
+}
