@@ -228,13 +228,14 @@ def run_ours(args, cfg):
             ms = float(t.item())
         return ms
 
+    clk = ClockSampler(local_rank)
+    clk.__enter__()                      # sampled from warm-up to the end of the e2e region: all of it is under load
     for i in range(max(args.warmup, 3)):
         step_dev(i)
     torch.cuda.synchronize()
 
     h.reset_launch_count()
-    with ClockSampler(local_rank) as clk:
-        ms = timed(step_dev, args.steps)
+    ms = timed(step_dev, args.steps)
     launches = h.launch_count()
     value = world * B * T * args.steps / (ms * 1e-3)
 
@@ -255,6 +256,7 @@ def run_ours(args, cfg):
     e2e_value = world * B * T * e2e_steps / (ms_e2e * 1e-3)
     h2d = B * T * E * 4
     d2h = B * cap * 8 + B * cap * 4 + B * 4 + B * 4
+    clk.__exit__(None, None, None)
 
     # dominant kernel: the joiner GEMM of every frame, bracketed with CUDA events on the launch stream
     h.profile_enable(True)
@@ -269,8 +271,11 @@ def run_ours(args, cfg):
     flops_per_launch = 2.0 * (B * K) * J * V * (T if fused_loop else 1)
     avg_ms = tot_ms / max(n_l, 1)
     achieved_tf = flops_per_launch / (avg_ms * 1e-3) / 1e12 if n_l else 0.0
+    # dram__bytes_read.sum + dram__bytes_write.sum of one cluster_beam_kernel launch on this workload, from the
+    # ncu --set full capture profiles/r01_cluster_beam_v3_full.ncu-rep (241.3 MB + 6.2 MB); none taken for the fp32 path
+    traffic = 247.5e6 if (fused_loop and args.workload == "cfg2") else None
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved_tf / peaks["tf_sustained"], "traffic": None, "kernel": ("cluster_beam_kernel: whole time loop (joiner tcgen05 GEMM + log-softmax/top-k + merge)" if fused_loop
+                "frac": achieved_tf / peaks["tf_sustained"], "traffic": traffic, "kernel": ("cluster_beam_kernel: whole time loop (joiner tcgen05 GEMM + log-softmax/top-k + merge)" if fused_loop
                            else "joiner GEMM (+log-softmax/top-k epilogue), one launch per frame"),
                 "avg_launch_us": avg_ms * 1e3, "launches_timed": n_l, "flop_per_launch": flops_per_launch,
                 "peak_source": peaks["src"] + ", sustained bf16",
