@@ -186,15 +186,19 @@ K2B_API int32_t k2b_selftest_umma_bench(k2b_handle* h, int32_t flavour, int32_t 
 /* k2b_selftest_collectives: dependent-chain latency (cycles) of REDUX, a 5-level SHFL butterfly and BALLOT,
  * for one warp alone [0..2] and with 16 warps running the chain concurrently [3..5].                  */
 K2B_API int32_t k2b_selftest_collectives(k2b_handle* h, int64_t* out6);
+/* k2b_selftest_dsmem_bw: cycles for every CTA of a cluster to push bytes_per_peer to each peer with 16-byte
+ * st.shared::cluster stores (two cluster barriers included).                                          */
+K2B_API int32_t k2b_selftest_dsmem_bw(k2b_handle* h, int32_t csize, int32_t nclusters, int32_t bytes_per_peer,
+                                      int64_t* cycles);
 /* k2b_selftest_cluster: nclusters clusters of csize CTAs exchange data through distributed shared
  * memory; *bad = mismatching words, *ctas_done = CTAs that ran.                                     */
 K2B_API int32_t k2b_selftest_cluster(k2b_handle* h, int32_t csize, int32_t nclusters, int32_t* bad,
                                      int32_t* ctas_done);
 
-/* Cycle totals of the eight phases of one frame step (build, sync, MMA issue, MMA wait, TMEM read-out,
+/* Cycle totals (12 slots) of the phases of one frame step (build, sync, MMA issue, MMA wait, TMEM read-out,
  * reductions + DSMEM, cluster barrier, merge) summed over the last cluster-kernel launch, CTA 0. The first
  * call switches the collection on.                                                                    */
-K2B_API int32_t k2b_cluster_phase_cycles(k2b_handle* h, int64_t* out8);
+K2B_API int32_t k2b_cluster_phase_cycles(k2b_handle* h, int64_t* out12);
 
 #ifdef __cplusplus
 }

@@ -69,6 +69,7 @@ _SIGS = {
     "k2b_cluster_phase_cycles": (C.c_int32, [_P, _P]),
     "k2b_selftest_umma_bench": (C.c_int32, [_P, _I, _I, _I, _P]),
     "k2b_selftest_collectives": (C.c_int32, [_P, _P]),
+    "k2b_selftest_dsmem_bw": (C.c_int32, [_P, _I, _I, _I, _P]),
     "k2b_selftest_cluster": (C.c_int32, [_P, _I, _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
 }
 
@@ -294,7 +295,7 @@ class Handle:
         return D
 
     def cluster_phase_cycles(self):
-        out = np.zeros(8, np.int64)
+        out = np.zeros(20, np.int64)
         self._check(self._lib.k2b_cluster_phase_cycles(self._h, _ptr(out)))
         return out
 
@@ -307,6 +308,11 @@ class Handle:
         out = np.zeros(6, np.int64)
         self._check(self._lib.k2b_selftest_collectives(self._h, _ptr(out)))
         return out
+
+    def selftest_dsmem_bw(self, csize: int, nclusters: int, bytes_per_peer: int) -> int:
+        out = np.zeros(1, np.int64)
+        self._check(self._lib.k2b_selftest_dsmem_bw(self._h, csize, nclusters, bytes_per_peer, _ptr(out)))
+        return int(out[0])
 
     def selftest_cluster(self, csize: int, nclusters: int):
         bad, done = C.c_int32(-1), C.c_int32(-1)

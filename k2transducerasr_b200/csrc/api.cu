@@ -337,13 +337,14 @@ int32_t k2b_profile_read(k2b_handle* h, int64_t* n_launches, double* total_ms) {
 K2B_API int32_t k2b_cluster_phase_cycles(k2b_handle* h, int64_t* out8) {
   K2B_TRY(enter(h));
   if (h->cluster_timing == nullptr) {
-    K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->cluster_timing), 8 * sizeof(long long)));
-    K2B_CUDA(h, cudaMemset(h->cluster_timing, 0, 8 * sizeof(long long)));
+    K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->cluster_timing), 20 * sizeof(long long)));
+    K2B_CUDA(h, cudaMemset(h->cluster_timing, 0, 20 * sizeof(long long)));
   }
   K2B_CUDA(h, cudaStreamSynchronize(h->stream));
-  long long v[8];
+  long long v[20];
   K2B_CUDA(h, cudaMemcpy(v, h->cluster_timing, sizeof(v), cudaMemcpyDeviceToHost));
-  for (int i = 0; i < 8; ++i) out8[i] = v[i];
+  for (int i = 0; i < 20; ++i) out8[i] = v[i];
+  K2B_CUDA(h, cudaMemset(h->cluster_timing, 0, sizeof(v)));
   return K2B_OK;
 }
 

@@ -87,9 +87,11 @@ __device__ __forceinline__ float funkey(int k) { return __int_as_float(k >= 0 ? 
 constexpr int kKeyNone = (int)0x80000000;
 
 // One warp: hypothesis merge of local stream s (beam_select_kernel in search.cu is the global-memory twin).
+// cand_tab[c] = (h << 16) | (slice << 8) | j for candidate c of a stream (built once per launch); scr = 2*K floats.
 template <int K>
-__device__ __forceinline__ void select_stream(int s, int V, int CS, const float* __restrict__ xb, const HypState& in,
-                                              HypState& out, int blank, int unk, int32_t* __restrict__ bp_row, int lane) {
+__device__ __noinline__ void select_stream(int s, int V, int CS, const float* __restrict__ xb, const HypState& in,
+                                           HypState& out, int blank, int unk, int32_t* __restrict__ bp_row, int lane,
+                                           const int* __restrict__ cand_tab, float* __restrict__ scr) {
   constexpr int XWP = xw_padded(K);
   const unsigned full = 0xffffffffu;
   const int nl = in.nlive[s];
@@ -101,68 +103,85 @@ __device__ __forceinline__ void select_stream(int s, int V, int CS, const float*
     if (lane == 0) out.nlive[s] = 0;
     return;
   }
-  // log_softmax constants: lane = (hyp h, slice c), 8 lanes per hypothesis, 4 hypotheses per pass
-  constexpr int kPass = (K + 3) / 4;
-  float Mp[kPass], Lp[kPass];
-#pragma unroll
-  for (int p = 0; p < kPass; ++p) {
-    const int h = p * 4 + (lane >> 3), c = lane & 7;
-    const bool valid = h < nl && c < CS;
-    const float* e = xb + ((size_t)c * kNH + s * K + h) * XWP;
-    const float pm = valid ? e[0] : -INFINITY, ps = valid ? e[1] : 0.f;
-    float M = pm;
-#pragma unroll
-    for (int off = 4; off >= 1; off >>= 1) M = fmaxf(M, __shfl_xor_sync(full, M, off));
-    float term = (pm > -INFINITY) ? ps * __expf(pm - M) : 0.f;
-#pragma unroll
-    for (int off = 4; off >= 1; off >>= 1) term += __shfl_xor_sync(full, term, off);
-    Mp[p] = M;
-    Lp[p] = __logf(term);
+  // log_softmax constants of the live hypotheses: lane h combines the CS slice partials (max, sum-exp)
+  if (lane < K) {
+    float M = -INFINITY, L = 0.f;
+    if (lane < nl) {
+      const float* e = xb + (size_t)(s * K + lane) * XWP;
+      for (int c = 0; c < CS; ++c) M = fmaxf(M, e[(size_t)c * kNH * XWP]);
+      float sum = 0.f;
+      for (int c = 0; c < CS; ++c) {
+        const float pm = e[(size_t)c * kNH * XWP], ps = e[(size_t)c * kNH * XWP + 1];
+        sum += (pm > -INFINITY) ? ps * __expf(pm - M) : 0.f;
+      }
+      L = __logf(sum);
+    }
+    scr[2 * lane] = M;
+    scr[2 * lane + 1] = L;
   }
-  // score this lane's share of the nl*CS*K candidates; lane = (slice, j), CPL candidates per lane in registers
-  constexpr int kSlots = (8 * K + 31) / 32;          // (slice, j) pairs per lane when CS = 8
-  constexpr int CPL = kSlots * K;                    // x up to K live hypotheses
-  int ckey[CPL], cflat[CPL];
+  __syncwarp();
+  // this lane's candidates (every (hyp, slice, j) triple is one): score key + flat index
+  constexpr int CPL = (K * 8 * K + 31) / 32;
+  int ck[CPL], cf[CPL];
+  const int ncand = K * CS * K;
 #pragma unroll
-  for (int i = 0; i < CPL; ++i) { ckey[i] = kKeyNone; cflat[i] = -1; }
-  const int per_h = CS * K;
-#pragma unroll
-  for (int h = 0; h < K; ++h) {
-    if (h < nl) {
-      const int src = (h & 3) * 8;
-      const float Mh = __shfl_sync(full, (h < 4) ? Mp[0] : Mp[kPass - 1], src);
-      const float Lh = __shfl_sync(full, (h < 4) ? Lp[0] : Lp[kPass - 1], src);
-      const float LPh = in.lp[s * K + h];
-#pragma unroll
-      for (int q = 0; q < kSlots; ++q) {
-        const int L = lane + 32 * q;
-        if (L < per_h) {
-          const int slice = L / K, j = L % K;
-          const float* e = xb + ((size_t)slice * kNH + s * K + h) * XWP;
-          const int idx = __float_as_int(e[2 + K + j]);
-          const float v = ((e[2 + j] - Mh) - Lh) + LPh;   // same operation order as log_softmax(x) + lp
-          if (idx >= 0 && v == v) { ckey[h * kSlots + q] = fkey(v); cflat[h * kSlots + q] = h * V + idx; }
-        }
+  for (int i = 0; i < CPL; ++i) {
+    ck[i] = kKeyNone; cf[i] = -1;
+    const int c = lane + 32 * i;
+    if (c < ncand) {
+      const int code = cand_tab[c];
+      const int h = code >> 16, slice = (code >> 8) & 0xff, j = code & 0xff;
+      if (h < nl) {
+        const float* e = xb + ((size_t)slice * kNH + s * K + h) * XWP;
+        const int idx = __float_as_int(e[2 + K + j]);
+        const float v = ((e[2 + j] - scr[2 * h]) - scr[2 * h + 1]) + in.lp[s * K + h];   // order of log_softmax(x) + lp
+        if (idx >= 0 && v == v) { ck[i] = fkey(v); cf[i] = h * V + idx; }
       }
     }
   }
-  // K rounds: warp max of the score key (REDUX), ties -> larger flat index (second REDUX), winner is retired
   float my_v = -INFINITY;
   int my_f = -1;
+  if constexpr (CPL <= 4) {
+    // sort the (at most four) local candidates once, best first, then K rounds of REDUX max + pop
+    if constexpr (CPL == 4) {
+#define K2B_CE(x, y)                                                                         \
+  do {                                                                                       \
+    const bool sw = ck[y] > ck[x] || (ck[y] == ck[x] && cf[y] > cf[x]);                      \
+    const int tk_ = sw ? ck[y] : ck[x], tf_ = sw ? cf[y] : cf[x];                            \
+    ck[y] = sw ? ck[x] : ck[y]; cf[y] = sw ? cf[x] : cf[y];                                  \
+    ck[x] = tk_; cf[x] = tf_;                                                                \
+  } while (0)
+      K2B_CE(0, 1); K2B_CE(2, 3); K2B_CE(0, 2); K2B_CE(1, 3); K2B_CE(1, 2);
+#undef K2B_CE
+    }
 #pragma unroll
-  for (int r = 0; r < K; ++r) {
-    int bk = kKeyNone, bf = -1;
+    for (int r = 0; r < K; ++r) {
+      const int wk = __reduce_max_sync(full, ck[0]);
+      const int wf = __reduce_max_sync(full, (cf[0] >= 0 && ck[0] == wk) ? cf[0] : -1);
+      if (wf >= 0 && cf[0] == wf) {
 #pragma unroll
-    for (int i = 0; i < CPL; ++i)
-      if (cflat[i] >= 0 && (ckey[i] > bk || (ckey[i] == bk && cflat[i] > bf))) { bk = ckey[i]; bf = cflat[i]; }
-    const int wk = __reduce_max_sync(full, bk);
-    const int wf = __reduce_max_sync(full, (bf >= 0 && bk == wk) ? bf : -1);
-    if (wf >= 0) {
+        for (int i = 0; i + 1 < CPL; ++i) { ck[i] = ck[i + 1]; cf[i] = cf[i + 1]; }
+        ck[CPL - 1] = kKeyNone; cf[CPL - 1] = -1;
+      }
+      if (lane == r) { my_v = funkey(wk); my_f = wf; }
+    }
+  } else {
+    // many candidates per lane (beam 8): rescan per round
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+      int bk = kKeyNone, bf = -1;
 #pragma unroll
       for (int i = 0; i < CPL; ++i)
-        if (cflat[i] == wf) cflat[i] = -1;
+        if (cf[i] >= 0 && (ck[i] > bk || (ck[i] == bk && cf[i] > bf))) { bk = ck[i]; bf = cf[i]; }
+      const int wk = __reduce_max_sync(full, bk);
+      const int wf = __reduce_max_sync(full, (bf >= 0 && bk == wk) ? bf : -1);
+      if (wf >= 0) {
+#pragma unroll
+        for (int i = 0; i < CPL; ++i)
+          if (cf[i] == wf) cf[i] = -1;
+      }
+      if (lane == r) { my_v = funkey(wk); my_f = wf; }
     }
-    if (lane == r) { my_v = funkey(wk); my_f = wf; }
   }
 
   const bool cand = lane < K && my_f >= 0;
@@ -220,6 +239,8 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ HypState st[2];
   __shared__ float bias_s[128];
+  __shared__ int cand_tab[kMaxBeam * 8 * kMaxBeam];
+  __shared__ float sel_scr[kCThreads / 32][2 * kMaxBeam];
   __shared__ uint64_t bar_w, bar_mma;
   __shared__ uint32_t tmem_slot;
 
@@ -268,6 +289,10 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
     tmem_st_wait();
   }
   if (tid < 128) bias_s[tid] = a.bias[rank * 128 + tid];
+  for (int c = tid; c < K * CS * K; c += kCThreads) {
+    const int h = c / (CS * K), r = c - h * (CS * K);
+    cand_tab[c] = (h << 16) | ((r / K) << 8) | (r % K);
+  }
   if (tid < kNH) {
     const int n = tid, h = n % K;
     for (int b = 0; b < 2; ++b) {
@@ -285,7 +310,7 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
   tc_fence_after();
   cluster_sync();            // every CTA of the cluster is resident: remote shared memory may be written
 
-  long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const bool timed = a.timing != nullptr && blockIdx.x == 0 && tid == 0;
   long long tlast = timed ? clock64() : 0;
 #define K2B_PHASE(i) do { if (timed) { const long long now = clock64(); tph[i] += now - tlast; tlast = now; } } while (0)
@@ -304,10 +329,14 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
   if (g_w >= a.B) g_w = a.B - 1;
   const float4* enc_row = reinterpret_cast<const float4*>(a.encE + (size_t)g_w * T * J);
   float4 ecur[4];
+  uint32_t xoff[2][4];           // loop-invariant swizzled byte offsets of this thread's 8 operand chunks (hi rows)
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int q = lane + 32 * i;
     if (q < nq) ecur[i] = __ldg(enc_row + q);
+    const int k = 4 * q;
+    xoff[0][i] = (uint32_t)(k >> 6) * kXTile + sw128_offset(n0, k & 63);
+    xoff[1][i] = (uint32_t)(k >> 6) * kXTile + sw128_offset(n0 + 1, k & 63);
   }
 
   for (int t = 0; t < T; ++t) {
@@ -324,7 +353,6 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
       }
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
-        const int n = n0 + r;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int q = lane + 32 * i;
@@ -332,13 +360,17 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
             const float4 d = r ? d1[i] : d0[i];
             const float x0 = tanh_from_exp(ecur[i].x, d.x), x1 = tanh_from_exp(ecur[i].y, d.y);
             const float x2 = tanh_from_exp(ecur[i].z, d.z), x3 = tanh_from_exp(ecur[i].w, d.w);
-            const int k = 4 * q;
-            uint8_t* tile = xop + (size_t)(k >> 6) * kXTile;
-            const float h0 = bf16_round(x0), h1 = bf16_round(x1), h2 = bf16_round(x2), h3 = bf16_round(x3);
-            *reinterpret_cast<uint2*>(tile + sw128_offset(n, k & 63)) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
-            if (a.x3)
-              *reinterpret_cast<uint2*>(tile + sw128_offset(32 + n, k & 63)) =
-                  make_uint2(pack_bf16x2(x0 - h0, x1 - h1), pack_bf16x2(x2 - h2, x3 - h3));
+            uint8_t* dst = xop + xoff[r][i];
+            if (a.x3) {
+              // split by truncation: hi = upper 16 bits (one PRMT per pair), lo = x - hi exactly, rounded to bf16
+              const uint32_t b0 = __float_as_uint(x0), b1 = __float_as_uint(x1), b2 = __float_as_uint(x2), b3 = __float_as_uint(x3);
+              *reinterpret_cast<uint2*>(dst) = make_uint2(__byte_perm(b0, b1, 0x7632), __byte_perm(b2, b3, 0x7632));
+              const float l0 = x0 - __uint_as_float(b0 & 0xffff0000u), l1 = x1 - __uint_as_float(b1 & 0xffff0000u);
+              const float l2 = x2 - __uint_as_float(b2 & 0xffff0000u), l3 = x3 - __uint_as_float(b3 & 0xffff0000u);
+              *reinterpret_cast<uint2*>(dst + 32 * 128) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+            } else {
+              *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(x0, x1), pack_bf16x2(x2, x3));
+            }
           }
         }
       }
@@ -362,7 +394,7 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
     //      x3: one SS MMA with the stacked operand (N = 64: cols 0-31 = Wh*xh, 32-63 = Wh*xl) + one TS MMA
     //      (A = Wl resident in TMEM, N = 32) accumulating Wl*xh into cols 0-31.
     if (warp_u == kCThreads / 32 - 1) {      // warp-uniform loop: descriptors stay in uniform registers, one lane issues
-      const uint32_t el = elect_one();
+      const uint32_t el = elect_one();       // (two issuing warps with separate accumulators were measured: no gain)
       uint32_t acc = 0;
       for (int kb = 0; kb < nkb; ++kb) {
 #pragma unroll
@@ -432,28 +464,42 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
         sum[0] += __shfl_xor_sync(0xffffffffu, sum[0], o);
         sum[1] += __shfl_xor_sync(0xffffffffu, sum[1], o);
       }
+      // sort this lane's four (key, j) pairs once, best first (equal keys: larger j = larger vocab index first) ...
+      int sk[2][4], sj[2][4];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { sk[r][j] = key[r][j]; sj[r][j] = j; }
+#define K2B_CE(x, y)                                                                                    \
+  do {                                                                                                  \
+    const bool sw = sk[r][y] > sk[r][x] || (sk[r][y] == sk[r][x] && sj[r][y] > sj[r][x]);               \
+    const int tk_ = sw ? sk[r][y] : sk[r][x], tj_ = sw ? sj[r][y] : sj[r][x];                           \
+    sk[r][y] = sw ? sk[r][x] : sk[r][y]; sj[r][y] = sw ? sj[r][x] : sj[r][y];                           \
+    sk[r][x] = tk_; sj[r][x] = tj_;                                                                     \
+  } while (0)
+        K2B_CE(0, 1); K2B_CE(2, 3); K2B_CE(0, 2); K2B_CE(1, 3); K2B_CE(1, 2);
+#undef K2B_CE
+      }
+      // ... then K rounds: REDUX max of the heads, ties -> larger vocab index (second REDUX), the winner pops its head
       float out_v[2] = {-INFINITY, -INFINITY};
       int out_i[2] = {-1, -1};
 #pragma unroll
       for (int rr = 0; rr < K; ++rr) {
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-          // this lane's best remaining logit; equal keys -> larger j = larger vocab index
-          int bk = kKeyNone, bj = -1;
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (key[r][j] != kKeyNone && key[r][j] >= bk) { bk = key[r][j]; bj = j; }
-          const int wk = __reduce_max_sync(0xffffffffu, bk);
-          const int ci = (bj >= 0 && bk == wk) ? (int)rank * 128 + lane + 32 * bj : -1;
+          const int wk = __reduce_max_sync(0xffffffffu, sk[r][0]);
+          const int ci = (sk[r][0] != kKeyNone && sk[r][0] == wk) ? (int)rank * 128 + lane + 32 * sj[r][0] : -1;
           const int wi = __reduce_max_sync(0xffffffffu, ci);
           if (ci == wi && wi >= 0) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (j == bj) key[r][j] = kKeyNone;
+            sk[r][0] = sk[r][1]; sj[r][0] = sj[r][1];
+            sk[r][1] = sk[r][2]; sj[r][1] = sj[r][2];
+            sk[r][2] = sk[r][3]; sj[r][2] = sj[r][3];
+            sk[r][3] = kKeyNone;
           }
           if (lane == rr) { out_v[r] = funkey(wk); out_i[r] = wi; }
         }
       }
+      K2B_PHASE(8);     // sub-phase: loads + max + sum + sort + K rounds
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         float* mine = xw + ((size_t)rank * kNH + warp * 2 + r) * XWP;
@@ -481,13 +527,14 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
     if (warp < S) {
       const int s = warp, g = cluster * S + s;
       int32_t* bp_row = (rank == 0 && g < a.B) ? a.bp + ((size_t)g * T + t) * K : nullptr;
-      select_stream<K>(s, V, CS, xw, st[cur], st[cur ^ 1], a.blank, a.unk, bp_row, lane);
+      select_stream<K>(s, V, CS, xw, st[cur], st[cur ^ 1], a.blank, a.unk, bp_row, lane, cand_tab, sel_scr[warp]);
     }
+    K2B_PHASE(9);       // sub-phase: this warp's own merge, before waiting for the others
     __syncthreads();
     cur ^= 1;
     K2B_PHASE(7);
   }
-  if (timed) for (int i = 0; i < 8; ++i) a.timing[i] = tph[i];
+  if (timed) for (int i = 0; i < 12; ++i) a.timing[i] = tph[i];
 #undef K2B_PHASE
 
   if (rank == 0 && tid < S * K) {
@@ -542,7 +589,7 @@ bool cluster_path_supported(const k2b_handle* h, int K) {
   if (c.vocab_size > 1024 || c.joiner_dim > 512 || c.joiner_dim % 64) return false;
   if (K != 2 && K != 4 && K != 8) return false;      // both rows of a build warp must share one stream
   const size_t dyn = (size_t)(c.joiner_dim / 64) * (16384 + 64 * 128) + 2ull * CS * kNH * xw_padded(K) * 4;
-  if (dyn + 4096 > 227 * 1024) return false;
+  if (dyn + 8192 > 227 * 1024) return false;
   const size_t tab = (size_t)(c.vocab_size + 1) * c.vocab_size * c.joiner_dim * sizeof(float);
   return tab <= ((size_t)16 << 30);
 }

@@ -258,6 +258,22 @@ __global__ void __launch_bounds__(64) cluster_selftest_kernel(int* __restrict__ 
   cluster_sync();                      // nobody exits while a peer may still write into it
 }
 
+// every CTA of the cluster pushes `words16` 16-byte chunks to each peer with st.shared::cluster.v4 (512 threads)
+__global__ void __launch_bounds__(512) dsmem_bw_kernel(int words16, long long* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t buf[];
+  const uint32_t rank = cluster_ctarank(), n = cluster_nctarank();
+  cluster_sync();
+  const long long t0 = clock64();
+  for (uint32_t p = 1; p < n; ++p) {
+    const uint32_t dst = (rank + p) % n;
+    const uint32_t base = dsmem_map(smem_u32(buf), dst);
+    for (int i = threadIdx.x; i < words16; i += blockDim.x) dsmem_st_v4(base + 16u * i, i, rank, p, 7u);
+  }
+  cluster_sync();
+  const long long t1 = clock64();
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+}
+
 }  // namespace
 
 }  // namespace k2b
@@ -348,6 +364,29 @@ K2B_API int32_t k2b_selftest_collectives(k2b_handle* h, int64_t* out6) {
   K2B_CUDA(h, cudaMemcpy(r, d, sizeof(r), cudaMemcpyDeviceToHost));
   cudaFree(d); cudaFree(sink);
   for (int i = 0; i < 6; ++i) out6[i] = r[i];
+  return K2B_OK;
+}
+
+// cycles for every CTA of `nclusters` clusters of `csize` CTAs to push bytes_per_peer to each peer (incl. two cluster barriers)
+K2B_API int32_t k2b_selftest_dsmem_bw(k2b_handle* h, int32_t csize, int32_t nclusters, int32_t bytes_per_peer, int64_t* cycles) {
+  if (h == nullptr || csize < 2 || csize > 8 || bytes_per_peer % 16 || bytes_per_peer > 128 * 1024) return K2B_ERR_INVALID;
+  K2B_CUDA(h, cudaSetDevice(h->cfg.device));
+  long long* d;
+  K2B_CUDA(h, cudaMalloc(&d, sizeof(long long)));
+  K2B_CUDA(h, cudaFuncSetAttribute(dsmem_bw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes_per_peer));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(csize * nclusters); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = bytes_per_peer; cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  K2B_CUDA(h, cudaLaunchKernelEx(&cfg, dsmem_bw_kernel, bytes_per_peer / 16, d));
+  h->launches++;
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  long long r;
+  K2B_CUDA(h, cudaMemcpy(&r, d, sizeof(r), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  *cycles = r;
   return K2B_OK;
 }
 

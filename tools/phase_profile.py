@@ -8,7 +8,8 @@ build.build()
 cfg = synth.CONFIGS["cfg2"]
 d = cfg.dims
 names = ["build x (gather+tanh+split)", "sync+fence", "MMA issue", "MMA wait", "TMEM->smem transpose", "reduce+DSMEM st",
-         "cluster barrier", "merge+sync"]
+         "cluster barrier", "(after merge) sync wait", "  reduce: loads+max+sum+sort+rounds", "  merge: warp 0 select_stream", "-", "-",
+         "    select: lse", "    select: candidate scoring", "    select: K rounds", "    select: extension+dedupe", "    select: log-add", "    select: write-back", "-", "-"]
 for prec in ("bf16x3", "bf16"):
     h = _native.Handle(vocab_size=d.vocab_size, joiner_dim=d.joiner_dim, decoder_dim=d.decoder_dim, encoder_dim=d.encoder_dim,
                        precision=_native.PREC_NAMES[prec])
