@@ -85,7 +85,7 @@ int32_t frames_for_search(k2b_handle* h, const float* enc_dev, int enc_is_raw, i
 // modified_beam_search on the persistent cluster kernel (tcgen05 precisions): frames -> exp(2x) (fused into the
 // encoder_proj epilogue when the frames are raw), one launch for the whole time loop, then the back-trace.
 int32_t beam_cluster_path(k2b_handle* h, const float* enc, int enc_is_raw, int B, int T, int K, int64_t* tokens, int32_t* ts,
-                          int32_t* n_out, float* score, int cap) {
+                          int32_t* n_out, float* score, int cap, int extra_mask = -1, int64_t* hyp_inout = nullptr) {
   K2B_TRY(ensure_cluster_assets(h));
   const size_t n = (size_t)B * T, J = h->cfg.joiner_dim;
   K2B_TRY(ensure(h, h->ws_encproj, sizeof(float) * n * J));
@@ -104,15 +104,16 @@ int32_t beam_cluster_path(k2b_handle* h, const float* enc, int enc_is_raw, int B
     K2B_TRY(exp2x_frames(h, enc, encE, n * J));
   }
   const size_t NK = (size_t)B * K;
-  const size_t bytes = ((NK * 4 + 255) & ~size_t(255)) * 2 + (((size_t)B * 4 + 255) & ~size_t(255));
+  const size_t bytes = ((NK * 4 + 255) & ~size_t(255)) * 2 + (((size_t)B * 4 + 255) & ~size_t(255)) * 2;
   K2B_TRY(ensure(h, h->ws_state, bytes));
   K2B_TRY(ensure(h, h->ws_bp, sizeof(int32_t) * (size_t)B * T * K));
   char* p = static_cast<char*>(h->ws_state.p);
   float* fin_lp = reinterpret_cast<float*>(p); p += (NK * 4 + 255) & ~size_t(255);
   int32_t* fin_len = reinterpret_cast<int32_t*>(p); p += (NK * 4 + 255) & ~size_t(255);
-  int32_t* fin_nlive = reinterpret_cast<int32_t*>(p);
+  int32_t* fin_nlive = reinterpret_cast<int32_t*>(p); p += ((size_t)B * 4 + 255) & ~size_t(255);
+  if (score == nullptr) score = reinterpret_cast<float*>(p);        // greedy callers have no use for the score
   int32_t* bp = static_cast<int32_t*>(h->ws_bp.p);
-  K2B_TRY(beam_cluster_dev(h, encE, B, T, K, bp, fin_lp, fin_len, fin_nlive));
+  K2B_TRY(beam_cluster_dev(h, encE, B, T, K, bp, fin_lp, fin_len, fin_nlive, extra_mask, hyp_inout, hyp_inout));
   return beam_backtrace_dev(h, B, K, T, fin_lp, fin_len, fin_nlive, bp, tokens, ts, n_out, score, cap);
 }
 
@@ -453,6 +454,11 @@ int32_t k2b_greedy_offline_dev(k2b_handle* h, const float* enc, int32_t enc_is_r
   if (mode < K2B_GREEDY_SINGLE || mode > K2B_GREEDY_PER_STREAM) return fail(h, K2B_ERR_INVALID, "k2b_greedy_offline: unknown mode");
   if (mode == K2B_GREEDY_SINGLE && B != 1) return fail(h, K2B_ERR_INVALID, "k2b_greedy_offline: SINGLE mode needs B == 1");
   if (B == 0) return K2B_OK;
+  // greedy search == beam 1 with the same tie rule: SINGLE / PER_STREAM run on the persistent cluster kernel in the tcgen05
+  // precisions. BATCH_COMPAT (Q6) couples every stream of the batch at every frame and stays on the per-frame path, as does
+  // an utterance long enough to meet the 1000-symbol cap of the single-stream loop (ref OfflineRecognizer.cs:122).
+  if (h->cfg.precision != K2B_PREC_FP32 && mode != K2B_GREEDY_BATCH_COMPAT && cluster_path_supported(h, 1) && T > 0 && T <= 1000)
+    return beam_cluster_path(h, enc, enc_is_raw, B, T, 1, tokens, ts, n_out, nullptr, cap);
   const float* frames = nullptr;
   K2B_TRY(frames_for_search(h, enc, enc_is_raw, B, T, &frames));
   return greedy_dev(h, frames, B, T, mode, false, nullptr, tokens, ts, n_out, cap);
@@ -477,6 +483,7 @@ int32_t k2b_greedy_offline(k2b_handle* h, const float* enc, int32_t enc_is_raw, 
   }
   K2B_CUDA(h, cudaMemcpyAsync(n_out, o.n, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
   K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->cfg.precision != K2B_PREC_FP32) K2B_TRY(cluster_status(h));
   return K2B_OK;
 }
 
@@ -487,6 +494,8 @@ int32_t k2b_greedy_online_chunk_dev(k2b_handle* h, const float* enc, int32_t enc
   K2B_TRY(check_search_args(h, enc, B, Tc, cap, tokens, ts, n_out, "k2b_greedy_online_chunk"));
   if (B > 0 && hyp_inout == nullptr) return fail(h, K2B_ERR_INVALID, "k2b_greedy_online_chunk: hyp_inout is NULL");
   if (B == 0) return K2B_OK;
+  if (h->cfg.precision != K2B_PREC_FP32 && cluster_path_supported(h, 1) && Tc > 0)   // online: Q6 is a no-op (ctx == list tail)
+    return beam_cluster_path(h, enc, enc_is_raw, B, Tc, 1, tokens, ts, n_out, nullptr, cap, 1, hyp_inout);
   const float* frames = nullptr;
   K2B_TRY(frames_for_search(h, enc, enc_is_raw, B, Tc, &frames));
   return greedy_dev(h, frames, B, Tc, K2B_GREEDY_BATCH_COMPAT, true, hyp_inout, tokens, ts, n_out, cap);
@@ -514,6 +523,7 @@ int32_t k2b_greedy_online_chunk(k2b_handle* h, const float* enc, int32_t enc_is_
   K2B_CUDA(h, cudaMemcpyAsync(n_out, o.n, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
   K2B_CUDA(h, cudaMemcpyAsync(hyp_inout, o.hyp, sizeof(int64_t) * 2 * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
   K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->cfg.precision != K2B_PREC_FP32) K2B_TRY(cluster_status(h));
   return K2B_OK;
 }
 

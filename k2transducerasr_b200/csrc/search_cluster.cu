@@ -18,6 +18,7 @@
 //     (log_softmax constants, per-stream top-K, dedupe by sequence hash, log-add, prune) redundantly and
 //     deterministically, so no second exchange is needed. CTA 0 records the back-pointers.
 #include <math.h>
+#include <stdlib.h>
 
 #include "k2b_internal.h"
 #include "sm100_ptx.cuh"
@@ -48,6 +49,9 @@ struct ClusterArgs {
   const uint32_t* wo_lo;    // [CS*128][J/2] packed bf16 pairs
   const float* bias;        // [CS*128], -inf beyond V
   int B, T, K, V, J, S, CS, blank, unk, x3;
+  int extra_mask;           // third non-emitting id (the literal 1 of ref OnlineRecognizer.cs:181), or -1
+  const int64_t* hyp_in;    // [B,2] initial contexts (online: OnlineStream.Hyp), or null = {-1, blank}
+  int64_t* hyp_out;         // [B,2] final context of slot 0 (online), or null
   int32_t* bp;              // [B,T,K]
   float* fin_lp;            // [B*K]
   int32_t* fin_len;         // [B*K]
@@ -88,9 +92,9 @@ constexpr int kKeyNone = (int)0x80000000;
 
 // One warp: hypothesis merge of local stream s (beam_select_kernel in search.cu is the global-memory twin).
 // cand_tab[c] = (h << 16) | (slice << 8) | j for candidate c of a stream (built once per launch); scr = 2*K floats.
-template <int K>
+template <int K, int NHS>
 __device__ __noinline__ void select_stream(int s, int V, int CS, const float* __restrict__ xb, const HypState& in,
-                                           HypState& out, int blank, int unk, int32_t* __restrict__ bp_row, int lane,
+                                           HypState& out, int blank, int unk, int extra_mask, int32_t* __restrict__ bp_row, int lane,
                                            const int* __restrict__ cand_tab, float* __restrict__ scr) {
   constexpr int XWP = xw_padded(K);
   const unsigned full = 0xffffffffu;
@@ -108,10 +112,10 @@ __device__ __noinline__ void select_stream(int s, int V, int CS, const float* __
     float M = -INFINITY, L = 0.f;
     if (lane < nl) {
       const float* e = xb + (size_t)(s * K + lane) * XWP;
-      for (int c = 0; c < CS; ++c) M = fmaxf(M, e[(size_t)c * kNH * XWP]);
+      for (int c = 0; c < CS; ++c) M = fmaxf(M, e[(size_t)c * NHS * XWP]);
       float sum = 0.f;
       for (int c = 0; c < CS; ++c) {
-        const float pm = e[(size_t)c * kNH * XWP], ps = e[(size_t)c * kNH * XWP + 1];
+        const float pm = e[(size_t)c * NHS * XWP], ps = e[(size_t)c * NHS * XWP + 1];
         sum += (pm > -INFINITY) ? ps * __expf(pm - M) : 0.f;
       }
       L = __logf(sum);
@@ -132,7 +136,7 @@ __device__ __noinline__ void select_stream(int s, int V, int CS, const float* __
       const int code = cand_tab[c];
       const int h = code >> 16, slice = (code >> 8) & 0xff, j = code & 0xff;
       if (h < nl) {
-        const float* e = xb + ((size_t)slice * kNH + s * K + h) * XWP;
+        const float* e = xb + ((size_t)slice * NHS + s * K + h) * XWP;
         const int idx = __float_as_int(e[2 + K + j]);
         const float v = ((e[2 + j] - scr[2 * h]) - scr[2 * h + 1]) + in.lp[s * K + h];   // order of log_softmax(x) + lp
         if (idx >= 0 && v == v) { ck[i] = fkey(v); cf[i] = h * V + idx; }
@@ -193,7 +197,7 @@ __device__ __noinline__ void select_stream(int s, int V, int CS, const float* __
     const int y = my_f - par * V;
     const int prow = s * K + par;
     hs = in.hash[prow]; ln = in.len[prow]; c0 = in.ctx0[prow]; c1 = in.ctx1[prow];
-    if (y != blank && y != unk) { tok = y; hs = hash_push_c(hs, y); ln += 1; c0 = c1; c1 = y; }
+    if (y != blank && y != unk && y != extra_mask) { tok = y; hs = hash_push_c(hs, y); ln += 1; c0 = c1; c1 = y; }
   }
   int root = lane;
 #pragma unroll
@@ -296,7 +300,10 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
   if (tid < kNH) {
     const int n = tid, h = n % K;
     for (int b = 0; b < 2; ++b) {
-      st[b].ctx0[n] = -1; st[b].ctx1[n] = a.blank;
+      int c0i = -1, c1i = a.blank;
+      const int gs = cluster * S + n / K;
+      if (a.hyp_in != nullptr && h == 0 && gs < a.B) { c0i = (int)a.hyp_in[2 * gs]; c1i = (int)a.hyp_in[2 * gs + 1]; }
+      st[b].ctx0[n] = c0i; st[b].ctx1[n] = c1i;
       st[b].lp[n] = (h == 0) ? 0.f : -INFINITY;
       st[b].len[n] = 2; st[b].hash[n] = kHashSeedC;
       st[b].nlive[n] = 0;
@@ -323,17 +330,23 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
   const int nq = J / 4;
   int cur = 0;
 
-  // the two hypothesis rows of this warp belong to one stream (K is even): its frame is prefetched one step ahead
+  // the two hypothesis rows of this warp belong to one stream when K is even (two streams for K = 1); the frame rows
+  // are prefetched one step ahead
+  constexpr int NE = (K % 2 == 0) ? 1 : 2;
   const int n0 = warp * 2;
   int g_w = cluster * S + n0 / K;
   if (g_w >= a.B) g_w = a.B - 1;
   const float4* enc_row = reinterpret_cast<const float4*>(a.encE + (size_t)g_w * T * J);
-  float4 ecur[4];
+  int g_w1 = cluster * S + (n0 + 1) / K;
+  if (g_w1 >= a.B) g_w1 = a.B - 1;
+  const float4* enc_row1 = reinterpret_cast<const float4*>(a.encE + (size_t)g_w1 * T * J);
+  float4 ecur[4], ecur1[NE == 2 ? 4 : 1];
   uint32_t xoff[2][4];           // loop-invariant swizzled byte offsets of this thread's 8 operand chunks (hi rows)
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int q = lane + 32 * i;
     if (q < nq) ecur[i] = __ldg(enc_row + q);
+    if (NE == 2 && q < nq) ecur1[NE == 2 ? i : 0] = __ldg(enc_row1 + q);
     const int k = 4 * q;
     xoff[0][i] = (uint32_t)(k >> 6) * kXTile + sw128_offset(n0, k & 63);
     xoff[1][i] = (uint32_t)(k >> 6) * kXTile + sw128_offset(n0 + 1, k & 63);
@@ -358,8 +371,9 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
           const int q = lane + 32 * i;
           if (q < nq) {
             const float4 d = r ? d1[i] : d0[i];
-            const float x0 = tanh_from_exp(ecur[i].x, d.x), x1 = tanh_from_exp(ecur[i].y, d.y);
-            const float x2 = tanh_from_exp(ecur[i].z, d.z), x3 = tanh_from_exp(ecur[i].w, d.w);
+            const float4 ev = (NE == 2 && r) ? ecur1[NE == 2 ? i : 0] : ecur[i];
+            const float x0 = tanh_from_exp(ev.x, d.x), x1 = tanh_from_exp(ev.y, d.y);
+            const float x2 = tanh_from_exp(ev.z, d.z), x3 = tanh_from_exp(ev.w, d.w);
             uint8_t* dst = xop + xoff[r][i];
             if (a.x3) {
               // split by truncation: hi = upper 16 bits (one PRMT per pair), lo = x - hi exactly, rounded to bf16
@@ -380,6 +394,7 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
         for (int i = 0; i < 4; ++i) {
           const int q = lane + 32 * i;
           if (q < nq) ecur[i] = __ldg(pe + q);
+          if (NE == 2 && q < nq) ecur1[NE == 2 ? i : 0] = __ldg(enc_row1 + (size_t)(t + 1) * nq + q);
         }
       }
     }
@@ -524,10 +539,10 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
     K2B_PHASE(6);
 
     // ---- (e) hypothesis merge, redundantly in every CTA --------------------------------------------------------
-    if (warp < S) {
-      const int s = warp, g = cluster * S + s;
+    for (int s = warp; s < S; s += kCThreads / 32) {
+      const int g = cluster * S + s;
       int32_t* bp_row = (rank == 0 && g < a.B) ? a.bp + ((size_t)g * T + t) * K : nullptr;
-      select_stream<K>(s, V, CS, xw, st[cur], st[cur ^ 1], a.blank, a.unk, bp_row, lane, cand_tab, sel_scr[warp]);
+      select_stream<K, kNH>(s, V, CS, xw, st[cur], st[cur ^ 1], a.blank, a.unk, a.extra_mask, bp_row, lane, cand_tab, sel_scr[warp]);
     }
     K2B_PHASE(9);       // sub-phase: this warp's own merge, before waiting for the others
     __syncthreads();
@@ -543,6 +558,323 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
       a.fin_lp[(size_t)g * K + hslot] = st[cur].lp[tid];
       a.fin_len[(size_t)g * K + hslot] = st[cur].len[tid];
       if (hslot == 0) a.fin_nlive[g] = st[cur].nlive[s];
+      if (hslot == 0 && a.hyp_out != nullptr) {          // ref OnlineRecognizer.cs:208: last ctx tokens back into stream.Hyp
+        a.hyp_out[2 * g] = st[cur].ctx0[tid];
+        a.hyp_out[2 * g + 1] = st[cur].ctx1[tid];
+      }
+    }
+  }
+  if (!ok) atomicExch(a.status, 1);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, 512);
+  cluster_sync();
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Two-group variant: the 32 hypothesis rows of a cluster are split into two independent groups of 16 (8 warps each) that
+// run the same frame loop out of phase. Every phase of one group that is pure latency (MMA issue/dispatch, DSMEM exchange,
+// the one-warp-per-stream merge) overlaps the instruction-bound phases (prologue, reductions) of the other. Groups never
+// synchronise with each other: named barriers inside the CTA, and - instead of barrier.cluster, which is CTA-wide - one
+// mbarrier per group whose CS arrivals come from the CTAs of the cluster (mbarrier.arrive.release.cluster on the mapped
+// address) once their partials for this frame are in place.
+constexpr int kG = 2, kGH = 16, kGW = 8;
+constexpr int kXTileG = 32 * 128;        // k-block of one group's stacked operand: 16 hi rows + 16 lo rows
+constexpr int kLtStrideG = 17;
+
+template <int K>
+__global__ void __launch_bounds__(kCThreads, 1) cluster_beam2_kernel(const ClusterArgs a) {
+  constexpr int XWP = xw_padded(K);
+  constexpr int SG = kGH / K;            // streams per group
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ HypState st[kG][2];
+  __shared__ float bias_s[128];
+  __shared__ int cand_tab[kMaxBeam * 8 * kMaxBeam];
+  __shared__ float sel_scr[kCThreads / 32][2 * kMaxBeam];
+  __shared__ uint64_t bar_w, bar_mma[kG], xfull[kG];
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const int grp = warp_u / kGW, wg = warp_u % kGW;
+  const uint32_t x3u = (uint32_t)a.x3;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster = blockIdx.x / a.CS;
+  const int J = a.J, V = a.V, CS = a.CS, T = a.T;
+  const int nkb = J / 64;
+  uint8_t* w_hi = smem;
+  uint8_t* xop = w_hi + (size_t)nkb * 16384 + (size_t)grp * nkb * kXTileG;       // this group's operand
+  float* Lt = reinterpret_cast<float*>(xop);
+  float* xch = reinterpret_cast<float*>(w_hi + (size_t)nkb * 16384 + (size_t)kG * nkb * kXTileG) +
+               (size_t)grp * 2 * CS * kGH * XWP;                                  // [2][CS][kGH][XWP] of this group
+
+  if (tid == 0) {
+    mbar_init(&bar_w, 1);
+    for (int g = 0; g < kG; ++g) { mbar_init(&bar_mma[g], 1); mbar_init(&xfull[g], (uint32_t)CS); }
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  const uint32_t t_d = tbase + (uint32_t)(32 * grp), t_wlo = tbase + 64;
+  const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+
+  if (tid == 0) {
+    mbar_expect_tx(&bar_w, (uint32_t)(nkb * 16384));
+    for (int kb = 0; kb < nkb; ++kb)
+      tma_bulk_g2s(w_hi + (size_t)kb * 16384, a.wo_hi_img + ((size_t)rank * nkb + kb) * 16384, 16384, &bar_w);
+  }
+  if (a.x3 && warp < 4) {
+    const uint32_t* src = a.wo_lo + ((size_t)rank * 128 + tid) * (J / 2);
+    for (int c0 = 0; c0 < J / 2; c0 += 32) {
+      uint32_t v[32];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + c0) + q);
+        v[4 * q] = u.x; v[4 * q + 1] = u.y; v[4 * q + 2] = u.z; v[4 * q + 3] = u.w;
+      }
+      tmem_st32(t_wlo + lane_base + (uint32_t)c0, v);
+    }
+    tmem_st_wait();
+  }
+  if (tid < 128) bias_s[tid] = a.bias[rank * 128 + tid];
+  for (int c = tid; c < K * CS * K; c += kCThreads) {
+    const int h = c / (CS * K), r = c - h * (CS * K);
+    cand_tab[c] = (h << 16) | ((r / K) << 8) | (r % K);
+  }
+  if (tid < kG * kGH) {
+    const int g = tid / kGH, n = tid % kGH, h = n % K;
+    for (int b = 0; b < 2; ++b) {
+      st[g][b].ctx0[n] = -1; st[g][b].ctx1[n] = a.blank;
+      st[g][b].lp[n] = (h == 0) ? 0.f : -INFINITY;
+      st[g][b].len[n] = 2; st[g][b].hash[n] = kHashSeedC;
+      st[g][b].nlive[n] = 0;
+    }
+    if (n < SG) st[g][0].nlive[n] = (cluster * (kG * SG) + g * SG + n < a.B) ? 1 : 0;
+  }
+  bool ok = true;
+  if (tid == 0) ok = mbar_wait(&bar_w, 0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_sync();
+
+  const uint32_t idesc32 = umma_idesc_bf16_f32(128, 32), idesc16 = umma_idesc_bf16_f32(128, 16);
+  const uint32_t desc_hi = 64u | (1u << 14) | (2u << 29);
+  const uint32_t w_lo0 = ((smem_u32(w_hi) & 0x3FFFFu) >> 4) | (1u << 16);
+  const uint32_t x_lo0 = ((smem_u32(xop) & 0x3FFFFu) >> 4) | (1u << 16);
+  const uint32_t gbar = 1u + (uint32_t)grp;
+  const int nq = J / 4;
+  int cur = 0;
+
+  const int n0 = wg * 2;                         // the two rows of this warp inside its group (one stream: K is even)
+  const int s_base = cluster * (kG * SG) + grp * SG;
+  int g_w = s_base + n0 / K;
+  if (g_w >= a.B) g_w = a.B - 1;
+  const float4* enc_row = reinterpret_cast<const float4*>(a.encE + (size_t)g_w * T * J);
+  float4 ecur[4];
+  uint32_t xoff[2][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = lane + 32 * i;
+    if (q < nq) ecur[i] = __ldg(enc_row + q);
+    const int k = 4 * q;
+    xoff[0][i] = (uint32_t)(k >> 6) * kXTileG + sw128_offset(n0, k & 63);
+    xoff[1][i] = (uint32_t)(k >> 6) * kXTileG + sw128_offset(n0 + 1, k & 63);
+  }
+
+  for (int t = 0; t < T; ++t) {
+    // ---- (a) prologue ----------------------------------------------------------------------------------------------
+    {
+      const HypState& sc = st[grp][cur];
+      const float4* pd0 = reinterpret_cast<const float4*>(a.dec_tab + ((size_t)(sc.ctx0[n0] + 1) * V + sc.ctx1[n0]) * J);
+      const float4* pd1 = reinterpret_cast<const float4*>(a.dec_tab + ((size_t)(sc.ctx0[n0 + 1] + 1) * V + sc.ctx1[n0 + 1]) * J);
+      float4 d0[4], d1[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int q = lane + 32 * i;
+        if (q < nq) { d0[i] = __ldg(pd0 + q); d1[i] = __ldg(pd1 + q); }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int q = lane + 32 * i;
+          if (q < nq) {
+            const float4 d = r ? d1[i] : d0[i];
+            const float x0 = tanh_from_exp(ecur[i].x, d.x), x1 = tanh_from_exp(ecur[i].y, d.y);
+            const float x2 = tanh_from_exp(ecur[i].z, d.z), x3 = tanh_from_exp(ecur[i].w, d.w);
+            uint8_t* dst = xop + xoff[r][i];
+            if (a.x3) {
+              const uint32_t b0 = __float_as_uint(x0), b1 = __float_as_uint(x1), b2 = __float_as_uint(x2), b3 = __float_as_uint(x3);
+              *reinterpret_cast<uint2*>(dst) = make_uint2(__byte_perm(b0, b1, 0x7632), __byte_perm(b2, b3, 0x7632));
+              const float l0 = x0 - __uint_as_float(b0 & 0xffff0000u), l1 = x1 - __uint_as_float(b1 & 0xffff0000u);
+              const float l2 = x2 - __uint_as_float(b2 & 0xffff0000u), l3 = x3 - __uint_as_float(b3 & 0xffff0000u);
+              *reinterpret_cast<uint2*>(dst + 16 * 128) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+            } else {
+              *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(x0, x1), pack_bf16x2(x2, x3));
+            }
+          }
+        }
+      }
+      if (t + 1 < T) {
+        const float4* pe = enc_row + (size_t)(t + 1) * nq;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int q = lane + 32 * i;
+          if (q < nq) ecur[i] = __ldg(pe + q);
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    named_bar_sync(gbar, kGW * 32);
+    tc_fence_after();
+
+    // ---- (b) MMAs of this group (its last warp issues) ----------------------------------------------------------------
+    if (wg == kGW - 1) {
+      const uint32_t el = elect_one();
+      uint32_t acc = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t dw = ((uint64_t)desc_hi << 32) | (uint64_t)(w_lo0 + (uint32_t)(kb * (16384 >> 4) + k * 2));
+          const uint64_t dx = ((uint64_t)desc_hi << 32) | (uint64_t)(x_lo0 + (uint32_t)(kb * (kXTileG >> 4) + k * 2));
+          umma_ss_e(t_d, dw, dx, x3u ? idesc32 : idesc16, acc, el);
+          acc = 1;
+          if (x3u) umma_ts_e(t_d, t_wlo + (uint32_t)((kb * 4 + k) * 8), dx, idesc16, 1, el);
+        }
+      }
+      umma_commit_e(&bar_mma[grp], el);
+    }
+
+    // ---- (c) read-out: the group's first four warps own the 128 TMEM lanes -------------------------------------------------
+    if (wg < 4) {
+      if (!mbar_wait(&bar_mma[grp], (uint32_t)(t & 1))) ok = false;
+      tc_fence_after();
+      const int row = wg * 32 + lane;
+      const float bsv = bias_s[row];
+      uint32_t va[16], vb[16];
+      tmem_ld16(t_d + lane_base, va);
+      if (a.x3) tmem_ld16(t_d + lane_base + 16u, vb);
+      tmem_ld_wait();
+#pragma unroll
+      for (int n = 0; n < kGH; ++n) {
+        float v = __uint_as_float(va[n]) + bsv;
+        if (a.x3) v += __uint_as_float(vb[n]);
+        Lt[row * kLtStrideG + n] = v;
+      }
+      tc_fence_before();
+    }
+    named_bar_sync(gbar, kGW * 32);
+
+    // ---- (d) reductions + exchange ----------------------------------------------------------------------------------------
+    float* xw = xch + (size_t)(t & 1) * CS * kGH * XWP;
+    {
+      float v[2][4];
+      int key[2][4];
+      float m[2], sum[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int n = n0 + r;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[r][j] = Lt[(lane + 32 * j) * kLtStrideG + n];
+          const int idx = (int)rank * 128 + lane + 32 * j;
+          key[r][j] = idx < V ? fkey(v[r][j]) : kKeyNone;
+        }
+        m[r] = funkey(__reduce_max_sync(0xffffffffu, max(max(key[r][0], key[r][1]), max(key[r][2], key[r][3]))));
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        sum[r] = 0.f;
+        if (m[r] > -INFINITY) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sum[r] += (key[r][j] != kKeyNone) ? __expf(v[r][j] - m[r]) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        sum[0] += __shfl_xor_sync(0xffffffffu, sum[0], o);
+        sum[1] += __shfl_xor_sync(0xffffffffu, sum[1], o);
+      }
+      int sk[2][4], sj[2][4];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { sk[r][j] = key[r][j]; sj[r][j] = j; }
+#define K2B_CE(x, y)                                                                                    \
+  do {                                                                                                  \
+    const bool sw = sk[r][y] > sk[r][x] || (sk[r][y] == sk[r][x] && sj[r][y] > sj[r][x]);               \
+    const int tk_ = sw ? sk[r][y] : sk[r][x], tj_ = sw ? sj[r][y] : sj[r][x];                           \
+    sk[r][y] = sw ? sk[r][x] : sk[r][y]; sj[r][y] = sw ? sj[r][x] : sj[r][y];                           \
+    sk[r][x] = tk_; sj[r][x] = tj_;                                                                     \
+  } while (0)
+        K2B_CE(0, 1); K2B_CE(2, 3); K2B_CE(0, 2); K2B_CE(1, 3); K2B_CE(1, 2);
+#undef K2B_CE
+      }
+      float out_v[2] = {-INFINITY, -INFINITY};
+      int out_i[2] = {-1, -1};
+#pragma unroll
+      for (int rr = 0; rr < K; ++rr) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int wk = __reduce_max_sync(0xffffffffu, sk[r][0]);
+          const int ci = (sk[r][0] != kKeyNone && sk[r][0] == wk) ? (int)rank * 128 + lane + 32 * sj[r][0] : -1;
+          const int wi = __reduce_max_sync(0xffffffffu, ci);
+          if (ci == wi && wi >= 0) {
+            sk[r][0] = sk[r][1]; sj[r][0] = sj[r][1];
+            sk[r][1] = sk[r][2]; sj[r][1] = sj[r][2];
+            sk[r][2] = sk[r][3]; sj[r][2] = sj[r][3];
+            sk[r][3] = kKeyNone;
+          }
+          if (lane == rr) { out_v[r] = funkey(wk); out_i[r] = wi; }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float* mine = xw + ((size_t)rank * kGH + n0 + r) * XWP;
+        if (lane == 0) { mine[0] = m[r]; mine[1] = sum[r]; }
+        if (lane < K) { mine[2 + lane] = out_v[r]; reinterpret_cast<int*>(mine)[2 + K + lane] = out_i[r]; }
+      }
+      __syncwarp();
+      constexpr int kChunks = 2 * XWP / 4;
+      const uint32_t base = smem_u32(xw + ((size_t)rank * kGH + n0) * XWP);
+      for (int it = lane; it < kChunks * (CS - 1); it += 32) {
+        const int dsel = it / kChunks, ch = it - dsel * kChunks;
+        uint32_t dst = rank + 1 + (uint32_t)dsel;
+        if (dst >= (uint32_t)CS) dst -= (uint32_t)CS;
+        const uint4 q = lds_v4(base + 16u * ch);
+        dsmem_st_v4(dsmem_map(base + 16u * ch, dst), q.x, q.y, q.z, q.w);
+      }
+    }
+    // all of this group's partials are issued -> tell every CTA of the cluster (itself included), then wait for all CS
+    named_bar_sync(gbar, kGW * 32);
+    if (wg == 0 && lane == 0) {
+      fence_acq_rel_cluster();
+      const uint32_t bar_addr = smem_u32(&xfull[grp]);
+      for (uint32_t dst = 0; dst < (uint32_t)CS; ++dst) mbar_arrive_remote(dsmem_map(bar_addr, dst));
+    }
+    if (wg < SG) {
+      if (!mbar_wait_cluster(&xfull[grp], (uint32_t)(t & 1))) ok = false;
+      // ---- (e) hypothesis merge of this group's streams ---------------------------------------------------------------
+      const int s = wg, g = s_base + s;
+      int32_t* bp_row = (rank == 0 && g < a.B) ? a.bp + ((size_t)g * T + t) * K : nullptr;
+      select_stream<K, kGH>(s, V, CS, xw, st[grp][cur], st[grp][cur ^ 1], a.blank, a.unk, a.extra_mask, bp_row, lane, cand_tab, sel_scr[warp]);
+    }
+    named_bar_sync(gbar, kGW * 32);
+    cur ^= 1;
+  }
+
+  if (rank == 0 && wg * 32 + lane < SG * K) {
+    const int i = wg * 32 + lane;
+    const int s = i / K, hslot = i % K, g = s_base + s;
+    if (g < a.B) {
+      a.fin_lp[(size_t)g * K + hslot] = st[grp][cur].lp[i];
+      a.fin_len[(size_t)g * K + hslot] = st[grp][cur].len[i];
+      if (hslot == 0) a.fin_nlive[g] = st[grp][cur].nlive[s];
     }
   }
   if (!ok) atomicExch(a.status, 1);
@@ -587,7 +919,7 @@ bool cluster_path_supported(const k2b_handle* h, int K) {
   const k2b_config& c = h->cfg;
   const int CS = (c.vocab_size + 127) / 128;
   if (c.vocab_size > 1024 || c.joiner_dim > 512 || c.joiner_dim % 64) return false;
-  if (K != 2 && K != 4 && K != 8) return false;      // both rows of a build warp must share one stream
+  if (K != 1 && K != 2 && K != 4 && K != 8) return false;
   const size_t dyn = (size_t)(c.joiner_dim / 64) * (16384 + 64 * 128) + 2ull * CS * kNH * xw_padded(K) * 4;
   if (dyn + 8192 > 227 * 1024) return false;
   const size_t tab = (size_t)(c.vocab_size + 1) * c.vocab_size * c.joiner_dim * sizeof(float);
@@ -636,7 +968,7 @@ int32_t exp2x_frames(k2b_handle* h, const float* in, float* out, size_t n) {
 
 // encE: [B,T,J] frames already mapped through exp(2x). Writes bp + final state; the caller runs the back-trace.
 int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, int32_t* bp, float* fin_lp, int32_t* fin_len,
-                         int32_t* fin_nlive) {
+                         int32_t* fin_nlive, int extra_mask, const int64_t* hyp_in, int64_t* hyp_out) {
   const k2b_config& c = h->cfg;
   const int V = c.vocab_size, J = c.joiner_dim, CS = (V + 127) / 128;
   const int S = kNH / K;
@@ -646,10 +978,15 @@ int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, 
   a.encE = encE; a.dec_tab = h->dec_tab; a.wo_hi_img = h->wo_hi_img; a.wo_lo = h->wo_lo; a.bias = h->bias_pad;
   a.B = B; a.T = T; a.K = K; a.V = V; a.J = J; a.S = S; a.CS = CS; a.blank = c.blank_id; a.unk = c.unk_id;
   a.x3 = c.precision == K2B_PREC_BF16X3 ? 1 : 0;
+  a.extra_mask = extra_mask; a.hyp_in = hyp_in; a.hyp_out = hyp_out;
   a.timing = h->cluster_timing;
   a.bp = bp; a.fin_lp = fin_lp; a.fin_len = fin_len; a.fin_nlive = fin_nlive; a.status = status;
   const size_t dyn = (size_t)(J / 64) * (16384 + 64 * 128) + 2ull * CS * kNH * xw_padded(K) * 4;
-  void (*kern)(const ClusterArgs) = K == 2 ? cluster_beam_kernel<2> : (K == 4 ? cluster_beam_kernel<4> : cluster_beam_kernel<8>);
+  // K2B_CLUSTER_GROUPS=2 selects the two-group variant (measured ~7 % slower on cfg2: the phases are latency-bound per warp)
+  const char* ge = getenv("K2B_CLUSTER_GROUPS");
+  const bool two_groups = ge != nullptr && ge[0] == '2' && K != 1;
+  void (*kern)(const ClusterArgs) = K == 1 ? cluster_beam_kernel<1> : (K == 2 ? cluster_beam_kernel<2> : (K == 4 ? cluster_beam_kernel<4> : cluster_beam_kernel<8>));
+  if (two_groups) kern = K == 2 ? cluster_beam2_kernel<2> : (K == 4 ? cluster_beam2_kernel<4> : cluster_beam2_kernel<8>);
   K2B_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(nclusters * CS));

@@ -126,3 +126,55 @@ def test_encoder_proj_tcgen05(setup, n):
     np.testing.assert_allclose(got, O.encoder_proj(mb, x), rtol=0, atol=3e-5)
     assert np.abs(got - want).max() > 1e-4
     h.close()
+
+
+def test_cluster_greedy_single_per_stream_and_online(setup):
+    """greedy_search on the cluster kernel (beam 1, same tie rule): offline single / per-stream and online chunks."""
+    m, w, raw, enc = setup
+    h = make(MID, w, "bf16x3")
+    h.greedy_offline(enc[:1, :2], _native.GREEDY_SINGLE)   # first tensor-path call builds the tables (one-off launches)
+    n_before = h.launch_count()
+    t, s = h.greedy_offline(enc[:1], _native.GREEDY_SINGLE)
+    assert h.launch_count() - n_before <= 4            # exp2x + cluster kernel + back-trace, not 3 launches per frame
+    compare_streams(t, s, [O.greedy_search_single(m, enc[0])], "cluster greedy single", allow_frac=1.0)
+    t, s = h.greedy_offline(raw, _native.GREEDY_PER_STREAM)
+    compare_streams(t, s, O.greedy_search_batch(m, enc, compat=False), "cluster greedy per_stream", allow_frac=0.12)
+    # BATCH_COMPAT keeps the reference's whole-batch coupling (Q6) on the per-frame path
+    t, s = h.greedy_offline(raw, _native.GREEDY_BATCH_COMPAT)
+    compare_streams(t, s, O.greedy_search_batch(m, enc, compat=True), "compat on per-frame path", allow_frac=0.12)
+    # online chunks: Hyp carried between calls, id 1 masked, chunk-local timestamps
+    B, Tc = raw.shape[0], 8
+    hyp = np.zeros((B, 2), np.int64)
+    ohyp, otoks = [[0, 0]] * B, [[0, 0]] * B
+    for c in range(4):
+        t, s, hyp = h.greedy_online_chunk(np.ascontiguousarray(raw[:, Tc * c:Tc * c + Tc]), hyp)
+        res = O.greedy_search_online_chunk(m, enc[:, Tc * c:Tc * c + Tc], ohyp, otoks)
+        ex = compare_streams(t, s, res, f"cluster online chunk {c}", allow_frac=0.12)
+        if ex:
+            break
+        ohyp, otoks = [r.hyp for r in res], [r.tokens for r in res]
+        assert hyp.tolist() == ohyp
+    h.close()
+
+
+def test_cluster_online_masks_id_1(setup):
+    m, w, raw, enc = setup
+    w2 = {k: (None if v is None else v.copy()) for k, v in w.items()}
+    w2["out_b"][1] += 50.0                                   # id 1 wins every frame
+    h = make(MID, w2, "bf16x3")
+    t, s = h.greedy_offline(enc[:3, :6], _native.GREEDY_PER_STREAM)
+    assert t == [[1] * 6] * 3                                # offline emits id 1 (ref OfflineRecognizer.cs:161)
+    t, s, hyp = h.greedy_online_chunk(np.ascontiguousarray(enc[:3, :6]), np.zeros((3, 2), np.int64), enc_is_raw=False)
+    assert t == [[]] * 3 and hyp.tolist() == [[0, 0]] * 3    # online masks the literal 1 (ref OnlineRecognizer.cs:181)
+    h.close()
+
+
+def test_two_group_variant_matches(setup, monkeypatch):
+    m, w, raw, enc = setup
+    h = make(MID, w, "bf16x3")
+    t1, s1, sc1 = h.modified_beam_search(raw, 4)
+    monkeypatch.setenv("K2B_CLUSTER_GROUPS", "2")
+    t2, s2, sc2 = h.modified_beam_search(raw, 4)
+    assert t1 == t2 and s1 == s2
+    np.testing.assert_allclose(sc1, sc2, atol=1e-4)
+    h.close()
