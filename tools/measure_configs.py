@@ -56,13 +56,14 @@ which = sys.argv[1:] or ["cfg1", "cfg3", "cfg4", "cfg5"]
 
 if "cfg1" in which:
     cfg = synth.CONFIGS["cfg1"]
-    h = handle(cfg)
-    x = torch.from_numpy(synth.make_frames(1, cfg.frames, cfg.dims.encoder_dim, cfg.seed)).to(dev)
-    tok, ts, n, sc = outbufs(1, cfg.frames)
-    ms = timed(lambda: h.call("k2b_greedy_offline_dev", x, 1, 1, cfg.frames, _native.GREEDY_SINGLE, tok, ts, n, cfg.frames), 5)
-    emit(config="cfg1", workload=cfg.name, mode="greedy_search single stream, per-frame fp32 path", frames_per_s=cfg.frames / (ms * 1e-3),
-         ms_per_utterance=ms, us_per_frame_step=ms * 1e3 / cfg.frames, emitted=int(n.item()))
-    h.close()
+    for prec, label in (("fp32", "per-frame fp32 path"), ("bf16x3", "persistent cluster kernel, split-bf16 x3")):
+        h = handle(cfg, prec)
+        x = torch.from_numpy(synth.make_frames(1, cfg.frames, cfg.dims.encoder_dim, cfg.seed)).to(dev)
+        tok, ts, n, sc = outbufs(1, cfg.frames)
+        ms = timed(lambda: h.call("k2b_greedy_offline_dev", x, 1, 1, cfg.frames, _native.GREEDY_SINGLE, tok, ts, n, cfg.frames), 5)
+        emit(config="cfg1", workload=cfg.name, mode="greedy_search single stream, " + label, frames_per_s=cfg.frames / (ms * 1e-3),
+             ms_per_utterance=ms, us_per_frame_step=ms * 1e3 / cfg.frames, emitted=int(n.item()))
+        h.close()
 
 if "cfg3" in which:
     cfg = synth.CONFIGS["cfg3"]
