@@ -77,6 +77,7 @@ struct k2b_handle {
   float* bias_pad = nullptr;      // [CS*128] out_b, -inf beyond V
   float* dec_tab = nullptr;       // [(V+1)*V, J] exp(2*decoder(y0,y1)): the memoised stateless decoder
 
+  int cluster16_ok = -1;          // 16-CTA cluster launchable on this device? (-1 unknown; occupancy query, cached)
   bool enc_ready = false;         // encproj_tc.cu: pre-split, pre-swizzled encoder_proj weight images
   uint8_t* we_hi_img = nullptr;
   uint8_t* we_lo_img = nullptr;

@@ -915,15 +915,48 @@ __global__ void exp2x_kernel(const float* __restrict__ in, float* __restrict__ o
 
 }  // namespace
 
+static void (*cluster_kernel_for(int K, bool two_groups))(const ClusterArgs) {
+  if (two_groups && K != 1) return K == 2 ? cluster_beam2_kernel<2> : (K == 4 ? cluster_beam2_kernel<4> : cluster_beam2_kernel<8>);
+  return K == 1 ? cluster_beam_kernel<1> : (K == 2 ? cluster_beam_kernel<2> : (K == 4 ? cluster_beam_kernel<4> : cluster_beam_kernel<8>));
+}
+
+static size_t cluster_dyn_smem(int J, int CS, int K) {
+  return (size_t)(J / 64) * (16384 + 64 * 128) + 2ull * CS * kNH * xw_padded(K) * 4;
+}
+
+// V <= 1024: portable clusters of up to 8 CTAs, beams 1/2/4/8. 1024 < V <= 2048: 16-CTA (non-portable) clusters, greedy
+// (beam 1) only, and only if the device can co-schedule such a cluster (occupancy query, cached on the handle).
 bool cluster_path_supported(const k2b_handle* h, int K) {
   const k2b_config& c = h->cfg;
   const int CS = (c.vocab_size + 127) / 128;
-  if (c.vocab_size > 1024 || c.joiner_dim > 512 || c.joiner_dim % 64) return false;
+  if (c.vocab_size > 2048 || c.joiner_dim > 512 || c.joiner_dim % 64) return false;
   if (K != 1 && K != 2 && K != 4 && K != 8) return false;
-  const size_t dyn = (size_t)(c.joiner_dim / 64) * (16384 + 64 * 128) + 2ull * CS * kNH * xw_padded(K) * 4;
+  if (CS > 8 && K != 1) return false;
+  const size_t dyn = cluster_dyn_smem(c.joiner_dim, CS, K);
   if (dyn + 8192 > 227 * 1024) return false;
   const size_t tab = (size_t)(c.vocab_size + 1) * c.vocab_size * c.joiner_dim * sizeof(float);
-  return tab <= ((size_t)16 << 30);
+  if (tab > ((size_t)16 << 30)) return false;
+  if (CS > 8) {
+    k2b_handle* hm = const_cast<k2b_handle*>(h);
+    if (hm->cluster16_ok < 0) {
+      hm->cluster16_ok = 0;
+      auto kern = cluster_kernel_for(1, false);
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) == cudaSuccess) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)CS); cfg.blockDim = dim3(kCThreads); cfg.dynamicSmemBytes = dyn;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) == cudaSuccess && nc > 0) hm->cluster16_ok = 1;
+      }
+      cudaGetLastError();   // a failed query must not poison later launches
+    }
+    if (hm->cluster16_ok != 1) return false;
+  }
+  return true;
 }
 
 // Builds (once per weight load) the shared-memory image / TMEM source / padded bias of the joiner weight and the
@@ -981,12 +1014,12 @@ int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, 
   a.extra_mask = extra_mask; a.hyp_in = hyp_in; a.hyp_out = hyp_out;
   a.timing = h->cluster_timing;
   a.bp = bp; a.fin_lp = fin_lp; a.fin_len = fin_len; a.fin_nlive = fin_nlive; a.status = status;
-  const size_t dyn = (size_t)(J / 64) * (16384 + 64 * 128) + 2ull * CS * kNH * xw_padded(K) * 4;
+  const size_t dyn = cluster_dyn_smem(J, CS, K);
   // K2B_CLUSTER_GROUPS=2 selects the two-group variant (measured ~7 % slower on cfg2: the phases are latency-bound per warp)
   const char* ge = getenv("K2B_CLUSTER_GROUPS");
   const bool two_groups = ge != nullptr && ge[0] == '2' && K != 1;
-  void (*kern)(const ClusterArgs) = K == 1 ? cluster_beam_kernel<1> : (K == 2 ? cluster_beam_kernel<2> : (K == 4 ? cluster_beam_kernel<4> : cluster_beam_kernel<8>));
-  if (two_groups) kern = K == 2 ? cluster_beam2_kernel<2> : (K == 4 ? cluster_beam2_kernel<4> : cluster_beam2_kernel<8>);
+  void (*kern)(const ClusterArgs) = cluster_kernel_for(K, two_groups);
+  if (CS > 8) K2B_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   K2B_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(nclusters * CS));

@@ -178,3 +178,28 @@ def test_two_group_variant_matches(setup, monkeypatch):
     assert t1 == t2 and s1 == s2
     np.testing.assert_allclose(sc1, sc2, atol=1e-4)
     h.close()
+
+
+def test_cluster16_greedy_online_vocab_2000(built_lib):
+    """cfg3 shape (V = 2000): 16-CTA non-portable clusters, greedy online chunks, against the oracle."""
+    dims = synth.CONFIGS["cfg3"].dims
+    m, w = model_and_weights(dims, blank_bias=synth.CONFIGS["cfg3"].blank_bias)
+    h = make(dims, w, "bf16x3")
+    B, Tc = 37, 8
+    raw = synth.make_frames(B, 3 * Tc, dims.encoder_dim, 41)
+    enc = O.encoder_proj(m, raw)
+    hyp = np.zeros((B, 2), np.int64)
+    ohyp, otoks = [[0, 0]] * B, [[0, 0]] * B
+    h.greedy_online_chunk(np.ascontiguousarray(raw[:, :Tc]), hyp.copy(), enc_is_raw=True)     # builds the 8 GB table
+    n0 = h.launch_count()
+    for c in range(3):
+        t, s, hyp = h.greedy_online_chunk(np.ascontiguousarray(raw[:, Tc * c:Tc * c + Tc]), hyp, enc_is_raw=True)
+        res = O.greedy_search_online_chunk(m, enc[:, Tc * c:Tc * c + Tc], ohyp, otoks)
+        ex = compare_streams(t, s, res, f"cluster16 online chunk {c}", allow_frac=0.1)
+        if ex:
+            break
+        ohyp, otoks = [r.hyp for r in res], [r.tokens for r in res]
+        assert hyp.tolist() == ohyp
+    per_chunk = (h.launch_count() - n0) / 3
+    assert per_chunk <= 4, f"{per_chunk} launches per chunk: the 16-CTA cluster path was not taken"
+    h.close()

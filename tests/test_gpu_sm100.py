@@ -45,7 +45,7 @@ def test_umma_operand_through_bulk_tma(h):
     np.testing.assert_array_equal(h.selftest_umma(A, B, 0, use_tma=True), h.selftest_umma(A, B, 0, use_tma=False))
 
 
-@pytest.mark.parametrize("csize,ncl", [(1, 3), (2, 5), (4, 37), (8, 18)])
+@pytest.mark.parametrize("csize,ncl", [(1, 3), (2, 5), (4, 37), (8, 18), (16, 4)])
 def test_cluster_dsmem_roundtrip(h, csize, ncl):
     bad, done = h.selftest_cluster(csize, ncl)
     assert bad == 0 and done == csize * ncl

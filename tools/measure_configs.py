@@ -65,9 +65,9 @@ if "cfg1" in which:
              ms_per_utterance=ms, us_per_frame_step=ms * 1e3 / cfg.frames, emitted=int(n.item()))
         h.close()
 
-if "cfg3" in which:
+for _prec3 in (("fp32", "bf16x3") if "cfg3" in which else ()):
     cfg = synth.CONFIGS["cfg3"]
-    h = handle(cfg)
+    h = handle(cfg, _prec3)
     B, Tc, C = cfg.streams, cfg.frames, cfg.chunks
     x = torch.from_numpy(synth.make_frames(B, Tc * C, cfg.dims.encoder_dim, cfg.seed)).to(dev)
     chunks = [x[:, c * Tc:(c + 1) * Tc].contiguous() for c in range(C)]
@@ -79,7 +79,7 @@ if "cfg3" in which:
         for c in range(C):
             h.call("k2b_greedy_online_chunk_dev", chunks[c], 1, B, Tc, hyp, tok, ts, n, Tc)
     ms = timed(run, 2, warm=1)
-    emit(config="cfg3", workload=cfg.name, mode="online greedy, 32 chunks x 8 frames, per-frame fp32 path", frames_per_s=B * Tc * C / (ms * 1e-3),
+    emit(config="cfg3", workload=cfg.name, mode="online greedy, 32 chunks x 8 frames, " + ("per-frame fp32 path" if _prec3 == "fp32" else "16-CTA cluster kernel per chunk, split-bf16 x3"), frames_per_s=B * Tc * C / (ms * 1e-3),
          ms_per_32_chunks=ms, us_per_frame_step=ms * 1e3 / (Tc * C))
     h.close()
 
