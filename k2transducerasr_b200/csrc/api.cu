@@ -40,6 +40,10 @@ void free_cluster_assets(k2b_handle* h) {
   if (h->we_lo_img) cudaFree(h->we_lo_img);
   h->we_hi_img = nullptr; h->we_lo_img = nullptr;
   h->enc_ready = false;
+  if (h->wj_hi_img) cudaFree(h->wj_hi_img);
+  if (h->wj_lo_img) cudaFree(h->wj_lo_img);
+  h->wj_hi_img = nullptr; h->wj_lo_img = nullptr;
+  h->wj_ready = false;
 }
 
 int32_t enter(k2b_handle* h) {
@@ -285,8 +289,8 @@ int32_t k2b_load_weights(k2b_handle* h, const float* emb, const float* conv_w, c
 int32_t k2b_set_precision(k2b_handle* h, int32_t precision) {
   K2B_TRY(enter(h));
   if (precision < K2B_PREC_FP32 || precision > K2B_PREC_BF16) return fail(h, K2B_ERR_INVALID, "unknown precision");
-  if (precision != K2B_PREC_FP32 && !cluster_path_supported(h, 4) && !encproj_tc_supported(h))
-    return fail(h, K2B_ERR_UNSUPPORTED, "tcgen05 precisions need V <= 1024, J <= 512 (multiple of 64) or an encoder_proj with E % 64 == 0, J % 256 == 0");
+  if (precision != K2B_PREC_FP32 && h->cfg.joiner_dim % 64 != 0)
+    return fail(h, K2B_ERR_UNSUPPORTED, "tcgen05 precisions need joiner_dim % 64 == 0");
   h->cfg.precision = precision;
   return K2B_OK;
 }
@@ -565,7 +569,7 @@ int32_t k2b_modified_beam_search(k2b_handle* h, const float* enc, int32_t enc_is
   K2B_CUDA(h, cudaMemcpyAsync(n_out, o.n, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
   K2B_CUDA(h, cudaMemcpyAsync(score, o.score, sizeof(float) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
   K2B_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (h->cfg.precision != K2B_PREC_FP32 && cluster_path_supported(h, K) && T > 0) K2B_TRY(cluster_status(h));
+  if (h->cfg.precision != K2B_PREC_FP32) K2B_TRY(cluster_status(h));
   return K2B_OK;
 }
 

@@ -23,7 +23,8 @@ constexpr int kEM = 128, kEN = 256, kBKc = 64, kStages = 2;
 constexpr int kATile = kEM * 128;        // 16 KB: 128 rows x 64 bf16
 constexpr int kWTile = kEN * 128;        // 32 KB
 constexpr int kStageBytes = 2 * kATile + 2 * kWTile;   // 96 KB
-constexpr int kEThreads = 192;
+constexpr int kEThreads = 320;          // loader + MMA issuer + 8 producer warps (the first four of them are also the epilogue)
+constexpr int kProducers = 8;
 
 struct EncArgs {
   const float* A;            // [M,K] fp32
@@ -33,12 +34,20 @@ struct EncArgs {
   float* C;                  // [M,N]
   int M, N, K, x3, exp2x;
   int* status;
+  // epi 0: store C (optionally exp2x). epi 2 / 3: joiner epilogues - no logits are written, only per (row, 256-column vocab
+  // tile) partials: max / sum-exp / top-k (2, modified_beam_search) or the argmax fold with ties and NaN -> larger index (3).
+  int epi, nvalid, topk;
+  float* part_m; float* part_s; float* part_tv; int32_t* part_ti;     // epi 2: [M,nt], [M,nt], [M,nt,topk] x2
+  float* part_val; int32_t* part_idx; int32_t* part_nan;              // epi 3: [M,nt] each
 };
+
+__device__ __forceinline__ bool better_e(float v, int i, float ev, int ei) { return v > ev || (v == ev && i > ei); }
 
 __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_w[kStages], full_a[kStages], empty[kStages], acc_full;
   __shared__ uint32_t tmem_slot;
+  __shared__ float bias_t[kEN];          // this tile's bias (-inf beyond the valid columns): broadcast reads in the epilogue
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
@@ -50,13 +59,17 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_w[s], 1);
-      mbar_init(&full_a[s], 4);
+      mbar_init(&full_a[s], kProducers);
       mbar_init(&empty[s], 1);
     }
     mbar_init(&acc_full, 1);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  for (int c = tid; c < kEN; c += kEThreads) {
+    const int col = tile_n * kEN + c;
+    bias_t[c] = col < a.nvalid ? __ldg(a.bias + col) : -INFINITY;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -112,25 +125,26 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
     umma_commit_e(&acc_full, el);
   } else {
     // ---- A producers (warps 2..5), then epilogue ------------------------------------------------------------
-    const int pw = warp - 2;              // 0..3: rows pw*32 .. pw*32+31 of the tile
+    const int pw = warp - 2;              // 0..7: rows pw*16 .. pw*16+15 of the tile
     const int half = lane >> 4, c4 = lane & 15;     // two rows per warp instruction, 16 float4 per 64-wide row
+    constexpr int kRowsPerWarp = kEM / kProducers, kIters = kRowsPerWarp / 2;
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % kStages;
       const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
       if (!mbar_wait(&empty[s], ph ^ 1u)) ok = false;
       uint8_t* a_hi = smem + (size_t)s * kStageBytes;
       uint8_t* a_lo = a_hi + kATile;
-      float4 v[16];
+      float4 v[kIters];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int r = pw * 32 + 2 * i + half;
+      for (int i = 0; i < kIters; ++i) {
+        const int r = pw * kRowsPerWarp + 2 * i + half;
         const int m = tile_m * kEM + r;
         v[i] = (m < a.M) ? __ldg(reinterpret_cast<const float4*>(a.A + (size_t)m * a.K + (size_t)kb * kBKc) + c4)
                          : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int r = pw * 32 + 2 * i + half;
+      for (int i = 0; i < kIters; ++i) {
+        const int r = pw * kRowsPerWarp + 2 * i + half;
         const float h0 = bf16_round(v[i].x), h1 = bf16_round(v[i].y), h2 = bf16_round(v[i].z), h3 = bf16_round(v[i].w);
         const uint32_t off = sw128_offset(r, 4 * c4);
         *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
@@ -142,35 +156,113 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_a[s]);
     }
-    // epilogue: this warp owns TMEM lanes 32*(warp%4) .. +31 = tile rows of the same numbers
+    // epilogue (producer warps 0..3 = CTA warps 2..5): a warp owns TMEM lanes 32*(warp%4) .. +31 = those tile rows
+    if (pw < 4) {
     if (!mbar_wait(&acc_full, 0)) ok = false;
     tc_fence_after();
     const int lg = warp & 3;
     const int row = lg * 32 + lane;
     const int m = tile_m * kEM + row;
-    float* crow = a.C + (size_t)m * a.N + (size_t)tile_n * kEN;
-    const float* brow = a.bias + (size_t)tile_n * kEN;
-    for (int c0 = 0; c0 < kEN; c0 += 32) {
-      uint32_t u[32];
-      tmem_ld32(t_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, u);
-      tmem_ld_wait();
-      if (m < a.M) {
+    const uint32_t trow = t_d + ((uint32_t)(lg * 32) << 16);
+    if (a.epi == 0) {
+      float* crow = a.C + (size_t)m * a.N + (size_t)tile_n * kEN;
+      const float* brow = a.bias + (size_t)tile_n * kEN;
+      for (int c0 = 0; c0 < kEN; c0 += 32) {
+        uint32_t u[32];
+        tmem_ld32(trow + (uint32_t)c0, u);
+        tmem_ld_wait();
+        if (m < a.M) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 o;
-          o.x = __uint_as_float(u[4 * q + 0]) + __ldg(brow + c0 + 4 * q + 0);
-          o.y = __uint_as_float(u[4 * q + 1]) + __ldg(brow + c0 + 4 * q + 1);
-          o.z = __uint_as_float(u[4 * q + 2]) + __ldg(brow + c0 + 4 * q + 2);
-          o.w = __uint_as_float(u[4 * q + 3]) + __ldg(brow + c0 + 4 * q + 3);
-          if (a.exp2x) {
-            o.x = expf(2.f * fminf(fmaxf(o.x, -21.f), 21.f));
-            o.y = expf(2.f * fminf(fmaxf(o.y, -21.f), 21.f));
-            o.z = expf(2.f * fminf(fmaxf(o.z, -21.f), 21.f));
-            o.w = expf(2.f * fminf(fmaxf(o.w, -21.f), 21.f));
+          for (int q = 0; q < 8; ++q) {
+            float4 o;
+            o.x = __uint_as_float(u[4 * q + 0]) + __ldg(brow + c0 + 4 * q + 0);
+            o.y = __uint_as_float(u[4 * q + 1]) + __ldg(brow + c0 + 4 * q + 1);
+            o.z = __uint_as_float(u[4 * q + 2]) + __ldg(brow + c0 + 4 * q + 2);
+            o.w = __uint_as_float(u[4 * q + 3]) + __ldg(brow + c0 + 4 * q + 3);
+            if (a.exp2x) {
+              o.x = expf(2.f * fminf(fmaxf(o.x, -21.f), 21.f));
+              o.y = expf(2.f * fminf(fmaxf(o.y, -21.f), 21.f));
+              o.z = expf(2.f * fminf(fmaxf(o.z, -21.f), 21.f));
+              o.w = expf(2.f * fminf(fmaxf(o.w, -21.f), 21.f));
+            }
+            *reinterpret_cast<float4*>(crow + c0 + 4 * q) = o;
           }
-          *reinterpret_cast<float4*>(crow + c0 + 4 * q) = o;
         }
       }
+    } else {
+      // the thread owns one hypothesis row and walks its 256 logits of this vocab tile straight out of TMEM
+      const int col0 = tile_n * kEN;
+      const size_t po = (size_t)m * ntn + tile_n;
+      if (a.epi == 3) {
+        float bv = 0.f;
+        int bi = -1, bnan = 0;
+        for (int c0 = 0; c0 < kEN; c0 += 32) {
+          uint32_t u[32];
+          tmem_ld32(trow + (uint32_t)c0, u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + c0 + j;
+            if (col < a.nvalid) {
+              const float v = __uint_as_float(u[j]) + bias_t[c0 + j];
+              const int vn = (v != v) ? 1 : 0;
+              // sequential fold  token = logits[token] > logits[k] ? token : k  (ref OfflineRecognizer.cs:153)
+              if (bi < 0 || vn || !(bv > v)) { bv = v; bi = col; if (vn) bnan = 1; }
+            }
+          }
+        }
+        if (m < a.M) { a.part_val[po] = bv; a.part_idx[po] = bi; a.part_nan[po] = bnan; }
+      } else {
+        const int K = a.topk;
+        float mx = -INFINITY;
+        for (int c0 = 0; c0 < kEN; c0 += 32) {
+          uint32_t u[32];
+          tmem_ld32(trow + (uint32_t)c0, u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(u[j]) + bias_t[c0 + j]);   // padding columns: -inf
+        }
+        float tv[kMaxBeam];
+        int ti[kMaxBeam];
+#pragma unroll
+        for (int i = 0; i < kMaxBeam; ++i) { tv[i] = -INFINITY; ti[i] = -1; }
+        float thr_v = -INFINITY, sum = 0.f;
+        int thr_i = -1;
+        for (int c0 = 0; c0 < kEN; c0 += 32) {
+          uint32_t u[32];
+          tmem_ld32(trow + (uint32_t)c0, u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + c0 + j;
+            {
+              float v = __uint_as_float(u[j]) + bias_t[c0 + j];     // -inf on padding columns: exp -> 0, never inserted
+              sum += __expf(v - mx);
+              if (better_e(v, col, thr_v, thr_i) && col < a.nvalid) {      // beats the current K-th best: insert
+                int idx = col;
+#pragma unroll
+                for (int i = 0; i < kMaxBeam; ++i) {
+                  if (i < K && better_e(v, idx, tv[i], ti[i])) {
+                    const float fv = tv[i]; const int fi = ti[i];
+                    tv[i] = v; ti[i] = idx; v = fv; idx = fi;
+                  }
+                }
+#pragma unroll
+                for (int i = 0; i < kMaxBeam; ++i)
+                  if (i == K - 1) { thr_v = tv[i]; thr_i = ti[i]; }
+              }
+            }
+          }
+        }
+        if (m < a.M) {
+          a.part_m[po] = mx;
+          a.part_s[po] = (mx == -INFINITY) ? 0.f : sum;
+#pragma unroll
+          for (int i = 0; i < kMaxBeam; ++i)
+            if (i < K) { a.part_tv[po * K + i] = tv[i]; a.part_ti[po * K + i] = ti[i]; }
+        }
+      }
+    }
     }
   }
   if (!ok) atomicExch(a.status, 1);
@@ -209,22 +301,58 @@ int32_t ensure_encproj_assets(k2b_handle* h) {
   return K2B_OK;
 }
 
-// raw [n,E] -> out [n,J] = f(raw * We^T + be) on tcgen05; f = identity or exp(2*clamp(., +-21))
-int32_t encoder_proj_tc(k2b_handle* h, const float* raw, int n, float* out, bool exp2x) {
-  K2B_TRY(ensure_encproj_assets(h));
-  int* status = h->dev_status + 1;
-  EncArgs a;
-  a.A = raw; a.w_hi_img = h->we_hi_img; a.w_lo_img = h->we_lo_img; a.bias = h->enc_b; a.C = out;
-  a.M = n; a.N = h->cfg.joiner_dim; a.K = h->cfg.encoder_dim;
+static int32_t launch_tc(k2b_handle* h, EncArgs& a) {
   a.x3 = h->cfg.precision == K2B_PREC_BF16 ? 0 : 1;
-  a.exp2x = exp2x ? 1 : 0;
-  a.status = status;
-  const int tiles = ((n + kEM - 1) / kEM) * (a.N / kEN);
+  a.status = h->dev_status + 1;
+  const int tiles = ((a.M + kEM - 1) / kEM) * (a.N / kEN);
   const size_t smem = (size_t)kStages * kStageBytes;
   K2B_CUDA(h, cudaFuncSetAttribute(encproj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   encproj_tc_kernel<<<tiles, kEThreads, smem, h->stream>>>(a);
   K2B_LAUNCH_CHECK(h);
   return K2B_OK;
+}
+
+// raw [n,E] -> out [n,J] = f(raw * We^T + be) on tcgen05; f = identity or exp(2*clamp(., +-21))
+int32_t encoder_proj_tc(k2b_handle* h, const float* raw, int n, float* out, bool exp2x) {
+  K2B_TRY(ensure_encproj_assets(h));
+  EncArgs a = {};
+  a.A = raw; a.w_hi_img = h->we_hi_img; a.w_lo_img = h->we_lo_img; a.bias = h->enc_b; a.C = out;
+  a.M = n; a.N = h->cfg.joiner_dim; a.K = h->cfg.encoder_dim;
+  a.exp2x = exp2x ? 1 : 0;
+  a.epi = 0; a.nvalid = a.N;
+  return launch_tc(h, a);
+}
+
+// ---- per-frame tensor-core joiner (any vocabulary): logits tile = x * out_w^T + out_b, reduced in the epilogue ----------
+bool joiner_tc_supported(const k2b_handle* h) { return h->cfg.joiner_dim % 64 == 0 && h->out_w != nullptr; }
+
+int joiner_tc_tiles(const k2b_handle* h) { return (h->cfg.vocab_size + kEN - 1) / kEN; }
+
+static int32_t ensure_joiner_assets(k2b_handle* h) {
+  if (h->wj_ready) return K2B_OK;
+  const int V = h->cfg.vocab_size, K = h->cfg.joiner_dim, Np = joiner_tc_tiles(h) * kEN;
+  K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->wj_hi_img), (size_t)Np * K * 2));
+  K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->wj_lo_img), (size_t)Np * K * 2));
+  K2B_CUDA(h, cudaMemsetAsync(h->wj_hi_img, 0, (size_t)Np * K * 2, h->stream));
+  K2B_CUDA(h, cudaMemsetAsync(h->wj_lo_img, 0, (size_t)Np * K * 2, h->stream));
+  pack_enc_w_kernel<<<V, 128, 0, h->stream>>>(h->out_w, V, K, h->wj_hi_img, h->wj_lo_img);
+  K2B_LAUNCH_CHECK(h);
+  h->wj_ready = true;
+  return K2B_OK;
+}
+
+// x [M,J] fp32 (already tanh(enc+dec)). topk > 0: softmax/top-k partials; topk == 0: argmax partials. nt = joiner_tc_tiles().
+int32_t joiner_tc_partials(k2b_handle* h, const float* x, int M, int topk, float* part_m, float* part_s, float* part_tv,
+                           int32_t* part_ti, float* part_val, int32_t* part_idx, int32_t* part_nan) {
+  K2B_TRY(ensure_joiner_assets(h));
+  EncArgs a = {};
+  a.A = x; a.w_hi_img = h->wj_hi_img; a.w_lo_img = h->wj_lo_img; a.bias = h->out_b; a.C = nullptr;
+  a.M = M; a.N = joiner_tc_tiles(h) * kEN; a.K = h->cfg.joiner_dim;
+  a.exp2x = 0;
+  a.epi = topk > 0 ? 2 : 3; a.nvalid = h->cfg.vocab_size; a.topk = topk;
+  a.part_m = part_m; a.part_s = part_s; a.part_tv = part_tv; a.part_ti = part_ti;
+  a.part_val = part_val; a.part_idx = part_idx; a.part_nan = part_nan;
+  return launch_tc(h, a);
 }
 
 }  // namespace k2b

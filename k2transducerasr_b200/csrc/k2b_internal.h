@@ -81,6 +81,9 @@ struct k2b_handle {
   bool enc_ready = false;         // encproj_tc.cu: pre-split, pre-swizzled encoder_proj weight images
   uint8_t* we_hi_img = nullptr;
   uint8_t* we_lo_img = nullptr;
+  bool wj_ready = false;          // out_w in 256-row tiles for the per-frame tcgen05 joiner (any vocabulary)
+  uint8_t* wj_hi_img = nullptr;
+  uint8_t* wj_lo_img = nullptr;
   int* dev_status = nullptr;      // [4] error flags written by the tcgen05 kernels (mbarrier time-outs)
   long long* cluster_timing = nullptr;   // device [8]: per-phase cycle totals of the cluster kernel (diagnostic)
 
@@ -181,6 +184,10 @@ int32_t cluster_status(k2b_handle* h);
 // ---- encproj_tc.cu -----------------------------------------------------------------------------
 bool encproj_tc_supported(const k2b_handle* h);
 int32_t encoder_proj_tc(k2b_handle* h, const float* raw, int n, float* out, bool exp2x);
+bool joiner_tc_supported(const k2b_handle* h);
+int joiner_tc_tiles(const k2b_handle* h);
+int32_t joiner_tc_partials(k2b_handle* h, const float* x, int M, int topk, float* part_m, float* part_s, float* part_tv,
+                           int32_t* part_ti, float* part_val, int32_t* part_idx, int32_t* part_nan);
 
 // profiling bracket around the dominant GEMM
 void prof_begin(k2b_handle* h);

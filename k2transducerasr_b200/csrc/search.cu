@@ -348,7 +348,8 @@ int32_t greedy_dev(k2b_handle* h, const float* enc, int B, int T, int mode, bool
                    int64_t* tokens, int32_t* ts, int32_t* n_out, int cap) {
   const k2b_config& c = h->cfg;
   const int J = c.joiner_dim, V = c.vocab_size, D = c.decoder_dim;
-  const int nt = num_vocab_tiles(V);
+  const bool tc = c.precision != K2B_PREC_FP32 && joiner_tc_supported(h);   // per-frame tcgen05 joiner (256-column tiles)
+  const int nt = tc ? joiner_tc_tiles(h) : num_vocab_tiles(V);
   K2B_TRY(ensure(h, h->ws_x, sizeof(float) * (size_t)B * J));
   K2B_TRY(ensure(h, h->ws_part, (size_t)B * nt * 12));
   K2B_TRY(ensure(h, h->ws_state, align256((size_t)B * 8) + 256));
@@ -381,7 +382,8 @@ int32_t greedy_dev(k2b_handle* h, const float* enc, int B, int T, int mode, bool
     j.W = h->out_w; j.bias = h->out_b; j.A = x;
     j.part_val = pval; j.part_idx = pidx; j.part_nan = pnan;
     prof_begin(h);
-    K2B_TRY(launch_gemm_simt(h, PRO_PLAIN, EPI_ARGMAX, j));
+    if (tc) K2B_TRY(joiner_tc_partials(h, x, B, 0, nullptr, nullptr, nullptr, nullptr, pval, pidx, pnan));
+    else K2B_TRY(launch_gemm_simt(h, PRO_PLAIN, EPI_ARGMAX, j));
     prof_end(h);
 
     greedy_select_kernel<<<gb, tb, 0, h->stream>>>(B, nt, pval, pidx, pnan, ctx, tokens, ts, n_out, cap, t, c.blank_id,
@@ -399,7 +401,8 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
                  float* score, int cap) {
   const k2b_config& c = h->cfg;
   const int J = c.joiner_dim, V = c.vocab_size, D = c.decoder_dim;
-  const int nt = num_vocab_tiles(V);
+  const bool tc = c.precision != K2B_PREC_FP32 && joiner_tc_supported(h);   // per-frame tcgen05 joiner (256-column tiles)
+  const int nt = tc ? joiner_tc_tiles(h) : num_vocab_tiles(V);
   const int N = B * K;
   K2B_TRY(ensure(h, h->ws_x, sizeof(float) * (size_t)N * J));
   K2B_TRY(ensure(h, h->ws_part, (size_t)N * nt * (8 + 8 * (size_t)K)));
@@ -435,7 +438,8 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
     j.W = h->out_w; j.bias = h->out_b; j.A = x;
     j.part_m = part_m; j.part_s = part_s; j.part_tv = part_tv; j.part_ti = part_ti; j.topk = K;
     prof_begin(h);
-    K2B_TRY(launch_gemm_simt(h, PRO_PLAIN, EPI_TOPK, j));
+    if (tc) K2B_TRY(joiner_tc_partials(h, x, N, K, part_m, part_s, part_tv, part_ti, nullptr, nullptr, nullptr));
+    else K2B_TRY(launch_gemm_simt(h, PRO_PLAIN, EPI_TOPK, j));
     prof_end(h);
 
     beam_select_kernel<<<(B + 3) / 4, 128, 0, h->stream>>>(B, K, V, nt, T, t, c.blank_id, c.unk_id, part_m, part_s,

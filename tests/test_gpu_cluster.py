@@ -203,3 +203,22 @@ def test_cluster16_greedy_online_vocab_2000(built_lib):
     per_chunk = (h.launch_count() - n0) / 3
     assert per_chunk <= 4, f"{per_chunk} launches per chunk: the 16-CTA cluster path was not taken"
     h.close()
+
+
+def test_per_frame_tcgen05_joiner_large_vocab(built_lib):
+    """cfg4 shape (V = 5537, does not fit a cluster): per-frame path with the tcgen05 joiner (256-column vocab tiles, reducing
+    epilogue) for beam search and for greedy, against the oracle."""
+    dims = synth.CONFIGS["cfg4"].dims
+    m, w = model_and_weights(dims, blank_bias=synth.CONFIGS["cfg4"].blank_bias)
+    h = make(dims, w, "bf16x3")
+    raw = synth.make_frames(9, 20, dims.encoder_dim, 43)
+    enc = O.encoder_proj(m, raw)
+    t, s, sc = h.modified_beam_search(raw, 4, enc_is_raw=True)
+    want = O.modified_beam_search(m, enc, 4)
+    ex = compare_streams(t, s, want, "per-frame tc joiner mbs V=5537", allow_frac=0.25)
+    for b, r in enumerate(want):
+        if b not in ex:
+            assert abs(float(sc[b]) - r.score) < SCORE_TOL
+    t, s = h.greedy_offline(raw, _native.GREEDY_BATCH_COMPAT, enc_is_raw=True)
+    compare_streams(t, s, O.greedy_search_batch(m, enc, compat=True), "per-frame tc joiner greedy V=5537", allow_frac=0.25)
+    h.close()
