@@ -222,3 +222,59 @@ def test_per_frame_tcgen05_joiner_large_vocab(built_lib):
     t, s = h.greedy_offline(raw, _native.GREEDY_BATCH_COMPAT, enc_is_raw=True)
     compare_streams(t, s, O.greedy_search_batch(m, enc, compat=True), "per-frame tc joiner greedy V=5537", allow_frac=0.25)
     h.close()
+
+
+SHAPES = [
+    synth.ModelDims(vocab_size=97, joiner_dim=64, decoder_dim=48, encoder_dim=64),      # one CTA per cluster, 1 k-block
+    synth.ModelDims(vocab_size=130, joiner_dim=128, decoder_dim=32, encoder_dim=192),   # 2 slices, last one nearly empty
+    synth.ModelDims(vocab_size=1000, joiner_dim=256, decoder_dim=128, encoder_dim=128), # 8 slices, J = 256 (tc encoder_proj)
+]
+
+
+@pytest.mark.parametrize("dims", SHAPES, ids=lambda d: f"V{d.vocab_size}_J{d.joiner_dim}_D{d.decoder_dim}_E{d.encoder_dim}")
+def test_tensor_paths_over_odd_shapes(built_lib, dims):
+    """Every engine of the tcgen05 precisions on shapes that stress the indexing: cluster sizes 1 / 2 / 8, J != 512, D != J,
+    vocabulary not a multiple of 128, stream counts that do not fill a cluster, all supported beams."""
+    m, w = model_and_weights(dims, blank_bias=0.5)
+    h = make(dims, w, "bf16x3")
+    raw = synth.make_frames(11, 17, dims.encoder_dim, 1000 + dims.vocab_size)
+    enc = O.encoder_proj(m, raw)
+    np.testing.assert_allclose(h.encoder_proj(raw), enc, rtol=0, atol=5e-5)
+    for beam in (2, 4, 8, 3):
+        if beam > dims.vocab_size:
+            continue
+        want = O.modified_beam_search(m, enc, beam)
+        t, s, sc = h.modified_beam_search(raw, beam, enc_is_raw=True)
+        ex = compare_streams(t, s, want, f"{dims.vocab_size}: beam {beam}", allow_frac=0.3)
+        for b, r in enumerate(want):
+            if b not in ex:
+                assert abs(float(sc[b]) - r.score) < SCORE_TOL
+    t, s = h.greedy_offline(raw, _native.GREEDY_PER_STREAM, enc_is_raw=True)
+    compare_streams(t, s, O.greedy_search_batch(m, enc, compat=False), "greedy per_stream", allow_frac=0.3)
+    t, s = h.greedy_offline(raw, _native.GREEDY_BATCH_COMPAT, enc_is_raw=True)
+    compare_streams(t, s, O.greedy_search_batch(m, enc, compat=True), "greedy compat", allow_frac=0.3)
+    hyp = np.zeros((11, 2), np.int64)
+    t, s, hyp = h.greedy_online_chunk(raw, hyp, enc_is_raw=True)
+    res = O.greedy_search_online_chunk(m, enc, [[0, 0]] * 11, [[0, 0]] * 11)
+    ex = compare_streams(t, s, res, "online", allow_frac=0.3)
+    assert [hyp[b].tolist() for b in range(11) if b not in ex] == [r.hyp for b, r in enumerate(res) if b not in ex]
+    h.close()
+
+
+def test_cluster_beam_merge_with_crafted_collisions(built_lib):
+    """blank and unk dominate (both keep ys unchanged) so that merged hypotheses and log-adds occur at every frame."""
+    dims = SHAPES[1]
+    m, w = model_and_weights(dims)
+    w["out_b"] = w["out_b"].copy()
+    w["out_b"][0] += 5.0
+    w["out_b"][2] += 5.0
+    m = O.Model.from_dict(w)
+    h = make(dims, w, "bf16x3")
+    enc = synth.make_frames(5, 12, dims.joiner_dim, 9)
+    for beam in (2, 4):
+        want = O.modified_beam_search(m, enc, beam)
+        t, s, sc = h.modified_beam_search(enc, beam, enc_is_raw=False)
+        ex = compare_streams(t, s, want, f"collisions beam {beam}", allow_frac=0.4)
+        np.testing.assert_allclose([sc[b] for b in range(5) if b not in ex], [r.score for b, r in enumerate(want) if b not in ex],
+                                   atol=SCORE_TOL)
+    h.close()
