@@ -63,6 +63,12 @@ struct ClusterArgs {
 __device__ __forceinline__ bool better_c(float v, int i, float ev, int ei) { return v > ev || (v == ev && i > ei); }
 
 __host__ __device__ constexpr int xw_padded(int K) { return ((2 + 2 * K + 3) / 4) * 4; }   // words per partial, 16 B multiple
+// Bytes of the joiner-operand region: nkb k-block tiles, but never less than the transposed logits tile [128][33] fp32 that
+// aliases it between the MMA and the next prologue (matters for J < 192).
+__host__ __device__ constexpr size_t xop_region_bytes(int nkb, int tile_bytes, int lt_stride) {
+  const size_t ops = (size_t)nkb * tile_bytes, lt = ((size_t)128 * lt_stride * 4 + 1023) / 1024 * 1024;
+  return ops > lt ? ops : lt;
+}
 
 __device__ __forceinline__ uint64_t hash_push_c(uint64_t h, int tok) {
   h = (h ^ (uint64_t)(uint32_t)(tok + 1)) * 0x100000001B3ull;
@@ -258,7 +264,7 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
   uint8_t* w_hi = smem;
   uint8_t* xop = w_hi + (size_t)nkb * 16384;                          // nkb tiles of 64 rows x 128 B
   float* Lt = reinterpret_cast<float*>(xop);                          // aliases the operand between MMA and next build
-  float* xch = reinterpret_cast<float*>(xop + (size_t)nkb * kXTile);  // [2][CS][NH][XWP]
+  float* xch = reinterpret_cast<float*>(xop + xop_region_bytes(nkb, kXTile, kLtStride));  // [2][CS][NH][XWP]
 
   if (tid == 0) {
     mbar_init(&bar_w, 1);
@@ -603,9 +609,9 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam2_kernel(const Clust
   const int J = a.J, V = a.V, CS = a.CS, T = a.T;
   const int nkb = J / 64;
   uint8_t* w_hi = smem;
-  uint8_t* xop = w_hi + (size_t)nkb * 16384 + (size_t)grp * nkb * kXTileG;       // this group's operand
+  uint8_t* xop = w_hi + (size_t)nkb * 16384 + (size_t)grp * xop_region_bytes(nkb, kXTileG, kLtStrideG);   // this group's operand
   float* Lt = reinterpret_cast<float*>(xop);
-  float* xch = reinterpret_cast<float*>(w_hi + (size_t)nkb * 16384 + (size_t)kG * nkb * kXTileG) +
+  float* xch = reinterpret_cast<float*>(w_hi + (size_t)nkb * 16384 + (size_t)kG * xop_region_bytes(nkb, kXTileG, kLtStrideG)) +
                (size_t)grp * 2 * CS * kGH * XWP;                                  // [2][CS][kGH][XWP] of this group
 
   if (tid == 0) {
@@ -921,7 +927,9 @@ static void (*cluster_kernel_for(int K, bool two_groups))(const ClusterArgs) {
 }
 
 static size_t cluster_dyn_smem(int J, int CS, int K) {
-  return (size_t)(J / 64) * (16384 + 64 * 128) + 2ull * CS * kNH * xw_padded(K) * 4;
+  const int nkb = J / 64;
+  const size_t one = xop_region_bytes(nkb, 64 * 128, 33), two = 2 * xop_region_bytes(nkb, 32 * 128, 17);
+  return (size_t)nkb * 16384 + (one > two ? one : two) + 2ull * CS * kNH * xw_padded(K) * 4;
 }
 
 // V <= 1024: portable clusters of up to 8 CTAs, beams 1/2/4/8. 1024 < V <= 2048: 16-CTA (non-portable) clusters, greedy
