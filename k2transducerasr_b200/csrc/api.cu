@@ -121,6 +121,55 @@ int32_t beam_cluster_path(k2b_handle* h, const float* enc, int enc_is_raw, int B
   return beam_backtrace_dev(h, B, K, T, fin_lp, fin_len, fin_nlive, bp, tokens, ts, n_out, score, cap);
 }
 
+// Host-pointer modified_beam_search with the input copy hidden behind the search: the batch is cut into time chunks;
+// chunk c+1 crosses PCIe (strided 2-D copy into a compact [B,Tc,E] staging buffer, on a copy stream) while chunk c is
+// projected and decoded (one cluster-kernel launch per chunk, hypothesis state carried through global memory).
+int32_t beam_cluster_pipelined(k2b_handle* h, const float* enc_host, int B, int T, int K, int64_t* tokens, int32_t* ts,
+                               int32_t* n_out, float* score, int cap) {
+  K2B_TRY(ensure_cluster_assets(h));
+  const int E = h->cfg.encoder_dim, J = h->cfg.joiner_dim;
+  const int nchunk = 4, Tc = (T + nchunk - 1) / nchunk;
+  if (h->copy_stream == nullptr) {
+    K2B_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      K2B_CUDA(h, cudaEventCreateWithFlags(&h->ev_ready[i], cudaEventDisableTiming));
+      K2B_CUDA(h, cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
+    }
+  }
+  const size_t buf_bytes = ((sizeof(float) * (size_t)B * Tc * E) + 255) & ~size_t(255);
+  K2B_TRY(ensure(h, h->ws_in, 2 * buf_bytes));
+  K2B_TRY(ensure(h, h->ws_encproj, sizeof(float) * (size_t)B * T * J));
+  const size_t NK = (size_t)B * K;
+  const size_t a4 = (NK * 4 + 255) & ~size_t(255), a8 = (NK * 8 + 255) & ~size_t(255), ab = ((size_t)B * 4 + 255) & ~size_t(255);
+  K2B_TRY(ensure(h, h->ws_state, 2 * a4 + ab + a8 + a8));
+  K2B_TRY(ensure(h, h->ws_bp, sizeof(int32_t) * (size_t)B * T * K));
+  char* p = static_cast<char*>(h->ws_state.p);
+  float* fin_lp = reinterpret_cast<float*>(p); p += a4;
+  int32_t* fin_len = reinterpret_cast<int32_t*>(p); p += a4;
+  int32_t* fin_nlive = reinterpret_cast<int32_t*>(p); p += ab;
+  int32_t* io_ctx = reinterpret_cast<int32_t*>(p); p += a8;
+  unsigned long long* io_hash = reinterpret_cast<unsigned long long*>(p);
+  float* encE = static_cast<float*>(h->ws_encproj.p);
+  int32_t* bp = static_cast<int32_t*>(h->ws_bp.p);
+  // the staging buffers may still be in use by earlier work on the compute stream
+  K2B_CUDA(h, cudaEventRecord(h->ev_free[0], h->stream));
+  K2B_CUDA(h, cudaEventRecord(h->ev_free[1], h->stream));
+  int c = 0;
+  for (int t0 = 0; t0 < T; t0 += Tc, ++c) {
+    const int tc = (T - t0) < Tc ? (T - t0) : Tc, sb = c & 1;
+    float* stage = reinterpret_cast<float*>(static_cast<char*>(h->ws_in.p) + (size_t)sb * buf_bytes);
+    K2B_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_free[sb], 0));
+    K2B_CUDA(h, cudaMemcpy2DAsync(stage, sizeof(float) * (size_t)tc * E, enc_host + (size_t)t0 * E, sizeof(float) * (size_t)T * E,
+                                  sizeof(float) * (size_t)tc * E, (size_t)B, cudaMemcpyHostToDevice, h->copy_stream));
+    K2B_CUDA(h, cudaEventRecord(h->ev_ready[sb], h->copy_stream));
+    K2B_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_ready[sb], 0));
+    K2B_TRY(encoder_proj_tc(h, stage, B * tc, encE, true, tc, T, t0));
+    K2B_CUDA(h, cudaEventRecord(h->ev_free[sb], h->stream));
+    K2B_TRY(beam_cluster_dev(h, encE, B, tc, K, bp, fin_lp, fin_len, fin_nlive, -1, nullptr, nullptr, t0, T, c > 0 ? 1 : 0, io_ctx, io_hash));
+  }
+  return beam_backtrace_dev(h, B, K, T, fin_lp, fin_len, fin_nlive, bp, tokens, ts, n_out, score, cap);
+}
+
 struct OutStage {
   int64_t* tokens;
   int32_t* ts;
@@ -243,6 +292,8 @@ int32_t k2b_destroy(k2b_handle* h) {
   free_cluster_assets(h);
   if (h->cluster_timing) cudaFree(h->cluster_timing);
   if (h->dev_status) cudaFree(h->dev_status);
+  for (int i = 0; i < 2; ++i) { if (h->ev_ready[i]) cudaEventDestroy(h->ev_ready[i]); if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]); }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   DevBuf* bufs[] = {&h->ws_in, &h->ws_encproj, &h->ws_x, &h->ws_dec, &h->ws_logits, &h->ws_part, &h->ws_state, &h->ws_bp,
                     &h->ws_out, &h->ws_misc, &h->ws_ctc};
   for (DevBuf* b : bufs) free_buf(*b);
@@ -556,12 +607,19 @@ int32_t k2b_modified_beam_search(k2b_handle* h, const float* enc, int32_t enc_is
   if (B == 0) return K2B_OK;
   const size_t width = enc_is_raw ? h->cfg.encoder_dim : h->cfg.joiner_dim;
   const size_t in_bytes = sizeof(float) * (size_t)B * T * width;
-  K2B_TRY(ensure(h, h->ws_in, in_bytes > 0 ? in_bytes : 4));
   OutStage o;
   K2B_TRY(stage_out(h, B, cap > 0 ? cap : 1, &o));
-  if (in_bytes) K2B_CUDA(h, cudaMemcpyAsync(h->ws_in.p, enc, in_bytes, cudaMemcpyHostToDevice, h->stream));
-  K2B_TRY(k2b_modified_beam_search_dev(h, static_cast<const float*>(h->ws_in.p), enc_is_raw, B, T, K, o.tokens, o.ts, o.n,
-                                       o.score, cap));
+  if (K < 1 || K > kMaxBeam) return fail(h, K2B_ERR_INVALID, "k2b_modified_beam_search: beam must be in 1..8");
+  const bool pipelined = enc_is_raw && h->cfg.precision != K2B_PREC_FP32 && cluster_path_supported(h, K) && encproj_tc_supported(h) &&
+                         T >= 32 && !h->profile_on && K <= h->cfg.vocab_size;
+  if (pipelined) {
+    K2B_TRY(beam_cluster_pipelined(h, enc, B, T, K, o.tokens, o.ts, o.n, o.score, cap));
+  } else {
+    K2B_TRY(ensure(h, h->ws_in, in_bytes > 0 ? in_bytes : 4));
+    if (in_bytes) K2B_CUDA(h, cudaMemcpyAsync(h->ws_in.p, enc, in_bytes, cudaMemcpyHostToDevice, h->stream));
+    K2B_TRY(k2b_modified_beam_search_dev(h, static_cast<const float*>(h->ws_in.p), enc_is_raw, B, T, K, o.tokens, o.ts, o.n,
+                                         o.score, cap));
+  }
   if (cap > 0) {
     K2B_CUDA(h, cudaMemcpyAsync(tokens, o.tokens, sizeof(int64_t) * (size_t)B * cap, cudaMemcpyDeviceToHost, h->stream));
     K2B_CUDA(h, cudaMemcpyAsync(ts, o.ts, sizeof(int32_t) * (size_t)B * cap, cudaMemcpyDeviceToHost, h->stream));

@@ -37,6 +37,7 @@ struct EncArgs {
   // epi 0: store C (optionally exp2x). epi 2 / 3: joiner epilogues - no logits are written, only per (row, 256-column vocab
   // tile) partials: max / sum-exp / top-k (2, modified_beam_search) or the argmax fold with ties and NaN -> larger index (3).
   int epi, nvalid, topk;
+  int rows_per_stream, out_T, out_t0;     // epi 0 with rows_per_stream > 0: row m = (b, tt) of a time chunk -> output row b*out_T + out_t0 + tt
   float* part_m; float* part_s; float* part_tv; int32_t* part_ti;     // epi 2: [M,nt], [M,nt], [M,nt,topk] x2
   float* part_val; int32_t* part_idx; int32_t* part_nan;              // epi 3: [M,nt] each
 };
@@ -165,7 +166,9 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
     const int m = tile_m * kEM + row;
     const uint32_t trow = t_d + ((uint32_t)(lg * 32) << 16);
     if (a.epi == 0) {
-      float* crow = a.C + (size_t)m * a.N + (size_t)tile_n * kEN;
+      size_t orow = (size_t)m;
+      if (a.rows_per_stream > 0) { const int b = m / a.rows_per_stream; orow = (size_t)b * a.out_T + a.out_t0 + (m - b * a.rows_per_stream); }
+      float* crow = a.C + orow * a.N + (size_t)tile_n * kEN;
       const float* brow = a.bias + (size_t)tile_n * kEN;
       for (int c0 = 0; c0 < kEN; c0 += 32) {
         uint32_t u[32];
@@ -313,9 +316,10 @@ static int32_t launch_tc(k2b_handle* h, EncArgs& a) {
 }
 
 // raw [n,E] -> out [n,J] = f(raw * We^T + be) on tcgen05; f = identity or exp(2*clamp(., +-21))
-int32_t encoder_proj_tc(k2b_handle* h, const float* raw, int n, float* out, bool exp2x) {
+int32_t encoder_proj_tc(k2b_handle* h, const float* raw, int n, float* out, bool exp2x, int rows_per_stream, int out_T, int out_t0) {
   K2B_TRY(ensure_encproj_assets(h));
   EncArgs a = {};
+  a.rows_per_stream = rows_per_stream; a.out_T = out_T; a.out_t0 = out_t0;
   a.A = raw; a.w_hi_img = h->we_hi_img; a.w_lo_img = h->we_lo_img; a.bias = h->enc_b; a.C = out;
   a.M = n; a.N = h->cfg.joiner_dim; a.K = h->cfg.encoder_dim;
   a.exp2x = exp2x ? 1 : 0;

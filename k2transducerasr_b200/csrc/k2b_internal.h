@@ -84,6 +84,8 @@ struct k2b_handle {
   bool wj_ready = false;          // out_w in 256-row tiles for the per-frame tcgen05 joiner (any vocabulary)
   uint8_t* wj_hi_img = nullptr;
   uint8_t* wj_lo_img = nullptr;
+  cudaStream_t copy_stream = nullptr;   // host-pointer calls: H2D of time chunk c+1 overlaps compute of chunk c
+  cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   int* dev_status = nullptr;      // [4] error flags written by the tcgen05 kernels (mbarrier time-outs)
   long long* cluster_timing = nullptr;   // device [8]: per-phase cycle totals of the cluster kernel (diagnostic)
 
@@ -178,12 +180,14 @@ bool cluster_path_supported(const k2b_handle* h, int K);
 int32_t ensure_cluster_assets(k2b_handle* h);
 int32_t exp2x_frames(k2b_handle* h, const float* in, float* out, size_t n);
 int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, int32_t* bp, float* fin_lp, int32_t* fin_len,
-                         int32_t* fin_nlive, int extra_mask, const int64_t* hyp_in, int64_t* hyp_out);
+                         int32_t* fin_nlive, int extra_mask, const int64_t* hyp_in, int64_t* hyp_out, int t0 = 0, int Ttot = 0,
+                         int resume = 0, int32_t* io_ctx = nullptr, unsigned long long* io_hash = nullptr);
 int32_t cluster_status(k2b_handle* h);
 
 // ---- encproj_tc.cu -----------------------------------------------------------------------------
 bool encproj_tc_supported(const k2b_handle* h);
-int32_t encoder_proj_tc(k2b_handle* h, const float* raw, int n, float* out, bool exp2x);
+int32_t encoder_proj_tc(k2b_handle* h, const float* raw, int n, float* out, bool exp2x, int rows_per_stream = 0, int out_T = 0,
+                        int out_t0 = 0);
 bool joiner_tc_supported(const k2b_handle* h);
 int joiner_tc_tiles(const k2b_handle* h);
 int32_t joiner_tc_partials(k2b_handle* h, const float* x, int M, int topk, float* part_m, float* part_s, float* part_tv,

@@ -52,6 +52,11 @@ struct ClusterArgs {
   int extra_mask;           // third non-emitting id (the literal 1 of ref OnlineRecognizer.cs:181), or -1
   const int64_t* hyp_in;    // [B,2] initial contexts (online: OnlineStream.Hyp), or null = {-1, blank}
   int64_t* hyp_out;         // [B,2] final context of slot 0 (online), or null
+  // time-chunked operation: this launch decodes frames [t0, t0+T) of utterances Ttot frames long; with resume != 0 the
+  // hypothesis state is read from fin_lp / fin_len / fin_nlive / io_ctx / io_hash (written by the previous launch)
+  int t0, Ttot, resume;
+  int32_t* io_ctx;          // [B*K,2]
+  unsigned long long* io_hash;  // [B*K]
   int32_t* bp;              // [B,T,K]
   float* fin_lp;            // [B*K]
   int32_t* fin_len;         // [B*K]
@@ -314,7 +319,18 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
       st[b].len[n] = 2; st[b].hash[n] = kHashSeedC;
       st[b].nlive[n] = 0;
     }
-    if (n < S) st[0].nlive[n] = (cluster * S + n < a.B) ? 1 : 0;
+    if (n < S) {
+      const int gs = cluster * S + n;
+      st[0].nlive[n] = gs < a.B ? (a.resume ? a.fin_nlive[gs] : 1) : 0;
+    }
+    if (a.resume) {                       // continue where the previous time chunk stopped
+      const int gs = cluster * S + n / K;
+      if (gs < a.B) {
+        const size_t gi = (size_t)gs * K + h;
+        st[0].ctx0[n] = a.io_ctx[2 * gi]; st[0].ctx1[n] = a.io_ctx[2 * gi + 1];
+        st[0].lp[n] = a.fin_lp[gi]; st[0].len[n] = a.fin_len[gi]; st[0].hash[n] = a.io_hash[gi];
+      }
+    }
   }
   bool ok = true;
   if (tid == 0) ok = mbar_wait(&bar_w, 0);
@@ -342,10 +358,10 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
   const int n0 = warp * 2;
   int g_w = cluster * S + n0 / K;
   if (g_w >= a.B) g_w = a.B - 1;
-  const float4* enc_row = reinterpret_cast<const float4*>(a.encE + (size_t)g_w * T * J);
+  const float4* enc_row = reinterpret_cast<const float4*>(a.encE + ((size_t)g_w * a.Ttot + a.t0) * J);
   int g_w1 = cluster * S + (n0 + 1) / K;
   if (g_w1 >= a.B) g_w1 = a.B - 1;
-  const float4* enc_row1 = reinterpret_cast<const float4*>(a.encE + (size_t)g_w1 * T * J);
+  const float4* enc_row1 = reinterpret_cast<const float4*>(a.encE + ((size_t)g_w1 * a.Ttot + a.t0) * J);
   float4 ecur[4], ecur1[NE == 2 ? 4 : 1];
   uint32_t xoff[2][4];           // loop-invariant swizzled byte offsets of this thread's 8 operand chunks (hi rows)
 #pragma unroll
@@ -547,7 +563,7 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
     // ---- (e) hypothesis merge, redundantly in every CTA --------------------------------------------------------
     for (int s = warp; s < S; s += kCThreads / 32) {
       const int g = cluster * S + s;
-      int32_t* bp_row = (rank == 0 && g < a.B) ? a.bp + ((size_t)g * T + t) * K : nullptr;
+      int32_t* bp_row = (rank == 0 && g < a.B) ? a.bp + ((size_t)g * a.Ttot + a.t0 + t) * K : nullptr;
       select_stream<K, kNH>(s, V, CS, xw, st[cur], st[cur ^ 1], a.blank, a.unk, a.extra_mask, bp_row, lane, cand_tab, sel_scr[warp]);
     }
     K2B_PHASE(9);       // sub-phase: this warp's own merge, before waiting for the others
@@ -563,6 +579,11 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
     if (g < a.B) {
       a.fin_lp[(size_t)g * K + hslot] = st[cur].lp[tid];
       a.fin_len[(size_t)g * K + hslot] = st[cur].len[tid];
+      if (a.io_ctx != nullptr) {
+        a.io_ctx[2 * ((size_t)g * K + hslot)] = st[cur].ctx0[tid];
+        a.io_ctx[2 * ((size_t)g * K + hslot) + 1] = st[cur].ctx1[tid];
+        a.io_hash[(size_t)g * K + hslot] = st[cur].hash[tid];
+      }
       if (hslot == 0) a.fin_nlive[g] = st[cur].nlive[s];
       if (hslot == 0 && a.hyp_out != nullptr) {          // ref OnlineRecognizer.cs:208: last ctx tokens back into stream.Hyp
         a.hyp_out[2 * g] = st[cur].ctx0[tid];
@@ -679,7 +700,7 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam2_kernel(const Clust
   const int s_base = cluster * (kG * SG) + grp * SG;
   int g_w = s_base + n0 / K;
   if (g_w >= a.B) g_w = a.B - 1;
-  const float4* enc_row = reinterpret_cast<const float4*>(a.encE + (size_t)g_w * T * J);
+  const float4* enc_row = reinterpret_cast<const float4*>(a.encE + ((size_t)g_w * a.Ttot + a.t0) * J);
   float4 ecur[4];
   uint32_t xoff[2][4];
 #pragma unroll
@@ -867,7 +888,7 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam2_kernel(const Clust
       if (!mbar_wait_cluster(&xfull[grp], (uint32_t)(t & 1))) ok = false;
       // ---- (e) hypothesis merge of this group's streams ---------------------------------------------------------------
       const int s = wg, g = s_base + s;
-      int32_t* bp_row = (rank == 0 && g < a.B) ? a.bp + ((size_t)g * T + t) * K : nullptr;
+      int32_t* bp_row = (rank == 0 && g < a.B) ? a.bp + ((size_t)g * a.Ttot + a.t0 + t) * K : nullptr;
       select_stream<K, kGH>(s, V, CS, xw, st[grp][cur], st[grp][cur ^ 1], a.blank, a.unk, a.extra_mask, bp_row, lane, cand_tab, sel_scr[warp]);
     }
     named_bar_sync(gbar, kGW * 32);
@@ -1009,7 +1030,8 @@ int32_t exp2x_frames(k2b_handle* h, const float* in, float* out, size_t n) {
 
 // encE: [B,T,J] frames already mapped through exp(2x). Writes bp + final state; the caller runs the back-trace.
 int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, int32_t* bp, float* fin_lp, int32_t* fin_len,
-                         int32_t* fin_nlive, int extra_mask, const int64_t* hyp_in, int64_t* hyp_out) {
+                         int32_t* fin_nlive, int extra_mask, const int64_t* hyp_in, int64_t* hyp_out, int t0, int Ttot, int resume,
+                         int32_t* io_ctx, unsigned long long* io_hash) {
   const k2b_config& c = h->cfg;
   const int V = c.vocab_size, J = c.joiner_dim, CS = (V + 127) / 128;
   const int S = kNH / K;
@@ -1020,12 +1042,13 @@ int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, 
   a.B = B; a.T = T; a.K = K; a.V = V; a.J = J; a.S = S; a.CS = CS; a.blank = c.blank_id; a.unk = c.unk_id;
   a.x3 = c.precision == K2B_PREC_BF16X3 ? 1 : 0;
   a.extra_mask = extra_mask; a.hyp_in = hyp_in; a.hyp_out = hyp_out;
+  a.t0 = t0; a.Ttot = Ttot > 0 ? Ttot : T; a.resume = resume; a.io_ctx = io_ctx; a.io_hash = io_hash;
   a.timing = h->cluster_timing;
   a.bp = bp; a.fin_lp = fin_lp; a.fin_len = fin_len; a.fin_nlive = fin_nlive; a.status = status;
   const size_t dyn = cluster_dyn_smem(J, CS, K);
   // K2B_CLUSTER_GROUPS=2 selects the two-group variant (measured ~7 % slower on cfg2: the phases are latency-bound per warp)
   const char* ge = getenv("K2B_CLUSTER_GROUPS");
-  const bool two_groups = ge != nullptr && ge[0] == '2' && K != 1;
+  const bool two_groups = ge != nullptr && ge[0] == '2' && K != 1 && io_ctx == nullptr;
   void (*kern)(const ClusterArgs) = cluster_kernel_for(K, two_groups);
   if (CS > 8) K2B_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   K2B_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
