@@ -44,6 +44,19 @@ struct EncArgs {
 
 __device__ __forceinline__ bool better_e(float v, int i, float ev, int ei) { return v > ev || (v == ev && i > ei); }
 
+// Rare path of the top-k epilogue, kept out of line so that the 256-element scan stays small enough for the instruction
+// cache: insert (v, idx) into the sorted list (value desc, index desc) and return the new K-th entry as threshold.
+__device__ __noinline__ void topk_insert(float* tv, int* ti, int K, float v, int idx, float* thr_v, int* thr_i) {
+  for (int i = 0; i < K; ++i) {
+    if (better_e(v, idx, tv[i], ti[i])) {
+      const float fv = tv[i]; const int fi = ti[i];
+      tv[i] = v; ti[i] = idx; v = fv; idx = fi;
+    }
+  }
+  *thr_v = tv[K - 1];
+  *thr_i = ti[K - 1];
+}
+
 __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_w[kStages], full_a[kStages], empty[kStages], acc_full;
@@ -241,19 +254,7 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
             {
               float v = __uint_as_float(u[j]) + bias_t[c0 + j];     // -inf on padding columns: exp -> 0, never inserted
               sum += __expf(v - mx);
-              if (better_e(v, col, thr_v, thr_i) && col < a.nvalid) {      // beats the current K-th best: insert
-                int idx = col;
-#pragma unroll
-                for (int i = 0; i < kMaxBeam; ++i) {
-                  if (i < K && better_e(v, idx, tv[i], ti[i])) {
-                    const float fv = tv[i]; const int fi = ti[i];
-                    tv[i] = v; ti[i] = idx; v = fv; idx = fi;
-                  }
-                }
-#pragma unroll
-                for (int i = 0; i < kMaxBeam; ++i)
-                  if (i == K - 1) { thr_v = tv[i]; thr_i = ti[i]; }
-              }
+              if (better_e(v, col, thr_v, thr_i) && col < a.nvalid) topk_insert(tv, ti, K, v, col, &thr_v, &thr_i);
             }
           }
         }
