@@ -30,7 +30,9 @@ namespace {
 using namespace ptx;
 
 constexpr int kNH = 32;          // hypothesis rows per cluster (UMMA N)
-constexpr int kCThreads = 512;
+constexpr int kCThreads = 512;   // 16 warps
+constexpr int kCAll = kCThreads;
+constexpr int kBuilders = 15;    // one-group kernel: warps 0..14 build the joiner operand, warp 15 only issues MMAs
 constexpr int kLtStride = 33;
 constexpr uint64_t kHashSeedC = 0x9E3779B97F4A7C15ull;
 
@@ -247,7 +249,7 @@ __device__ __noinline__ void select_stream(int s, int V, int CS, const float* __
 }
 
 template <int K>
-__global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const ClusterArgs a) {
+__global__ void __launch_bounds__(kCAll, 1) cluster_beam_kernel(const ClusterArgs a) {
   constexpr int XWP = xw_padded(K);
   constexpr int S = kNH / K;
   constexpr int kXTile = 64 * 128;       // one k-block of the stacked [x_hi (32 rows); x_lo (32 rows)] operand
@@ -256,12 +258,14 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
   __shared__ float bias_s[128];
   __shared__ int cand_tab[kMaxBeam * 8 * kMaxBeam];
   __shared__ float sel_scr[kCThreads / 32][2 * kMaxBeam];
-  __shared__ uint64_t bar_w, bar_mma;
+  __shared__ uint64_t bar_w, bar_mma, bar_q[4];   // bar_q[i]: K-quarter i of the joiner operand is in shared memory (16 warps arrive)
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);     // the compiler knows this one is warp-uniform
   const uint32_t x3u = (uint32_t)a.x3;
+  const bool builder = warp_u < kBuilders;               // warp 15 only issues MMAs; its rows 30, 31 are built as
+                                                         // eight extra quarter-items by warps 0..7
   const uint32_t rank = cluster_ctarank();
   const int cluster = blockIdx.x / a.CS;
   const int J = a.J, V = a.V, CS = a.CS, T = a.T;
@@ -274,6 +278,7 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
   if (tid == 0) {
     mbar_init(&bar_w, 1);
     mbar_init(&bar_mma, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_q[i], kBuilders);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
@@ -304,7 +309,7 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
     tmem_st_wait();
   }
   if (tid < 128) bias_s[tid] = a.bias[rank * 128 + tid];
-  for (int c = tid; c < K * CS * K; c += kCThreads) {
+  for (int c = tid; c < K * CS * K; c += kCAll) {
     const int h = c / (CS * K), r = c - h * (CS * K);
     cand_tab[c] = (h << 16) | ((r / K) << 8) | (r % K);
   }
@@ -373,24 +378,54 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
     xoff[0][i] = (uint32_t)(k >> 6) * kXTile + sw128_offset(n0, k & 63);
     xoff[1][i] = (uint32_t)(k >> 6) * kXTile + sw128_offset(n0 + 1, k & 63);
   }
+  // extra item of warps 0..7: row xn = 30 or 31 (the issuing warp's rows), K-quarter xi
+  const bool has_extra = warp_u < 8;
+  const int xn = 30 + (warp_u >> 2), xi = warp_u & 3, xq = lane + 32 * xi;
+  int g_x = cluster * S + xn / K;
+  if (g_x >= a.B) g_x = a.B - 1;
+  const float4* enc_rowx = reinterpret_cast<const float4*>(a.encE + ((size_t)g_x * a.Ttot + a.t0) * J);
+  const uint32_t xoffx = (uint32_t)((4 * xq) >> 6) * kXTile + sw128_offset(xn, (4 * xq) & 63);
+  float4 ex = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (has_extra && xq < nq) ex = __ldg(enc_rowx + xq);
 
   for (int t = 0; t < T; ++t) {
-    // ---- (a) joiner prologue: x[n,:] = tanh(enc[stream(n),t,:] + dec(ctx(n))) as bf16 hi/lo, K-major swizzled --
-    {
+    // ---- (a) joiner prologue: x[n,:] = tanh(enc[stream(n),t,:] + dec(ctx(n))) as bf16 hi/lo, K-major swizzled.
+    //      Built K-quarter by K-quarter: after each quarter the 16 builder warps arrive on bar_q[i] and the MMA warp
+    //      starts on those two k-blocks while the next quarter is still being computed.
+    if (builder) {
       const HypState& sc = st[cur];
       const float4* pd0 = reinterpret_cast<const float4*>(a.dec_tab + ((size_t)(sc.ctx0[n0] + 1) * V + sc.ctx1[n0]) * J);
       const float4* pd1 = reinterpret_cast<const float4*>(a.dec_tab + ((size_t)(sc.ctx0[n0 + 1] + 1) * V + sc.ctx1[n0 + 1]) * J);
-      float4 d0[4], d1[4];
+      float4 d0[4], d1[4], dx = make_float4(1.f, 1.f, 1.f, 1.f);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int q = lane + 32 * i;
         if (q < nq) { d0[i] = __ldg(pd0 + q); d1[i] = __ldg(pd1 + q); }
       }
+      if (has_extra && xq < nq)
+        dx = __ldg(reinterpret_cast<const float4*>(a.dec_tab + ((size_t)(sc.ctx0[xn] + 1) * V + sc.ctx1[xn]) * J) + xq);
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
+      for (int i = 0; i < 4; ++i) {
+        const int q = lane + 32 * i;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int q = lane + 32 * i;
+        for (int r = 0; r < 3; ++r) {
+          if (r == 2) {                         // the extra item (one float4 of row xn), in its own quarter
+            if (has_extra && xi == i && xq < nq) {
+              const float x0 = tanh_from_exp(ex.x, dx.x), x1 = tanh_from_exp(ex.y, dx.y);
+              const float x2 = tanh_from_exp(ex.z, dx.z), x3 = tanh_from_exp(ex.w, dx.w);
+              uint8_t* dst = xop + xoffx;
+              if (a.x3) {
+                const uint32_t b0 = __float_as_uint(x0), b1 = __float_as_uint(x1), b2 = __float_as_uint(x2), b3 = __float_as_uint(x3);
+                *reinterpret_cast<uint2*>(dst) = make_uint2(__byte_perm(b0, b1, 0x7632), __byte_perm(b2, b3, 0x7632));
+                const float l0 = x0 - __uint_as_float(b0 & 0xffff0000u), l1 = x1 - __uint_as_float(b1 & 0xffff0000u);
+                const float l2 = x2 - __uint_as_float(b2 & 0xffff0000u), l3 = x3 - __uint_as_float(b3 & 0xffff0000u);
+                *reinterpret_cast<uint2*>(dst + 32 * 128) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+              } else {
+                *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(x0, x1), pack_bf16x2(x2, x3));
+              }
+            }
+            continue;
+          }
           if (q < nq) {
             const float4 d = r ? d1[i] : d0[i];
             const float4 ev = (NE == 2 && r) ? ecur1[NE == 2 ? i : 0] : ecur[i];
@@ -409,6 +444,9 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
             }
           }
         }
+        fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_q[i]);
       }
       if (t + 1 < T) {
         const float4* pe = enc_row + (size_t)(t + 1) * nq;
@@ -418,29 +456,30 @@ __global__ void __launch_bounds__(kCThreads, 1) cluster_beam_kernel(const Cluste
           if (q < nq) ecur[i] = __ldg(pe + q);
           if (NE == 2 && q < nq) ecur1[NE == 2 ? i : 0] = __ldg(enc_row1 + (size_t)(t + 1) * nq + q);
         }
+        if (has_extra && xq < nq) ex = __ldg(enc_rowx + (size_t)(t + 1) * nq + xq);
       }
     }
     K2B_PHASE(0);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
     K2B_PHASE(1);
 
-    // ---- (b) D[128 vocab, hyps] = W_slice * x^T on the tensor core; the top warp issues, nobody spins on it -------
+    // ---- (b) D[128 vocab, hyps] = W_slice * x^T on the tensor core, issued by the dedicated warp as the quarters land ----
     //      x3: one SS MMA with the stacked operand (N = 64: cols 0-31 = Wh*xh, 32-63 = Wh*xl) + one TS MMA
     //      (A = Wl resident in TMEM, N = 32) accumulating Wl*xh into cols 0-31.
-    if (warp_u == kCThreads / 32 - 1) {      // warp-uniform loop: descriptors stay in uniform registers, one lane issues
-      const uint32_t el = elect_one();       // (two issuing warps with separate accumulators were measured: no gain)
+    if (!builder) {                          // warp-uniform loop: descriptors stay in uniform registers, one lane issues
+      const uint32_t el = elect_one();
       uint32_t acc = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int qd = 0; qd < 4; ++qd) {
+        if (!mbar_wait(&bar_q[qd], (uint32_t)(t & 1))) ok = false;
+        tc_fence_after();
+        for (int kb = 2 * qd; kb < 2 * qd + 2 && kb < nkb; ++kb) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t dw = ((uint64_t)desc_hi << 32) | (uint64_t)(w_lo0 + (uint32_t)(kb * (16384 >> 4) + k * 2));
-          const uint64_t dx = ((uint64_t)desc_hi << 32) | (uint64_t)(x_lo0 + (uint32_t)(kb * (kXTile >> 4) + k * 2));
-          umma_ss_e(t_d, dw, dx, x3u ? idesc64 : idesc32, acc, el);
-          acc = 1;
-          if (x3u) umma_ts_e(t_d, t_wlo + (uint32_t)((kb * 4 + k) * 8), dx, idesc32, 1, el);
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t dw = ((uint64_t)desc_hi << 32) | (uint64_t)(w_lo0 + (uint32_t)(kb * (16384 >> 4) + k * 2));
+            const uint64_t dx = ((uint64_t)desc_hi << 32) | (uint64_t)(x_lo0 + (uint32_t)(kb * (kXTile >> 4) + k * 2));
+            umma_ss_e(t_d, dw, dx, x3u ? idesc64 : idesc32, acc, el);
+            acc = 1;
+            if (x3u) umma_ts_e(t_d, t_wlo + (uint32_t)((kb * 4 + k) * 8), dx, idesc32, 1, el);
+          }
         }
       }
       umma_commit_e(&bar_mma, el);
@@ -973,7 +1012,7 @@ bool cluster_path_supported(const k2b_handle* h, int K) {
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
           cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) == cudaSuccess) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)CS); cfg.blockDim = dim3(kCThreads); cfg.dynamicSmemBytes = dyn;
+        cfg.gridDim = dim3((unsigned)CS); cfg.blockDim = dim3(kCAll); cfg.dynamicSmemBytes = dyn;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = (unsigned)CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1054,7 +1093,7 @@ int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, 
   K2B_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(nclusters * CS));
-  cfg.blockDim = dim3(kCThreads);
+  cfg.blockDim = dim3(two_groups ? kCThreads : kCAll);
   cfg.dynamicSmemBytes = dyn;
   cfg.stream = h->stream;
   cudaLaunchAttribute at[1];
