@@ -30,9 +30,8 @@ namespace {
 using namespace ptx;
 
 constexpr int kNH = 32;          // hypothesis rows per cluster (UMMA N)
-constexpr int kCThreads = 512;   // 16 warps
-constexpr int kCAll = kCThreads;
-constexpr int kBuilders = 15;    // one-group kernel: warps 0..14 build the joiner operand, warp 15 only issues MMAs
+constexpr int kWorkers = 16;     // warps 0..15: prologue / read-out / reductions / merge
+constexpr int kCAll = (kWorkers + 1) * 32;   // + warp 16, which only issues MMAs
 constexpr int kLtStride = 33;
 constexpr uint64_t kHashSeedC = 0x9E3779B97F4A7C15ull;
 
@@ -65,6 +64,7 @@ struct ClusterArgs {
   int32_t* fin_nlive;       // [B]
   int* status;
   long long* timing;        // optional [8] cycle totals of the step phases (cluster 0, CTA 0, thread 0)
+  int dbg;                  // experiment switches (K2B_DBG), 0 in production
 };
 
 __device__ __forceinline__ bool better_c(float v, int i, float ev, int ei) { return v > ev || (v == ev && i > ei); }
@@ -99,17 +99,27 @@ __device__ __forceinline__ float tanh_from_exp(float ee, float ed) {
   return fmaf(-2.0f, r, 1.0f);
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ int fkey(float f) { const int k = __float_as_int(f); return k >= 0 ? k : (k ^ 0x7fffffff); }
 __device__ __forceinline__ float funkey(int k) { return __int_as_float(k >= 0 ? k : (k ^ 0x7fffffff)); }
 constexpr int kKeyNone = (int)0x80000000;
 
 // One warp: hypothesis merge of local stream s (beam_select_kernel in search.cu is the global-memory twin).
-// cand_tab[c] = (h << 16) | (slice << 8) | j for candidate c of a stream (built once per launch); scr = 2*K floats.
-template <int K, int NHS>
-__device__ __noinline__ void select_stream(int s, int V, int CS, const float* __restrict__ xb, const HypState& in,
-                                           HypState& out, int blank, int unk, int extra_mask, int32_t* __restrict__ bp_row, int lane,
-                                           const int* __restrict__ cand_tab, float* __restrict__ scr) {
+// Lane (h, c) = (hypothesis, vocabulary slice) owns the record of that pair - its slice max / sum-exp and its K best
+// (value, index) candidates - so log-softmax constants are a segmented butterfly over the slice lanes and every candidate is
+// scored in the lane that loaded it. Then K rounds of two REDUX pick the stream's top K over K*V (value, then flat index).
+template <int K>
+__device__ __forceinline__ void select_stream(int s, int V, int CS, int cs_shift, const float* __restrict__ xb, const HypState& in,
+                                              HypState& out, int blank, int unk, int extra_mask, int32_t* __restrict__ bp_row,
+                                              int lane, const float* __restrict__ dec_tab, int J, bool do_prefetch, long long* tp) {
+#define K2B_SUB(i) do { if (tp != nullptr) { const long long now = clock64(); tp[i] += now - tp[19]; tp[19] = now; } } while (0)
+  if (tp != nullptr) tp[19] = clock64();
   constexpr int XWP = xw_padded(K);
+  constexpr int NP = (K == 8) ? 2 : 1;            // K * CS2 <= 32 * NP on every supported shape
   const unsigned full = 0xffffffffu;
   const int nl = in.nlive[s];
   if (nl == 0) {
@@ -120,87 +130,67 @@ __device__ __noinline__ void select_stream(int s, int V, int CS, const float* __
     if (lane == 0) out.nlive[s] = 0;
     return;
   }
-  // log_softmax constants of the live hypotheses: lane h combines the CS slice partials (max, sum-exp)
-  if (lane < K) {
-    float M = -INFINITY, L = 0.f;
-    if (lane < nl) {
-      const float* e = xb + (size_t)(s * K + lane) * XWP;
-      for (int c = 0; c < CS; ++c) M = fmaxf(M, e[(size_t)c * NHS * XWP]);
-      float sum = 0.f;
-      for (int c = 0; c < CS; ++c) {
-        const float pm = e[(size_t)c * NHS * XWP], ps = e[(size_t)c * NHS * XWP + 1];
-        sum += (pm > -INFINITY) ? ps * __expf(pm - M) : 0.f;
-      }
-      L = __logf(sum);
-    }
-    scr[2 * lane] = M;
-    scr[2 * lane + 1] = L;
-  }
-  __syncwarp();
-  // this lane's candidates (every (hyp, slice, j) triple is one): score key + flat index
-  constexpr int CPL = (K * 8 * K + 31) / 32;
-  int ck[CPL], cf[CPL];
-  const int ncand = K * CS * K;
+  const int cs2 = 1 << cs_shift;
+  int ck[NP * K], cf[NP * K];
 #pragma unroll
-  for (int i = 0; i < CPL; ++i) {
-    ck[i] = kKeyNone; cf[i] = -1;
-    const int c = lane + 32 * i;
-    if (c < ncand) {
-      const int code = cand_tab[c];
-      const int h = code >> 16, slice = (code >> 8) & 0xff, j = code & 0xff;
-      if (h < nl) {
-        const float* e = xb + ((size_t)slice * NHS + s * K + h) * XWP;
-        const int idx = __float_as_int(e[2 + K + j]);
-        const float v = ((e[2 + j] - scr[2 * h]) - scr[2 * h + 1]) + in.lp[s * K + h];   // order of log_softmax(x) + lp
-        if (idx >= 0 && v == v) { ck[i] = fkey(v); cf[i] = h * V + idx; }
+  for (int p = 0; p < NP; ++p) {
+    const int pi = p * 32 + lane;
+    const int h = pi >> cs_shift, c = pi & (cs2 - 1);
+    const bool valid = h < nl && c < CS;
+    float w[XWP];
+#pragma unroll
+    for (int i = 0; i < XWP; ++i) w[i] = 0.f;
+    if (valid) {
+      const float4* rec = reinterpret_cast<const float4*>(xb + ((size_t)c * kNH + s * K + h) * XWP);
+#pragma unroll
+      for (int i = 0; i < XWP / 4; ++i) {
+        const float4 q = rec[i];
+        w[4 * i] = q.x; w[4 * i + 1] = q.y; w[4 * i + 2] = q.z; w[4 * i + 3] = q.w;
       }
     }
+    const float pm = valid ? w[0] : -INFINITY;
+    float M = pm;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1)
+      if (o < cs2) M = fmaxf(M, __shfl_xor_sync(full, M, o));
+    float sum = (pm > -INFINITY) ? w[1] * __expf(pm - M) : 0.f;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1)
+      if (o < cs2) sum += __shfl_xor_sync(full, sum, o);
+    const float L = __logf(sum);
+    const float lp = valid ? in.lp[s * K + h] : 0.f;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const int idx = __float_as_int(w[2 + K + j]);
+      const float v = ((w[2 + j] - M) - L) + lp;                       // order of log_softmax(x) + lp
+      const bool okc = valid && idx >= 0 && v == v;
+      ck[p * K + j] = okc ? fkey(v) : kKeyNone;
+      cf[p * K + j] = okc ? h * V + idx : -1;
+    }
   }
+  K2B_SUB(8);
   float my_v = -INFINITY;
   int my_f = -1;
-  if constexpr (CPL <= 4) {
-    // sort the (at most four) local candidates once, best first, then K rounds of REDUX max + pop
-    if constexpr (CPL == 4) {
-#define K2B_CE(x, y)                                                                         \
-  do {                                                                                       \
-    const bool sw = ck[y] > ck[x] || (ck[y] == ck[x] && cf[y] > cf[x]);                      \
-    const int tk_ = sw ? ck[y] : ck[x], tf_ = sw ? cf[y] : cf[x];                            \
-    ck[y] = sw ? ck[x] : ck[y]; cf[y] = sw ? cf[x] : cf[y];                                  \
-    ck[x] = tk_; cf[x] = tf_;                                                                \
-  } while (0)
-      K2B_CE(0, 1); K2B_CE(2, 3); K2B_CE(0, 2); K2B_CE(1, 3); K2B_CE(1, 2);
-#undef K2B_CE
+#pragma unroll
+  for (int r = 0; r < K; ++r) {
+    int bk = ck[0], bf = cf[0];
+#pragma unroll
+    for (int i = 1; i < NP * K; ++i) {                      // predicated selects, no divergent branches
+      const bool b = (ck[i] > bk) | ((ck[i] == bk) & (cf[i] > bf));
+      bk = b ? ck[i] : bk; bf = b ? cf[i] : bf;
     }
+    const int wk = __reduce_max_sync(full, bk);
+    const int wf = __reduce_max_sync(full, (bk == wk) ? bf : -1);
 #pragma unroll
-    for (int r = 0; r < K; ++r) {
-      const int wk = __reduce_max_sync(full, ck[0]);
-      const int wf = __reduce_max_sync(full, (cf[0] >= 0 && ck[0] == wk) ? cf[0] : -1);
-      if (wf >= 0 && cf[0] == wf) {
-#pragma unroll
-        for (int i = 0; i + 1 < CPL; ++i) { ck[i] = ck[i + 1]; cf[i] = cf[i + 1]; }
-        ck[CPL - 1] = kKeyNone; cf[CPL - 1] = -1;
-      }
-      if (lane == r) { my_v = funkey(wk); my_f = wf; }
+    for (int i = 0; i < NP * K; ++i) {
+      const bool hit = (cf[i] == wf) & (wf >= 0);
+      cf[i] = hit ? -1 : cf[i]; ck[i] = hit ? kKeyNone : ck[i];
     }
-  } else {
-    // many candidates per lane (beam 8): rescan per round
-#pragma unroll
-    for (int r = 0; r < K; ++r) {
-      int bk = kKeyNone, bf = -1;
-#pragma unroll
-      for (int i = 0; i < CPL; ++i)
-        if (cf[i] >= 0 && (ck[i] > bk || (ck[i] == bk && cf[i] > bf))) { bk = ck[i]; bf = cf[i]; }
-      const int wk = __reduce_max_sync(full, bk);
-      const int wf = __reduce_max_sync(full, (bf >= 0 && bk == wk) ? bf : -1);
-      if (wf >= 0) {
-#pragma unroll
-        for (int i = 0; i < CPL; ++i)
-          if (cf[i] == wf) cf[i] = -1;
-      }
-      if (lane == r) { my_v = funkey(wk); my_f = wf; }
-    }
+    my_v = (lane == r) ? funkey(wk) : my_v;
+    my_f = (lane == r) ? wf : my_f;
   }
 
+  K2B_SUB(9);
   const bool cand = lane < K && my_f >= 0;
   int par = 0, tok = -1, c0 = -1, c1 = blank, ln = 2;
   uint64_t hs = kHashSeedC;
@@ -212,14 +202,29 @@ __device__ __noinline__ void select_stream(int s, int V, int CS, const float* __
     hs = in.hash[prow]; ln = in.len[prow]; c0 = in.ctx0[prow]; c1 = in.ctx1[prow];
     if (y != blank && y != unk && y != extra_mask) { tok = y; hs = hash_push_c(hs, y); ln += 1; c0 = c1; c1 = y; }
   }
-  int root = lane;
+  if (do_prefetch && cand && tok >= 0)   // pull the new context's decoder row towards L2 while the merge finishes (one TMA-unit op)
+    l2_prefetch_bulk(dec_tab + ((size_t)(c0 + 1) * V + c1) * J, (uint32_t)(J * 4));
+  K2B_SUB(10);
+  // all K*K winner pairs (i, q) compared at once, one pair per lane: bit q of `eqm` of lane i = "winner q < i is the same
+  // token sequence" (hash, length and context all equal); the root of i is its lowest such q
+  unsigned eqm = 0;
+  {
+    const int lnc = cand ? ln : -1 - lane;            // non-candidates never compare equal
 #pragma unroll
-  for (int q = 0; q < K; ++q) {
-    const uint64_t qh = __shfl_sync(full, hs, q);
-    const int ql = __shfl_sync(full, ln, q), q0 = __shfl_sync(full, c0, q), q1 = __shfl_sync(full, c1, q);
-    const int qc = __shfl_sync(full, (int)cand, q);
-    if (cand && qc && q < lane && root == lane && qh == hs && ql == ln && q0 == c0 && q1 == c1) root = q;
+    for (int pass = 0; pass < (K * K + 31) / 32; ++pass) {
+      const int l2 = pass * 32 + lane, i = l2 / K, q = l2 % K;
+      const uint64_t ah = __shfl_sync(full, hs, i), bh = __shfl_sync(full, hs, q);
+      const int al = __shfl_sync(full, lnc, i), bl = __shfl_sync(full, lnc, q);
+      const int a0 = __shfl_sync(full, c0, i), b0 = __shfl_sync(full, c0, q);
+      const int a1 = __shfl_sync(full, c1, i), b1 = __shfl_sync(full, c1, q);
+      const bool eq = (i < K) & (q < i) & (ah == bh) & (al == bl) & (a0 == b0) & (a1 == b1);
+      const unsigned bal = __ballot_sync(full, eq);
+      const int sh = lane * K - pass * 32;
+      if (lane < K && sh >= 0 && sh < 32) eqm |= (bal >> sh) & ((1u << K) - 1u);
+    }
   }
+  const int root = (cand && eqm != 0) ? (__ffs(eqm) - 1) : lane;
+  K2B_SUB(11);
   float lp = my_v;
   const unsigned merged = __ballot_sync(full, cand && root != lane);
   if (merged) {                      // log-add merged scores into their root, in insertion (rank) order
@@ -231,6 +236,7 @@ __device__ __noinline__ void select_stream(int s, int V, int CS, const float* __
       if (cand && qc && q != lane && qroot == lane) lp = logaddexp_c(lp, qv);
     }
   }
+  K2B_SUB(12);
   const bool is_root = cand && root == lane;
   const unsigned roots = __ballot_sync(full, is_root);
   const int nnew = __popc(roots);
@@ -246,30 +252,34 @@ __device__ __noinline__ void select_stream(int s, int V, int CS, const float* __
     if (bp_row != nullptr) bp_row[lane] = 0;
   }
   if (lane == 0) out.nlive[s] = nnew;
+  K2B_SUB(13);
+#undef K2B_SUB
 }
 
-template <int K>
-__global__ void __launch_bounds__(kCAll, 1) cluster_beam_kernel(const ClusterArgs a) {
+// Warp roles: warps 0..15 build the joiner operand (two hypothesis rows each), read the accumulator out, reduce and merge;
+// warp 16 only issues MMAs (as the K-quarters of the operand land) - so the tensor pipe starts on the first quarter while
+// the other three are still being computed.
+template <int K, bool X3>
+__global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
   constexpr int XWP = xw_padded(K);
   constexpr int S = kNH / K;
   constexpr int kXTile = 64 * 128;       // one k-block of the stacked [x_hi (32 rows); x_lo (32 rows)] operand
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ HypState st[2];
   __shared__ float bias_s[128];
-  __shared__ int cand_tab[kMaxBeam * 8 * kMaxBeam];
-  __shared__ float sel_scr[kCThreads / 32][2 * kMaxBeam];
-  __shared__ uint64_t bar_w, bar_mma, bar_q[4];   // bar_q[i]: K-quarter i of the joiner operand is in shared memory (16 warps arrive)
+  __shared__ uint64_t bar_w, bar_mma, bar_q[4];   // bar_q[i]: K-quarter i of the joiner operand is in shared memory
+  __shared__ uint64_t xbar[2];                    // partials of frame t (buffer t & 1): 16 local warps + remote st.async bytes
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);     // the compiler knows this one is warp-uniform
-  const uint32_t x3u = (uint32_t)a.x3;
-  const bool builder = warp_u < kBuilders;               // warp 15 only issues MMAs; its rows 30, 31 are built as
-                                                         // eight extra quarter-items by warps 0..7
+  const bool worker = warp_u < kWorkers;
   const uint32_t rank = cluster_ctarank();
   const int cluster = blockIdx.x / a.CS;
   const int J = a.J, V = a.V, CS = a.CS, T = a.T;
   const int nkb = J / 64;
+  int cs_shift = 0;
+  while ((1 << cs_shift) < CS) ++cs_shift;
   uint8_t* w_hi = smem;
   uint8_t* xop = w_hi + (size_t)nkb * 16384;                          // nkb tiles of 64 rows x 128 B
   float* Lt = reinterpret_cast<float*>(xop);                          // aliases the operand between MMA and next build
@@ -278,7 +288,8 @@ __global__ void __launch_bounds__(kCAll, 1) cluster_beam_kernel(const ClusterArg
   if (tid == 0) {
     mbar_init(&bar_w, 1);
     mbar_init(&bar_mma, 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&bar_q[i], kBuilders);
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_q[i], kWorkers);
+    for (int i = 0; i < 2; ++i) mbar_init(&xbar[i], kWorkers);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
@@ -295,7 +306,7 @@ __global__ void __launch_bounds__(kCAll, 1) cluster_beam_kernel(const ClusterArg
     for (int kb = 0; kb < nkb; ++kb)
       tma_bulk_g2s(w_hi + (size_t)kb * 16384, a.wo_hi_img + ((size_t)rank * nkb + kb) * 16384, 16384, &bar_w);
   }
-  if (a.x3 && warp < 4) {
+  if (X3 && warp < 4) {
     const uint32_t* src = a.wo_lo + ((size_t)rank * 128 + tid) * (J / 2);
     for (int c0 = 0; c0 < J / 2; c0 += 32) {
       uint32_t v[32];
@@ -309,10 +320,6 @@ __global__ void __launch_bounds__(kCAll, 1) cluster_beam_kernel(const ClusterArg
     tmem_st_wait();
   }
   if (tid < 128) bias_s[tid] = a.bias[rank * 128 + tid];
-  for (int c = tid; c < K * CS * K; c += kCAll) {
-    const int h = c / (CS * K), r = c - h * (CS * K);
-    cand_tab[c] = (h << 16) | ((r / K) << 8) | (r % K);
-  }
   if (tid < kNH) {
     const int n = tid, h = n % K;
     for (int b = 0; b < 2; ++b) {
@@ -344,129 +351,25 @@ __global__ void __launch_bounds__(kCAll, 1) cluster_beam_kernel(const ClusterArg
   tc_fence_after();
   cluster_sync();            // every CTA of the cluster is resident: remote shared memory may be written
 
-  long long tph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  __shared__ long long tph[20];          // phase cycle totals live in shared memory: no registers held across the loop
   const bool timed = a.timing != nullptr && blockIdx.x == 0 && tid == 0;
+  if (timed) for (int i = 0; i < 20; ++i) tph[i] = 0;
   long long tlast = timed ? clock64() : 0;
 #define K2B_PHASE(i) do { if (timed) { const long long now = clock64(); tph[i] += now - tlast; tlast = now; } } while (0)
 
-  // UMMA descriptors: constant high word (SBO = 1024 B, version 1, SWIZZLE_128B), low word = address >> 4 | LBO
-  const uint32_t idesc64 = umma_idesc_bf16_f32(128, 64), idesc32 = umma_idesc_bf16_f32(128, 32);
-  const uint32_t desc_hi = 64u | (1u << 14) | (2u << 29);
-  const uint32_t w_lo0 = ((smem_u32(w_hi) & 0x3FFFFu) >> 4) | (1u << 16);
-  const uint32_t x_lo0 = ((smem_u32(xop) & 0x3FFFFu) >> 4) | (1u << 16);
   const int nq = J / 4;
-  int cur = 0;
 
-  // the two hypothesis rows of this warp belong to one stream when K is even (two streams for K = 1); the frame rows
-  // are prefetched one step ahead
-  constexpr int NE = (K % 2 == 0) ? 1 : 2;
-  const int n0 = warp * 2;
-  int g_w = cluster * S + n0 / K;
-  if (g_w >= a.B) g_w = a.B - 1;
-  const float4* enc_row = reinterpret_cast<const float4*>(a.encE + ((size_t)g_w * a.Ttot + a.t0) * J);
-  int g_w1 = cluster * S + (n0 + 1) / K;
-  if (g_w1 >= a.B) g_w1 = a.B - 1;
-  const float4* enc_row1 = reinterpret_cast<const float4*>(a.encE + ((size_t)g_w1 * a.Ttot + a.t0) * J);
-  float4 ecur[4], ecur1[NE == 2 ? 4 : 1];
-  uint32_t xoff[2][4];           // loop-invariant swizzled byte offsets of this thread's 8 operand chunks (hi rows)
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int q = lane + 32 * i;
-    if (q < nq) ecur[i] = __ldg(enc_row + q);
-    if (NE == 2 && q < nq) ecur1[NE == 2 ? i : 0] = __ldg(enc_row1 + q);
-    const int k = 4 * q;
-    xoff[0][i] = (uint32_t)(k >> 6) * kXTile + sw128_offset(n0, k & 63);
-    xoff[1][i] = (uint32_t)(k >> 6) * kXTile + sw128_offset(n0 + 1, k & 63);
-  }
-  // extra item of warps 0..7: row xn = 30 or 31 (the issuing warp's rows), K-quarter xi
-  const bool has_extra = warp_u < 8;
-  const int xn = 30 + (warp_u >> 2), xi = warp_u & 3, xq = lane + 32 * xi;
-  int g_x = cluster * S + xn / K;
-  if (g_x >= a.B) g_x = a.B - 1;
-  const float4* enc_rowx = reinterpret_cast<const float4*>(a.encE + ((size_t)g_x * a.Ttot + a.t0) * J);
-  const uint32_t xoffx = (uint32_t)((4 * xq) >> 6) * kXTile + sw128_offset(xn, (4 * xq) & 63);
-  float4 ex = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (has_extra && xq < nq) ex = __ldg(enc_rowx + xq);
-
-  for (int t = 0; t < T; ++t) {
-    // ---- (a) joiner prologue: x[n,:] = tanh(enc[stream(n),t,:] + dec(ctx(n))) as bf16 hi/lo, K-major swizzled.
-    //      Built K-quarter by K-quarter: after each quarter the 16 builder warps arrive on bar_q[i] and the MMA warp
-    //      starts on those two k-blocks while the next quarter is still being computed.
-    if (builder) {
-      const HypState& sc = st[cur];
-      const float4* pd0 = reinterpret_cast<const float4*>(a.dec_tab + ((size_t)(sc.ctx0[n0] + 1) * V + sc.ctx1[n0]) * J);
-      const float4* pd1 = reinterpret_cast<const float4*>(a.dec_tab + ((size_t)(sc.ctx0[n0 + 1] + 1) * V + sc.ctx1[n0 + 1]) * J);
-      float4 d0[4], d1[4], dx = make_float4(1.f, 1.f, 1.f, 1.f);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int q = lane + 32 * i;
-        if (q < nq) { d0[i] = __ldg(pd0 + q); d1[i] = __ldg(pd1 + q); }
-      }
-      if (has_extra && xq < nq)
-        dx = __ldg(reinterpret_cast<const float4*>(a.dec_tab + ((size_t)(sc.ctx0[xn] + 1) * V + sc.ctx1[xn]) * J) + xq);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int q = lane + 32 * i;
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          if (r == 2) {                         // the extra item (one float4 of row xn), in its own quarter
-            if (has_extra && xi == i && xq < nq) {
-              const float x0 = tanh_from_exp(ex.x, dx.x), x1 = tanh_from_exp(ex.y, dx.y);
-              const float x2 = tanh_from_exp(ex.z, dx.z), x3 = tanh_from_exp(ex.w, dx.w);
-              uint8_t* dst = xop + xoffx;
-              if (a.x3) {
-                const uint32_t b0 = __float_as_uint(x0), b1 = __float_as_uint(x1), b2 = __float_as_uint(x2), b3 = __float_as_uint(x3);
-                *reinterpret_cast<uint2*>(dst) = make_uint2(__byte_perm(b0, b1, 0x7632), __byte_perm(b2, b3, 0x7632));
-                const float l0 = x0 - __uint_as_float(b0 & 0xffff0000u), l1 = x1 - __uint_as_float(b1 & 0xffff0000u);
-                const float l2 = x2 - __uint_as_float(b2 & 0xffff0000u), l3 = x3 - __uint_as_float(b3 & 0xffff0000u);
-                *reinterpret_cast<uint2*>(dst + 32 * 128) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
-              } else {
-                *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(x0, x1), pack_bf16x2(x2, x3));
-              }
-            }
-            continue;
-          }
-          if (q < nq) {
-            const float4 d = r ? d1[i] : d0[i];
-            const float4 ev = (NE == 2 && r) ? ecur1[NE == 2 ? i : 0] : ecur[i];
-            const float x0 = tanh_from_exp(ev.x, d.x), x1 = tanh_from_exp(ev.y, d.y);
-            const float x2 = tanh_from_exp(ev.z, d.z), x3 = tanh_from_exp(ev.w, d.w);
-            uint8_t* dst = xop + xoff[r][i];
-            if (a.x3) {
-              // split by truncation: hi = upper 16 bits (one PRMT per pair), lo = x - hi exactly, rounded to bf16
-              const uint32_t b0 = __float_as_uint(x0), b1 = __float_as_uint(x1), b2 = __float_as_uint(x2), b3 = __float_as_uint(x3);
-              *reinterpret_cast<uint2*>(dst) = make_uint2(__byte_perm(b0, b1, 0x7632), __byte_perm(b2, b3, 0x7632));
-              const float l0 = x0 - __uint_as_float(b0 & 0xffff0000u), l1 = x1 - __uint_as_float(b1 & 0xffff0000u);
-              const float l2 = x2 - __uint_as_float(b2 & 0xffff0000u), l3 = x3 - __uint_as_float(b3 & 0xffff0000u);
-              *reinterpret_cast<uint2*>(dst + 32 * 128) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
-            } else {
-              *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(x0, x1), pack_bf16x2(x2, x3));
-            }
-          }
-        }
-        fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's async proxy
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_q[i]);
-      }
-      if (t + 1 < T) {
-        const float4* pe = enc_row + (size_t)(t + 1) * nq;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int q = lane + 32 * i;
-          if (q < nq) ecur[i] = __ldg(pe + q);
-          if (NE == 2 && q < nq) ecur1[NE == 2 ? i : 0] = __ldg(enc_row1 + (size_t)(t + 1) * nq + q);
-        }
-        if (has_extra && xq < nq) ex = __ldg(enc_rowx + (size_t)(t + 1) * nq + xq);
-      }
-    }
-    K2B_PHASE(0);
-    K2B_PHASE(1);
-
-    // ---- (b) D[128 vocab, hyps] = W_slice * x^T on the tensor core, issued by the dedicated warp as the quarters land ----
-    //      x3: one SS MMA with the stacked operand (N = 64: cols 0-31 = Wh*xh, 32-63 = Wh*xl) + one TS MMA
-    //      (A = Wl resident in TMEM, N = 32) accumulating Wl*xh into cols 0-31.
-    if (!builder) {                          // warp-uniform loop: descriptors stay in uniform registers, one lane issues
-      const uint32_t el = elect_one();
+  if (!worker) {
+    // =============================== MMA warp =================================================================
+    // D[128 vocab, hyps] = W_slice * x^T. X3: one SS MMA with the stacked operand (N = 64: cols 0-31 = Wh*xh, 32-63 = Wh*xl)
+    // + one TS MMA (A = Wl resident in TMEM, N = 32) accumulating Wl*xh into cols 0-31. Warp-uniform loop: the descriptors
+    // stay in uniform registers, one elected lane issues.
+    const uint32_t idesc64 = umma_idesc_bf16_f32(128, 64), idesc32 = umma_idesc_bf16_f32(128, 32);
+    const uint32_t desc_hi = 64u | (1u << 14) | (2u << 29);
+    const uint32_t w_lo0 = ((smem_u32(w_hi) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t x_lo0 = ((smem_u32(xop) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t el = elect_one();
+    for (int t = 0; t < T; ++t) {
       uint32_t acc = 0;
       for (int qd = 0; qd < 4; ++qd) {
         if (!mbar_wait(&bar_q[qd], (uint32_t)(t & 1))) ok = false;
@@ -476,473 +379,239 @@ __global__ void __launch_bounds__(kCAll, 1) cluster_beam_kernel(const ClusterArg
           for (int k = 0; k < 4; ++k) {
             const uint64_t dw = ((uint64_t)desc_hi << 32) | (uint64_t)(w_lo0 + (uint32_t)(kb * (16384 >> 4) + k * 2));
             const uint64_t dx = ((uint64_t)desc_hi << 32) | (uint64_t)(x_lo0 + (uint32_t)(kb * (kXTile >> 4) + k * 2));
-            umma_ss_e(t_d, dw, dx, x3u ? idesc64 : idesc32, acc, el);
+            umma_ss_e(t_d, dw, dx, X3 ? idesc64 : idesc32, acc, el);
             acc = 1;
-            if (x3u) umma_ts_e(t_d, t_wlo + (uint32_t)((kb * 4 + k) * 8), dx, idesc32, 1, el);
+            if (X3) umma_ts_e(t_d, t_wlo + (uint32_t)((kb * 4 + k) * 8), dx, idesc32, 1, el);
           }
         }
       }
       umma_commit_e(&bar_mma, el);
     }
-    K2B_PHASE(2);
+  } else {
+    // =============================== worker warps ===============================================================
+    // the two hypothesis rows of this warp belong to one stream when K is even (two streams for K = 1); the frame rows
+    // are prefetched one step ahead
+    constexpr int NE = (K % 2 == 0) ? 1 : 2;
+    const int n0 = warp * 2;
+    int g_w = cluster * S + n0 / K;
+    if (g_w >= a.B) g_w = a.B - 1;
+    const float4* enc_row = reinterpret_cast<const float4*>(a.encE + ((size_t)g_w * a.Ttot + a.t0) * J);
+    int g_w1 = cluster * S + (n0 + 1) / K;
+    if (g_w1 >= a.B) g_w1 = a.B - 1;
+    const float4* enc_row1 = reinterpret_cast<const float4*>(a.encE + ((size_t)g_w1 * a.Ttot + a.t0) * J);
+    float4 ecur[4], ecur1[NE == 2 ? 4 : 1];
+    uint32_t xoff[2][4];           // loop-invariant swizzled byte offsets of this thread's 8 operand chunks (hi rows)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int q = lane + 32 * i;
+      if (q < nq) ecur[i] = __ldg(enc_row + q);
+      if (NE == 2 && q < nq) ecur1[NE == 2 ? i : 0] = __ldg(enc_row1 + q);
+      const int k = 4 * q;
+      xoff[0][i] = (uint32_t)(k >> 6) * kXTile + sw128_offset(n0, k & 63);
+      xoff[1][i] = (uint32_t)(k >> 6) * kXTile + sw128_offset(n0 + 1, k & 63);
+    }
+    const size_t rm = (a.dbg & 1) ? 0 : ~(size_t)0;
+    const int col0 = 8 * (warp >> 2);            // this warp's 8 accumulator columns (hypotheses) in the read-out
+    const int vrow = 32 * (warp & 3) + lane;     // ... and its vocabulary row of the slice
+    const float bsv = bias_s[vrow];
+    const int nvalid = min(128, V - (int)rank * 128);   // vocabulary entries of this slice
+    int cur = 0;
 
-    // ---- (c) accumulator -> registers (+bias) -> transposed shared tile (warps 0-3 own the 128 TMEM lanes) ----------
-    if (warp < 4) {
-      if (!mbar_wait(&bar_mma, (uint32_t)(t & 1))) ok = false;
-      tc_fence_after();
-      K2B_PHASE(3);
-      const float bsv = bias_s[tid];
+    for (int t = 0; t < T; ++t) {
+      // ---- (a) joiner prologue: x[n,:] = tanh(enc[stream(n),t,:] + dec(ctx(n))) as bf16 hi/lo, K-major swizzled,
+      //      K-quarter by K-quarter (each warp arrives on bar_q[i] after its part of quarter i)
+      {
+        const HypState& sc = st[cur];
+        const float4* pd0 = reinterpret_cast<const float4*>(a.dec_tab + (((size_t)(sc.ctx0[n0] + 1) * V + sc.ctx1[n0]) & rm) * J);
+        const float4* pd1 = reinterpret_cast<const float4*>(a.dec_tab + (((size_t)(sc.ctx0[n0 + 1] + 1) * V + sc.ctx1[n0 + 1]) & rm) * J);
+        float4 d0[4], d1[4];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t va[16], vb[16];
-        tmem_ld16(t_d + lane_base + (uint32_t)(16 * half), va);
-        if (a.x3) tmem_ld16(t_d + lane_base + (uint32_t)(32 + 16 * half), vb);
-        tmem_ld_wait();
-#pragma unroll
-        for (int n = 0; n < 16; ++n) {
-          float v = __uint_as_float(va[n]) + bsv;
-          if (a.x3) v += __uint_as_float(vb[n]);
-          Lt[tid * kLtStride + 16 * half + n] = v;
+        for (int i = 0; i < 4; ++i) {
+          const int q = lane + 32 * i;
+          if (q < nq) { d0[i] = __ldg(pd0 + q); d1[i] = __ldg(pd1 + q); }
         }
-      }
-      tc_fence_before();
-    }
-    __syncthreads();
-    K2B_PHASE(4);
-
-    // ---- (d) per hypothesis (two per warp, interleaved): max, sum-exp and top-K over this slice's 128 logits ---------
-    float* xw = xch + (size_t)(t & 1) * CS * kNH * XWP;
-    {
-      float v[2][4];
-      int key[2][4];
-      float m[2], sum[2];
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int n = warp * 2 + r;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          v[r][j] = Lt[(lane + 32 * j) * kLtStride + n];
-          const int idx = (int)rank * 128 + lane + 32 * j;
-          key[r][j] = idx < V ? fkey(v[r][j]) : kKeyNone;
-        }
-        m[r] = funkey(__reduce_max_sync(0xffffffffu, max(max(key[r][0], key[r][1]), max(key[r][2], key[r][3]))));
-      }
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        sum[r] = 0.f;
-        if (m[r] > -INFINITY) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) sum[r] += (key[r][j] != kKeyNone) ? __expf(v[r][j] - m[r]) : 0.f;
-        }
-      }
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) {
-        sum[0] += __shfl_xor_sync(0xffffffffu, sum[0], o);
-        sum[1] += __shfl_xor_sync(0xffffffffu, sum[1], o);
-      }
-      // sort this lane's four (key, j) pairs once, best first (equal keys: larger j = larger vocab index first) ...
-      int sk[2][4], sj[2][4];
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { sk[r][j] = key[r][j]; sj[r][j] = j; }
-#define K2B_CE(x, y)                                                                                    \
-  do {                                                                                                  \
-    const bool sw = sk[r][y] > sk[r][x] || (sk[r][y] == sk[r][x] && sj[r][y] > sj[r][x]);               \
-    const int tk_ = sw ? sk[r][y] : sk[r][x], tj_ = sw ? sj[r][y] : sj[r][x];                           \
-    sk[r][y] = sw ? sk[r][x] : sk[r][y]; sj[r][y] = sw ? sj[r][x] : sj[r][y];                           \
-    sk[r][x] = tk_; sj[r][x] = tj_;                                                                     \
-  } while (0)
-        K2B_CE(0, 1); K2B_CE(2, 3); K2B_CE(0, 2); K2B_CE(1, 3); K2B_CE(1, 2);
-#undef K2B_CE
-      }
-      // ... then K rounds: REDUX max of the heads, ties -> larger vocab index (second REDUX), the winner pops its head
-      float out_v[2] = {-INFINITY, -INFINITY};
-      int out_i[2] = {-1, -1};
-#pragma unroll
-      for (int rr = 0; rr < K; ++rr) {
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int wk = __reduce_max_sync(0xffffffffu, sk[r][0]);
-          const int ci = (sk[r][0] != kKeyNone && sk[r][0] == wk) ? (int)rank * 128 + lane + 32 * sj[r][0] : -1;
-          const int wi = __reduce_max_sync(0xffffffffu, ci);
-          if (ci == wi && wi >= 0) {
-            sk[r][0] = sk[r][1]; sj[r][0] = sj[r][1];
-            sk[r][1] = sk[r][2]; sj[r][1] = sj[r][2];
-            sk[r][2] = sk[r][3]; sj[r][2] = sj[r][3];
-            sk[r][3] = kKeyNone;
-          }
-          if (lane == rr) { out_v[r] = funkey(wk); out_i[r] = wi; }
-        }
-      }
-      K2B_PHASE(8);     // sub-phase: loads + max + sum + sort + K rounds
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        float* mine = xw + ((size_t)rank * kNH + warp * 2 + r) * XWP;
-        if (lane == 0) { mine[0] = m[r]; mine[1] = sum[r]; }
-        if (lane < K) { mine[2 + lane] = out_v[r]; reinterpret_cast<int*>(mine)[2 + K + lane] = out_i[r]; }
-      }
-      __syncwarp();
-      // copy both partials (contiguous) into the same slots of every other CTA of the cluster, 16 bytes per lane
-      constexpr int kChunks = 2 * XWP / 4;
-      const uint32_t base = smem_u32(xw + ((size_t)rank * kNH + warp * 2) * XWP);
-      for (int it = lane; it < kChunks * (CS - 1); it += 32) {
-        const int dsel = it / kChunks, ch = it - dsel * kChunks;
-        uint32_t dst = rank + 1 + (uint32_t)dsel;
-        if (dst >= (uint32_t)CS) dst -= (uint32_t)CS;
-        const uint4 q = lds_v4(base + 16u * ch);
-        dsmem_st_v4(dsmem_map(base + 16u * ch, dst), q.x, q.y, q.z, q.w);
-      }
-    }
-    K2B_PHASE(5);
-    cluster_arrive();
-    cluster_wait();
-    K2B_PHASE(6);
-
-    // ---- (e) hypothesis merge, redundantly in every CTA --------------------------------------------------------
-    for (int s = warp; s < S; s += kCThreads / 32) {
-      const int g = cluster * S + s;
-      int32_t* bp_row = (rank == 0 && g < a.B) ? a.bp + ((size_t)g * a.Ttot + a.t0 + t) * K : nullptr;
-      select_stream<K, kNH>(s, V, CS, xw, st[cur], st[cur ^ 1], a.blank, a.unk, a.extra_mask, bp_row, lane, cand_tab, sel_scr[warp]);
-    }
-    K2B_PHASE(9);       // sub-phase: this warp's own merge, before waiting for the others
-    __syncthreads();
-    cur ^= 1;
-    K2B_PHASE(7);
-  }
-  if (timed) for (int i = 0; i < 12; ++i) a.timing[i] = tph[i];
-#undef K2B_PHASE
-
-  if (rank == 0 && tid < S * K) {
-    const int s = tid / K, hslot = tid % K, g = cluster * S + s;
-    if (g < a.B) {
-      a.fin_lp[(size_t)g * K + hslot] = st[cur].lp[tid];
-      a.fin_len[(size_t)g * K + hslot] = st[cur].len[tid];
-      if (a.io_ctx != nullptr) {
-        a.io_ctx[2 * ((size_t)g * K + hslot)] = st[cur].ctx0[tid];
-        a.io_ctx[2 * ((size_t)g * K + hslot) + 1] = st[cur].ctx1[tid];
-        a.io_hash[(size_t)g * K + hslot] = st[cur].hash[tid];
-      }
-      if (hslot == 0) a.fin_nlive[g] = st[cur].nlive[s];
-      if (hslot == 0 && a.hyp_out != nullptr) {          // ref OnlineRecognizer.cs:208: last ctx tokens back into stream.Hyp
-        a.hyp_out[2 * g] = st[cur].ctx0[tid];
-        a.hyp_out[2 * g + 1] = st[cur].ctx1[tid];
-      }
-    }
-  }
-  if (!ok) atomicExch(a.status, 1);
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tbase, 512);
-  cluster_sync();
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Two-group variant: the 32 hypothesis rows of a cluster are split into two independent groups of 16 (8 warps each) that
-// run the same frame loop out of phase. Every phase of one group that is pure latency (MMA issue/dispatch, DSMEM exchange,
-// the one-warp-per-stream merge) overlaps the instruction-bound phases (prologue, reductions) of the other. Groups never
-// synchronise with each other: named barriers inside the CTA, and - instead of barrier.cluster, which is CTA-wide - one
-// mbarrier per group whose CS arrivals come from the CTAs of the cluster (mbarrier.arrive.release.cluster on the mapped
-// address) once their partials for this frame are in place.
-constexpr int kG = 2, kGH = 16, kGW = 8;
-constexpr int kXTileG = 32 * 128;        // k-block of one group's stacked operand: 16 hi rows + 16 lo rows
-constexpr int kLtStrideG = 17;
-
-template <int K>
-__global__ void __launch_bounds__(kCThreads, 1) cluster_beam2_kernel(const ClusterArgs a) {
-  constexpr int XWP = xw_padded(K);
-  constexpr int SG = kGH / K;            // streams per group
-  extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ HypState st[kG][2];
-  __shared__ float bias_s[128];
-  __shared__ int cand_tab[kMaxBeam * 8 * kMaxBeam];
-  __shared__ float sel_scr[kCThreads / 32][2 * kMaxBeam];
-  __shared__ uint64_t bar_w, bar_mma[kG], xfull[kG];
-  __shared__ uint32_t tmem_slot;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
-  const int grp = warp_u / kGW, wg = warp_u % kGW;
-  const uint32_t x3u = (uint32_t)a.x3;
-  const uint32_t rank = cluster_ctarank();
-  const int cluster = blockIdx.x / a.CS;
-  const int J = a.J, V = a.V, CS = a.CS, T = a.T;
-  const int nkb = J / 64;
-  uint8_t* w_hi = smem;
-  uint8_t* xop = w_hi + (size_t)nkb * 16384 + (size_t)grp * xop_region_bytes(nkb, kXTileG, kLtStrideG);   // this group's operand
-  float* Lt = reinterpret_cast<float*>(xop);
-  float* xch = reinterpret_cast<float*>(w_hi + (size_t)nkb * 16384 + (size_t)kG * xop_region_bytes(nkb, kXTileG, kLtStrideG)) +
-               (size_t)grp * 2 * CS * kGH * XWP;                                  // [2][CS][kGH][XWP] of this group
-
-  if (tid == 0) {
-    mbar_init(&bar_w, 1);
-    for (int g = 0; g < kG; ++g) { mbar_init(&bar_mma[g], 1); mbar_init(&xfull[g], (uint32_t)CS); }
-    mbar_fence_init();
-  }
-  if (warp == 0) tmem_alloc(&tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tbase = tmem_slot;
-  const uint32_t t_d = tbase + (uint32_t)(32 * grp), t_wlo = tbase + 64;
-  const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
-
-  if (tid == 0) {
-    mbar_expect_tx(&bar_w, (uint32_t)(nkb * 16384));
-    for (int kb = 0; kb < nkb; ++kb)
-      tma_bulk_g2s(w_hi + (size_t)kb * 16384, a.wo_hi_img + ((size_t)rank * nkb + kb) * 16384, 16384, &bar_w);
-  }
-  if (a.x3 && warp < 4) {
-    const uint32_t* src = a.wo_lo + ((size_t)rank * 128 + tid) * (J / 2);
-    for (int c0 = 0; c0 < J / 2; c0 += 32) {
-      uint32_t v[32];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + c0) + q);
-        v[4 * q] = u.x; v[4 * q + 1] = u.y; v[4 * q + 2] = u.z; v[4 * q + 3] = u.w;
-      }
-      tmem_st32(t_wlo + lane_base + (uint32_t)c0, v);
-    }
-    tmem_st_wait();
-  }
-  if (tid < 128) bias_s[tid] = a.bias[rank * 128 + tid];
-  for (int c = tid; c < K * CS * K; c += kCThreads) {
-    const int h = c / (CS * K), r = c - h * (CS * K);
-    cand_tab[c] = (h << 16) | ((r / K) << 8) | (r % K);
-  }
-  if (tid < kG * kGH) {
-    const int g = tid / kGH, n = tid % kGH, h = n % K;
-    for (int b = 0; b < 2; ++b) {
-      st[g][b].ctx0[n] = -1; st[g][b].ctx1[n] = a.blank;
-      st[g][b].lp[n] = (h == 0) ? 0.f : -INFINITY;
-      st[g][b].len[n] = 2; st[g][b].hash[n] = kHashSeedC;
-      st[g][b].nlive[n] = 0;
-    }
-    if (n < SG) st[g][0].nlive[n] = (cluster * (kG * SG) + g * SG + n < a.B) ? 1 : 0;
-  }
-  bool ok = true;
-  if (tid == 0) ok = mbar_wait(&bar_w, 0);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  cluster_sync();
-
-  const uint32_t idesc32 = umma_idesc_bf16_f32(128, 32), idesc16 = umma_idesc_bf16_f32(128, 16);
-  const uint32_t desc_hi = 64u | (1u << 14) | (2u << 29);
-  const uint32_t w_lo0 = ((smem_u32(w_hi) & 0x3FFFFu) >> 4) | (1u << 16);
-  const uint32_t x_lo0 = ((smem_u32(xop) & 0x3FFFFu) >> 4) | (1u << 16);
-  const uint32_t gbar = 1u + (uint32_t)grp;
-  const int nq = J / 4;
-  int cur = 0;
-
-  const int n0 = wg * 2;                         // the two rows of this warp inside its group (one stream: K is even)
-  const int s_base = cluster * (kG * SG) + grp * SG;
-  int g_w = s_base + n0 / K;
-  if (g_w >= a.B) g_w = a.B - 1;
-  const float4* enc_row = reinterpret_cast<const float4*>(a.encE + ((size_t)g_w * a.Ttot + a.t0) * J);
-  float4 ecur[4];
-  uint32_t xoff[2][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int q = lane + 32 * i;
-    if (q < nq) ecur[i] = __ldg(enc_row + q);
-    const int k = 4 * q;
-    xoff[0][i] = (uint32_t)(k >> 6) * kXTileG + sw128_offset(n0, k & 63);
-    xoff[1][i] = (uint32_t)(k >> 6) * kXTileG + sw128_offset(n0 + 1, k & 63);
-  }
-
-  for (int t = 0; t < T; ++t) {
-    // ---- (a) prologue ----------------------------------------------------------------------------------------------
-    {
-      const HypState& sc = st[grp][cur];
-      const float4* pd0 = reinterpret_cast<const float4*>(a.dec_tab + ((size_t)(sc.ctx0[n0] + 1) * V + sc.ctx1[n0]) * J);
-      const float4* pd1 = reinterpret_cast<const float4*>(a.dec_tab + ((size_t)(sc.ctx0[n0 + 1] + 1) * V + sc.ctx1[n0 + 1]) * J);
-      float4 d0[4], d1[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int q = lane + 32 * i;
-        if (q < nq) { d0[i] = __ldg(pd0 + q); d1[i] = __ldg(pd1 + q); }
-      }
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int q = lane + 32 * i;
           if (q < nq) {
-            const float4 d = r ? d1[i] : d0[i];
-            const float x0 = tanh_from_exp(ecur[i].x, d.x), x1 = tanh_from_exp(ecur[i].y, d.y);
-            const float x2 = tanh_from_exp(ecur[i].z, d.z), x3 = tanh_from_exp(ecur[i].w, d.w);
-            uint8_t* dst = xop + xoff[r][i];
-            if (a.x3) {
-              const uint32_t b0 = __float_as_uint(x0), b1 = __float_as_uint(x1), b2 = __float_as_uint(x2), b3 = __float_as_uint(x3);
-              *reinterpret_cast<uint2*>(dst) = make_uint2(__byte_perm(b0, b1, 0x7632), __byte_perm(b2, b3, 0x7632));
-              const float l0 = x0 - __uint_as_float(b0 & 0xffff0000u), l1 = x1 - __uint_as_float(b1 & 0xffff0000u);
-              const float l2 = x2 - __uint_as_float(b2 & 0xffff0000u), l3 = x3 - __uint_as_float(b3 & 0xffff0000u);
-              *reinterpret_cast<uint2*>(dst + 16 * 128) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
-            } else {
-              *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(x0, x1), pack_bf16x2(x2, x3));
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              const float4 d = r ? d1[i] : d0[i];
+              const float4 ev = (NE == 2 && r) ? ecur1[NE == 2 ? i : 0] : ecur[i];
+              const float x0 = tanh_from_exp(ev.x, d.x), x1 = tanh_from_exp(ev.y, d.y);
+              const float x2 = tanh_from_exp(ev.z, d.z), x3 = tanh_from_exp(ev.w, d.w);
+              uint8_t* dst = xop + xoff[r][i];
+              if (X3) {
+                // split by truncation: hi = upper 16 bits (one PRMT per pair), lo = x - hi exactly, rounded to bf16
+                const uint32_t b0 = __float_as_uint(x0), b1 = __float_as_uint(x1), b2 = __float_as_uint(x2), b3 = __float_as_uint(x3);
+                *reinterpret_cast<uint2*>(dst) = make_uint2(__byte_perm(b0, b1, 0x7632), __byte_perm(b2, b3, 0x7632));
+                const float l0 = x0 - __uint_as_float(b0 & 0xffff0000u), l1 = x1 - __uint_as_float(b1 & 0xffff0000u);
+                const float l2 = x2 - __uint_as_float(b2 & 0xffff0000u), l3 = x3 - __uint_as_float(b3 & 0xffff0000u);
+                *reinterpret_cast<uint2*>(dst + 32 * 128) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+              } else {
+                *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(x0, x1), pack_bf16x2(x2, x3));
+              }
+            }
+          }
+          fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's async proxy
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_q[i]);
+          K2B_PHASE(14 + i);
+        }
+        if (t + 1 < T) {
+          const float4* pe = enc_row + (size_t)(t + 1) * nq;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int q = lane + 32 * i;
+            if (q < nq) ecur[i] = __ldg(pe + q);
+            if (NE == 2 && q < nq) ecur1[NE == 2 ? i : 0] = __ldg(enc_row1 + (size_t)(t + 1) * nq + q);
+          }
+        }
+      }
+      K2B_PHASE(0);
+
+      // ---- (c) accumulator -> registers (+bias) -> transposed shared tile; every warp reads 8 columns of its lane quarter
+      if (lane == 0 && !mbar_wait(&bar_mma, (uint32_t)(t & 1))) ok = false;
+      __syncwarp();
+      tc_fence_after();
+      K2B_PHASE(1);
+      {
+        uint32_t va[8], vb[8];
+        tmem_ld8(t_d + lane_base + (uint32_t)col0, va);
+        if (X3) tmem_ld8(t_d + lane_base + (uint32_t)(32 + col0), vb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+          float v = __uint_as_float(va[n]) + bsv;
+          if (X3) v += __uint_as_float(vb[n]);
+          Lt[vrow * kLtStride + col0 + n] = v;
+        }
+        tc_fence_before();
+      }
+      named_bar_sync(1, kWorkers * 32);
+      K2B_PHASE(2);
+
+      // ---- (d) per hypothesis (two per warp, interleaved): sum-exp and top-K over this slice's 128 logits. Selection keys
+      //      are the order-preserving integer image of the logit with its low 7 bits replaced by the position in the slice:
+      //      unique, so one REDUX per round finds value and position at once (ties and values closer than 2^-16 relative
+      //      resolve to the larger vocabulary index; the exact fp32 logit is re-read for the record).
+      float* xw = xch + (size_t)(t & 1) * CS * kNH * XWP;
+      {
+        float v[2][4];
+        int pk[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int pos = lane + 32 * j;
+            v[r][j] = Lt[pos * kLtStride + n0 + r];
+            const int kb = __float_as_int(v[r][j]);
+            const int key = kb ^ ((kb >> 31) & 0x7fffffff);
+            pk[r][j] = pos < nvalid ? ((key & ~127) | pos) : kKeyNone;
+          }
+          // sort the four unique keys of this lane once, best first: every round then pops the head
+#define K2B_CE(x, y) do { const int hi_ = max(pk[r][x], pk[r][y]), lo_ = min(pk[r][x], pk[r][y]); pk[r][x] = hi_; pk[r][y] = lo_; } while (0)
+          K2B_CE(0, 1); K2B_CE(2, 3); K2B_CE(0, 2); K2B_CE(1, 3); K2B_CE(1, 2);
+#undef K2B_CE
+        }
+        int keep[2] = {kKeyNone, kKeyNone};
+        float m[2], sum[2];
+#pragma unroll
+        for (int rr = 0; rr < K; ++rr) {
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int wk = __reduce_max_sync(0xffffffffu, pk[r][0]);
+            const bool won = pk[r][0] == wk;
+            pk[r][0] = won ? pk[r][1] : pk[r][0];
+            pk[r][1] = won ? pk[r][2] : pk[r][1];
+            pk[r][2] = won ? pk[r][3] : pk[r][2];
+            pk[r][3] = won ? kKeyNone : pk[r][3];
+            keep[r] = (lane == rr) ? wk : keep[r];
+            if (rr == 0) {
+              // softmax offset = the (truncated, hence <=) slice maximum; fixed-point sum: order-independent, one REDUX
+              const int mk = wk & ~127;
+              m[r] = (wk == kKeyNone) ? -INFINITY : __int_as_float(mk ^ ((mk >> 31) & 0x7fffffff));
+              const float mneg = (wk == kKeyNone) ? 0.f : -m[r] * 1.4426950408889634f;
+              float ls = 0.f;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float ex = ex2_approx(fmaf(v[r][j], 1.4426950408889634f, mneg));
+                ls += (lane + 32 * j < nvalid) ? ex : 0.f;
+              }
+              const unsigned tot = __reduce_add_sync(0xffffffffu, __float2uint_rn(ls * 16777216.f));
+              sum[r] = (wk == kKeyNone) ? 0.f : (float)tot * (1.f / 16777216.f);
             }
           }
         }
-      }
-      if (t + 1 < T) {
-        const float4* pe = enc_row + (size_t)(t + 1) * nq;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int q = lane + 32 * i;
-          if (q < nq) ecur[i] = __ldg(pe + q);
-        }
-      }
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    named_bar_sync(gbar, kGW * 32);
-    tc_fence_after();
-
-    // ---- (b) MMAs of this group (its last warp issues) ----------------------------------------------------------------
-    if (wg == kGW - 1) {
-      const uint32_t el = elect_one();
-      uint32_t acc = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t dw = ((uint64_t)desc_hi << 32) | (uint64_t)(w_lo0 + (uint32_t)(kb * (16384 >> 4) + k * 2));
-          const uint64_t dx = ((uint64_t)desc_hi << 32) | (uint64_t)(x_lo0 + (uint32_t)(kb * (kXTileG >> 4) + k * 2));
-          umma_ss_e(t_d, dw, dx, x3u ? idesc32 : idesc16, acc, el);
-          acc = 1;
-          if (x3u) umma_ts_e(t_d, t_wlo + (uint32_t)((kb * 4 + k) * 8), dx, idesc16, 1, el);
-        }
-      }
-      umma_commit_e(&bar_mma[grp], el);
-    }
-
-    // ---- (c) read-out: the group's first four warps own the 128 TMEM lanes -------------------------------------------------
-    if (wg < 4) {
-      if (!mbar_wait(&bar_mma[grp], (uint32_t)(t & 1))) ok = false;
-      tc_fence_after();
-      const int row = wg * 32 + lane;
-      const float bsv = bias_s[row];
-      uint32_t va[16], vb[16];
-      tmem_ld16(t_d + lane_base, va);
-      if (a.x3) tmem_ld16(t_d + lane_base + 16u, vb);
-      tmem_ld_wait();
-#pragma unroll
-      for (int n = 0; n < kGH; ++n) {
-        float v = __uint_as_float(va[n]) + bsv;
-        if (a.x3) v += __uint_as_float(vb[n]);
-        Lt[row * kLtStrideG + n] = v;
-      }
-      tc_fence_before();
-    }
-    named_bar_sync(gbar, kGW * 32);
-
-    // ---- (d) reductions + exchange ----------------------------------------------------------------------------------------
-    float* xw = xch + (size_t)(t & 1) * CS * kGH * XWP;
-    {
-      float v[2][4];
-      int key[2][4];
-      float m[2], sum[2];
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int n = n0 + r;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          v[r][j] = Lt[(lane + 32 * j) * kLtStrideG + n];
-          const int idx = (int)rank * 128 + lane + 32 * j;
-          key[r][j] = idx < V ? fkey(v[r][j]) : kKeyNone;
-        }
-        m[r] = funkey(__reduce_max_sync(0xffffffffu, max(max(key[r][0], key[r][1]), max(key[r][2], key[r][3]))));
-      }
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        sum[r] = 0.f;
-        if (m[r] > -INFINITY) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) sum[r] += (key[r][j] != kKeyNone) ? __expf(v[r][j] - m[r]) : 0.f;
-        }
-      }
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) {
-        sum[0] += __shfl_xor_sync(0xffffffffu, sum[0], o);
-        sum[1] += __shfl_xor_sync(0xffffffffu, sum[1], o);
-      }
-      int sk[2][4], sj[2][4];
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { sk[r][j] = key[r][j]; sj[r][j] = j; }
-#define K2B_CE(x, y)                                                                                    \
-  do {                                                                                                  \
-    const bool sw = sk[r][y] > sk[r][x] || (sk[r][y] == sk[r][x] && sj[r][y] > sj[r][x]);               \
-    const int tk_ = sw ? sk[r][y] : sk[r][x], tj_ = sw ? sj[r][y] : sj[r][x];                           \
-    sk[r][y] = sw ? sk[r][x] : sk[r][y]; sj[r][y] = sw ? sj[r][x] : sj[r][y];                           \
-    sk[r][x] = tk_; sj[r][x] = tj_;                                                                     \
-  } while (0)
-        K2B_CE(0, 1); K2B_CE(2, 3); K2B_CE(0, 2); K2B_CE(1, 3); K2B_CE(1, 2);
-#undef K2B_CE
-      }
-      float out_v[2] = {-INFINITY, -INFINITY};
-      int out_i[2] = {-1, -1};
-#pragma unroll
-      for (int rr = 0; rr < K; ++rr) {
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-          const int wk = __reduce_max_sync(0xffffffffu, sk[r][0]);
-          const int ci = (sk[r][0] != kKeyNone && sk[r][0] == wk) ? (int)rank * 128 + lane + 32 * sj[r][0] : -1;
-          const int wi = __reduce_max_sync(0xffffffffu, ci);
-          if (ci == wi && wi >= 0) {
-            sk[r][0] = sk[r][1]; sj[r][0] = sj[r][1];
-            sk[r][1] = sk[r][2]; sj[r][1] = sj[r][2];
-            sk[r][2] = sk[r][3]; sj[r][2] = sj[r][3];
-            sk[r][3] = kKeyNone;
+          float* mine = xw + ((size_t)rank * kNH + n0 + r) * XWP;
+          if (lane == 0) *reinterpret_cast<float2*>(mine) = make_float2(m[r], sum[r]);
+          if (lane < K) {
+            const int pos = keep[r] & 127;
+            const bool has = keep[r] != kKeyNone;
+            mine[2 + lane] = has ? Lt[pos * kLtStride + n0 + r] : -INFINITY;
+            reinterpret_cast<int*>(mine)[2 + K + lane] = has ? (int)rank * 128 + pos : -1;
           }
-          if (lane == rr) { out_v[r] = funkey(wk); out_i[r] = wi; }
+        }
+        __syncwarp();
+        K2B_PHASE(3);
+        // both records (contiguous) go into the same slots of every other CTA of the cluster: 16-byte asynchronous
+        // stores that complete on the destination's mbarrier
+        constexpr int kChunks = 2 * XWP / 4;
+        const uint32_t base = smem_u32(xw + ((size_t)rank * kNH + n0) * XWP);
+        const uint32_t xb_addr = smem_u32(&xbar[t & 1]);
+        for (int it = lane; it < kChunks * (CS - 1); it += 32) {
+          const int dsel = it / kChunks, ch = it - dsel * kChunks;
+          uint32_t dst = rank + 1 + (uint32_t)dsel;
+          if (dst >= (uint32_t)CS) dst -= (uint32_t)CS;
+          const uint4 q = lds_v4(base + 16u * ch);
+          dsmem_st_async_v4(dsmem_map(base + 16u * ch, dst), q.x, q.y, q.z, q.w, dsmem_map(xb_addr, dst));
+        }
+        if (lane == 0) {
+          if (warp == 0) mbar_expect_tx(&xbar[t & 1], (uint32_t)((CS - 1) * kNH * XWP * 4));
+          else mbar_arrive(&xbar[t & 1]);
         }
       }
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        float* mine = xw + ((size_t)rank * kGH + n0 + r) * XWP;
-        if (lane == 0) { mine[0] = m[r]; mine[1] = sum[r]; }
-        if (lane < K) { mine[2 + lane] = out_v[r]; reinterpret_cast<int*>(mine)[2 + K + lane] = out_i[r]; }
-      }
-      __syncwarp();
-      constexpr int kChunks = 2 * XWP / 4;
-      const uint32_t base = smem_u32(xw + ((size_t)rank * kGH + n0) * XWP);
-      for (int it = lane; it < kChunks * (CS - 1); it += 32) {
-        const int dsel = it / kChunks, ch = it - dsel * kChunks;
-        uint32_t dst = rank + 1 + (uint32_t)dsel;
-        if (dst >= (uint32_t)CS) dst -= (uint32_t)CS;
-        const uint4 q = lds_v4(base + 16u * ch);
-        dsmem_st_v4(dsmem_map(base + 16u * ch, dst), q.x, q.y, q.z, q.w);
-      }
-    }
-    // all of this group's partials are issued -> tell every CTA of the cluster (itself included), then wait for all CS
-    named_bar_sync(gbar, kGW * 32);
-    if (wg == 0 && lane == 0) {
-      fence_acq_rel_cluster();
-      const uint32_t bar_addr = smem_u32(&xfull[grp]);
-      for (uint32_t dst = 0; dst < (uint32_t)CS; ++dst) mbar_arrive_remote(dsmem_map(bar_addr, dst));
-    }
-    if (wg < SG) {
-      if (!mbar_wait_cluster(&xfull[grp], (uint32_t)(t & 1))) ok = false;
-      // ---- (e) hypothesis merge of this group's streams ---------------------------------------------------------------
-      const int s = wg, g = s_base + s;
-      int32_t* bp_row = (rank == 0 && g < a.B) ? a.bp + ((size_t)g * a.Ttot + a.t0 + t) * K : nullptr;
-      select_stream<K, kGH>(s, V, CS, xw, st[grp][cur], st[grp][cur ^ 1], a.blank, a.unk, a.extra_mask, bp_row, lane, cand_tab, sel_scr[warp]);
-    }
-    named_bar_sync(gbar, kGW * 32);
-    cur ^= 1;
-  }
+      K2B_PHASE(4);
 
-  if (rank == 0 && wg * 32 + lane < SG * K) {
-    const int i = wg * 32 + lane;
-    const int s = i / K, hslot = i % K, g = s_base + s;
-    if (g < a.B) {
-      a.fin_lp[(size_t)g * K + hslot] = st[grp][cur].lp[i];
-      a.fin_len[(size_t)g * K + hslot] = st[grp][cur].len[i];
-      if (hslot == 0) a.fin_nlive[g] = st[grp][cur].nlive[s];
+      // ---- (e) hypothesis merge, redundantly in every CTA (deterministic, so no second exchange) ---------------------
+      if (warp < S) {
+        if (!mbar_wait(&xbar[t & 1], (uint32_t)((t >> 1) & 1))) ok = false;
+        K2B_PHASE(5);
+        for (int s = warp; s < S; s += kWorkers) {
+          const int g = cluster * S + s;
+          int32_t* bp_row = (rank == 0 && g < a.B) ? a.bp + ((size_t)g * a.Ttot + a.t0 + t) * K : nullptr;
+          select_stream<K>(s, V, CS, cs_shift, xw, st[cur], st[cur ^ 1], a.blank, a.unk, a.extra_mask, bp_row, lane, a.dec_tab, J,
+                           (a.dbg & 2) == 0 && (int)rank == (s % CS), timed ? tph : nullptr);
+        }
+      }
+      K2B_PHASE(6);
+      named_bar_sync(1, kWorkers * 32);
+      cur ^= 1;
+      K2B_PHASE(7);
+    }
+    if (timed) for (int i = 0; i < 20; ++i) a.timing[i] = tph[i];
+
+    if (rank == 0 && tid < S * K) {
+      const int s = tid / K, hslot = tid % K, g = cluster * S + s;
+      if (g < a.B) {
+        a.fin_lp[(size_t)g * K + hslot] = st[cur].lp[tid];
+        a.fin_len[(size_t)g * K + hslot] = st[cur].len[tid];
+        if (a.io_ctx != nullptr) {
+          a.io_ctx[2 * ((size_t)g * K + hslot)] = st[cur].ctx0[tid];
+          a.io_ctx[2 * ((size_t)g * K + hslot) + 1] = st[cur].ctx1[tid];
+          a.io_hash[(size_t)g * K + hslot] = st[cur].hash[tid];
+        }
+        if (hslot == 0) a.fin_nlive[g] = st[cur].nlive[s];
+        if (hslot == 0 && a.hyp_out != nullptr) {          // ref OnlineRecognizer.cs:208: last ctx tokens back into stream.Hyp
+          a.hyp_out[2 * g] = st[cur].ctx0[tid];
+          a.hyp_out[2 * g + 1] = st[cur].ctx1[tid];
+        }
+      }
     }
   }
+#undef K2B_PHASE
   if (!ok) atomicExch(a.status, 1);
   tc_fence_before();
   __syncthreads();
@@ -981,15 +650,14 @@ __global__ void exp2x_kernel(const float* __restrict__ in, float* __restrict__ o
 
 }  // namespace
 
-static void (*cluster_kernel_for(int K, bool two_groups))(const ClusterArgs) {
-  if (two_groups && K != 1) return K == 2 ? cluster_beam2_kernel<2> : (K == 4 ? cluster_beam2_kernel<4> : cluster_beam2_kernel<8>);
-  return K == 1 ? cluster_beam_kernel<1> : (K == 2 ? cluster_beam_kernel<2> : (K == 4 ? cluster_beam_kernel<4> : cluster_beam_kernel<8>));
+static void (*cluster_kernel_for(int K, bool x3))(const ClusterArgs) {
+  if (x3) return K == 1 ? cluster_beam_kernel<1, true> : (K == 2 ? cluster_beam_kernel<2, true> : (K == 4 ? cluster_beam_kernel<4, true> : cluster_beam_kernel<8, true>));
+  return K == 1 ? cluster_beam_kernel<1, false> : (K == 2 ? cluster_beam_kernel<2, false> : (K == 4 ? cluster_beam_kernel<4, false> : cluster_beam_kernel<8, false>));
 }
 
 static size_t cluster_dyn_smem(int J, int CS, int K) {
   const int nkb = J / 64;
-  const size_t one = xop_region_bytes(nkb, 64 * 128, 33), two = 2 * xop_region_bytes(nkb, 32 * 128, 17);
-  return (size_t)nkb * 16384 + (one > two ? one : two) + 2ull * CS * kNH * xw_padded(K) * 4;
+  return (size_t)nkb * 16384 + xop_region_bytes(nkb, 64 * 128, kLtStride) + 2ull * CS * kNH * xw_padded(K) * 4;
 }
 
 // V <= 1024: portable clusters of up to 8 CTAs, beams 1/2/4/8. 1024 < V <= 2048: 16-CTA (non-portable) clusters, greedy
@@ -1008,7 +676,7 @@ bool cluster_path_supported(const k2b_handle* h, int K) {
     k2b_handle* hm = const_cast<k2b_handle*>(h);
     if (hm->cluster16_ok < 0) {
       hm->cluster16_ok = 0;
-      auto kern = cluster_kernel_for(1, false);
+      auto kern = cluster_kernel_for(1, c.precision == K2B_PREC_BF16X3);
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
           cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) == cudaSuccess) {
         cudaLaunchConfig_t cfg = {};
@@ -1083,17 +751,15 @@ int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, 
   a.extra_mask = extra_mask; a.hyp_in = hyp_in; a.hyp_out = hyp_out;
   a.t0 = t0; a.Ttot = Ttot > 0 ? Ttot : T; a.resume = resume; a.io_ctx = io_ctx; a.io_hash = io_hash;
   a.timing = h->cluster_timing;
+  { const char* de = getenv("K2B_DBG"); a.dbg = de ? atoi(de) : 0; }
   a.bp = bp; a.fin_lp = fin_lp; a.fin_len = fin_len; a.fin_nlive = fin_nlive; a.status = status;
   const size_t dyn = cluster_dyn_smem(J, CS, K);
-  // K2B_CLUSTER_GROUPS=2 selects the two-group variant (measured ~7 % slower on cfg2: the phases are latency-bound per warp)
-  const char* ge = getenv("K2B_CLUSTER_GROUPS");
-  const bool two_groups = ge != nullptr && ge[0] == '2' && K != 1 && io_ctx == nullptr;
-  void (*kern)(const ClusterArgs) = cluster_kernel_for(K, two_groups);
+  void (*kern)(const ClusterArgs) = cluster_kernel_for(K, a.x3 != 0);
   if (CS > 8) K2B_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   K2B_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(nclusters * CS));
-  cfg.blockDim = dim3(two_groups ? kCThreads : kCAll);
+  cfg.blockDim = dim3(kCAll);
   cfg.dynamicSmemBytes = dyn;
   cfg.stream = h->stream;
   cudaLaunchAttribute at[1];

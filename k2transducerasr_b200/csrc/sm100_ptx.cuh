@@ -31,6 +31,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded spin: a mis-programmed pipeline must not hang the GPU box (returns false on timeout).
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32_t max_spins = 20000000u) {
+#pragma unroll 1
   for (uint32_t i = 0; i < max_spins; ++i)
     if (mbar_try_wait(bar, parity)) return true;
   return false;
@@ -40,6 +41,12 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32
 __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// asynchronous L2 prefetch of `bytes` (multiple of 16) starting at a 16-byte aligned global address: one instruction, run by the
+// TMA unit (SASS UBLKPF)
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
 }
 
 // generic-proxy writes to shared memory -> visible to the async proxy (UMMA operand reads)
@@ -74,6 +81,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
@@ -180,6 +192,12 @@ __device__ __forceinline__ void dsmem_st_v4(uint32_t addr, uint32_t a, uint32_t 
   asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// asynchronous 16-byte store into another CTA's shared memory; its bytes complete on that CTA's mbarrier (both operands are
+// shared::cluster addresses from mapa): data and signal travel together, no fence / barrier.cluster needed. SASS: STAS.128
+__device__ __forceinline__ void dsmem_st_async_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];"
+               ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(mbar) : "memory");
+}
 // remote (any CTA of the cluster) mbarrier arrive with cluster-scope release; `addr` is a shared::cluster address (mapa)
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
@@ -192,6 +210,7 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
   return ok != 0;
 }
 __device__ __forceinline__ bool mbar_wait_cluster(uint64_t* bar, uint32_t parity, uint32_t max_spins = 20000000u) {
+#pragma unroll 1
   for (uint32_t i = 0; i < max_spins; ++i)
     if (mbar_try_wait_cluster(bar, parity)) return true;
   return false;
