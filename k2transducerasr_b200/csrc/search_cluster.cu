@@ -87,7 +87,7 @@ __device__ __forceinline__ uint64_t hash_push_c(uint64_t h, int tok) {
 __device__ __forceinline__ float logaddexp_c(float a, float b) {
   const float mx = fmaxf(a, b), mn = fminf(a, b);
   if (mx == -INFINITY) return -INFINITY;
-  return mx + log1pf(expf(mn - mx));
+  return mx + __logf(1.f + __expf(mn - mx));       // |error| < 1e-7 absolute: the argument of log is in [1, 2]
 }
 
 // tanh(e + d) from Ee = exp(2e), Ed = exp(2d). e and d are clamped to +-21 when the tables are built, so the
@@ -109,20 +109,36 @@ __device__ __forceinline__ float funkey(int k) { return __int_as_float(k >= 0 ? 
 constexpr int kKeyNone = (int)0x80000000;
 
 // One warp: hypothesis merge of local stream s (beam_select_kernel in search.cu is the global-memory twin).
-// Lane (h, c) = (hypothesis, vocabulary slice) owns the record of that pair - its slice max / sum-exp and its K best
-// (value, index) candidates - so log-softmax constants are a segmented butterfly over the slice lanes and every candidate is
-// scored in the lane that loaded it. Then K rounds of two REDUX pick the stream's top K over K*V (value, then flat index).
+// Lane c*K + h owns the record of (vocabulary slice c, hypothesis h) - its slice max / sum-exp and its K best (value, index)
+// candidates - so the log-softmax constants are two unconditional butterflies over the slice bits of the lane id (lanes
+// without a record contribute the neutral element) and every candidate is scored in the lane that loaded it. K rounds of
+// two REDUX then pick the stream's top K over K*V (value, then flat index). The K winners meet in a small per-warp scratch
+// (broadcast loads instead of shuffles) for the dedupe by token sequence (hash, length, context) and the log-add.
 template <int K>
-__device__ __forceinline__ void select_stream(int s, int V, int CS, int cs_shift, const float* __restrict__ xb, const HypState& in,
+__device__ __forceinline__ void select_stream(int s, int V, int CS, const float* __restrict__ xb, const HypState& in,
                                               HypState& out, int blank, int unk, int extra_mask, int32_t* __restrict__ bp_row,
-                                              int lane, const float* __restrict__ dec_tab, int J, bool do_prefetch, long long* tp) {
-#define K2B_SUB(i) do { if (tp != nullptr) { const long long now = clock64(); tp[i] += now - tp[19]; tp[19] = now; } } while (0)
-  if (tp != nullptr) tp[19] = clock64();
+                                              int lane, const float* __restrict__ dec_tab, int J, bool do_prefetch,
+                                              uint32_t* __restrict__ scr) {
   constexpr int XWP = xw_padded(K);
-  constexpr int NP = (K == 8) ? 2 : 1;            // K * CS2 <= 32 * NP on every supported shape
+  constexpr int CPP = 32 / K;                     // slices per pass
+  constexpr int NP = (K == 8) ? 2 : 1;            // K * CS <= 32 * NP on every supported shape
   const unsigned full = 0xffffffffu;
   const int nl = in.nlive[s];
-  if (nl == 0) {
+  const int h = lane % K;
+  float w[NP][XWP];
+  float pm[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    const int c = p * CPP + lane / K;
+    const float4* rec = reinterpret_cast<const float4*>(xb + ((size_t)min(c, CS - 1) * kNH + s * K + h) * XWP);
+#pragma unroll
+    for (int i = 0; i < XWP / 4; ++i) {
+      const float4 q = rec[i];
+      w[p][4 * i] = q.x; w[p][4 * i + 1] = q.y; w[p][4 * i + 2] = q.z; w[p][4 * i + 3] = q.w;
+    }
+  }
+  const float lp_h = in.lp[s * K + h];
+  if (nl == 0) {                                   // warp-uniform
     if (lane < K) {
       const int o = s * K + lane;
       out.ctx0[o] = -1; out.ctx1[o] = blank; out.lp[o] = -INFINITY; out.len[o] = 2; out.hash[o] = kHashSeedC;
@@ -130,45 +146,33 @@ __device__ __forceinline__ void select_stream(int s, int V, int CS, int cs_shift
     if (lane == 0) out.nlive[s] = 0;
     return;
   }
-  const int cs2 = 1 << cs_shift;
+  float M = -INFINITY;
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    const bool valid = h < nl && p * CPP + lane / K < CS;
+    pm[p] = valid ? w[p][0] : -INFINITY;
+    M = fmaxf(M, pm[p]);
+  }
+#pragma unroll
+  for (int o = K; o < 32; o <<= 1) M = fmaxf(M, __shfl_xor_sync(full, M, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int p = 0; p < NP; ++p) sum += (pm[p] > -INFINITY) ? w[p][1] * __expf(pm[p] - M) : 0.f;
+#pragma unroll
+  for (int o = K; o < 32; o <<= 1) sum += __shfl_xor_sync(full, sum, o);
+  const float L = __logf(sum);
   int ck[NP * K], cf[NP * K];
 #pragma unroll
   for (int p = 0; p < NP; ++p) {
-    const int pi = p * 32 + lane;
-    const int h = pi >> cs_shift, c = pi & (cs2 - 1);
-    const bool valid = h < nl && c < CS;
-    float w[XWP];
-#pragma unroll
-    for (int i = 0; i < XWP; ++i) w[i] = 0.f;
-    if (valid) {
-      const float4* rec = reinterpret_cast<const float4*>(xb + ((size_t)c * kNH + s * K + h) * XWP);
-#pragma unroll
-      for (int i = 0; i < XWP / 4; ++i) {
-        const float4 q = rec[i];
-        w[4 * i] = q.x; w[4 * i + 1] = q.y; w[4 * i + 2] = q.z; w[4 * i + 3] = q.w;
-      }
-    }
-    const float pm = valid ? w[0] : -INFINITY;
-    float M = pm;
-#pragma unroll
-    for (int o = 1; o < 16; o <<= 1)
-      if (o < cs2) M = fmaxf(M, __shfl_xor_sync(full, M, o));
-    float sum = (pm > -INFINITY) ? w[1] * __expf(pm - M) : 0.f;
-#pragma unroll
-    for (int o = 1; o < 16; o <<= 1)
-      if (o < cs2) sum += __shfl_xor_sync(full, sum, o);
-    const float L = __logf(sum);
-    const float lp = valid ? in.lp[s * K + h] : 0.f;
 #pragma unroll
     for (int j = 0; j < K; ++j) {
-      const int idx = __float_as_int(w[2 + K + j]);
-      const float v = ((w[2 + j] - M) - L) + lp;                       // order of log_softmax(x) + lp
-      const bool okc = valid && idx >= 0 && v == v;
+      const int idx = __float_as_int(w[p][2 + K + j]);
+      const float v = ((w[p][2 + j] - M) - L) + lp_h;                       // order of log_softmax(x) + lp
+      const bool okc = (pm[p] > -INFINITY) & (idx >= 0) & (v == v);
       ck[p * K + j] = okc ? fkey(v) : kKeyNone;
       cf[p * K + j] = okc ? h * V + idx : -1;
     }
   }
-  K2B_SUB(8);
   float my_v = -INFINITY;
   int my_f = -1;
 #pragma unroll
@@ -190,7 +194,7 @@ __device__ __forceinline__ void select_stream(int s, int V, int CS, int cs_shift
     my_f = (lane == r) ? wf : my_f;
   }
 
-  K2B_SUB(9);
+  // ---- lanes 0..K-1 hold the winners, best first -------------------------------------------------------------
   const bool cand = lane < K && my_f >= 0;
   int par = 0, tok = -1, c0 = -1, c1 = blank, ln = 2;
   uint64_t hs = kHashSeedC;
@@ -200,43 +204,40 @@ __device__ __forceinline__ void select_stream(int s, int V, int CS, int cs_shift
     const int y = my_f - par * V;
     const int prow = s * K + par;
     hs = in.hash[prow]; ln = in.len[prow]; c0 = in.ctx0[prow]; c1 = in.ctx1[prow];
-    if (y != blank && y != unk && y != extra_mask) { tok = y; hs = hash_push_c(hs, y); ln += 1; c0 = c1; c1 = y; }
-  }
-  if (do_prefetch && cand && tok >= 0)   // pull the new context's decoder row towards L2 while the merge finishes (one TMA-unit op)
-    l2_prefetch_bulk(dec_tab + ((size_t)(c0 + 1) * V + c1) * J, (uint32_t)(J * 4));
-  K2B_SUB(10);
-  // all K*K winner pairs (i, q) compared at once, one pair per lane: bit q of `eqm` of lane i = "winner q < i is the same
-  // token sequence" (hash, length and context all equal); the root of i is its lowest such q
-  unsigned eqm = 0;
-  {
-    const int lnc = cand ? ln : -1 - lane;            // non-candidates never compare equal
-#pragma unroll
-    for (int pass = 0; pass < (K * K + 31) / 32; ++pass) {
-      const int l2 = pass * 32 + lane, i = l2 / K, q = l2 % K;
-      const uint64_t ah = __shfl_sync(full, hs, i), bh = __shfl_sync(full, hs, q);
-      const int al = __shfl_sync(full, lnc, i), bl = __shfl_sync(full, lnc, q);
-      const int a0 = __shfl_sync(full, c0, i), b0 = __shfl_sync(full, c0, q);
-      const int a1 = __shfl_sync(full, c1, i), b1 = __shfl_sync(full, c1, q);
-      const bool eq = (i < K) & (q < i) & (ah == bh) & (al == bl) & (a0 == b0) & (a1 == b1);
-      const unsigned bal = __ballot_sync(full, eq);
-      const int sh = lane * K - pass * 32;
-      if (lane < K && sh >= 0 && sh < 32) eqm |= (bal >> sh) & ((1u << K) - 1u);
+    if (y != blank && y != unk && y != extra_mask) {
+      tok = y; hs = hash_push_c(hs, y); ln += 1; c0 = c1; c1 = y;
+      if (do_prefetch)    // pull the new context's decoder row towards L2 while the merge finishes (one TMA-unit op)
+        l2_prefetch_bulk(dec_tab + ((size_t)(c0 + 1) * V + c1) * J, (uint32_t)(J * 4));
     }
   }
-  const int root = (cand && eqm != 0) ? (__ffs(eqm) - 1) : lane;
-  K2B_SUB(11);
+  // scratch row q: {hash lo, hash hi, length (negative = no candidate), ctx0 | ctx1, score, root, -, -}
+  uint4* scr4 = reinterpret_cast<uint4*>(scr);
+  if (lane < K) {
+    scr4[2 * lane] = make_uint4((uint32_t)hs, (uint32_t)(hs >> 32), (uint32_t)(cand ? ln : -1 - lane), (uint32_t)c0);
+    scr4[2 * lane + 1] = make_uint4((uint32_t)c1, __float_as_uint(my_v), 0u, 0u);
+  }
+  __syncwarp();
+  int root = lane;
+#pragma unroll
+  for (int q = K - 1; q >= 0; --q) {            // descending: the lowest equal q wins
+    const uint4 u = scr4[2 * q];
+    const uint32_t uc1 = scr[8 * q + 4];
+    const bool eq = (q < lane) & cand & (u.x == (uint32_t)hs) & (u.y == (uint32_t)(hs >> 32)) & (u.z == (uint32_t)ln) &
+                    (u.w == (uint32_t)c0) & (uc1 == (uint32_t)c1);
+    root = eq ? q : root;
+  }
   float lp = my_v;
   const unsigned merged = __ballot_sync(full, cand && root != lane);
   if (merged) {                      // log-add merged scores into their root, in insertion (rank) order
+    if (lane < K) scr[8 * lane + 6] = (uint32_t)root;
+    __syncwarp();
 #pragma unroll
-    for (int q = 0; q < K; ++q) {
-      const int qroot = __shfl_sync(full, root, q);
-      const float qv = __shfl_sync(full, my_v, q);
-      const int qc = __shfl_sync(full, (int)cand, q);
-      if (cand && qc && q != lane && qroot == lane) lp = logaddexp_c(lp, qv);
+    for (int q = 1; q < K; ++q) {
+      const int qroot = (int)scr[8 * q + 6];
+      const float qv = __uint_as_float(scr[8 * q + 5]);
+      if (cand && ((merged >> q) & 1u) && qroot == lane) lp = logaddexp_c(lp, qv);
     }
   }
-  K2B_SUB(12);
   const bool is_root = cand && root == lane;
   const unsigned roots = __ballot_sync(full, is_root);
   const int nnew = __popc(roots);
@@ -252,8 +253,7 @@ __device__ __forceinline__ void select_stream(int s, int V, int CS, int cs_shift
     if (bp_row != nullptr) bp_row[lane] = 0;
   }
   if (lane == 0) out.nlive[s] = nnew;
-  K2B_SUB(13);
-#undef K2B_SUB
+  __syncwarp();                       // the scratch is reused by this warp's next stream
 }
 
 // Warp roles: warps 0..15 build the joiner operand (two hypothesis rows each), read the accumulator out, reduce and merge;
@@ -270,6 +270,7 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
   __shared__ uint64_t bar_w, bar_mma, bar_q[4];   // bar_q[i]: K-quarter i of the joiner operand is in shared memory
   __shared__ uint64_t xbar[2];                    // partials of frame t (buffer t & 1): 16 local warps + remote st.async bytes
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) uint32_t sel_scr[kWorkers][8 * K];   // per-warp winner exchange of the merge
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);     // the compiler knows this one is warp-uniform
@@ -278,8 +279,6 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
   const int cluster = blockIdx.x / a.CS;
   const int J = a.J, V = a.V, CS = a.CS, T = a.T;
   const int nkb = J / 64;
-  int cs_shift = 0;
-  while ((1 << cs_shift) < CS) ++cs_shift;
   uint8_t* w_hi = smem;
   uint8_t* xop = w_hi + (size_t)nkb * 16384;                          // nkb tiles of 64 rows x 128 B
   float* Lt = reinterpret_cast<float*>(xop);                          // aliases the operand between MMA and next build
@@ -422,6 +421,10 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
       //      K-quarter by K-quarter (each warp arrives on bar_q[i] after its part of quarter i)
       {
         const HypState& sc = st[cur];
+        if ((a.dbg & 4) && warp >= 8) {            // experiment: half of the operand rows only (garbage results, timing only)
+          for (int i = 0; i < 4; ++i) { if (lane == 0) mbar_arrive(&bar_q[i]); }
+          goto build_done;
+        }
         const float4* pd0 = reinterpret_cast<const float4*>(a.dec_tab + (((size_t)(sc.ctx0[n0] + 1) * V + sc.ctx1[n0]) & rm) * J);
         const float4* pd1 = reinterpret_cast<const float4*>(a.dec_tab + (((size_t)(sc.ctx0[n0 + 1] + 1) * V + sc.ctx1[n0 + 1]) & rm) * J);
         float4 d0[4], d1[4];
@@ -468,6 +471,7 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
           }
         }
       }
+    build_done:
       K2B_PHASE(0);
 
       // ---- (c) accumulator -> registers (+bias) -> transposed shared tile; every warp reads 8 columns of its lane quarter
@@ -582,8 +586,8 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
         for (int s = warp; s < S; s += kWorkers) {
           const int g = cluster * S + s;
           int32_t* bp_row = (rank == 0 && g < a.B) ? a.bp + ((size_t)g * a.Ttot + a.t0 + t) * K : nullptr;
-          select_stream<K>(s, V, CS, cs_shift, xw, st[cur], st[cur ^ 1], a.blank, a.unk, a.extra_mask, bp_row, lane, a.dec_tab, J,
-                           (a.dbg & 2) == 0 && (int)rank == (s % CS), timed ? tph : nullptr);
+          select_stream<K>(s, V, CS, xw, st[cur], st[cur ^ 1], a.blank, a.unk, a.extra_mask, bp_row, lane, a.dec_tab, J,
+                           (int)rank == (s % CS), sel_scr[warp]);
         }
       }
       K2B_PHASE(6);

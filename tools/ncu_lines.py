@@ -37,3 +37,6 @@ print(f"total warp-instructions executed {ti}, samples {ts}, mapped {len(addr2li
 print("--- by executed instructions")
 for (f, l), k in inst.most_common(40):
     print(f"{100 * k / ti:5.1f}% inst {100 * samp[(f, l)] / max(ts, 1):5.1f}% smp  {f}:{l:<4} {text(f, l)}")
+print("--- by stall samples")
+for (f, l), k in samp.most_common(45):
+    print(f"{100 * k / max(ts, 1):5.1f}% smp {100 * inst[(f, l)] / ti:5.1f}% inst  {f}:{l:<4} {text(f, l)}")

@@ -8,7 +8,7 @@ build.build()
 cfg = synth.CONFIGS["cfg2"]
 d = cfg.dims
 names = ["build x (gather+tanh+split) + enc prefetch", "wait MMA", "TMEM->smem transpose + barrier", "reduce (keys, rounds, sum)",
-         "st.async exchange + arrive", "wait partials (xbar)", "merge: warp 0 select_stream", "end-of-step barrier", "  sel: load+lse+score", "  sel: K rounds", "  sel: extension+prefetch", "  sel: dedupe", "  sel: log-add", "  sel: write-back", "  build: quarter 0 (incl. load wait)", "  build: quarter 1", "  build: quarter 2", "  build: quarter 3"]
+         "st.async exchange + arrive", "wait partials (xbar)", "merge: warp 0 select_stream", "end-of-step barrier", "-", "-", "-", "-", "-", "-", "  build: quarter 0 (incl. load wait)", "  build: quarter 1", "  build: quarter 2", "  build: quarter 3"]
 for prec in ("bf16x3", "bf16"):
     h = _native.Handle(vocab_size=d.vocab_size, joiner_dim=d.joiner_dim, decoder_dim=d.decoder_dim, encoder_dim=d.encoder_dim,
                        precision=_native.PREC_NAMES[prec])
