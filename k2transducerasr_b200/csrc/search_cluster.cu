@@ -210,6 +210,7 @@ __device__ __forceinline__ void select_stream(int s, int V, int CS, const float*
         l2_prefetch_bulk(dec_tab + ((size_t)(c0 + 1) * V + c1) * J, (uint32_t)(J * 4));
     }
   }
+  __syncwarp();
   // scratch row q: {hash lo, hash hi, length (negative = no candidate), ctx0 | ctx1, score, root, -, -}
   uint4* scr4 = reinterpret_cast<uint4*>(scr);
   if (lane < K) {
@@ -259,7 +260,7 @@ __device__ __forceinline__ void select_stream(int s, int V, int CS, const float*
 // Warp roles: warps 0..15 build the joiner operand (two hypothesis rows each), read the accumulator out, reduce and merge;
 // warp 16 only issues MMAs (as the K-quarters of the operand land) - so the tensor pipe starts on the first quarter while
 // the other three are still being computed.
-template <int K, bool X3>
+template <int K, bool X3, bool TIMED>
 __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
   constexpr int XWP = xw_padded(K);
   constexpr int S = kNH / K;
@@ -351,10 +352,10 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
   cluster_sync();            // every CTA of the cluster is resident: remote shared memory may be written
 
   __shared__ long long tph[20];          // phase cycle totals live in shared memory: no registers held across the loop
-  const bool timed = a.timing != nullptr && blockIdx.x == 0 && tid == 0;
+  const bool timed = TIMED && a.timing != nullptr && blockIdx.x == 0 && tid == 0;
   if (timed) for (int i = 0; i < 20; ++i) tph[i] = 0;
   long long tlast = timed ? clock64() : 0;
-#define K2B_PHASE(i) do { if (timed) { const long long now = clock64(); tph[i] += now - tlast; tlast = now; } } while (0)
+#define K2B_PHASE(i) do { if (TIMED && timed) { const long long now = clock64(); tph[i] += now - tlast; tlast = now; } } while (0)
 
   const int nq = J / 4;
 
@@ -459,6 +460,7 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
           fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's async proxy
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_q[i]);
+          __syncwarp();                      // reconverge: without it the compiler may leave lane 0 split off for the rest of the step
           K2B_PHASE(14 + i);
         }
         if (t + 1 < T) {
@@ -576,6 +578,7 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
           if (warp == 0) mbar_expect_tx(&xbar[t & 1], (uint32_t)((CS - 1) * kNH * XWP * 4));
           else mbar_arrive(&xbar[t & 1]);
         }
+        __syncwarp();                        // reconverge (see above)
       }
       K2B_PHASE(4);
 
@@ -587,7 +590,7 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
           const int g = cluster * S + s;
           int32_t* bp_row = (rank == 0 && g < a.B) ? a.bp + ((size_t)g * a.Ttot + a.t0 + t) * K : nullptr;
           select_stream<K>(s, V, CS, xw, st[cur], st[cur ^ 1], a.blank, a.unk, a.extra_mask, bp_row, lane, a.dec_tab, J,
-                           (int)rank == (s % CS), sel_scr[warp]);
+                           (a.dbg & 2) == 0 && (int)rank == (s % CS), sel_scr[warp]);
         }
       }
       K2B_PHASE(6);
@@ -654,9 +657,11 @@ __global__ void exp2x_kernel(const float* __restrict__ in, float* __restrict__ o
 
 }  // namespace
 
-static void (*cluster_kernel_for(int K, bool x3))(const ClusterArgs) {
-  if (x3) return K == 1 ? cluster_beam_kernel<1, true> : (K == 2 ? cluster_beam_kernel<2, true> : (K == 4 ? cluster_beam_kernel<4, true> : cluster_beam_kernel<8, true>));
-  return K == 1 ? cluster_beam_kernel<1, false> : (K == 2 ? cluster_beam_kernel<2, false> : (K == 4 ? cluster_beam_kernel<4, false> : cluster_beam_kernel<8, false>));
+// `timed` selects the instrumented build of the beam-4 kernel (per-phase clock64 totals); production launches never carry it
+static void (*cluster_kernel_for(int K, bool x3, bool timed))(const ClusterArgs) {
+  if (timed && K == 4) return x3 ? cluster_beam_kernel<4, true, true> : cluster_beam_kernel<4, false, true>;
+  if (x3) return K == 1 ? cluster_beam_kernel<1, true, false> : (K == 2 ? cluster_beam_kernel<2, true, false> : (K == 4 ? cluster_beam_kernel<4, true, false> : cluster_beam_kernel<8, true, false>));
+  return K == 1 ? cluster_beam_kernel<1, false, false> : (K == 2 ? cluster_beam_kernel<2, false, false> : (K == 4 ? cluster_beam_kernel<4, false, false> : cluster_beam_kernel<8, false, false>));
 }
 
 static size_t cluster_dyn_smem(int J, int CS, int K) {
@@ -680,7 +685,7 @@ bool cluster_path_supported(const k2b_handle* h, int K) {
     k2b_handle* hm = const_cast<k2b_handle*>(h);
     if (hm->cluster16_ok < 0) {
       hm->cluster16_ok = 0;
-      auto kern = cluster_kernel_for(1, c.precision == K2B_PREC_BF16X3);
+      auto kern = cluster_kernel_for(1, c.precision == K2B_PREC_BF16X3, false);
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
           cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) == cudaSuccess) {
         cudaLaunchConfig_t cfg = {};
@@ -758,7 +763,7 @@ int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, 
   { const char* de = getenv("K2B_DBG"); a.dbg = de ? atoi(de) : 0; }
   a.bp = bp; a.fin_lp = fin_lp; a.fin_len = fin_len; a.fin_nlive = fin_nlive; a.status = status;
   const size_t dyn = cluster_dyn_smem(J, CS, K);
-  void (*kern)(const ClusterArgs) = cluster_kernel_for(K, a.x3 != 0);
+  void (*kern)(const ClusterArgs) = cluster_kernel_for(K, a.x3 != 0, a.timing != nullptr);
   if (CS > 8) K2B_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   K2B_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   cudaLaunchConfig_t cfg = {};

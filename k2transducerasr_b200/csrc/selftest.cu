@@ -158,8 +158,9 @@ __global__ void __launch_bounds__(128) umma_bench_kernel(int flavour, int nkb, i
   if (flavour >= 11 && wu == 3) {
     // warp-uniform issue loop (flavour 11: SS N=32, 12: TS N=32, 13: SS N=64): descriptors live in uniform registers
     const uint32_t el = elect_one();
-    const int N2 = flavour == 13 ? 64 : 32;
+    const int N2 = (flavour == 13 || flavour == 14 || flavour == 15) ? 64 : 32;
     const uint32_t idesc2 = umma_idesc_bf16_f32(128, N2);
+    const uint32_t idesc64u = umma_idesc_bf16_f32(128, 64), idesc32u = umma_idesc_bf16_f32(128, 32);
     long long t0 = clock64();
     for (int r = 0; r < reps; ++r) {
       for (int kb = 0; kb < nkb; ++kb) {
@@ -168,6 +169,19 @@ __global__ void __launch_bounds__(128) umma_bench_kernel(int flavour, int nkb, i
           const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a0 + (uint32_t)(kb * 1024 + k * 2));
           const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b0 + (uint32_t)(kb * 1024 + k * 2));
           if (flavour == 12) umma_ts_e(tb, tb + 384 + (uint32_t)((kb * 4 + k) * 8), db, idesc2, 1, el);
+          else if (flavour == 14) umma_ss_e(tb + (uint32_t)(((kb * 4 + k) & 1) * 64), da, db, idesc2, 1, el);      // 2 accumulators
+          else if (flavour == 15) umma_ss_e(tb + (uint32_t)(((kb * 4 + k) & 3) * 64), da, db, idesc2, 1, el);      // 4 accumulators
+          else if (flavour == 16) {            // the kernel's pair, same accumulator: SS N=64 then TS N=32
+            umma_ss_e(tb, da, db, idesc64u, 1, el);
+            umma_ts_e(tb, tb + 384 + (uint32_t)((kb * 4 + k) * 8), db, idesc32u, 1, el);
+          } else if (flavour == 17) {          // the pair on separate accumulators
+            umma_ss_e(tb, da, db, idesc64u, 1, el);
+            umma_ts_e(tb + 64, tb + 384 + (uint32_t)((kb * 4 + k) * 8), db, idesc32u, 1, el);
+          } else if (flavour == 18) {          // the pair, separate accumulators, K split over two more
+            const uint32_t o = (uint32_t)((k & 1) * 96);
+            umma_ss_e(tb + o, da, db, idesc64u, 1, el);
+            umma_ts_e(tb + o + 64, tb + 384 + (uint32_t)((kb * 4 + k) * 8), db, idesc32u, 1, el);
+          }
           else umma_ss_e(tb, da, db, idesc2, 1, el);
         }
       }
