@@ -171,7 +171,94 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
       if (lane == 0) mbar_arrive(&full_a[s]);
     }
     // epilogue (producer warps 0..3 = CTA warps 2..5): a warp owns TMEM lanes 32*(warp%4) .. +31 = those tile rows
-    if (pw < 4) {
+    if (a.epi == 2) {
+      // ---- softmax / top-k partials of this 128 x 256 logits tile (modified_beam_search), all eight warps -----------
+      // (1) accumulator (+bias) -> shared memory, row-major with a 257-word stride (the pipeline stages are dead now);
+      // (2) one warp per row, lanes across the 256 columns: selection keys are the order-preserving integer image of the
+      //     logit with its low 8 bits replaced by the column, so they are unique and one REDUX per round finds value and
+      //     position at once (values closer than 2^-15 relative resolve to the larger vocabulary index; the exact fp32
+      //     logit is re-read for the record); sum-exp is a fixed-point REDUX (order-independent).
+      if (!mbar_wait(&acc_full, 0)) ok = false;
+      tc_fence_after();
+      float* tile = reinterpret_cast<float*>(smem);
+      constexpr int kTS = kEN + 1;
+      {
+        const int lg = warp & 3, chalf = pw >> 2;
+        const int row = lg * 32 + lane;
+        const uint32_t trow = t_d + ((uint32_t)(lg * 32) << 16);
+        for (int c0 = chalf * 128; c0 < chalf * 128 + 128; c0 += 32) {
+          uint32_t u[32];
+          tmem_ld32(trow + (uint32_t)c0, u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tile[row * kTS + c0 + j] = __uint_as_float(u[j]) + bias_t[c0 + j];
+        }
+      }
+      tc_fence_before();
+      named_bar_sync(1, kProducers * 32);
+      const int K = a.topk;
+      const int col0 = tile_n * kEN;
+      const int nval = min(kEN, a.nvalid - col0);
+      constexpr int kNone = (int)0x80000000;
+      for (int rr = 0; rr < kEM / kProducers; rr += 2) {
+        float v[2][8];
+        int pk[2][8];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int row = pw * (kEM / kProducers) + rr + r;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int pos = lane + 32 * j;
+            v[r][j] = tile[row * kTS + pos];
+            const int kb = __float_as_int(v[r][j]);
+            const int key = kb ^ ((kb >> 31) & 0x7fffffff);
+            pk[r][j] = pos < nval ? ((key & ~255) | pos) : kNone;
+          }
+        }
+        int keep[2] = {kNone, kNone};
+        float mx[2], sum[2];
+        for (int q = 0; q < K; ++q) {
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int hk = max(max(max(pk[r][0], pk[r][1]), max(pk[r][2], pk[r][3])), max(max(pk[r][4], pk[r][5]), max(pk[r][6], pk[r][7])));
+            const int wk = __reduce_max_sync(0xffffffffu, hk);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pk[r][j] = (pk[r][j] == wk) ? kNone : pk[r][j];
+            keep[r] = (lane == q) ? wk : keep[r];
+            if (q == 0) {
+              const int mk = wk & ~255;
+              mx[r] = (wk == kNone) ? -INFINITY : __int_as_float(mk ^ ((mk >> 31) & 0x7fffffff));
+              const float mneg = (wk == kNone) ? 0.f : -mx[r] * 1.4426950408889634f;
+              float ls = 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float ex;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fmaf(v[r][j], 1.4426950408889634f, mneg)));
+                ls += (lane + 32 * j < nval) ? ex : 0.f;
+              }
+              const unsigned tot = __reduce_add_sync(0xffffffffu, __float2uint_rn(ls * 8388608.f));
+              sum[r] = (wk == kNone) ? 0.f : (float)tot * (1.f / 8388608.f);
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int row = pw * (kEM / kProducers) + rr + r;
+          const int m = tile_m * kEM + row;
+          if (m < a.M) {
+            const size_t po = (size_t)m * ntn + tile_n;
+            if (lane == 0) { a.part_m[po] = mx[r]; a.part_s[po] = sum[r]; }
+            if (lane < K) {
+              const bool has = keep[r] != kNone;
+              const int pos = keep[r] & 255;
+              a.part_tv[po * K + lane] = has ? tile[row * kTS + pos] : -INFINITY;
+              a.part_ti[po * K + lane] = has ? col0 + pos : -1;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    } else if (pw < 4) {
     if (!mbar_wait(&acc_full, 0)) ok = false;
     tc_fence_after();
     const int lg = warp & 3;
@@ -228,43 +315,6 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
           }
         }
         if (m < a.M) { a.part_val[po] = bv; a.part_idx[po] = bi; a.part_nan[po] = bnan; }
-      } else {
-        const int K = a.topk;
-        float mx = -INFINITY;
-        for (int c0 = 0; c0 < kEN; c0 += 32) {
-          uint32_t u[32];
-          tmem_ld32(trow + (uint32_t)c0, u);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(u[j]) + bias_t[c0 + j]);   // padding columns: -inf
-        }
-        float tv[kMaxBeam];
-        int ti[kMaxBeam];
-#pragma unroll
-        for (int i = 0; i < kMaxBeam; ++i) { tv[i] = -INFINITY; ti[i] = -1; }
-        float thr_v = -INFINITY, sum = 0.f;
-        int thr_i = -1;
-        for (int c0 = 0; c0 < kEN; c0 += 32) {
-          uint32_t u[32];
-          tmem_ld32(trow + (uint32_t)c0, u);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = col0 + c0 + j;
-            {
-              float v = __uint_as_float(u[j]) + bias_t[c0 + j];     // -inf on padding columns: exp -> 0, never inserted
-              sum += __expf(v - mx);
-              if (better_e(v, col, thr_v, thr_i) && col < a.nvalid) topk_insert(tv, ti, K, v, col, &thr_v, &thr_i);
-            }
-          }
-        }
-        if (m < a.M) {
-          a.part_m[po] = mx;
-          a.part_s[po] = (mx == -INFINITY) ? 0.f : sum;
-#pragma unroll
-          for (int i = 0; i < kMaxBeam; ++i)
-            if (i < K) { a.part_tv[po * K + i] = tv[i]; a.part_ti[po * K + i] = ti[i]; }
-        }
       }
     }
     }
