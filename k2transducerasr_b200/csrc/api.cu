@@ -44,6 +44,10 @@ void free_cluster_assets(k2b_handle* h) {
   if (h->wj_lo_img) cudaFree(h->wj_lo_img);
   h->wj_hi_img = nullptr; h->wj_lo_img = nullptr;
   h->wj_ready = false;
+  if (h->wd_hi_img) cudaFree(h->wd_hi_img);
+  if (h->wd_lo_img) cudaFree(h->wd_lo_img);
+  h->wd_hi_img = nullptr; h->wd_lo_img = nullptr;
+  h->wd_ready = false;
 }
 
 int32_t enter(k2b_handle* h) {

@@ -40,7 +40,27 @@ struct EncArgs {
   int rows_per_stream, out_T, out_t0;     // epi 0 with rows_per_stream > 0: row m = (b, tt) of a time chunk -> output row b*out_T + out_t0 + tt
   float* part_m; float* part_s; float* part_tv; int32_t* part_ti;     // epi 2: [M,nt], [M,nt], [M,nt,topk] x2
   float* part_val; int32_t* part_idx; int32_t* part_nan;              // epi 3: [M,nt] each
+  // pro 1: stateless decoder as the A producer - A(m,k) = relu(tab0[row(y0(m))][k] + tab1[row(y1(m))][k]) (embedding gather +
+  // folded grouped conv1d + ReLU, ref OfflineProjOfTransducer.cs:116 [EXT]); epi 4: C = tanh(acc + bias + enc[m / rows_per_stream])
+  // = decoder_proj fused with the joiner prologue (x = tanh(enc + dec))
+  int pro, V, neg_wrap;
+  const int32_t* ctx; const float* tab0; const float* tab1;
+  const float* enc; long long enc_stride;
 };
+
+__device__ __forceinline__ int table_row_e(int y, int V, int neg_wrap) {
+  if (y >= 0) return y < V ? y : V;      // out-of-range ids read the zero row
+  if (neg_wrap) { const int r = y + V; return r >= 0 ? r : V; }
+  return V;
+}
+
+// tanh(x) = 1 - 2 / (1 + e^(2x)); |x| is clamped where tanh is already 1 to the last bit, so e^(2x) stays finite
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float y = __expf(2.f * fminf(fmaxf(x, -15.f), 15.f));
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y + 1.f));
+  return fmaf(-2.f, r, 1.f);
+}
 
 __device__ __forceinline__ bool better_e(float v, int i, float ev, int ei) { return v > ev || (v == ev && i > ei); }
 
@@ -61,7 +81,7 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_w[kStages], full_a[kStages], empty[kStages], acc_full;
   __shared__ uint32_t tmem_slot;
-  __shared__ float bias_t[kEN];          // this tile's bias (-inf beyond the valid columns): broadcast reads in the epilogue
+  __shared__ __align__(16) float bias_t[kEN];          // this tile's bias (-inf beyond the valid columns): broadcast reads in the epilogue
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
@@ -142,6 +162,18 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
     const int pw = warp - 2;              // 0..7: rows pw*16 .. pw*16+15 of the tile
     const int half = lane >> 4, c4 = lane & 15;     // two rows per warp instruction, 16 float4 per 64-wide row
     constexpr int kRowsPerWarp = kEM / kProducers, kIters = kRowsPerWarp / 2;
+    int r0[kIters], r1[kIters];          // pro 1: table rows of this thread's hypothesis rows
+    if (a.pro == 1) {
+#pragma unroll
+      for (int i = 0; i < kIters; ++i) {
+        const int m = tile_m * kEM + pw * kRowsPerWarp + 2 * i + half;
+        r0[i] = r1[i] = a.V;
+        if (m < a.M) {
+          r0[i] = table_row_e(a.ctx[2 * m], a.V, a.neg_wrap);
+          r1[i] = table_row_e(a.ctx[2 * m + 1], a.V, a.neg_wrap);
+        }
+      }
+    }
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % kStages;
       const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
@@ -149,12 +181,21 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
       uint8_t* a_hi = smem + (size_t)s * kStageBytes;
       uint8_t* a_lo = a_hi + kATile;
       float4 v[kIters];
+      if (a.pro == 1) {
+#pragma unroll
+        for (int i = 0; i < kIters; ++i) {
+          const float4 x = __ldg(reinterpret_cast<const float4*>(a.tab0 + (size_t)r0[i] * a.K + (size_t)kb * kBKc) + c4);
+          const float4 y = __ldg(reinterpret_cast<const float4*>(a.tab1 + (size_t)r1[i] * a.K + (size_t)kb * kBKc) + c4);
+          v[i] = make_float4(fmaxf(x.x + y.x, 0.f), fmaxf(x.y + y.y, 0.f), fmaxf(x.z + y.z, 0.f), fmaxf(x.w + y.w, 0.f));
+        }
+      } else {
 #pragma unroll
       for (int i = 0; i < kIters; ++i) {
         const int r = pw * kRowsPerWarp + 2 * i + half;
         const int m = tile_m * kEM + r;
         v[i] = (m < a.M) ? __ldg(reinterpret_cast<const float4*>(a.A + (size_t)m * a.K + (size_t)kb * kBKc) + c4)
                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       }
 #pragma unroll
       for (int i = 0; i < kIters; ++i) {
@@ -258,6 +299,55 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
         }
         __syncwarp();
       }
+    } else if (a.epi == 0 || a.epi == 4) {
+      // ---- store epilogues, all eight warps: accumulator -> shared memory (row stride 260 words: 16-byte vector accesses both
+      //      ways without bank conflicts), then one warp per row with the lanes across the 256 columns, so bias / encoder frame
+      //      loads and the output stores are coalesced 512-byte rows
+      if (!mbar_wait(&acc_full, 0)) ok = false;
+      tc_fence_after();
+      float* tile = reinterpret_cast<float*>(smem);
+      constexpr int kTS4 = kEN + 4;
+      {
+        const int lg = warp & 3, chalf = pw >> 2;
+        const int row = lg * 32 + lane;
+        const uint32_t trow = t_d + ((uint32_t)(lg * 32) << 16);
+        for (int c0 = chalf * 128; c0 < chalf * 128 + 128; c0 += 32) {
+          uint32_t u[32];
+          tmem_ld32(trow + (uint32_t)c0, u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(tile + row * kTS4 + c0 + 4 * q) = make_uint4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
+        }
+      }
+      tc_fence_before();
+      named_bar_sync(1, kProducers * 32);
+      for (int rr = 0; rr < kEM / kProducers; ++rr) {
+        const int row = pw * (kEM / kProducers) + rr;
+        const int m = tile_m * kEM + row;
+        if (m >= a.M) break;
+        size_t orow = (size_t)m;
+        if (a.epi == 0 && a.rows_per_stream > 0) { const int b = m / a.rows_per_stream; orow = (size_t)b * a.out_T + a.out_t0 + (m - b * a.rows_per_stream); }
+        float* crow = a.C + orow * a.N + (size_t)tile_n * kEN;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int col = hf * 128 + 4 * lane;
+          float4 o = *reinterpret_cast<const float4*>(tile + row * kTS4 + col);
+          const float4 bb = *reinterpret_cast<const float4*>(bias_t + col);
+          o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+          if (a.epi == 4) {
+            const float4 e = __ldg(reinterpret_cast<const float4*>(a.enc + (size_t)(m / a.rows_per_stream) * a.enc_stride +
+                                                                    (size_t)tile_n * kEN + col));
+            o.x = tanh_fast(o.x + e.x); o.y = tanh_fast(o.y + e.y); o.z = tanh_fast(o.z + e.z); o.w = tanh_fast(o.w + e.w);
+          } else if (a.exp2x) {
+            o.x = expf(2.f * fminf(fmaxf(o.x, -21.f), 21.f));
+            o.y = expf(2.f * fminf(fmaxf(o.y, -21.f), 21.f));
+            o.z = expf(2.f * fminf(fmaxf(o.z, -21.f), 21.f));
+            o.w = expf(2.f * fminf(fmaxf(o.w, -21.f), 21.f));
+          }
+          *reinterpret_cast<float4*>(crow + col) = o;
+        }
+      }
     } else if (pw < 4) {
     if (!mbar_wait(&acc_full, 0)) ok = false;
     tc_fence_after();
@@ -265,34 +355,7 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
     const int row = lg * 32 + lane;
     const int m = tile_m * kEM + row;
     const uint32_t trow = t_d + ((uint32_t)(lg * 32) << 16);
-    if (a.epi == 0) {
-      size_t orow = (size_t)m;
-      if (a.rows_per_stream > 0) { const int b = m / a.rows_per_stream; orow = (size_t)b * a.out_T + a.out_t0 + (m - b * a.rows_per_stream); }
-      float* crow = a.C + orow * a.N + (size_t)tile_n * kEN;
-      const float* brow = a.bias + (size_t)tile_n * kEN;
-      for (int c0 = 0; c0 < kEN; c0 += 32) {
-        uint32_t u[32];
-        tmem_ld32(trow + (uint32_t)c0, u);
-        tmem_ld_wait();
-        if (m < a.M) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 o;
-            o.x = __uint_as_float(u[4 * q + 0]) + __ldg(brow + c0 + 4 * q + 0);
-            o.y = __uint_as_float(u[4 * q + 1]) + __ldg(brow + c0 + 4 * q + 1);
-            o.z = __uint_as_float(u[4 * q + 2]) + __ldg(brow + c0 + 4 * q + 2);
-            o.w = __uint_as_float(u[4 * q + 3]) + __ldg(brow + c0 + 4 * q + 3);
-            if (a.exp2x) {
-              o.x = expf(2.f * fminf(fmaxf(o.x, -21.f), 21.f));
-              o.y = expf(2.f * fminf(fmaxf(o.y, -21.f), 21.f));
-              o.z = expf(2.f * fminf(fmaxf(o.z, -21.f), 21.f));
-              o.w = expf(2.f * fminf(fmaxf(o.w, -21.f), 21.f));
-            }
-            *reinterpret_cast<float4*>(crow + c0 + 4 * q) = o;
-          }
-        }
-      }
-    } else {
+    {
       // the thread owns one hypothesis row and walks its 256 logits of this vocab tile straight out of TMEM
       const int col0 = tile_n * kEN;
       const size_t po = (size_t)m * ntn + tile_n;
@@ -375,6 +438,32 @@ int32_t encoder_proj_tc(k2b_handle* h, const float* raw, int n, float* out, bool
   a.M = n; a.N = h->cfg.joiner_dim; a.K = h->cfg.encoder_dim;
   a.exp2x = exp2x ? 1 : 0;
   a.epi = 0; a.nvalid = a.N;
+  return launch_tc(h, a);
+}
+
+// ---- stateless decoder + joiner prologue on the tensor cores: x[m,:] = tanh(enc[m / rows_per_stream] + decoder(ctx[m])) -----
+bool decoder_tc_supported(const k2b_handle* h) {
+  const k2b_config& c = h->cfg;
+  return c.decoder_dim % 64 == 0 && c.joiner_dim % kEN == 0 && h->dec_w != nullptr && h->tab0 != nullptr;
+}
+
+int32_t decoder_joinin_tc(k2b_handle* h, const int32_t* ctx, int M, const float* enc, long long enc_stride, int rows_per_stream,
+                          float* x) {
+  if (!h->wd_ready) {
+    const int N = h->cfg.joiner_dim, K = h->cfg.decoder_dim;
+    K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->wd_hi_img), (size_t)N * K * 2));
+    K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->wd_lo_img), (size_t)N * K * 2));
+    pack_enc_w_kernel<<<N, 128, 0, h->stream>>>(h->dec_w, N, K, h->wd_hi_img, h->wd_lo_img);
+    K2B_LAUNCH_CHECK(h);
+    h->wd_ready = true;
+  }
+  EncArgs a = {};
+  a.pro = 1; a.ctx = ctx; a.tab0 = h->tab0; a.tab1 = h->tab1; a.V = h->cfg.vocab_size;
+  a.neg_wrap = h->cfg.neg_id_mode == K2B_NEGID_WRAP ? 1 : 0;
+  a.enc = enc; a.enc_stride = enc_stride; a.rows_per_stream = rows_per_stream;
+  a.w_hi_img = h->wd_hi_img; a.w_lo_img = h->wd_lo_img; a.bias = h->dec_b; a.C = x;
+  a.M = M; a.N = h->cfg.joiner_dim; a.K = h->cfg.decoder_dim;
+  a.epi = 4; a.nvalid = a.N;
   return launch_tc(h, a);
 }
 

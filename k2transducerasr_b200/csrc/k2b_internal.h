@@ -84,6 +84,9 @@ struct k2b_handle {
   bool wj_ready = false;          // out_w in 256-row tiles for the per-frame tcgen05 joiner (any vocabulary)
   uint8_t* wj_hi_img = nullptr;
   uint8_t* wj_lo_img = nullptr;
+  bool wd_ready = false;          // dec_proj_w in 256-row tiles for the tcgen05 decoder (per-frame path)
+  uint8_t* wd_hi_img = nullptr;
+  uint8_t* wd_lo_img = nullptr;
   cudaStream_t copy_stream = nullptr;   // host-pointer calls: H2D of time chunk c+1 overlaps compute of chunk c
   cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   int* dev_status = nullptr;      // [4] error flags written by the tcgen05 kernels (mbarrier time-outs)
@@ -188,6 +191,9 @@ int32_t cluster_status(k2b_handle* h);
 bool encproj_tc_supported(const k2b_handle* h);
 int32_t encoder_proj_tc(k2b_handle* h, const float* raw, int n, float* out, bool exp2x, int rows_per_stream = 0, int out_T = 0,
                         int out_t0 = 0);
+bool decoder_tc_supported(const k2b_handle* h);
+int32_t decoder_joinin_tc(k2b_handle* h, const int32_t* ctx, int M, const float* enc, long long enc_stride, int rows_per_stream,
+                          float* x);
 bool joiner_tc_supported(const k2b_handle* h);
 int joiner_tc_tiles(const k2b_handle* h);
 int32_t joiner_tc_partials(k2b_handle* h, const float* x, int M, int topk, float* part_m, float* part_s, float* part_tv,

@@ -119,86 +119,133 @@ __device__ __forceinline__ bool better(float v, int i, float ev, int ei) {
 // One warp per stream ("hyp_merge"): log_softmax constants per live hypothesis from the tile partials,
 // per-stream top-K over the K*V extensions (value desc, flat index desc), extension, dedupe by
 // token-sequence hash with log-add, compaction in insertion order, back-pointer record.
+// Branch-free throughout (predicated selects, REDUX max for the arg-best rounds): the lanes of a warp never diverge.
+__device__ __forceinline__ int fkey_s(float f) { const int k = __float_as_int(f); return k ^ ((k >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float funkey_s(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+
 __global__ void __launch_bounds__(128)
 beam_select_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
                    const float* __restrict__ part_m, const float* __restrict__ part_s,
                    const float* __restrict__ part_tv, const int32_t* __restrict__ part_ti,
                    BeamState in, BeamState out, int32_t* __restrict__ bp) {
   __shared__ float s_mx[4][kMaxBeam], s_ls[4][kMaxBeam], s_lp[4][kMaxBeam];
+  constexpr int kNone = (int)0x80000000;
+  const unsigned full = 0xffffffffu;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.x * 4 + wib;
   if (s >= B) return;
   const int nl = in.nlive[s];
 
-  for (int h = 0; h < nl; ++h) {
-    const size_t row = (size_t)s * K + h;
-    float mx = -INFINITY, sum = 0.f;
-    for (int tile = lane; tile < nt; tile += 32) {
-      const float pm = part_m[row * nt + tile], ps = part_s[row * nt + tile];
-      const float nm = fmaxf(mx, pm);
-      if (nm != -INFINITY) sum = sum * expf(mx - nm) + ps * expf(pm - nm);
-      mx = nm;
+  // log_softmax constants. Every (hypothesis, tile) pair is one work item, lane-strided, with all loads of a batch of four
+  // items in flight at once (the partials sit in L2 / HBM: latency, not bandwidth, is what this kernel pays for):
+  // pass 1 folds the tile maxima per hypothesis (REDUX max), pass 2 the rescaled sums (butterfly).
+  const int npair = nl * nt;
+  const size_t prow0 = (size_t)s * K * nt;                 // pair p of this stream = element prow0 + p of part_m / part_s
+  int mk[kMaxBeam];
+#pragma unroll
+  for (int h = 0; h < kMaxBeam; ++h) mk[h] = kNone;
+  for (int p0 = 0; p0 < npair; p0 += 128) {
+    float pm[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int p = p0 + 32 * u + lane; pm[u] = p < npair ? part_m[prow0 + p] : -INFINITY; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + 32 * u + lane;
+      const int hp = p / nt, key = p < npair ? fkey_s(pm[u]) : kNone;
+#pragma unroll
+      for (int h = 0; h < kMaxBeam; ++h) mk[h] = (hp == h) ? max(mk[h], key) : mk[h];
+    }
+  }
+  float mxh[kMaxBeam], sumh[kMaxBeam];
+#pragma unroll
+  for (int h = 0; h < kMaxBeam; ++h) {
+    mxh[h] = (h < K) ? funkey_s(__reduce_max_sync(full, mk[h])) : -INFINITY;
+    sumh[h] = 0.f;
+  }
+  for (int p0 = 0; p0 < npair; p0 += 128) {
+    float pm[4], ps[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + 32 * u + lane;
+      pm[u] = p < npair ? part_m[prow0 + p] : -INFINITY;
+      ps[u] = p < npair ? part_s[prow0 + p] : 0.f;
     }
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-      const float omx = __shfl_xor_sync(0xffffffffu, mx, o), osum = __shfl_xor_sync(0xffffffffu, sum, o);
-      const float nm = fmaxf(mx, omx);
-      sum = (nm == -INFINITY) ? 0.f : sum * expf(mx - nm) + osum * expf(omx - nm);
-      mx = nm;
+    for (int u = 0; u < 4; ++u) {
+      const int hp = (p0 + 32 * u + lane) / nt;
+      float mh = -INFINITY;
+#pragma unroll
+      for (int h = 0; h < kMaxBeam; ++h) mh = (hp == h) ? mxh[h] : mh;
+      const float term = (pm[u] > -INFINITY) ? ps[u] * __expf(pm[u] - mh) : 0.f;
+#pragma unroll
+      for (int h = 0; h < kMaxBeam; ++h) sumh[h] += (hp == h) ? term : 0.f;
     }
-    if (lane == 0) {
-      s_mx[wib][h] = mx;
-      s_ls[wib][h] = logf(sum);
-      s_lp[wib][h] = in.lp[row];
+  }
+#pragma unroll
+  for (int h = 0; h < kMaxBeam; ++h) {
+    if (h < K) {
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) sumh[h] += __shfl_xor_sync(full, sumh[h], o);
+      if (lane == 0 && h < nl) {
+        s_mx[wib][h] = mxh[h];
+        s_ls[wib][h] = __logf(sumh[h]);
+        s_lp[wib][h] = in.lp[(size_t)s * K + h];
+      }
     }
   }
   __syncwarp();
 
-  // lane-local top-K of this lane's share of the candidates
-  float tv[kMaxBeam];
-  int tf[kMaxBeam];
+  // lane-local top-K (sorted, best first) of this lane's share of the candidates: predicated insertion network,
+  // candidates loaded four at a time
+  int tk[kMaxBeam], tf[kMaxBeam];
 #pragma unroll
-  for (int i = 0; i < kMaxBeam; ++i) { tv[i] = -INFINITY; tf[i] = -1; }
+  for (int i = 0; i < kMaxBeam; ++i) { tk[i] = kNone; tf[i] = -1; }
   const int per_h = nt * K;
   const int total = nl * per_h;
   const size_t base = (size_t)s * K * per_h;
-  for (int c = lane; c < total; c += 32) {
-    const int idx = part_ti[base + c];
-    if (idx < 0) continue;
-    const int h = c / per_h;
-    // same operation order as log_softmax(x) + lp : ((x - max) - log(sum)) + lp
-    float v = ((part_tv[base + c] - s_mx[wib][h]) - s_ls[wib][h]) + s_lp[wib][h];
-    int f = h * V + idx;
-    if (!(v == v)) continue;
+  for (int c0 = 0; c0 < total; c0 += 128) {
+    int cidx[4];
+    float cval[4];
 #pragma unroll
-    for (int i = 0; i < kMaxBeam; ++i) {
-      if (i < K && better(v, f, tv[i], tf[i])) {
-        const float fv = tv[i]; const int ff = tf[i];
-        tv[i] = v; tf[i] = f; v = fv; f = ff;
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + 32 * u + lane;
+      cidx[u] = c < total ? part_ti[base + c] : -1;
+      cval[u] = c < total ? part_tv[base + c] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + 32 * u + lane;
+      const int h = min(c / per_h, kMaxBeam - 1);
+      // same operation order as log_softmax(x) + lp : ((x - max) - log(sum)) + lp
+      const float v = ((cval[u] - s_mx[wib][h]) - s_ls[wib][h]) + s_lp[wib][h];
+      const bool okc = (cidx[u] >= 0) & (v == v);
+      int key = okc ? fkey_s(v) : kNone;
+      int f = okc ? h * V + cidx[u] : -1;
+#pragma unroll
+      for (int i = 0; i < kMaxBeam; ++i) {
+        if (i < K) {
+          const bool b = (key > tk[i]) | ((key == tk[i]) & (f > tf[i]));
+          const int nk = b ? tk[i] : key, nf = b ? tf[i] : f;
+          tk[i] = b ? key : tk[i]; tf[i] = b ? f : tf[i];
+          key = nk; f = nf;
+        }
       }
     }
   }
 
-  // K rounds of warp arg-best; lane r (< K) keeps winner r
+  // K rounds of warp arg-best over the heads (REDUX on the key, then on the flat index among the ties); lane r keeps winner r
   float my_v = -INFINITY;
   int my_f = -1;
 #pragma unroll
   for (int r = 0; r < kMaxBeam; ++r) {
     if (r < K) {
-      float bv = tv[0];
-      int bf = tf[0];
+      const int wk = __reduce_max_sync(full, tk[0]);
+      const int wf = __reduce_max_sync(full, (tk[0] == wk) ? tf[0] : -1);
+      const bool pop = (tf[0] == wf) & (wf >= 0);      // flat indices are unique: exactly one lane pops
 #pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int of = __shfl_xor_sync(0xffffffffu, bf, o);
-        if (of >= 0 && (bf < 0 || better(ov, of, bv, bf))) { bv = ov; bf = of; }
-      }
-      if (bf >= 0 && tf[0] == bf) {   // flat indices are unique: exactly one lane pops
-#pragma unroll
-        for (int i = 0; i + 1 < kMaxBeam; ++i) { tv[i] = tv[i + 1]; tf[i] = tf[i + 1]; }
-        tv[kMaxBeam - 1] = -INFINITY; tf[kMaxBeam - 1] = -1;
-      }
-      if (lane == r) { my_v = bv; my_f = bf; }
+      for (int i = 0; i + 1 < kMaxBeam; ++i) { tk[i] = pop ? tk[i + 1] : tk[i]; tf[i] = pop ? tf[i + 1] : tf[i]; }
+      tk[kMaxBeam - 1] = pop ? kNone : tk[kMaxBeam - 1]; tf[kMaxBeam - 1] = pop ? -1 : tf[kMaxBeam - 1];
+      if (lane == r) { my_v = wf >= 0 ? funkey_s(wk) : -INFINITY; my_f = wf; }
     }
   }
 
@@ -431,7 +478,8 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
     d.blank = c.blank_id;
     d.enc = enc + (size_t)t * J; d.enc_stride = (long long)T * J; d.rows_per_stream = K;
     d.C = x;
-    K2B_TRY(launch_gemm_simt(h, PRO_DEC, EPI_TANH_ADD, d));
+    if (tc && decoder_tc_supported(h)) K2B_TRY(decoder_joinin_tc(h, st[cur].ctx, N, enc + (size_t)t * J, (long long)T * J, K, x));
+    else K2B_TRY(launch_gemm_simt(h, PRO_DEC, EPI_TANH_ADD, d));
 
     GemmArgs j;
     j.M = N; j.N = V; j.K = J;
