@@ -118,7 +118,9 @@ template <int K>
 __device__ __forceinline__ void select_stream(int s, int V, int CS, const float* __restrict__ xb, const HypState& in,
                                               HypState& out, int blank, int unk, int extra_mask, int32_t* __restrict__ bp_row,
                                               int lane, const float* __restrict__ dec_tab, int J, bool do_prefetch,
-                                              uint32_t* __restrict__ scr) {
+                                              uint32_t* __restrict__ scr, long long* tp = nullptr) {
+#define K2B_SUB(i) do { if (tp != nullptr) { const long long now = clock64(); tp[i] += now - tp[19]; tp[19] = now; } } while (0)
+  if (tp != nullptr) tp[19] = clock64();
   constexpr int XWP = xw_padded(K);
   constexpr int CPP = 32 / K;                     // slices per pass
   constexpr int NP = (K == 8) ? 2 : 1;            // K * CS <= 32 * NP on every supported shape
@@ -146,6 +148,7 @@ __device__ __forceinline__ void select_stream(int s, int V, int CS, const float*
     if (lane == 0) out.nlive[s] = 0;
     return;
   }
+  K2B_SUB(8);
   float M = -INFINITY;
 #pragma unroll
   for (int p = 0; p < NP; ++p) {
@@ -173,27 +176,54 @@ __device__ __forceinline__ void select_stream(int s, int V, int CS, const float*
       cf[p * K + j] = okc ? h * V + idx : -1;
     }
   }
+  K2B_SUB(9);
   float my_v = -INFINITY;
   int my_f = -1;
+  if constexpr (NP * K <= 4) {
+    // few candidates per lane: sort them once (value, then flat index, best first); a round is then two REDUX and a pop
+#define K2B_CE2(x, y)                                                                      \
+  do {                                                                                     \
+    const bool sw = (ck[y] > ck[x]) | ((ck[y] == ck[x]) & (cf[y] > cf[x]));                \
+    const int k_ = sw ? ck[y] : ck[x], f_ = sw ? cf[y] : cf[x];                            \
+    ck[y] = sw ? ck[x] : ck[y]; cf[y] = sw ? cf[x] : cf[y];                                \
+    ck[x] = k_; cf[x] = f_;                                                                \
+  } while (0)
+    if constexpr (NP * K == 4) { K2B_CE2(0, 1); K2B_CE2(2, 3); K2B_CE2(0, 2); K2B_CE2(1, 3); K2B_CE2(1, 2); }
+    if constexpr (NP * K == 2) { K2B_CE2(0, 1); }
+#undef K2B_CE2
 #pragma unroll
-  for (int r = 0; r < K; ++r) {
-    int bk = ck[0], bf = cf[0];
+    for (int r = 0; r < K; ++r) {
+      const int wk = __reduce_max_sync(full, ck[0]);
+      const int wf = __reduce_max_sync(full, (ck[0] == wk) ? cf[0] : -1);
+      const bool pop = (cf[0] == wf) & (wf >= 0);
 #pragma unroll
-    for (int i = 1; i < NP * K; ++i) {                      // predicated selects, no divergent branches
-      const bool b = (ck[i] > bk) | ((ck[i] == bk) & (cf[i] > bf));
-      bk = b ? ck[i] : bk; bf = b ? cf[i] : bf;
+      for (int i = 0; i + 1 < NP * K; ++i) { ck[i] = pop ? ck[i + 1] : ck[i]; cf[i] = pop ? cf[i + 1] : cf[i]; }
+      ck[NP * K - 1] = pop ? kKeyNone : ck[NP * K - 1]; cf[NP * K - 1] = pop ? -1 : cf[NP * K - 1];
+      my_v = (lane == r) ? funkey(wk) : my_v;
+      my_f = (lane == r) ? wf : my_f;
     }
-    const int wk = __reduce_max_sync(full, bk);
-    const int wf = __reduce_max_sync(full, (bk == wk) ? bf : -1);
+  } else {
 #pragma unroll
-    for (int i = 0; i < NP * K; ++i) {
-      const bool hit = (cf[i] == wf) & (wf >= 0);
-      cf[i] = hit ? -1 : cf[i]; ck[i] = hit ? kKeyNone : ck[i];
+    for (int r = 0; r < K; ++r) {
+      int bk = ck[0], bf = cf[0];
+#pragma unroll
+      for (int i = 1; i < NP * K; ++i) {                      // predicated selects, no divergent branches
+        const bool b = (ck[i] > bk) | ((ck[i] == bk) & (cf[i] > bf));
+        bk = b ? ck[i] : bk; bf = b ? cf[i] : bf;
+      }
+      const int wk = __reduce_max_sync(full, bk);
+      const int wf = __reduce_max_sync(full, (bk == wk) ? bf : -1);
+#pragma unroll
+      for (int i = 0; i < NP * K; ++i) {
+        const bool hit = (cf[i] == wf) & (wf >= 0);
+        cf[i] = hit ? -1 : cf[i]; ck[i] = hit ? kKeyNone : ck[i];
+      }
+      my_v = (lane == r) ? funkey(wk) : my_v;
+      my_f = (lane == r) ? wf : my_f;
     }
-    my_v = (lane == r) ? funkey(wk) : my_v;
-    my_f = (lane == r) ? wf : my_f;
   }
 
+  K2B_SUB(10);
   // ---- lanes 0..K-1 hold the winners, best first -------------------------------------------------------------
   const bool cand = lane < K && my_f >= 0;
   int par = 0, tok = -1, c0 = -1, c1 = blank, ln = 2;
@@ -211,6 +241,7 @@ __device__ __forceinline__ void select_stream(int s, int V, int CS, const float*
     }
   }
   __syncwarp();
+  K2B_SUB(11);
   // scratch row q: {hash lo, hash hi, length (negative = no candidate), ctx0 | ctx1, score, root, -, -}
   uint4* scr4 = reinterpret_cast<uint4*>(scr);
   if (lane < K) {
@@ -227,6 +258,7 @@ __device__ __forceinline__ void select_stream(int s, int V, int CS, const float*
                     (u.w == (uint32_t)c0) & (uc1 == (uint32_t)c1);
     root = eq ? q : root;
   }
+  K2B_SUB(12);
   float lp = my_v;
   const unsigned merged = __ballot_sync(full, cand && root != lane);
   if (merged) {                      // log-add merged scores into their root, in insertion (rank) order
@@ -239,6 +271,7 @@ __device__ __forceinline__ void select_stream(int s, int V, int CS, const float*
       if (cand && ((merged >> q) & 1u) && qroot == lane) lp = logaddexp_c(lp, qv);
     }
   }
+  K2B_SUB(13);
   const bool is_root = cand && root == lane;
   const unsigned roots = __ballot_sync(full, is_root);
   const int nnew = __popc(roots);
@@ -255,6 +288,8 @@ __device__ __forceinline__ void select_stream(int s, int V, int CS, const float*
   }
   if (lane == 0) out.nlive[s] = nnew;
   __syncwarp();                       // the scratch is reused by this warp's next stream
+  K2B_SUB(14);
+#undef K2B_SUB
 }
 
 // Warp roles: warps 0..15 build the joiner operand (two hypothesis rows each), read the accumulator out, reduce and merge;
@@ -428,15 +463,21 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
         }
         const float4* pd0 = reinterpret_cast<const float4*>(a.dec_tab + (((size_t)(sc.ctx0[n0] + 1) * V + sc.ctx1[n0]) & rm) * J);
         const float4* pd1 = reinterpret_cast<const float4*>(a.dec_tab + (((size_t)(sc.ctx0[n0 + 1] + 1) * V + sc.ctx1[n0 + 1]) & rm) * J);
+        // fence.proxy.async waits for every outstanding load of the thread (MEMBAR.ALL.CTA), so only the first quarter's
+        // decoder-row loads are issued before the first fence: the tensor pipe starts after one L2 round trip for 1/4 of
+        // the rows, and the other three quarters' loads (issued right after that fence) land while it works
         float4 d0[4], d1[4];
+        if (lane < nq) { d0[0] = __ldg(pd0 + lane); d1[0] = __ldg(pd1 + lane); }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int q = lane + 32 * i;
-          if (q < nq) { d0[i] = __ldg(pd0 + q); d1[i] = __ldg(pd1 + q); }
-        }
+          if (i == 1) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int q = lane + 32 * i;
+            for (int i2 = 1; i2 < 4; ++i2) {
+              const int q2 = lane + 32 * i2;
+              if (q2 < nq) { d0[i2] = __ldg(pd0 + q2); d1[i2] = __ldg(pd1 + q2); }
+            }
+          }
           if (q < nq) {
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
@@ -461,7 +502,7 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_q[i]);
           __syncwarp();                      // reconverge: without it the compiler may leave lane 0 split off for the rest of the step
-          K2B_PHASE(14 + i);
+          K2B_PHASE(15 + i);
         }
         if (t + 1 < T) {
           const float4* pe = enc_row + (size_t)(t + 1) * nq;
@@ -590,7 +631,7 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
           const int g = cluster * S + s;
           int32_t* bp_row = (rank == 0 && g < a.B) ? a.bp + ((size_t)g * a.Ttot + a.t0 + t) * K : nullptr;
           select_stream<K>(s, V, CS, xw, st[cur], st[cur ^ 1], a.blank, a.unk, a.extra_mask, bp_row, lane, a.dec_tab, J,
-                           (a.dbg & 2) == 0 && (int)rank == (s % CS), sel_scr[warp]);
+                           (a.dbg & 2) == 0 && (int)rank == (s % CS), sel_scr[warp], (TIMED && timed) ? tph : nullptr);
         }
       }
       K2B_PHASE(6);
