@@ -35,6 +35,9 @@ namespace K2TransducerAsr.B200
         [DllImport(Lib)] public static extern int k2b_encoder_proj(IntPtr h, float[] raw, int n, [Out] float[] outp);
 
         // fused: 1:1 with the Forward* delegates
+        // per-stream frame counts (EncoderOutputEntity.encoder_out_lens, which the stock search loops never read) for the next
+        // k2b_greedy_offline (SINGLE / PER_STREAM) or k2b_modified_beam_search call
+        [DllImport(Lib)] public static extern int k2b_set_encoder_out_lens(IntPtr h, long[]? lens, int B);
         [DllImport(Lib)] public static extern int k2b_greedy_offline(IntPtr h, float[] enc, int enc_is_raw, int B, int T, int mode,
             [Out] long[] tokens, [Out] int[] ts, [Out] int[] n_out, int cap);
         [DllImport(Lib)] public static extern int k2b_greedy_online_chunk(IntPtr h, float[] enc, int enc_is_raw, int B, int Tc,

@@ -133,6 +133,14 @@ K2B_API int32_t k2b_encoder_proj_dev(k2b_handle* h, const float* raw, int32_t n,
  * `enc` is [B,T,J] already projected when enc_is_raw == 0, or raw [B,T,E] (then encoder_proj
  * runs first, on device) when enc_is_raw != 0.                                                  */
 
+/* Ragged batches. The reference carries `encoder_out_lens` through its seam (ref Model/EncoderOutputEntity.cs:10-20,
+ * OfflineProjOfTransducer.cs:84) but never consumes it: padded frames are decoded like speech (Q7). This call hands the
+ * per-stream frame counts (HOST pointer, [B], each 0..T) to the NEXT k2b_greedy_offline[_dev] (modes SINGLE / PER_STREAM)
+ * or k2b_modified_beam_search[_dev] call of this handle; stream b is then decoded over frames [0, lens[b]) only, its
+ * hypotheses frozen afterwards. The setting is consumed by that call. lens == NULL clears it. BATCH_COMPAT greedy (the
+ * reference's own loop, which couples the streams of a batch) rejects it with K2B_ERR_UNSUPPORTED.                  */
+K2B_API int32_t k2b_set_encoder_out_lens(k2b_handle* h, const int64_t* lens, int32_t B);
+
 /* replaces: ForwardGreedySearch / ForwardBatchGreedySearch (ref OfflineRecognizer.cs:93-303).
  * ts = frame index t (ref :164, :271).                                                          */
 K2B_API int32_t k2b_greedy_offline(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t T,

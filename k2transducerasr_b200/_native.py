@@ -57,6 +57,7 @@ _SIGS = {
     "k2b_joiner_proj_dev": (C.c_int32, [_P, _P, _P, _I, _P]),
     "k2b_encoder_proj": (C.c_int32, [_P, _P, _I, _P]),
     "k2b_encoder_proj_dev": (C.c_int32, [_P, _P, _I, _P]),
+    "k2b_set_encoder_out_lens": (C.c_int32, [_P, _P, _I]),
     "k2b_greedy_offline": (C.c_int32, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _I]),
     "k2b_greedy_offline_dev": (C.c_int32, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _I]),
     "k2b_greedy_online_chunk": (C.c_int32, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _I]),
@@ -239,10 +240,20 @@ class Handle:
     def _unpack(tokens, ts, n):
         return [tokens[b, :n[b]].tolist() for b in range(len(n))], [ts[b, :n[b]].tolist() for b in range(len(n))]
 
-    def greedy_offline(self, enc: np.ndarray, mode: int, enc_is_raw: Optional[bool] = None):
+    def set_encoder_out_lens(self, lens: Optional[Sequence[int]]):
+        """Per-stream frame counts (the seam's `encoder_out_lens`) for the NEXT greedy_offline / modified_beam_search call."""
+        if lens is None:
+            self._check(self._lib.k2b_set_encoder_out_lens(self._h, None, 0))
+            return
+        v = np.ascontiguousarray(lens, dtype=np.int64)
+        self._check(self._lib.k2b_set_encoder_out_lens(self._h, _ptr(v), int(v.size)))
+
+    def greedy_offline(self, enc: np.ndarray, mode: int, enc_is_raw: Optional[bool] = None, lens: Optional[Sequence[int]] = None):
         enc, B, T, raw = self._frames(enc)
         if enc_is_raw is not None:
             raw = int(enc_is_raw)
+        if lens is not None:
+            self.set_encoder_out_lens(lens)
         cap = max(T, 1)
         tokens = np.zeros((B, cap), np.int64); ts = np.zeros((B, cap), np.int32); n = np.zeros(B, np.int32)
         self._check(self._lib.k2b_greedy_offline(self._h, _ptr(enc), raw, B, T, mode, _ptr(tokens), _ptr(ts), _ptr(n), cap))
@@ -260,10 +271,13 @@ class Handle:
         toks, tss = self._unpack(tokens, ts, n)
         return toks, tss, hyp
 
-    def modified_beam_search(self, enc: np.ndarray, beam: int = 4, enc_is_raw: Optional[bool] = None):
+    def modified_beam_search(self, enc: np.ndarray, beam: int = 4, enc_is_raw: Optional[bool] = None,
+                             lens: Optional[Sequence[int]] = None):
         enc, B, T, raw = self._frames(enc)
         if enc_is_raw is not None:
             raw = int(enc_is_raw)
+        if lens is not None:
+            self.set_encoder_out_lens(lens)
         cap = max(T, 1)
         tokens = np.zeros((B, cap), np.int64); ts = np.zeros((B, cap), np.int32); n = np.zeros(B, np.int32)
         score = np.zeros(B, np.float32)

@@ -3,6 +3,8 @@
 #include <string.h>
 
 #include <mutex>
+#include <string>
+#include <vector>
 
 #include "k2b_internal.h"
 
@@ -294,6 +296,7 @@ int32_t k2b_destroy(k2b_handle* h) {
   float** ws[] = {&h->emb, &h->conv_w, &h->dec_w, &h->dec_b, &h->enc_w, &h->enc_b, &h->out_w, &h->out_b, &h->tab0, &h->tab1};
   for (float** p : ws) { if (*p) cudaFree(*p); *p = nullptr; }
   free_cluster_assets(h);
+  if (h->lens_dev) cudaFree(h->lens_dev);
   if (h->cluster_timing) cudaFree(h->cluster_timing);
   if (h->dev_status) cudaFree(h->dev_status);
   for (int i = 0; i < 2; ++i) { if (h->ev_ready[i]) cudaEventDestroy(h->ev_ready[i]); if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]); }
@@ -504,13 +507,56 @@ int32_t k2b_encoder_proj(k2b_handle* h, const float* raw, int32_t n, float* out)
   return K2B_OK;
 }
 
+// ---- ragged batches -----------------------------------------------------------------------------------
+// The per-stream frame counts set by k2b_set_encoder_out_lens are consumed by the next fused offline search call.
+namespace {
+struct LensGuard {
+  k2b_handle* h;
+  explicit LensGuard(k2b_handle* hh) : h(hh) {}
+  ~LensGuard() { if (h != nullptr) h->lens_active = false; }
+};
+int32_t check_lens(k2b_handle* h, int B, const char* who) {
+  if (h->lens_active && h->lens_n != B) {
+    return fail(h, K2B_ERR_INVALID, std::string(who) + ": k2b_set_encoder_out_lens was given " + std::to_string(h->lens_n) +
+                                        " streams, this call has " + std::to_string(B));
+  }
+  return K2B_OK;
+}
+}  // namespace
+
+int32_t k2b_set_encoder_out_lens(k2b_handle* h, const int64_t* lens, int32_t B) {
+  K2B_TRY(enter(h));
+  h->lens_active = false;
+  if (lens == nullptr || B <= 0) return K2B_OK;
+  std::vector<int32_t> v((size_t)B);
+  for (int32_t b = 0; b < B; ++b) {
+    if (lens[b] < 0 || lens[b] > 0x7fffffff) return fail(h, K2B_ERR_INVALID, "k2b_set_encoder_out_lens: negative or oversized length");
+    v[(size_t)b] = (int32_t)lens[b];
+  }
+  if (h->lens_n < B || h->lens_dev == nullptr) {
+    if (h->lens_dev) cudaFree(h->lens_dev);
+    h->lens_dev = nullptr;
+    K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->lens_dev), sizeof(int32_t) * (size_t)B));
+  }
+  // synchronous on purpose: `v` is pageable and goes out of scope; earlier searches that still read the buffer finish first
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  K2B_CUDA(h, cudaMemcpy(h->lens_dev, v.data(), sizeof(int32_t) * (size_t)B, cudaMemcpyHostToDevice));
+  h->lens_n = B;
+  h->lens_active = true;
+  return K2B_OK;
+}
+
 // ---- fused search ---------------------------------------------------------------------------------
 int32_t k2b_greedy_offline_dev(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t T, int32_t mode,
                                int64_t* tokens, int32_t* ts, int32_t* n_out, int32_t cap) {
   K2B_TRY(enter(h));
   K2B_TRY(need_weights(h));
+  LensGuard lens_guard(h);
   K2B_TRY(check_search_args(h, enc, B, T, cap, tokens, ts, n_out, "k2b_greedy_offline"));
+  K2B_TRY(check_lens(h, B, "k2b_greedy_offline"));
   if (mode < K2B_GREEDY_SINGLE || mode > K2B_GREEDY_PER_STREAM) return fail(h, K2B_ERR_INVALID, "k2b_greedy_offline: unknown mode");
+  if (h->lens_active && mode == K2B_GREEDY_BATCH_COMPAT)
+    return fail(h, K2B_ERR_UNSUPPORTED, "k2b_greedy_offline: BATCH_COMPAT decodes the padding like the reference (Q7); use PER_STREAM with lengths");
   if (mode == K2B_GREEDY_SINGLE && B != 1) return fail(h, K2B_ERR_INVALID, "k2b_greedy_offline: SINGLE mode needs B == 1");
   if (B == 0) return K2B_OK;
   // greedy search == beam 1 with the same tie rule: SINGLE / PER_STREAM run on the persistent cluster kernel in the tcgen05
@@ -526,6 +572,7 @@ int32_t k2b_greedy_offline_dev(k2b_handle* h, const float* enc, int32_t enc_is_r
 int32_t k2b_greedy_offline(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t T, int32_t mode,
                            int64_t* tokens, int32_t* ts, int32_t* n_out, int32_t cap) {
   K2B_TRY(enter(h));
+  LensGuard lens_guard(h);
   K2B_TRY(need_weights(h));
   K2B_TRY(check_search_args(h, enc, B, T, cap, tokens, ts, n_out, "k2b_greedy_offline"));
   if (B == 0) return K2B_OK;
@@ -590,7 +637,9 @@ int32_t k2b_modified_beam_search_dev(k2b_handle* h, const float* enc, int32_t en
                                      int64_t* tokens, int32_t* ts, int32_t* n_out, float* score, int32_t cap) {
   K2B_TRY(enter(h));
   K2B_TRY(need_weights(h));
+  LensGuard lens_guard(h);
   K2B_TRY(check_search_args(h, enc, B, T, cap, tokens, ts, n_out, "k2b_modified_beam_search"));
+  K2B_TRY(check_lens(h, B, "k2b_modified_beam_search"));
   if (K < 1 || K > kMaxBeam) return fail(h, K2B_ERR_INVALID, "k2b_modified_beam_search: beam must be in 1..8");
   if (K > h->cfg.vocab_size) return fail(h, K2B_ERR_INVALID, "k2b_modified_beam_search: beam exceeds vocab_size");
   if (B > 0 && score == nullptr) return fail(h, K2B_ERR_INVALID, "k2b_modified_beam_search: score is NULL");
@@ -605,8 +654,10 @@ int32_t k2b_modified_beam_search_dev(k2b_handle* h, const float* enc, int32_t en
 int32_t k2b_modified_beam_search(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t T, int32_t K,
                                  int64_t* tokens, int32_t* ts, int32_t* n_out, float* score, int32_t cap) {
   K2B_TRY(enter(h));
+  LensGuard lens_guard(h);
   K2B_TRY(need_weights(h));
   K2B_TRY(check_search_args(h, enc, B, T, cap, tokens, ts, n_out, "k2b_modified_beam_search"));
+  K2B_TRY(check_lens(h, B, "k2b_modified_beam_search"));
   if (B > 0 && score == nullptr) return fail(h, K2B_ERR_INVALID, "k2b_modified_beam_search: score is NULL");
   if (B == 0) return K2B_OK;
   const size_t width = enc_is_raw ? h->cfg.encoder_dim : h->cfg.joiner_dim;

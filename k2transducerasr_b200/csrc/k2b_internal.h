@@ -93,6 +93,9 @@ struct k2b_handle {
   long long* cluster_timing = nullptr;   // device [8]: per-phase cycle totals of the cluster kernel (diagnostic)
 
   bool profile_on = false;
+  int32_t* lens_dev = nullptr;    // k2b_set_encoder_out_lens: per-stream frame counts for the next fused offline search
+  int lens_n = 0;
+  bool lens_active = false;
   k2b::ProfEvents prof;
 };
 

@@ -53,9 +53,10 @@ __global__ void greedy_select_kernel(int B, int nt, const float* __restrict__ pv
                                      const int32_t* __restrict__ pnan, int32_t* __restrict__ ctx,
                                      int64_t* __restrict__ tokens, int32_t* __restrict__ ts, int32_t* __restrict__ n_out,
                                      int cap, int t, int blank, int unk, int extra_mask, int max_sym,
-                                     int32_t* __restrict__ flag) {
+                                     int32_t* __restrict__ flag, const int32_t* __restrict__ lens) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
+  if (lens != nullptr && t >= lens[b]) return;      // ragged batch: this stream has ended
   float bv = 0.f;
   int bi = -1, bn = 0;
   for (int i = 0; i < nt; ++i) {
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(128)
 beam_select_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
                    const float* __restrict__ part_m, const float* __restrict__ part_s,
                    const float* __restrict__ part_tv, const int32_t* __restrict__ part_ti,
-                   BeamState in, BeamState out, int32_t* __restrict__ bp) {
+                   BeamState in, BeamState out, int32_t* __restrict__ bp, const int32_t* __restrict__ lens) {
   __shared__ float s_mx[4][kMaxBeam], s_ls[4][kMaxBeam], s_lp[4][kMaxBeam];
   constexpr int kNone = (int)0x80000000;
   const unsigned full = 0xffffffffu;
@@ -135,6 +136,16 @@ beam_select_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk
   const int s = blockIdx.x * 4 + wib;
   if (s >= B) return;
   const int nl = in.nlive[s];
+  if (lens != nullptr && t >= lens[s]) {            // ragged batch: past the end of this stream, the hypotheses are frozen
+    if (lane < K) {
+      const size_t o = (size_t)s * K + lane;
+      out.ctx[2 * o] = in.ctx[2 * o]; out.ctx[2 * o + 1] = in.ctx[2 * o + 1];
+      out.lp[o] = in.lp[o]; out.len[o] = in.len[o]; out.hash[o] = in.hash[o];
+      bp[((size_t)s * T + t) * K + lane] = lane < nl ? (lane << 28) : 0;
+    }
+    if (lane == 0) out.nlive[s] = nl;
+    return;
+  }
 
   // log_softmax constants. Every (hypothesis, tile) pair is one work item, lane-strided, with all loads of a batch of four
   // items in flight at once (the partials sit in L2 / HBM: latency, not bandwidth, is what this kernel pays for):
@@ -434,7 +445,8 @@ int32_t greedy_dev(k2b_handle* h, const float* enc, int B, int T, int mode, bool
     prof_end(h);
 
     greedy_select_kernel<<<gb, tb, 0, h->stream>>>(B, nt, pval, pidx, pnan, ctx, tokens, ts, n_out, cap, t, c.blank_id,
-                                                   c.unk_id, extra_mask, max_sym, flag);
+                                                   c.unk_id, extra_mask, max_sym, flag,
+                                                   (!online && h->lens_active) ? h->lens_dev : nullptr);
     K2B_LAUNCH_CHECK(h);
   }
   if (online) {
@@ -491,7 +503,8 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
     prof_end(h);
 
     beam_select_kernel<<<(B + 3) / 4, 128, 0, h->stream>>>(B, K, V, nt, T, t, c.blank_id, c.unk_id, part_m, part_s,
-                                                          part_tv, part_ti, st[cur], st[cur ^ 1], bp);
+                                                          part_tv, part_ti, st[cur], st[cur ^ 1], bp,
+                                                          h->lens_active ? h->lens_dev : nullptr);
     K2B_LAUNCH_CHECK(h);
     cur ^= 1;
   }

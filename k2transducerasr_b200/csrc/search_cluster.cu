@@ -65,6 +65,7 @@ struct ClusterArgs {
   int* status;
   long long* timing;        // optional [8] cycle totals of the step phases (cluster 0, CTA 0, thread 0)
   int dbg;                  // experiment switches (K2B_DBG), 0 in production
+  const int32_t* lens;      // [B] frames to decode per stream (k2b_set_encoder_out_lens), or null = all T
 };
 
 __device__ __forceinline__ bool better_c(float v, int i, float ev, int ei) { return v > ev || (v == ev && i > ei); }
@@ -630,6 +631,18 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
         for (int s = warp; s < S; s += kWorkers) {
           const int g = cluster * S + s;
           int32_t* bp_row = (rank == 0 && g < a.B) ? a.bp + ((size_t)g * a.Ttot + a.t0 + t) * K : nullptr;
+          if (a.lens != nullptr && g < a.B && a.t0 + t >= a.lens[g]) {
+            // past the end of this stream (ragged batch): the hypotheses stay as they are, the back-pointers are the identity
+            if (lane < K) {
+              const int o = s * K + lane;
+              st[cur ^ 1].ctx0[o] = st[cur].ctx0[o]; st[cur ^ 1].ctx1[o] = st[cur].ctx1[o]; st[cur ^ 1].lp[o] = st[cur].lp[o];
+              st[cur ^ 1].len[o] = st[cur].len[o]; st[cur ^ 1].hash[o] = st[cur].hash[o];
+              if (bp_row != nullptr) bp_row[lane] = lane < st[cur].nlive[s] ? (lane << 28) : 0;
+            }
+            if (lane == 0) st[cur ^ 1].nlive[s] = st[cur].nlive[s];
+            __syncwarp();
+            continue;
+          }
           select_stream<K>(s, V, CS, xw, st[cur], st[cur ^ 1], a.blank, a.unk, a.extra_mask, bp_row, lane, a.dec_tab, J,
                            (a.dbg & 2) == 0 && (int)rank == (s % CS), sel_scr[warp], (TIMED && timed) ? tph : nullptr);
         }
@@ -801,6 +814,7 @@ int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, 
   a.extra_mask = extra_mask; a.hyp_in = hyp_in; a.hyp_out = hyp_out;
   a.t0 = t0; a.Ttot = Ttot > 0 ? Ttot : T; a.resume = resume; a.io_ctx = io_ctx; a.io_hash = io_hash;
   a.timing = h->cluster_timing;
+  a.lens = h->lens_active ? h->lens_dev : nullptr;
   { const char* de = getenv("K2B_DBG"); a.dbg = de ? atoi(de) : 0; }
   a.bp = bp; a.fin_lp = fin_lp; a.fin_len = fin_len; a.fin_nlive = fin_nlive; a.status = status;
   const size_t dyn = cluster_dyn_smem(J, CS, K);

@@ -440,3 +440,15 @@ def modified_beam_search(m: Model, enc: np.ndarray, beam: int = 4) -> List[Strea
         out.append(StreamResult(tokens=h.ys, timestamps=h.ts, appended=h.ys[m.context_size:], score=float(h.lp),
                                 min_gap=float(gap[b])))
     return out
+
+
+def ragged(search, m: Model, enc: np.ndarray, lens: Sequence[int], *args, **kw) -> List[StreamResult]:
+    """Ragged batch = every stream decoded alone over its own frames [0, lens[b]) (streams are independent in
+    modified_beam_search and in the per-stream greedy loop, ref OfflineRecognizer.cs:93-187). The reference itself never
+    consumes encoder_out_lens (ref OfflineProjOfTransducer.cs:84, Q7: padding is decoded like speech); this is the
+    semantics of k2b_set_encoder_out_lens. `search` is modified_beam_search or greedy_search_batch (compat=False)."""
+    enc = np.asarray(enc, F32)
+    out: List[StreamResult] = []
+    for b, n in enumerate(lens):
+        out.extend(search(m, enc[b:b + 1, :int(n)], *args, **kw))
+    return out

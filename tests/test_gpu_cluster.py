@@ -169,14 +169,37 @@ def test_cluster_online_masks_id_1(setup):
     h.close()
 
 
-def test_two_group_variant_matches(setup, monkeypatch):
+@pytest.mark.parametrize("prec", ["bf16x3", "fp32"])
+def test_ragged_lengths_freeze_streams(setup, prec):
+    """k2b_set_encoder_out_lens (the seam's encoder_out_lens, which the reference never consumes): stream b is decoded over its
+    first lens[b] frames only - both engines (persistent cluster kernel, per-frame kernels), beam search and per-stream greedy,
+    lengths 0 and T included; the setting is consumed by one call."""
     m, w, raw, enc = setup
-    h = make(MID, w, "bf16x3")
-    t1, s1, sc1 = h.modified_beam_search(raw, 4)
-    monkeypatch.setenv("K2B_CLUSTER_GROUPS", "2")
-    t2, s2, sc2 = h.modified_beam_search(raw, 4)
-    assert t1 == t2 and s1 == s2
-    np.testing.assert_allclose(sc1, sc2, atol=1e-4)
+    h = make(MID, w, prec)
+    B, T = 11, 24
+    lens = [24, 0, 5, 17, 1, 24, 9, 13, 2, 20, 7]
+    want = O.ragged(O.modified_beam_search, m, enc[:B, :T], lens, 4)
+    t, s, sc = h.modified_beam_search(raw[:B, :T], 4, lens=lens)
+    ex = compare_streams(t, s, want, f"ragged mbs {prec}", allow_frac=0.3)
+    for b, r in enumerate(want):
+        if b not in ex:
+            assert abs(float(sc[b]) - r.score) < SCORE_TOL
+        assert all(x < lens[b] for x in s[b])
+    t2, s2, _ = h.modified_beam_search(raw[:B, :T], 4)               # consumed: the next call decodes all T frames
+    full = O.modified_beam_search(m, enc[:B, :T], 4)
+    compare_streams(t2, s2, full, f"after ragged {prec}", allow_frac=0.3)
+    wantg = O.ragged(O.greedy_search_batch, m, enc[:B, :T], lens, compat=False)
+    t, s = h.greedy_offline(raw[:B, :T], _native.GREEDY_PER_STREAM, lens=lens)
+    compare_streams(t, s, wantg, f"ragged greedy {prec}", allow_frac=0.3)
+    if prec == "bf16x3":            # T >= 32 raw frames: the time-chunk pipelined host call (lengths cross chunk boundaries)
+        lens40 = [40, 0, 5, 17, 31, 10, 9, 33, 2, 20, 11]
+        want = O.ragged(O.modified_beam_search, m, enc[:B, :40], lens40, 4)
+        t, s, sc = h.modified_beam_search(raw[:B, :40], 4, lens=lens40)
+        compare_streams(t, s, want, "ragged mbs pipelined", allow_frac=0.3)
+    with pytest.raises(_native.K2bError):
+        h.greedy_offline(raw[:B, :T], _native.GREEDY_BATCH_COMPAT, lens=lens)      # the reference's coupled loop decodes padding
+    with pytest.raises(_native.K2bError):
+        h.modified_beam_search(raw[:B - 1, :T], 4, lens=lens)                       # stream count mismatch
     h.close()
 
 
