@@ -187,6 +187,9 @@ K2B_API int32_t k2b_ctc_greedy_dev(k2b_handle* h, const float* logp, int32_t B, 
  * TMEM, 3 = bf16 with A resident in TMEM; use_tma != 0 stages A through one bulk TMA copy.          */
 K2B_API int32_t k2b_selftest_umma(k2b_handle* h, const float* A, const float* B, int32_t N, int32_t K,
                                   int32_t mode, int32_t use_tma, float* D);
+/* k2b_selftest_umma2: D[256,N] = bf16(A[256,K]) * bf16(B[N,K])^T through one CTA pair (tcgen05.mma.cta_group::2, B operand split
+ * between the two CTAs, multicast commit); ts != 0 takes A from TMEM. N % 32 == 0, N <= 256; K % 64 == 0, K <= 256.               */
+K2B_API int32_t k2b_selftest_umma2(k2b_handle* h, const float* A, const float* B, int32_t N, int32_t K, int32_t ts, float* D);
 /* k2b_selftest_umma_bench: cycles to issue / complete reps*nkb*4 tcgen05.mma of one flavour
  * (0 SS N=32, 1 SS N=64, 2 TS N=32, 3 TS N=64, 4 SS M=64 N=32, 5 SS N=128, 6 TS N=128).             */
 K2B_API int32_t k2b_selftest_umma_bench(k2b_handle* h, int32_t flavour, int32_t nkb, int32_t reps,

@@ -67,6 +67,7 @@ _SIGS = {
     "k2b_ctc_greedy": (C.c_int32, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I]),
     "k2b_ctc_greedy_dev": (C.c_int32, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I]),
     "k2b_selftest_umma": (C.c_int32, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "k2b_selftest_umma2": (C.c_int32, [_P, _P, _P, _I, _I, _I, _P]),
     "k2b_cluster_phase_cycles": (C.c_int32, [_P, _P]),
     "k2b_selftest_umma_bench": (C.c_int32, [_P, _I, _I, _I, _P]),
     "k2b_selftest_collectives": (C.c_int32, [_P, _P]),
@@ -312,6 +313,13 @@ class Handle:
         out = np.zeros(20, np.int64)
         self._check(self._lib.k2b_cluster_phase_cycles(self._h, _ptr(out)))
         return out
+
+    def selftest_umma2(self, A: np.ndarray, B: np.ndarray, ts: bool = False) -> np.ndarray:
+        A = np.ascontiguousarray(A, np.float32); B = np.ascontiguousarray(B, np.float32)
+        N, K = B.shape
+        D = np.zeros((256, N), np.float32)
+        self._check(self._lib.k2b_selftest_umma2(self._h, _ptr(A), _ptr(B), N, K, int(ts), _ptr(D)))
+        return D
 
     def selftest_umma_bench(self, flavour: int, nkb: int = 4, reps: int = 8):
         out = np.zeros(2, np.int64)

@@ -129,6 +129,89 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, c
   if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
+// CTA-pair MMA (cta_group::2): D[256,N] = bf16(A[256,K]) * bf16(B[N,K])^T on a cluster of two CTAs. CTA r stages rows
+// 128r.. of A (shared memory, or TMEM with ts != 0) and rows (N/2)r.. of B; the leader issues, both read their own half of D.
+__global__ void __launch_bounds__(128)
+umma2_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, int N, int K, int ts, float* __restrict__ D,
+                      int* __restrict__ status) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int nkb = K / 64, NH = N / 2;
+  uint8_t* a_s = smem;                                   // nkb tiles of 128 x 128 B
+  uint8_t* b_s = a_s + (size_t)nkb * 16384;              // nkb tiles of NH x 128 B
+  __shared__ uint64_t bar_mma, bar_peer;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  if (tid == 0) {
+    mbar_init(&bar_mma, 1);
+    mbar_init(&bar_peer, 1);
+    mbar_fence_init();
+  }
+  cluster_sync();
+  if (warp == 0) tmem_alloc2(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  const uint32_t t_d = tbase, t_a = tbase + 256;
+  const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
+  {
+    const float* row = A + ((size_t)rank * 128 + tid) * K;
+    for (int k0 = 0; k0 < K; k0 += 64) {
+      uint32_t pk[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) pk[j] = pack_bf16x2(bf16_round(row[k0 + 2 * j]), bf16_round(row[k0 + 2 * j + 1]));
+      uint8_t* th = a_s + (size_t)(k0 / 64) * 16384;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) *reinterpret_cast<uint32_t*>(th + sw128_offset(tid, 2 * j)) = pk[j];
+      if (ts) tmem_st32(t_a + lane_base + (uint32_t)(k0 / 2), pk);
+    }
+    if (ts) tmem_st_wait();
+  }
+  if (tid < NH) {
+    const float* row = B + ((size_t)rank * NH + tid) * K;
+    for (int k = 0; k < K; k += 2)
+      *reinterpret_cast<uint32_t*>(b_s + (size_t)(k / 64) * NH * 128 + sw128_offset(tid, k & 63)) =
+          pack_bf16x2(bf16_round(row[k]), bf16_round(row[k + 1]));
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  // the peer tells the leader that its operands are in place (remote arrive, cluster-scope release)
+  if (rank == 1 && tid == 0) mbar_arrive_remote(dsmem_map(smem_u32(&bar_peer), 0));
+  bool ok = true;
+  if (rank == 0 && warp == 0) {
+    if (!mbar_wait_cluster(&bar_peer, 0)) ok = false;
+    tc_fence_after();
+    const uint32_t el = elect_one();
+    const uint32_t idesc = umma_idesc_bf16_f32(256, N);
+    uint32_t acc = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t da = umma_desc_k_sw128(smem_u32(a_s + (size_t)kb * 16384) + k * 32);
+        const uint64_t db = umma_desc_k_sw128(smem_u32(b_s + (size_t)kb * NH * 128) + k * 32);
+        if (ts) umma2_ts_e(t_d, t_a + (uint32_t)((kb * 4 + k) * 8), db, idesc, acc, el);
+        else umma2_ss_e(t_d, da, db, idesc, acc, el);
+        acc = 1;
+      }
+    }
+    umma2_commit_e(&bar_mma, (uint16_t)0x3, el);
+  }
+  if (!mbar_wait(&bar_mma, 0)) ok = false;
+  tc_fence_after();
+  if (!ok) atomicExch(status, 1);
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(t_d + lane_base + (uint32_t)c0, v);
+    tmem_ld_wait();
+    for (int n = 0; n < 32 && c0 + n < N; ++n) D[((size_t)rank * 128 + tid) * N + c0 + n] = __uint_as_float(v[n]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == 0) tmem_dealloc2(tbase, 512);
+}
+
 // MMA timing microbenchmark: `reps` back-to-back k-loops (nkb*4 MMAs each) of one flavour, cycles from first issue to
 // commit completion. flavour 0: SS N=32, 1: SS N=64, 2: TS N=32, 3: TS N=64, 4: SS N=32 with M=64, 5: SS N=128, 6: TS N=128,
 // 7/8/9: SS N=32 rotating over 2/4/8 independent TMEM accumulators, 10: SS N=64 over 4 accumulators
@@ -348,6 +431,36 @@ K2B_API int32_t k2b_selftest_umma(k2b_handle* h, const float* A, const float* B,
 }
 
 // cycles[0] = issue loop, cycles[1] = until the commit barrier flips, for reps*nkb*4 MMAs of the given flavour.
+// D[256,N] through a CTA pair (cta_group::2). N: multiple of 32, <= 256; K: multiple of 64, <= 256. ts != 0: A from TMEM.
+K2B_API int32_t k2b_selftest_umma2(k2b_handle* h, const float* A, const float* B, int32_t N, int32_t K, int32_t ts, float* D) {
+  if (h == nullptr || A == nullptr || B == nullptr || D == nullptr || N < 32 || N > 256 || N % 32 || K < 64 || K > 256 || K % 64)
+    return K2B_ERR_INVALID;
+  K2B_CUDA(h, cudaSetDevice(h->cfg.device));
+  float *dA, *dB, *dD; int* st;
+  K2B_CUDA(h, cudaMalloc(&dA, sizeof(float) * 256 * K));
+  K2B_CUDA(h, cudaMalloc(&dB, sizeof(float) * N * K));
+  K2B_CUDA(h, cudaMalloc(&dD, sizeof(float) * 256 * N));
+  K2B_CUDA(h, cudaMalloc(&st, sizeof(int)));
+  K2B_CUDA(h, cudaMemset(st, 0, sizeof(int)));
+  K2B_CUDA(h, cudaMemcpy(dA, A, sizeof(float) * 256 * K, cudaMemcpyHostToDevice));
+  K2B_CUDA(h, cudaMemcpy(dB, B, sizeof(float) * N * K, cudaMemcpyHostToDevice));
+  const size_t smem = (size_t)(K / 64) * (16384 + (size_t)(N / 2) * 128);
+  K2B_CUDA(h, cudaFuncSetAttribute(umma2_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  K2B_CUDA(h, cudaLaunchKernelEx(&cfg, umma2_selftest_kernel, (const float*)dA, (const float*)dB, (int)N, (int)K, (int)ts, dD, st));
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  int hs = 0;
+  K2B_CUDA(h, cudaMemcpy(&hs, st, sizeof(int), cudaMemcpyDeviceToHost));
+  K2B_CUDA(h, cudaMemcpy(D, dD, sizeof(float) * 256 * N, cudaMemcpyDeviceToHost));
+  cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(st);
+  return hs ? fail(h, K2B_ERR_STATE, "cta_group::2 self-test: an mbarrier wait timed out") : K2B_OK;
+}
+
 K2B_API int32_t k2b_selftest_umma_bench(k2b_handle* h, int32_t flavour, int32_t nkb, int32_t reps, int64_t* cycles2) {
   if (h == nullptr || nkb < 1 || nkb > 6 || reps < 1) return K2B_ERR_INVALID;
   K2B_CUDA(h, cudaSetDevice(h->cfg.device));

@@ -33,9 +33,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded spin: a mis-programmed pipeline must not hang the GPU box (returns false on timeout).
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32_t max_spins = 20000000u) {
+// (about two seconds of SM clock, measured with clock64 so that the hardware-suspended tries count by time, not by number)
+constexpr long long kWaitTimeoutCycles = 4000000000ll;
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
 #pragma unroll 1
-  for (uint32_t i = 0; i < max_spins; ++i)
+  while (clock64() - t0 < kWaitTimeoutCycles)
     if (mbar_try_wait(bar, parity)) return true;
   return false;
 }
@@ -165,6 +169,38 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- CTA pairs (cta_group::2): one MMA spans two CTAs of a cluster (ranks 2i, 2i+1). M = 256: each CTA holds its own 128 rows
+// of A and of the accumulator; the B operand is split by columns - each CTA stages N/2 of its rows at the same shared-memory
+// offset - so a pair builds every B row only once. Only the even ("leader") CTA issues; the commit is multicast to both.
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_ss_e(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                           uint32_t elected) {
+  asm volatile(
+      "{\n .reg .pred p, q;\n setp.ne.b32 p, %4, 0;\n setp.ne.b32 q, %5, 0;\n"
+      " @q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(elected) : "memory");
+}
+__device__ __forceinline__ void umma2_ts_e(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                           uint32_t elected) {
+  asm volatile(
+      "{\n .reg .pred p, q;\n setp.ne.b32 p, %4, 0;\n setp.ne.b32 q, %5, 0;\n"
+      " @q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(elected) : "memory");
+}
+// all previously issued cta_group::2 MMAs of this thread arrive on `bar` (same offset) in every CTA of `cta_mask` when complete
+__device__ __forceinline__ void umma2_commit_e(uint64_t* bar, uint16_t cta_mask, uint32_t elected) {
+  asm volatile(
+      "{\n .reg .pred q;\n setp.ne.b32 q, %2, 0;\n"
+      " @q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n}"
+      ::"r"(smem_u32(bar)), "h"(cta_mask), "r"(elected) : "memory");
+}
+
 // byte offset of element (row, k) inside one K-major SW128 tile of 64 bf16 per row
 __device__ __forceinline__ uint32_t sw128_offset(int row, int k) {
   const int chunk = (k >> 3) ^ (row & 7);
@@ -212,9 +248,11 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ bool mbar_wait_cluster(uint64_t* bar, uint32_t parity, uint32_t max_spins = 20000000u) {
+__device__ __forceinline__ bool mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return true;
+  const long long t0 = clock64();
 #pragma unroll 1
-  for (uint32_t i = 0; i < max_spins; ++i)
+  while (clock64() - t0 < kWaitTimeoutCycles)
     if (mbar_try_wait_cluster(bar, parity)) return true;
   return false;
 }
