@@ -296,11 +296,19 @@ __device__ __forceinline__ void select_stream(int s, int V, int CS, const float*
 // Warp roles: warps 0..15 build the joiner operand (two hypothesis rows each), read the accumulator out, reduce and merge;
 // warp 16 only issues MMAs (as the K-quarters of the operand land) - so the tensor pipe starts on the first quarter while
 // the other three are still being computed.
-template <int K, bool X3, bool TIMED>
+//
+// PAIR (even cluster sizes): the CTAs 2i, 2i+1 of the cluster form a tcgen05 CTA pair (cta_group::2, M = 256 = their two
+// vocabulary slices). The B operand of a pair MMA is split by columns between the two CTAs, so each CTA builds only 16 of
+// the 32 hypothesis rows (one per worker warp): half the decoder-row traffic, half the tanh / split work, half the stores.
+// The even CTA's MMA warp issues for both (its bar_q mbarriers also count the peer's warps, arriving through DSMEM), the
+// commit is multicast to both CTAs' bar_mma; everything after the accumulator read-out is unchanged.
+template <int K, bool X3, bool TIMED, bool PAIR>
 __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
   constexpr int XWP = xw_padded(K);
   constexpr int S = kNH / K;
-  constexpr int kXTile = 64 * 128;       // one k-block of the stacked [x_hi (32 rows); x_lo (32 rows)] operand
+  constexpr int kRowsCta = PAIR ? 16 : 32;            // hypothesis rows this CTA builds
+  constexpr int kXTile = 2 * kRowsCta * 128;          // one k-block of the stacked [x_hi rows; x_lo rows] operand
+  constexpr int RPW = PAIR ? 1 : 2;                   // rows built per worker warp
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ HypState st[2];
   __shared__ float bias_s[128];
@@ -324,16 +332,19 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
   if (tid == 0) {
     mbar_init(&bar_w, 1);
     mbar_init(&bar_mma, 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&bar_q[i], kWorkers);
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_q[i], PAIR ? 2 * kWorkers : kWorkers);
     for (int i = 0; i < 2; ++i) mbar_init(&xbar[i], kWorkers);
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (PAIR) cluster_sync();                       // both CTAs of a pair are resident before the pair-wide TMEM allocation
+  if (warp == 0) { if (PAIR) tmem_alloc2(&tmem_slot, 512); else tmem_alloc(&tmem_slot, 512); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = tmem_slot;
-  const uint32_t t_d = tbase, t_wlo = tbase + 64;
+  // TMEM columns: accumulator 64 | (PAIR: second accumulator 32 for the W_lo product, whose column order differs) | W_lo 256
+  const uint32_t t_d = tbase, t_d2 = tbase + 64, t_wlo = PAIR ? tbase + 128 : tbase + 64;
+  const uint32_t prank = PAIR ? (rank & 1u) : 0u;
   const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
 
   // ---- one-time staging of this CTA's weight slice ------------------------------------------------------
@@ -400,51 +411,64 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
     // D[128 vocab, hyps] = W_slice * x^T. X3: one SS MMA with the stacked operand (N = 64: cols 0-31 = Wh*xh, 32-63 = Wh*xl)
     // + one TS MMA (A = Wl resident in TMEM, N = 32) accumulating Wl*xh into cols 0-31. Warp-uniform loop: the descriptors
     // stay in uniform registers, one elected lane issues.
-    const uint32_t idesc64 = umma_idesc_bf16_f32(128, 64), idesc32 = umma_idesc_bf16_f32(128, 32);
+    const uint32_t idesc64 = umma_idesc_bf16_f32(PAIR ? 256 : 128, 64), idesc32 = umma_idesc_bf16_f32(PAIR ? 256 : 128, 32);
     const uint32_t desc_hi = 64u | (1u << 14) | (2u << 29);
     const uint32_t w_lo0 = ((smem_u32(w_hi) & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t x_lo0 = ((smem_u32(xop) & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t el = elect_one();
-    for (int t = 0; t < T; ++t) {
-      uint32_t acc = 0;
-      for (int qd = 0; qd < 4; ++qd) {
-        if (!mbar_wait(&bar_q[qd], (uint32_t)(t & 1))) ok = false;
-        tc_fence_after();
-        for (int kb = 2 * qd; kb < 2 * qd + 2 && kb < nkb; ++kb) {
+    if (!PAIR || prank == 0) {
+      for (int t = 0; t < T; ++t) {
+        uint32_t acc = 0;
+        for (int qd = 0; qd < 4; ++qd) {
+          if (PAIR) { if (!mbar_wait_cluster(&bar_q[qd], (uint32_t)(t & 1))) ok = false; }
+          else { if (!mbar_wait(&bar_q[qd], (uint32_t)(t & 1))) ok = false; }
+          tc_fence_after();
+          for (int kb = 2 * qd; kb < 2 * qd + 2 && kb < nkb; ++kb) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t dw = ((uint64_t)desc_hi << 32) | (uint64_t)(w_lo0 + (uint32_t)(kb * (16384 >> 4) + k * 2));
-            const uint64_t dx = ((uint64_t)desc_hi << 32) | (uint64_t)(x_lo0 + (uint32_t)(kb * (kXTile >> 4) + k * 2));
-            umma_ss_e(t_d, dw, dx, X3 ? idesc64 : idesc32, acc, el);
-            acc = 1;
-            if (X3) umma_ts_e(t_d, t_wlo + (uint32_t)((kb * 4 + k) * 8), dx, idesc32, 1, el);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t dw = ((uint64_t)desc_hi << 32) | (uint64_t)(w_lo0 + (uint32_t)(kb * (16384 >> 4) + k * 2));
+              const uint64_t dx = ((uint64_t)desc_hi << 32) | (uint64_t)(x_lo0 + (uint32_t)(kb * (kXTile >> 4) + k * 2));
+              if (PAIR) {
+                // pair MMA: columns [0,16) Wh*xh(rows of CTA 0), [16,32) Wh*xl(CTA 0), [32,48) Wh*xh(CTA 1), [48,64) Wh*xl(CTA 1);
+                // the W_lo product (each CTA supplies its 16 hi rows) goes to its own 32 columns
+                umma2_ss_e(t_d, dw, dx, X3 ? idesc64 : idesc32, acc, el);
+                if (X3) umma2_ts_e(t_d2, t_wlo + (uint32_t)((kb * 4 + k) * 8), dx, idesc32, acc, el);
+              } else {
+                umma_ss_e(t_d, dw, dx, X3 ? idesc64 : idesc32, acc, el);
+                if (X3) umma_ts_e(t_d, t_wlo + (uint32_t)((kb * 4 + k) * 8), dx, idesc32, 1, el);
+              }
+              acc = 1;
+            }
           }
         }
+        if (PAIR) umma2_commit_e(&bar_mma, (uint16_t)(3u << (rank & ~1u)), el);
+        else umma_commit_e(&bar_mma, el);
       }
-      umma_commit_e(&bar_mma, el);
     }
   } else {
     // =============================== worker warps ===============================================================
     // the two hypothesis rows of this warp belong to one stream when K is even (two streams for K = 1); the frame rows
     // are prefetched one step ahead
-    constexpr int NE = (K % 2 == 0) ? 1 : 2;
-    const int n0 = warp * 2;
-    int g_w = cluster * S + n0 / K;
+    constexpr int NE = (K % 2 == 0 || PAIR) ? 1 : 2;
+    const int n0 = warp * 2;                                     // hypotheses this warp reduces / exchanges
+    const int nb0 = PAIR ? (int)(16 * prank) + warp : warp * 2;  // first hypothesis row this warp builds (RPW of them)
+    const int lr0 = PAIR ? warp : warp * 2;                      // ... and its row in this CTA's operand tile
+    int g_w = cluster * S + nb0 / K;
     if (g_w >= a.B) g_w = a.B - 1;
     const float4* enc_row = reinterpret_cast<const float4*>(a.encE + ((size_t)g_w * a.Ttot + a.t0) * J);
-    int g_w1 = cluster * S + (n0 + 1) / K;
+    int g_w1 = cluster * S + (nb0 + RPW - 1) / K;
     if (g_w1 >= a.B) g_w1 = a.B - 1;
     const float4* enc_row1 = reinterpret_cast<const float4*>(a.encE + ((size_t)g_w1 * a.Ttot + a.t0) * J);
     float4 ecur[4], ecur1[NE == 2 ? 4 : 1];
-    uint32_t xoff[2][4];           // loop-invariant swizzled byte offsets of this thread's 8 operand chunks (hi rows)
+    uint32_t xoff[RPW][4];         // loop-invariant swizzled byte offsets of this thread's operand chunks (hi rows)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int q = lane + 32 * i;
       if (q < nq) ecur[i] = __ldg(enc_row + q);
       if (NE == 2 && q < nq) ecur1[NE == 2 ? i : 0] = __ldg(enc_row1 + q);
       const int k = 4 * q;
-      xoff[0][i] = (uint32_t)(k >> 6) * kXTile + sw128_offset(n0, k & 63);
-      xoff[1][i] = (uint32_t)(k >> 6) * kXTile + sw128_offset(n0 + 1, k & 63);
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) xoff[r][i] = (uint32_t)(k >> 6) * kXTile + sw128_offset(lr0 + r, k & 63);
     }
     const size_t rm = (a.dbg & 1) ? 0 : ~(size_t)0;
     const int col0 = 8 * (warp >> 2);            // this warp's 8 accumulator columns (hypotheses) in the read-out
@@ -458,17 +482,17 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
       //      K-quarter by K-quarter (each warp arrives on bar_q[i] after its part of quarter i)
       {
         const HypState& sc = st[cur];
-        if ((a.dbg & 4) && warp >= 8) {            // experiment: half of the operand rows only (garbage results, timing only)
-          for (int i = 0; i < 4; ++i) { if (lane == 0) mbar_arrive(&bar_q[i]); }
-          goto build_done;
-        }
-        const float4* pd0 = reinterpret_cast<const float4*>(a.dec_tab + (((size_t)(sc.ctx0[n0] + 1) * V + sc.ctx1[n0]) & rm) * J);
-        const float4* pd1 = reinterpret_cast<const float4*>(a.dec_tab + (((size_t)(sc.ctx0[n0 + 1] + 1) * V + sc.ctx1[n0 + 1]) & rm) * J);
+        const float4* pd[RPW];
+#pragma unroll
+        for (int r = 0; r < RPW; ++r)
+          pd[r] = reinterpret_cast<const float4*>(a.dec_tab + (((size_t)(sc.ctx0[nb0 + r] + 1) * V + sc.ctx1[nb0 + r]) & rm) * J);
         // fence.proxy.async waits for every outstanding load of the thread (MEMBAR.ALL.CTA), so only the first quarter's
         // decoder-row loads are issued before the first fence: the tensor pipe starts after one L2 round trip for 1/4 of
         // the rows, and the other three quarters' loads (issued right after that fence) land while it works
-        float4 d0[4], d1[4];
-        if (lane < nq) { d0[0] = __ldg(pd0 + lane); d1[0] = __ldg(pd1 + lane); }
+        float4 dd[RPW][4];
+#pragma unroll
+        for (int r = 0; r < RPW; ++r)
+          if (lane < nq) dd[r][0] = __ldg(pd[r] + lane);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int q = lane + 32 * i;
@@ -476,13 +500,15 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
 #pragma unroll
             for (int i2 = 1; i2 < 4; ++i2) {
               const int q2 = lane + 32 * i2;
-              if (q2 < nq) { d0[i2] = __ldg(pd0 + q2); d1[i2] = __ldg(pd1 + q2); }
+#pragma unroll
+              for (int r = 0; r < RPW; ++r)
+                if (q2 < nq) dd[r][i2] = __ldg(pd[r] + q2);
             }
           }
           if (q < nq) {
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-              const float4 d = r ? d1[i] : d0[i];
+            for (int r = 0; r < RPW; ++r) {
+              const float4 d = dd[r][i];
               const float4 ev = (NE == 2 && r) ? ecur1[NE == 2 ? i : 0] : ecur[i];
               const float x0 = tanh_from_exp(ev.x, d.x), x1 = tanh_from_exp(ev.y, d.y);
               const float x2 = tanh_from_exp(ev.z, d.z), x3 = tanh_from_exp(ev.w, d.w);
@@ -493,7 +519,7 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
                 *reinterpret_cast<uint2*>(dst) = make_uint2(__byte_perm(b0, b1, 0x7632), __byte_perm(b2, b3, 0x7632));
                 const float l0 = x0 - __uint_as_float(b0 & 0xffff0000u), l1 = x1 - __uint_as_float(b1 & 0xffff0000u);
                 const float l2 = x2 - __uint_as_float(b2 & 0xffff0000u), l3 = x3 - __uint_as_float(b3 & 0xffff0000u);
-                *reinterpret_cast<uint2*>(dst + 32 * 128) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+                *reinterpret_cast<uint2*>(dst + kRowsCta * 128) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
               } else {
                 *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(x0, x1), pack_bf16x2(x2, x3));
               }
@@ -501,7 +527,10 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
           }
           fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's async proxy
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_q[i]);
+          if (lane == 0) {
+            if (PAIR && prank) mbar_arrive_remote(dsmem_map(smem_u32(&bar_q[i]), rank ^ 1u));   // the pair's leader issues the MMAs
+            else mbar_arrive(&bar_q[i]);
+          }
           __syncwarp();                      // reconverge: without it the compiler may leave lane 0 split off for the rest of the step
           K2B_PHASE(15 + i);
         }
@@ -515,7 +544,6 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
           }
         }
       }
-    build_done:
       K2B_PHASE(0);
 
       // ---- (c) accumulator -> registers (+bias) -> transposed shared tile; every warp reads 8 columns of its lane quarter
@@ -524,14 +552,26 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
       tc_fence_after();
       K2B_PHASE(1);
       {
-        uint32_t va[8], vb[8];
-        tmem_ld8(t_d + lane_base + (uint32_t)col0, va);
-        if (X3) tmem_ld8(t_d + lane_base + (uint32_t)(32 + col0), vb);
+        uint32_t va[8], vb[8], vc[8];
+        if (PAIR) {
+          // hypothesis h = 16 p + j was built by CTA p of the pair: Wh*xh in column 32 p + j, Wh*xl in 32 p + 16 + j, Wl*xh in
+          // column 16 p + j of the second accumulator (without X3: Wh*xh in column 16 p + j)
+          const uint32_t pp = (uint32_t)(col0 >> 4), j0 = (uint32_t)(col0 & 15);
+          tmem_ld8(t_d + lane_base + (X3 ? 32u * pp + j0 : 16u * pp + j0), va);
+          if (X3) {
+            tmem_ld8(t_d + lane_base + 32u * pp + 16u + j0, vb);
+            tmem_ld8(t_d2 + lane_base + 16u * pp + j0, vc);
+          }
+        } else {
+          tmem_ld8(t_d + lane_base + (uint32_t)col0, va);
+          if (X3) tmem_ld8(t_d + lane_base + (uint32_t)(32 + col0), vb);
+        }
         tmem_ld_wait();
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
           float v = __uint_as_float(va[n]) + bsv;
           if (X3) v += __uint_as_float(vb[n]);
+          if (X3 && PAIR) v += __uint_as_float(vc[n]);
           Lt[vrow * kLtStride + col0 + n] = v;
         }
         tc_fence_before();
@@ -676,8 +716,8 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
   if (!ok) atomicExch(a.status, 1);
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tbase, 512);
   cluster_sync();
+  if (warp == 0) { if (PAIR) tmem_dealloc2(tbase, 512); else tmem_dealloc(tbase, 512); }
 }
 
 // ---- weight-load-time packing ----------------------------------------------------------------------------------
@@ -711,11 +751,26 @@ __global__ void exp2x_kernel(const float* __restrict__ in, float* __restrict__ o
 
 }  // namespace
 
-// `timed` selects the instrumented build of the beam-4 kernel (per-phase clock64 totals); production launches never carry it
-static void (*cluster_kernel_for(int K, bool x3, bool timed))(const ClusterArgs) {
-  if (timed && K == 4) return x3 ? cluster_beam_kernel<4, true, true> : cluster_beam_kernel<4, false, true>;
-  if (x3) return K == 1 ? cluster_beam_kernel<1, true, false> : (K == 2 ? cluster_beam_kernel<2, true, false> : (K == 4 ? cluster_beam_kernel<4, true, false> : cluster_beam_kernel<8, true, false>));
-  return K == 1 ? cluster_beam_kernel<1, false, false> : (K == 2 ? cluster_beam_kernel<2, false, false> : (K == 4 ? cluster_beam_kernel<4, false, false> : cluster_beam_kernel<8, false, false>));
+// `timed` selects the instrumented build of the beam-4 kernel (per-phase clock64 totals); production launches never carry it.
+// `pair`: CTA-pair variant (even cluster sizes), opt-in with K2B_PAIR=1: measured on cfg2 it halves the prologue (quarters
+// 1053 + 742 + 368 + 325 cycles against 1169 + 1028 + 474 + 438) but a cta_group::2 MMA at N <= 64 costs ~70 cycles against
+// ~57 for the single-CTA form, so the step gets longer (1449 us per launch against 1383 us).
+template <bool X3, bool PAIR>
+static void (*cluster_kernel_kx(int K))(const ClusterArgs) {
+  return K == 1 ? cluster_beam_kernel<1, X3, false, PAIR> : (K == 2 ? cluster_beam_kernel<2, X3, false, PAIR>
+       : (K == 4 ? cluster_beam_kernel<4, X3, false, PAIR> : cluster_beam_kernel<8, X3, false, PAIR>));
+}
+static void (*cluster_kernel_for(int K, bool x3, bool timed, bool pair))(const ClusterArgs) {
+  if (timed && K == 4) {
+    if (pair) return x3 ? cluster_beam_kernel<4, true, true, true> : cluster_beam_kernel<4, false, true, true>;
+    return x3 ? cluster_beam_kernel<4, true, true, false> : cluster_beam_kernel<4, false, true, false>;
+  }
+  if (pair) return x3 ? cluster_kernel_kx<true, true>(K) : cluster_kernel_kx<false, true>(K);
+  return x3 ? cluster_kernel_kx<true, false>(K) : cluster_kernel_kx<false, false>(K);
+}
+static bool cluster_pair_mode(int CS) {
+  const char* e = getenv("K2B_PAIR");
+  return CS % 2 == 0 && e != nullptr && e[0] == '1';
 }
 
 static size_t cluster_dyn_smem(int J, int CS, int K) {
@@ -739,7 +794,7 @@ bool cluster_path_supported(const k2b_handle* h, int K) {
     k2b_handle* hm = const_cast<k2b_handle*>(h);
     if (hm->cluster16_ok < 0) {
       hm->cluster16_ok = 0;
-      auto kern = cluster_kernel_for(1, c.precision == K2B_PREC_BF16X3, false);
+      auto kern = cluster_kernel_for(1, c.precision == K2B_PREC_BF16X3, false, cluster_pair_mode(CS));
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
           cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) == cudaSuccess) {
         cudaLaunchConfig_t cfg = {};
@@ -818,7 +873,7 @@ int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, 
   { const char* de = getenv("K2B_DBG"); a.dbg = de ? atoi(de) : 0; }
   a.bp = bp; a.fin_lp = fin_lp; a.fin_len = fin_len; a.fin_nlive = fin_nlive; a.status = status;
   const size_t dyn = cluster_dyn_smem(J, CS, K);
-  void (*kern)(const ClusterArgs) = cluster_kernel_for(K, a.x3 != 0, a.timing != nullptr);
+  void (*kern)(const ClusterArgs) = cluster_kernel_for(K, a.x3 != 0, a.timing != nullptr, cluster_pair_mode(CS));
   if (CS > 8) K2B_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   K2B_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   cudaLaunchConfig_t cfg = {};

@@ -169,6 +169,28 @@ def test_cluster_online_masks_id_1(setup):
     h.close()
 
 
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+def test_cta_pair_variant_matches_oracle(setup, monkeypatch, prec):
+    """K2B_PAIR=1: the CTAs 2i, 2i+1 of a cluster issue tcgen05.mma.cta_group::2 (M = 256, the B operand split between them, so
+    each builds 16 of the 32 hypothesis rows). Opt-in (measured slower); must decode like the default kernel."""
+    m, w, raw, enc = setup
+    monkeypatch.setenv("K2B_PAIR", "1")
+    h = make(MID, w, prec)
+    if prec == "bf16x3":
+        mo, want_enc = m, enc
+    else:
+        mo = O.Model.from_dict(w, prec_joiner="bf16", prec_enc="bf16")
+        want_enc = O.encoder_proj(mo, raw)
+    for beam in (4, 1, 8):
+        want = O.modified_beam_search(mo, want_enc, beam)
+        t, s, sc = h.modified_beam_search(raw, beam)
+        ex = compare_streams(t, s, want, f"pair {prec} beam={beam}", allow_frac=0.3)
+        for b, r in enumerate(want):
+            if b not in ex:
+                assert abs(float(sc[b]) - r.score) < (SCORE_TOL if prec == "bf16x3" else 5e-3)
+    h.close()
+
+
 @pytest.mark.parametrize("prec", ["bf16x3", "fp32"])
 def test_ragged_lengths_freeze_streams(setup, prec):
     """k2b_set_encoder_out_lens (the seam's encoder_out_lens, which the reference never consumes): stream b is decoded over its
