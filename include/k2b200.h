@@ -180,6 +180,24 @@ K2B_API int32_t k2b_ctc_greedy_dev(k2b_handle* h, const float* logp, int32_t B, 
                            const int32_t* frame_offset, int64_t* prev_inout, int64_t* tokens, int32_t* ts,
                            int32_t* n_out, int32_t* trailing_blank_inout, int32_t cap);
 
+/* ---- on-device streaming state (the step either side of the online path) ---------------------- */
+/* replaces: stack_states / unstack_states (ref OnlineProjOfZipformer2.cs:144-362, :363-489; OnlineProjOfZipformer.cs,
+ * OnlineProjOfLstm.cs and OnlineProjOfConformer.cs hold the same loops), which re-lay the per-stream encoder caches into
+ * batched tensors (batch on axis 1) with Array.Copy before every encoder call and back after it. Here a stream's caches
+ * live concatenated in one slot of a device pool (OnlineStream.States, ref OnlineStream.cs:15) and the re-layout is one
+ * launch. For cache tensor i with per-stream length item_len[i] and "axisnum" A = axis_len[i] (X = item_len/A):
+ *     stacked_i[(x*B + n)*A + a] = slot(slots[n])_i[x*A + a],     stacked_i starts at float B * off_i of `stacked`,
+ * off_i = sum of the lengths before i, each rounded up to 4 floats. axis_len is an argument of BOTH calls because the
+ * reference does not use the same A in both directions for every tensor (cached_nonlin_attn: ref :250 vs :409).
+ * item_len, axis_len, slots, state: HOST pointers; stacked: DEVICE pointer of k2b_state_pool_stacked_floats(h, B) floats. */
+K2B_API int32_t k2b_state_pool_create(k2b_handle* h, const int32_t* item_len, int32_t n_tensors, int32_t max_streams);
+K2B_API int64_t k2b_state_pool_stacked_floats(k2b_handle* h, int32_t B);
+/* upload / download one stream's caches (plain concatenation of the tensors, e.g. from GetEncoderInitStates) */
+K2B_API int32_t k2b_state_pool_put(k2b_handle* h, int32_t slot, const float* state);
+K2B_API int32_t k2b_state_pool_get(k2b_handle* h, int32_t slot, float* state);
+K2B_API int32_t k2b_stack_states(k2b_handle* h, const int32_t* slots, int32_t B, const int32_t* axis_len, float* stacked);
+K2B_API int32_t k2b_unstack_states(k2b_handle* h, const int32_t* slots, int32_t B, const int32_t* axis_len, const float* stacked);
+
 /* ---- diagnostics ---------------------------------------------------------------------------- */
 /* Hardware self-tests of the tcgen05 / TMEM / bulk-TMA / cluster building blocks (HOST pointers).
  * k2b_selftest_umma: D[128,N] = A[128,K] * B[N,K]^T through tcgen05.mma; mode 0 = bf16 operands in

@@ -67,6 +67,12 @@ _SIGS = {
     "k2b_ctc_greedy": (C.c_int32, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I]),
     "k2b_ctc_greedy_dev": (C.c_int32, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I]),
     "k2b_selftest_umma": (C.c_int32, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "k2b_state_pool_create": (C.c_int32, [_P, _P, _I, _I]),
+    "k2b_state_pool_stacked_floats": (C.c_int64, [_P, _I]),
+    "k2b_state_pool_put": (C.c_int32, [_P, _I, _P]),
+    "k2b_state_pool_get": (C.c_int32, [_P, _I, _P]),
+    "k2b_stack_states": (C.c_int32, [_P, _P, _I, _P, _P]),
+    "k2b_unstack_states": (C.c_int32, [_P, _P, _I, _P, _P]),
     "k2b_selftest_umma2": (C.c_int32, [_P, _P, _P, _I, _I, _I, _P]),
     "k2b_cluster_phase_cycles": (C.c_int32, [_P, _P]),
     "k2b_selftest_umma_bench": (C.c_int32, [_P, _I, _I, _I, _P]),
@@ -300,6 +306,33 @@ class Handle:
                                              _ptr(ts), _ptr(n), _ptr(tb), cap))
         toks, tss = self._unpack(tokens, ts, n)
         return toks, tss, tb, pv
+
+    # -- on-device streaming state (stack_states / unstack_states) ------------------------------------------
+    def state_pool_create(self, item_len: Sequence[int], max_streams: int):
+        il = np.ascontiguousarray(item_len, dtype=np.int32)
+        self._check(self._lib.k2b_state_pool_create(self._h, _ptr(il), int(il.size), int(max_streams)))
+        self._pool_len = il.copy()
+
+    def state_pool_stacked_floats(self, B: int) -> int:
+        return int(self._lib.k2b_state_pool_stacked_floats(self._h, int(B)))
+
+    def state_pool_put(self, slot: int, state: np.ndarray):
+        st = np.ascontiguousarray(state, dtype=np.float32)
+        assert st.size == int(self._pool_len.sum())
+        self._check(self._lib.k2b_state_pool_put(self._h, int(slot), _ptr(st)))
+
+    def state_pool_get(self, slot: int) -> np.ndarray:
+        st = np.zeros(int(self._pool_len.sum()), np.float32)
+        self._check(self._lib.k2b_state_pool_get(self._h, int(slot), _ptr(st)))
+        return st
+
+    def stack_states_dev(self, slots: Sequence[int], axis_len: Sequence[int], stacked_dev_ptr: int):
+        sl = np.ascontiguousarray(slots, dtype=np.int32); ax = np.ascontiguousarray(axis_len, dtype=np.int32)
+        self._check(self._lib.k2b_stack_states(self._h, _ptr(sl), int(sl.size), _ptr(ax), C.c_void_p(stacked_dev_ptr)))
+
+    def unstack_states_dev(self, slots: Sequence[int], axis_len: Sequence[int], stacked_dev_ptr: int):
+        sl = np.ascontiguousarray(slots, dtype=np.int32); ax = np.ascontiguousarray(axis_len, dtype=np.int32)
+        self._check(self._lib.k2b_unstack_states(self._h, _ptr(sl), int(sl.size), _ptr(ax), C.c_void_p(stacked_dev_ptr)))
 
     # -- diagnostics ------------------------------------------------------------------------------------------
     def selftest_umma(self, A: np.ndarray, B: np.ndarray, mode: int, use_tma: bool = False) -> np.ndarray:

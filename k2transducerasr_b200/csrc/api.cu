@@ -296,6 +296,7 @@ int32_t k2b_destroy(k2b_handle* h) {
   float** ws[] = {&h->emb, &h->conv_w, &h->dec_w, &h->dec_b, &h->enc_w, &h->enc_b, &h->out_w, &h->out_b, &h->tab0, &h->tab1};
   for (float** p : ws) { if (*p) cudaFree(*p); *p = nullptr; }
   free_cluster_assets(h);
+  state_pool_free(h);
   if (h->lens_dev) cudaFree(h->lens_dev);
   if (h->cluster_timing) cudaFree(h->cluster_timing);
   if (h->dev_status) cudaFree(h->dev_status);
@@ -505,6 +506,34 @@ int32_t k2b_encoder_proj(k2b_handle* h, const float* raw, int32_t n, float* out)
   K2B_CUDA(h, cudaStreamSynchronize(h->stream));
   if (h->cfg.precision != K2B_PREC_FP32) K2B_TRY(cluster_status(h));
   return K2B_OK;
+}
+
+// ---- on-device streaming state ---------------------------------------------------------------------------
+int32_t k2b_state_pool_create(k2b_handle* h, const int32_t* item_len, int32_t n_tensors, int32_t max_streams) {
+  K2B_TRY(enter(h));
+  if (item_len == nullptr || n_tensors <= 0 || max_streams <= 0) return fail(h, K2B_ERR_INVALID, "k2b_state_pool_create: bad arguments");
+  return state_pool_create(h, item_len, n_tensors, max_streams);
+}
+int64_t k2b_state_pool_stacked_floats(k2b_handle* h, int32_t B) { return h == nullptr ? 0 : (int64_t)state_pool_stacked_floats(h, B); }
+int32_t k2b_state_pool_put(k2b_handle* h, int32_t slot, const float* state) {
+  K2B_TRY(enter(h));
+  if (state == nullptr) return fail(h, K2B_ERR_INVALID, "k2b_state_pool_put: state is NULL");
+  return state_pool_io(h, slot, const_cast<float*>(state), true);
+}
+int32_t k2b_state_pool_get(k2b_handle* h, int32_t slot, float* state) {
+  K2B_TRY(enter(h));
+  if (state == nullptr) return fail(h, K2B_ERR_INVALID, "k2b_state_pool_get: state is NULL");
+  return state_pool_io(h, slot, state, false);
+}
+int32_t k2b_stack_states(k2b_handle* h, const int32_t* slots, int32_t B, const int32_t* axis_len, float* stacked) {
+  K2B_TRY(enter(h));
+  if (B < 0 || (B > 0 && (slots == nullptr || axis_len == nullptr || stacked == nullptr))) return fail(h, K2B_ERR_INVALID, "k2b_stack_states: bad arguments");
+  return state_pool_restack(h, slots, B, axis_len, stacked, false);
+}
+int32_t k2b_unstack_states(k2b_handle* h, const int32_t* slots, int32_t B, const int32_t* axis_len, const float* stacked) {
+  K2B_TRY(enter(h));
+  if (B < 0 || (B > 0 && (slots == nullptr || axis_len == nullptr || stacked == nullptr))) return fail(h, K2B_ERR_INVALID, "k2b_unstack_states: bad arguments");
+  return state_pool_restack(h, slots, B, axis_len, const_cast<float*>(stacked), true);
 }
 
 // ---- ragged batches -----------------------------------------------------------------------------------

@@ -33,6 +33,8 @@ struct ProfEvents {
 
 }  // namespace k2b
 
+namespace k2b { struct StatePool; }
+
 struct k2b_handle {
   k2b_config cfg{};
   cudaStream_t own_stream = nullptr;
@@ -93,6 +95,7 @@ struct k2b_handle {
   long long* cluster_timing = nullptr;   // device [8]: per-phase cycle totals of the cluster kernel (diagnostic)
 
   bool profile_on = false;
+  k2b::StatePool* state_pool = nullptr;   // on-device streaming state (state_pool.cu)
   int32_t* lens_dev = nullptr;    // k2b_set_encoder_out_lens: per-stream frame counts for the next fused offline search
   int lens_n = 0;
   bool lens_active = false;
@@ -194,6 +197,11 @@ int32_t cluster_status(k2b_handle* h);
 bool encproj_tc_supported(const k2b_handle* h);
 int32_t encoder_proj_tc(k2b_handle* h, const float* raw, int n, float* out, bool exp2x, int rows_per_stream = 0, int out_T = 0,
                         int out_t0 = 0);
+int32_t state_pool_create(k2b_handle* h, const int32_t* item_len, int n_tensors, int max_streams);
+void state_pool_free(k2b_handle* h);
+int32_t state_pool_restack(k2b_handle* h, const int32_t* slots, int B, const int32_t* axis_len, float* stacked_dev, bool unstack);
+int32_t state_pool_io(k2b_handle* h, int slot, float* host, bool put);
+size_t state_pool_stacked_floats(const k2b_handle* h, int B);
 bool decoder_tc_supported(const k2b_handle* h);
 int32_t decoder_joinin_tc(k2b_handle* h, const int32_t* ctx, int M, const float* enc, long long enc_stride, int rows_per_stream,
                           float* x);

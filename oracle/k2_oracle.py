@@ -452,3 +452,31 @@ def ragged(search, m: Model, enc: np.ndarray, lens: Sequence[int], *args, **kw) 
     for b, n in enumerate(lens):
         out.extend(search(m, enc[b:b + 1, :int(n)], *args, **kw))
     return out
+
+
+def stack_states(items: Sequence[Sequence[np.ndarray]], axis_len: Sequence[int]) -> List[np.ndarray]:
+    """ref OnlineProjOfZipformer2.cs:144-362 (and the Zipformer / Lstm / Conformer siblings): per cache tensor i, with A = its
+    "axisnum", stacked_i[(x*B + n)*A + a] = items[n][i][x*A + a] - the Array.Copy loops, e.g. :237-246 for cached_key."""
+    B = len(items)
+    out = []
+    for i, A in enumerate(axis_len):
+        L = items[0][i].size
+        st = np.zeros(L * B, F32)
+        for x in range(L // A):
+            for n in range(B):
+                st[(x * B + n) * A:(x * B + n + 1) * A] = items[n][i][x * A:(x + 1) * A]
+        out.append(st)
+    return out
+
+
+def unstack_states(stacked: Sequence[np.ndarray], B: int, axis_len: Sequence[int]) -> List[List[np.ndarray]]:
+    """ref OnlineProjOfZipformer2.cs:363-489: item_{n,i}[k*A + a] = stacked_i[(B*k + n)*A + a] (e.g. :399-404)."""
+    items = [[None] * len(axis_len) for _ in range(B)]
+    for i, A in enumerate(axis_len):
+        L = stacked[i].size // B
+        for n in range(B):
+            it = np.zeros(L, F32)
+            for k in range(L // A):
+                it[k * A:(k + 1) * A] = stacked[i][(B * k + n) * A:(B * k + n + 1) * A]
+            items[n][i] = it
+    return items
