@@ -121,9 +121,11 @@ int32_t beam_cluster_path(k2b_handle* h, const float* enc, int enc_is_raw, int B
   float* fin_lp = reinterpret_cast<float*>(p); p += (NK * 4 + 255) & ~size_t(255);
   int32_t* fin_len = reinterpret_cast<int32_t*>(p); p += (NK * 4 + 255) & ~size_t(255);
   int32_t* fin_nlive = reinterpret_cast<int32_t*>(p); p += ((size_t)B * 4 + 255) & ~size_t(255);
-  if (score == nullptr) score = reinterpret_cast<float*>(p);        // greedy callers have no use for the score
+  const bool need_lp = score != nullptr;                            // greedy callers have no use for the score
+  if (score == nullptr) score = reinterpret_cast<float*>(p);
   int32_t* bp = static_cast<int32_t*>(h->ws_bp.p);
-  K2B_TRY(beam_cluster_dev(h, encE, B, T, K, bp, fin_lp, fin_len, fin_nlive, extra_mask, hyp_inout, hyp_inout));
+  K2B_TRY(beam_cluster_dev(h, encE, B, T, K, bp, fin_lp, fin_len, fin_nlive, extra_mask, hyp_inout, hyp_inout, 0, 0, 0, nullptr, nullptr,
+                           need_lp));
   return beam_backtrace_dev(h, B, K, T, fin_lp, fin_len, fin_nlive, bp, tokens, ts, n_out, score, cap);
 }
 

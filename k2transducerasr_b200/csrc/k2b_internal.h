@@ -190,7 +190,7 @@ int32_t ensure_cluster_assets(k2b_handle* h);
 int32_t exp2x_frames(k2b_handle* h, const float* in, float* out, size_t n);
 int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, int32_t* bp, float* fin_lp, int32_t* fin_len,
                          int32_t* fin_nlive, int extra_mask, const int64_t* hyp_in, int64_t* hyp_out, int t0 = 0, int Ttot = 0,
-                         int resume = 0, int32_t* io_ctx = nullptr, unsigned long long* io_hash = nullptr);
+                         int resume = 0, int32_t* io_ctx = nullptr, unsigned long long* io_hash = nullptr, bool need_lp = true);
 int32_t cluster_status(k2b_handle* h);
 
 // ---- encproj_tc.cu -----------------------------------------------------------------------------

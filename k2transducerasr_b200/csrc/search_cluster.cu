@@ -51,6 +51,7 @@ struct ClusterArgs {
   const float* bias;        // [CS*128], -inf beyond V
   int B, T, K, V, J, S, CS, blank, unk, x3;
   int extra_mask;           // third non-emitting id (the literal 1 of ref OnlineRecognizer.cs:181), or -1
+  int need_lp;              // 0: greedy search (beam 1, no score wanted): log-softmax is monotone, so raw logits are ranked
   const int64_t* hyp_in;    // [B,2] initial contexts (online: OnlineStream.Hyp), or null = {-1, blank}
   int64_t* hyp_out;         // [B,2] final context of slot 0 (online), or null
   // time-chunked operation: this launch decodes frames [t0, t0+T) of utterances Ttot frames long; with resume != 0 the
@@ -119,7 +120,7 @@ template <int K>
 __device__ __forceinline__ void select_stream(int s, int V, int CS, const float* __restrict__ xb, const HypState& in,
                                               HypState& out, int blank, int unk, int extra_mask, int32_t* __restrict__ bp_row,
                                               int lane, const float* __restrict__ dec_tab, int J, bool do_prefetch,
-                                              uint32_t* __restrict__ scr, long long* tp = nullptr) {
+                                              uint32_t* __restrict__ scr, bool need_lp, long long* tp = nullptr) {
 #define K2B_SUB(i) do { if (tp != nullptr) { const long long now = clock64(); tp[i] += now - tp[19]; tp[19] = now; } } while (0)
   if (tp != nullptr) tp[19] = clock64();
   constexpr int XWP = xw_padded(K);
@@ -157,14 +158,19 @@ __device__ __forceinline__ void select_stream(int s, int V, int CS, const float*
     pm[p] = valid ? w[p][0] : -INFINITY;
     M = fmaxf(M, pm[p]);
   }
+  float L = 0.f;
+  if (K > 1 || need_lp) {              // warp-uniform
 #pragma unroll
-  for (int o = K; o < 32; o <<= 1) M = fmaxf(M, __shfl_xor_sync(full, M, o));
-  float sum = 0.f;
+    for (int o = K; o < 32; o <<= 1) M = fmaxf(M, __shfl_xor_sync(full, M, o));
+    float sum = 0.f;
 #pragma unroll
-  for (int p = 0; p < NP; ++p) sum += (pm[p] > -INFINITY) ? w[p][1] * __expf(pm[p] - M) : 0.f;
+    for (int p = 0; p < NP; ++p) sum += (pm[p] > -INFINITY) ? w[p][1] * __expf(pm[p] - M) : 0.f;
 #pragma unroll
-  for (int o = K; o < 32; o <<= 1) sum += __shfl_xor_sync(full, sum, o);
-  const float L = __logf(sum);
+    for (int o = K; o < 32; o <<= 1) sum += __shfl_xor_sync(full, sum, o);
+    L = __logf(sum);
+  } else {
+    M = 0.f;                           // greedy: rank the raw logits (one hypothesis, log-softmax is monotone)
+  }
   int ck[NP * K], cf[NP * K];
 #pragma unroll
   for (int p = 0; p < NP; ++p) {
@@ -243,33 +249,35 @@ __device__ __forceinline__ void select_stream(int s, int V, int CS, const float*
   }
   __syncwarp();
   K2B_SUB(11);
-  // scratch row q: {hash lo, hash hi, length (negative = no candidate), ctx0 | ctx1, score, root, -, -}
-  uint4* scr4 = reinterpret_cast<uint4*>(scr);
-  if (lane < K) {
-    scr4[2 * lane] = make_uint4((uint32_t)hs, (uint32_t)(hs >> 32), (uint32_t)(cand ? ln : -1 - lane), (uint32_t)c0);
-    scr4[2 * lane + 1] = make_uint4((uint32_t)c1, __float_as_uint(my_v), 0u, 0u);
-  }
-  __syncwarp();
   int root = lane;
-#pragma unroll
-  for (int q = K - 1; q >= 0; --q) {            // descending: the lowest equal q wins
-    const uint4 u = scr4[2 * q];
-    const uint32_t uc1 = scr[8 * q + 4];
-    const bool eq = (q < lane) & cand & (u.x == (uint32_t)hs) & (u.y == (uint32_t)(hs >> 32)) & (u.z == (uint32_t)ln) &
-                    (u.w == (uint32_t)c0) & (uc1 == (uint32_t)c1);
-    root = eq ? q : root;
-  }
-  K2B_SUB(12);
   float lp = my_v;
-  const unsigned merged = __ballot_sync(full, cand && root != lane);
-  if (merged) {                      // log-add merged scores into their root, in insertion (rank) order
-    if (lane < K) scr[8 * lane + 6] = (uint32_t)root;
+  if constexpr (K > 1) {
+    // scratch row q: {hash lo, hash hi, length (negative = no candidate), ctx0 | ctx1, score, root, -, -}
+    uint4* scr4 = reinterpret_cast<uint4*>(scr);
+    if (lane < K) {
+      scr4[2 * lane] = make_uint4((uint32_t)hs, (uint32_t)(hs >> 32), (uint32_t)(cand ? ln : -1 - lane), (uint32_t)c0);
+      scr4[2 * lane + 1] = make_uint4((uint32_t)c1, __float_as_uint(my_v), 0u, 0u);
+    }
     __syncwarp();
 #pragma unroll
-    for (int q = 1; q < K; ++q) {
-      const int qroot = (int)scr[8 * q + 6];
-      const float qv = __uint_as_float(scr[8 * q + 5]);
-      if (cand && ((merged >> q) & 1u) && qroot == lane) lp = logaddexp_c(lp, qv);
+    for (int q = K - 1; q >= 0; --q) {            // descending: the lowest equal q wins
+      const uint4 u = scr4[2 * q];
+      const uint32_t uc1 = scr[8 * q + 4];
+      const bool eq = (q < lane) & cand & (u.x == (uint32_t)hs) & (u.y == (uint32_t)(hs >> 32)) & (u.z == (uint32_t)ln) &
+                      (u.w == (uint32_t)c0) & (uc1 == (uint32_t)c1);
+      root = eq ? q : root;
+    }
+    K2B_SUB(12);
+    const unsigned merged = __ballot_sync(full, cand && root != lane);
+    if (merged) {                      // log-add merged scores into their root, in insertion (rank) order
+      if (lane < K) scr[8 * lane + 6] = (uint32_t)root;
+      __syncwarp();
+#pragma unroll
+      for (int q = 1; q < K; ++q) {
+        const int qroot = (int)scr[8 * q + 6];
+        const float qv = __uint_as_float(scr[8 * q + 5]);
+        if (cand && ((merged >> q) & 1u) && qroot == lane) lp = logaddexp_c(lp, qv);
+      }
     }
   }
   K2B_SUB(13);
@@ -619,15 +627,18 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
               // softmax offset = the (truncated, hence <=) slice maximum; fixed-point sum: order-independent, one REDUX
               const int mk = wk & ~127;
               m[r] = (wk == kKeyNone) ? -INFINITY : __int_as_float(mk ^ ((mk >> 31) & 0x7fffffff));
-              const float mneg = (wk == kKeyNone) ? 0.f : -m[r] * 1.4426950408889634f;
-              float ls = 0.f;
+              sum[r] = 1.f;
+              if (K > 1 || a.need_lp) {
+                const float mneg = (wk == kKeyNone) ? 0.f : -m[r] * 1.4426950408889634f;
+                float ls = 0.f;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float ex = ex2_approx(fmaf(v[r][j], 1.4426950408889634f, mneg));
-                ls += (lane + 32 * j < nvalid) ? ex : 0.f;
+                for (int j = 0; j < 4; ++j) {
+                  const float ex = ex2_approx(fmaf(v[r][j], 1.4426950408889634f, mneg));
+                  ls += (lane + 32 * j < nvalid) ? ex : 0.f;
+                }
+                const unsigned tot = __reduce_add_sync(0xffffffffu, __float2uint_rn(ls * 16777216.f));
+                sum[r] = (wk == kKeyNone) ? 0.f : (float)tot * (1.f / 16777216.f);
               }
-              const unsigned tot = __reduce_add_sync(0xffffffffu, __float2uint_rn(ls * 16777216.f));
-              sum[r] = (wk == kKeyNone) ? 0.f : (float)tot * (1.f / 16777216.f);
             }
           }
         }
@@ -684,7 +695,7 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
             continue;
           }
           select_stream<K>(s, V, CS, xw, st[cur], st[cur ^ 1], a.blank, a.unk, a.extra_mask, bp_row, lane, a.dec_tab, J,
-                           (a.dbg & 2) == 0 && (int)rank == (s % CS), sel_scr[warp], (TIMED && timed) ? tph : nullptr);
+                           (a.dbg & 2) == 0 && (int)rank == (s % CS), sel_scr[warp], a.need_lp != 0, (TIMED && timed) ? tph : nullptr);
         }
       }
       K2B_PHASE(6);
@@ -765,6 +776,7 @@ static void (*cluster_kernel_for(int K, bool x3, bool timed, bool pair))(const C
     if (pair) return x3 ? cluster_beam_kernel<4, true, true, true> : cluster_beam_kernel<4, false, true, true>;
     return x3 ? cluster_beam_kernel<4, true, true, false> : cluster_beam_kernel<4, false, true, false>;
   }
+  if (timed && K == 1 && x3 && !pair) return cluster_beam_kernel<1, true, true, false>;
   if (pair) return x3 ? cluster_kernel_kx<true, true>(K) : cluster_kernel_kx<false, true>(K);
   return x3 ? cluster_kernel_kx<true, false>(K) : cluster_kernel_kx<false, false>(K);
 }
@@ -856,7 +868,7 @@ int32_t exp2x_frames(k2b_handle* h, const float* in, float* out, size_t n) {
 // encE: [B,T,J] frames already mapped through exp(2x). Writes bp + final state; the caller runs the back-trace.
 int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, int32_t* bp, float* fin_lp, int32_t* fin_len,
                          int32_t* fin_nlive, int extra_mask, const int64_t* hyp_in, int64_t* hyp_out, int t0, int Ttot, int resume,
-                         int32_t* io_ctx, unsigned long long* io_hash) {
+                         int32_t* io_ctx, unsigned long long* io_hash, bool need_lp) {
   const k2b_config& c = h->cfg;
   const int V = c.vocab_size, J = c.joiner_dim, CS = (V + 127) / 128;
   const int S = kNH / K;
@@ -866,7 +878,7 @@ int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, 
   a.encE = encE; a.dec_tab = h->dec_tab; a.wo_hi_img = h->wo_hi_img; a.wo_lo = h->wo_lo; a.bias = h->bias_pad;
   a.B = B; a.T = T; a.K = K; a.V = V; a.J = J; a.S = S; a.CS = CS; a.blank = c.blank_id; a.unk = c.unk_id;
   a.x3 = c.precision == K2B_PREC_BF16X3 ? 1 : 0;
-  a.extra_mask = extra_mask; a.hyp_in = hyp_in; a.hyp_out = hyp_out;
+  a.extra_mask = extra_mask; a.hyp_in = hyp_in; a.hyp_out = hyp_out; a.need_lp = need_lp ? 1 : 0;
   a.t0 = t0; a.Ttot = Ttot > 0 ? Ttot : T; a.resume = resume; a.io_ctx = io_ctx; a.io_hash = io_hash;
   a.timing = h->cluster_timing;
   a.lens = h->lens_active ? h->lens_dev : nullptr;

@@ -11,18 +11,19 @@ names = ["enc prefetch issue (after the quarters)", "wait MMA", "TMEM->smem tran
          "st.async exchange + arrive", "wait partials (xbar)", "merge: warp 0 select_stream", "end-of-step barrier",
          "  sel: record loads", "  sel: lse + scoring", "  sel: K rounds", "  sel: extension + prefetch", "  sel: dedupe", "  sel: log-add",
          "  sel: write-back", "  build: quarter 0 (incl. load wait)", "  build: quarter 1", "  build: quarter 2", "  build: quarter 3"]
-for prec in ("bf16x3", "bf16"):
-    h = _native.Handle(vocab_size=d.vocab_size, joiner_dim=d.joiner_dim, decoder_dim=d.decoder_dim, encoder_dim=d.encoder_dim,
-                       precision=_native.PREC_NAMES[prec])
-    h.load_weights(synth.make_weights(d, blank_bias=cfg.blank_bias))
-    raw = synth.make_frames(cfg.streams, cfg.frames, d.encoder_dim, cfg.seed)
-    enc = h.encoder_proj(raw)           # projected frames in -> the host call is not time-chunked: one kernel launch
-    h.modified_beam_search(enc, 4, enc_is_raw=False)
-    h.cluster_phase_cycles()            # switch collection on
-    h.modified_beam_search(enc, 4, enc_is_raw=False)
-    cyc = h.cluster_phase_cycles()
-    tot = cyc[:8].sum() + cyc[15:19].sum()
-    print(f"== {prec}: {tot / cfg.frames:.0f} cycles per frame step (CTA 0)")
-    for n, c in zip(names, cyc[:19]):
-        print(f"   {n:32s} {c / cfg.frames:8.0f} cyc  {100.0 * c / tot:5.1f} %")
-    h.close()
+if __name__ == "__main__":
+    for prec in ("bf16x3", "bf16"):
+        h = _native.Handle(vocab_size=d.vocab_size, joiner_dim=d.joiner_dim, decoder_dim=d.decoder_dim, encoder_dim=d.encoder_dim,
+                           precision=_native.PREC_NAMES[prec])
+        h.load_weights(synth.make_weights(d, blank_bias=cfg.blank_bias))
+        raw = synth.make_frames(cfg.streams, cfg.frames, d.encoder_dim, cfg.seed)
+        enc = h.encoder_proj(raw)           # projected frames in -> the host call is not time-chunked: one kernel launch
+        h.modified_beam_search(enc, 4, enc_is_raw=False)
+        h.cluster_phase_cycles()            # switch collection on
+        h.modified_beam_search(enc, 4, enc_is_raw=False)
+        cyc = h.cluster_phase_cycles()
+        tot = cyc[:8].sum() + cyc[15:19].sum()
+        print(f"== {prec}: {tot / cfg.frames:.0f} cycles per frame step (CTA 0)")
+        for n, c in zip(names, cyc[:19]):
+            print(f"   {n:32s} {c / cfg.frames:8.0f} cyc  {100.0 * c / tot:5.1f} %")
+        h.close()
