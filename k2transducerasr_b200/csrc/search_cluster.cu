@@ -65,7 +65,6 @@ struct ClusterArgs {
   int32_t* fin_nlive;       // [B]
   int* status;
   long long* timing;        // optional [8] cycle totals of the step phases (cluster 0, CTA 0, thread 0)
-  int dbg;                  // experiment switches (K2B_DBG), 0 in production
   const int32_t* lens;      // [B] frames to decode per stream (k2b_set_encoder_out_lens), or null = all T
 };
 
@@ -478,7 +477,6 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
 #pragma unroll
       for (int r = 0; r < RPW; ++r) xoff[r][i] = (uint32_t)(k >> 6) * kXTile + sw128_offset(lr0 + r, k & 63);
     }
-    const size_t rm = (a.dbg & 1) ? 0 : ~(size_t)0;
     const int col0 = 8 * (warp >> 2);            // this warp's 8 accumulator columns (hypotheses) in the read-out
     const int vrow = 32 * (warp & 3) + lane;     // ... and its vocabulary row of the slice
     const float bsv = bias_s[vrow];
@@ -493,7 +491,7 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
         const float4* pd[RPW];
 #pragma unroll
         for (int r = 0; r < RPW; ++r)
-          pd[r] = reinterpret_cast<const float4*>(a.dec_tab + (((size_t)(sc.ctx0[nb0 + r] + 1) * V + sc.ctx1[nb0 + r]) & rm) * J);
+          pd[r] = reinterpret_cast<const float4*>(a.dec_tab + ((size_t)(sc.ctx0[nb0 + r] + 1) * V + sc.ctx1[nb0 + r]) * J);
         // fence.proxy.async waits for every outstanding load of the thread (MEMBAR.ALL.CTA), so only the first quarter's
         // decoder-row loads are issued before the first fence: the tensor pipe starts after one L2 round trip for 1/4 of
         // the rows, and the other three quarters' loads (issued right after that fence) land while it works
@@ -695,7 +693,7 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
             continue;
           }
           select_stream<K>(s, V, CS, xw, st[cur], st[cur ^ 1], a.blank, a.unk, a.extra_mask, bp_row, lane, a.dec_tab, J,
-                           (a.dbg & 2) == 0 && (int)rank == (s % CS), sel_scr[warp], a.need_lp != 0, (TIMED && timed) ? tph : nullptr);
+                           (int)rank == (s % CS), sel_scr[warp], a.need_lp != 0, (TIMED && timed) ? tph : nullptr);
         }
       }
       K2B_PHASE(6);
@@ -882,7 +880,6 @@ int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, 
   a.t0 = t0; a.Ttot = Ttot > 0 ? Ttot : T; a.resume = resume; a.io_ctx = io_ctx; a.io_hash = io_hash;
   a.timing = h->cluster_timing;
   a.lens = h->lens_active ? h->lens_dev : nullptr;
-  { const char* de = getenv("K2B_DBG"); a.dbg = de ? atoi(de) : 0; }
   a.bp = bp; a.fin_lp = fin_lp; a.fin_len = fin_len; a.fin_nlive = fin_nlive; a.status = status;
   const size_t dyn = cluster_dyn_smem(J, CS, K);
   void (*kern)(const ClusterArgs) = cluster_kernel_for(K, a.x3 != 0, a.timing != nullptr, cluster_pair_mode(CS));
