@@ -352,3 +352,62 @@ def test_full_size_cfg5_ctc_properties(built_lib):
         assert all(tok != 0 for tok in t[bi])
     assert sum(len(x) for x in t) == int(((ids != 0) & (ids != np.concatenate([np.full((128, 1), -1), ids[:, :-1]], 1))).sum())
     h.close()
+
+
+def test_full_size_cfg4_properties(built_lib):
+    """cfg4 shape (B=256, T=250 cut to 60 here, K=4, V=5537: per-frame path - tcgen05 decoder, tcgen05 joiner with the reducing
+    epilogue, merge kernel): determinism, shard-invariance, token range, an oracle spot check, and ragged lengths."""
+    cfg = synth.CONFIGS["cfg4"]
+    T = 60
+    m, w = model_and_weights(cfg.dims, blank_bias=cfg.blank_bias)
+    h = make_handle(cfg.dims, w, precision=_native.PREC_NAMES["bf16x3"])
+    raw = synth.make_frames(cfg.streams, T, cfg.dims.encoder_dim, cfg.seed)
+    t1, s1, sc1 = h.modified_beam_search(raw, 4, enc_is_raw=True)
+    t2, s2, sc2 = h.modified_beam_search(raw, 4, enc_is_raw=True)
+    assert t1 == t2 and s1 == s2 and sc1.tolist() == sc2.tolist()
+    ta, sa, sca = h.modified_beam_search(np.ascontiguousarray(raw[128:160]), 4, enc_is_raw=True)
+    assert ta == t1[128:160] and sa == s1[128:160]
+    np.testing.assert_allclose(sca, sc1[128:160], atol=0)
+    assert all(len(t) == len(s) and all(0 <= x < T for x in s) and s == sorted(s) for t, s in zip(t1, s1))
+    assert all(all(3 <= tok < cfg.dims.vocab_size or tok == 1 for tok in t) for t in t1)
+    enc = O.encoder_proj(m, raw[:4])
+    want = O.modified_beam_search(m, enc, 4)
+    ex = compare_streams(t1[:4], s1[:4], want, "cfg4 spot", allow_frac=0.5)
+    for b in range(4):
+        if b not in ex:
+            assert abs(float(sc1[b]) - want[b].score) < SCORE_TOL
+    lens = [T - (7 * b) % T for b in range(cfg.streams)]
+    tr, sr, _ = h.modified_beam_search(raw, 4, enc_is_raw=True, lens=lens)
+    assert all(all(x < lens[b] for x in sr[b]) for b in range(cfg.streams))
+    assert [tr[b] for b in range(cfg.streams) if lens[b] == T] == [t1[b] for b in range(cfg.streams) if lens[b] == T]
+    h.close()
+
+
+def test_full_size_cfg3_online_properties(built_lib):
+    """cfg3 shape (512 online streams, V=2000, chunks of 8 frames, 16-CTA clusters): chunked == one long chunk, determinism,
+    shard-invariance, Hyp carried through, and an oracle spot check."""
+    cfg = synth.CONFIGS["cfg3"]
+    m, w = model_and_weights(cfg.dims, blank_bias=cfg.blank_bias)
+    h = make_handle(cfg.dims, w, precision=_native.PREC_NAMES["bf16x3"])
+    B, Tc, nch = cfg.streams, cfg.frames, 4
+    raw = synth.make_frames(B, Tc * nch, cfg.dims.encoder_dim, cfg.seed)
+    hyp = np.zeros((B, 2), np.int64)
+    toks = [[] for _ in range(B)]
+    tss = [[] for _ in range(B)]
+    for c in range(nch):
+        t, s, hyp = h.greedy_online_chunk(np.ascontiguousarray(raw[:, Tc * c:Tc * c + Tc]), hyp, enc_is_raw=True)
+        for b in range(B):
+            toks[b] += t[b]
+            tss[b] += [x + Tc * c for x in s[b]]
+    t_all, s_all, hyp_all = h.greedy_online_chunk(raw, np.zeros((B, 2), np.int64), enc_is_raw=True)
+    assert toks == t_all and tss == s_all and hyp.tolist() == hyp_all.tolist()
+    t_sub, s_sub, _ = h.greedy_online_chunk(np.ascontiguousarray(raw[100:140]), np.zeros((40, 2), np.int64), enc_is_raw=True)
+    assert t_sub == t_all[100:140] and s_sub == s_all[100:140]
+    for b in range(B):
+        tail = ([0, 0] + t_all[b])[-2:]
+        assert hyp_all[b].tolist() == tail                      # ref OnlineRecognizer.cs:208: Hyp = last two tokens
+        assert all(tok not in (0, 1, 2) for tok in t_all[b])    # ref :181: blank, unk and the literal 1 are never emitted
+    enc = O.encoder_proj(m, raw[:6])
+    res = O.greedy_search_online_chunk(m, enc, [[0, 0]] * 6, [[0, 0]] * 6)
+    compare_streams(t_all[:6], s_all[:6], res, "cfg3 spot", allow_frac=0.5)
+    h.close()
