@@ -46,6 +46,12 @@ struct EncArgs {
   int pro, V, neg_wrap;
   const int32_t* ctx; const float* tab0; const float* tab1;
   const float* enc; long long enc_stride;
+  // epi 4 can also leave its result as the next GEMM's A operand: bf16 hi / lo tiles in the K-major SWIZZLE_128B shared-memory
+  // image, [M/128][N/64][hi 16 KB | lo 16 KB] (x_img != null). pro 2 takes such an image as A: the loader warp fetches the
+  // tiles with bulk TMA copies and there is no conversion pass at all - the 22 vocabulary-tile CTAs of a joiner launch used to
+  // convert the same fp32 rows 22 times.
+  uint8_t* x_img;
+  const uint8_t* a_img;
 };
 
 __device__ __forceinline__ int table_row_e(int y, int V, int neg_wrap) {
@@ -119,9 +125,14 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
         if (!mbar_wait(&empty[s], ph ^ 1u)) ok = false;
         uint8_t* st = smem + (size_t)s * kStageBytes;
         const size_t off = ((size_t)tile_n * nkb + kb) * kWTile;
-        mbar_expect_tx(&full_w[s], (uint32_t)(x3 ? 2 * kWTile : kWTile));
+        const uint32_t a_bytes = a.pro == 2 ? (uint32_t)(x3 ? 2 * kATile : kATile) : 0u;
+        mbar_expect_tx(&full_w[s], (uint32_t)(x3 ? 2 * kWTile : kWTile) + a_bytes);
         tma_bulk_g2s(st + 2 * kATile, a.w_hi_img + off, kWTile, &full_w[s]);
         if (x3) tma_bulk_g2s(st + 2 * kATile + kWTile, a.w_lo_img + off, kWTile, &full_w[s]);
+        if (a.pro == 2) {          // A hi (and lo, adjacent) of this row tile and k-block
+          const uint8_t* src = a.a_img + ((size_t)tile_m * nkb + kb) * (2 * kATile);
+          tma_bulk_g2s(st, src, a_bytes, &full_w[s]);
+        }
       }
     }
   } else if (warp_u == 1) {
@@ -134,7 +145,7 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
       const int s = kb % kStages;
       const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
       if (!mbar_wait(&full_w[s], ph)) ok = false;
-      if (!mbar_wait(&full_a[s], ph)) ok = false;
+      if (a.pro != 2 && !mbar_wait(&full_a[s], ph)) ok = false;
       tc_fence_after();
       const uint32_t sb = smem_u32(smem + (size_t)s * kStageBytes);
       const uint32_t ah = (((sb) & 0x3FFFFu) >> 4) | (1u << 16);
@@ -174,7 +185,7 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
         }
       }
     }
-    for (int kb = 0; kb < nkb; ++kb) {
+    for (int kb = 0; kb < (a.pro == 2 ? 0 : nkb); ++kb) {
       const int s = kb % kStages;
       const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
       if (!mbar_wait(&empty[s], ph ^ 1u)) ok = false;
@@ -328,7 +339,7 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
         if (m >= a.M) break;
         size_t orow = (size_t)m;
         if (a.epi == 0 && a.rows_per_stream > 0) { const int b = m / a.rows_per_stream; orow = (size_t)b * a.out_T + a.out_t0 + (m - b * a.rows_per_stream); }
-        float* crow = a.C + orow * a.N + (size_t)tile_n * kEN;
+        float* crow = a.C != nullptr ? a.C + orow * a.N + (size_t)tile_n * kEN : nullptr;
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           const int col = hf * 128 + 4 * lane;
@@ -345,7 +356,14 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
             o.z = expf(2.f * fminf(fmaxf(o.z, -21.f), 21.f));
             o.w = expf(2.f * fminf(fmaxf(o.w, -21.f), 21.f));
           }
-          *reinterpret_cast<float4*>(crow + col) = o;
+          if (a.C != nullptr) *reinterpret_cast<float4*>(crow + col) = o;
+          if (a.epi == 4 && a.x_img != nullptr) {
+            const int n = tile_n * kEN + col;                        // 4 consecutive K positions of the next GEMM
+            uint8_t* timg = a.x_img + ((size_t)tile_m * (a.N / kBKc) + (n >> 6)) * (2 * kATile) + sw128_offset(row, n & 63);
+            const float h0 = bf16_round(o.x), h1 = bf16_round(o.y), h2 = bf16_round(o.z), h3 = bf16_round(o.w);
+            *reinterpret_cast<uint2*>(timg) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+            *reinterpret_cast<uint2*>(timg + kATile) = make_uint2(pack_bf16x2(o.x - h0, o.y - h1), pack_bf16x2(o.z - h2, o.w - h3));
+          }
         }
       }
     } else if (pw < 4) {
@@ -448,7 +466,7 @@ bool decoder_tc_supported(const k2b_handle* h) {
 }
 
 int32_t decoder_joinin_tc(k2b_handle* h, const int32_t* ctx, int M, const float* enc, long long enc_stride, int rows_per_stream,
-                          float* x) {
+                          float* x, uint8_t* x_img) {
   if (!h->wd_ready) {
     const int N = h->cfg.joiner_dim, K = h->cfg.decoder_dim;
     K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->wd_hi_img), (size_t)N * K * 2));
@@ -461,7 +479,7 @@ int32_t decoder_joinin_tc(k2b_handle* h, const int32_t* ctx, int M, const float*
   a.pro = 1; a.ctx = ctx; a.tab0 = h->tab0; a.tab1 = h->tab1; a.V = h->cfg.vocab_size;
   a.neg_wrap = h->cfg.neg_id_mode == K2B_NEGID_WRAP ? 1 : 0;
   a.enc = enc; a.enc_stride = enc_stride; a.rows_per_stream = rows_per_stream;
-  a.w_hi_img = h->wd_hi_img; a.w_lo_img = h->wd_lo_img; a.bias = h->dec_b; a.C = x;
+  a.w_hi_img = h->wd_hi_img; a.w_lo_img = h->wd_lo_img; a.bias = h->dec_b; a.C = x; a.x_img = x_img;
   a.M = M; a.N = h->cfg.joiner_dim; a.K = h->cfg.decoder_dim;
   a.epi = 4; a.nvalid = a.N;
   return launch_tc(h, a);
@@ -486,11 +504,16 @@ static int32_t ensure_joiner_assets(k2b_handle* h) {
 }
 
 // x [M,J] fp32 (already tanh(enc+dec)). topk > 0: softmax/top-k partials; topk == 0: argmax partials. nt = joiner_tc_tiles().
-int32_t joiner_tc_partials(k2b_handle* h, const float* x, int M, int topk, float* part_m, float* part_s, float* part_tv,
-                           int32_t* part_ti, float* part_val, int32_t* part_idx, int32_t* part_nan) {
+size_t joiner_tc_image_bytes(const k2b_handle* h, int M) {
+  return (size_t)((M + kEM - 1) / kEM) * (size_t)(h->cfg.joiner_dim / kBKc) * (2 * kATile);
+}
+
+int32_t joiner_tc_partials(k2b_handle* h, const float* x, const uint8_t* x_img, int M, int topk, float* part_m, float* part_s,
+                           float* part_tv, int32_t* part_ti, float* part_val, int32_t* part_idx, int32_t* part_nan) {
   K2B_TRY(ensure_joiner_assets(h));
   EncArgs a = {};
   a.A = x; a.w_hi_img = h->wj_hi_img; a.w_lo_img = h->wj_lo_img; a.bias = h->out_b; a.C = nullptr;
+  if (x_img != nullptr) { a.pro = 2; a.a_img = x_img; }
   a.M = M; a.N = joiner_tc_tiles(h) * kEN; a.K = h->cfg.joiner_dim;
   a.exp2x = 0;
   a.epi = topk > 0 ? 2 : 3; a.nvalid = h->cfg.vocab_size; a.topk = topk;

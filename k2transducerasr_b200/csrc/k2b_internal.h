@@ -63,6 +63,7 @@ struct k2b_handle {
   k2b::DevBuf ws_in;        // host-variant staging of the input frames / log-probs
   k2b::DevBuf ws_encproj;   // [B,T,J] projected frames when the caller passes raw frames
   k2b::DevBuf ws_x;         // [N,J] joiner A operand tanh(enc+dec)
+  k2b::DevBuf ws_ximg;      // the same operand as bf16 hi/lo tile images (written by the tcgen05 decoder, read by TMA)
   k2b::DevBuf ws_dec;       // [N,J] decoder_proj output (fine-grained path)
   k2b::DevBuf ws_logits;    // [N,V] (fine-grained path staging)
   k2b::DevBuf ws_part;      // per-(row, vocab tile) partial argmax / softmax / top-k
@@ -204,11 +205,12 @@ int32_t state_pool_io(k2b_handle* h, int slot, float* host, bool put);
 size_t state_pool_stacked_floats(const k2b_handle* h, int B);
 bool decoder_tc_supported(const k2b_handle* h);
 int32_t decoder_joinin_tc(k2b_handle* h, const int32_t* ctx, int M, const float* enc, long long enc_stride, int rows_per_stream,
-                          float* x);
+                          float* x, uint8_t* x_img);
+size_t joiner_tc_image_bytes(const k2b_handle* h, int M);
 bool joiner_tc_supported(const k2b_handle* h);
 int joiner_tc_tiles(const k2b_handle* h);
-int32_t joiner_tc_partials(k2b_handle* h, const float* x, int M, int topk, float* part_m, float* part_s, float* part_tv,
-                           int32_t* part_ti, float* part_val, int32_t* part_idx, int32_t* part_nan);
+int32_t joiner_tc_partials(k2b_handle* h, const float* x, const uint8_t* x_img, int M, int topk, float* part_m, float* part_s,
+                           float* part_tv, int32_t* part_ti, float* part_val, int32_t* part_idx, int32_t* part_nan);
 
 // profiling bracket around the dominant GEMM
 void prof_begin(k2b_handle* h);

@@ -440,7 +440,7 @@ int32_t greedy_dev(k2b_handle* h, const float* enc, int B, int T, int mode, bool
     j.W = h->out_w; j.bias = h->out_b; j.A = x;
     j.part_val = pval; j.part_idx = pidx; j.part_nan = pnan;
     prof_begin(h);
-    if (tc) K2B_TRY(joiner_tc_partials(h, x, B, 0, nullptr, nullptr, nullptr, nullptr, pval, pidx, pnan));
+    if (tc) K2B_TRY(joiner_tc_partials(h, x, nullptr, B, 0, nullptr, nullptr, nullptr, nullptr, pval, pidx, pnan));
     else K2B_TRY(launch_gemm_simt(h, PRO_PLAIN, EPI_ARGMAX, j));
     prof_end(h);
 
@@ -464,6 +464,11 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
   const int nt = tc ? joiner_tc_tiles(h) : num_vocab_tiles(V);
   const int N = B * K;
   K2B_TRY(ensure(h, h->ws_x, sizeof(float) * (size_t)N * J));
+  uint8_t* ximg = nullptr;
+  if (tc && decoder_tc_supported(h)) {
+    K2B_TRY(ensure(h, h->ws_ximg, joiner_tc_image_bytes(h, N)));
+    ximg = static_cast<uint8_t*>(h->ws_ximg.p);
+  }
   K2B_TRY(ensure(h, h->ws_part, (size_t)N * nt * (8 + 8 * (size_t)K)));
   K2B_TRY(ensure(h, h->ws_state, 2 * state_bytes(B, K)));
   K2B_TRY(ensure(h, h->ws_bp, sizeof(int32_t) * (size_t)B * (T > 0 ? T : 1) * K));
@@ -490,7 +495,10 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
     d.blank = c.blank_id;
     d.enc = enc + (size_t)t * J; d.enc_stride = (long long)T * J; d.rows_per_stream = K;
     d.C = x;
-    if (tc && decoder_tc_supported(h)) K2B_TRY(decoder_joinin_tc(h, st[cur].ctx, N, enc + (size_t)t * J, (long long)T * J, K, x));
+    // tcgen05 decoder: its epilogue leaves x = tanh(enc + dec) as bf16 hi/lo tile images, which the joiner's loader warp
+    // fetches by TMA (no fp32 round trip, no per-CTA conversion)
+    const bool img = tc && decoder_tc_supported(h);
+    if (img) K2B_TRY(decoder_joinin_tc(h, st[cur].ctx, N, enc + (size_t)t * J, (long long)T * J, K, nullptr, ximg));
     else K2B_TRY(launch_gemm_simt(h, PRO_DEC, EPI_TANH_ADD, d));
 
     GemmArgs j;
@@ -498,7 +506,7 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
     j.W = h->out_w; j.bias = h->out_b; j.A = x;
     j.part_m = part_m; j.part_s = part_s; j.part_tv = part_tv; j.part_ti = part_ti; j.topk = K;
     prof_begin(h);
-    if (tc) K2B_TRY(joiner_tc_partials(h, x, N, K, part_m, part_s, part_tv, part_ti, nullptr, nullptr, nullptr));
+    if (tc) K2B_TRY(joiner_tc_partials(h, x, img ? ximg : nullptr, N, K, part_m, part_s, part_tv, part_ti, nullptr, nullptr, nullptr));
     else K2B_TRY(launch_gemm_simt(h, PRO_PLAIN, EPI_TOPK, j));
     prof_end(h);
 
