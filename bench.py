@@ -285,7 +285,7 @@ def run_ours(args, cfg):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = run_cpu_baseline(cfg, streams=32)
+        cpu = run_cpu_baseline(cfg, streams=cfg.streams, repeats=2)     # two full batches: ~10 s of CPU work
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
