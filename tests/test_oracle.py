@@ -137,3 +137,36 @@ def test_bf16_emulation_modes_are_close(model):
     assert np.abs(O.decoder(m3, y) - ref).max() < 2e-5
     assert 1e-5 < np.abs(O.decoder(m1, y) - ref).max() < 5e-2
     assert O.round_bf16(np.array([1.00390625], np.float32))[0] == np.float32(1.0)    # RNE tie -> even
+
+
+def test_stack_unstack_states_restate_the_reference_loops():
+    """ref OnlineProjOfZipformer2.cs:236-246 (stack: (x*B + n)*A + a  <-  n-th item [x*A + a]) and :399-404 (unstack); batch on
+    axis 1 of [X, B, A], so stacking is a transpose of the two leading axes and unstacking inverts it for the same A."""
+    rng = np.random.default_rng(0)
+    B, shapes = 3, [(4, 6), (1, 5), (7, 1)]                      # (X, A) per cache tensor
+    items = [[rng.standard_normal(x * a).astype(np.float32) for x, a in shapes] for _ in range(B)]
+    axis = [a for _, a in shapes]
+    st = O.stack_states(items, axis)
+    for i, (x, a) in enumerate(shapes):
+        want = np.stack([items[n][i].reshape(x, a) for n in range(B)], axis=1).reshape(-1)
+        np.testing.assert_array_equal(st[i], want)
+    back = O.unstack_states(st, B, axis)
+    for n in range(B):
+        for i in range(len(shapes)):
+            np.testing.assert_array_equal(back[n][i], items[n][i])
+    # a different A in the two directions (the reference's cached_nonlin_attn, :250 vs :409) is NOT an inverse pair for B > 1
+    st2 = O.stack_states(items, [2, 5, 1])
+    back2 = O.unstack_states(st2, B, [6, 5, 1])
+    assert not all(np.array_equal(back2[n][0], items[n][0]) for n in range(B))
+
+
+def test_ragged_wrapper_is_per_stream_decoding():
+    m, w = model_and_weights(SMALL, blank_bias=0.6)
+    enc = synth.make_frames(4, 9, m.J, 5)
+    lens = [9, 0, 4, 7]
+    got = O.ragged(O.modified_beam_search, m, enc, lens, 3)
+    for b, n in enumerate(lens):
+        one = O.modified_beam_search(m, enc[b:b + 1, :n], 3)[0]
+        assert got[b].appended == one.appended and got[b].timestamps == one.timestamps
+        assert all(t < n for t in got[b].timestamps)
+    assert got[1].appended == []
