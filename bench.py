@@ -272,8 +272,8 @@ def run_ours(args, cfg):
     avg_ms = tot_ms / max(n_l, 1)
     achieved_tf = flops_per_launch / (avg_ms * 1e-3) / 1e12 if n_l else 0.0
     # dram__bytes_read.sum + dram__bytes_write.sum of one cluster_beam_kernel launch on this workload, from the
-    # ncu --set full capture profiles/r01_cluster_beam_v7_full.ncu-rep (240.3 MB + 5.8 MB); none taken for the fp32 path
-    traffic = 246.1e6 if (fused_loop and args.workload == "cfg2") else None
+    # ncu --set full capture profiles/r01_cluster_beam_v8_full.ncu-rep (240.5 MB + 6.8 MB); none taken for the fp32 path
+    traffic = 247.2e6 if (fused_loop and args.workload == "cfg2") else None
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": achieved_tf / peaks["tf_sustained"], "traffic": traffic, "kernel": ("cluster_beam_kernel: whole time loop (joiner tcgen05 GEMM + log-softmax/top-k + merge)" if fused_loop
                            else "joiner GEMM (+log-softmax/top-k epilogue), one launch per frame"),
