@@ -37,7 +37,7 @@ void free_cluster_assets(k2b_handle* h) {
   if (h->wo_lo) cudaFree(h->wo_lo);
   if (h->bias_pad) cudaFree(h->bias_pad);
   if (h->dec_tab) cudaFree(h->dec_tab);
-  h->wo_hi_img = nullptr; h->wo_lo = nullptr; h->bias_pad = nullptr; h->dec_tab = nullptr;
+  h->wo_hi_img = nullptr; h->wo_lo = nullptr; h->bias_pad = nullptr; h->dec_tab = nullptr; h->dec_tab_state = 0;
   h->tc_ready = false;
   if (h->we_hi_img) cudaFree(h->we_hi_img);
   if (h->we_lo_img) cudaFree(h->we_lo_img);

@@ -459,6 +459,41 @@ int32_t encoder_proj_tc(k2b_handle* h, const float* raw, int n, float* out, bool
   return launch_tc(h, a);
 }
 
+// ---- joiner operand from the memoised decoder table: x[m,:] = tanh(enc[m / rows_per_stream] + decoder(ctx[m])) written straight as
+//      the bf16 hi / lo tile images the joiner GEMM's loader warp fetches (one block per hypothesis row, one float4 per thread) ----
+namespace {
+__global__ void joinin_table_kernel(const float* __restrict__ dec_tab, const int32_t* __restrict__ ctx, int M, int V, int J,
+                                    const float* __restrict__ enc, long long enc_stride, int rows_per_stream,
+                                    uint8_t* __restrict__ x_img) {
+  const int m = blockIdx.x, k = 4 * threadIdx.x;
+  if (k >= J) return;
+  const float4 d = __ldg(reinterpret_cast<const float4*>(dec_tab + ((size_t)(ctx[2 * m] + 1) * V + ctx[2 * m + 1]) * J + k));
+  const float4 e = __ldg(reinterpret_cast<const float4*>(enc + (size_t)(m / rows_per_stream) * enc_stride + k));
+  float x[4];
+  const float ev[4] = {e.x, e.y, e.z, e.w}, dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {           // tanh(e + d) = 1 - 2 / (1 + exp(2e) * exp(2d)); the table holds exp(2d)
+    const float y = fmaf(expf(2.f * fminf(fmaxf(ev[i], -21.f), 21.f)), dv[i], 1.f);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));
+    x[i] = fmaf(-2.f, r, 1.f);
+  }
+  uint8_t* timg = x_img + ((size_t)(m / kEM) * (J / kBKc) + (k >> 6)) * (2 * kATile) + sw128_offset(m % kEM, k & 63);
+  const float h0 = bf16_round(x[0]), h1 = bf16_round(x[1]), h2 = bf16_round(x[2]), h3 = bf16_round(x[3]);
+  *reinterpret_cast<uint2*>(timg) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+  *reinterpret_cast<uint2*>(timg + kATile) = make_uint2(pack_bf16x2(x[0] - h0, x[1] - h1), pack_bf16x2(x[2] - h2, x[3] - h3));
+}
+}  // namespace
+
+int32_t joinin_table_tc(k2b_handle* h, const int32_t* ctx, int M, const float* enc, long long enc_stride, int rows_per_stream,
+                        uint8_t* x_img) {
+  const int J = h->cfg.joiner_dim;
+  joinin_table_kernel<<<M, (J / 4 + 31) / 32 * 32, 0, h->stream>>>(h->dec_tab, ctx, M, h->cfg.vocab_size, J, enc, enc_stride,
+                                                                      rows_per_stream, x_img);
+  K2B_LAUNCH_CHECK(h);
+  return K2B_OK;
+}
+
 // ---- stateless decoder + joiner prologue on the tensor cores: x[m,:] = tanh(enc[m / rows_per_stream] + decoder(ctx[m])) -----
 bool decoder_tc_supported(const k2b_handle* h) {
   const k2b_config& c = h->cfg;

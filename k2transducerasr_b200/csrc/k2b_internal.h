@@ -79,6 +79,7 @@ struct k2b_handle {
   uint32_t* wo_lo = nullptr;      // [CS*128][J/2] bf16 lo of out_w, packed pairs (TMEM source)
   float* bias_pad = nullptr;      // [CS*128] out_b, -inf beyond V
   float* dec_tab = nullptr;       // [(V+1)*V, J] exp(2*decoder(y0,y1)): the memoised stateless decoder
+  int dec_tab_state = 0;          // 0 not tried, 1 built, -1 does not fit (decoder GEMM per frame instead)
 
   int cluster16_ok = -1;          // 16-CTA cluster launchable on this device? (-1 unknown; occupancy query, cached)
   bool enc_ready = false;         // encproj_tc.cu: pre-split, pre-swizzled encoder_proj weight images
@@ -188,6 +189,9 @@ int32_t beam_backtrace_dev(k2b_handle* h, int B, int K, int T, const float* lp, 
 // ---- search_cluster.cu -------------------------------------------------------------------------
 bool cluster_path_supported(const k2b_handle* h, int K);
 int32_t ensure_cluster_assets(k2b_handle* h);
+int32_t ensure_dec_table(k2b_handle* h, bool* have);
+int32_t joinin_table_tc(k2b_handle* h, const int32_t* ctx, int M, const float* enc, long long enc_stride, int rows_per_stream,
+                        uint8_t* x_img);
 int32_t exp2x_frames(k2b_handle* h, const float* in, float* out, size_t n);
 int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, int32_t* bp, float* fin_lp, int32_t* fin_len,
                          int32_t* fin_nlive, int extra_mask, const int64_t* hyp_in, int64_t* hyp_out, int t0 = 0, int Ttot = 0,

@@ -465,6 +465,8 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
   const int N = B * K;
   K2B_TRY(ensure(h, h->ws_x, sizeof(float) * (size_t)N * J));
   uint8_t* ximg = nullptr;
+  bool have_tab = false;         // memoised decoder (fits in HBM up to V ~ 6800 at J = 512): no decoder GEMM in the loop
+  if (tc && decoder_tc_supported(h)) K2B_TRY(ensure_dec_table(h, &have_tab));
   if (tc && decoder_tc_supported(h)) {
     K2B_TRY(ensure(h, h->ws_ximg, joiner_tc_image_bytes(h, N)));
     ximg = static_cast<uint8_t*>(h->ws_ximg.p);
@@ -498,7 +500,8 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
     // tcgen05 decoder: its epilogue leaves x = tanh(enc + dec) as bf16 hi/lo tile images, which the joiner's loader warp
     // fetches by TMA (no fp32 round trip, no per-CTA conversion)
     const bool img = tc && decoder_tc_supported(h);
-    if (img) K2B_TRY(decoder_joinin_tc(h, st[cur].ctx, N, enc + (size_t)t * J, (long long)T * J, K, nullptr, ximg));
+    if (img && have_tab) K2B_TRY(joinin_table_tc(h, st[cur].ctx, N, enc + (size_t)t * J, (long long)T * J, K, ximg));
+    else if (img) K2B_TRY(decoder_joinin_tc(h, st[cur].ctx, N, enc + (size_t)t * J, (long long)T * J, K, nullptr, ximg));
     else K2B_TRY(launch_gemm_simt(h, PRO_DEC, EPI_TANH_ADD, d));
 
     GemmArgs j;

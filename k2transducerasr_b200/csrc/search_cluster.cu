@@ -823,20 +823,26 @@ bool cluster_path_supported(const k2b_handle* h, int K) {
   return true;
 }
 
-// Builds (once per weight load) the shared-memory image / TMEM source / padded bias of the joiner weight and the
-// memoised decoder table.
-int32_t ensure_cluster_assets(k2b_handle* h) {
-  if (h->tc_ready) return K2B_OK;
+// The memoised stateless decoder: dec_tab[(y0+1)*V + y1] = exp(2*clamp(decoder(y0, y1))) for every context, J floats per row
+// (513 MB at V = 500, 8.2 GB at V = 2000, 62.8 GB at V = 5537 - HBM capacity traded for a [N,D]x[D,J] GEMM per frame).
+// Built once per weight load if it fits: at most 96 GiB and at most 60 % of the free device memory. *have = false otherwise
+// (callers then run the decoder GEMM every frame).
+int32_t ensure_dec_table(k2b_handle* h, bool* have) {
+  *have = h->dec_tab != nullptr;
+  if (h->dec_tab != nullptr || h->dec_tab_state < 0) return K2B_OK;
   const k2b_config& c = h->cfg;
-  const int V = c.vocab_size, J = c.joiner_dim, D = c.decoder_dim, CS = (V + 127) / 128;
-  const size_t rows = (size_t)CS * 128;
-  K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->wo_hi_img), rows * J * 2));
-  K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->wo_lo), rows * J * 2));
-  K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->bias_pad), rows * sizeof(float)));
-  pack_out_w_kernel<<<(unsigned)rows, 128, 0, h->stream>>>(h->out_w, h->out_b, V, J, CS, h->wo_hi_img, h->wo_lo, h->bias_pad);
-  K2B_LAUNCH_CHECK(h);
+  const int V = c.vocab_size, J = c.joiner_dim, D = c.decoder_dim;
   const long long nctx = (long long)(V + 1) * V;
-  K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->dec_tab), (size_t)nctx * J * sizeof(float)));
+  const size_t bytes = (size_t)nctx * J * sizeof(float);
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
+  if (bytes > ((size_t)96 << 30) || (double)bytes > 0.6 * (double)free_b ||
+      cudaMalloc(reinterpret_cast<void**>(&h->dec_tab), bytes) != cudaSuccess) {
+    cudaGetLastError();
+    h->dec_tab = nullptr;
+    h->dec_tab_state = -1;
+    return K2B_OK;
+  }
   const int chunk = 1 << 18;
   int32_t* ctx = nullptr;
   K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&ctx), sizeof(int32_t) * 2 * chunk));
@@ -853,6 +859,26 @@ int32_t ensure_cluster_assets(k2b_handle* h) {
   }
   K2B_CUDA(h, cudaStreamSynchronize(h->stream));
   cudaFree(ctx);
+  h->dec_tab_state = 1;
+  *have = true;
+  return K2B_OK;
+}
+
+// Builds (once per weight load) the shared-memory image / TMEM source / padded bias of the joiner weight and the
+// memoised decoder table.
+int32_t ensure_cluster_assets(k2b_handle* h) {
+  if (h->tc_ready) return K2B_OK;
+  const k2b_config& c = h->cfg;
+  const int V = c.vocab_size, J = c.joiner_dim, D = c.decoder_dim, CS = (V + 127) / 128;
+  const size_t rows = (size_t)CS * 128;
+  K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->wo_hi_img), rows * J * 2));
+  K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->wo_lo), rows * J * 2));
+  K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->bias_pad), rows * sizeof(float)));
+  pack_out_w_kernel<<<(unsigned)rows, 128, 0, h->stream>>>(h->out_w, h->out_b, V, J, CS, h->wo_hi_img, h->wo_lo, h->bias_pad);
+  K2B_LAUNCH_CHECK(h);
+  bool have = false;
+  K2B_TRY(ensure_dec_table(h, &have));
+  if (!have) return fail(h, K2B_ERR_STATE, "cluster search: the memoised decoder table could not be allocated");
   h->tc_ready = true;
   return K2B_OK;
 }

@@ -166,7 +166,6 @@ int32_t state_pool_restack(k2b_handle* h, const int32_t* slots, int B, const int
   if (unstack) restack_kernel<true><<<grid, 256, 0, h->stream>>>(p->mem, p->slot_stride, p->d_slots, B, p->d_td, p->d_chunks, stacked_dev);
   else restack_kernel<false><<<grid, 256, 0, h->stream>>>(p->mem, p->slot_stride, p->d_slots, B, p->d_td, p->d_chunks, stacked_dev);
   K2B_LAUNCH_CHECK(h);
-  h->launches++;
   return K2B_OK;
 }
 
