@@ -252,11 +252,12 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
       const int col0 = tile_n * kEN;
       const int nval = min(kEN, a.nvalid - col0);
       constexpr int kNone = (int)0x80000000;
-      for (int rr = 0; rr < kEM / kProducers; rr += 2) {
-        float v[2][8];
-        int pk[2][8];
+      constexpr int kRI = 4;             // rows in flight per warp: independent REDUX chains hide each other's latency
+      for (int rr = 0; rr < kEM / kProducers; rr += kRI) {
+        float v[kRI][8];
+        int pk[kRI][8];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < kRI; ++r) {
           const int row = pw * (kEM / kProducers) + rr + r;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -267,11 +268,13 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
             pk[r][j] = pos < nval ? ((key & ~255) | pos) : kNone;
           }
         }
-        int keep[2] = {kNone, kNone};
-        float mx[2], sum[2];
+        int keep[kRI];
+#pragma unroll
+        for (int r = 0; r < kRI; ++r) keep[r] = kNone;
+        float mx[kRI], sum[kRI];
         for (int q = 0; q < K; ++q) {
 #pragma unroll
-          for (int r = 0; r < 2; ++r) {
+          for (int r = 0; r < kRI; ++r) {
             const int hk = max(max(max(pk[r][0], pk[r][1]), max(pk[r][2], pk[r][3])), max(max(pk[r][4], pk[r][5]), max(pk[r][6], pk[r][7])));
             const int wk = __reduce_max_sync(0xffffffffu, hk);
 #pragma unroll
@@ -294,7 +297,7 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
           }
         }
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < kRI; ++r) {
           const int row = pw * (kEM / kProducers) + rr + r;
           const int m = tile_m * kEM + row;
           if (m < a.M) {
