@@ -83,7 +83,10 @@ __device__ __noinline__ void topk_insert(float* tv, int* ti, int K, float v, int
   *thr_i = ti[K - 1];
 }
 
-__global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs a) {
+// EW = warps that run the epilogue: the 8 producer warps, or 16 (the joiner with a TMA-fed A operand has nothing to produce, so
+// eight more warps share its reducing epilogue - the longest serial part of a tile).
+template <int EW>
+__global__ void __launch_bounds__((2 + EW) * 32, 1) encproj_tc_kernel(const EncArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_w[kStages], full_a[kStages], empty[kStages], acc_full;
   __shared__ uint32_t tmem_slot;
@@ -106,7 +109,7 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, 256);
-  for (int c = tid; c < kEN; c += kEThreads) {
+  for (int c = tid; c < kEN; c += (2 + EW) * 32) {
     const int col = tile_n * kEN + c;
     bias_t[c] = col < a.nvalid ? __ldg(a.bias + col) : -INFINITY;
   }
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
         }
       }
     }
-    for (int kb = 0; kb < (a.pro == 2 ? 0 : nkb); ++kb) {
+    for (int kb = 0; kb < ((a.pro == 2 || pw >= kProducers) ? 0 : nkb); ++kb) {
       const int s = kb % kStages;
       const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
       if (!mbar_wait(&empty[s], ph ^ 1u)) ok = false;
@@ -235,10 +238,10 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
       float* tile = reinterpret_cast<float*>(smem);
       constexpr int kTS = kEN + 1;
       {
-        const int lg = warp & 3, chalf = pw >> 2;
+        const int lg = warp & 3, cq = pw >> 2;            // EW / 4 column chunks of kEN * 4 / EW columns
         const int row = lg * 32 + lane;
         const uint32_t trow = t_d + ((uint32_t)(lg * 32) << 16);
-        for (int c0 = chalf * 128; c0 < chalf * 128 + 128; c0 += 32) {
+        for (int c0 = cq * (kEN * 4 / EW); c0 < (cq + 1) * (kEN * 4 / EW); c0 += 32) {
           uint32_t u[32];
           tmem_ld32(trow + (uint32_t)c0, u);
           tmem_ld_wait();
@@ -247,18 +250,18 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
         }
       }
       tc_fence_before();
-      named_bar_sync(1, kProducers * 32);
+      named_bar_sync(1, EW * 32);
       const int K = a.topk;
       const int col0 = tile_n * kEN;
       const int nval = min(kEN, a.nvalid - col0);
       constexpr int kNone = (int)0x80000000;
       constexpr int kRI = 4;             // rows in flight per warp: independent REDUX chains hide each other's latency
-      for (int rr = 0; rr < kEM / kProducers; rr += kRI) {
+      for (int rr = 0; rr < kEM / EW; rr += kRI) {
         float v[kRI][8];
         int pk[kRI][8];
 #pragma unroll
         for (int r = 0; r < kRI; ++r) {
-          const int row = pw * (kEM / kProducers) + rr + r;
+          const int row = pw * (kEM / EW) + rr + r;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int pos = lane + 32 * j;
@@ -298,7 +301,7 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
         }
 #pragma unroll
         for (int r = 0; r < kRI; ++r) {
-          const int row = pw * (kEM / kProducers) + rr + r;
+          const int row = pw * (kEM / EW) + rr + r;
           const int m = tile_m * kEM + row;
           if (m < a.M) {
             const size_t po = (size_t)m * ntn + tile_n;
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(kEThreads, 1) encproj_tc_kernel(const EncArgs 
         }
         __syncwarp();
       }
-    } else if (a.epi == 0 || a.epi == 4) {
+    } else if ((a.epi == 0 || a.epi == 4) && pw < kProducers) {
       // ---- store epilogues, all eight warps: accumulator -> shared memory (row stride 260 words: 16-byte vector accesses both
       //      ways without bank conflicts), then one warp per row with the lanes across the 256 columns, so bias / encoder frame
       //      loads and the output stores are coalesced 512-byte rows
@@ -444,8 +447,13 @@ static int32_t launch_tc(k2b_handle* h, EncArgs& a) {
   a.status = h->dev_status + 1;
   const int tiles = ((a.M + kEM - 1) / kEM) * (a.N / kEN);
   const size_t smem = (size_t)kStages * kStageBytes;
-  K2B_CUDA(h, cudaFuncSetAttribute(encproj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  encproj_tc_kernel<<<tiles, kEThreads, smem, h->stream>>>(a);
+  K2B_CUDA(h, cudaFuncSetAttribute(encproj_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (a.pro == 2 && a.epi == 2) {
+    K2B_CUDA(h, cudaFuncSetAttribute(encproj_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    encproj_tc_kernel<16><<<tiles, 18 * 32, smem, h->stream>>>(a);
+  } else {
+    encproj_tc_kernel<8><<<tiles, kEThreads, smem, h->stream>>>(a);
+  }
   K2B_LAUNCH_CHECK(h);
   return K2B_OK;
 }
