@@ -12,11 +12,12 @@
 //   * the stateless decoder is memoised at weight-load time: dec_tab[(y0+1)*V + y1] = exp(2*decoder(y0,y1))
 //     for every context (513 MB at V=500 - HBM capacity traded for a GEMM per step), the frames arrive as
 //     exp(2*enc), and the joiner prologue tanh(enc+dec) = 1 - 2/(1 + Ee*Ed) costs one MUFU per element;
-//   * epilogue: TMEM -> registers (+bias) -> shared transpose -> per hypothesis max / sum-exp / top-K with
-//     warp REDUX; the (2+2K)-word partial of every (slice, hypothesis) is written into every CTA of the cluster
-//     through distributed shared memory; one cluster barrier; every CTA then runs the hypothesis merge
-//     (log_softmax constants, per-stream top-K, dedupe by sequence hash, log-add, prune) redundantly and
-//     deterministically, so no second exchange is needed. CTA 0 records the back-pointers.
+//   * epilogue: TMEM -> registers (+bias) -> shared transpose (all 16 worker warps) -> per hypothesis sum-exp (fixed-point REDUX)
+//     and top-K (unique packed keys, one REDUX per round); the (2+2K)-word record of every (slice, hypothesis) goes to every
+//     other CTA of the cluster with st.async stores that complete on the destination's mbarrier - no barrier.cluster in the
+//     frame loop; every CTA then runs the hypothesis merge (log_softmax constants, per-stream top-K, dedupe by sequence hash,
+//     log-add, prune) redundantly and deterministically, so no second exchange is needed. CTA 0 records the back-pointers.
+//   * 17 warps: 16 workers + one that only issues the MMAs, K-quarter by K-quarter as the operand lands.
 #include <math.h>
 #include <stdlib.h>
 
