@@ -20,6 +20,9 @@ namespace {
 using namespace ptx;
 
 constexpr int kEM = 128, kEN = 256, kBKc = 64, kStages = 2;
+// The per-frame joiner uses 160-column vocabulary tiles: 35 x 8 = 280 tiles at V = 5537 run as two waves of small tiles on 148
+// SMs, where 256-column tiles (22 x 8 = 176) run as two waves of large ones.
+constexpr int kJN = 160;
 constexpr int kATile = kEM * 128;        // 16 KB: 128 rows x 64 bf16
 constexpr int kWTile = kEN * 128;        // 32 KB
 constexpr int kStageBytes = 2 * kATile + 2 * kWTile;   // 96 KB
@@ -85,8 +88,11 @@ __device__ __noinline__ void topk_insert(float* tv, int* ti, int K, float v, int
 
 // EW = warps that run the epilogue: the 8 producer warps, or 16 (the joiner with a TMA-fed A operand has nothing to produce, so
 // eight more warps share its reducing epilogue - the longest serial part of a tile).
-template <int EW>
+template <int EW, int BN>
 __global__ void __launch_bounds__((2 + EW) * 32, 1) encproj_tc_kernel(const EncArgs a) {
+  constexpr int kEN = BN;                                  // tile width of this instantiation (shadows the default)
+  constexpr int kWTile = kEN * 128;
+  constexpr int kStageBytes = 2 * kATile + 2 * kWTile;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_w[kStages], full_a[kStages], empty[kStages], acc_full;
   __shared__ uint32_t tmem_slot;
@@ -241,12 +247,24 @@ __global__ void __launch_bounds__((2 + EW) * 32, 1) encproj_tc_kernel(const EncA
         const int lg = warp & 3, cq = pw >> 2;            // EW / 4 column chunks of kEN * 4 / EW columns
         const int row = lg * 32 + lane;
         const uint32_t trow = t_d + ((uint32_t)(lg * 32) << 16);
-        for (int c0 = cq * (kEN * 4 / EW); c0 < (cq + 1) * (kEN * 4 / EW); c0 += 32) {
-          uint32_t u[32];
-          tmem_ld32(trow + (uint32_t)c0, u);
-          tmem_ld_wait();
+        constexpr int kChunk = kEN * 4 / EW;               // columns of this warp
+        if constexpr (kChunk % 32 == 0) {
+          for (int c0 = cq * kChunk; c0 < (cq + 1) * kChunk; c0 += 32) {
+            uint32_t u[32];
+            tmem_ld32(trow + (uint32_t)c0, u);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) tile[row * kTS + c0 + j] = __uint_as_float(u[j]) + bias_t[c0 + j];
+            for (int j = 0; j < 32; ++j) tile[row * kTS + c0 + j] = __uint_as_float(u[j]) + bias_t[c0 + j];
+          }
+        } else {
+          static_assert(kChunk % 8 == 0, "tile width / epilogue warps");
+          for (int c0 = cq * kChunk; c0 < (cq + 1) * kChunk; c0 += 8) {
+            uint32_t u[8];
+            tmem_ld8(trow + (uint32_t)c0, u);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tile[row * kTS + c0 + j] = __uint_as_float(u[j]) + bias_t[c0 + j];
+          }
         }
       }
       tc_fence_before();
@@ -257,13 +275,14 @@ __global__ void __launch_bounds__((2 + EW) * 32, 1) encproj_tc_kernel(const EncA
       constexpr int kNone = (int)0x80000000;
       constexpr int kRI = 4;             // rows in flight per warp: independent REDUX chains hide each other's latency
       for (int rr = 0; rr < kEM / EW; rr += kRI) {
-        float v[kRI][8];
-        int pk[kRI][8];
+        constexpr int VPL = kEN / 32;        // logits per lane and row
+        float v[kRI][VPL];
+        int pk[kRI][VPL];
 #pragma unroll
         for (int r = 0; r < kRI; ++r) {
           const int row = pw * (kEM / EW) + rr + r;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < VPL; ++j) {
             const int pos = lane + 32 * j;
             v[r][j] = tile[row * kTS + pos];
             const int kb = __float_as_int(v[r][j]);
@@ -278,10 +297,12 @@ __global__ void __launch_bounds__((2 + EW) * 32, 1) encproj_tc_kernel(const EncA
         for (int q = 0; q < K; ++q) {
 #pragma unroll
           for (int r = 0; r < kRI; ++r) {
-            const int hk = max(max(max(pk[r][0], pk[r][1]), max(pk[r][2], pk[r][3])), max(max(pk[r][4], pk[r][5]), max(pk[r][6], pk[r][7])));
+            int hk = pk[r][0];
+#pragma unroll
+            for (int j = 1; j < VPL; ++j) hk = max(hk, pk[r][j]);
             const int wk = __reduce_max_sync(0xffffffffu, hk);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) pk[r][j] = (pk[r][j] == wk) ? kNone : pk[r][j];
+            for (int j = 0; j < VPL; ++j) pk[r][j] = (pk[r][j] == wk) ? kNone : pk[r][j];
             keep[r] = (lane == q) ? wk : keep[r];
             if (q == 0) {
               const int mk = wk & ~255;
@@ -289,7 +310,7 @@ __global__ void __launch_bounds__((2 + EW) * 32, 1) encproj_tc_kernel(const EncA
               const float mneg = (wk == kNone) ? 0.f : -mx[r] * 1.4426950408889634f;
               float ls = 0.f;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
+              for (int j = 0; j < VPL; ++j) {
                 float ex;
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fmaf(v[r][j], 1.4426950408889634f, mneg)));
                 ls += (lane + 32 * j < nval) ? ex : 0.f;
@@ -316,7 +337,7 @@ __global__ void __launch_bounds__((2 + EW) * 32, 1) encproj_tc_kernel(const EncA
         }
         __syncwarp();
       }
-    } else if ((a.epi == 0 || a.epi == 4) && pw < kProducers) {
+    } else if (kEN == 256 && (a.epi == 0 || a.epi == 4) && pw < kProducers) {
       // ---- store epilogues, all eight warps: accumulator -> shared memory (row stride 260 words: 16-byte vector accesses both
       //      ways without bank conflicts), then one warp per row with the lanes across the 256 columns, so bias / encoder frame
       //      loads and the output stores are coalesced 512-byte rows
@@ -412,13 +433,13 @@ __global__ void __launch_bounds__((2 + EW) * 32, 1) encproj_tc_kernel(const EncA
   if (warp == 0) tmem_dealloc(t_d, 256);
 }
 
-__global__ void pack_enc_w_kernel(const float* __restrict__ w, int N, int K, uint8_t* __restrict__ hi, uint8_t* __restrict__ lo) {
+__global__ void pack_enc_w_kernel(const float* __restrict__ w, int N, int K, int BN, uint8_t* __restrict__ hi, uint8_t* __restrict__ lo) {
   const int n = blockIdx.x;                 // weight row
-  const int tn = n / kEN, r = n % kEN, nkb = K / kBKc;
+  const int tn = n / BN, r = n % BN, nkb = K / kBKc;
   for (int k = 2 * threadIdx.x; k < K; k += 2 * blockDim.x) {
     const float x0 = w[(size_t)n * K + k], x1 = w[(size_t)n * K + k + 1];
     const float h0 = bf16_round(x0), h1 = bf16_round(x1);
-    const size_t off = ((size_t)tn * nkb + (k >> 6)) * kWTile + sw128_offset(r, k & 63);
+    const size_t off = ((size_t)tn * nkb + (k >> 6)) * ((size_t)BN * 128) + sw128_offset(r, k & 63);
     *reinterpret_cast<uint32_t*>(hi + off) = pack_bf16x2(h0, h1);
     *reinterpret_cast<uint32_t*>(lo + off) = pack_bf16x2(x0 - h0, x1 - h1);
   }
@@ -436,26 +457,29 @@ int32_t ensure_encproj_assets(k2b_handle* h) {
   const int N = h->cfg.joiner_dim, K = h->cfg.encoder_dim;
   K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->we_hi_img), (size_t)N * K * 2));
   K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->we_lo_img), (size_t)N * K * 2));
-  pack_enc_w_kernel<<<N, 128, 0, h->stream>>>(h->enc_w, N, K, h->we_hi_img, h->we_lo_img);
+  pack_enc_w_kernel<<<N, 128, 0, h->stream>>>(h->enc_w, N, K, kEN, h->we_hi_img, h->we_lo_img);
   K2B_LAUNCH_CHECK(h);
   h->enc_ready = true;
   return K2B_OK;
 }
 
+template <int EW, int BN>
+static int32_t launch_tc_as(k2b_handle* h, const EncArgs& a) {
+  const int tiles = ((a.M + kEM - 1) / kEM) * (a.N / BN);
+  const size_t smem = (size_t)kStages * (2 * kATile + 2 * BN * 128);
+  K2B_CUDA(h, cudaFuncSetAttribute(encproj_tc_kernel<EW, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  encproj_tc_kernel<EW, BN><<<tiles, (2 + EW) * 32, smem, h->stream>>>(a);
+  K2B_LAUNCH_CHECK(h);
+  return K2B_OK;
+}
+
+// joiner launches (epi 2 / 3) use kJN-column tiles - their weight images are packed that way -, everything else kEN
 static int32_t launch_tc(k2b_handle* h, EncArgs& a) {
   a.x3 = h->cfg.precision == K2B_PREC_BF16 ? 0 : 1;
   a.status = h->dev_status + 1;
-  const int tiles = ((a.M + kEM - 1) / kEM) * (a.N / kEN);
-  const size_t smem = (size_t)kStages * kStageBytes;
-  K2B_CUDA(h, cudaFuncSetAttribute(encproj_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (a.pro == 2 && a.epi == 2) {
-    K2B_CUDA(h, cudaFuncSetAttribute(encproj_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    encproj_tc_kernel<16><<<tiles, 18 * 32, smem, h->stream>>>(a);
-  } else {
-    encproj_tc_kernel<8><<<tiles, kEThreads, smem, h->stream>>>(a);
-  }
-  K2B_LAUNCH_CHECK(h);
-  return K2B_OK;
+  if (a.epi == 2 && a.pro == 2) return launch_tc_as<16, kJN>(h, a);
+  if (a.epi == 2 || a.epi == 3) return launch_tc_as<8, kJN>(h, a);
+  return launch_tc_as<8, kEN>(h, a);
 }
 
 // raw [n,E] -> out [n,J] = f(raw * We^T + be) on tcgen05; f = identity or exp(2*clamp(., +-21))
@@ -517,7 +541,7 @@ int32_t decoder_joinin_tc(k2b_handle* h, const int32_t* ctx, int M, const float*
     const int N = h->cfg.joiner_dim, K = h->cfg.decoder_dim;
     K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->wd_hi_img), (size_t)N * K * 2));
     K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->wd_lo_img), (size_t)N * K * 2));
-    pack_enc_w_kernel<<<N, 128, 0, h->stream>>>(h->dec_w, N, K, h->wd_hi_img, h->wd_lo_img);
+    pack_enc_w_kernel<<<N, 128, 0, h->stream>>>(h->dec_w, N, K, kEN, h->wd_hi_img, h->wd_lo_img);
     K2B_LAUNCH_CHECK(h);
     h->wd_ready = true;
   }
@@ -534,16 +558,16 @@ int32_t decoder_joinin_tc(k2b_handle* h, const int32_t* ctx, int M, const float*
 // ---- per-frame tensor-core joiner (any vocabulary): logits tile = x * out_w^T + out_b, reduced in the epilogue ----------
 bool joiner_tc_supported(const k2b_handle* h) { return h->cfg.joiner_dim % 64 == 0 && h->out_w != nullptr; }
 
-int joiner_tc_tiles(const k2b_handle* h) { return (h->cfg.vocab_size + kEN - 1) / kEN; }
+int joiner_tc_tiles(const k2b_handle* h) { return (h->cfg.vocab_size + kJN - 1) / kJN; }
 
 static int32_t ensure_joiner_assets(k2b_handle* h) {
   if (h->wj_ready) return K2B_OK;
-  const int V = h->cfg.vocab_size, K = h->cfg.joiner_dim, Np = joiner_tc_tiles(h) * kEN;
+  const int V = h->cfg.vocab_size, K = h->cfg.joiner_dim, Np = joiner_tc_tiles(h) * kJN;
   K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->wj_hi_img), (size_t)Np * K * 2));
   K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->wj_lo_img), (size_t)Np * K * 2));
   K2B_CUDA(h, cudaMemsetAsync(h->wj_hi_img, 0, (size_t)Np * K * 2, h->stream));
   K2B_CUDA(h, cudaMemsetAsync(h->wj_lo_img, 0, (size_t)Np * K * 2, h->stream));
-  pack_enc_w_kernel<<<V, 128, 0, h->stream>>>(h->out_w, V, K, h->wj_hi_img, h->wj_lo_img);
+  pack_enc_w_kernel<<<V, 128, 0, h->stream>>>(h->out_w, V, K, kJN, h->wj_hi_img, h->wj_lo_img);
   K2B_LAUNCH_CHECK(h);
   h->wj_ready = true;
   return K2B_OK;
@@ -560,7 +584,7 @@ int32_t joiner_tc_partials(k2b_handle* h, const float* x, const uint8_t* x_img, 
   EncArgs a = {};
   a.A = x; a.w_hi_img = h->wj_hi_img; a.w_lo_img = h->wj_lo_img; a.bias = h->out_b; a.C = nullptr;
   if (x_img != nullptr) { a.pro = 2; a.a_img = x_img; }
-  a.M = M; a.N = joiner_tc_tiles(h) * kEN; a.K = h->cfg.joiner_dim;
+  a.M = M; a.N = joiner_tc_tiles(h) * kJN; a.K = h->cfg.joiner_dim;
   a.exp2x = 0;
   a.epi = topk > 0 ? 2 : 3; a.nvalid = h->cfg.vocab_size; a.topk = topk;
   a.part_m = part_m; a.part_s = part_s; a.part_tv = part_tv; a.part_ti = part_ti;
