@@ -385,6 +385,7 @@ int32_t k2b_reset_launch_count(k2b_handle* h) {
 int32_t k2b_profile_enable(k2b_handle* h, int32_t on) {
   K2B_TRY(enter(h));
   h->profile_on = on != 0;
+  if (const char* w = getenv("K2B_PROF_WHICH")) h->prof_which = atoi(w);
   return K2B_OK;
 }
 

@@ -10,6 +10,8 @@
 //               afterwards the same four warps are the epilogue: TMEM -> registers -> +bias -> optional exp(2x)
 //               (the form the cluster search kernel's tanh prologue consumes) -> global.
 // Algorithmic HBM traffic: M*K*4 (frames in) + M*N*4 (projected frames out); the weights stay in L2.
+#include <stdlib.h>
+
 #include "k2b_internal.h"
 #include "sm100_ptx.cuh"
 
@@ -55,6 +57,7 @@ struct EncArgs {
   // convert the same fp32 rows 22 times.
   uint8_t* x_img;
   const uint8_t* a_img;
+  long long* dbg;            // diagnostic (null in production): CTA 0 adds its phase cycle counts to dbg[10..14]
 };
 
 __device__ __forceinline__ int table_row_e(int y, int V, int neg_wrap) {
@@ -99,6 +102,7 @@ __global__ void __launch_bounds__((2 + EW) * 32, 1) encproj_tc_kernel(const EncA
   __shared__ __align__(16) float bias_t[kEN];          // this tile's bias (-inf beyond the valid columns): broadcast reads in the epilogue
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long c_start = a.dbg != nullptr ? clock64() : 0;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   const int ntn = a.N / kEN;
   const int tile_m = blockIdx.x / ntn, tile_n = blockIdx.x - tile_m * ntn;
@@ -239,7 +243,9 @@ __global__ void __launch_bounds__((2 + EW) * 32, 1) encproj_tc_kernel(const EncA
       //     logit with its low 8 bits replaced by the column, so they are unique and one REDUX per round finds value and
       //     position at once (values closer than 2^-15 relative resolve to the larger vocabulary index; the exact fp32
       //     logit is re-read for the record); sum-exp is a fixed-point REDUX (order-independent).
+      const bool dbg = a.dbg != nullptr && blockIdx.x == 0 && tid == 64;
       if (!mbar_wait(&acc_full, 0)) ok = false;
+      const long long c_acc = dbg ? clock64() : 0;
       tc_fence_after();
       float* tile = reinterpret_cast<float*>(smem);
       constexpr int kTS = kEN + 1;
@@ -269,6 +275,7 @@ __global__ void __launch_bounds__((2 + EW) * 32, 1) encproj_tc_kernel(const EncA
       }
       tc_fence_before();
       named_bar_sync(1, EW * 32);
+      const long long c_tile = dbg ? clock64() : 0;
       const int K = a.topk;
       const int col0 = tile_n * kEN;
       const int nval = min(kEN, a.nvalid - col0);
@@ -336,6 +343,13 @@ __global__ void __launch_bounds__((2 + EW) * 32, 1) encproj_tc_kernel(const EncA
           }
         }
         __syncwarp();
+      }
+      if (dbg) {
+        const long long c_end = clock64();
+        atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg + 10), (unsigned long long)(c_acc - c_start));
+        atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg + 11), (unsigned long long)(c_tile - c_acc));
+        atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg + 12), (unsigned long long)(c_end - c_tile));
+        atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg + 13), 1ull);
       }
     } else if (kEN == 256 && (a.epi == 0 || a.epi == 4) && pw < kProducers) {
       // ---- store epilogues, all eight warps: accumulator -> shared memory (row stride 260 words: 16-byte vector accesses both
@@ -501,9 +515,11 @@ __global__ void joinin_table_kernel(const float* __restrict__ dec_tab, const int
                                     const float* __restrict__ enc, long long enc_stride, int rows_per_stream,
                                     uint8_t* __restrict__ x_img) {
   const int m = blockIdx.x, k = 4 * threadIdx.x;
+  griddep_launch_dependents();
   if (k >= J) return;
-  const float4 d = __ldg(reinterpret_cast<const float4*>(dec_tab + ((size_t)(ctx[2 * m] + 1) * V + ctx[2 * m + 1]) * J + k));
   const float4 e = __ldg(reinterpret_cast<const float4*>(enc + (size_t)(m / rows_per_stream) * enc_stride + k));
+  griddep_wait();           // the contexts are the merge kernel's output; the frames are not
+  const float4 d = __ldg(reinterpret_cast<const float4*>(dec_tab + ((size_t)(ctx[2 * m] + 1) * V + ctx[2 * m + 1]) * J + k));
   float x[4];
   const float ev[4] = {e.x, e.y, e.z, e.w}, dv[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
@@ -523,8 +539,8 @@ __global__ void joinin_table_kernel(const float* __restrict__ dec_tab, const int
 int32_t joinin_table_tc(k2b_handle* h, const int32_t* ctx, int M, const float* enc, long long enc_stride, int rows_per_stream,
                         uint8_t* x_img) {
   const int J = h->cfg.joiner_dim;
-  joinin_table_kernel<<<M, (J / 4 + 31) / 32 * 32, 0, h->stream>>>(h->dec_tab, ctx, M, h->cfg.vocab_size, J, enc, enc_stride,
-                                                                      rows_per_stream, x_img);
+  K2B_CUDA(h, launch_pdl(joinin_table_kernel, dim3(M), dim3((J / 4 + 31) / 32 * 32), 0, h->stream, (const float*)h->dec_tab, ctx, M,
+                          h->cfg.vocab_size, J, enc, enc_stride, rows_per_stream, x_img));
   K2B_LAUNCH_CHECK(h);
   return K2B_OK;
 }
@@ -581,6 +597,11 @@ size_t joiner_tc_image_bytes(const k2b_handle* h, int M) {
 int32_t joiner_tc_partials(k2b_handle* h, const float* x, const uint8_t* x_img, int M, int topk, float* part_m, float* part_s,
                            float* part_tv, int32_t* part_ti, float* part_val, int32_t* part_idx, int32_t* part_nan) {
   K2B_TRY(ensure_joiner_assets(h));
+  // beam search with a TMA-fed operand: the persistent kernel of joiner_tc.cu (K2B_OLD_JOINER=1 keeps the one-tile-per-CTA kernel
+  // below, for comparison runs)
+  static const bool old_joiner = getenv("K2B_OLD_JOINER") != nullptr;
+  if (x_img != nullptr && topk > 0 && !old_joiner && joiner_topk_supported(h, topk))
+    return joiner_topk_tc(h, x_img, M, topk, part_m, part_s, part_tv, part_ti);
   EncArgs a = {};
   a.A = x; a.w_hi_img = h->wj_hi_img; a.w_lo_img = h->wj_lo_img; a.bias = h->out_b; a.C = nullptr;
   if (x_img != nullptr) { a.pro = 2; a.a_img = x_img; }
@@ -589,6 +610,7 @@ int32_t joiner_tc_partials(k2b_handle* h, const float* x, const uint8_t* x_img, 
   a.epi = topk > 0 ? 2 : 3; a.nvalid = h->cfg.vocab_size; a.topk = topk;
   a.part_m = part_m; a.part_s = part_s; a.part_tv = part_tv; a.part_ti = part_ti;
   a.part_val = part_val; a.part_idx = part_idx; a.part_nan = part_nan;
+  a.dbg = h->cluster_timing;
   return launch_tc(h, a);
 }
 

@@ -1,0 +1,286 @@
+// Per-frame fused joiner for large vocabularies (cfg4: V = 5537): logits tile = x * out_w^T + out_b on tcgen05, reduced to
+// softmax / top-k partials in the epilogue - the logits never reach HBM (ref JoinerProj, OfflineProjOfTransducer.cs:125-152,
+// followed by the log_softmax / top-k of modified_beam_search [EXT]).
+//
+// Persistent: one CTA per SM walks the 128 x 160 output tiles (280 at M = 1024, V = 5537: two per CTA) with
+//   warp 0      loader: bulk TMA copies of the pre-swizzled bf16 hi / lo images of both operands (x was left in that form by the
+//               operand kernel, out_w is packed at load time) into a 2-stage ring of 72 KB stages;
+//   warp 1      MMA issuer (warp-uniform loop, one elected lane): tcgen05.mma M = 128, N = 160, K = 16, split-bf16 x3, into one
+//               of TWO TMEM accumulators, so the mainloop of tile i+1 runs under the epilogue of tile i;
+//   warps 2-5   epilogue, one thread per logits row (= TMEM lane): pass 1 walks the 160 columns out of TMEM, adds the bias, keeps
+//               the fp32 value in a per-thread shared-memory row and pushes an order-preserving integer key (low 8 bits = column)
+//               through a branch-free max/min insertion network - no shuffles, no divergence, 7 integer ops per logit for K <= 4;
+//               pass 2 re-reads the row for the sum of exponentials and fetches the exact fp32 logits of the K winners.
+// Launched with programmatic stream serialization: barrier set-up, TMEM allocation and the first weight copies overlap the tail of
+// the operand kernel; griddepcontrol.wait precedes the first read of x and every write.
+#include <stdlib.h>
+
+#include "k2b_internal.h"
+#include "sm100_ptx.cuh"
+
+namespace k2b {
+
+namespace {
+
+using namespace ptx;
+
+constexpr int kJM = 128, kJNc = 160, kJBK = 64, kStages = 2;
+constexpr int kATile = kJM * 128;                          // 16 KB: 128 rows x 64 bf16
+constexpr int kWTile = kJNc * 128;                          // 20 KB
+constexpr int kStageBytes = 2 * kATile + 2 * kWTile;      // 72 KB
+constexpr int kTS = kJNc + 1;                               // row stride of the fp32 scratch rows (conflict-free across rows)
+constexpr int kTileBytes = kJM * kTS * 4;
+constexpr int kThreads = 192;
+constexpr int kAccCols = 256;                             // TMEM column distance of the two accumulators
+constexpr int kNoneKey = (int)0x80000000;
+constexpr int kInfKey = (int)0x807fffff;                  // keys of -inf logits (invalid columns) are <= this
+
+struct JArgs {
+  const uint8_t* a_img;      // [M/128][J/64][hi 16 KB | lo 16 KB]
+  const uint8_t* w_hi_img;   // [ntn][J/64][20 KB]
+  const uint8_t* w_lo_img;
+  const float* bias;         // [V]
+  int M, ntm, ntn, nkb, x3, nvalid, topk;
+  float* part_m; float* part_s; float* part_tv; int32_t* part_ti;     // [M,ntn], [M,ntn], [M,ntn,topk] x2
+  int* status;
+  long long* dbg;
+};
+
+template <int KK>
+__device__ __forceinline__ void push_key(int (&a)[KK], int t) {
+#pragma unroll
+  for (int i = 0; i < KK; ++i) {
+    const int hi = max(a[i], t);
+    t = min(a[i], t);
+    a[i] = hi;
+  }
+}
+
+template <int KK>
+__global__ void __launch_bounds__(kThreads, 1) joiner_topk_kernel(const JArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full[kStages], empty[kStages], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float bias_t[kJNc];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long c_start = a.dbg != nullptr ? clock64() : 0;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const int ntiles = a.ntm * a.ntn;
+  const int nkb = a.nkb;
+  const uint32_t x3 = (uint32_t)a.x3;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t t_d = tmem_slot;
+  bool ok = true;
+  griddep_launch_dependents();
+
+  if (warp_u == 0) {
+    // ---- loader ------------------------------------------------------------------------------------------------------
+    if (lane == 0) {
+      const uint32_t w_bytes = (uint32_t)(x3 ? 2 * kWTile : kWTile), a_bytes = (uint32_t)(x3 ? 2 * kATile : kATile);
+      uint32_t kc = 0;
+      bool waited = false;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int tile_n = tile / a.ntm, tile_m = tile - tile_n * a.ntm;
+        for (int kb = 0; kb < nkb; ++kb, ++kc) {
+          const int s = kc % kStages;
+          const uint32_t ph = (kc / kStages) & 1u;
+          if (!mbar_wait(&empty[s], ph ^ 1u)) ok = false;
+          uint8_t* st = smem + (size_t)s * kStageBytes;
+          const size_t off = ((size_t)tile_n * nkb + kb) * kWTile;
+          mbar_expect_tx(&full[s], w_bytes + a_bytes);
+          tma_bulk_g2s(st + 2 * kATile, a.w_hi_img + off, kWTile, &full[s]);
+          if (x3) tma_bulk_g2s(st + 2 * kATile + kWTile, a.w_lo_img + off, kWTile, &full[s]);
+          if (!waited) { griddep_wait(); waited = true; }      // x is the previous kernel's output; the weights are not
+          tma_bulk_g2s(st, a.a_img + ((size_t)tile_m * nkb + kb) * (2 * kATile), a_bytes, &full[s]);
+        }
+      }
+    }
+  } else if (warp_u == 1) {
+    // ---- MMA issuer ----------------------------------------------------------------------------------------------------
+    const uint32_t el = elect_one();
+    const uint32_t idesc = umma_idesc_bf16_f32(kJM, kJNc);
+    const uint32_t desc_hi = 64u | (1u << 14) | (2u << 29);
+    uint32_t kc = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+      if (!mbar_wait(&acc_empty[as], aph ^ 1u)) ok = false;
+      tc_fence_after();
+      const uint32_t d = t_d + (uint32_t)(as * kAccCols);
+      uint32_t acc = 0;
+      for (int kb = 0; kb < nkb; ++kb, ++kc) {
+        const int s = kc % kStages;
+        const uint32_t ph = (kc / kStages) & 1u;
+        if (!mbar_wait(&full[s], ph)) ok = false;
+        tc_fence_after();
+        const uint32_t sb = smem_u32(smem + (size_t)s * kStageBytes);
+        const uint32_t ah = (((sb) & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t al = (((sb + kATile) & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t wh = (((sb + 2 * kATile) & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t wl = (((sb + 2 * kATile + kWTile) & 0x3FFFFu) >> 4) | (1u << 16);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t dah = ((uint64_t)desc_hi << 32) | (uint64_t)(ah + 2u * k);
+          const uint64_t dwh = ((uint64_t)desc_hi << 32) | (uint64_t)(wh + 2u * k);
+          umma_ss_e(d, dah, dwh, idesc, acc, el);
+          acc = 1;
+          if (x3) {
+            const uint64_t dal = ((uint64_t)desc_hi << 32) | (uint64_t)(al + 2u * k);
+            const uint64_t dwl = ((uint64_t)desc_hi << 32) | (uint64_t)(wl + 2u * k);
+            umma_ss_e(d, dah, dwl, idesc, 1, el);
+            umma_ss_e(d, dal, dwh, idesc, 1, el);
+          }
+        }
+        umma_commit_e(&empty[s], el);       // frees the stage once these MMAs have read it
+      }
+      umma_commit_e(&acc_full[as], el);
+    }
+  } else {
+    // ---- epilogue: thread = logits row ------------------------------------------------------------------------------------
+    const int lg = warp & 3;                              // TMEM lane quarter this warp may read
+    const int row = lg * 32 + lane;
+    const int etid = tid - 64;
+    float* myrow = reinterpret_cast<float*>(smem + (size_t)kStages * kStageBytes) + (size_t)row * kTS;
+    const bool dbg = a.dbg != nullptr && blockIdx.x == 0 && tid == 64;
+    long long c_acc = 0, c_epi = 0;
+    const int K = a.topk;
+    int it = 0;
+    griddep_wait();                                       // partials are read by the previous frame's merge kernel
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int tile_n = tile / a.ntm, tile_m = tile - tile_n * a.ntm;
+      const int as = it & 1;
+      const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+      const int col0 = tile_n * kJNc;
+      named_bar_sync(1, 128);                             // every row is done with the previous tile's bias
+      for (int c = etid; c < kJNc; c += 128) bias_t[c] = col0 + c < a.nvalid ? __ldg(a.bias + col0 + c) : -INFINITY;
+      named_bar_sync(1, 128);
+      if (!mbar_wait(&acc_full[as], aph)) ok = false;
+      if (dbg && it == 0) c_acc = clock64();
+      tc_fence_after();
+      const uint32_t trow = t_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * kAccCols);
+      int key[KK];
+#pragma unroll
+      for (int i = 0; i < KK; ++i) key[i] = kNoneKey;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kJNc; c0 += 32) {
+        uint32_t u[32];
+        tmem_ld32(trow + (uint32_t)c0, u);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 bb = *reinterpret_cast<const float4*>(bias_t + c0 + 4 * q);
+          const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = 4 * q + e;
+            const float v = __uint_as_float(u[j]) + bv[e];
+            myrow[c0 + j] = v;
+            const int kb = __float_as_int(v);
+            const int ok_key = kb ^ ((kb >> 31) & 0x7fffffff);
+            push_key<KK>(key, (ok_key & ~255) | (c0 + j));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);         // the accumulator may be overwritten by tile it + 2
+      __syncwarp();
+      // pass 2: sum of exponentials against the (key-precision) maximum, then the winners' exact logits
+      const bool any = key[0] > kInfKey;
+      const int mk = key[0] & ~255;
+      const float mx = any ? __int_as_float(mk ^ ((mk >> 31) & 0x7fffffff)) : -INFINITY;
+      const float mneg = any ? -mx * 1.4426950408889634f : 0.f;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 8
+      for (int j = 0; j < kJNc; j += 4) {
+        float e0, e1, e2, e3;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(myrow[j], 1.4426950408889634f, mneg)));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(myrow[j + 1], 1.4426950408889634f, mneg)));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fmaf(myrow[j + 2], 1.4426950408889634f, mneg)));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(fmaf(myrow[j + 3], 1.4426950408889634f, mneg)));
+        s0 += e0; s1 += e1; s2 += e2; s3 += e3;
+      }
+      const int m = tile_m * kJM + row;
+      if (m < a.M) {
+        const size_t po = (size_t)m * a.ntn + tile_n;
+        a.part_m[po] = mx;
+        a.part_s[po] = any ? (s0 + s1) + (s2 + s3) : 0.f;
+#pragma unroll
+        for (int i = 0; i < KK; ++i) {
+          if (i < K) {
+            const bool has = key[i] > kInfKey;
+            const int pos = key[i] & 255;
+            a.part_tv[po * K + i] = has ? myrow[pos] : -INFINITY;
+            a.part_ti[po * K + i] = has ? col0 + pos : -1;
+          }
+        }
+      }
+      if (dbg && it == 0) c_epi = clock64();
+    }
+    if (dbg) {
+      const long long c_end = clock64();
+      atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg + 10), (unsigned long long)(c_acc - c_start));
+      atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg + 11), (unsigned long long)(c_epi - c_acc));
+      atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg + 12), (unsigned long long)(c_end - c_start));
+      atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg + 13), 1ull);
+    }
+  }
+  if (!ok) atomicExch(a.status, 1);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(t_d, 512);
+}
+
+template <int KK>
+int32_t launch_as(k2b_handle* h, const JArgs& a) {
+  static bool attr_set = false;
+  const size_t smem = (size_t)kStages * kStageBytes + kTileBytes;
+  if (!attr_set) {
+    K2B_CUDA(h, cudaFuncSetAttribute(joiner_topk_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int tiles = a.ntm * a.ntn;
+  const int grid = tiles < h->sm_count ? tiles : h->sm_count;
+  K2B_CUDA(h, launch_pdl(joiner_topk_kernel<KK>, dim3(grid), dim3(kThreads), smem, h->stream, a));
+  K2B_LAUNCH_CHECK(h);
+  return K2B_OK;
+}
+
+}  // namespace
+
+bool joiner_topk_supported(const k2b_handle* h, int topk) {
+  return topk >= 1 && topk <= 8 && h->cfg.joiner_dim % kJBK == 0 && h->wj_ready;
+}
+
+bool joiner_topk_usable(const k2b_handle* h, int topk) {
+  static const bool old_joiner = getenv("K2B_OLD_JOINER") != nullptr;
+  return !old_joiner && topk >= 1 && topk <= 8 && h->cfg.joiner_dim % kJBK == 0;
+}
+
+// x_img: the joiner operand as bf16 hi / lo tile images (joinin_table_tc / decoder_joinin_tc). Partials per (row, 160-column
+// vocabulary tile) as joiner_tc_partials writes them. The weight images must exist (ensure_joiner_assets).
+int32_t joiner_topk_tc(k2b_handle* h, const uint8_t* x_img, int M, int topk, float* part_m, float* part_s, float* part_tv,
+                       int32_t* part_ti) {
+  JArgs a = {};
+  a.a_img = x_img; a.w_hi_img = h->wj_hi_img; a.w_lo_img = h->wj_lo_img; a.bias = h->out_b;
+  a.M = M; a.ntm = (M + kJM - 1) / kJM; a.ntn = (h->cfg.vocab_size + kJNc - 1) / kJNc; a.nkb = h->cfg.joiner_dim / kJBK;
+  a.x3 = h->cfg.precision == K2B_PREC_BF16 ? 0 : 1;
+  a.nvalid = h->cfg.vocab_size; a.topk = topk;
+  a.part_m = part_m; a.part_s = part_s; a.part_tv = part_tv; a.part_ti = part_ti;
+  a.status = h->dev_status + 1;
+  a.dbg = h->cluster_timing;
+  return topk <= 4 ? launch_as<4>(h, a) : launch_as<8>(h, a);
+}
+
+}  // namespace k2b

@@ -97,6 +97,7 @@ struct k2b_handle {
   long long* cluster_timing = nullptr;   // device [8]: per-phase cycle totals of the cluster kernel (diagnostic)
 
   bool profile_on = false;
+  int prof_which = 0;             // which launch of the per-frame beam path the profile events bracket (K2B_PROF_WHICH: 0 joiner, 1 operand build, 2 merge)
   k2b::StatePool* state_pool = nullptr;   // on-device streaming state (state_pool.cu)
   int32_t* lens_dev = nullptr;    // k2b_set_encoder_out_lens: per-stream frame counts for the next fused offline search
   int lens_n = 0;
@@ -109,6 +110,19 @@ namespace k2b {
 int32_t fail(k2b_handle* h, int32_t code, const std::string& msg);
 int32_t cuda_fail(k2b_handle* h, cudaError_t e, const char* what, const char* file, int line);
 int32_t ensure(k2b_handle* h, DevBuf& b, size_t bytes);
+
+// Launch with programmatic stream serialization: the kernel may begin while the previous kernel of the stream drains (it calls
+// griddep_wait() before reading that kernel's output). Used for the back-to-back launches of the per-frame search path.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 #define K2B_CUDA(h, expr)                                                        \
   do {                                                                           \
@@ -215,6 +229,12 @@ bool joiner_tc_supported(const k2b_handle* h);
 int joiner_tc_tiles(const k2b_handle* h);
 int32_t joiner_tc_partials(k2b_handle* h, const float* x, const uint8_t* x_img, int M, int topk, float* part_m, float* part_s,
                            float* part_tv, int32_t* part_ti, float* part_val, int32_t* part_idx, int32_t* part_nan);
+
+// ---- joiner_tc.cu ------------------------------------------------------------------------------
+bool joiner_topk_supported(const k2b_handle* h, int topk);
+bool joiner_topk_usable(const k2b_handle* h, int topk);   // the persistent joiner will serve joiner_tc_partials(x_img, topk)
+int32_t joiner_topk_tc(k2b_handle* h, const uint8_t* x_img, int M, int topk, float* part_m, float* part_s, float* part_tv,
+                       int32_t* part_ti);
 
 // profiling bracket around the dominant GEMM
 void prof_begin(k2b_handle* h);

@@ -6,8 +6,10 @@
 //                     beam:   log_softmax constants, per-stream top-K over K*V, hypothesis merge
 // Nothing crosses PCIe inside the loop and the logits are never written to HBM.
 #include <math.h>
+#include <stdlib.h>
 
 #include "k2b_internal.h"
+#include "sm100_ptx.cuh"
 
 namespace k2b {
 
@@ -134,6 +136,8 @@ beam_select_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk
   const unsigned full = 0xffffffffu;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.x * 4 + wib;
+  k2b::ptx::griddep_launch_dependents();
+  k2b::ptx::griddep_wait();                             // everything read below is the output of the kernels before this one
   if (s >= B) return;
   const int nl = in.nlive[s];
   if (lens != nullptr && t >= lens[s]) {            // ragged batch: past the end of this stream, the hypotheses are frozen
@@ -323,6 +327,259 @@ beam_select_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk
   if (lane == 0) out.nlive[s] = nnew;
 }
 
+// Fused frame step of the memoised-decoder path, one CTA per stream ("hyp_merge" + the next frame's joiner operand):
+//   A. warp h <-> live hypothesis h: log_softmax constants from its tile partials, its K best extensions (all loads of a
+//      hypothesis are issued before the first use: the partials sit in L2, the kernel pays latency, not bandwidth);
+//   B. warp 0: the stream's top K over the K*K survivors (value desc, flat index desc), extension, dedupe by token-sequence hash
+//      with log-add in rank order, compaction, back-pointer record - the code of beam_select_kernel;
+//   C. all threads: x[m,:] = tanh(enc[s,t+1] + decoder(ctx[m])) of the K new hypotheses from the memoised decoder table, written
+//      as the bf16 hi / lo tile images the joiner's loader warp fetches (what joinin_table_kernel does in a launch of its own).
+// Same results as beam_select_kernel + joinin_table_kernel; one launch and one round trip of the contexts through HBM less.
+__global__ void __launch_bounds__(128)
+beam_step_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
+                 const float* __restrict__ part_m, const float* __restrict__ part_s,
+                 const float* __restrict__ part_tv, const int32_t* __restrict__ part_ti,
+                 BeamState in, BeamState out, int32_t* __restrict__ bp, const int32_t* __restrict__ lens,
+                 const float* __restrict__ dec_tab, const float* __restrict__ enc_next, long long enc_stride, int J,
+                 uint8_t* __restrict__ x_img) {
+  __shared__ float c_v[kMaxBeam * kMaxBeam];
+  __shared__ int c_f[kMaxBeam * kMaxBeam];
+  __shared__ int s_ctx[2 * kMaxBeam];
+  constexpr int kNone = (int)0x80000000;
+  constexpr int kPairs = 2, kCands = 8;            // per-lane register batches: nt <= 64, nt * K <= 256 without a tail pass
+  const unsigned full = 0xffffffffu;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int s = blockIdx.x;
+  k2b::ptx::griddep_launch_dependents();
+  // the next frame of this stream does not depend on the kernels before this one: fetch it ahead of the wait
+  const bool build = enc_next != nullptr;
+  float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (build && 4 * tid < J) e4 = __ldg(reinterpret_cast<const float4*>(enc_next + (size_t)s * enc_stride + 4 * tid));
+  k2b::ptx::griddep_wait();
+  const int nl = in.nlive[s];
+  const bool frozen = lens != nullptr && t >= lens[s];      // ragged batch: past the end of this stream
+  for (int i = tid; i < K * K; i += 128) { c_v[i] = -INFINITY; c_f[i] = -1; }
+  // parents' state, lane q of warp 0 <-> hypothesis q
+  uint64_t p_hash = kHashSeed;
+  int p_len = 2, p_c0 = -1, p_c1 = blank;
+  if (warp == 0 && lane < K) {
+    const size_t o = (size_t)s * K + lane;
+    p_hash = in.hash[o]; p_len = in.len[o]; p_c0 = in.ctx[2 * o]; p_c1 = in.ctx[2 * o + 1];
+  }
+  __syncthreads();
+  if (frozen) {
+    if (warp == 0) {
+      if (lane < K) {
+        const size_t o = (size_t)s * K + lane;
+        out.ctx[2 * o] = p_c0; out.ctx[2 * o + 1] = p_c1;
+        out.lp[o] = in.lp[o]; out.len[o] = p_len; out.hash[o] = p_hash;
+        bp[((size_t)s * T + t) * K + lane] = lane < nl ? (lane << 28) : 0;
+        s_ctx[2 * lane] = p_c0; s_ctx[2 * lane + 1] = p_c1;
+      }
+      if (lane == 0) out.nlive[s] = nl;
+    }
+  } else {
+    // ---- A: per live hypothesis --------------------------------------------------------------------------------------------
+    for (int h = warp; h < nl; h += 4) {
+      const size_t row = (size_t)s * K + h;
+      const float* pmr = part_m + row * nt;
+      const float* psr = part_s + row * nt;
+      const size_t cbase = row * nt * K;
+      const int ncand = nt * K;
+      float pm[kPairs], ps[kPairs], cval[kCands];
+      int cidx[kCands];
+#pragma unroll
+      for (int u = 0; u < kPairs; ++u) {
+        const int i = lane + 32 * u;
+        pm[u] = i < nt ? pmr[i] : -INFINITY;
+        ps[u] = i < nt ? psr[i] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kCands; ++u) {
+        const int c = lane + 32 * u;
+        cidx[u] = c < ncand ? part_ti[cbase + c] : -1;
+        cval[u] = c < ncand ? part_tv[cbase + c] : 0.f;
+      }
+      const float lp = in.lp[row];
+      int mk = kNone;
+#pragma unroll
+      for (int u = 0; u < kPairs; ++u) mk = max(mk, lane + 32 * u < nt ? fkey_s(pm[u]) : kNone);
+      for (int i = lane + 32 * kPairs; i < nt; i += 32) mk = max(mk, fkey_s(pmr[i]));
+      const float mx = funkey_s(__reduce_max_sync(full, mk));
+      float sum = 0.f;
+#pragma unroll
+      for (int u = 0; u < kPairs; ++u) sum += (pm[u] > -INFINITY) ? ps[u] * __expf(pm[u] - mx) : 0.f;
+      for (int i = lane + 32 * kPairs; i < nt; i += 32) {
+        const float m2 = pmr[i];
+        sum += (m2 > -INFINITY) ? psr[i] * __expf(m2 - mx) : 0.f;
+      }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(full, sum, o);
+      const float ls = __logf(sum);
+      // lane-local top-K (sorted, best first), then K rounds of warp arg-best (REDUX on the key, then on the flat index)
+      int tk[kMaxBeam], tf[kMaxBeam];
+#pragma unroll
+      for (int i = 0; i < kMaxBeam; ++i) { tk[i] = kNone; tf[i] = -1; }
+      auto push = [&](float val, int idx) {
+        // same operation order as log_softmax(x) + lp : ((x - max) - log(sum)) + lp
+        const float v = ((val - mx) - ls) + lp;
+        const bool okc = (idx >= 0) & (v == v);
+        int key = okc ? fkey_s(v) : kNone;
+        int f = okc ? h * V + idx : -1;
+#pragma unroll
+        for (int i = 0; i < kMaxBeam; ++i) {
+          if (i < K) {
+            const bool b = (key > tk[i]) | ((key == tk[i]) & (f > tf[i]));
+            const int nk = b ? tk[i] : key, nf = b ? tf[i] : f;
+            tk[i] = b ? key : tk[i]; tf[i] = b ? f : tf[i];
+            key = nk; f = nf;
+          }
+        }
+      };
+#pragma unroll
+      for (int u = 0; u < kCands; ++u) push(cval[u], cidx[u]);
+      for (int c = lane + 32 * kCands; c < ncand; c += 32) push(part_tv[cbase + c], part_ti[cbase + c]);
+#pragma unroll
+      for (int r = 0; r < kMaxBeam; ++r) {
+        if (r < K) {
+          const int wk = __reduce_max_sync(full, tk[0]);
+          const int wf = __reduce_max_sync(full, (tk[0] == wk) ? tf[0] : -1);
+          const bool pop = (tf[0] == wf) & (wf >= 0);      // flat indices are unique: exactly one lane pops
+#pragma unroll
+          for (int i = 0; i + 1 < kMaxBeam; ++i) { tk[i] = pop ? tk[i + 1] : tk[i]; tf[i] = pop ? tf[i + 1] : tf[i]; }
+          tk[kMaxBeam - 1] = pop ? kNone : tk[kMaxBeam - 1]; tf[kMaxBeam - 1] = pop ? -1 : tf[kMaxBeam - 1];
+          if (lane == r) { c_v[h * K + r] = wf >= 0 ? funkey_s(wk) : -INFINITY; c_f[h * K + r] = wf; }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- B: the stream's top K, extension, merge ---------------------------------------------------------------------------
+    if (warp == 0) {
+      int tk[2], tf[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = lane + 32 * u;
+        const bool okc = i < K * K && c_f[i] >= 0;
+        tk[u] = okc ? fkey_s(c_v[i]) : kNone;
+        tf[u] = okc ? c_f[i] : -1;
+      }
+      if ((tk[1] > tk[0]) | ((tk[1] == tk[0]) & (tf[1] > tf[0]))) {
+        const int a = tk[0], b = tf[0];
+        tk[0] = tk[1]; tf[0] = tf[1]; tk[1] = a; tf[1] = b;
+      }
+      float my_v = -INFINITY;
+      int my_f = -1;
+#pragma unroll
+      for (int r = 0; r < kMaxBeam; ++r) {
+        if (r < K) {
+          const int wk = __reduce_max_sync(full, tk[0]);
+          const int wf = __reduce_max_sync(full, (tk[0] == wk) ? tf[0] : -1);
+          const bool pop = (tf[0] == wf) & (wf >= 0);
+          tk[0] = pop ? tk[1] : tk[0]; tf[0] = pop ? tf[1] : tf[0];
+          tk[1] = pop ? kNone : tk[1]; tf[1] = pop ? -1 : tf[1];
+          if (lane == r) { my_v = wf >= 0 ? funkey_s(wk) : -INFINITY; my_f = wf; }
+        }
+      }
+      // lane r < K: the r-th extension in rank order
+      const bool cand = lane < K && my_f >= 0;
+      const int par = cand ? my_f / V : 0;
+      const uint64_t ph = __shfl_sync(full, p_hash, par);
+      const int pl = __shfl_sync(full, p_len, par), pc0 = __shfl_sync(full, p_c0, par), pc1 = __shfl_sync(full, p_c1, par);
+      int tok = -1, c0 = -1, c1 = blank, ln = 2;
+      uint64_t hs = kHashSeed;
+      if (cand) {
+        const int y = my_f - par * V;
+        hs = ph; ln = pl; c0 = pc0; c1 = pc1;
+        if (y != blank && y != unk) {      // ys unchanged for blank / unk
+          tok = y;
+          hs = hash_push(hs, y);
+          ln += 1;
+          c0 = c1;
+          c1 = y;
+        }
+      }
+      // dedupe: first earlier lane holding the same token sequence
+      int root = lane;
+      for (int q = 0; q < K; ++q) {
+        const uint64_t qh = __shfl_sync(full, hs, q);
+        const int ql = __shfl_sync(full, ln, q);
+        const int q0 = __shfl_sync(full, c0, q);
+        const int q1 = __shfl_sync(full, c1, q);
+        const int qc = __shfl_sync(full, (int)cand, q);
+        if (cand && qc && q < lane && root == lane && qh == hs && ql == ln && q0 == c0 && q1 == c1) root = q;
+      }
+      // log-add the merged scores into their root, in insertion (rank) order
+      float lp = my_v;
+      for (int q = 0; q < K; ++q) {
+        const int qroot = __shfl_sync(full, root, q);
+        const float qv = __shfl_sync(full, my_v, q);
+        const int qc = __shfl_sync(full, (int)cand, q);
+        if (cand && qc && q != lane && qroot == lane) lp = logaddexp_f(lp, qv);
+      }
+      const bool is_root = cand && root == lane;
+      const unsigned roots = __ballot_sync(full, is_root);
+      const int nnew = __popc(roots);
+      if (is_root) {
+        const int slot = __popc(roots & ((1u << lane) - 1u));
+        const size_t o = (size_t)s * K + slot;
+        out.ctx[2 * o] = c0;
+        out.ctx[2 * o + 1] = c1;
+        out.lp[o] = lp;
+        out.len[o] = ln;
+        out.hash[o] = hs;
+        bp[((size_t)s * T + t) * K + slot] = (par << 28) | (tok + 1);
+        s_ctx[2 * slot] = c0; s_ctx[2 * slot + 1] = c1;
+      }
+      if (lane >= nnew && lane < K) {      // dead slots keep a valid context for the next joiner operand
+        const size_t o = (size_t)s * K + lane;
+        out.ctx[2 * o] = -1;
+        out.ctx[2 * o + 1] = blank;
+        out.lp[o] = -INFINITY;
+        out.len[o] = 2;
+        out.hash[o] = kHashSeed;
+        bp[((size_t)s * T + t) * K + lane] = 0;
+        s_ctx[2 * lane] = -1; s_ctx[2 * lane + 1] = blank;
+      }
+      if (lane == 0) out.nlive[s] = nnew;
+    }
+  }
+  __syncthreads();
+  // ---- C: the next frame's joiner operand of this stream's K hypotheses -------------------------------------------------------
+  if (!build) return;
+  constexpr int kRowTile = 128, kImgTile = 128 * 128;        // rows per image tile, bytes of one 128 x 64 bf16 tile
+  for (int k = 4 * tid; k < J; k += 512) {
+    const float4 e = k == 4 * tid ? e4 : __ldg(reinterpret_cast<const float4*>(enc_next + (size_t)s * enc_stride + k));
+    const float ex[4] = {expf(2.f * fminf(fmaxf(e.x, -21.f), 21.f)), expf(2.f * fminf(fmaxf(e.y, -21.f), 21.f)),
+                         expf(2.f * fminf(fmaxf(e.z, -21.f), 21.f)), expf(2.f * fminf(fmaxf(e.w, -21.f), 21.f))};
+    float4 d[kMaxBeam];
+#pragma unroll
+    for (int q = 0; q < kMaxBeam; ++q)
+      if (q < K)
+        d[q] = __ldg(reinterpret_cast<const float4*>(dec_tab + ((size_t)(s_ctx[2 * q] + 1) * V + s_ctx[2 * q + 1]) * J + k));
+#pragma unroll
+    for (int q = 0; q < kMaxBeam; ++q) {
+      if (q < K) {
+        const int m = s * K + q;
+        const float dv[4] = {d[q].x, d[q].y, d[q].z, d[q].w};
+        float x[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {       // tanh(e + d) = 1 - 2 / (1 + exp(2e) * exp(2d)); the table holds exp(2d)
+          float r;
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(ex[i], dv[i], 1.f)));
+          x[i] = fmaf(-2.f, r, 1.f);
+        }
+        uint8_t* timg = x_img + ((size_t)(m / kRowTile) * (J / 64) + (k >> 6)) * (2 * kImgTile) +
+                        k2b::ptx::sw128_offset(m % kRowTile, k & 63);
+        const float h0 = k2b::ptx::bf16_round(x[0]), h1 = k2b::ptx::bf16_round(x[1]), h2 = k2b::ptx::bf16_round(x[2]),
+                    h3 = k2b::ptx::bf16_round(x[3]);
+        *reinterpret_cast<uint2*>(timg) = make_uint2(k2b::ptx::pack_bf16x2(h0, h1), k2b::ptx::pack_bf16x2(h2, h3));
+        *reinterpret_cast<uint2*>(timg + kImgTile) =
+            make_uint2(k2b::ptx::pack_bf16x2(x[0] - h0, x[1] - h1), k2b::ptx::pack_bf16x2(x[2] - h2, x[3] - h3));
+      }
+    }
+  }
+}
+
 // One warp per stream: pick argmax lp/len (first maximum in slot order), walk the back-pointers in
 // shared memory, write tokens / timestamps in forward order.
 __global__ void __launch_bounds__(32)
@@ -489,6 +746,26 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
   K2B_LAUNCH_CHECK(h);
 
   int cur = 0;
+  // memoised decoder + persistent joiner: two launches per frame (joiner, fused merge + next operand), chained by programmatic
+  // dependent launches. K2B_UNFUSED_STEP=1 keeps the three-launch sequence below (comparison runs).
+  static const bool unfused = getenv("K2B_UNFUSED_STEP") != nullptr;
+  if (tc && have_tab && ximg != nullptr && !unfused && joiner_topk_usable(h, K) && T > 0) {
+    K2B_TRY(joinin_table_tc(h, st[0].ctx, N, enc, (long long)T * J, K, ximg));
+    for (int t = 0; t < T; ++t) {
+      if (h->prof_which == 0) prof_begin(h);
+      K2B_TRY(joiner_tc_partials(h, x, ximg, N, K, part_m, part_s, part_tv, part_ti, nullptr, nullptr, nullptr));
+      if (h->prof_which == 0) prof_end(h);
+      if (h->prof_which == 2) prof_begin(h);
+      K2B_CUDA(h, launch_pdl(beam_step_kernel, dim3(B), dim3(128), 0, h->stream, B, K, V, nt, T, t, (int)c.blank_id, (int)c.unk_id,
+                              (const float*)part_m, (const float*)part_s, (const float*)part_tv, (const int32_t*)part_ti, st[cur],
+                              st[cur ^ 1], bp, (const int32_t*)(h->lens_active ? h->lens_dev : nullptr), (const float*)h->dec_tab,
+                              (const float*)(t + 1 < T ? enc + (size_t)(t + 1) * J : nullptr), (long long)T * J, J, ximg));
+      K2B_LAUNCH_CHECK(h);
+      if (h->prof_which == 2) prof_end(h);
+      cur ^= 1;
+    }
+    return beam_backtrace_dev(h, B, K, T, st[cur].lp, st[cur].len, st[cur].nlive, bp, tokens, ts, n_out, score, cap);
+  }
   for (int t = 0; t < T; ++t) {
     GemmArgs d;
     d.M = N; d.N = J; d.K = D;
@@ -500,23 +777,28 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
     // tcgen05 decoder: its epilogue leaves x = tanh(enc + dec) as bf16 hi/lo tile images, which the joiner's loader warp
     // fetches by TMA (no fp32 round trip, no per-CTA conversion)
     const bool img = tc && decoder_tc_supported(h);
+    if (h->prof_which == 1) prof_begin(h);
     if (img && have_tab) K2B_TRY(joinin_table_tc(h, st[cur].ctx, N, enc + (size_t)t * J, (long long)T * J, K, ximg));
     else if (img) K2B_TRY(decoder_joinin_tc(h, st[cur].ctx, N, enc + (size_t)t * J, (long long)T * J, K, nullptr, ximg));
     else K2B_TRY(launch_gemm_simt(h, PRO_DEC, EPI_TANH_ADD, d));
+    if (h->prof_which == 1) prof_end(h);
 
     GemmArgs j;
     j.M = N; j.N = V; j.K = J;
     j.W = h->out_w; j.bias = h->out_b; j.A = x;
     j.part_m = part_m; j.part_s = part_s; j.part_tv = part_tv; j.part_ti = part_ti; j.topk = K;
-    prof_begin(h);
+    if (h->prof_which == 0) prof_begin(h);
     if (tc) K2B_TRY(joiner_tc_partials(h, x, img ? ximg : nullptr, N, K, part_m, part_s, part_tv, part_ti, nullptr, nullptr, nullptr));
     else K2B_TRY(launch_gemm_simt(h, PRO_PLAIN, EPI_TOPK, j));
-    prof_end(h);
+    if (h->prof_which == 0) prof_end(h);
 
-    beam_select_kernel<<<(B + 3) / 4, 128, 0, h->stream>>>(B, K, V, nt, T, t, c.blank_id, c.unk_id, part_m, part_s,
-                                                          part_tv, part_ti, st[cur], st[cur ^ 1], bp,
-                                                          h->lens_active ? h->lens_dev : nullptr);
+    if (h->prof_which == 2) prof_begin(h);
+    K2B_CUDA(h, launch_pdl(beam_select_kernel, dim3((B + 3) / 4), dim3(128), 0, h->stream, B, K, V, nt, T, t, (int)c.blank_id,
+                            (int)c.unk_id, (const float*)part_m, (const float*)part_s, (const float*)part_tv,
+                            (const int32_t*)part_ti, st[cur], st[cur ^ 1], bp,
+                            (const int32_t*)(h->lens_active ? h->lens_dev : nullptr)));
     K2B_LAUNCH_CHECK(h);
+    if (h->prof_which == 2) prof_end(h);
     cur ^= 1;
   }
 

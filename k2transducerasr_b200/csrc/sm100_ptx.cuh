@@ -207,6 +207,13 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int k) {
   return (uint32_t)(row * 128 + chunk * 16 + (k & 7) * 2);
 }
 
+// ---- programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (its
+// prologue) once every CTA of the kernel before it in the stream has called launch_dependents or exited; it must call
+// griddep_wait() before touching anything that kernel wrote (the wait returns when that grid has completed and flushed).
+// Both are no-ops in a kernel launched the ordinary way.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- clusters / distributed shared memory ----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
