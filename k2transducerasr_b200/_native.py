@@ -75,6 +75,7 @@ _SIGS = {
     "k2b_unstack_states": (C.c_int32, [_P, _P, _I, _P, _P]),
     "k2b_selftest_umma2": (C.c_int32, [_P, _P, _P, _I, _I, _I, _P]),
     "k2b_cluster_phase_cycles": (C.c_int32, [_P, _P]),
+    "k2b_debug_timeline": (C.c_int32, [_P, _P]),
     "k2b_selftest_umma_bench": (C.c_int32, [_P, _I, _I, _I, _P]),
     "k2b_selftest_collectives": (C.c_int32, [_P, _P]),
     "k2b_selftest_dsmem_bw": (C.c_int32, [_P, _I, _I, _I, _P]),
@@ -341,6 +342,11 @@ class Handle:
         D = np.zeros((128, N), np.float32)
         self._check(self._lib.k2b_selftest_umma(self._h, _ptr(A), _ptr(B), N, K, mode, int(use_tma), _ptr(D)))
         return D
+
+    def debug_timeline(self):
+        out = np.zeros((64, 148, 8), np.int64)
+        self._check(self._lib.k2b_debug_timeline(self._h, _ptr(out)))
+        return out
 
     def cluster_phase_cycles(self):
         out = np.zeros(20, np.int64)

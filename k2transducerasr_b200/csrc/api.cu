@@ -306,6 +306,7 @@ int32_t k2b_destroy(k2b_handle* h) {
   state_pool_free(h);
   if (h->lens_dev) cudaFree(h->lens_dev);
   if (h->cluster_timing) cudaFree(h->cluster_timing);
+  if (h->timeline) cudaFree(h->timeline);
   if (h->dev_status) cudaFree(h->dev_status);
   for (int i = 0; i < 2; ++i) { if (h->ev_ready[i]) cudaEventDestroy(h->ev_ready[i]); if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]); }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -417,6 +418,25 @@ K2B_API int32_t k2b_cluster_phase_cycles(k2b_handle* h, int64_t* out8) {
   K2B_CUDA(h, cudaMemcpy(v, h->cluster_timing, sizeof(v), cudaMemcpyDeviceToHost));
   for (int i = 0; i < 20; ++i) out8[i] = v[i];
   K2B_CUDA(h, cudaMemset(h->cluster_timing, 0, sizeof(v)));
+  return K2B_OK;
+}
+
+// diagnostic: the first call allocates the per-SM clock64 timeline of the per-frame beam path and switches collection on; later
+// calls copy out [64][148][8] stamps (joiner: start, wait done, first accumulator, end; merge: first start, first wait done, last
+// merge done, last end) and re-arm
+K2B_API int32_t k2b_debug_timeline(k2b_handle* h, int64_t* out) {
+  K2B_TRY(enter(h));
+  const size_t n = (size_t)64 * 148 * 8;
+  std::vector<long long> init(n);
+  for (size_t i = 0; i < n; ++i) init[i] = ((i & 7) == 4 || (i & 7) == 5) ? 0x7fffffffffffffffll : 0ll;
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->timeline == nullptr) {
+    K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->timeline), n * sizeof(long long)));
+  } else if (out != nullptr) {
+    K2B_CUDA(h, cudaMemcpy(out, h->timeline, n * sizeof(long long), cudaMemcpyDeviceToHost));
+  }
+  K2B_CUDA(h, cudaMemcpy(h->timeline, init.data(), n * sizeof(long long), cudaMemcpyHostToDevice));
+  h->timeline_frame = 0;
   return K2B_OK;
 }
 

@@ -44,6 +44,7 @@ struct JArgs {
   float* part_m; float* part_s; float* part_tv; int32_t* part_ti;     // [M,ntn], [M,ntn], [M,ntn,topk] x2
   int* status;
   long long* dbg;
+  long long* tl;             // diagnostic timeline of this launch: [sm][8] clock64 stamps (slots 0..3), or null
 };
 
 template <int KK>
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(kThreads, 1) joiner_topk_kernel(const JArgs a)
   __shared__ __align__(16) float bias_t[kJNc];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long c_start = a.dbg != nullptr ? clock64() : 0;
+  const long long c_start = (a.dbg != nullptr || a.tl != nullptr) ? clock64() : 0;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   const int ntiles = a.ntm * a.ntn;
   const int nkb = a.nkb;
@@ -82,6 +83,13 @@ __global__ void __launch_bounds__(kThreads, 1) joiner_topk_kernel(const JArgs a)
   const uint32_t t_d = tmem_slot;
   bool ok = true;
   griddep_launch_dependents();
+  long long* tl = nullptr;
+  if (a.tl != nullptr) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    tl = a.tl + (size_t)smid * 8;
+    if (tid == 64) tl[0] = c_start;
+  }
 
   if (warp_u == 0) {
     // ---- loader ------------------------------------------------------------------------------------------------------
@@ -157,6 +165,7 @@ __global__ void __launch_bounds__(kThreads, 1) joiner_topk_kernel(const JArgs a)
     const int K = a.topk;
     int it = 0;
     griddep_wait();                                       // partials are read by the previous frame's merge kernel
+    if (tl != nullptr && tid == 64) tl[1] = clock64();
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int tile_n = tile / a.ntm, tile_m = tile - tile_n * a.ntm;
       const int as = it & 1;
@@ -167,6 +176,7 @@ __global__ void __launch_bounds__(kThreads, 1) joiner_topk_kernel(const JArgs a)
       named_bar_sync(1, 128);
       if (!mbar_wait(&acc_full[as], aph)) ok = false;
       if (dbg && it == 0) c_acc = clock64();
+      if (tl != nullptr && tid == 64 && it == 0) tl[2] = clock64();
       tc_fence_after();
       const uint32_t trow = t_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * kAccCols);
       int key[KK];
@@ -228,6 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) joiner_topk_kernel(const JArgs a)
       }
       if (dbg && it == 0) c_epi = clock64();
     }
+    if (tl != nullptr && tid == 64) tl[3] = clock64();
     if (dbg) {
       const long long c_end = clock64();
       atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg + 10), (unsigned long long)(c_acc - c_start));
@@ -280,6 +291,7 @@ int32_t joiner_topk_tc(k2b_handle* h, const uint8_t* x_img, int M, int topk, flo
   a.part_m = part_m; a.part_s = part_s; a.part_tv = part_tv; a.part_ti = part_ti;
   a.status = h->dev_status + 1;
   a.dbg = h->cluster_timing;
+  a.tl = h->timeline != nullptr ? h->timeline + (size_t)(h->timeline_frame % 64) * 148 * 8 : nullptr;
   return topk <= 4 ? launch_as<4>(h, a) : launch_as<8>(h, a);
 }
 

@@ -96,6 +96,8 @@ struct k2b_handle {
   int* dev_status = nullptr;      // [4] error flags written by the tcgen05 kernels (mbarrier time-outs)
   long long* cluster_timing = nullptr;   // device [8]: per-phase cycle totals of the cluster kernel (diagnostic)
 
+  long long* timeline = nullptr;  // diagnostic: [64 frames][148 SMs][8] clock64 stamps of the per-frame beam path (k2b_debug_timeline)
+  int timeline_frame = 0;
   bool profile_on = false;
   int prof_which = 0;             // which launch of the per-frame beam path the profile events bracket (K2B_PROF_WHICH: 0 joiner, 1 operand build, 2 merge)
   k2b::StatePool* state_pool = nullptr;   // on-device streaming state (state_pool.cu)

@@ -335,18 +335,22 @@ beam_select_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk
 //   C. all threads: x[m,:] = tanh(enc[s,t+1] + decoder(ctx[m])) of the K new hypotheses from the memoised decoder table, written
 //      as the bf16 hi / lo tile images the joiner's loader warp fetches (what joinin_table_kernel does in a launch of its own).
 // Same results as beam_select_kernel + joinin_table_kernel; one launch and one round trip of the contexts through HBM less.
+// KB = 4 or 8: compile-time bound of the beam (the kernel is latency-bound and every instruction is executed once per frame,
+// so its code size is its run time: loops are unrolled to exactly KB levels).
+template <int KB>
 __global__ void __launch_bounds__(128)
 beam_step_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
                  const float* __restrict__ part_m, const float* __restrict__ part_s,
                  const float* __restrict__ part_tv, const int32_t* __restrict__ part_ti,
                  BeamState in, BeamState out, int32_t* __restrict__ bp, const int32_t* __restrict__ lens,
                  const float* __restrict__ dec_tab, const float* __restrict__ enc_next, long long enc_stride, int J,
-                 uint8_t* __restrict__ x_img) {
-  __shared__ float c_v[kMaxBeam * kMaxBeam];
-  __shared__ int c_f[kMaxBeam * kMaxBeam];
-  __shared__ int s_ctx[2 * kMaxBeam];
+                 uint8_t* __restrict__ x_img, long long* __restrict__ tl) {
+  __shared__ float c_v[KB * KB];
+  __shared__ int c_f[KB * KB];
+  __shared__ int s_ctx[2 * KB];
   constexpr int kNone = (int)0x80000000;
   constexpr int kPairs = 2, kCands = 8;            // per-lane register batches: nt <= 64, nt * K <= 256 without a tail pass
+  static_assert(kCands >= KB, "a lane must be able to hold a whole top-K");
   const unsigned full = 0xffffffffu;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int s = blockIdx.x;
@@ -355,16 +359,24 @@ beam_step_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
   const bool build = enc_next != nullptr;
   float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (build && 4 * tid < J) e4 = __ldg(reinterpret_cast<const float4*>(enc_next + (size_t)s * enc_stride + 4 * tid));
+  if (tl != nullptr) {                                      // diagnostic timeline: [sm][8], slots 4..7 = first start, first wait-done,
+    uint32_t smid;                                          // last merge-done, last end of the CTAs of this launch on that SM
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    tl += (size_t)smid * 8;
+    if (tid == 0) atomicMin(reinterpret_cast<long long*>(tl + 4), clock64());
+  }
   k2b::ptx::griddep_wait();
+  if (tl != nullptr && tid == 0) atomicMin(reinterpret_cast<long long*>(tl + 5), clock64());
   const int nl = in.nlive[s];
   const bool frozen = lens != nullptr && t >= lens[s];      // ragged batch: past the end of this stream
-  for (int i = tid; i < K * K; i += 128) { c_v[i] = -INFINITY; c_f[i] = -1; }
+  if (tid < KB * KB) { c_v[tid] = -INFINITY; c_f[tid] = -1; }
   // parents' state, lane q of warp 0 <-> hypothesis q
   uint64_t p_hash = kHashSeed;
   int p_len = 2, p_c0 = -1, p_c1 = blank;
+  float p_lp = -INFINITY;
   if (warp == 0 && lane < K) {
     const size_t o = (size_t)s * K + lane;
-    p_hash = in.hash[o]; p_len = in.len[o]; p_c0 = in.ctx[2 * o]; p_c1 = in.ctx[2 * o + 1];
+    p_hash = in.hash[o]; p_len = in.len[o]; p_c0 = in.ctx[2 * o]; p_c1 = in.ctx[2 * o + 1]; p_lp = in.lp[o];
   }
   __syncthreads();
   if (frozen) {
@@ -372,7 +384,7 @@ beam_step_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
       if (lane < K) {
         const size_t o = (size_t)s * K + lane;
         out.ctx[2 * o] = p_c0; out.ctx[2 * o + 1] = p_c1;
-        out.lp[o] = in.lp[o]; out.len[o] = p_len; out.hash[o] = p_hash;
+        out.lp[o] = p_lp; out.len[o] = p_len; out.hash[o] = p_hash;
         bp[((size_t)s * T + t) * K + lane] = lane < nl ? (lane << 28) : 0;
         s_ctx[2 * lane] = p_c0; s_ctx[2 * lane + 1] = p_c1;
       }
@@ -380,6 +392,7 @@ beam_step_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
     }
   } else {
     // ---- A: per live hypothesis --------------------------------------------------------------------------------------------
+#pragma unroll 1
     for (int h = warp; h < nl; h += 4) {
       const size_t row = (size_t)s * K + h;
       const float* pmr = part_m + row * nt;
@@ -401,14 +414,14 @@ beam_step_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
         cval[u] = c < ncand ? part_tv[cbase + c] : 0.f;
       }
       const float lp = in.lp[row];
-      int mk = kNone;
-#pragma unroll
-      for (int u = 0; u < kPairs; ++u) mk = max(mk, lane + 32 * u < nt ? fkey_s(pm[u]) : kNone);
+      int mk = max(fkey_s(pm[0]), fkey_s(pm[1]));           // absent tiles read as -inf
+#pragma unroll 1
       for (int i = lane + 32 * kPairs; i < nt; i += 32) mk = max(mk, fkey_s(pmr[i]));
       const float mx = funkey_s(__reduce_max_sync(full, mk));
       float sum = 0.f;
 #pragma unroll
       for (int u = 0; u < kPairs; ++u) sum += (pm[u] > -INFINITY) ? ps[u] * __expf(pm[u] - mx) : 0.f;
+#pragma unroll 1
       for (int i = lane + 32 * kPairs; i < nt; i += 32) {
         const float m2 = pmr[i];
         sum += (m2 > -INFINITY) ? psr[i] * __expf(m2 - mx) : 0.f;
@@ -416,38 +429,51 @@ beam_step_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(full, sum, o);
       const float ls = __logf(sum);
-      // lane-local top-K (sorted, best first), then K rounds of warp arg-best (REDUX on the key, then on the flat index)
-      int tk[kMaxBeam], tf[kMaxBeam];
+      // this lane's candidates as (key, flat index); same operation order as log_softmax(x) + lp : ((x - max) - log(sum)) + lp
+      int ck[kCands], cf[kCands];
 #pragma unroll
-      for (int i = 0; i < kMaxBeam; ++i) { tk[i] = kNone; tf[i] = -1; }
-      auto push = [&](float val, int idx) {
-        // same operation order as log_softmax(x) + lp : ((x - max) - log(sum)) + lp
-        const float v = ((val - mx) - ls) + lp;
+      for (int u = 0; u < kCands; ++u) {
+        const float v = ((cval[u] - mx) - ls) + lp;
+        const bool okc = (cidx[u] >= 0) & (v == v);
+        ck[u] = okc ? fkey_s(v) : kNone;
+        cf[u] = okc ? h * V + cidx[u] : -1;
+      }
+      // more than 32 * kCands candidates (rare): a lane keeps its best kCands >= K of them (its worst one is replaced)
+#pragma unroll 1
+      for (int c = lane + 32 * kCands; c < ncand; c += 32) {
+        const int idx = part_ti[cbase + c];
+        const float v = ((part_tv[cbase + c] - mx) - ls) + lp;
         const bool okc = (idx >= 0) & (v == v);
-        int key = okc ? fkey_s(v) : kNone;
-        int f = okc ? h * V + idx : -1;
+        const int key = okc ? fkey_s(v) : kNone, f = okc ? h * V + idx : -1;
+        int wk = ck[0], wf = cf[0];
 #pragma unroll
-        for (int i = 0; i < kMaxBeam; ++i) {
-          if (i < K) {
-            const bool b = (key > tk[i]) | ((key == tk[i]) & (f > tf[i]));
-            const int nk = b ? tk[i] : key, nf = b ? tf[i] : f;
-            tk[i] = b ? key : tk[i]; tf[i] = b ? f : tf[i];
-            key = nk; f = nf;
-          }
+        for (int u = 1; u < kCands; ++u) {
+          const bool lower = (ck[u] < wk) | ((ck[u] == wk) & (cf[u] < wf));
+          wk = lower ? ck[u] : wk; wf = lower ? cf[u] : wf;
         }
-      };
+        const bool take = (key > wk) | ((key == wk) & (f > wf));
+        bool done = !take;
 #pragma unroll
-      for (int u = 0; u < kCands; ++u) push(cval[u], cidx[u]);
-      for (int c = lane + 32 * kCands; c < ncand; c += 32) push(part_tv[cbase + c], part_ti[cbase + c]);
+        for (int u = 0; u < kCands; ++u) {
+          const bool hit = !done & (ck[u] == wk) & (cf[u] == wf);
+          ck[u] = hit ? key : ck[u]; cf[u] = hit ? f : cf[u];
+          done |= hit;
+        }
+      }
+      // K rounds of warp arg-best over all registers: REDUX on the key, then on the flat index among the ties
 #pragma unroll
-      for (int r = 0; r < kMaxBeam; ++r) {
+      for (int r = 0; r < KB; ++r) {
         if (r < K) {
-          const int wk = __reduce_max_sync(full, tk[0]);
-          const int wf = __reduce_max_sync(full, (tk[0] == wk) ? tf[0] : -1);
-          const bool pop = (tf[0] == wf) & (wf >= 0);      // flat indices are unique: exactly one lane pops
+          int lk = ck[0];
 #pragma unroll
-          for (int i = 0; i + 1 < kMaxBeam; ++i) { tk[i] = pop ? tk[i + 1] : tk[i]; tf[i] = pop ? tf[i + 1] : tf[i]; }
-          tk[kMaxBeam - 1] = pop ? kNone : tk[kMaxBeam - 1]; tf[kMaxBeam - 1] = pop ? -1 : tf[kMaxBeam - 1];
+          for (int u = 1; u < kCands; ++u) lk = max(lk, ck[u]);
+          const int wk = __reduce_max_sync(full, lk);
+          int lf = -1;
+#pragma unroll
+          for (int u = 0; u < kCands; ++u) lf = max(lf, (ck[u] == wk) ? cf[u] : -1);
+          const int wf = __reduce_max_sync(full, lf);      // flat indices are unique: exactly one register of one lane matches
+#pragma unroll
+          for (int u = 0; u < kCands; ++u) ck[u] = ((ck[u] == wk) & (cf[u] == wf)) ? kNone : ck[u];
           if (lane == r) { c_v[h * K + r] = wf >= 0 ? funkey_s(wk) : -INFINITY; c_f[h * K + r] = wf; }
         }
       }
@@ -459,24 +485,19 @@ beam_step_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int i = lane + 32 * u;
-        const bool okc = i < K * K && c_f[i] >= 0;
-        tk[u] = okc ? fkey_s(c_v[i]) : kNone;
-        tf[u] = okc ? c_f[i] : -1;
-      }
-      if ((tk[1] > tk[0]) | ((tk[1] == tk[0]) & (tf[1] > tf[0]))) {
-        const int a = tk[0], b = tf[0];
-        tk[0] = tk[1]; tf[0] = tf[1]; tk[1] = a; tf[1] = b;
+        const bool okc = i < K * K && c_f[i < KB * KB ? i : 0] >= 0;
+        tk[u] = okc ? fkey_s(c_v[i < KB * KB ? i : 0]) : kNone;
+        tf[u] = okc ? c_f[i < KB * KB ? i : 0] : -1;
       }
       float my_v = -INFINITY;
       int my_f = -1;
 #pragma unroll
-      for (int r = 0; r < kMaxBeam; ++r) {
+      for (int r = 0; r < KB; ++r) {
         if (r < K) {
-          const int wk = __reduce_max_sync(full, tk[0]);
-          const int wf = __reduce_max_sync(full, (tk[0] == wk) ? tf[0] : -1);
-          const bool pop = (tf[0] == wf) & (wf >= 0);
-          tk[0] = pop ? tk[1] : tk[0]; tf[0] = pop ? tf[1] : tf[0];
-          tk[1] = pop ? kNone : tk[1]; tf[1] = pop ? -1 : tf[1];
+          const int wk = __reduce_max_sync(full, max(tk[0], tk[1]));
+          const int wf = __reduce_max_sync(full, max((tk[0] == wk) ? tf[0] : -1, (tk[1] == wk) ? tf[1] : -1));
+          tk[0] = ((tk[0] == wk) & (tf[0] == wf)) ? kNone : tk[0];
+          tk[1] = ((tk[1] == wk) & (tf[1] == wf)) ? kNone : tk[1];
           if (lane == r) { my_v = wf >= 0 ? funkey_s(wk) : -INFINITY; my_f = wf; }
         }
       }
@@ -498,18 +519,21 @@ beam_step_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
           c1 = y;
         }
       }
-      // dedupe: first earlier lane holding the same token sequence
+      // dedupe: first earlier lane holding the same token sequence; log-add the merged scores into their root in rank order
       int root = lane;
-      for (int q = 0; q < K; ++q) {
-        const uint64_t qh = __shfl_sync(full, hs, q);
-        const int ql = __shfl_sync(full, ln, q);
-        const int q0 = __shfl_sync(full, c0, q);
-        const int q1 = __shfl_sync(full, c1, q);
-        const int qc = __shfl_sync(full, (int)cand, q);
-        if (cand && qc && q < lane && root == lane && qh == hs && ql == ln && q0 == c0 && q1 == c1) root = q;
-      }
-      // log-add the merged scores into their root, in insertion (rank) order
       float lp = my_v;
+#pragma unroll
+      for (int q = 0; q < KB; ++q) {
+        if (q < K) {
+          const uint64_t qh = __shfl_sync(full, hs, q);
+          const int ql = __shfl_sync(full, ln, q);
+          const int q0 = __shfl_sync(full, c0, q);
+          const int q1 = __shfl_sync(full, c1, q);
+          const int qc = __shfl_sync(full, (int)cand, q);
+          if (cand && qc && q < lane && root == lane && qh == hs && ql == ln && q0 == c0 && q1 == c1) root = q;
+        }
+      }
+#pragma unroll 1
       for (int q = 0; q < K; ++q) {
         const int qroot = __shfl_sync(full, root, q);
         const float qv = __shfl_sync(full, my_v, q);
@@ -544,6 +568,7 @@ beam_step_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
     }
   }
   __syncthreads();
+  if (tl != nullptr && tid == 0) atomicMax(reinterpret_cast<long long*>(tl + 6), clock64());
   // ---- C: the next frame's joiner operand of this stream's K hypotheses -------------------------------------------------------
   if (!build) return;
   constexpr int kRowTile = 128, kImgTile = 128 * 128;        // rows per image tile, bytes of one 128 x 64 bf16 tile
@@ -551,13 +576,13 @@ beam_step_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
     const float4 e = k == 4 * tid ? e4 : __ldg(reinterpret_cast<const float4*>(enc_next + (size_t)s * enc_stride + k));
     const float ex[4] = {expf(2.f * fminf(fmaxf(e.x, -21.f), 21.f)), expf(2.f * fminf(fmaxf(e.y, -21.f), 21.f)),
                          expf(2.f * fminf(fmaxf(e.z, -21.f), 21.f)), expf(2.f * fminf(fmaxf(e.w, -21.f), 21.f))};
-    float4 d[kMaxBeam];
+    float4 d[KB];
 #pragma unroll
-    for (int q = 0; q < kMaxBeam; ++q)
+    for (int q = 0; q < KB; ++q)
       if (q < K)
         d[q] = __ldg(reinterpret_cast<const float4*>(dec_tab + ((size_t)(s_ctx[2 * q] + 1) * V + s_ctx[2 * q + 1]) * J + k));
 #pragma unroll
-    for (int q = 0; q < kMaxBeam; ++q) {
+    for (int q = 0; q < KB; ++q) {
       if (q < K) {
         const int m = s * K + q;
         const float dv[4] = {d[q].x, d[q].y, d[q].z, d[q].w};
@@ -578,6 +603,7 @@ beam_step_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
       }
     }
   }
+  if (tl != nullptr && tid == 0) atomicMax(reinterpret_cast<long long*>(tl + 7), clock64());
 }
 
 // One warp per stream: pick argmax lp/len (first maximum in slot order), walk the back-pointers in
@@ -756,11 +782,14 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
       K2B_TRY(joiner_tc_partials(h, x, ximg, N, K, part_m, part_s, part_tv, part_ti, nullptr, nullptr, nullptr));
       if (h->prof_which == 0) prof_end(h);
       if (h->prof_which == 2) prof_begin(h);
-      K2B_CUDA(h, launch_pdl(beam_step_kernel, dim3(B), dim3(128), 0, h->stream, B, K, V, nt, T, t, (int)c.blank_id, (int)c.unk_id,
+      K2B_CUDA(h, launch_pdl(K <= 4 ? beam_step_kernel<4> : beam_step_kernel<8>, dim3(B), dim3(128), 0, h->stream, B, K, V, nt, T, t,
+                              (int)c.blank_id, (int)c.unk_id,
                               (const float*)part_m, (const float*)part_s, (const float*)part_tv, (const int32_t*)part_ti, st[cur],
                               st[cur ^ 1], bp, (const int32_t*)(h->lens_active ? h->lens_dev : nullptr), (const float*)h->dec_tab,
-                              (const float*)(t + 1 < T ? enc + (size_t)(t + 1) * J : nullptr), (long long)T * J, J, ximg));
+                              (const float*)(t + 1 < T ? enc + (size_t)(t + 1) * J : nullptr), (long long)T * J, J, ximg,
+                              (long long*)(h->timeline != nullptr ? h->timeline + (size_t)(h->timeline_frame % 64) * 148 * 8 : nullptr)));
       K2B_LAUNCH_CHECK(h);
+      h->timeline_frame++;
       if (h->prof_which == 2) prof_end(h);
       cur ^= 1;
     }
