@@ -311,7 +311,7 @@ int32_t k2b_destroy(k2b_handle* h) {
   for (int i = 0; i < 2; ++i) { if (h->ev_ready[i]) cudaEventDestroy(h->ev_ready[i]); if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]); }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   DevBuf* bufs[] = {&h->ws_in, &h->ws_encproj, &h->ws_x, &h->ws_ximg, &h->ws_dec, &h->ws_logits, &h->ws_part, &h->ws_state, &h->ws_bp,
-                    &h->ws_out, &h->ws_misc, &h->ws_ctc};
+                    &h->ws_out, &h->ws_misc, &h->ws_ctc, &h->ws_sync};
   for (DevBuf* b : bufs) free_buf(*b);
   for (cudaEvent_t ev : h->prof.start) cudaEventDestroy(ev);
   for (cudaEvent_t ev : h->prof.stop) cudaEventDestroy(ev);

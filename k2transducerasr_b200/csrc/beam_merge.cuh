@@ -1,0 +1,302 @@
+// Hypothesis state of modified_beam_search and the per-stream frame step ("hyp_merge" + the next frame's joiner operand), shared by
+// the stand-alone merge kernel (search.cu) and the persistent beam-search kernel (joiner_tc.cu).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "sm100_ptx.cuh"
+
+namespace k2b {
+
+struct BeamState {
+  int32_t* ctx;    // [N,2]
+  float* lp;       // [N]
+  int32_t* len;    // [N]
+  uint64_t* hash;  // [N]
+  int32_t* nlive;  // [B]
+};
+
+constexpr uint64_t kHashSeed = 0x9E3779B97F4A7C15ull;
+
+__device__ __forceinline__ uint64_t hash_push(uint64_t h, int tok) {
+  h = (h ^ (uint64_t)(uint32_t)(tok + 1)) * 0x100000001B3ull;
+  h ^= h >> 29;
+  h *= 0xBF58476D1CE4E5B9ull;
+  h ^= h >> 32;
+  return h;
+}
+
+__device__ __forceinline__ float logaddexp_f(float a, float b) {
+  const float mx = fmaxf(a, b), mn = fminf(a, b);
+  if (mx == -INFINITY) return -INFINITY;
+  return mx + log1pf(expf(mn - mx));
+}
+
+// order-preserving integer image of a float
+__device__ __forceinline__ int fkey_s(float f) { const int k = __float_as_int(f); return k ^ ((k >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float funkey_s(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+
+// One frame step of stream s by a group of 128 threads (tid 0..127, synchronised with named barrier `bar_id`):
+//   A. warp h <-> live hypothesis h: log_softmax constants from its tile partials, its K best extensions (all loads of a
+//      hypothesis are issued before the first use: the partials sit in L2, the step pays latency, not bandwidth);
+//   B. warp 0: the stream's top K over the K*K survivors (value desc, flat index desc), extension, dedupe by token-sequence hash
+//      with log-add in rank order, compaction, back-pointer record;
+//   C. all threads: x[m,:] = tanh(enc[s,t+1] + decoder(ctx[m])) of the K new hypotheses from the memoised decoder table, written
+//      as the bf16 hi / lo tile images the joiner's loader warp fetches.
+// Everything another CTA may have produced during the same launch (partials, state) is read with ld.global.cg.
+// KB = 4 or 8: compile-time bound of the beam (the step is latency-bound and most of its instructions are executed once, so its
+// code size is its run time: loops are unrolled to exactly KB levels). c_v / c_f [KB*KB] and s_ctx [2*KB] are shared scratch.
+template <int KB>
+__device__ __forceinline__ void beam_merge_stream(
+    int tid, int bar_id, int s, int K, int V, int nt, int T, int t, int blank, int unk, const float* part_m, const float* part_s,
+    const float* part_tv, const int32_t* part_ti, const BeamState& in, const BeamState& out, int32_t* bp, const int32_t* lens,
+    const float* dec_tab, const float* enc_next, long long enc_stride, int J, uint8_t* x_img, float4 e4, float* c_v, int* c_f,
+    int* s_ctx, long long* tl) {
+  constexpr int kNone = (int)0x80000000;
+  constexpr int kPairs = 2, kCands = 8;            // per-lane register batches: nt <= 64, nt * K <= 256 without a tail pass
+  static_assert(kCands >= KB, "a lane must be able to hold a whole top-K");
+  const unsigned full = 0xffffffffu;
+  const int warp = tid >> 5, lane = tid & 31;
+  const bool build = enc_next != nullptr;
+  const int nl = __ldcg(in.nlive + s);
+  const bool frozen = lens != nullptr && t >= __ldg(lens + s);      // ragged batch: past the end of this stream
+  if (tid < KB * KB) { c_v[tid] = -INFINITY; c_f[tid] = -1; }
+  // parents' state, lane q of warp 0 <-> hypothesis q
+  uint64_t p_hash = kHashSeed;
+  int p_len = 2, p_c0 = -1, p_c1 = blank;
+  float p_lp = -INFINITY;
+  if (warp == 0 && lane < K) {
+    const size_t o = (size_t)s * K + lane;
+    p_hash = __ldcg(in.hash + o); p_len = __ldcg(in.len + o); p_c0 = __ldcg(in.ctx + 2 * o); p_c1 = __ldcg(in.ctx + 2 * o + 1);
+    p_lp = __ldcg(in.lp + o);
+  }
+  k2b::ptx::named_bar_sync(bar_id, 128);
+  if (frozen) {
+    if (warp == 0) {
+      if (lane < K) {
+        const size_t o = (size_t)s * K + lane;
+        out.ctx[2 * o] = p_c0; out.ctx[2 * o + 1] = p_c1;
+        out.lp[o] = p_lp; out.len[o] = p_len; out.hash[o] = p_hash;
+        bp[((size_t)s * T + t) * K + lane] = lane < nl ? (lane << 28) : 0;
+        s_ctx[2 * lane] = p_c0; s_ctx[2 * lane + 1] = p_c1;
+      }
+      if (lane == 0) out.nlive[s] = nl;
+    }
+  } else {
+    // ---- A: per live hypothesis --------------------------------------------------------------------------------------------
+#pragma unroll 1
+    for (int h = warp; h < nl; h += 4) {
+      const size_t row = (size_t)s * K + h;
+      const float* pmr = part_m + row * nt;
+      const float* psr = part_s + row * nt;
+      const size_t cbase = row * nt * K;
+      const int ncand = nt * K;
+      float pm[kPairs], ps[kPairs], cval[kCands];
+      int cidx[kCands];
+#pragma unroll
+      for (int u = 0; u < kPairs; ++u) {
+        const int i = lane + 32 * u;
+        pm[u] = i < nt ? __ldcg(pmr + i) : -INFINITY;
+        ps[u] = i < nt ? __ldcg(psr + i) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kCands; ++u) {
+        const int c = lane + 32 * u;
+        cidx[u] = c < ncand ? __ldcg(part_ti + cbase + c) : -1;
+        cval[u] = c < ncand ? __ldcg(part_tv + cbase + c) : 0.f;
+      }
+      const float lp = __ldcg(in.lp + row);
+      int mk = max(fkey_s(pm[0]), fkey_s(pm[1]));           // absent tiles read as -inf
+#pragma unroll 1
+      for (int i = lane + 32 * kPairs; i < nt; i += 32) mk = max(mk, fkey_s(__ldcg(pmr + i)));
+      const float mx = funkey_s(__reduce_max_sync(full, mk));
+      float sum = 0.f;
+#pragma unroll
+      for (int u = 0; u < kPairs; ++u) sum += (pm[u] > -INFINITY) ? ps[u] * __expf(pm[u] - mx) : 0.f;
+#pragma unroll 1
+      for (int i = lane + 32 * kPairs; i < nt; i += 32) {
+        const float m2 = __ldcg(pmr + i);
+        sum += (m2 > -INFINITY) ? __ldcg(psr + i) * __expf(m2 - mx) : 0.f;
+      }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(full, sum, o);
+      const float ls = __logf(sum);
+      // this lane's candidates as (key, flat index); same operation order as log_softmax(x) + lp : ((x - max) - log(sum)) + lp
+      int ck[kCands], cf[kCands];
+#pragma unroll
+      for (int u = 0; u < kCands; ++u) {
+        const float v = ((cval[u] - mx) - ls) + lp;
+        const bool okc = (cidx[u] >= 0) & (v == v);
+        ck[u] = okc ? fkey_s(v) : kNone;
+        cf[u] = okc ? h * V + cidx[u] : -1;
+      }
+      // more than 32 * kCands candidates (rare): a lane keeps its best kCands >= K of them (its worst one is replaced)
+#pragma unroll 1
+      for (int c = lane + 32 * kCands; c < ncand; c += 32) {
+        const int idx = __ldcg(part_ti + cbase + c);
+        const float v = ((__ldcg(part_tv + cbase + c) - mx) - ls) + lp;
+        const bool okc = (idx >= 0) & (v == v);
+        const int key = okc ? fkey_s(v) : kNone, f = okc ? h * V + idx : -1;
+        int wk = ck[0], wf = cf[0];
+#pragma unroll
+        for (int u = 1; u < kCands; ++u) {
+          const bool lower = (ck[u] < wk) | ((ck[u] == wk) & (cf[u] < wf));
+          wk = lower ? ck[u] : wk; wf = lower ? cf[u] : wf;
+        }
+        const bool take = (key > wk) | ((key == wk) & (f > wf));
+        bool done = !take;
+#pragma unroll
+        for (int u = 0; u < kCands; ++u) {
+          const bool hit = !done & (ck[u] == wk) & (cf[u] == wf);
+          ck[u] = hit ? key : ck[u]; cf[u] = hit ? f : cf[u];
+          done |= hit;
+        }
+      }
+      // K rounds of warp arg-best over all registers: REDUX on the key, then on the flat index among the ties
+#pragma unroll
+      for (int r = 0; r < KB; ++r) {
+        if (r < K) {
+          int lk = ck[0];
+#pragma unroll
+          for (int u = 1; u < kCands; ++u) lk = max(lk, ck[u]);
+          const int wk = __reduce_max_sync(full, lk);
+          int lf = -1;
+#pragma unroll
+          for (int u = 0; u < kCands; ++u) lf = max(lf, (ck[u] == wk) ? cf[u] : -1);
+          const int wf = __reduce_max_sync(full, lf);      // flat indices are unique: exactly one register of one lane matches
+#pragma unroll
+          for (int u = 0; u < kCands; ++u) ck[u] = ((ck[u] == wk) & (cf[u] == wf)) ? kNone : ck[u];
+          if (lane == r) { c_v[h * K + r] = wf >= 0 ? funkey_s(wk) : -INFINITY; c_f[h * K + r] = wf; }
+        }
+      }
+    }
+    k2b::ptx::named_bar_sync(bar_id, 128);
+    // ---- B: the stream's top K, extension, merge ---------------------------------------------------------------------------
+    if (warp == 0) {
+      int tk[2], tf[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = lane + 32 * u;
+        const bool okc = i < K * K && c_f[i < KB * KB ? i : 0] >= 0;
+        tk[u] = okc ? fkey_s(c_v[i < KB * KB ? i : 0]) : kNone;
+        tf[u] = okc ? c_f[i < KB * KB ? i : 0] : -1;
+      }
+      float my_v = -INFINITY;
+      int my_f = -1;
+#pragma unroll
+      for (int r = 0; r < KB; ++r) {
+        if (r < K) {
+          const int wk = __reduce_max_sync(full, max(tk[0], tk[1]));
+          const int wf = __reduce_max_sync(full, max((tk[0] == wk) ? tf[0] : -1, (tk[1] == wk) ? tf[1] : -1));
+          tk[0] = ((tk[0] == wk) & (tf[0] == wf)) ? kNone : tk[0];
+          tk[1] = ((tk[1] == wk) & (tf[1] == wf)) ? kNone : tk[1];
+          if (lane == r) { my_v = wf >= 0 ? funkey_s(wk) : -INFINITY; my_f = wf; }
+        }
+      }
+      // lane r < K: the r-th extension in rank order
+      const bool cand = lane < K && my_f >= 0;
+      const int par = cand ? my_f / V : 0;
+      const uint64_t ph = __shfl_sync(full, p_hash, par);
+      const int pl = __shfl_sync(full, p_len, par), pc0 = __shfl_sync(full, p_c0, par), pc1 = __shfl_sync(full, p_c1, par);
+      int tok = -1, c0 = -1, c1 = blank, ln = 2;
+      uint64_t hs = kHashSeed;
+      if (cand) {
+        const int y = my_f - par * V;
+        hs = ph; ln = pl; c0 = pc0; c1 = pc1;
+        if (y != blank && y != unk) {      // ys unchanged for blank / unk
+          tok = y;
+          hs = hash_push(hs, y);
+          ln += 1;
+          c0 = c1;
+          c1 = y;
+        }
+      }
+      // dedupe: first earlier lane holding the same token sequence; log-add the merged scores into their root in rank order
+      int root = lane;
+      float lp = my_v;
+#pragma unroll
+      for (int q = 0; q < KB; ++q) {
+        if (q < K) {
+          const uint64_t qh = __shfl_sync(full, hs, q);
+          const int ql = __shfl_sync(full, ln, q);
+          const int q0 = __shfl_sync(full, c0, q);
+          const int q1 = __shfl_sync(full, c1, q);
+          const int qc = __shfl_sync(full, (int)cand, q);
+          if (cand && qc && q < lane && root == lane && qh == hs && ql == ln && q0 == c0 && q1 == c1) root = q;
+        }
+      }
+#pragma unroll 1
+      for (int q = 0; q < K; ++q) {
+        const int qroot = __shfl_sync(full, root, q);
+        const float qv = __shfl_sync(full, my_v, q);
+        const int qc = __shfl_sync(full, (int)cand, q);
+        if (cand && qc && q != lane && qroot == lane) lp = logaddexp_f(lp, qv);
+      }
+      const bool is_root = cand && root == lane;
+      const unsigned roots = __ballot_sync(full, is_root);
+      const int nnew = __popc(roots);
+      if (is_root) {
+        const int slot = __popc(roots & ((1u << lane) - 1u));
+        const size_t o = (size_t)s * K + slot;
+        out.ctx[2 * o] = c0;
+        out.ctx[2 * o + 1] = c1;
+        out.lp[o] = lp;
+        out.len[o] = ln;
+        out.hash[o] = hs;
+        bp[((size_t)s * T + t) * K + slot] = (par << 28) | (tok + 1);
+        s_ctx[2 * slot] = c0; s_ctx[2 * slot + 1] = c1;
+      }
+      if (lane >= nnew && lane < K) {      // dead slots keep a valid context for the next joiner operand
+        const size_t o = (size_t)s * K + lane;
+        out.ctx[2 * o] = -1;
+        out.ctx[2 * o + 1] = blank;
+        out.lp[o] = -INFINITY;
+        out.len[o] = 2;
+        out.hash[o] = kHashSeed;
+        bp[((size_t)s * T + t) * K + lane] = 0;
+        s_ctx[2 * lane] = -1; s_ctx[2 * lane + 1] = blank;
+      }
+      if (lane == 0) out.nlive[s] = nnew;
+    }
+  }
+  k2b::ptx::named_bar_sync(bar_id, 128);
+  if (tl != nullptr && tid == 0) atomicMax(reinterpret_cast<unsigned long long*>(tl + 6), (unsigned long long)clock64());
+  // ---- C: the next frame's joiner operand of this stream's K hypotheses -------------------------------------------------------
+  if (!build) return;
+  constexpr int kRowTile = 128, kImgTile = 128 * 128;        // rows per image tile, bytes of one 128 x 64 bf16 tile
+  for (int k = 4 * tid; k < J; k += 512) {
+    const float4 e = k == 4 * tid ? e4 : __ldg(reinterpret_cast<const float4*>(enc_next + (size_t)s * enc_stride + k));
+    const float ex[4] = {expf(2.f * fminf(fmaxf(e.x, -21.f), 21.f)), expf(2.f * fminf(fmaxf(e.y, -21.f), 21.f)),
+                         expf(2.f * fminf(fmaxf(e.z, -21.f), 21.f)), expf(2.f * fminf(fmaxf(e.w, -21.f), 21.f))};
+    float4 d[KB];
+#pragma unroll
+    for (int q = 0; q < KB; ++q)
+      if (q < K)
+        d[q] = __ldg(reinterpret_cast<const float4*>(dec_tab + ((size_t)(s_ctx[2 * q] + 1) * V + s_ctx[2 * q + 1]) * J + k));
+#pragma unroll
+    for (int q = 0; q < KB; ++q) {
+      if (q < K) {
+        const int m = s * K + q;
+        const float dv[4] = {d[q].x, d[q].y, d[q].z, d[q].w};
+        float x[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {       // tanh(e + d) = 1 - 2 / (1 + exp(2e) * exp(2d)); the table holds exp(2d)
+          float r;
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(ex[i], dv[i], 1.f)));
+          x[i] = fmaf(-2.f, r, 1.f);
+        }
+        uint8_t* timg = x_img + ((size_t)(m / kRowTile) * (J / 64) + (k >> 6)) * (2 * kImgTile) +
+                        k2b::ptx::sw128_offset(m % kRowTile, k & 63);
+        const float h0 = k2b::ptx::bf16_round(x[0]), h1 = k2b::ptx::bf16_round(x[1]), h2 = k2b::ptx::bf16_round(x[2]),
+                    h3 = k2b::ptx::bf16_round(x[3]);
+        *reinterpret_cast<uint2*>(timg) = make_uint2(k2b::ptx::pack_bf16x2(h0, h1), k2b::ptx::pack_bf16x2(h2, h3));
+        *reinterpret_cast<uint2*>(timg + kImgTile) =
+            make_uint2(k2b::ptx::pack_bf16x2(x[0] - h0, x[1] - h1), k2b::ptx::pack_bf16x2(x[2] - h2, x[3] - h3));
+      }
+    }
+  }
+  if (tl != nullptr && tid == 0) atomicMax(reinterpret_cast<unsigned long long*>(tl + 7), (unsigned long long)clock64());
+}
+
+
+}  // namespace k2b

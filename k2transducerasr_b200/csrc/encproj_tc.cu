@@ -576,7 +576,7 @@ bool joiner_tc_supported(const k2b_handle* h) { return h->cfg.joiner_dim % 64 ==
 
 int joiner_tc_tiles(const k2b_handle* h) { return (h->cfg.vocab_size + kJN - 1) / kJN; }
 
-static int32_t ensure_joiner_assets(k2b_handle* h) {
+int32_t ensure_joiner_assets(k2b_handle* h) {
   if (h->wj_ready) return K2B_OK;
   const int V = h->cfg.vocab_size, K = h->cfg.joiner_dim, Np = joiner_tc_tiles(h) * kJN;
   K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->wj_hi_img), (size_t)Np * K * 2));

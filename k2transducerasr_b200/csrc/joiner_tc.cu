@@ -11,12 +11,19 @@
 //               the fp32 value in a per-thread shared-memory row and pushes an order-preserving integer key (low 8 bits = column)
 //               through a branch-free max/min insertion network - no shuffles, no divergence, 7 integer ops per logit for K <= 4;
 //               pass 2 re-reads the row for the sum of exponentials and fetches the exact fp32 logits of the K winners.
-// Launched with programmatic stream serialization: barrier set-up, TMEM allocation and the first weight copies overlap the tail of
+// MEGA = true is the whole modified_beam_search time loop in ONE launch (cfg4: 250 frames): four more warps per CTA run the
+// hypothesis merge + next-operand step (beam_merge.cuh) of the CTA's streams, and the two kinds of work are chained by per-frame,
+// per-row-tile counters in global memory (release / acquire) instead of kernel boundaries: a stream's merge of frame t starts when
+// the 35 column tiles of its row tile are reduced, a tile of frame t+1 is loaded when the 32 streams of its row tile have written
+// their operand rows. Tiles are walked row-major, so the merges of the first wave's row tiles run under the second wave's GEMMs
+// and vice versa - the merge leaves the critical path.
+// MEGA = false: launched with programmatic stream serialization: barrier set-up, TMEM allocation and the first weight copies overlap the tail of
 // the operand kernel; griddepcontrol.wait precedes the first read of x and every write.
 #include <stdlib.h>
 
 #include "k2b_internal.h"
 #include "sm100_ptx.cuh"
+#include "beam_merge.cuh"
 
 namespace k2b {
 
@@ -45,7 +52,41 @@ struct JArgs {
   int* status;
   long long* dbg;
   long long* tl;             // diagnostic timeline of this launch: [sm][8] clock64 stamps (slots 0..3), or null
+  // MEGA: the whole search
+  int B, V, T, blank, unk, J;
+  BeamState st[2];           // frame t reads st[t & 1], writes st[(t & 1) ^ 1]
+  int32_t* bp;
+  const int32_t* lens;
+  const float* dec_tab;
+  const float* enc;          // [B,T,J] projected frames
+  long long enc_stride;
+  uint8_t* x_img;            // = a_img
+  int* done;                 // [T][ntm]: column tiles of (frame, row tile) whose partials are written
+  int* ready;                // [T+1][ntm]: streams of (frame, row tile) whose operand rows are written
+  int* abort_flag;
 };
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// bounded wait for *p >= need (another CTA's release); false on time-out or when some CTA has given up
+__device__ __forceinline__ bool wait_count(const int* p, int need, int* abort_flag) {
+  if (ld_acquire_gpu(p) >= need) return true;
+  const long long t0 = clock64();
+#pragma unroll 1
+  while (clock64() - t0 < kWaitTimeoutCycles) {
+    if (ld_acquire_gpu(p) >= need) return true;
+    if (ld_acquire_gpu(abort_flag) != 0) return false;
+    __nanosleep(32);
+  }
+  atomicExch(abort_flag, 1);
+  return false;
+}
 
 template <int KK>
 __device__ __forceinline__ void push_key(int (&a)[KK], int t) {
@@ -57,12 +98,16 @@ __device__ __forceinline__ void push_key(int (&a)[KK], int t) {
   }
 }
 
-template <int KK>
-__global__ void __launch_bounds__(kThreads, 1) joiner_topk_kernel(const JArgs a) {
+template <int KK, bool MEGA>
+__global__ void __launch_bounds__(MEGA ? kThreads + 128 : kThreads, 1) joiner_topk_kernel(const JArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full[kStages], empty[kStages], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float bias_t[kJNc];
+  __shared__ float mg_v[MEGA ? KK * KK : 1];
+  __shared__ int mg_f[MEGA ? KK * KK : 1], mg_ctx[MEGA ? 2 * KK : 1];
+  const int nframes = MEGA ? a.T : 1;
+  const int spr = MEGA ? kJM / a.topk : 0;               // streams per row tile
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long c_start = (a.dbg != nullptr || a.tl != nullptr) ? clock64() : 0;
@@ -82,7 +127,7 @@ __global__ void __launch_bounds__(kThreads, 1) joiner_topk_kernel(const JArgs a)
   tc_fence_after();
   const uint32_t t_d = tmem_slot;
   bool ok = true;
-  griddep_launch_dependents();
+  if (!MEGA) griddep_launch_dependents();
   long long* tl = nullptr;
   if (a.tl != nullptr) {
     uint32_t smid;
@@ -96,20 +141,27 @@ __global__ void __launch_bounds__(kThreads, 1) joiner_topk_kernel(const JArgs a)
     if (lane == 0) {
       const uint32_t w_bytes = (uint32_t)(x3 ? 2 * kWTile : kWTile), a_bytes = (uint32_t)(x3 ? 2 * kATile : kATile);
       uint32_t kc = 0;
-      bool waited = false;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int tile_n = tile / a.ntm, tile_m = tile - tile_n * a.ntm;
-        for (int kb = 0; kb < nkb; ++kb, ++kc) {
-          const int s = kc % kStages;
-          const uint32_t ph = (kc / kStages) & 1u;
-          if (!mbar_wait(&empty[s], ph ^ 1u)) ok = false;
-          uint8_t* st = smem + (size_t)s * kStageBytes;
-          const size_t off = ((size_t)tile_n * nkb + kb) * kWTile;
-          mbar_expect_tx(&full[s], w_bytes + a_bytes);
-          tma_bulk_g2s(st + 2 * kATile, a.w_hi_img + off, kWTile, &full[s]);
-          if (x3) tma_bulk_g2s(st + 2 * kATile + kWTile, a.w_lo_img + off, kWTile, &full[s]);
-          if (!waited) { griddep_wait(); waited = true; }      // x is the previous kernel's output; the weights are not
-          tma_bulk_g2s(st, a.a_img + ((size_t)tile_m * nkb + kb) * (2 * kATile), a_bytes, &full[s]);
+      bool waited = MEGA;
+      for (int t = 0; t < nframes && ok; ++t) {
+        for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
+          const int tile_m = tile / a.ntn, tile_n = tile - tile_m * a.ntn;      // row-major: a row tile completes early
+          if (MEGA && t > 0) {       // the operand rows of this row tile are the merge step's output of frame t - 1
+            const int need = min(spr, a.B - tile_m * spr);
+            if (!wait_count(a.ready + (size_t)t * a.ntm + tile_m, need, a.abort_flag)) { ok = false; break; }
+            asm volatile("fence.proxy.async;" ::: "memory");
+          }
+          for (int kb = 0; kb < nkb; ++kb, ++kc) {
+            const int s = kc % kStages;
+            const uint32_t ph = (kc / kStages) & 1u;
+            if (!mbar_wait(&empty[s], ph ^ 1u)) ok = false;
+            uint8_t* st = smem + (size_t)s * kStageBytes;
+            const size_t off = ((size_t)tile_n * nkb + kb) * kWTile;
+            mbar_expect_tx(&full[s], w_bytes + a_bytes);
+            tma_bulk_g2s(st + 2 * kATile, a.w_hi_img + off, kWTile, &full[s]);
+            if (x3) tma_bulk_g2s(st + 2 * kATile + kWTile, a.w_lo_img + off, kWTile, &full[s]);
+            if (!waited) { griddep_wait(); waited = true; }      // x is the previous kernel's output; the weights are not
+            tma_bulk_g2s(st, a.a_img + ((size_t)tile_m * nkb + kb) * (2 * kATile), a_bytes, &full[s]);
+          }
         }
       }
     }
@@ -120,7 +172,8 @@ __global__ void __launch_bounds__(kThreads, 1) joiner_topk_kernel(const JArgs a)
     const uint32_t desc_hi = 64u | (1u << 14) | (2u << 29);
     uint32_t kc = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    for (int t = 0; t < nframes && ok; ++t)
+    for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
       if (!mbar_wait(&acc_empty[as], aph ^ 1u)) ok = false;
@@ -154,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, 1) joiner_topk_kernel(const JArgs a)
       }
       umma_commit_e(&acc_full[as], el);
     }
-  } else {
+  } else if (warp_u < 6) {
     // ---- epilogue: thread = logits row ------------------------------------------------------------------------------------
     const int lg = warp & 3;                              // TMEM lane quarter this warp may read
     const int row = lg * 32 + lane;
@@ -164,10 +217,11 @@ __global__ void __launch_bounds__(kThreads, 1) joiner_topk_kernel(const JArgs a)
     long long c_acc = 0, c_epi = 0;
     const int K = a.topk;
     int it = 0;
-    griddep_wait();                                       // partials are read by the previous frame's merge kernel
+    if (!MEGA) griddep_wait();                            // partials are read by the previous frame's merge kernel
     if (tl != nullptr && tid == 64) tl[1] = clock64();
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      const int tile_n = tile / a.ntm, tile_m = tile - tile_n * a.ntm;
+    for (int t = 0; t < nframes && ok; ++t)
+    for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x, ++it) {
+      const int tile_m = tile / a.ntn, tile_n = tile - tile_m * a.ntn;
       const int as = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
       const int col0 = tile_n * kJNc;
@@ -237,6 +291,11 @@ __global__ void __launch_bounds__(kThreads, 1) joiner_topk_kernel(const JArgs a)
         }
       }
       if (dbg && it == 0) c_epi = clock64();
+      if (MEGA) {                                         // publish: one more column tile of (frame, row tile) is reduced
+        __threadfence();
+        named_bar_sync(3, 128);
+        if (etid == 0) red_release_gpu(a.done + (size_t)t * a.ntm + tile_m, 1);
+      }
     }
     if (tl != nullptr && tid == 64) tl[3] = clock64();
     if (dbg) {
@@ -247,23 +306,69 @@ __global__ void __launch_bounds__(kThreads, 1) joiner_topk_kernel(const JArgs a)
       atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg + 13), 1ull);
     }
   }
+  else if (MEGA) {
+    // ---- merge warps: hypothesis merge + next operand of this CTA's streams, frame by frame -------------------------------------
+    const int mtid = tid - kThreads;
+    for (int t = 0; t < nframes && ok; ++t) {
+      const float* enc_next = t + 1 < a.T ? a.enc + (size_t)(t + 1) * a.J : nullptr;
+      for (int s = blockIdx.x; s < a.B && ok; s += gridDim.x) {
+        const int r = s / spr;
+        float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (enc_next != nullptr && 4 * mtid < a.J) e4 = __ldg(reinterpret_cast<const float4*>(enc_next + (size_t)s * a.enc_stride + 4 * mtid));
+        int good = 1;
+        if (mtid == 0) good = wait_count(a.done + (size_t)t * a.ntm + r, a.ntn, a.abort_flag) ? 1 : 0;
+        if (mtid == 0) mg_ctx[0] = good;
+        named_bar_sync(2, 128);
+        good = mg_ctx[0];
+        named_bar_sync(2, 128);                           // mg_ctx is rewritten by the merge step
+        if (!good) { ok = false; break; }
+        const bool odd = (t & 1) != 0;
+        BeamState sin, sout;
+        sin.ctx = odd ? a.st[1].ctx : a.st[0].ctx; sout.ctx = odd ? a.st[0].ctx : a.st[1].ctx;
+        sin.lp = odd ? a.st[1].lp : a.st[0].lp; sout.lp = odd ? a.st[0].lp : a.st[1].lp;
+        sin.len = odd ? a.st[1].len : a.st[0].len; sout.len = odd ? a.st[0].len : a.st[1].len;
+        sin.hash = odd ? a.st[1].hash : a.st[0].hash; sout.hash = odd ? a.st[0].hash : a.st[1].hash;
+        sin.nlive = odd ? a.st[1].nlive : a.st[0].nlive; sout.nlive = odd ? a.st[0].nlive : a.st[1].nlive;
+        beam_merge_stream<KK>(mtid, 2, s, a.topk, a.V, a.ntn, a.T, t, a.blank, a.unk, a.part_m, a.part_s, a.part_tv, a.part_ti,
+                              sin, sout, a.bp, a.lens, a.dec_tab, enc_next, a.enc_stride, a.J, a.x_img, e4,
+                              mg_v, mg_f, mg_ctx, nullptr);
+        if (t + 1 < a.T) {                                // publish: one more stream of (frame t + 1, row tile) has its operand rows
+          __threadfence();
+          asm volatile("fence.proxy.async;" ::: "memory");
+          named_bar_sync(2, 128);
+          if (mtid == 0) red_release_gpu(a.ready + (size_t)(t + 1) * a.ntm + r, 1);
+        }
+      }
+    }
+  }
   if (!ok) atomicExch(a.status, 1);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(t_d, 512);
 }
 
-template <int KK>
+template <int KK, bool MEGA>
 int32_t launch_as(k2b_handle* h, const JArgs& a) {
   static bool attr_set = false;
   const size_t smem = (size_t)kStages * kStageBytes + kTileBytes;
   if (!attr_set) {
-    K2B_CUDA(h, cudaFuncSetAttribute(joiner_topk_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    K2B_CUDA(h, (cudaFuncSetAttribute(joiner_topk_kernel<KK, MEGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
     attr_set = true;
   }
   const int tiles = a.ntm * a.ntn;
   const int grid = tiles < h->sm_count ? tiles : h->sm_count;
-  K2B_CUDA(h, launch_pdl(joiner_topk_kernel<KK>, dim3(grid), dim3(kThreads), smem, h->stream, a));
+  if (MEGA) {
+    // every CTA waits for counters other CTAs publish: all of them must be resident at once (cooperative launch checks that)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads + 128); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    K2B_CUDA(h, cudaLaunchKernelEx(&cfg, joiner_topk_kernel<KK, MEGA>, a));
+  } else {
+    K2B_CUDA(h, launch_pdl(joiner_topk_kernel<KK, MEGA>, dim3(grid), dim3(kThreads), smem, h->stream, a));
+  }
   K2B_LAUNCH_CHECK(h);
   return K2B_OK;
 }
@@ -292,7 +397,37 @@ int32_t joiner_topk_tc(k2b_handle* h, const uint8_t* x_img, int M, int topk, flo
   a.status = h->dev_status + 1;
   a.dbg = h->cluster_timing;
   a.tl = h->timeline != nullptr ? h->timeline + (size_t)(h->timeline_frame % 64) * 148 * 8 : nullptr;
-  return topk <= 4 ? launch_as<4>(h, a) : launch_as<8>(h, a);
+  return topk <= 4 ? launch_as<4, false>(h, a) : launch_as<8, false>(h, a);
+}
+
+
+// ---- the whole modified_beam_search time loop in one launch (memoised decoder, K in {2, 4, 8}) --------------------------------
+bool beam_mega_usable(const k2b_handle* h, int K) {
+  const bool off = getenv("K2B_NO_MEGA") != nullptr;       // read per call: tests compare the two engines in one process
+  return !off && (K == 2 || K == 4 || K == 8) && joiner_topk_usable(h, K) && h->dec_tab != nullptr;
+}
+
+int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8_t* x_img, float* part_m, float* part_s, float* part_tv,
+                     int32_t* part_ti, const BeamStatePtrs& s0, const BeamStatePtrs& s1, int32_t* bp, const int32_t* lens) {
+  const int M = B * K;
+  JArgs a = {};
+  a.a_img = x_img; a.x_img = x_img; a.w_hi_img = h->wj_hi_img; a.w_lo_img = h->wj_lo_img; a.bias = h->out_b;
+  a.M = M; a.ntm = (M + kJM - 1) / kJM; a.ntn = (h->cfg.vocab_size + kJNc - 1) / kJNc; a.nkb = h->cfg.joiner_dim / kJBK;
+  a.x3 = h->cfg.precision == K2B_PREC_BF16 ? 0 : 1;
+  a.nvalid = h->cfg.vocab_size; a.topk = K;
+  a.part_m = part_m; a.part_s = part_s; a.part_tv = part_tv; a.part_ti = part_ti;
+  a.status = h->dev_status + 1;
+  a.B = B; a.V = h->cfg.vocab_size; a.T = T; a.blank = h->cfg.blank_id; a.unk = h->cfg.unk_id; a.J = h->cfg.joiner_dim;
+  a.st[0] = BeamState{s0.ctx, s0.lp, s0.len, reinterpret_cast<uint64_t*>(s0.hash), s0.nlive};
+  a.st[1] = BeamState{s1.ctx, s1.lp, s1.len, reinterpret_cast<uint64_t*>(s1.hash), s1.nlive};
+  a.bp = bp; a.lens = lens; a.dec_tab = h->dec_tab; a.enc = enc; a.enc_stride = (long long)T * a.J;
+  const size_t nsync = (size_t)(2 * T + 1) * a.ntm + 1;
+  K2B_TRY(ensure(h, h->ws_sync, nsync * sizeof(int)));
+  K2B_CUDA(h, cudaMemsetAsync(h->ws_sync.p, 0, nsync * sizeof(int), h->stream));
+  a.done = static_cast<int*>(h->ws_sync.p);
+  a.ready = a.done + (size_t)T * a.ntm;
+  a.abort_flag = a.ready + (size_t)(T + 1) * a.ntm;
+  return K <= 4 ? launch_as<4, true>(h, a) : launch_as<8, true>(h, a);
 }
 
 }  // namespace k2b

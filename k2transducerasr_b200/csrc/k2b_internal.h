@@ -71,6 +71,7 @@ struct k2b_handle {
   k2b::DevBuf ws_bp;        // beam back-pointers [B,T,K]
   k2b::DevBuf ws_out;       // host-variant staging of tokens / ts / n / score
   k2b::DevBuf ws_misc;      // int32 contexts of the fine-grained decoder call
+  k2b::DevBuf ws_sync;      // persistent beam-search kernel: per-(frame, row tile) counters
   k2b::DevBuf ws_ctc;       // ctc: per-frame ids [B*T] + per-stream tickets [B] (tickets stay zero between launches)
 
   // tensor-core (cluster) path assets, built on first use after a weight load (search_cluster.cu)
@@ -228,6 +229,7 @@ int32_t decoder_joinin_tc(k2b_handle* h, const int32_t* ctx, int M, const float*
                           float* x, uint8_t* x_img);
 size_t joiner_tc_image_bytes(const k2b_handle* h, int M);
 bool joiner_tc_supported(const k2b_handle* h);
+int32_t ensure_joiner_assets(k2b_handle* h);
 int joiner_tc_tiles(const k2b_handle* h);
 int32_t joiner_tc_partials(k2b_handle* h, const float* x, const uint8_t* x_img, int M, int topk, float* part_m, float* part_s,
                            float* part_tv, int32_t* part_ti, float* part_val, int32_t* part_idx, int32_t* part_nan);
@@ -237,6 +239,11 @@ bool joiner_topk_supported(const k2b_handle* h, int topk);
 bool joiner_topk_usable(const k2b_handle* h, int topk);   // the persistent joiner will serve joiner_tc_partials(x_img, topk)
 int32_t joiner_topk_tc(k2b_handle* h, const uint8_t* x_img, int M, int topk, float* part_m, float* part_s, float* part_tv,
                        int32_t* part_ti);
+
+struct BeamStatePtrs { int32_t* ctx; float* lp; int32_t* len; unsigned long long* hash; int32_t* nlive; };
+bool beam_mega_usable(const k2b_handle* h, int K);
+int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8_t* x_img, float* part_m, float* part_s, float* part_tv,
+                     int32_t* part_ti, const BeamStatePtrs& s0, const BeamStatePtrs& s1, int32_t* bp, const int32_t* lens);
 
 // profiling bracket around the dominant GEMM
 void prof_begin(k2b_handle* h);

@@ -10,26 +10,12 @@
 
 #include "k2b_internal.h"
 #include "sm100_ptx.cuh"
+#include "beam_merge.cuh"
 
 namespace k2b {
 
 namespace {
 
-constexpr uint64_t kHashSeed = 0x9E3779B97F4A7C15ull;
-
-__device__ __forceinline__ uint64_t hash_push(uint64_t h, int tok) {
-  h = (h ^ (uint64_t)(uint32_t)(tok + 1)) * 0x100000001B3ull;
-  h ^= h >> 29;
-  h *= 0xBF58476D1CE4E5B9ull;
-  h ^= h >> 32;
-  return h;
-}
-
-__device__ __forceinline__ float logaddexp_f(float a, float b) {
-  const float mx = fmaxf(a, b), mn = fminf(a, b);
-  if (mx == -INFINITY) return -INFINITY;
-  return mx + log1pf(expf(mn - mx));
-}
 
 // ------------------------------------------------------------------------------------------------
 // greedy
@@ -95,13 +81,6 @@ __global__ void greedy_finish_online_kernel(int B, const int32_t* __restrict__ c
 // ------------------------------------------------------------------------------------------------
 // modified_beam_search
 // ------------------------------------------------------------------------------------------------
-struct BeamState {
-  int32_t* ctx;    // [N,2]
-  float* lp;       // [N]
-  int32_t* len;    // [N]
-  uint64_t* hash;  // [N]
-  int32_t* nlive;  // [B]
-};
 
 __global__ void beam_init_kernel(int B, int K, int blank, BeamState s0, BeamState s1) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -123,8 +102,6 @@ __device__ __forceinline__ bool better(float v, int i, float ev, int ei) {
 // per-stream top-K over the K*V extensions (value desc, flat index desc), extension, dedupe by
 // token-sequence hash with log-add, compaction in insertion order, back-pointer record.
 // Branch-free throughout (predicated selects, REDUX max for the arg-best rounds): the lanes of a warp never diverge.
-__device__ __forceinline__ int fkey_s(float f) { const int k = __float_as_int(f); return k ^ ((k >> 31) & 0x7fffffff); }
-__device__ __forceinline__ float funkey_s(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
 
 __global__ void __launch_bounds__(128)
 beam_select_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
@@ -335,8 +312,8 @@ beam_select_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk
 //   C. all threads: x[m,:] = tanh(enc[s,t+1] + decoder(ctx[m])) of the K new hypotheses from the memoised decoder table, written
 //      as the bf16 hi / lo tile images the joiner's loader warp fetches (what joinin_table_kernel does in a launch of its own).
 // Same results as beam_select_kernel + joinin_table_kernel; one launch and one round trip of the contexts through HBM less.
-// KB = 4 or 8: compile-time bound of the beam (the kernel is latency-bound and every instruction is executed once per frame,
-// so its code size is its run time: loops are unrolled to exactly KB levels).
+// Stand-alone launch of the frame step, one CTA per stream (beam_merge.cuh): same results as beam_select_kernel +
+// joinin_table_kernel; one launch and one round trip of the contexts through HBM less.
 template <int KB>
 __global__ void __launch_bounds__(128)
 beam_step_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
@@ -348,17 +325,11 @@ beam_step_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
   __shared__ float c_v[KB * KB];
   __shared__ int c_f[KB * KB];
   __shared__ int s_ctx[2 * KB];
-  constexpr int kNone = (int)0x80000000;
-  constexpr int kPairs = 2, kCands = 8;            // per-lane register batches: nt <= 64, nt * K <= 256 without a tail pass
-  static_assert(kCands >= KB, "a lane must be able to hold a whole top-K");
-  const unsigned full = 0xffffffffu;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int s = blockIdx.x;
+  const int tid = threadIdx.x, s = blockIdx.x;
   k2b::ptx::griddep_launch_dependents();
   // the next frame of this stream does not depend on the kernels before this one: fetch it ahead of the wait
-  const bool build = enc_next != nullptr;
   float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (build && 4 * tid < J) e4 = __ldg(reinterpret_cast<const float4*>(enc_next + (size_t)s * enc_stride + 4 * tid));
+  if (enc_next != nullptr && 4 * tid < J) e4 = __ldg(reinterpret_cast<const float4*>(enc_next + (size_t)s * enc_stride + 4 * tid));
   if (tl != nullptr) {                                      // diagnostic timeline: [sm][8], slots 4..7 = first start, first wait-done,
     uint32_t smid;                                          // last merge-done, last end of the CTAs of this launch on that SM
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -367,243 +338,8 @@ beam_step_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
   }
   k2b::ptx::griddep_wait();
   if (tl != nullptr && tid == 0) atomicMin(reinterpret_cast<long long*>(tl + 5), clock64());
-  const int nl = in.nlive[s];
-  const bool frozen = lens != nullptr && t >= lens[s];      // ragged batch: past the end of this stream
-  if (tid < KB * KB) { c_v[tid] = -INFINITY; c_f[tid] = -1; }
-  // parents' state, lane q of warp 0 <-> hypothesis q
-  uint64_t p_hash = kHashSeed;
-  int p_len = 2, p_c0 = -1, p_c1 = blank;
-  float p_lp = -INFINITY;
-  if (warp == 0 && lane < K) {
-    const size_t o = (size_t)s * K + lane;
-    p_hash = in.hash[o]; p_len = in.len[o]; p_c0 = in.ctx[2 * o]; p_c1 = in.ctx[2 * o + 1]; p_lp = in.lp[o];
-  }
-  __syncthreads();
-  if (frozen) {
-    if (warp == 0) {
-      if (lane < K) {
-        const size_t o = (size_t)s * K + lane;
-        out.ctx[2 * o] = p_c0; out.ctx[2 * o + 1] = p_c1;
-        out.lp[o] = p_lp; out.len[o] = p_len; out.hash[o] = p_hash;
-        bp[((size_t)s * T + t) * K + lane] = lane < nl ? (lane << 28) : 0;
-        s_ctx[2 * lane] = p_c0; s_ctx[2 * lane + 1] = p_c1;
-      }
-      if (lane == 0) out.nlive[s] = nl;
-    }
-  } else {
-    // ---- A: per live hypothesis --------------------------------------------------------------------------------------------
-#pragma unroll 1
-    for (int h = warp; h < nl; h += 4) {
-      const size_t row = (size_t)s * K + h;
-      const float* pmr = part_m + row * nt;
-      const float* psr = part_s + row * nt;
-      const size_t cbase = row * nt * K;
-      const int ncand = nt * K;
-      float pm[kPairs], ps[kPairs], cval[kCands];
-      int cidx[kCands];
-#pragma unroll
-      for (int u = 0; u < kPairs; ++u) {
-        const int i = lane + 32 * u;
-        pm[u] = i < nt ? pmr[i] : -INFINITY;
-        ps[u] = i < nt ? psr[i] : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < kCands; ++u) {
-        const int c = lane + 32 * u;
-        cidx[u] = c < ncand ? part_ti[cbase + c] : -1;
-        cval[u] = c < ncand ? part_tv[cbase + c] : 0.f;
-      }
-      const float lp = in.lp[row];
-      int mk = max(fkey_s(pm[0]), fkey_s(pm[1]));           // absent tiles read as -inf
-#pragma unroll 1
-      for (int i = lane + 32 * kPairs; i < nt; i += 32) mk = max(mk, fkey_s(pmr[i]));
-      const float mx = funkey_s(__reduce_max_sync(full, mk));
-      float sum = 0.f;
-#pragma unroll
-      for (int u = 0; u < kPairs; ++u) sum += (pm[u] > -INFINITY) ? ps[u] * __expf(pm[u] - mx) : 0.f;
-#pragma unroll 1
-      for (int i = lane + 32 * kPairs; i < nt; i += 32) {
-        const float m2 = pmr[i];
-        sum += (m2 > -INFINITY) ? psr[i] * __expf(m2 - mx) : 0.f;
-      }
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(full, sum, o);
-      const float ls = __logf(sum);
-      // this lane's candidates as (key, flat index); same operation order as log_softmax(x) + lp : ((x - max) - log(sum)) + lp
-      int ck[kCands], cf[kCands];
-#pragma unroll
-      for (int u = 0; u < kCands; ++u) {
-        const float v = ((cval[u] - mx) - ls) + lp;
-        const bool okc = (cidx[u] >= 0) & (v == v);
-        ck[u] = okc ? fkey_s(v) : kNone;
-        cf[u] = okc ? h * V + cidx[u] : -1;
-      }
-      // more than 32 * kCands candidates (rare): a lane keeps its best kCands >= K of them (its worst one is replaced)
-#pragma unroll 1
-      for (int c = lane + 32 * kCands; c < ncand; c += 32) {
-        const int idx = part_ti[cbase + c];
-        const float v = ((part_tv[cbase + c] - mx) - ls) + lp;
-        const bool okc = (idx >= 0) & (v == v);
-        const int key = okc ? fkey_s(v) : kNone, f = okc ? h * V + idx : -1;
-        int wk = ck[0], wf = cf[0];
-#pragma unroll
-        for (int u = 1; u < kCands; ++u) {
-          const bool lower = (ck[u] < wk) | ((ck[u] == wk) & (cf[u] < wf));
-          wk = lower ? ck[u] : wk; wf = lower ? cf[u] : wf;
-        }
-        const bool take = (key > wk) | ((key == wk) & (f > wf));
-        bool done = !take;
-#pragma unroll
-        for (int u = 0; u < kCands; ++u) {
-          const bool hit = !done & (ck[u] == wk) & (cf[u] == wf);
-          ck[u] = hit ? key : ck[u]; cf[u] = hit ? f : cf[u];
-          done |= hit;
-        }
-      }
-      // K rounds of warp arg-best over all registers: REDUX on the key, then on the flat index among the ties
-#pragma unroll
-      for (int r = 0; r < KB; ++r) {
-        if (r < K) {
-          int lk = ck[0];
-#pragma unroll
-          for (int u = 1; u < kCands; ++u) lk = max(lk, ck[u]);
-          const int wk = __reduce_max_sync(full, lk);
-          int lf = -1;
-#pragma unroll
-          for (int u = 0; u < kCands; ++u) lf = max(lf, (ck[u] == wk) ? cf[u] : -1);
-          const int wf = __reduce_max_sync(full, lf);      // flat indices are unique: exactly one register of one lane matches
-#pragma unroll
-          for (int u = 0; u < kCands; ++u) ck[u] = ((ck[u] == wk) & (cf[u] == wf)) ? kNone : ck[u];
-          if (lane == r) { c_v[h * K + r] = wf >= 0 ? funkey_s(wk) : -INFINITY; c_f[h * K + r] = wf; }
-        }
-      }
-    }
-    __syncthreads();
-    // ---- B: the stream's top K, extension, merge ---------------------------------------------------------------------------
-    if (warp == 0) {
-      int tk[2], tf[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int i = lane + 32 * u;
-        const bool okc = i < K * K && c_f[i < KB * KB ? i : 0] >= 0;
-        tk[u] = okc ? fkey_s(c_v[i < KB * KB ? i : 0]) : kNone;
-        tf[u] = okc ? c_f[i < KB * KB ? i : 0] : -1;
-      }
-      float my_v = -INFINITY;
-      int my_f = -1;
-#pragma unroll
-      for (int r = 0; r < KB; ++r) {
-        if (r < K) {
-          const int wk = __reduce_max_sync(full, max(tk[0], tk[1]));
-          const int wf = __reduce_max_sync(full, max((tk[0] == wk) ? tf[0] : -1, (tk[1] == wk) ? tf[1] : -1));
-          tk[0] = ((tk[0] == wk) & (tf[0] == wf)) ? kNone : tk[0];
-          tk[1] = ((tk[1] == wk) & (tf[1] == wf)) ? kNone : tk[1];
-          if (lane == r) { my_v = wf >= 0 ? funkey_s(wk) : -INFINITY; my_f = wf; }
-        }
-      }
-      // lane r < K: the r-th extension in rank order
-      const bool cand = lane < K && my_f >= 0;
-      const int par = cand ? my_f / V : 0;
-      const uint64_t ph = __shfl_sync(full, p_hash, par);
-      const int pl = __shfl_sync(full, p_len, par), pc0 = __shfl_sync(full, p_c0, par), pc1 = __shfl_sync(full, p_c1, par);
-      int tok = -1, c0 = -1, c1 = blank, ln = 2;
-      uint64_t hs = kHashSeed;
-      if (cand) {
-        const int y = my_f - par * V;
-        hs = ph; ln = pl; c0 = pc0; c1 = pc1;
-        if (y != blank && y != unk) {      // ys unchanged for blank / unk
-          tok = y;
-          hs = hash_push(hs, y);
-          ln += 1;
-          c0 = c1;
-          c1 = y;
-        }
-      }
-      // dedupe: first earlier lane holding the same token sequence; log-add the merged scores into their root in rank order
-      int root = lane;
-      float lp = my_v;
-#pragma unroll
-      for (int q = 0; q < KB; ++q) {
-        if (q < K) {
-          const uint64_t qh = __shfl_sync(full, hs, q);
-          const int ql = __shfl_sync(full, ln, q);
-          const int q0 = __shfl_sync(full, c0, q);
-          const int q1 = __shfl_sync(full, c1, q);
-          const int qc = __shfl_sync(full, (int)cand, q);
-          if (cand && qc && q < lane && root == lane && qh == hs && ql == ln && q0 == c0 && q1 == c1) root = q;
-        }
-      }
-#pragma unroll 1
-      for (int q = 0; q < K; ++q) {
-        const int qroot = __shfl_sync(full, root, q);
-        const float qv = __shfl_sync(full, my_v, q);
-        const int qc = __shfl_sync(full, (int)cand, q);
-        if (cand && qc && q != lane && qroot == lane) lp = logaddexp_f(lp, qv);
-      }
-      const bool is_root = cand && root == lane;
-      const unsigned roots = __ballot_sync(full, is_root);
-      const int nnew = __popc(roots);
-      if (is_root) {
-        const int slot = __popc(roots & ((1u << lane) - 1u));
-        const size_t o = (size_t)s * K + slot;
-        out.ctx[2 * o] = c0;
-        out.ctx[2 * o + 1] = c1;
-        out.lp[o] = lp;
-        out.len[o] = ln;
-        out.hash[o] = hs;
-        bp[((size_t)s * T + t) * K + slot] = (par << 28) | (tok + 1);
-        s_ctx[2 * slot] = c0; s_ctx[2 * slot + 1] = c1;
-      }
-      if (lane >= nnew && lane < K) {      // dead slots keep a valid context for the next joiner operand
-        const size_t o = (size_t)s * K + lane;
-        out.ctx[2 * o] = -1;
-        out.ctx[2 * o + 1] = blank;
-        out.lp[o] = -INFINITY;
-        out.len[o] = 2;
-        out.hash[o] = kHashSeed;
-        bp[((size_t)s * T + t) * K + lane] = 0;
-        s_ctx[2 * lane] = -1; s_ctx[2 * lane + 1] = blank;
-      }
-      if (lane == 0) out.nlive[s] = nnew;
-    }
-  }
-  __syncthreads();
-  if (tl != nullptr && tid == 0) atomicMax(reinterpret_cast<long long*>(tl + 6), clock64());
-  // ---- C: the next frame's joiner operand of this stream's K hypotheses -------------------------------------------------------
-  if (!build) return;
-  constexpr int kRowTile = 128, kImgTile = 128 * 128;        // rows per image tile, bytes of one 128 x 64 bf16 tile
-  for (int k = 4 * tid; k < J; k += 512) {
-    const float4 e = k == 4 * tid ? e4 : __ldg(reinterpret_cast<const float4*>(enc_next + (size_t)s * enc_stride + k));
-    const float ex[4] = {expf(2.f * fminf(fmaxf(e.x, -21.f), 21.f)), expf(2.f * fminf(fmaxf(e.y, -21.f), 21.f)),
-                         expf(2.f * fminf(fmaxf(e.z, -21.f), 21.f)), expf(2.f * fminf(fmaxf(e.w, -21.f), 21.f))};
-    float4 d[KB];
-#pragma unroll
-    for (int q = 0; q < KB; ++q)
-      if (q < K)
-        d[q] = __ldg(reinterpret_cast<const float4*>(dec_tab + ((size_t)(s_ctx[2 * q] + 1) * V + s_ctx[2 * q + 1]) * J + k));
-#pragma unroll
-    for (int q = 0; q < KB; ++q) {
-      if (q < K) {
-        const int m = s * K + q;
-        const float dv[4] = {d[q].x, d[q].y, d[q].z, d[q].w};
-        float x[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {       // tanh(e + d) = 1 - 2 / (1 + exp(2e) * exp(2d)); the table holds exp(2d)
-          float r;
-          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(ex[i], dv[i], 1.f)));
-          x[i] = fmaf(-2.f, r, 1.f);
-        }
-        uint8_t* timg = x_img + ((size_t)(m / kRowTile) * (J / 64) + (k >> 6)) * (2 * kImgTile) +
-                        k2b::ptx::sw128_offset(m % kRowTile, k & 63);
-        const float h0 = k2b::ptx::bf16_round(x[0]), h1 = k2b::ptx::bf16_round(x[1]), h2 = k2b::ptx::bf16_round(x[2]),
-                    h3 = k2b::ptx::bf16_round(x[3]);
-        *reinterpret_cast<uint2*>(timg) = make_uint2(k2b::ptx::pack_bf16x2(h0, h1), k2b::ptx::pack_bf16x2(h2, h3));
-        *reinterpret_cast<uint2*>(timg + kImgTile) =
-            make_uint2(k2b::ptx::pack_bf16x2(x[0] - h0, x[1] - h1), k2b::ptx::pack_bf16x2(x[2] - h2, x[3] - h3));
-      }
-    }
-  }
-  if (tl != nullptr && tid == 0) atomicMax(reinterpret_cast<long long*>(tl + 7), clock64());
+  beam_merge_stream<KB>(tid, 1, s, K, V, nt, T, t, blank, unk, part_m, part_s, part_tv, part_ti, in, out, bp, lens, dec_tab, enc_next,
+                        enc_stride, J, x_img, e4, c_v, c_f, s_ctx, tl);
 }
 
 // One warp per stream: pick argmax lp/len (first maximum in slot order), walk the back-pointers in
@@ -777,6 +513,16 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
   static const bool unfused = getenv("K2B_UNFUSED_STEP") != nullptr;
   if (tc && have_tab && ximg != nullptr && !unfused && joiner_topk_usable(h, K) && T > 0) {
     K2B_TRY(joinin_table_tc(h, st[0].ctx, N, enc, (long long)T * J, K, ximg));
+    if (beam_mega_usable(h, K) && h->timeline == nullptr && !h->profile_on) {       // the whole time loop in one launch
+      K2B_TRY(ensure_joiner_assets(h));
+      BeamStatePtrs sp[2];
+      for (int i = 0; i < 2; ++i)
+        sp[i] = BeamStatePtrs{st[i].ctx, st[i].lp, st[i].len, reinterpret_cast<unsigned long long*>(st[i].hash), st[i].nlive};
+      K2B_TRY(beam_mega_tc(h, enc, B, T, K, ximg, part_m, part_s, part_tv, part_ti, sp[0], sp[1], bp,
+                           h->lens_active ? h->lens_dev : nullptr));
+      cur = T & 1;
+      return beam_backtrace_dev(h, B, K, T, st[cur].lp, st[cur].len, st[cur].nlive, bp, tokens, ts, n_out, score, cap);
+    }
     for (int t = 0; t < T; ++t) {
       if (h->prof_which == 0) prof_begin(h);
       K2B_TRY(joiner_tc_partials(h, x, ximg, N, K, part_m, part_s, part_tv, part_ti, nullptr, nullptr, nullptr));

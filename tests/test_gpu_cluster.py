@@ -346,3 +346,36 @@ def test_time_chunk_pipelined_host_call_is_identical(setup):
         assert n_one == 3 and n_pipe == 5 * 2 + 1, (n_pipe, n_one)     # proj + cluster (+ per chunk) + back-trace
     compare_streams(t1, s1, O.modified_beam_search(m, enc, 2), "pipelined vs oracle", allow_frac=0.12)
     h.close()
+
+
+@pytest.mark.parametrize("beam", [2, 4, 8])
+def test_persistent_beam_kernel_large_vocab(built_lib, monkeypatch, beam):
+    """V = 5537, beams 2 / 4 / 8: the whole time loop in one launch (persistent tcgen05 joiner + merge warps chained by global
+    counters) against the oracle, against the per-frame launches (K2B_NO_MEGA=1: identical results required), with more streams
+    than fit one row tile, and with ragged lengths."""
+    dims = synth.CONFIGS["cfg4"].dims
+    m, w = model_and_weights(dims, blank_bias=synth.CONFIGS["cfg4"].blank_bias)
+    h = make(dims, w, "bf16x3")
+    B, T = 70, 24                       # 70 * beam rows: 2 .. 5 row tiles, the last one partly filled
+    raw = synth.make_frames(B, T, dims.encoder_dim, 77 + beam)
+    enc = O.encoder_proj(m, raw)
+    t1, s1, sc1 = h.modified_beam_search(raw, beam, enc_is_raw=True)
+    monkeypatch.setenv("K2B_NO_MEGA", "1")
+    t0, s0, sc0 = h.modified_beam_search(raw, beam, enc_is_raw=True)
+    monkeypatch.delenv("K2B_NO_MEGA")
+    assert t1 == t0 and s1 == s0
+    np.testing.assert_array_equal(np.asarray(sc1), np.asarray(sc0))
+    want = O.modified_beam_search(m, enc[:12], beam)
+    ex = compare_streams(t1[:12], s1[:12], want, f"persistent beam kernel K={beam}", allow_frac=0.25)
+    for b, r in enumerate(want):
+        if b not in ex:
+            assert abs(float(sc1[b]) - r.score) < SCORE_TOL
+    lens = np.array([(7 * b) % (T + 1) for b in range(B)], np.int64)
+    h.set_encoder_out_lens(lens)
+    t2, s2, _ = h.modified_beam_search(raw, beam, enc_is_raw=True)
+    monkeypatch.setenv("K2B_NO_MEGA", "1")
+    h.set_encoder_out_lens(lens)
+    t3, s3, _ = h.modified_beam_search(raw, beam, enc_is_raw=True)
+    assert t2 == t3 and s2 == s3
+    assert all(all(x < lens[b] for x in s2[b]) for b in range(B))
+    h.close()
