@@ -21,6 +21,8 @@
 // the operand kernel; griddepcontrol.wait precedes the first read of x and every write.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "k2b_internal.h"
 #include "sm100_ptx.cuh"
 #include "beam_merge.cuh"
@@ -37,7 +39,7 @@ constexpr int kWTile = kJNc * 128;                          // 20 KB
 constexpr int kStageBytes = 2 * kATile + 2 * kWTile;      // 72 KB
 constexpr int kTS = kJNc + 1;                               // row stride of the fp32 scratch rows (conflict-free across rows)
 constexpr int kTileBytes = kJM * kTS * 4;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                             // epilogue warps per CTA (4: one thread per row; 8: two column halves)
 constexpr int kAccCols = 256;                             // TMEM column distance of the two accumulators
 constexpr int kNoneKey = (int)0x80000000;
 constexpr int kInfKey = (int)0x807fffff;                  // keys of -inf logits (invalid columns) are <= this
@@ -98,8 +100,8 @@ __device__ __forceinline__ void push_key(int (&a)[KK], int t) {
   }
 }
 
-template <int KK, bool MEGA>
-__global__ void __launch_bounds__(MEGA ? kThreads + 128 : kThreads, 1) joiner_topk_kernel(const JArgs a) {
+template <int KK, bool MEGA, int EW>
+__global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_topk_kernel(const JArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full[kStages], empty[kStages], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(MEGA ? kThreads + 128 : kThreads, 1) joiner_to
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EW); }
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
@@ -129,7 +131,8 @@ __global__ void __launch_bounds__(MEGA ? kThreads + 128 : kThreads, 1) joiner_to
   bool ok = true;
   if (!MEGA) griddep_launch_dependents();
   long long* tl = nullptr;
-  if (a.tl != nullptr) {
+  long long* tlm = (MEGA && a.tl != nullptr && blockIdx.x == 0) ? a.tl : nullptr;   // MEGA: CTA 0 stamps [frame][16] for 40 frames
+  if (!MEGA && a.tl != nullptr) {
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     tl = a.tl + (size_t)smid * 8;
@@ -150,6 +153,7 @@ __global__ void __launch_bounds__(MEGA ? kThreads + 128 : kThreads, 1) joiner_to
             if (!wait_count(a.ready + (size_t)t * a.ntm + tile_m, need, a.abort_flag)) { ok = false; break; }
             asm volatile("fence.proxy.async;" ::: "memory");
           }
+          if (tlm != nullptr && t < 40) tlm[t * 16 + (tile == blockIdx.x ? 0 : 3)] = clock64();
           for (int kb = 0; kb < nkb; ++kb, ++kc) {
             const int s = kc % kStages;
             const uint32_t ph = (kc / kStages) & 1u;
@@ -207,9 +211,12 @@ __global__ void __launch_bounds__(MEGA ? kThreads + 128 : kThreads, 1) joiner_to
       }
       umma_commit_e(&acc_full[as], el);
     }
-  } else if (warp_u < 6) {
-    // ---- epilogue: thread = logits row ------------------------------------------------------------------------------------
+  } else if (warp_u < 2 + EW) {
+    // ---- epilogue: thread = logits row (EW = 4) or one 80-column half of it (EW = 8) ------------------------------------------
     const int lg = warp & 3;                              // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;                     // column half of this warp (always 0 when EW = 4)
+    constexpr int kCols = kJNc * 4 / EW;                  // columns per thread: 160 or 80
+    const int cbeg = half * kCols;
     const int row = lg * 32 + lane;
     const int etid = tid - 64;
     float* myrow = reinterpret_cast<float*>(smem + (size_t)kStages * kStageBytes) + (size_t)row * kTS;
@@ -225,24 +232,23 @@ __global__ void __launch_bounds__(MEGA ? kThreads + 128 : kThreads, 1) joiner_to
       const int as = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
       const int col0 = tile_n * kJNc;
-      named_bar_sync(1, 128);                             // every row is done with the previous tile's bias
-      for (int c = etid; c < kJNc; c += 128) bias_t[c] = col0 + c < a.nvalid ? __ldg(a.bias + col0 + c) : -INFINITY;
-      named_bar_sync(1, 128);
+      named_bar_sync(1, EW * 32);                         // every row is done with the previous tile's bias (and scratch records)
+      for (int c = etid; c < kJNc; c += EW * 32) bias_t[c] = col0 + c < a.nvalid ? __ldg(a.bias + col0 + c) : -INFINITY;
+      named_bar_sync(1, EW * 32);
       if (!mbar_wait(&acc_full[as], aph)) ok = false;
       if (dbg && it == 0) c_acc = clock64();
       if (tl != nullptr && tid == 64 && it == 0) tl[2] = clock64();
+      if (tlm != nullptr && tid == 64 && t < 40) tlm[t * 16 + (tile == blockIdx.x ? 1 : 4)] = clock64();
       tc_fence_after();
       const uint32_t trow = t_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * kAccCols);
       int key[KK];
 #pragma unroll
       for (int i = 0; i < KK; ++i) key[i] = kNoneKey;
-#pragma unroll 1
-      for (int c0 = 0; c0 < kJNc; c0 += 32) {
-        uint32_t u[32];
-        tmem_ld32(trow + (uint32_t)c0, u);
-        tmem_ld_wait();
+      // pass 1 over a chunk of NC accumulator columns starting at c0: + bias, scratch copy, key network
+      auto chunk = [&](const uint32_t* u, int c0, auto nc_tag) {
+        constexpr int NC = decltype(nc_tag)::value;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < NC / 4; ++q) {
           const float4 bb = *reinterpret_cast<const float4*>(bias_t + c0 + 4 * q);
           const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
@@ -255,19 +261,34 @@ __global__ void __launch_bounds__(MEGA ? kThreads + 128 : kThreads, 1) joiner_to
             push_key<KK>(key, (ok_key & ~255) | (c0 + j));
           }
         }
+      };
+#pragma unroll 1
+      for (int c0 = cbeg; c0 + 32 <= cbeg + kCols; c0 += 32) {
+        uint32_t u[32];
+        tmem_ld32(trow + (uint32_t)c0, u);
+        tmem_ld_wait();
+        chunk(u, c0, std::integral_constant<int, 32>{});
       }
+      if constexpr (kCols % 32 != 0) {                    // 80 = 2 x 32 + 16
+        uint32_t u[16];
+        const int c0 = cbeg + kCols - 16;
+        tmem_ld16(trow + (uint32_t)c0, u);
+        tmem_ld_wait();
+        chunk(u, c0, std::integral_constant<int, 16>{});
+      }
+      if (tlm != nullptr && tid == 64 && t < 40 && tile == blockIdx.x) tlm[t * 16 + 10] = clock64();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);         // the accumulator may be overwritten by tile it + 2
       __syncwarp();
       // pass 2: sum of exponentials against the (key-precision) maximum, then the winners' exact logits
-      const bool any = key[0] > kInfKey;
+      bool any = key[0] > kInfKey;
       const int mk = key[0] & ~255;
-      const float mx = any ? __int_as_float(mk ^ ((mk >> 31) & 0x7fffffff)) : -INFINITY;
+      float mx = any ? __int_as_float(mk ^ ((mk >> 31) & 0x7fffffff)) : -INFINITY;
       const float mneg = any ? -mx * 1.4426950408889634f : 0.f;
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll 8
-      for (int j = 0; j < kJNc; j += 4) {
+      for (int j = cbeg; j < cbeg + kCols; j += 4) {
         float e0, e1, e2, e3;
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(myrow[j], 1.4426950408889634f, mneg)));
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(myrow[j + 1], 1.4426950408889634f, mneg)));
@@ -275,26 +296,68 @@ __global__ void __launch_bounds__(MEGA ? kThreads + 128 : kThreads, 1) joiner_to
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(fmaf(myrow[j + 3], 1.4426950408889634f, mneg)));
         s0 += e0; s1 += e1; s2 += e2; s3 += e3;
       }
+      float sum = any ? (s0 + s1) + (s2 + s3) : 0.f;
+      if (tlm != nullptr && tid == 64 && t < 40 && tile == blockIdx.x) tlm[t * 16 + 11] = clock64();
+      float tv[KK];
+#pragma unroll
+      for (int i = 0; i < KK; ++i) tv[i] = key[i] > kInfKey ? myrow[key[i] & 255] : -INFINITY;
+      if constexpr (EW == 8) {
+        // the upper column half leaves (keys, exact logits, max, sum) at the start of its own scratch segment; the lower half folds
+        // them into its own: key network again, the logits follow their keys by equality (keys are unique)
+        int* rec = reinterpret_cast<int*>(myrow + kCols);
+        if (half == 1) {
+#pragma unroll
+          for (int i = 0; i < KK; ++i) { rec[i] = key[i]; rec[KK + i] = __float_as_int(tv[i]); }
+          rec[2 * KK] = __float_as_int(mx);
+          rec[2 * KK + 1] = __float_as_int(sum);
+        }
+        named_bar_sync(4 + lg, 64);
+        if (half == 0) {
+          int ka[KK], kb2[KK];
+          float ta[KK], tb[KK];
+#pragma unroll
+          for (int i = 0; i < KK; ++i) { ka[i] = key[i]; ta[i] = tv[i]; kb2[i] = rec[i]; tb[i] = __int_as_float(rec[KK + i]); }
+          const float mb = __int_as_float(rec[2 * KK]), sb = __int_as_float(rec[2 * KK + 1]);
+#pragma unroll
+          for (int i = 0; i < KK; ++i) push_key<KK>(key, kb2[i]);
+#pragma unroll
+          for (int i = 0; i < KK; ++i) {
+            float v = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < KK; ++j) { v = key[i] == ka[j] ? ta[j] : v; v = key[i] == kb2[j] ? tb[j] : v; }
+            tv[i] = key[i] > kInfKey ? v : -INFINITY;
+          }
+          const float mm = fmaxf(mx, mb);
+          float ea = 0.f, eb = 0.f;
+          if (mm > -INFINITY) {
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"((mx - mm) * 1.4426950408889634f));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"((mb - mm) * 1.4426950408889634f));
+          }
+          sum = (mx > -INFINITY ? sum * ea : 0.f) + (mb > -INFINITY ? sb * eb : 0.f);
+          mx = mm;
+          any = mm > -INFINITY;
+        }
+      }
       const int m = tile_m * kJM + row;
-      if (m < a.M) {
+      if (m < a.M && half == 0) {
         const size_t po = (size_t)m * a.ntn + tile_n;
         a.part_m[po] = mx;
-        a.part_s[po] = any ? (s0 + s1) + (s2 + s3) : 0.f;
+        a.part_s[po] = any ? sum : 0.f;
 #pragma unroll
         for (int i = 0; i < KK; ++i) {
           if (i < K) {
             const bool has = key[i] > kInfKey;
-            const int pos = key[i] & 255;
-            a.part_tv[po * K + i] = has ? myrow[pos] : -INFINITY;
-            a.part_ti[po * K + i] = has ? col0 + pos : -1;
+            a.part_tv[po * K + i] = has ? tv[i] : -INFINITY;
+            a.part_ti[po * K + i] = has ? col0 + (key[i] & 255) : -1;
           }
         }
       }
       if (dbg && it == 0) c_epi = clock64();
+      if (tlm != nullptr && tid == 64 && t < 40 && tile == blockIdx.x) tlm[t * 16 + 12] = clock64();
       if (MEGA) {                                         // publish: one more column tile of (frame, row tile) is reduced
-        __threadfence();
-        named_bar_sync(3, 128);
+        named_bar_sync(3, EW * 32);                       // (CTA barrier, then one gpu-scope release: cumulative over the CTA's stores)
         if (etid == 0) red_release_gpu(a.done + (size_t)t * a.ntm + tile_m, 1);
+        if (tlm != nullptr && tid == 64 && t < 40) tlm[t * 16 + (tile == blockIdx.x ? 2 : 5)] = clock64();
       }
     }
     if (tl != nullptr && tid == 64) tl[3] = clock64();
@@ -308,7 +371,7 @@ __global__ void __launch_bounds__(MEGA ? kThreads + 128 : kThreads, 1) joiner_to
   }
   else if (MEGA) {
     // ---- merge warps: hypothesis merge + next operand of this CTA's streams, frame by frame -------------------------------------
-    const int mtid = tid - kThreads;
+    const int mtid = tid - (64 + EW * 32);
     for (int t = 0; t < nframes && ok; ++t) {
       const float* enc_next = t + 1 < a.T ? a.enc + (size_t)(t + 1) * a.J : nullptr;
       for (int s = blockIdx.x; s < a.B && ok; s += gridDim.x) {
@@ -322,6 +385,7 @@ __global__ void __launch_bounds__(MEGA ? kThreads + 128 : kThreads, 1) joiner_to
         good = mg_ctx[0];
         named_bar_sync(2, 128);                           // mg_ctx is rewritten by the merge step
         if (!good) { ok = false; break; }
+        if (tlm != nullptr && mtid == 0 && t < 40) tlm[t * 16 + (s == blockIdx.x ? 6 : 8)] = clock64();
         const bool odd = (t & 1) != 0;
         BeamState sin, sout;
         sin.ctx = odd ? a.st[1].ctx : a.st[0].ctx; sout.ctx = odd ? a.st[0].ctx : a.st[1].ctx;
@@ -331,13 +395,13 @@ __global__ void __launch_bounds__(MEGA ? kThreads + 128 : kThreads, 1) joiner_to
         sin.nlive = odd ? a.st[1].nlive : a.st[0].nlive; sout.nlive = odd ? a.st[0].nlive : a.st[1].nlive;
         beam_merge_stream<KK>(mtid, 2, s, a.topk, a.V, a.ntn, a.T, t, a.blank, a.unk, a.part_m, a.part_s, a.part_tv, a.part_ti,
                               sin, sout, a.bp, a.lens, a.dec_tab, enc_next, a.enc_stride, a.J, a.x_img, e4,
-                              mg_v, mg_f, mg_ctx, nullptr);
+                              mg_v, mg_f, mg_ctx, (tlm != nullptr && t < 40 && s == blockIdx.x) ? tlm + t * 16 + 8 : nullptr);
         if (t + 1 < a.T) {                                // publish: one more stream of (frame t + 1, row tile) has its operand rows
-          __threadfence();
-          asm volatile("fence.proxy.async;" ::: "memory");
+          asm volatile("fence.proxy.async;" ::: "memory");       // the rows are read through the async proxy (TMA)
           named_bar_sync(2, 128);
           if (mtid == 0) red_release_gpu(a.ready + (size_t)(t + 1) * a.ntm + r, 1);
         }
+        if (tlm != nullptr && mtid == 0 && t < 40) tlm[t * 16 + (s == blockIdx.x ? 7 : 9)] = clock64();
       }
     }
   }
@@ -352,7 +416,7 @@ int32_t launch_as(k2b_handle* h, const JArgs& a) {
   static bool attr_set = false;
   const size_t smem = (size_t)kStages * kStageBytes + kTileBytes;
   if (!attr_set) {
-    K2B_CUDA(h, (cudaFuncSetAttribute(joiner_topk_kernel<KK, MEGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+    K2B_CUDA(h, (cudaFuncSetAttribute(joiner_topk_kernel<KK, MEGA, kEpiWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
     attr_set = true;
   }
   const int tiles = a.ntm * a.ntn;
@@ -360,14 +424,14 @@ int32_t launch_as(k2b_handle* h, const JArgs& a) {
   if (MEGA) {
     // every CTA waits for counters other CTAs publish: all of them must be resident at once (cooperative launch checks that)
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads + 128); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + kEpiWarps * 32 + 128); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeCooperative;
     at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    K2B_CUDA(h, cudaLaunchKernelEx(&cfg, joiner_topk_kernel<KK, MEGA>, a));
+    K2B_CUDA(h, (cudaLaunchKernelEx(&cfg, joiner_topk_kernel<KK, MEGA, kEpiWarps>, a)));
   } else {
-    K2B_CUDA(h, launch_pdl(joiner_topk_kernel<KK, MEGA>, dim3(grid), dim3(kThreads), smem, h->stream, a));
+    K2B_CUDA(h, (launch_pdl(joiner_topk_kernel<KK, MEGA, kEpiWarps>, dim3(grid), dim3(64 + kEpiWarps * 32), smem, h->stream, a)));
   }
   K2B_LAUNCH_CHECK(h);
   return K2B_OK;
@@ -427,6 +491,7 @@ int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8
   a.done = static_cast<int*>(h->ws_sync.p);
   a.ready = a.done + (size_t)T * a.ntm;
   a.abort_flag = a.ready + (size_t)(T + 1) * a.ntm;
+  a.tl = h->timeline;
   return K <= 4 ? launch_as<4, true>(h, a) : launch_as<8, true>(h, a);
 }
 

@@ -513,7 +513,7 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
   static const bool unfused = getenv("K2B_UNFUSED_STEP") != nullptr;
   if (tc && have_tab && ximg != nullptr && !unfused && joiner_topk_usable(h, K) && T > 0) {
     K2B_TRY(joinin_table_tc(h, st[0].ctx, N, enc, (long long)T * J, K, ximg));
-    if (beam_mega_usable(h, K) && h->timeline == nullptr && !h->profile_on) {       // the whole time loop in one launch
+    if (beam_mega_usable(h, K) && !h->profile_on) {       // the whole time loop in one launch
       K2B_TRY(ensure_joiner_assets(h));
       BeamStatePtrs sp[2];
       for (int i = 0; i < 2; ++i)
