@@ -85,7 +85,8 @@ __device__ __forceinline__ void beam_merge_stream(
   } else {
     // ---- A: per live hypothesis --------------------------------------------------------------------------------------------
 #pragma unroll 1
-    for (int h = warp; h < nl; h += 4) {
+    for (int h = warp; h < K; h += 4) {        // the loads of row h are issued before the live count has arrived (dead rows are
+                                               // valid memory: the joiner reduced them like any other row)
       const size_t row = (size_t)s * K + h;
       const float* pmr = part_m + row * nt;
       const float* psr = part_s + row * nt;
@@ -106,6 +107,7 @@ __device__ __forceinline__ void beam_merge_stream(
         cval[u] = c < ncand ? __ldcg(part_tv + cbase + c) : 0.f;
       }
       const float lp = __ldcg(in.lp + row);
+      if (h >= nl) continue;
       int mk = max(fkey_s(pm[0]), fkey_s(pm[1]));           // absent tiles read as -inf
 #pragma unroll 1
       for (int i = lane + 32 * kPairs; i < nt; i += 32) mk = max(mk, fkey_s(__ldcg(pmr + i)));

@@ -80,11 +80,11 @@ __device__ __forceinline__ void red_release_gpu(int* p, int v) {
 __device__ __forceinline__ bool wait_count(const int* p, int need, int* abort_flag) {
   if (ld_acquire_gpu(p) >= need) return true;
   const long long t0 = clock64();
+  int spins = 0;
 #pragma unroll 1
   while (clock64() - t0 < kWaitTimeoutCycles) {
     if (ld_acquire_gpu(p) >= need) return true;
-    if (ld_acquire_gpu(abort_flag) != 0) return false;
-    __nanosleep(32);
+    if (((++spins) & 63) == 0 && ld_acquire_gpu(abort_flag) != 0) return false;
   }
   atomicExch(abort_flag, 1);
   return false;
@@ -148,21 +148,37 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
       for (int t = 0; t < nframes && ok; ++t) {
         for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
           const int tile_m = tile / a.ntn, tile_n = tile - tile_m * a.ntn;      // row-major: a row tile completes early
+          bool w_ahead = false;
           if (MEGA && t > 0) {       // the operand rows of this row tile are the merge step's output of frame t - 1
             const int need = min(spr, a.B - tile_m * spr);
-            if (!wait_count(a.ready + (size_t)t * a.ntm + tile_m, need, a.abort_flag)) { ok = false; break; }
+            const int* cnt = a.ready + (size_t)t * a.ntm + tile_m;
+            if (ld_acquire_gpu(cnt) < need) {
+              // not there yet: the weight half of the first k-block does not depend on it - fetch it while waiting
+              const int s = kc % kStages;
+              const uint32_t ph = (kc / kStages) & 1u;
+              if (!mbar_wait(&empty[s], ph ^ 1u)) ok = false;
+              uint8_t* st = smem + (size_t)s * kStageBytes;
+              const size_t off = ((size_t)tile_n * nkb) * kWTile;
+              mbar_expect_tx(&full[s], w_bytes + a_bytes);
+              tma_bulk_g2s(st + 2 * kATile, a.w_hi_img + off, kWTile, &full[s]);
+              if (x3) tma_bulk_g2s(st + 2 * kATile + kWTile, a.w_lo_img + off, kWTile, &full[s]);
+              w_ahead = true;
+              if (!wait_count(cnt, need, a.abort_flag)) { ok = false; break; }
+            }
             asm volatile("fence.proxy.async;" ::: "memory");
           }
           if (tlm != nullptr && t < 40) tlm[t * 16 + (tile == blockIdx.x ? 0 : 3)] = clock64();
           for (int kb = 0; kb < nkb; ++kb, ++kc) {
             const int s = kc % kStages;
             const uint32_t ph = (kc / kStages) & 1u;
-            if (!mbar_wait(&empty[s], ph ^ 1u)) ok = false;
             uint8_t* st = smem + (size_t)s * kStageBytes;
-            const size_t off = ((size_t)tile_n * nkb + kb) * kWTile;
-            mbar_expect_tx(&full[s], w_bytes + a_bytes);
-            tma_bulk_g2s(st + 2 * kATile, a.w_hi_img + off, kWTile, &full[s]);
-            if (x3) tma_bulk_g2s(st + 2 * kATile + kWTile, a.w_lo_img + off, kWTile, &full[s]);
+            if (!(w_ahead && kb == 0)) {
+              if (!mbar_wait(&empty[s], ph ^ 1u)) ok = false;
+              const size_t off = ((size_t)tile_n * nkb + kb) * kWTile;
+              mbar_expect_tx(&full[s], w_bytes + a_bytes);
+              tma_bulk_g2s(st + 2 * kATile, a.w_hi_img + off, kWTile, &full[s]);
+              if (x3) tma_bulk_g2s(st + 2 * kATile + kWTile, a.w_lo_img + off, kWTile, &full[s]);
+            }
             if (!waited) { griddep_wait(); waited = true; }      // x is the previous kernel's output; the weights are not
             tma_bulk_g2s(st, a.a_img + ((size_t)tile_m * nkb + kb) * (2 * kATile), a_bytes, &full[s]);
           }
