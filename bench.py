@@ -37,6 +37,7 @@ sys.path.insert(0, str(ROOT))
 
 from k2transducerasr_b200 import synth  # noqa: E402
 
+CFG4_TRAFFIC = 342.3e6   # dram__bytes_read.sum + dram__bytes_write.sum of one whole-loop launch on cfg4 (337.1 MB + 5.2 MB)
 METRIC = "encoder frames/sec decoded (modified_beam_search beam=4, batch 256/GPU)"
 UNIT = "frames/s"
 
@@ -273,10 +274,12 @@ def run_ours(args, cfg):
     achieved_tf = flops_per_launch / (avg_ms * 1e-3) / 1e12 if n_l else 0.0
     # dram__bytes_read.sum + dram__bytes_write.sum of one cluster_beam_kernel launch on this workload, from the
     # ncu --set full capture profiles/r01_cluster_beam_v8_full.ncu-rep (240.5 MB + 6.8 MB); none taken for the fp32 path
-    traffic = 247.2e6 if (fused_loop and args.workload == "cfg2") else None
+    # cfg4 (persistent joiner_topk_kernel, whole time loop): profiles/r01_beam_mega_cfg4_T250_full.ncu-rep
+    traffic = {"cfg2": 247.2e6, "cfg4": CFG4_TRAFFIC}.get(args.workload) if fused_loop else None
+    kernel_name = ("cluster_beam_kernel: whole time loop (joiner tcgen05 GEMM + log-softmax/top-k + merge)" if args.workload == "cfg2"
+                   else "joiner_topk_kernel<MEGA>: whole time loop (persistent tcgen05 joiner with top-k epilogue + merge warps)")
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved_tf / peaks["tf_sustained"], "traffic": traffic, "kernel": ("cluster_beam_kernel: whole time loop (joiner tcgen05 GEMM + log-softmax/top-k + merge)" if fused_loop
-                           else "joiner GEMM (+log-softmax/top-k epilogue), one launch per frame"),
+                "frac": achieved_tf / peaks["tf_sustained"], "traffic": traffic, "kernel": (kernel_name if fused_loop else "joiner GEMM (+log-softmax/top-k epilogue), one launch per frame"),
                 "avg_launch_us": avg_ms * 1e3, "launches_timed": n_l, "flop_per_launch": flops_per_launch,
                 "peak_source": peaks["src"] + ", sustained bf16",
                 "frame_step_roofline_us": 2.0 * (B * K) * J * V / (peaks["tf_sustained"] * 1e12) * 1e6,
@@ -294,7 +297,7 @@ def run_ours(args, cfg):
                 "data": "synthetic",
                 "config": {"workload": cfg.name, "streams_per_gpu": B, "frames": T, "beam": K, "vocab": V, "joiner_dim": J,
                            "encoder_dim": E, "precision": args.precision, "parallelism": f"dp{world} (independent batches)",
-                           "l2": "inputs (196 MB/step, 2 alternating batches) larger than the 126 MB L2",
+                           "l2": f"inputs ({B * T * E * 4 / 1e6:.0f} MB/step, 2 alternating batches) larger than the 126 MB L2",
                            "blank_bias": cfg.blank_bias, "weights": "random-init, seed 7"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},

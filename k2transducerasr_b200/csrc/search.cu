@@ -513,13 +513,15 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
   static const bool unfused = getenv("K2B_UNFUSED_STEP") != nullptr;
   if (tc && have_tab && ximg != nullptr && !unfused && joiner_topk_usable(h, K) && T > 0) {
     K2B_TRY(joinin_table_tc(h, st[0].ctx, N, enc, (long long)T * J, K, ximg));
-    if (beam_mega_usable(h, K) && !h->profile_on) {       // the whole time loop in one launch
+    if (beam_mega_usable(h, K) && !(h->profile_on && h->prof_which != 0)) {       // the whole time loop in one launch
       K2B_TRY(ensure_joiner_assets(h));
       BeamStatePtrs sp[2];
       for (int i = 0; i < 2; ++i)
         sp[i] = BeamStatePtrs{st[i].ctx, st[i].lp, st[i].len, reinterpret_cast<unsigned long long*>(st[i].hash), st[i].nlive};
+      prof_begin(h);
       K2B_TRY(beam_mega_tc(h, enc, B, T, K, ximg, part_m, part_s, part_tv, part_ti, sp[0], sp[1], bp,
                            h->lens_active ? h->lens_dev : nullptr));
+      prof_end(h);
       cur = T & 1;
       return beam_backtrace_dev(h, B, K, T, st[cur].lp, st[cur].len, st[cur].nlive, bp, tokens, ts, n_out, score, cap);
     }
