@@ -445,7 +445,12 @@ int32_t launch_as(k2b_handle* h, const JArgs& a) {
     at[0].id = cudaLaunchAttributeCooperative;
     at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    K2B_CUDA(h, (cudaLaunchKernelEx(&cfg, joiner_topk_kernel<KK, MEGA, kEpiWarps>, a)));
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, joiner_topk_kernel<KK, MEGA, kEpiWarps>, a);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) {
+      cudaGetLastError();                 // not all CTAs can be resident (SMs taken by another context): per-frame launches instead
+      return kMegaUnavailable;
+    }
+    K2B_CUDA(h, e);
   } else {
     K2B_CUDA(h, (launch_pdl(joiner_topk_kernel<KK, MEGA, kEpiWarps>, dim3(grid), dim3(64 + kEpiWarps * 32), smem, h->stream, a)));
   }

@@ -241,6 +241,7 @@ int32_t joiner_topk_tc(k2b_handle* h, const uint8_t* x_img, int M, int topk, flo
                        int32_t* part_ti);
 
 struct BeamStatePtrs { int32_t* ctx; float* lp; int32_t* len; unsigned long long* hash; int32_t* nlive; };
+constexpr int32_t kMegaUnavailable = 0x4d454741;   // beam_mega_tc: the cooperative launch does not fit; nothing was enqueued
 bool beam_mega_usable(const k2b_handle* h, int K);
 int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8_t* x_img, float* part_m, float* part_s, float* part_tv,
                      int32_t* part_ti, const BeamStatePtrs& s0, const BeamStatePtrs& s1, int32_t* bp, const int32_t* lens);

@@ -519,11 +519,14 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
       for (int i = 0; i < 2; ++i)
         sp[i] = BeamStatePtrs{st[i].ctx, st[i].lp, st[i].len, reinterpret_cast<unsigned long long*>(st[i].hash), st[i].nlive};
       prof_begin(h);
-      K2B_TRY(beam_mega_tc(h, enc, B, T, K, ximg, part_m, part_s, part_tv, part_ti, sp[0], sp[1], bp,
-                           h->lens_active ? h->lens_dev : nullptr));
+      const int32_t ms = beam_mega_tc(h, enc, B, T, K, ximg, part_m, part_s, part_tv, part_ti, sp[0], sp[1], bp,
+                                      h->lens_active ? h->lens_dev : nullptr);
       prof_end(h);
-      cur = T & 1;
-      return beam_backtrace_dev(h, B, K, T, st[cur].lp, st[cur].len, st[cur].nlive, bp, tokens, ts, n_out, score, cap);
+      if (ms != kMegaUnavailable) {
+        K2B_TRY(ms);
+        cur = T & 1;
+        return beam_backtrace_dev(h, B, K, T, st[cur].lp, st[cur].len, st[cur].nlive, bp, tokens, ts, n_out, score, cap);
+      }
     }
     for (int t = 0; t < T; ++t) {
       if (h->prof_which == 0) prof_begin(h);

@@ -379,3 +379,27 @@ def test_persistent_beam_kernel_large_vocab(built_lib, monkeypatch, beam):
     assert t2 == t3 and s2 == s3
     assert all(all(x < lens[b] for x in s2[b]) for b in range(B))
     h.close()
+
+
+@pytest.mark.parametrize("V,J,D,B,T,beam", [
+    (1030, 64, 32, 1, 1, 4),          # just above the cluster kernel's vocabulary limit; one stream, one frame
+    (1030, 128, 64, 33, 9, 2),        # two k-blocks; 66 rows: one partly filled row tile
+    (2500, 64, 48, 70, 7, 8),         # beam 8: 560 rows = 4.4 row tiles, 16 column tiles
+    (10300, 64, 32, 5, 6, 4),         # 65 column tiles: more (max, sum) pairs and candidates than a lane keeps in registers
+])
+def test_persistent_beam_kernel_shapes(built_lib, V, J, D, B, T, beam):
+    """Shapes that stress the indexing of the persistent beam kernel and of the merge step (tile counts around the register
+    batches, partly filled row tiles, single stream / single frame), against the oracle."""
+    dims = synth.ModelDims(vocab_size=V, joiner_dim=J, decoder_dim=D, encoder_dim=64)
+    m, w = model_and_weights(dims, blank_bias=0.5)
+    h = make(dims, w, "bf16x3")
+    raw = synth.make_frames(B, T, dims.encoder_dim, 5000 + V)
+    enc = O.encoder_proj(m, raw)
+    t, s, sc = h.modified_beam_search(raw, beam, enc_is_raw=True)
+    nb = min(B, 10)
+    want = O.modified_beam_search(m, enc[:nb], beam)
+    ex = compare_streams(t[:nb], s[:nb], want, f"persistent beam kernel V={V} K={beam}", allow_frac=0.3)
+    for b, r in enumerate(want):
+        if b not in ex:
+            assert abs(float(sc[b]) - r.score) < SCORE_TOL
+    h.close()
