@@ -298,7 +298,7 @@ def run_ours(args, cfg):
                 "config": {"workload": cfg.name, "streams_per_gpu": B, "frames": T, "beam": K, "vocab": V, "joiner_dim": J,
                            "encoder_dim": E, "precision": args.precision, "parallelism": f"dp{world} (independent batches)",
                            "l2": f"inputs ({B * T * E * 4 / 1e6:.0f} MB/step, 2 alternating batches) larger than the 126 MB L2",
-                           "blank_bias": cfg.blank_bias, "weights": "random-init, seed 7"},
+                           "blank_bias": cfg.blank_bias, "regime": args.regime, "weights": "random-init, seed 7"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
                 "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline}
@@ -321,8 +321,14 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])
     ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--regime", default="speech", choices=["speech", "raw"],
+                    help="speech: blank bias calibrated so that 70-80 %% of the frames are blank (default); raw: random-init joiner as is, "
+                         "almost every frame emits (worst case for the decoder gather)")
     args = ap.parse_args()
     cfg = synth.CONFIGS[args.workload]
+    if args.regime == "raw":
+        import dataclasses
+        cfg = dataclasses.replace(cfg, blank_bias=0.0)
     if args.impl == "reference":
         run_reference_arm(args, cfg)
     else:

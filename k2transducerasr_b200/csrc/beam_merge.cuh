@@ -123,6 +123,7 @@ __device__ __forceinline__ void beam_merge_stream(
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(full, sum, o);
       const float ls = __logf(sum);
+      if (tl != nullptr && tid == 0) tl[0] = clock64();   // diagnostic stamp
       // this lane's candidates as (key, flat index); same operation order as log_softmax(x) + lp : ((x - max) - log(sum)) + lp
       int ck[kCands], cf[kCands];
 #pragma unroll
@@ -154,6 +155,7 @@ __device__ __forceinline__ void beam_merge_stream(
           done |= hit;
         }
       }
+      if (tl != nullptr && tid == 0) tl[1] = clock64();   // diagnostic stamp
       // K rounds of warp arg-best over all registers: REDUX on the key, then on the flat index among the ties
 #pragma unroll
       for (int r = 0; r < KB; ++r) {
@@ -174,6 +176,7 @@ __device__ __forceinline__ void beam_merge_stream(
     }
     k2b::ptx::named_bar_sync(bar_id, 128);
     // ---- B: the stream's top K, extension, merge ---------------------------------------------------------------------------
+    if (tl != nullptr && tid == 0) tl[2] = clock64();   // diagnostic stamp: phase A done (barrier passed)
     if (warp == 0) {
       int tk[2], tf[2];
 #pragma unroll
@@ -195,6 +198,7 @@ __device__ __forceinline__ void beam_merge_stream(
           if (lane == r) { my_v = wf >= 0 ? funkey_s(wk) : -INFINITY; my_f = wf; }
         }
       }
+      if (tl != nullptr && tid == 0) tl[3] = clock64();   // diagnostic stamp
       // lane r < K: the r-th extension in rank order
       const bool cand = lane < K && my_f >= 0;
       const int par = cand ? my_f / V : 0;
@@ -213,6 +217,7 @@ __device__ __forceinline__ void beam_merge_stream(
           c1 = y;
         }
       }
+      if (tl != nullptr && tid == 0) tl[4] = clock64();   // diagnostic stamp
       // dedupe: first earlier lane holding the same token sequence; log-add the merged scores into their root in rank order
       int root = lane;
       float lp = my_v;
@@ -234,6 +239,7 @@ __device__ __forceinline__ void beam_merge_stream(
         const int qc = __shfl_sync(full, (int)cand, q);
         if (cand && qc && q != lane && qroot == lane) lp = logaddexp_f(lp, qv);
       }
+      if (tl != nullptr && tid == 0) tl[5] = clock64();   // diagnostic stamp
       const bool is_root = cand && root == lane;
       const unsigned roots = __ballot_sync(full, is_root);
       const int nnew = __popc(roots);

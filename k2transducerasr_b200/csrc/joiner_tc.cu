@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
         sin.nlive = odd ? a.st[1].nlive : a.st[0].nlive; sout.nlive = odd ? a.st[0].nlive : a.st[1].nlive;
         beam_merge_stream<KK>(mtid, 2, s, a.topk, a.V, a.ntn, a.T, t, a.blank, a.unk, a.part_m, a.part_s, a.part_tv, a.part_ti,
                               sin, sout, a.bp, a.lens, a.dec_tab, enc_next, a.enc_stride, a.J, a.x_img, e4,
-                              mg_v, mg_f, mg_ctx, (tlm != nullptr && t < 40 && s == blockIdx.x) ? tlm + t * 16 + 8 : nullptr);
+                              mg_v, mg_f, mg_ctx, (tlm != nullptr && t < 40 && s == blockIdx.x) ? tlm + 640 + t * 8 : nullptr);
         if (t + 1 < a.T) {                                // publish: one more stream of (frame t + 1, row tile) has its operand rows
           asm volatile("fence.proxy.async;" ::: "memory");       // the rows are read through the async proxy (TMA)
           named_bar_sync(2, 128);

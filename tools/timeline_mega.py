@@ -17,7 +17,9 @@ raw = synth.make_frames(cfg.streams, T, d.encoder_dim, cfg.seed)
 h.modified_beam_search(raw, 4, enc_is_raw=True)
 h.debug_timeline()
 h.modified_beam_search(raw, 4, enc_is_raw=True)
-tl = h.debug_timeline().reshape(-1)[:T * 16].reshape(T, 16)
+raw_tl = h.debug_timeline().reshape(-1)
+tl = raw_tl[:T * 16].reshape(T, 16)
+mg = raw_tl[640:640 + T * 8].reshape(T, 8)
 names = ["ldA", "accA", "epiA", "ldB", "accB", "epiB", "m1go", "m1end", "m2go", "m2end", "A:pass1", "A:pass2", "A:comb", "-", "m1:B", "m1:C"]
 print("frame  period " + " ".join(f"{n:>7s}" for n in names))
 for t in range(8, 16):
@@ -25,3 +27,7 @@ for t in range(8, 16):
     print(f"{t:5d} {tl[t + 1, 1] - tl[t, 1]:7d} " + " ".join(f"{tl[t, i] - base:7d}" for i in range(len(names))))
 per = np.diff(tl[5:T - 1, 1])
 print("median frame period (cycles):", np.median(per))
+
+print("merge of the first stream, cycles after its go: lse, cands, A done, B rounds, extension, dedupe+logadd, B done(6), C done(7)")
+for t in range(8, 16):
+    print(f"{t:5d} " + " ".join(f"{mg[t, i] - tl[t, 6]:7d}" for i in range(8)))
