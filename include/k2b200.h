@@ -229,6 +229,12 @@ K2B_API int32_t k2b_selftest_cluster(k2b_handle* h, int32_t csize, int32_t nclus
  * call switches the collection on.                                                                    */
 K2B_API int32_t k2b_cluster_phase_cycles(k2b_handle* h, int64_t* out12);
 
+/* Diagnostic clock64 timeline of the large-vocabulary beam search (joiner_tc.cu). The first call allocates the buffer and
+ * switches the collection on; later calls copy out [64][148][8] int64 stamps and re-arm. Persistent kernel: CTA 0 writes
+ * [frame][16] role stamps for the first 40 frames and [frame][8] merge-step stamps from element 640 on
+ * (tools/timeline_mega.py); per-frame launches: [frame][sm][8] (tools/timeline_cfg4.py).                       */
+K2B_API int32_t k2b_debug_timeline(k2b_handle* h, int64_t* out);
+
 #ifdef __cplusplus
 }
 #endif
