@@ -32,6 +32,11 @@ __device__ __forceinline__ float logaddexp_f(float a, float b) {
   return mx + log1pf(expf(mn - mx));
 }
 
+// Partial record of one (row, vocabulary tile) as the fused joiner writes it: (max, sum-exp, KB values, KB indices), padded to whole
+// 16-byte vectors: three vector stores per row instead of ten scalar ones (the release that publishes a tile waits for them)
+template <int KB>
+constexpr int kBeamRecWords = (2 + 2 * KB + 3) & ~3;
+
 // order-preserving integer image of a float
 __device__ __forceinline__ int fkey_s(float f) { const int k = __float_as_int(f); return k ^ ((k >> 31) & 0x7fffffff); }
 __device__ __forceinline__ float funkey_s(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
@@ -43,18 +48,19 @@ __device__ __forceinline__ float funkey_s(int k) { return __int_as_float(k ^ ((k
 //      with log-add in rank order, compaction, back-pointer record;
 //   C. all threads: x[m,:] = tanh(enc[s,t+1] + decoder(ctx[m])) of the K new hypotheses from the memoised decoder table, written
 //      as the bf16 hi / lo tile images the joiner's loader warp fetches.
+// part_rec [N, nt, kBeamRecWords<KB>] is what joiner_topk_kernel<KB> writes.
 // Everything another CTA may have produced during the same launch (partials, state) is read with ld.global.cg.
 // KB = 4 or 8: compile-time bound of the beam (the step is latency-bound and most of its instructions are executed once, so its
 // code size is its run time: loops are unrolled to exactly KB levels). c_v / c_f [KB*KB] and s_ctx [2*KB] are shared scratch.
 template <int KB>
 __device__ __forceinline__ void beam_merge_stream(
-    int tid, int bar_id, int s, int K, int V, int nt, int T, int t, int blank, int unk, const float* part_m, const float* part_s,
-    const float* part_tv, const int32_t* part_ti, const BeamState& in, const BeamState& out, int32_t* bp, const int32_t* lens,
-    const float* dec_tab, const float* enc_next, long long enc_stride, int J, uint8_t* x_img, float4 e4, float* c_v, int* c_f,
+    int tid, int bar_id, int s, int K, int V, int nt, int T, int t, int blank, int unk, const float* part_rec,
+    const BeamState& in, const BeamState& out, int32_t* bp, const int32_t* lens,
+    const float* dec_tab, const float* enc_next, long long enc_stride, int J, uint8_t* x_img, float* c_v, int* c_f,
     int* s_ctx, long long* tl) {
   constexpr int kNone = (int)0x80000000;
-  constexpr int kPairs = 2, kCands = 8;            // per-lane register batches: nt <= 64, nt * K <= 256 without a tail pass
-  static_assert(kCands >= KB, "a lane must be able to hold a whole top-K");
+  // per-lane register batch: the records of tiles lane and lane + 32 (nt <= 64 without a tail pass), KB candidates each
+  constexpr int kPairs = 2, kCands = kPairs * KB, RW = kBeamRecWords<KB>;
   const unsigned full = 0xffffffffu;
   const int warp = tid >> 5, lane = tid & 31;
   const bool build = enc_next != nullptr;
@@ -88,37 +94,40 @@ __device__ __forceinline__ void beam_merge_stream(
     for (int h = warp; h < K; h += 4) {        // the loads of row h are issued before the live count has arrived (dead rows are
                                                // valid memory: the joiner reduced them like any other row)
       const size_t row = (size_t)s * K + h;
-      const float* pmr = part_m + row * nt;
-      const float* psr = part_s + row * nt;
-      const size_t cbase = row * nt * K;
-      const int ncand = nt * K;
+      const float* rrow = part_rec + row * nt * RW;          // this row's records: [nt][RW] = (max, sum-exp, KB values, KB indices)
       float pm[kPairs], ps[kPairs], cval[kCands];
       int cidx[kCands];
 #pragma unroll
       for (int u = 0; u < kPairs; ++u) {
         const int i = lane + 32 * u;
-        pm[u] = i < nt ? __ldcg(pmr + i) : -INFINITY;
-        ps[u] = i < nt ? __ldcg(psr + i) : 0.f;
-      }
+        uint32_t w[RW];
 #pragma unroll
-      for (int u = 0; u < kCands; ++u) {
-        const int c = lane + 32 * u;
-        cidx[u] = c < ncand ? __ldcg(part_ti + cbase + c) : -1;
-        cval[u] = c < ncand ? __ldcg(part_tv + cbase + c) : 0.f;
+        for (int v = 0; v < RW / 4; ++v) {
+          uint4 q4 = make_uint4(0xff800000u, 0u, 0xff800000u, 0xff800000u);
+          if (i < nt) q4 = __ldcg(reinterpret_cast<const uint4*>(rrow + (size_t)i * RW) + v);
+          w[4 * v] = q4.x; w[4 * v + 1] = q4.y; w[4 * v + 2] = q4.z; w[4 * v + 3] = q4.w;
+        }
+        pm[u] = i < nt ? __uint_as_float(w[0]) : -INFINITY;
+        ps[u] = i < nt ? __uint_as_float(w[1]) : 0.f;
+#pragma unroll
+        for (int j = 0; j < KB; ++j) {
+          cval[u * KB + j] = __uint_as_float(w[2 + j]);
+          cidx[u * KB + j] = i < nt ? (int)w[2 + KB + j] : -1;
+        }
       }
       const float lp = __ldcg(in.lp + row);
       if (h >= nl) continue;
       int mk = max(fkey_s(pm[0]), fkey_s(pm[1]));           // absent tiles read as -inf
 #pragma unroll 1
-      for (int i = lane + 32 * kPairs; i < nt; i += 32) mk = max(mk, fkey_s(__ldcg(pmr + i)));
+      for (int i = lane + 32 * kPairs; i < nt; i += 32) mk = max(mk, fkey_s(__ldcg(rrow + (size_t)i * RW)));
       const float mx = funkey_s(__reduce_max_sync(full, mk));
       float sum = 0.f;
 #pragma unroll
       for (int u = 0; u < kPairs; ++u) sum += (pm[u] > -INFINITY) ? ps[u] * __expf(pm[u] - mx) : 0.f;
 #pragma unroll 1
       for (int i = lane + 32 * kPairs; i < nt; i += 32) {
-        const float m2 = __ldcg(pmr + i);
-        sum += (m2 > -INFINITY) ? __ldcg(psr + i) * __expf(m2 - mx) : 0.f;
+        const float m2 = __ldcg(rrow + (size_t)i * RW);
+        sum += (m2 > -INFINITY) ? __ldcg(rrow + (size_t)i * RW + 1) * __expf(m2 - mx) : 0.f;
       }
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(full, sum, o);
@@ -133,26 +142,29 @@ __device__ __forceinline__ void beam_merge_stream(
         ck[u] = okc ? fkey_s(v) : kNone;
         cf[u] = okc ? h * V + cidx[u] : -1;
       }
-      // more than 32 * kCands candidates (rare): a lane keeps its best kCands >= K of them (its worst one is replaced)
+      // more than 64 tiles (rare): a lane keeps its best kCands >= K candidates (its worst one is replaced)
 #pragma unroll 1
-      for (int c = lane + 32 * kCands; c < ncand; c += 32) {
-        const int idx = __ldcg(part_ti + cbase + c);
-        const float v = ((__ldcg(part_tv + cbase + c) - mx) - ls) + lp;
-        const bool okc = (idx >= 0) & (v == v);
-        const int key = okc ? fkey_s(v) : kNone, f = okc ? h * V + idx : -1;
-        int wk = ck[0], wf = cf[0];
+      for (int i = lane + 32 * kPairs; i < nt; i += 32) {
+#pragma unroll 1
+        for (int j = 0; j < KB; ++j) {
+          const int idx = (int)__float_as_uint(__ldcg(rrow + (size_t)i * RW + 2 + KB + j));
+          const float v = ((__ldcg(rrow + (size_t)i * RW + 2 + j) - mx) - ls) + lp;
+          const bool okc = (idx >= 0) & (v == v);
+          const int key = okc ? fkey_s(v) : kNone, f = okc ? h * V + idx : -1;
+          int wk = ck[0], wf = cf[0];
 #pragma unroll
-        for (int u = 1; u < kCands; ++u) {
-          const bool lower = (ck[u] < wk) | ((ck[u] == wk) & (cf[u] < wf));
-          wk = lower ? ck[u] : wk; wf = lower ? cf[u] : wf;
-        }
-        const bool take = (key > wk) | ((key == wk) & (f > wf));
-        bool done = !take;
+          for (int u = 1; u < kCands; ++u) {
+            const bool lower = (ck[u] < wk) | ((ck[u] == wk) & (cf[u] < wf));
+            wk = lower ? ck[u] : wk; wf = lower ? cf[u] : wf;
+          }
+          const bool take = (key > wk) | ((key == wk) & (f > wf));
+          bool done = !take;
 #pragma unroll
-        for (int u = 0; u < kCands; ++u) {
-          const bool hit = !done & (ck[u] == wk) & (cf[u] == wf);
-          ck[u] = hit ? key : ck[u]; cf[u] = hit ? f : cf[u];
-          done |= hit;
+          for (int u = 0; u < kCands; ++u) {
+            const bool hit = !done & (ck[u] == wk) & (cf[u] == wf);
+            ck[u] = hit ? key : ck[u]; cf[u] = hit ? f : cf[u];
+            done |= hit;
+          }
         }
       }
       if (tl != nullptr && tid == 0) tl[1] = clock64();   // diagnostic stamp
@@ -272,36 +284,29 @@ __device__ __forceinline__ void beam_merge_stream(
   // ---- C: the next frame's joiner operand of this stream's K hypotheses -------------------------------------------------------
   if (!build) return;
   constexpr int kRowTile = 128, kImgTile = 128 * 128;        // rows per image tile, bytes of one 128 x 64 bf16 tile
-  for (int k = 4 * tid; k < J; k += 512) {
-    const float4 e = k == 4 * tid ? e4 : __ldg(reinterpret_cast<const float4*>(enc_next + (size_t)s * enc_stride + k));
-    const float ex[4] = {expf(2.f * fminf(fmaxf(e.x, -21.f), 21.f)), expf(2.f * fminf(fmaxf(e.y, -21.f), 21.f)),
-                         expf(2.f * fminf(fmaxf(e.z, -21.f), 21.f)), expf(2.f * fminf(fmaxf(e.w, -21.f), 21.f))};
-    float4 d[KB];
+  const int per_row = J >> 3;                                // work item = 8 consecutive k of one hypothesis: 16-byte image stores
+  for (int it = tid; it < K * per_row; it += 128) {
+    const int q = it / per_row, k = (it - q * per_row) << 3;
+    const float* erow = enc_next + (size_t)s * enc_stride + k;
+    const float* drow = dec_tab + ((size_t)(s_ctx[2 * q] + 1) * V + s_ctx[2 * q + 1]) * J + k;
+    const float4 e0 = __ldg(reinterpret_cast<const float4*>(erow)), e1 = __ldg(reinterpret_cast<const float4*>(erow) + 1);
+    const float4 d0 = __ldg(reinterpret_cast<const float4*>(drow)), d1 = __ldg(reinterpret_cast<const float4*>(drow) + 1);
+    const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w}, dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    float x[8], hi[8];
 #pragma unroll
-    for (int q = 0; q < KB; ++q)
-      if (q < K)
-        d[q] = __ldg(reinterpret_cast<const float4*>(dec_tab + ((size_t)(s_ctx[2 * q] + 1) * V + s_ctx[2 * q + 1]) * J + k));
-#pragma unroll
-    for (int q = 0; q < KB; ++q) {
-      if (q < K) {
-        const int m = s * K + q;
-        const float dv[4] = {d[q].x, d[q].y, d[q].z, d[q].w};
-        float x[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {       // tanh(e + d) = 1 - 2 / (1 + exp(2e) * exp(2d)); the table holds exp(2d)
-          float r;
-          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(ex[i], dv[i], 1.f)));
-          x[i] = fmaf(-2.f, r, 1.f);
-        }
-        uint8_t* timg = x_img + ((size_t)(m / kRowTile) * (J / 64) + (k >> 6)) * (2 * kImgTile) +
-                        k2b::ptx::sw128_offset(m % kRowTile, k & 63);
-        const float h0 = k2b::ptx::bf16_round(x[0]), h1 = k2b::ptx::bf16_round(x[1]), h2 = k2b::ptx::bf16_round(x[2]),
-                    h3 = k2b::ptx::bf16_round(x[3]);
-        *reinterpret_cast<uint2*>(timg) = make_uint2(k2b::ptx::pack_bf16x2(h0, h1), k2b::ptx::pack_bf16x2(h2, h3));
-        *reinterpret_cast<uint2*>(timg + kImgTile) =
-            make_uint2(k2b::ptx::pack_bf16x2(x[0] - h0, x[1] - h1), k2b::ptx::pack_bf16x2(x[2] - h2, x[3] - h3));
-      }
+    for (int i = 0; i < 8; ++i) {           // tanh(e + d) = 1 - 2 / (1 + exp(2e) * exp(2d)); the table holds exp(2d)
+      float r;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(expf(2.f * fminf(fmaxf(ev[i], -21.f), 21.f)), dv[i], 1.f)));
+      x[i] = fmaf(-2.f, r, 1.f);
+      hi[i] = k2b::ptx::bf16_round(x[i]);
     }
+    const int m = s * K + q;
+    uint8_t* timg = x_img + ((size_t)(m / kRowTile) * (J / 64) + (k >> 6)) * (2 * kImgTile) + k2b::ptx::sw128_offset(m % kRowTile, k & 63);
+    *reinterpret_cast<uint4*>(timg) = make_uint4(k2b::ptx::pack_bf16x2(hi[0], hi[1]), k2b::ptx::pack_bf16x2(hi[2], hi[3]),
+                                                 k2b::ptx::pack_bf16x2(hi[4], hi[5]), k2b::ptx::pack_bf16x2(hi[6], hi[7]));
+    *reinterpret_cast<uint4*>(timg + kImgTile) =
+        make_uint4(k2b::ptx::pack_bf16x2(x[0] - hi[0], x[1] - hi[1]), k2b::ptx::pack_bf16x2(x[2] - hi[2], x[3] - hi[3]),
+                   k2b::ptx::pack_bf16x2(x[4] - hi[4], x[5] - hi[5]), k2b::ptx::pack_bf16x2(x[6] - hi[6], x[7] - hi[7]));
   }
   if (tl != nullptr && tid == 0) atomicMax(reinterpret_cast<unsigned long long*>(tl + 7), (unsigned long long)clock64());
 }

@@ -597,11 +597,6 @@ size_t joiner_tc_image_bytes(const k2b_handle* h, int M) {
 int32_t joiner_tc_partials(k2b_handle* h, const float* x, const uint8_t* x_img, int M, int topk, float* part_m, float* part_s,
                            float* part_tv, int32_t* part_ti, float* part_val, int32_t* part_idx, int32_t* part_nan) {
   K2B_TRY(ensure_joiner_assets(h));
-  // beam search with a TMA-fed operand: the persistent kernel of joiner_tc.cu (K2B_OLD_JOINER=1 keeps the one-tile-per-CTA kernel
-  // below, for comparison runs)
-  static const bool old_joiner = getenv("K2B_OLD_JOINER") != nullptr;
-  if (x_img != nullptr && topk > 0 && !old_joiner && joiner_topk_supported(h, topk))
-    return joiner_topk_tc(h, x_img, M, topk, part_m, part_s, part_tv, part_ti);
   EncArgs a = {};
   a.A = x; a.w_hi_img = h->wj_hi_img; a.w_lo_img = h->wj_lo_img; a.bias = h->out_b; a.C = nullptr;
   if (x_img != nullptr) { a.pro = 2; a.a_img = x_img; }

@@ -50,7 +50,7 @@ struct JArgs {
   const uint8_t* w_lo_img;
   const float* bias;         // [V]
   int M, ntm, ntn, nkb, x3, nvalid, topk;
-  float* part_m; float* part_s; float* part_tv; int32_t* part_ti;     // [M,ntn], [M,ntn], [M,ntn,topk] x2
+  float* part_rec;           // [M,ntn,kBeamRecWords<KK>]: (max, sum-exp, KK values, KK indices) per (row, tile)
   int* status;
   long long* dbg;
   long long* tl;             // diagnostic timeline of this launch: [sm][8] clock64 stamps (slots 0..3), or null
@@ -356,17 +356,21 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
       }
       const int m = tile_m * kJM + row;
       if (m < a.M && half == 0) {
-        const size_t po = (size_t)m * a.ntn + tile_n;
-        a.part_m[po] = mx;
-        a.part_s[po] = any ? sum : 0.f;
+        constexpr int RW = kBeamRecWords<KK>;
+        uint32_t w[RW];
+#pragma unroll
+        for (int i = 0; i < RW; ++i) w[i] = 0u;
+        w[0] = __float_as_uint(mx);
+        w[1] = __float_as_uint(any ? sum : 0.f);
 #pragma unroll
         for (int i = 0; i < KK; ++i) {
-          if (i < K) {
-            const bool has = key[i] > kInfKey;
-            a.part_tv[po * K + i] = has ? tv[i] : -INFINITY;
-            a.part_ti[po * K + i] = has ? col0 + (key[i] & 255) : -1;
-          }
+          const bool has = i < K && key[i] > kInfKey;
+          w[2 + i] = __float_as_uint(has ? tv[i] : -INFINITY);
+          w[2 + KK + i] = (uint32_t)(has ? col0 + (key[i] & 255) : -1);
         }
+        uint4* dst = reinterpret_cast<uint4*>(a.part_rec + ((size_t)m * a.ntn + tile_n) * RW);
+#pragma unroll
+        for (int v = 0; v < RW / 4; ++v) dst[v] = make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
       }
       if (dbg && it == 0) c_epi = clock64();
       if (tlm != nullptr && tid == 64 && t < 40 && tile == blockIdx.x) tlm[t * 16 + 12] = clock64();
@@ -392,8 +396,6 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
       const float* enc_next = t + 1 < a.T ? a.enc + (size_t)(t + 1) * a.J : nullptr;
       for (int s = blockIdx.x; s < a.B && ok; s += gridDim.x) {
         const int r = s / spr;
-        float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (enc_next != nullptr && 4 * mtid < a.J) e4 = __ldg(reinterpret_cast<const float4*>(enc_next + (size_t)s * a.enc_stride + 4 * mtid));
         int good = 1;
         if (mtid == 0) good = wait_count(a.done + (size_t)t * a.ntm + r, a.ntn, a.abort_flag) ? 1 : 0;
         if (mtid == 0) mg_ctx[0] = good;
@@ -409,8 +411,8 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
         sin.len = odd ? a.st[1].len : a.st[0].len; sout.len = odd ? a.st[0].len : a.st[1].len;
         sin.hash = odd ? a.st[1].hash : a.st[0].hash; sout.hash = odd ? a.st[0].hash : a.st[1].hash;
         sin.nlive = odd ? a.st[1].nlive : a.st[0].nlive; sout.nlive = odd ? a.st[0].nlive : a.st[1].nlive;
-        beam_merge_stream<KK>(mtid, 2, s, a.topk, a.V, a.ntn, a.T, t, a.blank, a.unk, a.part_m, a.part_s, a.part_tv, a.part_ti,
-                              sin, sout, a.bp, a.lens, a.dec_tab, enc_next, a.enc_stride, a.J, a.x_img, e4,
+        beam_merge_stream<KK>(mtid, 2, s, a.topk, a.V, a.ntn, a.T, t, a.blank, a.unk, a.part_rec,
+                              sin, sout, a.bp, a.lens, a.dec_tab, enc_next, a.enc_stride, a.J, a.x_img,
                               mg_v, mg_f, mg_ctx, (tlm != nullptr && t < 40 && s == blockIdx.x) ? tlm + 640 + t * 8 : nullptr);
         if (t + 1 < a.T) {                                // publish: one more stream of (frame t + 1, row tile) has its operand rows
           asm volatile("fence.proxy.async;" ::: "memory");       // the rows are read through the async proxy (TMA)
@@ -469,16 +471,15 @@ bool joiner_topk_usable(const k2b_handle* h, int topk) {
   return !old_joiner && topk >= 1 && topk <= 8 && h->cfg.joiner_dim % kJBK == 0;
 }
 
-// x_img: the joiner operand as bf16 hi / lo tile images (joinin_table_tc / decoder_joinin_tc). Partials per (row, 160-column
-// vocabulary tile) as joiner_tc_partials writes them. The weight images must exist (ensure_joiner_assets).
-int32_t joiner_topk_tc(k2b_handle* h, const uint8_t* x_img, int M, int topk, float* part_m, float* part_s, float* part_tv,
-                       int32_t* part_ti) {
+// x_img: the joiner operand as bf16 hi / lo tile images (joinin_table_tc / decoder_joinin_tc). Partial records per (row, 160-column
+// vocabulary tile): beam_partial_words(topk) floats each (beam_merge.cuh). The weight images must exist (ensure_joiner_assets).
+int32_t joiner_topk_tc(k2b_handle* h, const uint8_t* x_img, int M, int topk, float* part_rec) {
   JArgs a = {};
   a.a_img = x_img; a.w_hi_img = h->wj_hi_img; a.w_lo_img = h->wj_lo_img; a.bias = h->out_b;
   a.M = M; a.ntm = (M + kJM - 1) / kJM; a.ntn = (h->cfg.vocab_size + kJNc - 1) / kJNc; a.nkb = h->cfg.joiner_dim / kJBK;
   a.x3 = h->cfg.precision == K2B_PREC_BF16 ? 0 : 1;
   a.nvalid = h->cfg.vocab_size; a.topk = topk;
-  a.part_m = part_m; a.part_s = part_s; a.part_tv = part_tv; a.part_ti = part_ti;
+  a.part_rec = part_rec;
   a.status = h->dev_status + 1;
   a.dbg = h->cluster_timing;
   a.tl = h->timeline != nullptr ? h->timeline + (size_t)(h->timeline_frame % 64) * 148 * 8 : nullptr;
@@ -492,15 +493,14 @@ bool beam_mega_usable(const k2b_handle* h, int K) {
   return !off && (K == 2 || K == 4 || K == 8) && joiner_topk_usable(h, K) && h->dec_tab != nullptr;
 }
 
-int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8_t* x_img, float* part_m, float* part_s, float* part_tv,
-                     int32_t* part_ti, const BeamStatePtrs& s0, const BeamStatePtrs& s1, int32_t* bp, const int32_t* lens) {
+int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8_t* x_img, float* part_rec, const BeamStatePtrs& s0, const BeamStatePtrs& s1, int32_t* bp, const int32_t* lens) {
   const int M = B * K;
   JArgs a = {};
   a.a_img = x_img; a.x_img = x_img; a.w_hi_img = h->wj_hi_img; a.w_lo_img = h->wj_lo_img; a.bias = h->out_b;
   a.M = M; a.ntm = (M + kJM - 1) / kJM; a.ntn = (h->cfg.vocab_size + kJNc - 1) / kJNc; a.nkb = h->cfg.joiner_dim / kJBK;
   a.x3 = h->cfg.precision == K2B_PREC_BF16 ? 0 : 1;
   a.nvalid = h->cfg.vocab_size; a.topk = K;
-  a.part_m = part_m; a.part_s = part_s; a.part_tv = part_tv; a.part_ti = part_ti;
+  a.part_rec = part_rec;
   a.status = h->dev_status + 1;
   a.B = B; a.V = h->cfg.vocab_size; a.T = T; a.blank = h->cfg.blank_id; a.unk = h->cfg.unk_id; a.J = h->cfg.joiner_dim;
   a.st[0] = BeamState{s0.ctx, s0.lp, s0.len, reinterpret_cast<uint64_t*>(s0.hash), s0.nlive};
@@ -515,5 +515,8 @@ int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8
   a.tl = h->timeline;
   return K <= 4 ? launch_as<4, true>(h, a) : launch_as<8, true>(h, a);
 }
+
+
+int beam_partial_words(int topk) { return topk <= 4 ? kBeamRecWords<4> : kBeamRecWords<8>; }
 
 }  // namespace k2b

@@ -237,14 +237,13 @@ int32_t joiner_tc_partials(k2b_handle* h, const float* x, const uint8_t* x_img, 
 // ---- joiner_tc.cu ------------------------------------------------------------------------------
 bool joiner_topk_supported(const k2b_handle* h, int topk);
 bool joiner_topk_usable(const k2b_handle* h, int topk);   // the persistent joiner will serve joiner_tc_partials(x_img, topk)
-int32_t joiner_topk_tc(k2b_handle* h, const uint8_t* x_img, int M, int topk, float* part_m, float* part_s, float* part_tv,
-                       int32_t* part_ti);
+int32_t joiner_topk_tc(k2b_handle* h, const uint8_t* x_img, int M, int topk, float* part_rec);
+int beam_partial_words(int topk);      // floats per (row, tile) record of joiner_topk_tc / beam_mega_tc
 
 struct BeamStatePtrs { int32_t* ctx; float* lp; int32_t* len; unsigned long long* hash; int32_t* nlive; };
 constexpr int32_t kMegaUnavailable = 0x4d454741;   // beam_mega_tc: the cooperative launch does not fit; nothing was enqueued
 bool beam_mega_usable(const k2b_handle* h, int K);
-int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8_t* x_img, float* part_m, float* part_s, float* part_tv,
-                     int32_t* part_ti, const BeamStatePtrs& s0, const BeamStatePtrs& s1, int32_t* bp, const int32_t* lens);
+int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8_t* x_img, float* part_rec, const BeamStatePtrs& s0, const BeamStatePtrs& s1, int32_t* bp, const int32_t* lens);
 
 // profiling bracket around the dominant GEMM
 void prof_begin(k2b_handle* h);

@@ -317,8 +317,7 @@ beam_select_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk
 template <int KB>
 __global__ void __launch_bounds__(128)
 beam_step_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
-                 const float* __restrict__ part_m, const float* __restrict__ part_s,
-                 const float* __restrict__ part_tv, const int32_t* __restrict__ part_ti,
+                 const float* __restrict__ part_rec,
                  BeamState in, BeamState out, int32_t* __restrict__ bp, const int32_t* __restrict__ lens,
                  const float* __restrict__ dec_tab, const float* __restrict__ enc_next, long long enc_stride, int J,
                  uint8_t* __restrict__ x_img, long long* __restrict__ tl) {
@@ -327,9 +326,6 @@ beam_step_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
   __shared__ int s_ctx[2 * KB];
   const int tid = threadIdx.x, s = blockIdx.x;
   k2b::ptx::griddep_launch_dependents();
-  // the next frame of this stream does not depend on the kernels before this one: fetch it ahead of the wait
-  float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (enc_next != nullptr && 4 * tid < J) e4 = __ldg(reinterpret_cast<const float4*>(enc_next + (size_t)s * enc_stride + 4 * tid));
   if (tl != nullptr) {                                      // diagnostic timeline: [sm][8], slots 4..7 = first start, first wait-done,
     uint32_t smid;                                          // last merge-done, last end of the CTAs of this launch on that SM
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -338,8 +334,8 @@ beam_step_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
   }
   k2b::ptx::griddep_wait();
   if (tl != nullptr && tid == 0) atomicMin(reinterpret_cast<long long*>(tl + 5), clock64());
-  beam_merge_stream<KB>(tid, 1, s, K, V, nt, T, t, blank, unk, part_m, part_s, part_tv, part_ti, in, out, bp, lens, dec_tab, enc_next,
-                        enc_stride, J, x_img, e4, c_v, c_f, s_ctx, tl);
+  beam_merge_stream<KB>(tid, 1, s, K, V, nt, T, t, blank, unk, part_rec, in, out, bp, lens, dec_tab, enc_next, enc_stride, J, x_img,
+                        c_v, c_f, s_ctx, tl);
 }
 
 // One warp per stream: pick argmax lp/len (first maximum in slot order), walk the back-pointers in
@@ -490,7 +486,8 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
     K2B_TRY(ensure(h, h->ws_ximg, joiner_tc_image_bytes(h, N)));
     ximg = static_cast<uint8_t*>(h->ws_ximg.p);
   }
-  K2B_TRY(ensure(h, h->ws_part, (size_t)N * nt * (8 + 8 * (size_t)K)));
+  // per (row, tile): four arrays of the per-frame kernels (8 + 8K bytes) or one record of the fused joiner (beam_partial_words)
+  K2B_TRY(ensure(h, h->ws_part, (size_t)N * nt * (size_t)max(8 + 8 * K, 4 * beam_partial_words(K))));
   K2B_TRY(ensure(h, h->ws_state, 2 * state_bytes(B, K)));
   K2B_TRY(ensure(h, h->ws_bp, sizeof(int32_t) * (size_t)B * (T > 0 ? T : 1) * K));
   char* p = static_cast<char*>(h->ws_state.p);
@@ -512,14 +509,14 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
   // dependent launches. K2B_UNFUSED_STEP=1 keeps the three-launch sequence below (comparison runs).
   static const bool unfused = getenv("K2B_UNFUSED_STEP") != nullptr;
   if (tc && have_tab && ximg != nullptr && !unfused && joiner_topk_usable(h, K) && T > 0) {
+    K2B_TRY(ensure_joiner_assets(h));
     K2B_TRY(joinin_table_tc(h, st[0].ctx, N, enc, (long long)T * J, K, ximg));
     if (beam_mega_usable(h, K) && !(h->profile_on && h->prof_which != 0)) {       // the whole time loop in one launch
-      K2B_TRY(ensure_joiner_assets(h));
       BeamStatePtrs sp[2];
       for (int i = 0; i < 2; ++i)
         sp[i] = BeamStatePtrs{st[i].ctx, st[i].lp, st[i].len, reinterpret_cast<unsigned long long*>(st[i].hash), st[i].nlive};
       prof_begin(h);
-      const int32_t ms = beam_mega_tc(h, enc, B, T, K, ximg, part_m, part_s, part_tv, part_ti, sp[0], sp[1], bp,
+      const int32_t ms = beam_mega_tc(h, enc, B, T, K, ximg, part_m, sp[0], sp[1], bp,
                                       h->lens_active ? h->lens_dev : nullptr);
       prof_end(h);
       if (ms != kMegaUnavailable) {
@@ -530,13 +527,12 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
     }
     for (int t = 0; t < T; ++t) {
       if (h->prof_which == 0) prof_begin(h);
-      K2B_TRY(joiner_tc_partials(h, x, ximg, N, K, part_m, part_s, part_tv, part_ti, nullptr, nullptr, nullptr));
+      K2B_TRY(joiner_topk_tc(h, ximg, N, K, part_m));
       if (h->prof_which == 0) prof_end(h);
       if (h->prof_which == 2) prof_begin(h);
       K2B_CUDA(h, launch_pdl(K <= 4 ? beam_step_kernel<4> : beam_step_kernel<8>, dim3(B), dim3(128), 0, h->stream, B, K, V, nt, T, t,
                               (int)c.blank_id, (int)c.unk_id,
-                              (const float*)part_m, (const float*)part_s, (const float*)part_tv, (const int32_t*)part_ti, st[cur],
-                              st[cur ^ 1], bp, (const int32_t*)(h->lens_active ? h->lens_dev : nullptr), (const float*)h->dec_tab,
+                              (const float*)part_m, st[cur], st[cur ^ 1], bp, (const int32_t*)(h->lens_active ? h->lens_dev : nullptr), (const float*)h->dec_tab,
                               (const float*)(t + 1 < T ? enc + (size_t)(t + 1) * J : nullptr), (long long)T * J, J, ximg,
                               (long long*)(h->timeline != nullptr ? h->timeline + (size_t)(h->timeline_frame % 64) * 148 * 8 : nullptr)));
       K2B_LAUNCH_CHECK(h);
