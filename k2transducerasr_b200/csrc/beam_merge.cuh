@@ -52,11 +52,25 @@ __device__ __forceinline__ float funkey_s(int k) { return __int_as_float(k ^ ((k
 // Everything another CTA may have produced during the same launch (partials, state) is read with ld.global.cg.
 // KB = 4 or 8: compile-time bound of the beam (the step is latency-bound and most of its instructions are executed once, so its
 // code size is its run time: loops are unrolled to exactly KB levels). c_v / c_f [KB*KB] and s_ctx [2*KB] are shared scratch.
+// the next frame's encoder values of thread tid's first operand item (8 consecutive k of hypothesis tid / (J/8)): they do not depend
+// on the search, so the callers fetch them before they wait
+__device__ __forceinline__ void beam_merge_prefetch(int tid, int s, int K, int J, const float* enc_next, long long enc_stride, float4* pe0,
+                                                    float4* pe1) {
+  *pe0 = *pe1 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int per_row = J >> 3;
+  if (enc_next != nullptr && tid < K * per_row) {
+    const float* erow = enc_next + (size_t)s * enc_stride + ((tid % per_row) << 3);
+    *pe0 = __ldg(reinterpret_cast<const float4*>(erow));
+    *pe1 = __ldg(reinterpret_cast<const float4*>(erow) + 1);
+  }
+}
+
 template <int KB>
 __device__ __forceinline__ void beam_merge_stream(
     int tid, int bar_id, int s, int K, int V, int nt, int T, int t, int blank, int unk, const float* part_rec,
     const BeamState& in, const BeamState& out, int32_t* bp, const int32_t* lens,
-    const float* dec_tab, const float* enc_next, long long enc_stride, int J, uint8_t* x_img, float* c_v, int* c_f,
+    const float* dec_tab, const float* enc_next, long long enc_stride, int J, uint8_t* x_img, float4 pe0, float4 pe1, float* c_v,
+    int* c_f,
     int* s_ctx, long long* tl) {
   constexpr int kNone = (int)0x80000000;
   // per-lane register batch: the records of tiles lane and lane + 32 (nt <= 64 without a tail pass), KB candidates each
@@ -200,14 +214,32 @@ __device__ __forceinline__ void beam_merge_stream(
       }
       float my_v = -INFINITY;
       int my_f = -1;
+      if constexpr (KB * KB <= 32) {
+        // one candidate per lane: its rank is the number of better candidates, found with independent shuffles (no chain of
+        // reductions); the K best reach lanes 0..K-1 through shared memory (valid candidates have distinct flat indices)
+        const int mk = tk[0], mf = tf[0];
+        int rank = 0;
 #pragma unroll
-      for (int r = 0; r < KB; ++r) {
-        if (r < K) {
-          const int wk = __reduce_max_sync(full, max(tk[0], tk[1]));
-          const int wf = __reduce_max_sync(full, max((tk[0] == wk) ? tf[0] : -1, (tk[1] == wk) ? tf[1] : -1));
-          tk[0] = ((tk[0] == wk) & (tf[0] == wf)) ? kNone : tk[0];
-          tk[1] = ((tk[1] == wk) & (tf[1] == wf)) ? kNone : tk[1];
-          if (lane == r) { my_v = wf >= 0 ? funkey_s(wk) : -INFINITY; my_f = wf; }
+        for (int j = 0; j < KB * KB; ++j) {
+          const int ok = __shfl_sync(full, mk, j), of = __shfl_sync(full, mf, j);
+          rank += ((ok > mk) | ((ok == mk) & (of > mf))) ? 1 : 0;
+        }
+        __syncwarp();
+        if (lane < KB) c_f[lane] = -1;
+        __syncwarp();
+        if (mf >= 0 && rank < K) { c_v[rank] = funkey_s(mk); c_f[rank] = mf; }
+        __syncwarp();
+        if (lane < K) { my_f = c_f[lane]; my_v = my_f >= 0 ? c_v[lane] : -INFINITY; }
+      } else {
+#pragma unroll
+        for (int r = 0; r < KB; ++r) {
+          if (r < K) {
+            const int wk = __reduce_max_sync(full, max(tk[0], tk[1]));
+            const int wf = __reduce_max_sync(full, max((tk[0] == wk) ? tf[0] : -1, (tk[1] == wk) ? tf[1] : -1));
+            tk[0] = ((tk[0] == wk) & (tf[0] == wf)) ? kNone : tk[0];
+            tk[1] = ((tk[1] == wk) & (tf[1] == wf)) ? kNone : tk[1];
+            if (lane == r) { my_v = wf >= 0 ? funkey_s(wk) : -INFINITY; my_f = wf; }
+          }
         }
       }
       if (tl != nullptr && tid == 0) tl[3] = clock64();   // diagnostic stamp
@@ -289,7 +321,9 @@ __device__ __forceinline__ void beam_merge_stream(
     const int q = it / per_row, k = (it - q * per_row) << 3;
     const float* erow = enc_next + (size_t)s * enc_stride + k;
     const float* drow = dec_tab + ((size_t)(s_ctx[2 * q] + 1) * V + s_ctx[2 * q + 1]) * J + k;
-    const float4 e0 = __ldg(reinterpret_cast<const float4*>(erow)), e1 = __ldg(reinterpret_cast<const float4*>(erow) + 1);
+    // (the caller fetched the frame values of this thread's first item before it waited for the partials)
+    const float4 e0 = it == tid ? pe0 : __ldg(reinterpret_cast<const float4*>(erow));
+    const float4 e1 = it == tid ? pe1 : __ldg(reinterpret_cast<const float4*>(erow) + 1);
     const float4 d0 = __ldg(reinterpret_cast<const float4*>(drow)), d1 = __ldg(reinterpret_cast<const float4*>(drow) + 1);
     const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w}, dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
     float x[8], hi[8];

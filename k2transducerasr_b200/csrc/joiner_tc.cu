@@ -396,6 +396,8 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
       const float* enc_next = t + 1 < a.T ? a.enc + (size_t)(t + 1) * a.J : nullptr;
       for (int s = blockIdx.x; s < a.B && ok; s += gridDim.x) {
         const int r = s / spr;
+        float4 pe0, pe1;
+        beam_merge_prefetch(mtid, s, a.topk, a.J, enc_next, a.enc_stride, &pe0, &pe1);
         int good = 1;
         if (mtid == 0) good = wait_count(a.done + (size_t)t * a.ntm + r, a.ntn, a.abort_flag) ? 1 : 0;
         if (mtid == 0) mg_ctx[0] = good;
@@ -412,7 +414,7 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
         sin.hash = odd ? a.st[1].hash : a.st[0].hash; sout.hash = odd ? a.st[0].hash : a.st[1].hash;
         sin.nlive = odd ? a.st[1].nlive : a.st[0].nlive; sout.nlive = odd ? a.st[0].nlive : a.st[1].nlive;
         beam_merge_stream<KK>(mtid, 2, s, a.topk, a.V, a.ntn, a.T, t, a.blank, a.unk, a.part_rec,
-                              sin, sout, a.bp, a.lens, a.dec_tab, enc_next, a.enc_stride, a.J, a.x_img,
+                              sin, sout, a.bp, a.lens, a.dec_tab, enc_next, a.enc_stride, a.J, a.x_img, pe0, pe1,
                               mg_v, mg_f, mg_ctx, (tlm != nullptr && t < 40 && s == blockIdx.x) ? tlm + 640 + t * 8 : nullptr);
         if (t + 1 < a.T) {                                // publish: one more stream of (frame t + 1, row tile) has its operand rows
           asm volatile("fence.proxy.async;" ::: "memory");       // the rows are read through the async proxy (TMA)

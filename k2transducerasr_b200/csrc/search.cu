@@ -326,6 +326,8 @@ beam_step_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
   __shared__ int s_ctx[2 * KB];
   const int tid = threadIdx.x, s = blockIdx.x;
   k2b::ptx::griddep_launch_dependents();
+  float4 pe0, pe1;            // the next frame of this stream does not depend on the kernels before this one: fetched ahead of the wait
+  beam_merge_prefetch(tid, s, K, J, enc_next, enc_stride, &pe0, &pe1);
   if (tl != nullptr) {                                      // diagnostic timeline: [sm][8], slots 4..7 = first start, first wait-done,
     uint32_t smid;                                          // last merge-done, last end of the CTAs of this launch on that SM
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -335,7 +337,7 @@ beam_step_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
   k2b::ptx::griddep_wait();
   if (tl != nullptr && tid == 0) atomicMin(reinterpret_cast<long long*>(tl + 5), clock64());
   beam_merge_stream<KB>(tid, 1, s, K, V, nt, T, t, blank, unk, part_rec, in, out, bp, lens, dec_tab, enc_next, enc_stride, J, x_img,
-                        c_v, c_f, s_ctx, tl);
+                        pe0, pe1, c_v, c_f, s_ctx, tl);
 }
 
 // One warp per stream: pick argmax lp/len (first maximum in slot order), walk the back-pointers in
