@@ -354,9 +354,10 @@ def test_full_size_cfg5_ctc_properties(built_lib):
     h.close()
 
 
-def test_full_size_cfg4_properties(built_lib):
-    """cfg4 shape (B=256, T=250 cut to 60 here, K=4, V=5537: per-frame path - tcgen05 decoder, tcgen05 joiner with the reducing
-    epilogue, merge kernel): determinism, shard-invariance, token range, an oracle spot check, and ragged lengths."""
+def test_full_size_cfg4_properties(built_lib, monkeypatch):
+    """cfg4 shape (B=256, T=250 cut to 60 here, K=4, V=5537: the persistent beam kernel - tcgen05 joiner CTAs + merge warps in one
+    launch): determinism, shard-invariance, token range, an oracle spot check, ragged lengths, and - at the full 250 frames -
+    bit-identical results from the per-frame launches (a different schedule of the same arithmetic)."""
     cfg = synth.CONFIGS["cfg4"]
     T = 60
     m, w = model_and_weights(cfg.dims, blank_bias=cfg.blank_bias)
@@ -380,6 +381,13 @@ def test_full_size_cfg4_properties(built_lib):
     tr, sr, _ = h.modified_beam_search(raw, 4, enc_is_raw=True, lens=lens)
     assert all(all(x < lens[b] for x in sr[b]) for b in range(cfg.streams))
     assert [tr[b] for b in range(cfg.streams) if lens[b] == T] == [t1[b] for b in range(cfg.streams) if lens[b] == T]
+    full = synth.make_frames(cfg.streams, cfg.frames, cfg.dims.encoder_dim, cfg.seed + 1)
+    tm, sm, scm = h.modified_beam_search(full, 4, enc_is_raw=True)
+    monkeypatch.setenv("K2B_NO_MEGA", "1")
+    tp, sp, scp = h.modified_beam_search(full, 4, enc_is_raw=True)
+    monkeypatch.delenv("K2B_NO_MEGA")
+    assert tm == tp and sm == sp and scm.tolist() == scp.tolist()
+    assert sum(len(t) for t in tm) > cfg.streams * 10            # it decoded something
     h.close()
 
 
