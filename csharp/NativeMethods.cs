@@ -48,6 +48,26 @@ namespace K2TransducerAsr.B200
             int[]? frame_offset, [In, Out] long[]? prev_inout, [Out] long[] tokens, [Out] int[] ts, [Out] int[] n_out,
             [In, Out] int[]? trailing_blank_inout, int cap);
 
+        // on-device streaming state (replaces the Array.Copy loops of stack_states / unstack_states, ref OnlineProjOfZipformer2.cs:144-489):
+        // one slot per OnlineStream; `stacked` is a DEVICE pointer of k2b_state_pool_stacked_floats(h, B) floats that the encoder
+        // session binds as its cache inputs / outputs (ORT IOBinding on the CUDA EP), so the caches never cross PCIe
+        [DllImport(Lib)] public static extern int k2b_state_pool_create(IntPtr h, int[] item_len, int n_tensors, int max_streams);
+        [DllImport(Lib)] public static extern long k2b_state_pool_stacked_floats(IntPtr h, int B);
+        [DllImport(Lib)] public static extern int k2b_state_pool_put(IntPtr h, int slot, float[] state);
+        [DllImport(Lib)] public static extern int k2b_state_pool_get(IntPtr h, int slot, [Out] float[] state);
+        [DllImport(Lib)] public static extern int k2b_stack_states(IntPtr h, int[] slots, int B, int[] axis_len, IntPtr stackedDev);
+        [DllImport(Lib)] public static extern int k2b_unstack_states(IntPtr h, int[] slots, int B, int[] axis_len, IntPtr stackedDev);
+
+        // device-pointer variants (frames already on the GPU, e.g. the encoder session's CUDA output): enqueue only, then k2b_sync
+        [DllImport(Lib)] public static extern int k2b_set_stream(IntPtr h, IntPtr cudaStream);
+        [DllImport(Lib)] public static extern int k2b_sync(IntPtr h);
+        [DllImport(Lib)] public static extern int k2b_greedy_offline_dev(IntPtr h, IntPtr enc, int enc_is_raw, int B, int T, int mode,
+            IntPtr tokens, IntPtr ts, IntPtr n_out, int cap);
+        [DllImport(Lib)] public static extern int k2b_greedy_online_chunk_dev(IntPtr h, IntPtr enc, int enc_is_raw, int B, int Tc,
+            IntPtr hyp_inout, IntPtr tokens, IntPtr ts, IntPtr n_out, int cap);
+        [DllImport(Lib)] public static extern int k2b_modified_beam_search_dev(IntPtr h, IntPtr enc, int enc_is_raw, int B, int T, int K,
+            IntPtr tokens, IntPtr ts, IntPtr n_out, IntPtr score, int cap);
+
         internal static void Check(IntPtr h, int status, string what)
         {
             if (status == K2B_OK) return;
