@@ -7,18 +7,21 @@
 //               operand kernel, out_w is packed at load time) into a 2-stage ring of 72 KB stages;
 //   warp 1      MMA issuer (warp-uniform loop, one elected lane): tcgen05.mma M = 128, N = 160, K = 16, split-bf16 x3, into one
 //               of TWO TMEM accumulators, so the mainloop of tile i+1 runs under the epilogue of tile i;
-//   warps 2-5   epilogue, one thread per logits row (= TMEM lane): pass 1 walks the 160 columns out of TMEM, adds the bias, keeps
-//               the fp32 value in a per-thread shared-memory row and pushes an order-preserving integer key (low 8 bits = column)
-//               through a branch-free max/min insertion network - no shuffles, no divergence, 7 integer ops per logit for K <= 4;
-//               pass 2 re-reads the row for the sum of exponentials and fetches the exact fp32 logits of the K winners.
-// MEGA = true is the whole modified_beam_search time loop in ONE launch (cfg4: 250 frames): four more warps per CTA run the
-// hypothesis merge + next-operand step (beam_merge.cuh) of the CTA's streams, and the two kinds of work are chained by per-frame,
-// per-row-tile counters in global memory (release / acquire) instead of kernel boundaries: a stream's merge of frame t starts when
-// the 35 column tiles of its row tile are reduced, a tile of frame t+1 is loaded when the 32 streams of its row tile have written
-// their operand rows. Tiles are walked row-major, so the merges of the first wave's row tiles run under the second wave's GEMMs
-// and vice versa - the merge leaves the critical path.
-// MEGA = false: launched with programmatic stream serialization: barrier set-up, TMEM allocation and the first weight copies overlap the tail of
-// the operand kernel; griddepcontrol.wait precedes the first read of x and every write.
+//   warps 2-9   epilogue: a thread owns one logits row (= TMEM lane) and one 80-column half of it. Pass 1 walks the accumulator
+//               columns out of TMEM, adds the bias, keeps the fp32 value in a per-row shared-memory scratch and pushes an
+//               order-preserving integer key (low 8 bits = column) through a branch-free max/min insertion network - no shuffles,
+//               no divergence, 7 integer ops per logit for K <= 4; pass 2 re-reads the scratch for the sum of exponentials and
+//               fetches the exact fp32 logits of the K winners; the upper half hands its (keys, logits, max, sum) to the lower
+//               half through the scratch row; one record of 16-byte vectors per (row, tile) goes to global memory.
+// MEGA = true is the whole modified_beam_search time loop in ONE cooperative launch (cfg4: 250 frames): four more warps per CTA
+// run the hypothesis merge + next-operand step (beam_merge.cuh) of the CTA's streams, and the two kinds of work are chained by
+// per-frame, per-row-tile counters in global memory (release / acquire) instead of kernel boundaries: a stream's merge of frame t
+// starts when the 35 column tiles of its row tile are reduced, a tile of frame t+1 is loaded when the 32 streams of its row tile
+// have written their operand rows. Tiles are walked row-major, so the merges of the first wave's row tiles run under the second
+// wave's GEMMs and vice versa.
+// MEGA = false (beams 3 / 5 / 6 / 7, or no room for a cooperative launch): one launch per frame with programmatic stream
+// serialization - barrier set-up, TMEM allocation and the first weight copies overlap the tail of the kernel before;
+// griddepcontrol.wait precedes the first read of x and every write.
 #include <stdlib.h>
 
 #include <type_traits>
@@ -469,8 +472,7 @@ bool joiner_topk_supported(const k2b_handle* h, int topk) {
 }
 
 bool joiner_topk_usable(const k2b_handle* h, int topk) {
-  static const bool old_joiner = getenv("K2B_OLD_JOINER") != nullptr;
-  return !old_joiner && topk >= 1 && topk <= 8 && h->cfg.joiner_dim % kJBK == 0;
+  return topk >= 1 && topk <= 8 && h->cfg.joiner_dim % kJBK == 0;
 }
 
 // x_img: the joiner operand as bf16 hi / lo tile images (joinin_table_tc / decoder_joinin_tc). Partial records per (row, 160-column
