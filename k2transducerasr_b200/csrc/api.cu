@@ -603,6 +603,15 @@ int32_t k2b_set_encoder_out_lens(k2b_handle* h, const int64_t* lens, int32_t B) 
   return K2B_OK;
 }
 
+// Greedy search of a large vocabulary (V > 1024: sixteen-CTA clusters) runs as beam 1 either on the cluster kernel or on the
+// persistent beam kernel. The cluster kernel steps a frame in ~5.4 us but only about six 16-CTA clusters (32 streams each) are
+// co-resident, so it takes ceil(B / 192) waves; the persistent kernel steps any batch in one chain (K2B_GREEDY_PERSISTENT=0/1
+// overrides the choice for comparison runs).
+static bool prefer_persistent_greedy(k2b_handle* h, int B) {
+  if (const char* e = getenv("K2B_GREEDY_PERSISTENT")) return atoi(e) != 0 && beam_greedy_usable(h);
+  return h->cfg.vocab_size > 1024 && B > 384 && beam_greedy_usable(h);
+}
+
 // ---- fused search ---------------------------------------------------------------------------------
 int32_t k2b_greedy_offline_dev(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t T, int32_t mode,
                                int64_t* tokens, int32_t* ts, int32_t* n_out, int32_t cap) {
@@ -619,10 +628,15 @@ int32_t k2b_greedy_offline_dev(k2b_handle* h, const float* enc, int32_t enc_is_r
   // greedy search == beam 1 with the same tie rule: SINGLE / PER_STREAM run on the persistent cluster kernel in the tcgen05
   // precisions. BATCH_COMPAT (Q6) couples every stream of the batch at every frame and stays on the per-frame path, as does
   // an utterance long enough to meet the 1000-symbol cap of the single-stream loop (ref OfflineRecognizer.cs:122).
-  if (h->cfg.precision != K2B_PREC_FP32 && mode != K2B_GREEDY_BATCH_COMPAT && cluster_path_supported(h, 1) && T > 0 && T <= 1000)
+  const bool as_beam1 = h->cfg.precision != K2B_PREC_FP32 && mode != K2B_GREEDY_BATCH_COMPAT && T > 0 && T <= 1000;
+  if (as_beam1 && cluster_path_supported(h, 1) && !prefer_persistent_greedy(h, B))
     return beam_cluster_path(h, enc, enc_is_raw, B, T, 1, tokens, ts, n_out, nullptr, cap);
   const float* frames = nullptr;
   K2B_TRY(frames_for_search(h, enc, enc_is_raw, B, T, &frames));
+  if (as_beam1 && beam_greedy_usable(h)) {           // large vocabulary: beam 1 on the persistent beam kernel
+    K2B_TRY(ensure(h, h->ws_misc, sizeof(float) * (size_t)B));
+    return beam_dev(h, frames, B, T, 1, tokens, ts, n_out, static_cast<float*>(h->ws_misc.p), cap);
+  }
   return greedy_dev(h, frames, B, T, mode, false, nullptr, tokens, ts, n_out, cap);
 }
 
@@ -657,10 +671,15 @@ int32_t k2b_greedy_online_chunk_dev(k2b_handle* h, const float* enc, int32_t enc
   K2B_TRY(check_search_args(h, enc, B, Tc, cap, tokens, ts, n_out, "k2b_greedy_online_chunk"));
   if (B > 0 && hyp_inout == nullptr) return fail(h, K2B_ERR_INVALID, "k2b_greedy_online_chunk: hyp_inout is NULL");
   if (B == 0) return K2B_OK;
-  if (h->cfg.precision != K2B_PREC_FP32 && cluster_path_supported(h, 1) && Tc > 0)   // online: Q6 is a no-op (ctx == list tail)
+  const bool as_beam1 = h->cfg.precision != K2B_PREC_FP32 && Tc > 0;                  // online: Q6 is a no-op (ctx == list tail)
+  if (as_beam1 && cluster_path_supported(h, 1) && !prefer_persistent_greedy(h, B))
     return beam_cluster_path(h, enc, enc_is_raw, B, Tc, 1, tokens, ts, n_out, nullptr, cap, 1, hyp_inout);
   const float* frames = nullptr;
   K2B_TRY(frames_for_search(h, enc, enc_is_raw, B, Tc, &frames));
+  if (as_beam1 && beam_greedy_usable(h)) {
+    K2B_TRY(ensure(h, h->ws_misc, sizeof(float) * (size_t)B));
+    return beam_dev(h, frames, B, Tc, 1, tokens, ts, n_out, static_cast<float*>(h->ws_misc.p), cap, 1, hyp_inout);
+  }
   return greedy_dev(h, frames, B, Tc, K2B_GREEDY_BATCH_COMPAT, true, hyp_inout, tokens, ts, n_out, cap);
 }
 

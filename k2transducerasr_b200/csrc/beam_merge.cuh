@@ -50,7 +50,8 @@ __device__ __forceinline__ float funkey_s(int k) { return __int_as_float(k ^ ((k
 //      as the bf16 hi / lo tile images the joiner's loader warp fetches.
 // part_rec [N, nt, kBeamRecWords<KB>] is what joiner_topk_kernel<KB> writes.
 // Everything another CTA may have produced during the same launch (partials, state) is read with ld.global.cg.
-// KB = 4 or 8: compile-time bound of the beam (the step is latency-bound and most of its instructions are executed once, so its
+// mask3: a third non-emitting id (the literal 1 of ref OnlineRecognizer.cs:181), or -1.
+// KB = 1, 4 or 8: compile-time bound of the beam (the step is latency-bound and most of its instructions are executed once, so its
 // code size is its run time: loops are unrolled to exactly KB levels). c_v / c_f [KB*KB] and s_ctx [2*KB] are shared scratch.
 // the next frame's encoder values of thread tid's first operand item (8 consecutive k of hypothesis tid / (J/8)): they do not depend
 // on the search, so the callers fetch them before they wait
@@ -67,7 +68,7 @@ __device__ __forceinline__ void beam_merge_prefetch(int tid, int s, int K, int J
 
 template <int KB>
 __device__ __forceinline__ void beam_merge_stream(
-    int tid, int bar_id, int s, int K, int V, int nt, int T, int t, int blank, int unk, const float* part_rec,
+    int tid, int bar_id, int s, int K, int V, int nt, int T, int t, int blank, int unk, int mask3, const float* part_rec,
     const BeamState& in, const BeamState& out, int32_t* bp, const int32_t* lens,
     const float* dec_tab, const float* enc_next, long long enc_stride, int J, uint8_t* x_img, float4 pe0, float4 pe1, float* c_v,
     int* c_f,
@@ -253,7 +254,7 @@ __device__ __forceinline__ void beam_merge_stream(
       if (cand) {
         const int y = my_f - par * V;
         hs = ph; ln = pl; c0 = pc0; c1 = pc1;
-        if (y != blank && y != unk) {      // ys unchanged for blank / unk
+        if (y != blank && y != unk && y != mask3) {      // ys unchanged for blank / unk (/ the literal 1 of the online loop)
           tok = y;
           hs = hash_push(hs, y);
           ln += 1;

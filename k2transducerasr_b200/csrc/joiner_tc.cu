@@ -58,7 +58,7 @@ struct JArgs {
   long long* dbg;
   long long* tl;             // diagnostic timeline of this launch: [sm][8] clock64 stamps (slots 0..3), or null
   // MEGA: the whole search
-  int B, V, T, blank, unk, J;
+  int B, V, T, blank, unk, mask3, J;
   BeamState st[2];           // frame t reads st[t & 1], writes st[(t & 1) ^ 1]
   int32_t* bp;
   const int32_t* lens;
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
         sin.len = odd ? a.st[1].len : a.st[0].len; sout.len = odd ? a.st[0].len : a.st[1].len;
         sin.hash = odd ? a.st[1].hash : a.st[0].hash; sout.hash = odd ? a.st[0].hash : a.st[1].hash;
         sin.nlive = odd ? a.st[1].nlive : a.st[0].nlive; sout.nlive = odd ? a.st[0].nlive : a.st[1].nlive;
-        beam_merge_stream<KK>(mtid, 2, s, a.topk, a.V, a.ntn, a.T, t, a.blank, a.unk, a.part_rec,
+        beam_merge_stream<KK>(mtid, 2, s, a.topk, a.V, a.ntn, a.T, t, a.blank, a.unk, a.mask3, a.part_rec,
                               sin, sout, a.bp, a.lens, a.dec_tab, enc_next, a.enc_stride, a.J, a.x_img, pe0, pe1,
                               mg_v, mg_f, mg_ctx, (tlm != nullptr && t < 40 && s == blockIdx.x) ? tlm + 640 + t * 8 : nullptr);
         if (t + 1 < a.T) {                                // publish: one more stream of (frame t + 1, row tile) has its operand rows
@@ -487,17 +487,18 @@ int32_t joiner_topk_tc(k2b_handle* h, const uint8_t* x_img, int M, int topk, flo
   a.status = h->dev_status + 1;
   a.dbg = h->cluster_timing;
   a.tl = h->timeline != nullptr ? h->timeline + (size_t)(h->timeline_frame % 64) * 148 * 8 : nullptr;
-  return topk <= 4 ? launch_as<4, false>(h, a) : launch_as<8, false>(h, a);
+  return topk == 1 ? launch_as<1, false>(h, a) : topk <= 4 ? launch_as<4, false>(h, a) : launch_as<8, false>(h, a);
 }
 
 
 // ---- the whole modified_beam_search time loop in one launch (memoised decoder, K in {2, 4, 8}) --------------------------------
 bool beam_mega_usable(const k2b_handle* h, int K) {
   const bool off = getenv("K2B_NO_MEGA") != nullptr;       // read per call: tests compare the two engines in one process
-  return !off && (K == 2 || K == 4 || K == 8) && joiner_topk_usable(h, K) && h->dec_tab != nullptr;
+  return !off && (K == 1 || K == 2 || K == 4 || K == 8) && joiner_topk_usable(h, K) && h->dec_tab != nullptr;
 }
 
-int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8_t* x_img, float* part_rec, const BeamStatePtrs& s0, const BeamStatePtrs& s1, int32_t* bp, const int32_t* lens) {
+int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8_t* x_img, float* part_rec, const BeamStatePtrs& s0,
+                     const BeamStatePtrs& s1, int32_t* bp, const int32_t* lens, int mask3) {
   const int M = B * K;
   JArgs a = {};
   a.a_img = x_img; a.x_img = x_img; a.w_hi_img = h->wj_hi_img; a.w_lo_img = h->wj_lo_img; a.bias = h->out_b;
@@ -506,7 +507,7 @@ int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8
   a.nvalid = h->cfg.vocab_size; a.topk = K;
   a.part_rec = part_rec;
   a.status = h->dev_status + 1;
-  a.B = B; a.V = h->cfg.vocab_size; a.T = T; a.blank = h->cfg.blank_id; a.unk = h->cfg.unk_id; a.J = h->cfg.joiner_dim;
+  a.B = B; a.V = h->cfg.vocab_size; a.T = T; a.blank = h->cfg.blank_id; a.unk = h->cfg.unk_id; a.mask3 = mask3; a.J = h->cfg.joiner_dim;
   a.st[0] = BeamState{s0.ctx, s0.lp, s0.len, reinterpret_cast<uint64_t*>(s0.hash), s0.nlive};
   a.st[1] = BeamState{s1.ctx, s1.lp, s1.len, reinterpret_cast<uint64_t*>(s1.hash), s1.nlive};
   a.bp = bp; a.lens = lens; a.dec_tab = h->dec_tab; a.enc = enc; a.enc_stride = (long long)T * a.J;
@@ -517,10 +518,10 @@ int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8
   a.ready = a.done + (size_t)T * a.ntm;
   a.abort_flag = a.ready + (size_t)(T + 1) * a.ntm;
   a.tl = h->timeline;
-  return K <= 4 ? launch_as<4, true>(h, a) : launch_as<8, true>(h, a);
+  return K == 1 ? launch_as<1, true>(h, a) : K <= 4 ? launch_as<4, true>(h, a) : launch_as<8, true>(h, a);
 }
 
 
-int beam_partial_words(int topk) { return topk <= 4 ? kBeamRecWords<4> : kBeamRecWords<8>; }
+int beam_partial_words(int topk) { return topk == 1 ? kBeamRecWords<1> : topk <= 4 ? kBeamRecWords<4> : kBeamRecWords<8>; }
 
 }  // namespace k2b

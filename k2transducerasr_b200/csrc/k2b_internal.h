@@ -197,8 +197,11 @@ int32_t ctc_greedy_dev(k2b_handle* h, const float* logp, int B, int T, int V, in
 // ---- search.cu ---------------------------------------------------------------------------------
 int32_t greedy_dev(k2b_handle* h, const float* enc, int B, int T, int mode, bool online,
                    int64_t* hyp_inout, int64_t* tokens, int32_t* ts, int32_t* n_out, int cap);
+// extra_mask / hyp_inout: greedy search as beam 1 (the literal-1 mask and OnlineStream.Hyp of the online loop); only the engines
+// built on beam_merge_stream implement them - beam_dev fails with K2B_ERR_UNSUPPORTED otherwise (beam_greedy_usable tells)
 int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* tokens, int32_t* ts,
-                 int32_t* n_out, float* score, int cap);
+                 int32_t* n_out, float* score, int cap, int extra_mask = -1, int64_t* hyp_inout = nullptr);
+bool beam_greedy_usable(k2b_handle* h);
 
 int32_t beam_backtrace_dev(k2b_handle* h, int B, int K, int T, const float* lp, const int32_t* len, const int32_t* nlive,
                            const int32_t* bp, int64_t* tokens, int32_t* ts, int32_t* n_out, float* score, int cap);
@@ -243,7 +246,8 @@ int beam_partial_words(int topk);      // floats per (row, tile) record of joine
 struct BeamStatePtrs { int32_t* ctx; float* lp; int32_t* len; unsigned long long* hash; int32_t* nlive; };
 constexpr int32_t kMegaUnavailable = 0x4d454741;   // beam_mega_tc: the cooperative launch does not fit; nothing was enqueued
 bool beam_mega_usable(const k2b_handle* h, int K);
-int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8_t* x_img, float* part_rec, const BeamStatePtrs& s0, const BeamStatePtrs& s1, int32_t* bp, const int32_t* lens);
+int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8_t* x_img, float* part_rec, const BeamStatePtrs& s0,
+                     const BeamStatePtrs& s1, int32_t* bp, const int32_t* lens, int mask3);
 
 // profiling bracket around the dominant GEMM
 void prof_begin(k2b_handle* h);

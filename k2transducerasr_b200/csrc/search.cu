@@ -316,7 +316,7 @@ beam_select_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk
 // joinin_table_kernel; one launch and one round trip of the contexts through HBM less.
 template <int KB>
 __global__ void __launch_bounds__(128)
-beam_step_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
+beam_step_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk, int mask3,
                  const float* __restrict__ part_rec,
                  BeamState in, BeamState out, int32_t* __restrict__ bp, const int32_t* __restrict__ lens,
                  const float* __restrict__ dec_tab, const float* __restrict__ enc_next, long long enc_stride, int J,
@@ -336,7 +336,7 @@ beam_step_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
   }
   k2b::ptx::griddep_wait();
   if (tl != nullptr && tid == 0) atomicMin(reinterpret_cast<long long*>(tl + 5), clock64());
-  beam_merge_stream<KB>(tid, 1, s, K, V, nt, T, t, blank, unk, part_rec, in, out, bp, lens, dec_tab, enc_next, enc_stride, J, x_img,
+  beam_merge_stream<KB>(tid, 1, s, K, V, nt, T, t, blank, unk, mask3, part_rec, in, out, bp, lens, dec_tab, enc_next, enc_stride, J, x_img,
                         pe0, pe1, c_v, c_f, s_ctx, tl);
 }
 
@@ -473,8 +473,32 @@ int32_t greedy_dev(k2b_handle* h, const float* enc, int B, int T, int mode, bool
   return K2B_OK;
 }
 
+namespace {
+// beam 1 as online greedy: slot 0's context comes from / goes back to OnlineStream.Hyp (ref OnlineRecognizer.cs:109,125,208)
+__global__ void beam_ctx_from_hyp_kernel(int B, const int64_t* __restrict__ hyp, int32_t* __restrict__ ctx) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  ctx[2 * b] = (int32_t)hyp[2 * b];
+  ctx[2 * b + 1] = (int32_t)hyp[2 * b + 1];
+}
+__global__ void beam_hyp_from_ctx_kernel(int B, const int32_t* __restrict__ ctx, int64_t* __restrict__ hyp) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  hyp[2 * b] = ctx[2 * b];
+  hyp[2 * b + 1] = ctx[2 * b + 1];
+}
+}  // namespace
+
+// greedy search as beam 1 on the persistent kernel: needs the tcgen05 precisions and the memoised decoder table
+bool beam_greedy_usable(k2b_handle* h) {
+  if (h->cfg.precision == K2B_PREC_FP32 || !joiner_tc_supported(h) || !decoder_tc_supported(h)) return false;
+  bool have = false;
+  if (ensure_dec_table(h, &have) != K2B_OK) return false;
+  return have && beam_mega_usable(h, 1);
+}
+
 int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* tokens, int32_t* ts, int32_t* n_out,
-                 float* score, int cap) {
+                 float* score, int cap, int extra_mask, int64_t* hyp_inout) {
   const k2b_config& c = h->cfg;
   const int J = c.joiner_dim, V = c.vocab_size, D = c.decoder_dim;
   const bool tc = c.precision != K2B_PREC_FP32 && joiner_tc_supported(h);   // per-frame tcgen05 joiner (256-column tiles)
@@ -505,6 +529,19 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
 
   beam_init_kernel<<<(N + 127) / 128, 128, 0, h->stream>>>(B, K, c.blank_id, st[0], st[1]);
   K2B_LAUNCH_CHECK(h);
+  const bool greedy_ext = extra_mask >= 0 || hyp_inout != nullptr;
+  if (greedy_ext && K != 1) return fail(h, K2B_ERR_INVALID, "beam_dev: mask / Hyp are beam-1 (greedy) options");
+  if (hyp_inout != nullptr) {
+    beam_ctx_from_hyp_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(B, hyp_inout, st[0].ctx);
+    K2B_LAUNCH_CHECK(h);
+  }
+  auto finish = [&](int fin) -> int32_t {
+    if (hyp_inout != nullptr) {
+      beam_hyp_from_ctx_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(B, st[fin].ctx, hyp_inout);
+      K2B_LAUNCH_CHECK(h);
+    }
+    return beam_backtrace_dev(h, B, K, T, st[fin].lp, st[fin].len, st[fin].nlive, bp, tokens, ts, n_out, score, cap);
+  };
 
   int cur = 0;
   // memoised decoder + persistent joiner: two launches per frame (joiner, fused merge + next operand), chained by programmatic
@@ -519,12 +556,11 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
         sp[i] = BeamStatePtrs{st[i].ctx, st[i].lp, st[i].len, reinterpret_cast<unsigned long long*>(st[i].hash), st[i].nlive};
       prof_begin(h);
       const int32_t ms = beam_mega_tc(h, enc, B, T, K, ximg, part_m, sp[0], sp[1], bp,
-                                      h->lens_active ? h->lens_dev : nullptr);
+                                      h->lens_active ? h->lens_dev : nullptr, extra_mask);
       prof_end(h);
       if (ms != kMegaUnavailable) {
         K2B_TRY(ms);
-        cur = T & 1;
-        return beam_backtrace_dev(h, B, K, T, st[cur].lp, st[cur].len, st[cur].nlive, bp, tokens, ts, n_out, score, cap);
+        return finish(T & 1);
       }
     }
     for (int t = 0; t < T; ++t) {
@@ -532,8 +568,8 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
       K2B_TRY(joiner_topk_tc(h, ximg, N, K, part_m));
       if (h->prof_which == 0) prof_end(h);
       if (h->prof_which == 2) prof_begin(h);
-      K2B_CUDA(h, launch_pdl(K <= 4 ? beam_step_kernel<4> : beam_step_kernel<8>, dim3(B), dim3(128), 0, h->stream, B, K, V, nt, T, t,
-                              (int)c.blank_id, (int)c.unk_id,
+      K2B_CUDA(h, launch_pdl(K == 1 ? beam_step_kernel<1> : K <= 4 ? beam_step_kernel<4> : beam_step_kernel<8>, dim3(B), dim3(128), 0,
+                              h->stream, B, K, V, nt, T, t, (int)c.blank_id, (int)c.unk_id, extra_mask,
                               (const float*)part_m, st[cur], st[cur ^ 1], bp, (const int32_t*)(h->lens_active ? h->lens_dev : nullptr), (const float*)h->dec_tab,
                               (const float*)(t + 1 < T ? enc + (size_t)(t + 1) * J : nullptr), (long long)T * J, J, ximg,
                               (long long*)(h->timeline != nullptr ? h->timeline + (size_t)(h->timeline_frame % 64) * 148 * 8 : nullptr)));
@@ -542,8 +578,9 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
       if (h->prof_which == 2) prof_end(h);
       cur ^= 1;
     }
-    return beam_backtrace_dev(h, B, K, T, st[cur].lp, st[cur].len, st[cur].nlive, bp, tokens, ts, n_out, score, cap);
+    return finish(cur);
   }
+  if (greedy_ext) return fail(h, K2B_ERR_UNSUPPORTED, "beam_dev: greedy options need the memoised decoder table");
   for (int t = 0; t < T; ++t) {
     GemmArgs d;
     d.M = N; d.N = J; d.K = D;

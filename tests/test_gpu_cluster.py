@@ -403,3 +403,53 @@ def test_persistent_beam_kernel_shapes(built_lib, V, J, D, B, T, beam):
         if b not in ex:
             assert abs(float(sc[b]) - r.score) < SCORE_TOL
     h.close()
+
+
+def test_persistent_greedy_large_vocab(built_lib, monkeypatch):
+    """Greedy search as beam 1 on the persistent beam kernel: V = 5537 (no cluster fits) offline PER_STREAM / SINGLE and online
+    chunks against the oracle; V = 2000 online chunks forced onto it (K2B_GREEDY_PERSISTENT=1) against the 16-CTA cluster kernel."""
+    dims = synth.CONFIGS["cfg4"].dims
+    m, w = model_and_weights(dims, blank_bias=synth.CONFIGS["cfg4"].blank_bias)
+    h = make(dims, w, "bf16x3")
+    B, T = 21, 24
+    raw = synth.make_frames(B, T, dims.encoder_dim, 91)
+    enc = O.encoder_proj(m, raw)
+    h.greedy_offline(raw, _native.GREEDY_PER_STREAM, enc_is_raw=True)           # builds the decoder table
+    n0 = h.launch_count()
+    t, s = h.greedy_offline(raw, _native.GREEDY_PER_STREAM, enc_is_raw=True)
+    assert h.launch_count() - n0 <= 8, "the persistent kernel was not taken"
+    compare_streams(t, s, O.greedy_search_batch(m, enc, compat=False), "persistent greedy per_stream V=5537", allow_frac=0.2)
+    t1, s1 = h.greedy_offline(raw[:1], _native.GREEDY_SINGLE, enc_is_raw=True)
+    ws = O.greedy_search_single(m, enc[0])
+    assert (t1[0] == ws.appended and s1[0] == ws.timestamps) or ws.min_gap < 1e-4
+    Tc = 8
+    hyp = np.zeros((B, 2), np.int64)
+    ohyp, otoks = [[0, 0]] * B, [[0, 0]] * B
+    for c in range(3):
+        t, s, hyp = h.greedy_online_chunk(np.ascontiguousarray(raw[:, Tc * c:Tc * c + Tc]), hyp, enc_is_raw=True)
+        res = O.greedy_search_online_chunk(m, enc[:, Tc * c:Tc * c + Tc], ohyp, otoks)
+        ex = compare_streams(t, s, res, f"persistent greedy online chunk {c}", allow_frac=0.2)
+        if ex:
+            break
+        ohyp, otoks = [r.hyp for r in res], [r.tokens for r in res]
+        assert hyp.tolist() == ohyp
+    h.close()
+
+    dims = synth.CONFIGS["cfg3"].dims
+    m, w = model_and_weights(dims, blank_bias=synth.CONFIGS["cfg3"].blank_bias)
+    h = make(dims, w, "bf16x3")
+    B = 150
+    raw = synth.make_frames(B, 2 * Tc, dims.encoder_dim, 92)
+    outs = []
+    for force in ("0", "1"):
+        monkeypatch.setenv("K2B_GREEDY_PERSISTENT", force)
+        hyp = np.zeros((B, 2), np.int64)
+        got = []
+        for c in range(2):
+            t, s, hyp = h.greedy_online_chunk(np.ascontiguousarray(raw[:, Tc * c:Tc * c + Tc]), hyp, enc_is_raw=True)
+            got.append((t, s, hyp.tolist()))
+        outs.append(got)
+    monkeypatch.delenv("K2B_GREEDY_PERSISTENT")
+    same = sum(1 for b in range(B) if all(outs[0][c][0][b] == outs[1][c][0][b] and outs[0][c][1][b] == outs[1][c][1][b] for c in range(2)))
+    assert same >= B - 2, f"persistent and cluster greedy disagree on {B - same} of {B} streams"      # near ties may differ
+    h.close()
