@@ -603,10 +603,11 @@ int32_t k2b_set_encoder_out_lens(k2b_handle* h, const int64_t* lens, int32_t B) 
   return K2B_OK;
 }
 
-// Greedy search of a large vocabulary (V > 1024: sixteen-CTA clusters) runs as beam 1 either on the cluster kernel or on the
-// persistent beam kernel. The cluster kernel steps a frame in ~5.4 us but only about six 16-CTA clusters (32 streams each) are
-// co-resident, so it takes ceil(B / 192) waves; the persistent kernel steps any batch in one chain (K2B_GREEDY_PERSISTENT=0/1
-// overrides the choice for comparison runs).
+// Greedy search runs as beam 1: on the cluster kernel wherever a cluster holds the vocabulary (V <= 2048 with sixteen-CTA clusters),
+// on the persistent beam kernel beyond that - and also for 1024 < V <= 2048 when the batch needs three or more waves of 16-CTA
+// clusters (about six of them, 32 streams each, are co-resident). Measured on cfg3 (V = 2000, 512 streams, chunks of 8 frames):
+// cluster kernel 185 us per chunk, persistent kernel 147 us (its merge warps step four streams at once, greedy_merge_warp).
+// K2B_GREEDY_PERSISTENT=0/1 overrides the choice (comparison runs, tests).
 static bool prefer_persistent_greedy(k2b_handle* h, int B) {
   if (const char* e = getenv("K2B_GREEDY_PERSISTENT")) return atoi(e) != 0 && beam_greedy_usable(h);
   return h->cfg.vocab_size > 1024 && B > 384 && beam_greedy_usable(h);

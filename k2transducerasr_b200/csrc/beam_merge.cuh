@@ -347,4 +347,63 @@ __device__ __forceinline__ void beam_merge_stream(
 }
 
 
+
+// Greedy search (beam 1) frame step of stream s by ONE warp: the arg-best over the tile records of its row (value desc, index
+// desc = the reference's fold, ref OfflineRecognizer.cs:145-159), the emission test, context shift, back-pointer, and the next
+// frame's joiner operand row. With a single hypothesis the log-softmax is a constant shift of every candidate, so neither the
+// maxima nor the sums are read and the score stays 0; nothing goes through shared memory, so the four merge warps of a CTA step
+// four streams at once. part_rec [B, nt, kBeamRecWords<1>] as joiner_topk_kernel<1> writes it.
+__device__ __forceinline__ void greedy_merge_warp(int lane, int s, int V, int nt, int T, int t, int blank, int unk, int mask3,
+                                                  const float* part_rec, const BeamState& in, const BeamState& out, int32_t* bp,
+                                                  const int32_t* lens, const float* dec_tab, const float* enc_next,
+                                                  long long enc_stride, int J, uint8_t* x_img) {
+  constexpr int kNone = (int)0x80000000, RW = kBeamRecWords<1>;
+  const unsigned full = 0xffffffffu;
+  const float* rrow = part_rec + (size_t)s * nt * RW;
+  int bk = kNone, bf = -1;
+  for (int i = lane; i < nt; i += 32) {
+    const uint4 q = __ldcg(reinterpret_cast<const uint4*>(rrow + (size_t)i * RW));
+    const float v = __uint_as_float(q.z);
+    const int idx = (int)q.w;
+    const bool okc = (idx >= 0) & (v == v);
+    const int key = okc ? fkey_s(v) : kNone, f = okc ? idx : -1;
+    const bool better = (key > bk) | ((key == bk) & (f > bf));
+    bk = better ? key : bk; bf = better ? f : bf;
+  }
+  int c0 = __ldcg(in.ctx + 2 * s), c1 = __ldcg(in.ctx + 2 * s + 1), ln = __ldcg(in.len + s);
+  const bool frozen = lens != nullptr && t >= __ldg(lens + s);
+  const int wk = __reduce_max_sync(full, bk);
+  const int y = __reduce_max_sync(full, bk == wk ? bf : -1);
+  int tok = -1;
+  if (!frozen && y >= 0 && y != blank && y != unk && y != mask3) { tok = y; c0 = c1; c1 = y; ln += 1; }
+  if (lane == 0) {
+    out.ctx[2 * s] = c0; out.ctx[2 * s + 1] = c1;
+    out.lp[s] = 0.f; out.len[s] = ln; out.hash[s] = kHashSeed; out.nlive[s] = 1;
+    bp[(size_t)s * T + t] = tok + 1;
+  }
+  if (enc_next == nullptr) return;
+  constexpr int kRowTile = 128, kImgTile = 128 * 128;
+  const float* erow = enc_next + (size_t)s * enc_stride;
+  const float* drow = dec_tab + ((size_t)(c0 + 1) * V + c1) * J;
+  for (int k = lane << 3; k < J; k += 256) {
+    const float4 e0 = __ldg(reinterpret_cast<const float4*>(erow + k)), e1 = __ldg(reinterpret_cast<const float4*>(erow + k) + 1);
+    const float4 d0 = __ldg(reinterpret_cast<const float4*>(drow + k)), d1 = __ldg(reinterpret_cast<const float4*>(drow + k) + 1);
+    const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w}, dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    float x[8], hi[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {           // tanh(e + d) = 1 - 2 / (1 + exp(2e) * exp(2d)); the table holds exp(2d)
+      float r;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(expf(2.f * fminf(fmaxf(ev[i], -21.f), 21.f)), dv[i], 1.f)));
+      x[i] = fmaf(-2.f, r, 1.f);
+      hi[i] = k2b::ptx::bf16_round(x[i]);
+    }
+    uint8_t* timg = x_img + ((size_t)(s / kRowTile) * (J / 64) + (k >> 6)) * (2 * kImgTile) + k2b::ptx::sw128_offset(s % kRowTile, k & 63);
+    *reinterpret_cast<uint4*>(timg) = make_uint4(k2b::ptx::pack_bf16x2(hi[0], hi[1]), k2b::ptx::pack_bf16x2(hi[2], hi[3]),
+                                                 k2b::ptx::pack_bf16x2(hi[4], hi[5]), k2b::ptx::pack_bf16x2(hi[6], hi[7]));
+    *reinterpret_cast<uint4*>(timg + kImgTile) =
+        make_uint4(k2b::ptx::pack_bf16x2(x[0] - hi[0], x[1] - hi[1]), k2b::ptx::pack_bf16x2(x[2] - hi[2], x[3] - hi[3]),
+                   k2b::ptx::pack_bf16x2(x[4] - hi[4], x[5] - hi[5]), k2b::ptx::pack_bf16x2(x[6] - hi[6], x[7] - hi[7]));
+  }
+}
+
 }  // namespace k2b

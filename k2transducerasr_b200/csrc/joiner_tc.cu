@@ -306,6 +306,7 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
       float mx = any ? __int_as_float(mk ^ ((mk >> 31) & 0x7fffffff)) : -INFINITY;
       const float mneg = any ? -mx * 1.4426950408889634f : 0.f;
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      if constexpr (KK > 1)                               // beam 1 (greedy): the log-softmax is a constant shift, nobody reads the sum
 #pragma unroll 8
       for (int j = cbeg; j < cbeg + kCols; j += 4) {
         float e0, e1, e2, e3;
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(fmaf(myrow[j + 3], 1.4426950408889634f, mneg)));
         s0 += e0; s1 += e1; s2 += e2; s3 += e3;
       }
-      float sum = any ? (s0 + s1) + (s2 + s3) : 0.f;
+      float sum = any ? (KK > 1 ? (s0 + s1) + (s2 + s3) : 1.f) : 0.f;     // beam 1: any positive constant (see above)
       if (tlm != nullptr && tid == 64 && t < 40 && tile == blockIdx.x) tlm[t * 16 + 11] = clock64();
       float tv[KK];
 #pragma unroll
@@ -395,6 +396,34 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
   else if (MEGA) {
     // ---- merge warps: hypothesis merge + next operand of this CTA's streams, frame by frame -------------------------------------
     const int mtid = tid - (64 + EW * 32);
+    if constexpr (KK == 1) {
+      // greedy (beam 1): a warp steps a stream on its own - the CTA's streams are dealt to its four merge warps
+      const int mw = mtid >> 5;
+      for (int t = 0; t < nframes && ok; ++t) {
+        const float* enc_next = t + 1 < a.T ? a.enc + (size_t)(t + 1) * a.J : nullptr;
+        const bool odd = (t & 1) != 0;
+        BeamState sin, sout;
+        sin.ctx = odd ? a.st[1].ctx : a.st[0].ctx; sout.ctx = odd ? a.st[0].ctx : a.st[1].ctx;
+        sin.lp = odd ? a.st[1].lp : a.st[0].lp; sout.lp = odd ? a.st[0].lp : a.st[1].lp;
+        sin.len = odd ? a.st[1].len : a.st[0].len; sout.len = odd ? a.st[0].len : a.st[1].len;
+        sin.hash = odd ? a.st[1].hash : a.st[0].hash; sout.hash = odd ? a.st[0].hash : a.st[1].hash;
+        sin.nlive = odd ? a.st[1].nlive : a.st[0].nlive; sout.nlive = odd ? a.st[0].nlive : a.st[1].nlive;
+        for (int s = blockIdx.x + mw * gridDim.x; s < a.B && ok; s += 4 * gridDim.x) {
+          const int r = s / spr;
+          int good = 1;
+          if (lane == 0) good = wait_count(a.done + (size_t)t * a.ntm + r, a.ntn, a.abort_flag) ? 1 : 0;
+          good = __shfl_sync(0xffffffffu, good, 0);
+          if (!good) { ok = false; break; }
+          greedy_merge_warp(lane, s, a.V, a.ntn, a.T, t, a.blank, a.unk, a.mask3, a.part_rec, sin, sout, a.bp, a.lens, a.dec_tab,
+                            enc_next, a.enc_stride, a.J, a.x_img);
+          if (t + 1 < a.T) {
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) red_release_gpu(a.ready + (size_t)(t + 1) * a.ntm + r, 1);
+          }
+        }
+      }
+    } else
     for (int t = 0; t < nframes && ok; ++t) {
       const float* enc_next = t + 1 < a.T ? a.enc + (size_t)(t + 1) * a.J : nullptr;
       for (int s = blockIdx.x; s < a.B && ok; s += gridDim.x) {
@@ -443,7 +472,9 @@ int32_t launch_as(k2b_handle* h, const JArgs& a) {
     attr_set = true;
   }
   const int tiles = a.ntm * a.ntn;
-  const int grid = tiles < h->sm_count ? tiles : h->sm_count;
+  // MEGA: CTAs beyond the tile count still merge their share of the streams
+  const int want = MEGA && a.B > tiles ? a.B : tiles;
+  const int grid = want < h->sm_count ? want : h->sm_count;
   if (MEGA) {
     // every CTA waits for counters other CTAs publish: all of them must be resident at once (cooperative launch checks that)
     cudaLaunchConfig_t cfg = {};

@@ -419,6 +419,10 @@ def test_persistent_greedy_large_vocab(built_lib, monkeypatch):
     t, s = h.greedy_offline(raw, _native.GREEDY_PER_STREAM, enc_is_raw=True)
     assert h.launch_count() - n0 <= 8, "the persistent kernel was not taken"
     compare_streams(t, s, O.greedy_search_batch(m, enc, compat=False), "persistent greedy per_stream V=5537", allow_frac=0.2)
+    monkeypatch.setenv("K2B_NO_MEGA", "1")            # the same search as one joiner + one merge launch per frame
+    tp, sp = h.greedy_offline(raw, _native.GREEDY_PER_STREAM, enc_is_raw=True)
+    monkeypatch.delenv("K2B_NO_MEGA")
+    assert tp == t and sp == s
     t1, s1 = h.greedy_offline(raw[:1], _native.GREEDY_SINGLE, enc_is_raw=True)
     ws = O.greedy_search_single(m, enc[0])
     assert (t1[0] == ws.appended and s1[0] == ws.timestamps) or ws.min_gap < 1e-4
