@@ -474,6 +474,46 @@ int32_t greedy_dev(k2b_handle* h, const float* enc, int B, int T, int mode, bool
 }
 
 namespace {
+// First launch of the fused path, one CTA per hypothesis row: the initial hypothesis state (beam_init_kernel), the context from
+// OnlineStream.Hyp for online greedy, and the joiner operand row of frame 0 (joinin_table_kernel) - three launches in one.
+__global__ void beam_start_kernel(int B, int K, int V, int J, int blank, const int64_t* __restrict__ hyp, BeamState s0, BeamState s1,
+                                  const float* __restrict__ dec_tab, const float* __restrict__ enc, long long enc_stride,
+                                  uint8_t* __restrict__ x_img) {
+  const int m = blockIdx.x, b = m / K, slot = m - b * K;
+  int c0 = -1, c1 = blank;
+  if (hyp != nullptr && slot == 0) { c0 = (int)hyp[2 * b]; c1 = (int)hyp[2 * b + 1]; }
+  if (threadIdx.x == 0) {
+    s0.ctx[2 * m] = c0; s0.ctx[2 * m + 1] = c1;
+    s1.ctx[2 * m] = -1; s1.ctx[2 * m + 1] = blank;
+    s0.lp[m] = slot == 0 ? 0.f : -INFINITY;
+    s0.len[m] = 2;
+    s0.hash[m] = kHashSeed;
+    if (slot == 0) s0.nlive[b] = 1;
+  }
+  constexpr int kRowTile = 128, kImgTile = 128 * 128;
+  const float* erow = enc + (size_t)b * enc_stride;
+  const float* drow = dec_tab + ((size_t)(c0 + 1) * V + c1) * J;
+  for (int k = threadIdx.x << 3; k < J; k += blockDim.x << 3) {
+    const float4 e0 = __ldg(reinterpret_cast<const float4*>(erow + k)), e1 = __ldg(reinterpret_cast<const float4*>(erow + k) + 1);
+    const float4 d0 = __ldg(reinterpret_cast<const float4*>(drow + k)), d1 = __ldg(reinterpret_cast<const float4*>(drow + k) + 1);
+    const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w}, dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    float x[8], hi[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {           // tanh(e + d) = 1 - 2 / (1 + exp(2e) * exp(2d)); the table holds exp(2d)
+      float r;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(expf(2.f * fminf(fmaxf(ev[i], -21.f), 21.f)), dv[i], 1.f)));
+      x[i] = fmaf(-2.f, r, 1.f);
+      hi[i] = k2b::ptx::bf16_round(x[i]);
+    }
+    uint8_t* timg = x_img + ((size_t)(m / kRowTile) * (J / 64) + (k >> 6)) * (2 * kImgTile) + k2b::ptx::sw128_offset(m % kRowTile, k & 63);
+    *reinterpret_cast<uint4*>(timg) = make_uint4(k2b::ptx::pack_bf16x2(hi[0], hi[1]), k2b::ptx::pack_bf16x2(hi[2], hi[3]),
+                                                 k2b::ptx::pack_bf16x2(hi[4], hi[5]), k2b::ptx::pack_bf16x2(hi[6], hi[7]));
+    *reinterpret_cast<uint4*>(timg + kImgTile) =
+        make_uint4(k2b::ptx::pack_bf16x2(x[0] - hi[0], x[1] - hi[1]), k2b::ptx::pack_bf16x2(x[2] - hi[2], x[3] - hi[3]),
+                   k2b::ptx::pack_bf16x2(x[4] - hi[4], x[5] - hi[5]), k2b::ptx::pack_bf16x2(x[6] - hi[6], x[7] - hi[7]));
+  }
+}
+
 // beam 1 as online greedy: slot 0's context comes from / goes back to OnlineStream.Hyp (ref OnlineRecognizer.cs:109,125,208)
 __global__ void beam_ctx_from_hyp_kernel(int B, const int64_t* __restrict__ hyp, int32_t* __restrict__ ctx) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -527,13 +567,21 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
   int32_t* bp = static_cast<int32_t*>(h->ws_bp.p);
   float* x = static_cast<float*>(h->ws_x.p);
 
-  beam_init_kernel<<<(N + 127) / 128, 128, 0, h->stream>>>(B, K, c.blank_id, st[0], st[1]);
-  K2B_LAUNCH_CHECK(h);
   const bool greedy_ext = extra_mask >= 0 || hyp_inout != nullptr;
   if (greedy_ext && K != 1) return fail(h, K2B_ERR_INVALID, "beam_dev: mask / Hyp are beam-1 (greedy) options");
-  if (hyp_inout != nullptr) {
-    beam_ctx_from_hyp_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(B, hyp_inout, st[0].ctx);
+  static const bool unfused = getenv("K2B_UNFUSED_STEP") != nullptr;
+  const bool fused = tc && have_tab && ximg != nullptr && !unfused && joiner_topk_usable(h, K) && T > 0;
+  if (fused) {              // state, Hyp and the operand of frame 0 in one launch
+    K2B_TRY(ensure_joiner_assets(h));
+    beam_start_kernel<<<N, 64, 0, h->stream>>>(B, K, V, J, c.blank_id, hyp_inout, st[0], st[1], h->dec_tab, enc, (long long)T * J, ximg);
     K2B_LAUNCH_CHECK(h);
+  } else {
+    beam_init_kernel<<<(N + 127) / 128, 128, 0, h->stream>>>(B, K, c.blank_id, st[0], st[1]);
+    K2B_LAUNCH_CHECK(h);
+    if (hyp_inout != nullptr) {
+      beam_ctx_from_hyp_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(B, hyp_inout, st[0].ctx);
+      K2B_LAUNCH_CHECK(h);
+    }
   }
   auto finish = [&](int fin) -> int32_t {
     if (hyp_inout != nullptr) {
@@ -546,10 +594,7 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
   int cur = 0;
   // memoised decoder + persistent joiner: two launches per frame (joiner, fused merge + next operand), chained by programmatic
   // dependent launches. K2B_UNFUSED_STEP=1 keeps the three-launch sequence below (comparison runs).
-  static const bool unfused = getenv("K2B_UNFUSED_STEP") != nullptr;
-  if (tc && have_tab && ximg != nullptr && !unfused && joiner_topk_usable(h, K) && T > 0) {
-    K2B_TRY(ensure_joiner_assets(h));
-    K2B_TRY(joinin_table_tc(h, st[0].ctx, N, enc, (long long)T * J, K, ximg));
+  if (fused) {
     if (beam_mega_usable(h, K) && !(h->profile_on && h->prof_which != 0)) {       // the whole time loop in one launch
       BeamStatePtrs sp[2];
       for (int i = 0; i < 2; ++i)
