@@ -38,10 +38,18 @@ using namespace ptx;
 
 constexpr int kJM = 128, kJNc = 160, kJBK = 64, kStages = 2;
 constexpr int kATile = kJM * 128;                          // 16 KB: 128 rows x 64 bf16
-constexpr int kWTile = kJNc * 128;                          // 20 KB
-constexpr int kStageBytes = 2 * kATile + 2 * kWTile;      // 72 KB
-constexpr int kTS = kJNc + 1;                               // row stride of the fp32 scratch rows (conflict-free across rows)
-constexpr int kTileBytes = kJM * kTS * 4;
+// kJNc is the width of the packed weight image's tiles; a kernel instantiation works on BN = 160 or 80 columns (an 80-column tile
+// is one contiguous half of every 160-row image block): the narrow one doubles the number of tiles when there are too few of them
+// to occupy the SMs (cfg3: 4 x 13 wide tiles), halving the GEMM and epilogue latency of the frame chain
+template <int BN> struct Tile {
+  static constexpr int kWTile = BN * 128;                          // 20 KB / 10 KB
+  static constexpr int kStageBytes = 2 * kATile + 2 * kWTile;      // 72 KB / 52 KB
+  static constexpr int kTS = BN + 1;                               // row stride of the fp32 scratch rows (conflict-free across rows)
+  static constexpr int kTileBytes = kJM * kTS * 4;
+};
+__device__ __forceinline__ size_t w_image_offset(int col0, int nkb, int kb) {      // byte offset of rows col0.. of k-block kb
+  return (((size_t)(col0 / kJNc) * nkb + kb) * kJNc + (size_t)(col0 % kJNc)) * 128;
+}
 constexpr int kEpiWarps = 8;                             // epilogue warps per CTA (4: one thread per row; 8: two column halves)
 constexpr int kAccCols = 256;                             // TMEM column distance of the two accumulators
 constexpr int kNoneKey = (int)0x80000000;
@@ -103,12 +111,13 @@ __device__ __forceinline__ void push_key(int (&a)[KK], int t) {
   }
 }
 
-template <int KK, bool MEGA, int EW>
+template <int KK, bool MEGA, int EW, int BN>
 __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_topk_kernel(const JArgs a) {
+  constexpr int kWTile = Tile<BN>::kWTile, kStageBytes = Tile<BN>::kStageBytes, kTS = Tile<BN>::kTS;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full[kStages], empty[kStages], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(16) float bias_t[kJNc];
+  __shared__ __align__(16) float bias_t[BN];
   __shared__ float mg_v[MEGA ? KK * KK : 1];
   __shared__ int mg_f[MEGA ? KK * KK : 1], mg_ctx[MEGA ? 2 * KK : 1];
   const int nframes = MEGA ? a.T : 1;
@@ -161,7 +170,7 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
               const uint32_t ph = (kc / kStages) & 1u;
               if (!mbar_wait(&empty[s], ph ^ 1u)) ok = false;
               uint8_t* st = smem + (size_t)s * kStageBytes;
-              const size_t off = ((size_t)tile_n * nkb) * kWTile;
+              const size_t off = w_image_offset(tile_n * BN, nkb, 0);
               mbar_expect_tx(&full[s], w_bytes + a_bytes);
               tma_bulk_g2s(st + 2 * kATile, a.w_hi_img + off, kWTile, &full[s]);
               if (x3) tma_bulk_g2s(st + 2 * kATile + kWTile, a.w_lo_img + off, kWTile, &full[s]);
@@ -177,7 +186,7 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
             uint8_t* st = smem + (size_t)s * kStageBytes;
             if (!(w_ahead && kb == 0)) {
               if (!mbar_wait(&empty[s], ph ^ 1u)) ok = false;
-              const size_t off = ((size_t)tile_n * nkb + kb) * kWTile;
+              const size_t off = w_image_offset(tile_n * BN, nkb, kb);
               mbar_expect_tx(&full[s], w_bytes + a_bytes);
               tma_bulk_g2s(st + 2 * kATile, a.w_hi_img + off, kWTile, &full[s]);
               if (x3) tma_bulk_g2s(st + 2 * kATile + kWTile, a.w_lo_img + off, kWTile, &full[s]);
@@ -191,7 +200,7 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
   } else if (warp_u == 1) {
     // ---- MMA issuer ----------------------------------------------------------------------------------------------------
     const uint32_t el = elect_one();
-    const uint32_t idesc = umma_idesc_bf16_f32(kJM, kJNc);
+    const uint32_t idesc = umma_idesc_bf16_f32(kJM, BN);
     const uint32_t desc_hi = 64u | (1u << 14) | (2u << 29);
     uint32_t kc = 0;
     int it = 0;
@@ -234,7 +243,7 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
     // ---- epilogue: thread = logits row (EW = 4) or one 80-column half of it (EW = 8) ------------------------------------------
     const int lg = warp & 3;                              // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;                     // column half of this warp (always 0 when EW = 4)
-    constexpr int kCols = kJNc * 4 / EW;                  // columns per thread: 160 or 80
+    constexpr int kCols = BN * 4 / EW;                    // columns per thread: 160, 80 or 40
     const int cbeg = half * kCols;
     const int row = lg * 32 + lane;
     const int etid = tid - 64;
@@ -250,9 +259,9 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
       const int tile_m = tile / a.ntn, tile_n = tile - tile_m * a.ntn;
       const int as = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-      const int col0 = tile_n * kJNc;
+      const int col0 = tile_n * BN;
       named_bar_sync(1, EW * 32);                         // every row is done with the previous tile's bias (and scratch records)
-      for (int c = etid; c < kJNc; c += EW * 32) bias_t[c] = col0 + c < a.nvalid ? __ldg(a.bias + col0 + c) : -INFINITY;
+      for (int c = etid; c < BN; c += EW * 32) bias_t[c] = col0 + c < a.nvalid ? __ldg(a.bias + col0 + c) : -INFINITY;
       named_bar_sync(1, EW * 32);
       if (!mbar_wait(&acc_full[as], aph)) ok = false;
       if (dbg && it == 0) c_acc = clock64();
@@ -288,12 +297,18 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
         tmem_ld_wait();
         chunk(u, c0, std::integral_constant<int, 32>{});
       }
-      if constexpr (kCols % 32 != 0) {                    // 80 = 2 x 32 + 16
+      if constexpr (kCols % 32 == 16) {                   // 80 = 2 x 32 + 16
         uint32_t u[16];
         const int c0 = cbeg + kCols - 16;
         tmem_ld16(trow + (uint32_t)c0, u);
         tmem_ld_wait();
         chunk(u, c0, std::integral_constant<int, 16>{});
+      } else if constexpr (kCols % 32 == 8) {             // 40 = 32 + 8
+        uint32_t u[8];
+        const int c0 = cbeg + kCols - 8;
+        tmem_ld8(trow + (uint32_t)c0, u);
+        tmem_ld_wait();
+        chunk(u, c0, std::integral_constant<int, 8>{});
       }
       if (tlm != nullptr && tid == 64 && t < 40 && tile == blockIdx.x) tlm[t * 16 + 10] = clock64();
       tc_fence_before();
@@ -463,12 +478,12 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
   if (warp == 0) tmem_dealloc(t_d, 512);
 }
 
-template <int KK, bool MEGA>
-int32_t launch_as(k2b_handle* h, const JArgs& a) {
+template <int KK, bool MEGA, int BN>
+int32_t launch_bn(k2b_handle* h, const JArgs& a) {
   static bool attr_set = false;
-  const size_t smem = (size_t)kStages * kStageBytes + kTileBytes;
+  const size_t smem = (size_t)kStages * Tile<BN>::kStageBytes + Tile<BN>::kTileBytes;
   if (!attr_set) {
-    K2B_CUDA(h, (cudaFuncSetAttribute(joiner_topk_kernel<KK, MEGA, kEpiWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+    K2B_CUDA(h, (cudaFuncSetAttribute(joiner_topk_kernel<KK, MEGA, kEpiWarps, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
     attr_set = true;
   }
   const int tiles = a.ntm * a.ntn;
@@ -483,17 +498,22 @@ int32_t launch_as(k2b_handle* h, const JArgs& a) {
     at[0].id = cudaLaunchAttributeCooperative;
     at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, joiner_topk_kernel<KK, MEGA, kEpiWarps>, a);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, joiner_topk_kernel<KK, MEGA, kEpiWarps, BN>, a);
     if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) {
       cudaGetLastError();                 // not all CTAs can be resident (SMs taken by another context): per-frame launches instead
       return kMegaUnavailable;
     }
     K2B_CUDA(h, e);
   } else {
-    K2B_CUDA(h, (launch_pdl(joiner_topk_kernel<KK, MEGA, kEpiWarps>, dim3(grid), dim3(64 + kEpiWarps * 32), smem, h->stream, a)));
+    K2B_CUDA(h, (launch_pdl(joiner_topk_kernel<KK, MEGA, kEpiWarps, BN>, dim3(grid), dim3(64 + kEpiWarps * 32), smem, h->stream, a)));
   }
   K2B_LAUNCH_CHECK(h);
   return K2B_OK;
+}
+
+template <int KK, bool MEGA>
+int32_t launch_as(k2b_handle* h, const JArgs& a, int bn) {
+  return bn == 80 ? launch_bn<KK, MEGA, 80>(h, a) : launch_bn<KK, MEGA, kJNc>(h, a);
 }
 
 }  // namespace
@@ -506,19 +526,30 @@ bool joiner_topk_usable(const k2b_handle* h, int topk) {
   return topk >= 1 && topk <= 8 && h->cfg.joiner_dim % kJBK == 0;
 }
 
+// Tile width for M hypothesis rows: 80 columns when the 160-column tiling leaves more than half of the SMs without a tile
+int joiner_topk_width(const k2b_handle* h, int M) {
+  const int tiles = ((M + kJM - 1) / kJM) * ((h->cfg.vocab_size + kJNc - 1) / kJNc);
+  return 2 * tiles <= h->sm_count ? 80 : kJNc;
+}
+int joiner_topk_tiles(const k2b_handle* h, int M) {
+  const int bn = joiner_topk_width(h, M);
+  return (h->cfg.vocab_size + bn - 1) / bn;
+}
+
 // x_img: the joiner operand as bf16 hi / lo tile images (joinin_table_tc / decoder_joinin_tc). Partial records per (row, 160-column
 // vocabulary tile): beam_partial_words(topk) floats each (beam_merge.cuh). The weight images must exist (ensure_joiner_assets).
 int32_t joiner_topk_tc(k2b_handle* h, const uint8_t* x_img, int M, int topk, float* part_rec) {
   JArgs a = {};
   a.a_img = x_img; a.w_hi_img = h->wj_hi_img; a.w_lo_img = h->wj_lo_img; a.bias = h->out_b;
-  a.M = M; a.ntm = (M + kJM - 1) / kJM; a.ntn = (h->cfg.vocab_size + kJNc - 1) / kJNc; a.nkb = h->cfg.joiner_dim / kJBK;
+  const int bn = joiner_topk_width(h, M);
+  a.M = M; a.ntm = (M + kJM - 1) / kJM; a.ntn = (h->cfg.vocab_size + bn - 1) / bn; a.nkb = h->cfg.joiner_dim / kJBK;
   a.x3 = h->cfg.precision == K2B_PREC_BF16 ? 0 : 1;
   a.nvalid = h->cfg.vocab_size; a.topk = topk;
   a.part_rec = part_rec;
   a.status = h->dev_status + 1;
   a.dbg = h->cluster_timing;
   a.tl = h->timeline != nullptr ? h->timeline + (size_t)(h->timeline_frame % 64) * 148 * 8 : nullptr;
-  return topk == 1 ? launch_as<1, false>(h, a) : topk <= 4 ? launch_as<4, false>(h, a) : launch_as<8, false>(h, a);
+  return topk == 1 ? launch_as<1, false>(h, a, bn) : topk <= 4 ? launch_as<4, false>(h, a, bn) : launch_as<8, false>(h, a, bn);
 }
 
 
@@ -533,7 +564,8 @@ int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8
   const int M = B * K;
   JArgs a = {};
   a.a_img = x_img; a.x_img = x_img; a.w_hi_img = h->wj_hi_img; a.w_lo_img = h->wj_lo_img; a.bias = h->out_b;
-  a.M = M; a.ntm = (M + kJM - 1) / kJM; a.ntn = (h->cfg.vocab_size + kJNc - 1) / kJNc; a.nkb = h->cfg.joiner_dim / kJBK;
+  const int bn = joiner_topk_width(h, M);
+  a.M = M; a.ntm = (M + kJM - 1) / kJM; a.ntn = (h->cfg.vocab_size + bn - 1) / bn; a.nkb = h->cfg.joiner_dim / kJBK;
   a.x3 = h->cfg.precision == K2B_PREC_BF16 ? 0 : 1;
   a.nvalid = h->cfg.vocab_size; a.topk = K;
   a.part_rec = part_rec;
@@ -549,7 +581,7 @@ int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8
   a.ready = a.done + (size_t)T * a.ntm;
   a.abort_flag = a.ready + (size_t)(T + 1) * a.ntm;
   a.tl = h->timeline;
-  return K == 1 ? launch_as<1, true>(h, a) : K <= 4 ? launch_as<4, true>(h, a) : launch_as<8, true>(h, a);
+  return K == 1 ? launch_as<1, true>(h, a, bn) : K <= 4 ? launch_as<4, true>(h, a, bn) : launch_as<8, true>(h, a, bn);
 }
 
 

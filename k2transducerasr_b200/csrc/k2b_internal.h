@@ -241,6 +241,7 @@ int32_t joiner_tc_partials(k2b_handle* h, const float* x, const uint8_t* x_img, 
 bool joiner_topk_supported(const k2b_handle* h, int topk);
 bool joiner_topk_usable(const k2b_handle* h, int topk);   // the persistent joiner will serve joiner_tc_partials(x_img, topk)
 int32_t joiner_topk_tc(k2b_handle* h, const uint8_t* x_img, int M, int topk, float* part_rec);
+int joiner_topk_tiles(const k2b_handle* h, int M);   // vocabulary tiles (= records per row) joiner_topk_tc / beam_mega_tc use for M rows
 int beam_partial_words(int topk);      // floats per (row, tile) record of joiner_topk_tc / beam_mega_tc
 
 struct BeamStatePtrs { int32_t* ctx; float* lp; int32_t* len; unsigned long long* hash; int32_t* nlive; };

@@ -542,8 +542,10 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
   const k2b_config& c = h->cfg;
   const int J = c.joiner_dim, V = c.vocab_size, D = c.decoder_dim;
   const bool tc = c.precision != K2B_PREC_FP32 && joiner_tc_supported(h);   // per-frame tcgen05 joiner (256-column tiles)
-  const int nt = tc ? joiner_tc_tiles(h) : num_vocab_tiles(V);
   const int N = B * K;
+  // vocabulary tiles per row: the fused joiner may use narrower tiles than the per-frame kernels (same buffer, sized for the larger)
+  const int nt_fused = tc ? joiner_topk_tiles(h, N) : 0;
+  const int nt = tc ? joiner_tc_tiles(h) : num_vocab_tiles(V);
   K2B_TRY(ensure(h, h->ws_x, sizeof(float) * (size_t)N * J));
   uint8_t* ximg = nullptr;
   bool have_tab = false;         // memoised decoder (fits in HBM up to V ~ 6800 at J = 512): no decoder GEMM in the loop
@@ -553,7 +555,7 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
     ximg = static_cast<uint8_t*>(h->ws_ximg.p);
   }
   // per (row, tile): four arrays of the per-frame kernels (8 + 8K bytes) or one record of the fused joiner (beam_partial_words)
-  K2B_TRY(ensure(h, h->ws_part, (size_t)N * nt * (size_t)max(8 + 8 * K, 4 * beam_partial_words(K))));
+  K2B_TRY(ensure(h, h->ws_part, (size_t)N * (size_t)max(nt * (8 + 8 * K), nt_fused * 4 * beam_partial_words(K))));
   K2B_TRY(ensure(h, h->ws_state, 2 * state_bytes(B, K)));
   K2B_TRY(ensure(h, h->ws_bp, sizeof(int32_t) * (size_t)B * (T > 0 ? T : 1) * K));
   char* p = static_cast<char*>(h->ws_state.p);
@@ -614,7 +616,7 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
       if (h->prof_which == 0) prof_end(h);
       if (h->prof_which == 2) prof_begin(h);
       K2B_CUDA(h, launch_pdl(K == 1 ? beam_step_kernel<1> : K <= 4 ? beam_step_kernel<4> : beam_step_kernel<8>, dim3(B), dim3(128), 0,
-                              h->stream, B, K, V, nt, T, t, (int)c.blank_id, (int)c.unk_id, extra_mask,
+                              h->stream, B, K, V, nt_fused, T, t, (int)c.blank_id, (int)c.unk_id, extra_mask,
                               (const float*)part_m, st[cur], st[cur ^ 1], bp, (const int32_t*)(h->lens_active ? h->lens_dev : nullptr), (const float*)h->dec_tab,
                               (const float*)(t + 1 < T ? enc + (size_t)(t + 1) * J : nullptr), (long long)T * J, J, ximg,
                               (long long*)(h->timeline != nullptr ? h->timeline + (size_t)(h->timeline_frame % 64) * 148 * 8 : nullptr)));
