@@ -1,6 +1,7 @@
 """Device-timed throughput of every BASELINE.json config (run on the GPU box). One JSON line per config.
 cfg2 is bench.py's job; here: cfg1 greedy single, cfg3 online greedy chunks, cfg4 large-vocab beam, cfg5 CTC (HBM roofline)."""
 import json
+import os
 import sys
 import time
 
@@ -79,7 +80,7 @@ for _prec3 in (("fp32", "bf16x3") if "cfg3" in which else ()):
         for c in range(C):
             h.call("k2b_greedy_online_chunk_dev", chunks[c], 1, B, Tc, hyp, tok, ts, n, Tc)
     ms = timed(run, 2, warm=1)
-    emit(config="cfg3", workload=cfg.name, mode="online greedy, 32 chunks x 8 frames, " + ("per-frame fp32 path" if _prec3 == "fp32" else "16-CTA cluster kernel per chunk, split-bf16 x3"), frames_per_s=B * Tc * C / (ms * 1e-3),
+    emit(config="cfg3", workload=cfg.name, mode="online greedy, 32 chunks x 8 frames, " + ("per-frame fp32 path" if _prec3 == "fp32" else ("16-CTA cluster kernel per chunk" if os.environ.get("K2B_GREEDY_PERSISTENT") == "0" else "persistent beam kernel as beam 1 per chunk") + ", split-bf16 x3"), frames_per_s=B * Tc * C / (ms * 1e-3),
          ms_per_32_chunks=ms, us_per_frame_step=ms * 1e3 / (Tc * C))
     h.close()
 
