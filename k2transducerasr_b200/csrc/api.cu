@@ -636,7 +636,7 @@ int32_t k2b_greedy_offline_dev(k2b_handle* h, const float* enc, int32_t enc_is_r
   K2B_TRY(frames_for_search(h, enc, enc_is_raw, B, T, &frames));
   if (as_beam1 && beam_greedy_usable(h)) {           // large vocabulary: beam 1 on the persistent beam kernel
     K2B_TRY(ensure(h, h->ws_misc, sizeof(float) * (size_t)B));
-    return beam_dev(h, frames, B, T, 1, tokens, ts, n_out, static_cast<float*>(h->ws_misc.p), cap);
+    return beam_dev(h, frames, B, T, 1, tokens, ts, n_out, static_cast<float*>(h->ws_misc.p), cap, -1, nullptr, true);
   }
   return greedy_dev(h, frames, B, T, mode, false, nullptr, tokens, ts, n_out, cap);
 }
@@ -679,7 +679,7 @@ int32_t k2b_greedy_online_chunk_dev(k2b_handle* h, const float* enc, int32_t enc
   K2B_TRY(frames_for_search(h, enc, enc_is_raw, B, Tc, &frames));
   if (as_beam1 && beam_greedy_usable(h)) {
     K2B_TRY(ensure(h, h->ws_misc, sizeof(float) * (size_t)B));
-    return beam_dev(h, frames, B, Tc, 1, tokens, ts, n_out, static_cast<float*>(h->ws_misc.p), cap, 1, hyp_inout);
+    return beam_dev(h, frames, B, Tc, 1, tokens, ts, n_out, static_cast<float*>(h->ws_misc.p), cap, 1, hyp_inout, true);
   }
   return greedy_dev(h, frames, B, Tc, K2B_GREEDY_BATCH_COMPAT, true, hyp_inout, tokens, ts, n_out, cap);
 }

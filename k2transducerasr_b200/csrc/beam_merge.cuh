@@ -352,9 +352,18 @@ __device__ __forceinline__ void beam_merge_stream(
 // desc = the reference's fold, ref OfflineRecognizer.cs:145-159), the emission test, context shift, back-pointer, and the next
 // frame's joiner operand row. With a single hypothesis the log-softmax is a constant shift of every candidate, so neither the
 // maxima nor the sums are read and the score stays 0; nothing goes through shared memory, so the four merge warps of a CTA step
-// four streams at once. part_rec [B, nt, kBeamRecWords<1>] as joiner_topk_kernel<1> writes it.
+// four streams at once. part_rec [B, nt, kBeamRecWords<1>] as joiner_topk_kernel<1> writes it. The emitted tokens / timestamps go
+// straight to the caller's arrays (the hypothesis length counts them), so beam 1 needs neither back-pointers nor a back-trace
+// launch; the last frame also leaves the count and, for online chunks, the context (OnlineStream.Hyp, ref OnlineRecognizer.cs:208).
+struct GreedyOut {
+  int64_t* tokens;   // [B,cap]
+  int32_t* ts;       // [B,cap]
+  int32_t* n;        // [B]
+  int64_t* hyp;      // [B,2] or null
+  int cap;
+};
 __device__ __forceinline__ void greedy_merge_warp(int lane, int s, int V, int nt, int T, int t, int blank, int unk, int mask3,
-                                                  const float* part_rec, const BeamState& in, const BeamState& out, int32_t* bp,
+                                                  const float* part_rec, const BeamState& in, const BeamState& out, const GreedyOut& go,
                                                   const int32_t* lens, const float* dec_tab, const float* enc_next,
                                                   long long enc_stride, int J, uint8_t* x_img) {
   constexpr int kNone = (int)0x80000000, RW = kBeamRecWords<1>;
@@ -374,12 +383,21 @@ __device__ __forceinline__ void greedy_merge_warp(int lane, int s, int V, int nt
   const bool frozen = lens != nullptr && t >= __ldg(lens + s);
   const int wk = __reduce_max_sync(full, bk);
   const int y = __reduce_max_sync(full, bk == wk ? bf : -1);
-  int tok = -1;
-  if (!frozen && y >= 0 && y != blank && y != unk && y != mask3) { tok = y; c0 = c1; c1 = y; ln += 1; }
+  const bool emit = !frozen && y >= 0 && y != blank && y != unk && y != mask3;
+  if (lane == 0) {
+    if (emit) {
+      const int pos = ln - 2;                 // the length starts at the two context tokens
+      if (pos < go.cap) { go.tokens[(size_t)s * go.cap + pos] = y; go.ts[(size_t)s * go.cap + pos] = t; }
+    }
+  }
+  if (emit) { c0 = c1; c1 = y; ln += 1; }
   if (lane == 0) {
     out.ctx[2 * s] = c0; out.ctx[2 * s + 1] = c1;
     out.lp[s] = 0.f; out.len[s] = ln; out.hash[s] = kHashSeed; out.nlive[s] = 1;
-    bp[(size_t)s * T + t] = tok + 1;
+    if (t == T - 1) {
+      go.n[s] = ln - 2;
+      if (go.hyp != nullptr) { go.hyp[2 * s] = c0; go.hyp[2 * s + 1] = c1; }
+    }
   }
   if (enc_next == nullptr) return;
   constexpr int kRowTile = 128, kImgTile = 128 * 128;

@@ -77,6 +77,7 @@ struct JArgs {
   int* done;                 // [T][ntm]: column tiles of (frame, row tile) whose partials are written
   int* ready;                // [T+1][ntm]: streams of (frame, row tile) whose operand rows are written
   int* abort_flag;
+  GreedyOut go;              // beam 1: where the merge warps leave tokens / timestamps / counts (/ Hyp)
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -429,7 +430,7 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
           if (lane == 0) good = wait_count(a.done + (size_t)t * a.ntm + r, a.ntn, a.abort_flag) ? 1 : 0;
           good = __shfl_sync(0xffffffffu, good, 0);
           if (!good) { ok = false; break; }
-          greedy_merge_warp(lane, s, a.V, a.ntn, a.T, t, a.blank, a.unk, a.mask3, a.part_rec, sin, sout, a.bp, a.lens, a.dec_tab,
+          greedy_merge_warp(lane, s, a.V, a.ntn, a.T, t, a.blank, a.unk, a.mask3, a.part_rec, sin, sout, a.go, a.lens, a.dec_tab,
                             enc_next, a.enc_stride, a.J, a.x_img);
           if (t + 1 < a.T) {
             asm volatile("fence.proxy.async;" ::: "memory");
@@ -538,7 +539,7 @@ int joiner_topk_tiles(const k2b_handle* h, int M) {
 
 // x_img: the joiner operand as bf16 hi / lo tile images (joinin_table_tc / decoder_joinin_tc). Partial records per (row, 160-column
 // vocabulary tile): beam_partial_words(topk) floats each (beam_merge.cuh). The weight images must exist (ensure_joiner_assets).
-int32_t joiner_topk_tc(k2b_handle* h, const uint8_t* x_img, int M, int topk, float* part_rec) {
+int32_t joiner_topk_tc(k2b_handle* h, const uint8_t* x_img, int M, int topk, int kk, float* part_rec) {
   JArgs a = {};
   a.a_img = x_img; a.w_hi_img = h->wj_hi_img; a.w_lo_img = h->wj_lo_img; a.bias = h->out_b;
   const int bn = joiner_topk_width(h, M);
@@ -549,9 +550,16 @@ int32_t joiner_topk_tc(k2b_handle* h, const uint8_t* x_img, int M, int topk, flo
   a.status = h->dev_status + 1;
   a.dbg = h->cluster_timing;
   a.tl = h->timeline != nullptr ? h->timeline + (size_t)(h->timeline_frame % 64) * 148 * 8 : nullptr;
-  return topk == 1 ? launch_as<1, false>(h, a, bn) : topk <= 4 ? launch_as<4, false>(h, a, bn) : launch_as<8, false>(h, a, bn);
+  return kk == 1 ? launch_as<1, false>(h, a, bn) : kk == 4 ? launch_as<4, false>(h, a, bn) : launch_as<8, false>(h, a, bn);
 }
 
+
+// ints of the per-(frame, row tile) counters + the abort flag of one persistent launch (zeroed before it)
+size_t beam_mega_sync_ints(const k2b_handle* h, int B, int T, int K) {
+  (void)h;
+  const int ntm = (B * K + kJM - 1) / kJM;
+  return (size_t)(2 * T + 1) * ntm + 1;
+}
 
 // ---- the whole modified_beam_search time loop in one launch (memoised decoder, K in {2, 4, 8}) --------------------------------
 bool beam_mega_usable(const k2b_handle* h, int K) {
@@ -560,7 +568,7 @@ bool beam_mega_usable(const k2b_handle* h, int K) {
 }
 
 int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8_t* x_img, float* part_rec, const BeamStatePtrs& s0,
-                     const BeamStatePtrs& s1, int32_t* bp, const int32_t* lens, int mask3) {
+                     const BeamStatePtrs& s1, int32_t* bp, const int32_t* lens, int mask3, int kk, const GreedyOutPtrs* go, bool sync_zeroed) {
   const int M = B * K;
   JArgs a = {};
   a.a_img = x_img; a.x_img = x_img; a.w_hi_img = h->wj_hi_img; a.w_lo_img = h->wj_lo_img; a.bias = h->out_b;
@@ -574,17 +582,22 @@ int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8
   a.st[0] = BeamState{s0.ctx, s0.lp, s0.len, reinterpret_cast<uint64_t*>(s0.hash), s0.nlive};
   a.st[1] = BeamState{s1.ctx, s1.lp, s1.len, reinterpret_cast<uint64_t*>(s1.hash), s1.nlive};
   a.bp = bp; a.lens = lens; a.dec_tab = h->dec_tab; a.enc = enc; a.enc_stride = (long long)T * a.J;
-  const size_t nsync = (size_t)(2 * T + 1) * a.ntm + 1;
+  const size_t nsync = beam_mega_sync_ints(h, B, T, K);
   K2B_TRY(ensure(h, h->ws_sync, nsync * sizeof(int)));
-  K2B_CUDA(h, cudaMemsetAsync(h->ws_sync.p, 0, nsync * sizeof(int), h->stream));
+  if (!sync_zeroed) K2B_CUDA(h, cudaMemsetAsync(h->ws_sync.p, 0, nsync * sizeof(int), h->stream));
+  if (kk == 1) {
+    if (go == nullptr) return fail(h, K2B_ERR_INVALID, "beam_mega_tc: beam 1 writes its tokens itself and needs the output arrays");
+    a.go = GreedyOut{go->tokens, go->ts, go->n, go->hyp, go->cap};
+  }
   a.done = static_cast<int*>(h->ws_sync.p);
   a.ready = a.done + (size_t)T * a.ntm;
   a.abort_flag = a.ready + (size_t)(T + 1) * a.ntm;
   a.tl = h->timeline;
-  return K == 1 ? launch_as<1, true>(h, a, bn) : K <= 4 ? launch_as<4, true>(h, a, bn) : launch_as<8, true>(h, a, bn);
+  return kk == 1 ? launch_as<1, true>(h, a, bn) : kk == 4 ? launch_as<4, true>(h, a, bn) : launch_as<8, true>(h, a, bn);
 }
 
 
-int beam_partial_words(int topk) { return topk == 1 ? kBeamRecWords<1> : topk <= 4 ? kBeamRecWords<4> : kBeamRecWords<8>; }
+// kk = compile-time beam bound of the instantiation: 1 (greedy: top-1 records without sums), 4 or 8
+int beam_partial_words(int kk) { return kk == 1 ? kBeamRecWords<1> : kk == 4 ? kBeamRecWords<4> : kBeamRecWords<8>; }
 
 }  // namespace k2b

@@ -200,7 +200,7 @@ int32_t greedy_dev(k2b_handle* h, const float* enc, int B, int T, int mode, bool
 // extra_mask / hyp_inout: greedy search as beam 1 (the literal-1 mask and OnlineStream.Hyp of the online loop); only the engines
 // built on beam_merge_stream implement them - beam_dev fails with K2B_ERR_UNSUPPORTED otherwise (beam_greedy_usable tells)
 int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* tokens, int32_t* ts,
-                 int32_t* n_out, float* score, int cap, int extra_mask = -1, int64_t* hyp_inout = nullptr);
+                 int32_t* n_out, float* score, int cap, int extra_mask = -1, int64_t* hyp_inout = nullptr, bool greedy = false);
 bool beam_greedy_usable(k2b_handle* h);
 
 int32_t beam_backtrace_dev(k2b_handle* h, int B, int K, int T, const float* lp, const int32_t* len, const int32_t* nlive,
@@ -240,15 +240,18 @@ int32_t joiner_tc_partials(k2b_handle* h, const float* x, const uint8_t* x_img, 
 // ---- joiner_tc.cu ------------------------------------------------------------------------------
 bool joiner_topk_supported(const k2b_handle* h, int topk);
 bool joiner_topk_usable(const k2b_handle* h, int topk);   // the persistent joiner will serve joiner_tc_partials(x_img, topk)
-int32_t joiner_topk_tc(k2b_handle* h, const uint8_t* x_img, int M, int topk, float* part_rec);
+int32_t joiner_topk_tc(k2b_handle* h, const uint8_t* x_img, int M, int topk, int kk, float* part_rec);
 int joiner_topk_tiles(const k2b_handle* h, int M);   // vocabulary tiles (= records per row) joiner_topk_tc / beam_mega_tc use for M rows
-int beam_partial_words(int topk);      // floats per (row, tile) record of joiner_topk_tc / beam_mega_tc
+int beam_partial_words(int kk);        // floats per (row, tile) record of joiner_topk_tc / beam_mega_tc (kk = 1: greedy, 4, 8)
 
+// beam 1 on the persistent kernel leaves its results itself (no back-pointers, no back-trace launch)
+struct GreedyOutPtrs { int64_t* tokens; int32_t* ts; int32_t* n; int64_t* hyp; int cap; };
 struct BeamStatePtrs { int32_t* ctx; float* lp; int32_t* len; unsigned long long* hash; int32_t* nlive; };
 constexpr int32_t kMegaUnavailable = 0x4d454741;   // beam_mega_tc: the cooperative launch does not fit; nothing was enqueued
 bool beam_mega_usable(const k2b_handle* h, int K);
 int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8_t* x_img, float* part_rec, const BeamStatePtrs& s0,
-                     const BeamStatePtrs& s1, int32_t* bp, const int32_t* lens, int mask3);
+                     const BeamStatePtrs& s1, int32_t* bp, const int32_t* lens, int mask3, int kk, const GreedyOutPtrs* go, bool sync_zeroed);
+size_t beam_mega_sync_ints(const k2b_handle* h, int B, int T, int K);
 
 // profiling bracket around the dominant GEMM
 void prof_begin(k2b_handle* h);

@@ -478,8 +478,9 @@ namespace {
 // OnlineStream.Hyp for online greedy, and the joiner operand row of frame 0 (joinin_table_kernel) - three launches in one.
 __global__ void beam_start_kernel(int B, int K, int V, int J, int blank, const int64_t* __restrict__ hyp, BeamState s0, BeamState s1,
                                   const float* __restrict__ dec_tab, const float* __restrict__ enc, long long enc_stride,
-                                  uint8_t* __restrict__ x_img) {
+                                  uint8_t* __restrict__ x_img, int* __restrict__ zero, int nzero) {
   const int m = blockIdx.x, b = m / K, slot = m - b * K;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nzero; i += gridDim.x * blockDim.x) zero[i] = 0;   // the persistent kernel's counters
   int c0 = -1, c1 = blank;
   if (hyp != nullptr && slot == 0) { c0 = (int)hyp[2 * b]; c1 = (int)hyp[2 * b + 1]; }
   if (threadIdx.x == 0) {
@@ -538,11 +539,13 @@ bool beam_greedy_usable(k2b_handle* h) {
 }
 
 int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* tokens, int32_t* ts, int32_t* n_out,
-                 float* score, int cap, int extra_mask, int64_t* hyp_inout) {
+                 float* score, int cap, int extra_mask, int64_t* hyp_inout, bool greedy) {
   const k2b_config& c = h->cfg;
   const int J = c.joiner_dim, V = c.vocab_size, D = c.decoder_dim;
   const bool tc = c.precision != K2B_PREC_FP32 && joiner_tc_supported(h);   // per-frame tcgen05 joiner (256-column tiles)
   const int N = B * K;
+  // greedy callers (no score wanted) get the beam-1 instantiations: top-1 records without sums, one warp per stream
+  const int kk = (K == 1 && greedy) ? 1 : (K <= 4 ? 4 : 8);
   // vocabulary tiles per row: the fused joiner may use narrower tiles than the per-frame kernels (same buffer, sized for the larger)
   const int nt_fused = tc ? joiner_topk_tiles(h, N) : 0;
   const int nt = tc ? joiner_tc_tiles(h) : num_vocab_tiles(V);
@@ -555,7 +558,7 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
     ximg = static_cast<uint8_t*>(h->ws_ximg.p);
   }
   // per (row, tile): four arrays of the per-frame kernels (8 + 8K bytes) or one record of the fused joiner (beam_partial_words)
-  K2B_TRY(ensure(h, h->ws_part, (size_t)N * (size_t)max(nt * (8 + 8 * K), nt_fused * 4 * beam_partial_words(K))));
+  K2B_TRY(ensure(h, h->ws_part, (size_t)N * (size_t)max(nt * (8 + 8 * K), nt_fused * 4 * beam_partial_words(kk))));
   K2B_TRY(ensure(h, h->ws_state, 2 * state_bytes(B, K)));
   K2B_TRY(ensure(h, h->ws_bp, sizeof(int32_t) * (size_t)B * (T > 0 ? T : 1) * K));
   char* p = static_cast<char*>(h->ws_state.p);
@@ -575,7 +578,10 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
   const bool fused = tc && have_tab && ximg != nullptr && !unfused && joiner_topk_usable(h, K) && T > 0;
   if (fused) {              // state, Hyp and the operand of frame 0 in one launch
     K2B_TRY(ensure_joiner_assets(h));
-    beam_start_kernel<<<N, 64, 0, h->stream>>>(B, K, V, J, c.blank_id, hyp_inout, st[0], st[1], h->dec_tab, enc, (long long)T * J, ximg);
+    const size_t nsync = beam_mega_sync_ints(h, B, T, K);
+    K2B_TRY(ensure(h, h->ws_sync, nsync * sizeof(int)));
+    beam_start_kernel<<<N, 64, 0, h->stream>>>(B, K, V, J, c.blank_id, hyp_inout, st[0], st[1], h->dec_tab, enc, (long long)T * J, ximg,
+                                              static_cast<int*>(h->ws_sync.p), (int)nsync);
     K2B_LAUNCH_CHECK(h);
   } else {
     beam_init_kernel<<<(N + 127) / 128, 128, 0, h->stream>>>(B, K, c.blank_id, st[0], st[1]);
@@ -602,20 +608,22 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
       for (int i = 0; i < 2; ++i)
         sp[i] = BeamStatePtrs{st[i].ctx, st[i].lp, st[i].len, reinterpret_cast<unsigned long long*>(st[i].hash), st[i].nlive};
       prof_begin(h);
+      const GreedyOutPtrs go{tokens, ts, n_out, hyp_inout, cap};
       const int32_t ms = beam_mega_tc(h, enc, B, T, K, ximg, part_m, sp[0], sp[1], bp,
-                                      h->lens_active ? h->lens_dev : nullptr, extra_mask);
+                                      h->lens_active ? h->lens_dev : nullptr, extra_mask, kk, kk == 1 ? &go : nullptr, true);
       prof_end(h);
       if (ms != kMegaUnavailable) {
         K2B_TRY(ms);
+        if (kk == 1) return K2B_OK;         // greedy: the merge warps have written tokens, timestamps, counts and Hyp
         return finish(T & 1);
       }
     }
     for (int t = 0; t < T; ++t) {
       if (h->prof_which == 0) prof_begin(h);
-      K2B_TRY(joiner_topk_tc(h, ximg, N, K, part_m));
+      K2B_TRY(joiner_topk_tc(h, ximg, N, K, kk, part_m));
       if (h->prof_which == 0) prof_end(h);
       if (h->prof_which == 2) prof_begin(h);
-      K2B_CUDA(h, launch_pdl(K == 1 ? beam_step_kernel<1> : K <= 4 ? beam_step_kernel<4> : beam_step_kernel<8>, dim3(B), dim3(128), 0,
+      K2B_CUDA(h, launch_pdl(kk == 1 ? beam_step_kernel<1> : kk == 4 ? beam_step_kernel<4> : beam_step_kernel<8>, dim3(B), dim3(128), 0,
                               h->stream, B, K, V, nt_fused, T, t, (int)c.blank_id, (int)c.unk_id, extra_mask,
                               (const float*)part_m, st[cur], st[cur ^ 1], bp, (const int32_t*)(h->lens_active ? h->lens_dev : nullptr), (const float*)h->dec_tab,
                               (const float*)(t + 1 < T ? enc + (size_t)(t + 1) * J : nullptr), (long long)T * J, J, ximg,

@@ -457,3 +457,22 @@ def test_persistent_greedy_large_vocab(built_lib, monkeypatch):
     same = sum(1 for b in range(B) if all(outs[0][c][0][b] == outs[1][c][0][b] and outs[0][c][1][b] == outs[1][c][1][b] for c in range(2)))
     assert same >= B - 2, f"persistent and cluster greedy disagree on {B - same} of {B} streams"      # near ties may differ
     h.close()
+
+
+def test_beam_one_large_vocab_reports_scores(built_lib):
+    """modified_beam_search with beam 1 over a large vocabulary wants the hypothesis score, so it must not take the greedy
+    instantiations (which skip the log-softmax): tokens and scores against the oracle."""
+    dims = synth.ModelDims(vocab_size=2500, joiner_dim=64, decoder_dim=48, encoder_dim=64)
+    m, w = model_and_weights(dims, blank_bias=0.5)
+    h = make(dims, w, "bf16x3")
+    raw = synth.make_frames(9, 12, dims.encoder_dim, 77)
+    enc = O.encoder_proj(m, raw)
+    t, s, sc = h.modified_beam_search(raw, 1, enc_is_raw=True)
+    want = O.modified_beam_search(m, enc, 1)
+    ex = compare_streams(t, s, want, "beam 1 V=2500", allow_frac=0.3)
+    for b, r in enumerate(want):
+        if b not in ex:
+            assert abs(float(sc[b]) - r.score) < SCORE_TOL
+    tg, sg = h.greedy_offline(raw, _native.GREEDY_PER_STREAM, enc_is_raw=True)
+    assert [tg[b] for b in range(9) if b not in ex] == [t[b] for b in range(9) if b not in ex]
+    h.close()
