@@ -91,7 +91,7 @@ for _prec4 in (("fp32", "bf16x3", "bf16") if "cfg4" in which else ()):
     x = torch.from_numpy(synth.make_frames(B, T, cfg.dims.encoder_dim, cfg.seed)).to(dev)
     tok, ts, n, sc = outbufs(B, T)
     ms = timed(lambda: h.call("k2b_modified_beam_search_dev", x, 1, B, T, 4, tok, ts, n, sc, T), 2, warm=1)
-    emit(config="cfg4", workload=cfg.name, mode="modified_beam_search V=5537, per-frame path, " + ("fp32 CUDA-core joiner" if _prec4 == "fp32" else "tcgen05 joiner " + _prec4), frames_per_s=B * T / (ms * 1e-3), ms_per_batch=ms,
+    emit(config="cfg4", workload=cfg.name, mode="modified_beam_search V=5537, " + ("per-frame path, fp32 CUDA-core joiner" if _prec4 == "fp32" else "persistent beam kernel (one launch), tcgen05 joiner " + _prec4), frames_per_s=B * T / (ms * 1e-3), ms_per_batch=ms,
          us_per_frame_step=ms * 1e3 / T, roofline_frames_per_s=61.1e6)
     h.close()
 
