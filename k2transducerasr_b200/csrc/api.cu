@@ -183,6 +183,58 @@ int32_t beam_cluster_pipelined(k2b_handle* h, const float* enc_host, int B, int 
   return beam_backtrace_dev(h, B, K, T, fin_lp, fin_len, fin_nlive, bp, tokens, ts, n_out, score, cap);
 }
 
+// projected frames of time chunk [t0, t0 + tc) of every stream, written into a [B,T,J] array (tcgen05 GEMM, or the CUDA-core one
+// into a compact buffer followed by a strided copy when J is not a multiple of the tensor-core tile)
+static int32_t encoder_proj_chunk(k2b_handle* h, const float* stage, int B, int tc, float* encP, int T, int t0) {
+  const int E = h->cfg.encoder_dim, J = h->cfg.joiner_dim;
+  if (encproj_tc_supported(h)) return encoder_proj_tc(h, stage, B * tc, encP, false, tc, T, t0);
+  K2B_TRY(ensure(h, h->ws_x, sizeof(float) * (size_t)B * tc * J));
+  GemmArgs g;
+  g.M = B * tc; g.N = J; g.K = E;
+  g.A = stage; g.W = h->enc_w; g.bias = h->enc_b; g.C = static_cast<float*>(h->ws_x.p);
+  K2B_TRY(launch_gemm_simt(h, PRO_PLAIN, EPI_STORE, g));
+  K2B_CUDA(h, cudaMemcpy2DAsync(encP + (size_t)t0 * J, sizeof(float) * (size_t)T * J, h->ws_x.p, sizeof(float) * (size_t)tc * J,
+                                sizeof(float) * (size_t)tc * J, (size_t)B, cudaMemcpyDeviceToDevice, h->stream));
+  return K2B_OK;
+}
+
+// The same for the engines of beam_dev that can be stepped in time chunks (persistent beam kernel: large vocabularies): chunk c+1
+// crosses PCIe while chunk c is projected and searched; the hypothesis state stays in the workspaces between the chunks.
+int32_t beam_chunked_host(k2b_handle* h, const float* enc_host, int B, int T, int K, int64_t* tokens, int32_t* ts, int32_t* n_out,
+                          float* score, int cap) {
+  const int E = h->cfg.encoder_dim, J = h->cfg.joiner_dim;
+  int nchunk = T / 32 < 5 ? (T / 32 > 0 ? T / 32 : 1) : 5;          // each chunk is one persistent launch (~20 us of set-up)
+  if (const char* e = getenv("K2B_PIPE_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= 64) nchunk = v; }
+  const int Tc = (T + nchunk - 1) / nchunk;
+  if (h->copy_stream == nullptr) {
+    K2B_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      K2B_CUDA(h, cudaEventCreateWithFlags(&h->ev_ready[i], cudaEventDisableTiming));
+      K2B_CUDA(h, cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
+    }
+  }
+  const size_t buf_bytes = ((sizeof(float) * (size_t)B * Tc * E) + 255) & ~size_t(255);
+  K2B_TRY(ensure(h, h->ws_in, 2 * buf_bytes));
+  K2B_TRY(ensure(h, h->ws_encproj, sizeof(float) * (size_t)B * T * J));
+  float* encP = static_cast<float*>(h->ws_encproj.p);
+  K2B_CUDA(h, cudaEventRecord(h->ev_free[0], h->stream));
+  K2B_CUDA(h, cudaEventRecord(h->ev_free[1], h->stream));
+  int c = 0;
+  for (int t0 = 0; t0 < T; t0 += Tc, ++c) {
+    const int tc = (T - t0) < Tc ? (T - t0) : Tc, sb = c & 1;
+    float* stage = reinterpret_cast<float*>(static_cast<char*>(h->ws_in.p) + (size_t)sb * buf_bytes);
+    K2B_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_free[sb], 0));
+    K2B_CUDA(h, cudaMemcpy2DAsync(stage, sizeof(float) * (size_t)tc * E, enc_host + (size_t)t0 * E, sizeof(float) * (size_t)T * E,
+                                  sizeof(float) * (size_t)tc * E, (size_t)B, cudaMemcpyHostToDevice, h->copy_stream));
+    K2B_CUDA(h, cudaEventRecord(h->ev_ready[sb], h->copy_stream));
+    K2B_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_ready[sb], 0));
+    K2B_TRY(encoder_proj_chunk(h, stage, B, tc, encP, T, t0));
+    K2B_CUDA(h, cudaEventRecord(h->ev_free[sb], h->stream));
+    K2B_TRY(beam_dev(h, encP + (size_t)t0 * J, B, tc, K, tokens, ts, n_out, score, cap, -1, nullptr, false, t0, T));
+  }
+  return K2B_OK;
+}
+
 struct OutStage {
   int64_t* tokens;
   int32_t* ts;
@@ -744,8 +796,12 @@ int32_t k2b_modified_beam_search(k2b_handle* h, const float* enc, int32_t enc_is
   if (K < 1 || K > kMaxBeam) return fail(h, K2B_ERR_INVALID, "k2b_modified_beam_search: beam must be in 1..8");
   const bool pipelined = enc_is_raw && h->cfg.precision != K2B_PREC_FP32 && cluster_path_supported(h, K) && encproj_tc_supported(h) &&
                          T >= 32 && !h->profile_on && K <= h->cfg.vocab_size;
+  const bool chunked = !pipelined && enc_is_raw && h->cfg.precision != K2B_PREC_FP32 && !cluster_path_supported(h, K) &&
+                       T >= 64 && !h->profile_on && K <= h->cfg.vocab_size && h->cfg.encoder_dim > 0 && beam_chunkable(h, K);
   if (pipelined) {
     K2B_TRY(beam_cluster_pipelined(h, enc, B, T, K, o.tokens, o.ts, o.n, o.score, cap));
+  } else if (chunked) {
+    K2B_TRY(beam_chunked_host(h, enc, B, T, K, o.tokens, o.ts, o.n, o.score, cap));
   } else {
     K2B_TRY(ensure(h, h->ws_in, in_bytes > 0 ? in_bytes : 4));
     if (in_bytes) K2B_CUDA(h, cudaMemcpyAsync(h->ws_in.p, enc, in_bytes, cudaMemcpyHostToDevice, h->stream));

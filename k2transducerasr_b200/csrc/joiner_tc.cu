@@ -67,6 +67,7 @@ struct JArgs {
   long long* tl;             // diagnostic timeline of this launch: [sm][8] clock64 stamps (slots 0..3), or null
   // MEGA: the whole search
   int B, V, T, blank, unk, mask3, J;
+  int t0, Ttot;              // this launch steps frames t0 .. t0 + T - 1 of a search over Ttot frames (time chunks of a host call)
   BeamState st[2];           // frame t reads st[t & 1], writes st[(t & 1) ^ 1]
   int32_t* bp;
   const int32_t* lens;
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
       const int mw = mtid >> 5;
       for (int t = 0; t < nframes && ok; ++t) {
         const float* enc_next = t + 1 < a.T ? a.enc + (size_t)(t + 1) * a.J : nullptr;
-        const bool odd = (t & 1) != 0;
+        const bool odd = ((a.t0 + t) & 1) != 0;
         BeamState sin, sout;
         sin.ctx = odd ? a.st[1].ctx : a.st[0].ctx; sout.ctx = odd ? a.st[0].ctx : a.st[1].ctx;
         sin.lp = odd ? a.st[1].lp : a.st[0].lp; sout.lp = odd ? a.st[0].lp : a.st[1].lp;
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
           if (lane == 0) good = wait_count(a.done + (size_t)t * a.ntm + r, a.ntn, a.abort_flag) ? 1 : 0;
           good = __shfl_sync(0xffffffffu, good, 0);
           if (!good) { ok = false; break; }
-          greedy_merge_warp(lane, s, a.V, a.ntn, a.T, t, a.blank, a.unk, a.mask3, a.part_rec, sin, sout, a.go, a.lens, a.dec_tab,
+          greedy_merge_warp(lane, s, a.V, a.ntn, a.Ttot, a.t0 + t, a.blank, a.unk, a.mask3, a.part_rec, sin, sout, a.go, a.lens, a.dec_tab,
                             enc_next, a.enc_stride, a.J, a.x_img);
           if (t + 1 < a.T) {
             asm volatile("fence.proxy.async;" ::: "memory");
@@ -454,14 +455,14 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
         named_bar_sync(2, 128);                           // mg_ctx is rewritten by the merge step
         if (!good) { ok = false; break; }
         if (tlm != nullptr && mtid == 0 && t < 40) tlm[t * 16 + (s == blockIdx.x ? 6 : 8)] = clock64();
-        const bool odd = (t & 1) != 0;
+        const bool odd = ((a.t0 + t) & 1) != 0;
         BeamState sin, sout;
         sin.ctx = odd ? a.st[1].ctx : a.st[0].ctx; sout.ctx = odd ? a.st[0].ctx : a.st[1].ctx;
         sin.lp = odd ? a.st[1].lp : a.st[0].lp; sout.lp = odd ? a.st[0].lp : a.st[1].lp;
         sin.len = odd ? a.st[1].len : a.st[0].len; sout.len = odd ? a.st[0].len : a.st[1].len;
         sin.hash = odd ? a.st[1].hash : a.st[0].hash; sout.hash = odd ? a.st[0].hash : a.st[1].hash;
         sin.nlive = odd ? a.st[1].nlive : a.st[0].nlive; sout.nlive = odd ? a.st[0].nlive : a.st[1].nlive;
-        beam_merge_stream<KK>(mtid, 2, s, a.topk, a.V, a.ntn, a.T, t, a.blank, a.unk, a.mask3, a.part_rec,
+        beam_merge_stream<KK>(mtid, 2, s, a.topk, a.V, a.ntn, a.Ttot, a.t0 + t, a.blank, a.unk, a.mask3, a.part_rec,
                               sin, sout, a.bp, a.lens, a.dec_tab, enc_next, a.enc_stride, a.J, a.x_img, pe0, pe1,
                               mg_v, mg_f, mg_ctx, (tlm != nullptr && t < 40 && s == blockIdx.x) ? tlm + 640 + t * 8 : nullptr);
         if (t + 1 < a.T) {                                // publish: one more stream of (frame t + 1, row tile) has its operand rows
@@ -568,7 +569,8 @@ bool beam_mega_usable(const k2b_handle* h, int K) {
 }
 
 int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8_t* x_img, float* part_rec, const BeamStatePtrs& s0,
-                     const BeamStatePtrs& s1, int32_t* bp, const int32_t* lens, int mask3, int kk, const GreedyOutPtrs* go, bool sync_zeroed) {
+                     const BeamStatePtrs& s1, int32_t* bp, const int32_t* lens, int mask3, int kk, const GreedyOutPtrs* go, bool sync_zeroed,
+                     int t0, int Ttot, long long enc_stride) {
   const int M = B * K;
   JArgs a = {};
   a.a_img = x_img; a.x_img = x_img; a.w_hi_img = h->wj_hi_img; a.w_lo_img = h->wj_lo_img; a.bias = h->out_b;
@@ -581,7 +583,8 @@ int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8
   a.B = B; a.V = h->cfg.vocab_size; a.T = T; a.blank = h->cfg.blank_id; a.unk = h->cfg.unk_id; a.mask3 = mask3; a.J = h->cfg.joiner_dim;
   a.st[0] = BeamState{s0.ctx, s0.lp, s0.len, reinterpret_cast<uint64_t*>(s0.hash), s0.nlive};
   a.st[1] = BeamState{s1.ctx, s1.lp, s1.len, reinterpret_cast<uint64_t*>(s1.hash), s1.nlive};
-  a.bp = bp; a.lens = lens; a.dec_tab = h->dec_tab; a.enc = enc; a.enc_stride = (long long)T * a.J;
+  a.bp = bp; a.lens = lens; a.dec_tab = h->dec_tab; a.enc = enc; a.enc_stride = enc_stride;
+  a.t0 = t0; a.Ttot = Ttot;
   const size_t nsync = beam_mega_sync_ints(h, B, T, K);
   K2B_TRY(ensure(h, h->ws_sync, nsync * sizeof(int)));
   if (!sync_zeroed) K2B_CUDA(h, cudaMemsetAsync(h->ws_sync.p, 0, nsync * sizeof(int), h->stream));

@@ -200,7 +200,11 @@ int32_t greedy_dev(k2b_handle* h, const float* enc, int B, int T, int mode, bool
 // extra_mask / hyp_inout: greedy search as beam 1 (the literal-1 mask and OnlineStream.Hyp of the online loop); only the engines
 // built on beam_merge_stream implement them - beam_dev fails with K2B_ERR_UNSUPPORTED otherwise (beam_greedy_usable tells)
 int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* tokens, int32_t* ts,
-                 int32_t* n_out, float* score, int cap, int extra_mask = -1, int64_t* hyp_inout = nullptr, bool greedy = false);
+                 int32_t* n_out, float* score, int cap, int extra_mask = -1, int64_t* hyp_inout = nullptr, bool greedy = false,
+                 int t0 = 0, int Ttot = 0);
+// a search may be stepped in time chunks (enc = frame t0 of a [B,Ttot,J] array, T frames per call: the host-pointer entry point hides
+// the input copy behind the search that way) on the engines built on beam_merge_stream
+bool beam_chunkable(k2b_handle* h, int K);
 bool beam_greedy_usable(k2b_handle* h);
 
 int32_t beam_backtrace_dev(k2b_handle* h, int B, int K, int T, const float* lp, const int32_t* len, const int32_t* nlive,
@@ -250,7 +254,8 @@ struct BeamStatePtrs { int32_t* ctx; float* lp; int32_t* len; unsigned long long
 constexpr int32_t kMegaUnavailable = 0x4d454741;   // beam_mega_tc: the cooperative launch does not fit; nothing was enqueued
 bool beam_mega_usable(const k2b_handle* h, int K);
 int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8_t* x_img, float* part_rec, const BeamStatePtrs& s0,
-                     const BeamStatePtrs& s1, int32_t* bp, const int32_t* lens, int mask3, int kk, const GreedyOutPtrs* go, bool sync_zeroed);
+                     const BeamStatePtrs& s1, int32_t* bp, const int32_t* lens, int mask3, int kk, const GreedyOutPtrs* go, bool sync_zeroed,
+                     int t0, int Ttot, long long enc_stride);
 size_t beam_mega_sync_ints(const k2b_handle* h, int B, int T, int K);
 
 // profiling bracket around the dominant GEMM

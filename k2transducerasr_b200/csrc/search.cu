@@ -530,17 +530,27 @@ __global__ void beam_hyp_from_ctx_kernel(int B, const int32_t* __restrict__ ctx,
 }
 }  // namespace
 
+bool beam_chunkable(k2b_handle* h, int K) {
+  if (h->cfg.precision == K2B_PREC_FP32 || !joiner_tc_supported(h) || h->tab0 == nullptr || !joiner_topk_usable(h, K)) return false;
+  bool have = false;
+  if (ensure_dec_table(h, &have) != K2B_OK) return false;
+  return have && getenv("K2B_UNFUSED_STEP") == nullptr;
+}
+
 // greedy search as beam 1 on the persistent kernel: needs the tcgen05 precisions and the memoised decoder table
 bool beam_greedy_usable(k2b_handle* h) {
-  if (h->cfg.precision == K2B_PREC_FP32 || !joiner_tc_supported(h) || !decoder_tc_supported(h)) return false;
+  if (h->cfg.precision == K2B_PREC_FP32 || !joiner_tc_supported(h) || h->tab0 == nullptr) return false;
   bool have = false;
   if (ensure_dec_table(h, &have) != K2B_OK) return false;
   return have && beam_mega_usable(h, 1);
 }
 
 int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* tokens, int32_t* ts, int32_t* n_out,
-                 float* score, int cap, int extra_mask, int64_t* hyp_inout, bool greedy) {
+                 float* score, int cap, int extra_mask, int64_t* hyp_inout, bool greedy, int t0, int Ttot) {
   const k2b_config& c = h->cfg;
+  if (Ttot <= 0) { Ttot = T; t0 = 0; }
+  const long long enc_stride = (long long)Ttot * c.joiner_dim;       // enc points at frame t0 of a [B,Ttot,J] array
+  const bool resume = t0 > 0, last = t0 + T >= Ttot;
   const int J = c.joiner_dim, V = c.vocab_size, D = c.decoder_dim;
   const bool tc = c.precision != K2B_PREC_FP32 && joiner_tc_supported(h);   // per-frame tcgen05 joiner (256-column tiles)
   const int N = B * K;
@@ -552,15 +562,17 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
   K2B_TRY(ensure(h, h->ws_x, sizeof(float) * (size_t)N * J));
   uint8_t* ximg = nullptr;
   bool have_tab = false;         // memoised decoder (fits in HBM up to V ~ 6800 at J = 512): no decoder GEMM in the loop
-  if (tc && decoder_tc_supported(h)) K2B_TRY(ensure_dec_table(h, &have_tab));
-  if (tc && decoder_tc_supported(h)) {
+  // the joiner operand as bf16 hi / lo tile images needs 64-column k-blocks; it is produced from the memoised table (any decoder
+  // width) or, when that does not fit, by the tcgen05 decoder (256-column tiles of J)
+  if (tc && J % 64 == 0 && h->tab0 != nullptr) K2B_TRY(ensure_dec_table(h, &have_tab));
+  if (tc && J % 64 == 0 && (have_tab || decoder_tc_supported(h))) {
     K2B_TRY(ensure(h, h->ws_ximg, joiner_tc_image_bytes(h, N)));
     ximg = static_cast<uint8_t*>(h->ws_ximg.p);
   }
   // per (row, tile): four arrays of the per-frame kernels (8 + 8K bytes) or one record of the fused joiner (beam_partial_words)
   K2B_TRY(ensure(h, h->ws_part, (size_t)N * (size_t)max(nt * (8 + 8 * K), nt_fused * 4 * beam_partial_words(kk))));
   K2B_TRY(ensure(h, h->ws_state, 2 * state_bytes(B, K)));
-  K2B_TRY(ensure(h, h->ws_bp, sizeof(int32_t) * (size_t)B * (T > 0 ? T : 1) * K));
+  K2B_TRY(ensure(h, h->ws_bp, sizeof(int32_t) * (size_t)B * (Ttot > 0 ? Ttot : 1) * K));
   char* p = static_cast<char*>(h->ws_state.p);
   BeamState st[2];
   st[0] = carve_state(p, B, K);
@@ -576,13 +588,19 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
   if (greedy_ext && K != 1) return fail(h, K2B_ERR_INVALID, "beam_dev: mask / Hyp are beam-1 (greedy) options");
   static const bool unfused = getenv("K2B_UNFUSED_STEP") != nullptr;
   const bool fused = tc && have_tab && ximg != nullptr && !unfused && joiner_topk_usable(h, K) && T > 0;
-  if (fused) {              // state, Hyp and the operand of frame 0 in one launch
+  if (resume && !fused) return fail(h, K2B_ERR_UNSUPPORTED, "beam_dev: time chunks need the memoised decoder table");
+  if (fused) {
     K2B_TRY(ensure_joiner_assets(h));
     const size_t nsync = beam_mega_sync_ints(h, B, T, K);
     K2B_TRY(ensure(h, h->ws_sync, nsync * sizeof(int)));
-    beam_start_kernel<<<N, 64, 0, h->stream>>>(B, K, V, J, c.blank_id, hyp_inout, st[0], st[1], h->dec_tab, enc, (long long)T * J, ximg,
-                                              static_cast<int*>(h->ws_sync.p), (int)nsync);
-    K2B_LAUNCH_CHECK(h);
+    if (!resume) {          // state, Hyp and the operand of frame 0 in one launch
+      beam_start_kernel<<<N, 64, 0, h->stream>>>(B, K, V, J, c.blank_id, hyp_inout, st[0], st[1], h->dec_tab, enc, enc_stride, ximg,
+                                                static_cast<int*>(h->ws_sync.p), (int)nsync);
+      K2B_LAUNCH_CHECK(h);
+    } else {                // next time chunk: the state is where the chunk before left it
+      K2B_CUDA(h, cudaMemsetAsync(h->ws_sync.p, 0, nsync * sizeof(int), h->stream));
+      K2B_TRY(joinin_table_tc(h, st[t0 & 1].ctx, N, enc, enc_stride, K, ximg));
+    }
   } else {
     beam_init_kernel<<<(N + 127) / 128, 128, 0, h->stream>>>(B, K, c.blank_id, st[0], st[1]);
     K2B_LAUNCH_CHECK(h);
@@ -596,10 +614,10 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
       beam_hyp_from_ctx_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(B, st[fin].ctx, hyp_inout);
       K2B_LAUNCH_CHECK(h);
     }
-    return beam_backtrace_dev(h, B, K, T, st[fin].lp, st[fin].len, st[fin].nlive, bp, tokens, ts, n_out, score, cap);
+    return beam_backtrace_dev(h, B, K, Ttot, st[fin].lp, st[fin].len, st[fin].nlive, bp, tokens, ts, n_out, score, cap);
   };
 
-  int cur = 0;
+  int cur = t0 & 1;
   // memoised decoder + persistent joiner: two launches per frame (joiner, fused merge + next operand), chained by programmatic
   // dependent launches. K2B_UNFUSED_STEP=1 keeps the three-launch sequence below (comparison runs).
   if (fused) {
@@ -610,12 +628,13 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
       prof_begin(h);
       const GreedyOutPtrs go{tokens, ts, n_out, hyp_inout, cap};
       const int32_t ms = beam_mega_tc(h, enc, B, T, K, ximg, part_m, sp[0], sp[1], bp,
-                                      h->lens_active ? h->lens_dev : nullptr, extra_mask, kk, kk == 1 ? &go : nullptr, true);
+                                      h->lens_active ? h->lens_dev : nullptr, extra_mask, kk, kk == 1 ? &go : nullptr, true, t0, Ttot,
+                                      enc_stride);
       prof_end(h);
       if (ms != kMegaUnavailable) {
         K2B_TRY(ms);
-        if (kk == 1) return K2B_OK;         // greedy: the merge warps have written tokens, timestamps, counts and Hyp
-        return finish(T & 1);
+        if (kk == 1 || !last) return K2B_OK;   // greedy: the merge warps have written tokens, timestamps, counts and Hyp
+        return finish(Ttot & 1);
       }
     }
     for (int t = 0; t < T; ++t) {
@@ -624,16 +643,16 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
       if (h->prof_which == 0) prof_end(h);
       if (h->prof_which == 2) prof_begin(h);
       K2B_CUDA(h, launch_pdl(kk == 1 ? beam_step_kernel<1> : kk == 4 ? beam_step_kernel<4> : beam_step_kernel<8>, dim3(B), dim3(128), 0,
-                              h->stream, B, K, V, nt_fused, T, t, (int)c.blank_id, (int)c.unk_id, extra_mask,
+                              h->stream, B, K, V, nt_fused, Ttot, t0 + t, (int)c.blank_id, (int)c.unk_id, extra_mask,
                               (const float*)part_m, st[cur], st[cur ^ 1], bp, (const int32_t*)(h->lens_active ? h->lens_dev : nullptr), (const float*)h->dec_tab,
-                              (const float*)(t + 1 < T ? enc + (size_t)(t + 1) * J : nullptr), (long long)T * J, J, ximg,
+                              (const float*)(t + 1 < T ? enc + (size_t)(t + 1) * J : nullptr), enc_stride, J, ximg,
                               (long long*)(h->timeline != nullptr ? h->timeline + (size_t)(h->timeline_frame % 64) * 148 * 8 : nullptr)));
       K2B_LAUNCH_CHECK(h);
       h->timeline_frame++;
       if (h->prof_which == 2) prof_end(h);
       cur ^= 1;
     }
-    return finish(cur);
+    return last ? finish(cur) : K2B_OK;
   }
   if (greedy_ext) return fail(h, K2B_ERR_UNSUPPORTED, "beam_dev: greedy options need the memoised decoder table");
   for (int t = 0; t < T; ++t) {
@@ -646,7 +665,7 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
     d.C = x;
     // tcgen05 decoder: its epilogue leaves x = tanh(enc + dec) as bf16 hi/lo tile images, which the joiner's loader warp
     // fetches by TMA (no fp32 round trip, no per-CTA conversion)
-    const bool img = tc && decoder_tc_supported(h);
+    const bool img = ximg != nullptr;
     if (h->prof_which == 1) prof_begin(h);
     if (img && have_tab) K2B_TRY(joinin_table_tc(h, st[cur].ctx, N, enc + (size_t)t * J, (long long)T * J, K, ximg));
     else if (img) K2B_TRY(decoder_joinin_tc(h, st[cur].ctx, N, enc + (size_t)t * J, (long long)T * J, K, nullptr, ximg));

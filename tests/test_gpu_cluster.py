@@ -476,3 +476,34 @@ def test_beam_one_large_vocab_reports_scores(built_lib):
     tg, sg = h.greedy_offline(raw, _native.GREEDY_PER_STREAM, enc_is_raw=True)
     assert [tg[b] for b in range(9) if b not in ex] == [t[b] for b in range(9) if b not in ex]
     h.close()
+
+
+@pytest.mark.parametrize("beam", [4, 3])
+def test_time_chunked_host_call_large_vocab(built_lib, monkeypatch, beam):
+    """Large vocabulary: the host-pointer call steps the persistent beam kernel (beam 4) / the per-frame fused launches (beam 3) in
+    time chunks so that the input copy hides behind the search; the hypothesis state is carried in the workspaces. Same arithmetic,
+    so bit-identical to the single-chunk call (K2B_PIPE_CHUNKS=1), with ragged lengths too."""
+    dims = synth.ModelDims(vocab_size=2500, joiner_dim=64, decoder_dim=48, encoder_dim=64)
+    m, w = model_and_weights(dims, blank_bias=0.5)
+    h = make(dims, w, "bf16x3")
+    B, T = 37, 100                                  # T >= 64: three chunks of 34 frames
+    raw = synth.make_frames(B, T, dims.encoder_dim, 123)
+    h.modified_beam_search(raw, beam, enc_is_raw=True)
+    n0 = h.launch_count()
+    t1, s1, sc1 = h.modified_beam_search(raw, beam, enc_is_raw=True)
+    n_chunked = h.launch_count() - n0
+    monkeypatch.setenv("K2B_PIPE_CHUNKS", "1")
+    n0 = h.launch_count()
+    t2, s2, sc2 = h.modified_beam_search(raw, beam, enc_is_raw=True)
+    n_one = h.launch_count() - n0
+    monkeypatch.delenv("K2B_PIPE_CHUNKS")
+    assert t1 == t2 and s1 == s2 and sc1.tolist() == sc2.tolist()
+    assert n_chunked > n_one, (n_chunked, n_one)
+    lens = [T - (11 * b) % T for b in range(B)]
+    t3, s3, _ = h.modified_beam_search(raw, beam, enc_is_raw=True, lens=lens)
+    monkeypatch.setenv("K2B_PIPE_CHUNKS", "1")
+    t4, s4, _ = h.modified_beam_search(raw, beam, enc_is_raw=True, lens=lens)
+    assert t3 == t4 and s3 == s4
+    enc = O.encoder_proj(m, raw[:6])
+    ex = compare_streams(t1[:6], s1[:6], O.modified_beam_search(m, enc, beam), "chunked vs oracle", allow_frac=0.35)
+    h.close()
