@@ -52,7 +52,7 @@ class WorkloadConfig:
 
 
 # cfg1..cfg5 of BASELINE.json; blank_bias values calibrated so that roughly 70-80 % of frames
-# are blank under greedy search (see tools/calibrate_blank_bias.py for how they were obtained).
+# are blank under greedy search (see tests/golden/calibrate_blank_bias.py for how they were obtained).
 CONFIGS = {
     "cfg1": WorkloadConfig("zipformer-small-en offline greedy B=1", "greedy_single",
                            ModelDims(500, 512, 512, 256), 1, 250, seed=1001, blank_bias=0.99),

@@ -1,6 +1,6 @@
 """Find the joiner blank bias that makes ~75 % of greedy frames blank for each config's dims.
 Uses the CPU oracle (test infrastructure); the constants it prints are pasted into
-k2transducerasr_b200/synth.py::CONFIGS.  Run: python tools/calibrate_blank_bias.py"""
+k2transducerasr_b200/synth.py::CONFIGS.  Run from the repo root: python tests/golden/calibrate_blank_bias.py"""
 import sys
 import numpy as np
 sys.path.insert(0, ".")

@@ -3,7 +3,15 @@ import sys
 import numpy as np
 sys.path.insert(0, ".")
 from k2transducerasr_b200 import _native, build
-from oracle.k2_oracle import round_bf16
+
+
+def round_bf16(x):
+    """float32 -> nearest-even bfloat16 -> float32"""
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32)
+    r = ((u >> 16) & 1) + 0x7FFF
+    return ((u + r) & 0xFFFF0000).astype(np.uint32).view(np.float32)
+
+
 build.build()
 h = _native.Handle(vocab_size=64, joiner_dim=64, decoder_dim=64)
 rng = np.random.default_rng(5)
