@@ -507,3 +507,29 @@ def test_time_chunked_host_call_large_vocab(built_lib, monkeypatch, beam):
     enc = O.encoder_proj(m, raw[:6])
     ex = compare_streams(t1[:6], s1[:6], O.modified_beam_search(m, enc, beam), "chunked vs oracle", allow_frac=0.35)
     h.close()
+
+
+def test_ragged_lengths_large_vocab(built_lib):
+    """encoder_out_lens on the persistent kernels (V = 2500: no cluster holds it): beam search and per-stream greedy against the
+    oracle's ragged wrapper, lengths 0 and T included."""
+    dims = synth.ModelDims(vocab_size=2500, joiner_dim=64, decoder_dim=48, encoder_dim=64)
+    m, w = model_and_weights(dims, blank_bias=0.5)
+    h = make(dims, w, "bf16x3")
+    B, T = 11, 24
+    raw = synth.make_frames(B, T, dims.encoder_dim, 55)
+    enc = O.encoder_proj(m, raw)
+    lens = [24, 0, 5, 17, 1, 24, 9, 13, 2, 20, 7]
+    want = O.ragged(O.modified_beam_search, m, enc, lens, 4)
+    t, s, sc = h.modified_beam_search(raw, 4, enc_is_raw=True, lens=lens)
+    ex = compare_streams(t, s, want, "ragged mbs persistent", allow_frac=0.3)
+    for b, r in enumerate(want):
+        if b not in ex:
+            assert abs(float(sc[b]) - r.score) < SCORE_TOL
+        assert all(x < lens[b] for x in s[b])
+    wantg = O.ragged(O.greedy_search_batch, m, enc, lens, compat=False)
+    t, s = h.greedy_offline(raw, _native.GREEDY_PER_STREAM, enc_is_raw=True, lens=lens)
+    compare_streams(t, s, wantg, "ragged greedy persistent", allow_frac=0.3)
+    assert all(all(x < lens[b] for x in s[b]) for b in range(B)) and s[1] == [] and t[1] == []
+    t2, s2 = h.greedy_offline(raw, _native.GREEDY_PER_STREAM, enc_is_raw=True)          # the lengths were consumed by one call
+    compare_streams(t2, s2, O.greedy_search_batch(m, enc, compat=False), "after ragged greedy persistent", allow_frac=0.3)
+    h.close()
