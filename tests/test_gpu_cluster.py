@@ -533,3 +533,23 @@ def test_ragged_lengths_large_vocab(built_lib):
     t2, s2 = h.greedy_offline(raw, _native.GREEDY_PER_STREAM, enc_is_raw=True)          # the lengths were consumed by one call
     compare_streams(t2, s2, O.greedy_search_batch(m, enc, compat=False), "after ragged greedy persistent", allow_frac=0.3)
     h.close()
+
+
+def test_persistent_kernel_bf16_matches_bf16_oracle(built_lib):
+    """Single-pass bf16 on the persistent kernels (V = 2500): against the oracle restated with bf16-rounded joiner / encoder_proj
+    operands (stated tolerance 5e-3 on the score), beam search and greedy."""
+    dims = synth.ModelDims(vocab_size=2500, joiner_dim=256, decoder_dim=48, encoder_dim=64)   # J % 256 == 0: tcgen05 encoder_proj too
+    m, w = model_and_weights(dims, blank_bias=0.5)
+    h = make(dims, w, "bf16")
+    raw = synth.make_frames(9, 16, dims.encoder_dim, 66)
+    mb = O.Model.from_dict(w, prec_joiner="bf16", prec_enc="bf16")
+    encb = O.encoder_proj(mb, raw)
+    want = O.modified_beam_search(mb, encb, 4)
+    t, s, sc = h.modified_beam_search(raw, 4, enc_is_raw=True)
+    ex = compare_streams(t, s, want, "persistent bf16 vs bf16 oracle", allow_frac=0.35)
+    for b, r in enumerate(want):
+        if b not in ex:
+            assert abs(float(sc[b]) - r.score) < 5e-3
+    tg, sg = h.greedy_offline(raw, _native.GREEDY_PER_STREAM, enc_is_raw=True)
+    compare_streams(tg, sg, O.greedy_search_batch(mb, encb, compat=False), "persistent greedy bf16", allow_frac=0.35)
+    h.close()
