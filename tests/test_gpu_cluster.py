@@ -553,3 +553,27 @@ def test_persistent_kernel_bf16_matches_bf16_oracle(built_lib):
     tg, sg = h.greedy_offline(raw, _native.GREEDY_PER_STREAM, enc_is_raw=True)
     compare_streams(tg, sg, O.greedy_search_batch(mb, encb, compat=False), "persistent greedy bf16", allow_frac=0.35)
     h.close()
+
+
+@pytest.mark.parametrize("a,b", [(10, 50), (10, 100), (10, 300), (1300, 2499)])
+def test_persistent_kernel_exact_ties_go_to_the_larger_index(built_lib, a, b):
+    """Q1 (ties -> larger index, ref OfflineRecognizer.cs:145-159) on the persistent kernels: two vocabulary rows with identical
+    weights and a dominant bias tie exactly in every frame - inside one thread's columns, across the two column halves of a tile,
+    across tiles. Greedy must emit the larger id every frame. (Beam search keeps both ids; which hypothesis ends up best depends on
+    1e-6 differences of the log-softmax normalisers of the two contexts, so only its score and alphabet are checked.)"""
+    dims = synth.ModelDims(vocab_size=2500, joiner_dim=64, decoder_dim=48, encoder_dim=64)
+    w = synth.make_weights(dims, blank_bias=0.0)
+    w["out_w"][b] = w["out_w"][a]
+    w["out_b"][a] = w["out_b"][b] = 60.0
+    h = make(dims, w, "bf16x3")
+    B, T = 5, 9
+    raw = synth.make_frames(B, T, dims.encoder_dim, 99)
+    t, s = h.greedy_offline(raw, _native.GREEDY_PER_STREAM, enc_is_raw=True)
+    assert all(t[i] == [b] * T and s[i] == list(range(T)) for i in range(B)), t
+    tb, sb, scb = h.modified_beam_search(raw, 4, enc_is_raw=True)
+    assert all(len(tb[i]) == T and set(tb[i]) <= {a, b} for i in range(B)), tb
+    m = O.Model.from_dict(w)
+    want = O.modified_beam_search(m, O.encoder_proj(m, raw[:2]), 4)
+    for i, r in enumerate(want):
+        assert abs(float(scb[i]) - r.score) < SCORE_TOL
+    h.close()
