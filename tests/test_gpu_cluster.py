@@ -577,3 +577,20 @@ def test_persistent_kernel_exact_ties_go_to_the_larger_index(built_lib, a, b):
     for i, r in enumerate(want):
         assert abs(float(scb[i]) - r.score) < SCORE_TOL
     h.close()
+
+
+def test_persistent_online_masks_id_1(built_lib):
+    """The literal `y != 1` of the online loop (ref OnlineRecognizer.cs:181) on the persistent greedy kernel: id 1 dominant in every
+    frame is emitted by the offline search and swallowed by the online one, which leaves Hyp untouched."""
+    dims = synth.ModelDims(vocab_size=2500, joiner_dim=64, decoder_dim=48, encoder_dim=64)
+    w = synth.make_weights(dims, blank_bias=0.0)
+    w["out_b"][1] = 60.0
+    h = make(dims, w, "bf16x3")
+    B, T = 4, 8
+    raw = synth.make_frames(B, T, dims.encoder_dim, 98)
+    t, s = h.greedy_offline(raw, _native.GREEDY_PER_STREAM, enc_is_raw=True)
+    assert all(t[i] == [1] * T for i in range(B))
+    hyp = np.array([[7, 9]] * B, np.int64)
+    t, s, hyp2 = h.greedy_online_chunk(raw, hyp.copy(), enc_is_raw=True)
+    assert all(t[i] == [] and s[i] == [] for i in range(B)) and hyp2.tolist() == hyp.tolist()
+    h.close()
