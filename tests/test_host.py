@@ -113,3 +113,19 @@ def test_pad_batch_pads_with_zero_frames():
     b = P.OfflineInputEntity(Speech=np.ones((5, 4), np.float32))
     x = P._pad_batch([a, b], 4)
     assert x.shape == (2, 5, 4) and x[0, 3:].sum() == 0
+
+
+def test_bench_clock_sampler_summary():
+    """bench.py's clock / throttle-reason summary (rows as nvidia-smi's csv or the NVML sampler produce them)."""
+    import importlib.util
+    import pathlib
+    spec = importlib.util.spec_from_file_location("bench_mod", pathlib.Path(__file__).resolve().parents[1] / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    c = bench.ClockSampler(0)
+    c.rows = [["1965", "1965", "700.0", "Not Active", "Not Active", "Not Active", "Not Active"],
+              ["1950", "1965", "990.0", "Not Active", "Not Active", "Not Active", "Active"],
+              ["1965", "1965", "710.0", "Not Active", "Not Active", "Not Active", "Not Active"]]
+    s = c.summary()
+    assert s["sm_mhz"] == 1965.0 and s["sm_max_mhz"] == 1965.0 and s["reasons"] == ["sw_power_cap"] and s["samples"] == 3
+    assert bench.ClockSampler(0).summary()["sm_mhz"] is None
