@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define K2B_ABI_VERSION 1
+#define K2B_ABI_VERSION 2
 
 #if defined(_WIN32)
 #define K2B_API __declspec(dllexport)
@@ -103,7 +103,20 @@ K2B_API int32_t k2b_set_precision(k2b_handle* h, int32_t precision);
 /* Make the handle launch on a caller-owned cudaStream_t (e.g. torch's current stream); NULL
  * restores the handle's own stream. */
 K2B_API int32_t k2b_set_stream(k2b_handle* h, void* cuda_stream);
+/* Waits for everything enqueued on the handle's stream, then reports what the kernels flagged since the last check: an mbarrier /
+ * counter time-out (K2B_ERR_STATE) or a Hyp with ids outside the vocabulary handed to a _dev entry point (K2B_ERR_INVALID).     */
 K2B_API int32_t k2b_sync(k2b_handle* h);
+/* Engine switches and search options by name (the K2B_* environment variables only seed them when the handle is created):
+ *   "max_sym_per_frame" 1..16  symbols one frame may emit in k2b_greedy_offline SINGLE / PER_STREAM (ref OfflineRecognizer.cs:19,
+ *                              :127-134; the reference fixes 1). Values > 1 run on the per-frame launches.
+ *   "async_d2h" 0/1            host-pointer fused calls return once their copies are enqueued (give them pinned buffers, see
+ *                              k2b_host_alloc); k2b_sync() completes them. Lets batch i's results leave while batch i+1 arrives.
+ *   "pipe_chunks" 0..64        time chunks of the host-pointer beam search (0 = automatic)
+ *   "no_mega", "unfused_step", "greedy_persistent" (-1 auto / 0 / 1), "pair", "prof_which", "cluster_timing" (0 = off):
+ *                              comparison switches between engines that must give identical results.        */
+K2B_API int32_t k2b_set_option(k2b_handle* h, const char* name, int32_t value);
+/* "decoder_table_bytes", "decoder_table_build_ms", "decoder_table_state" (0 not built, 1 built, -1 does not fit).               */
+K2B_API int32_t k2b_get_stat(k2b_handle* h, const char* name, double* value);
 /* number of this library's kernels launched on the handle since creation / last reset. */
 K2B_API int64_t k2b_launch_count(const k2b_handle* h);
 K2B_API int32_t k2b_reset_launch_count(k2b_handle* h);
@@ -133,12 +146,21 @@ K2B_API int32_t k2b_encoder_proj_dev(k2b_handle* h, const float* raw, int32_t n,
  * `enc` is [B,T,J] already projected when enc_is_raw == 0, or raw [B,T,E] (then encoder_proj
  * runs first, on device) when enc_is_raw != 0.                                                  */
 
+/* Page-locked host buffers. Managed arrays handed over P/Invoke are pageable: their copies go through the driver's staging buffer
+ * at a fraction of the PCIe rate and block the caller. Frame / result buffers taken from k2b_host_alloc (or registered in place
+ * with k2b_host_register, e.g. a pinned GCHandle) are copied by DMA, asynchronously.                                              */
+K2B_API int32_t k2b_host_alloc(void** out, int64_t bytes);
+K2B_API int32_t k2b_host_free(void* p);
+K2B_API int32_t k2b_host_register(void* p, int64_t bytes);
+K2B_API int32_t k2b_host_unregister(void* p);
+
 /* Ragged batches. The reference carries `encoder_out_lens` through its seam (ref Model/EncoderOutputEntity.cs:10-20,
  * OfflineProjOfTransducer.cs:84) but never consumes it: padded frames are decoded like speech (Q7). This call hands the
  * per-stream frame counts (HOST pointer, [B], each 0..T) to the NEXT k2b_greedy_offline[_dev] (modes SINGLE / PER_STREAM)
  * or k2b_modified_beam_search[_dev] call of this handle; stream b is then decoded over frames [0, lens[b]) only, its
- * hypotheses frozen afterwards. The setting is consumed by that call. lens == NULL clears it. BATCH_COMPAT greedy (the
- * reference's own loop, which couples the streams of a batch) rejects it with K2B_ERR_UNSUPPORTED.                  */
+ * hypotheses frozen afterwards. The setting is consumed by that call (an online chunk call in between discards it: the online
+ * loops have no lengths). lens == NULL clears it. BATCH_COMPAT greedy (the reference's own loop, which couples the streams of a
+ * batch) rejects it with K2B_ERR_UNSUPPORTED.                                                                          */
 K2B_API int32_t k2b_set_encoder_out_lens(k2b_handle* h, const int64_t* lens, int32_t B);
 
 /* replaces: ForwardGreedySearch / ForwardBatchGreedySearch (ref OfflineRecognizer.cs:93-303).
@@ -166,6 +188,28 @@ K2B_API int32_t k2b_modified_beam_search(k2b_handle* h, const float* enc, int32_
 K2B_API int32_t k2b_modified_beam_search_dev(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t T,
                                      int32_t K, int64_t* tokens, int32_t* ts, int32_t* n_out, float* score,
                                      int32_t cap);
+
+/* Streaming modified_beam_search: what `decodingMethod` / `maxActivePaths` of the online recognizer (ref OnlineRecognizer.cs:18-19,
+ * accepted and ignored there, :46-57) select on this path. A stream's K live hypotheses and the back-pointer history of every
+ * frame decoded so far live in a device slot (as the encoder caches do, k2b_state_pool_*); the slot takes the place of
+ * OnlineStream.Hyp as the state carried between GetResults calls (ref OnlineStream.cs:44-55, OnlineRecognizer.cs:206-213).
+ *   k2b_beam_pool_create   max_streams slots, beam K (1..8), max_frames frames of history per stream.
+ *   k2b_beam_pool_reset    new utterance in `slot`: one hypothesis with context hyp[0..1] = OnlineStream.Hyp ({blank, blank},
+ *                          ref OnlineStream.cs:44) or, hyp == NULL, the offline seed {-1, blank}.
+ *   ..._online_chunk       decodes Tc more frames of the B streams whose slots are listed (HOST pointer, distinct) and returns, per
+ *                          stream, the WHOLE best hypothesis so far (log_prob / len rule of k2b_modified_beam_search): tokens /
+ *                          ts [B,cap] (ts = frame index since the reset; the first cap symbols when n_out exceeds cap), score, and
+ *                          hyp_out [B,ctx] = its last ctx tokens (NULL: not wanted). Non-emitting ids: blank, unk and the literal 1
+ *                          of the online loop (ref OnlineRecognizer.cs:181). Decoding an utterance chunk by chunk gives exactly
+ *                          what k2b_modified_beam_search gives on the whole of it.                                               */
+K2B_API int32_t k2b_beam_pool_create(k2b_handle* h, int32_t max_streams, int32_t K, int32_t max_frames);
+K2B_API int32_t k2b_beam_pool_reset(k2b_handle* h, int32_t slot, const int64_t* hyp);
+K2B_API int32_t k2b_modified_beam_search_online_chunk(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t Tc,
+                                                      const int32_t* slots, int64_t* hyp_out, int64_t* tokens, int32_t* ts,
+                                                      int32_t* n_out, float* score, int32_t cap);
+K2B_API int32_t k2b_modified_beam_search_online_chunk_dev(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t Tc,
+                                                          const int32_t* slots, int64_t* hyp_out, int64_t* tokens, int32_t* ts,
+                                                          int32_t* n_out, float* score, int32_t cap);
 
 /* replaces: ForwardGreedySearchCTC / ForwardBatchGreedySearchCTC (ref OfflineRecognizer.cs:305-430)
  * and the online variant (ref OnlineRecognizer.cs:220-319). logp [B,T,V]; V is an argument because
@@ -198,7 +242,24 @@ K2B_API int32_t k2b_state_pool_get(k2b_handle* h, int32_t slot, float* state);
 K2B_API int32_t k2b_stack_states(k2b_handle* h, const int32_t* slots, int32_t B, const int32_t* axis_len, float* stacked);
 K2B_API int32_t k2b_unstack_states(k2b_handle* h, const int32_t* slots, int32_t B, const int32_t* axis_len, const float* stacked);
 
+/* ---- multi-GPU: results of all ranks (reporting only; no collective runs inside a search) ------ */
+/* One process per GPU, every rank decodes its own streams; the only exchange is one all-gather of the results over NVLink.
+ * libnccl.so.2 is loaded on first use (no link-time dependency). Rank 0 obtains a 128-byte id with k2b_nccl_unique_id and
+ * hands it to the other ranks by any means (bench.py: torch.distributed broadcast), every rank calls k2b_nccl_init once.
+ * k2b_gather_results_nccl: DEVICE pointers; tokens / ts [B,cap], n / score [B] of this rank in, rank-major [nranks*B, ...] out;
+ * enqueued on the handle's stream behind the search that produced the inputs, no host synchronisation. B and cap must be the same
+ * on every rank. score / all_score may both be NULL.                                                                           */
+K2B_API int32_t k2b_nccl_unique_id(void* id128);
+K2B_API int32_t k2b_nccl_init(k2b_handle* h, const void* id128, int32_t rank, int32_t nranks);
+K2B_API int32_t k2b_gather_results_nccl(k2b_handle* h, const int64_t* tokens, const int32_t* ts, const int32_t* n, const float* score,
+                                        int32_t B, int32_t cap, int64_t* all_tokens, int32_t* all_ts, int32_t* all_n, float* all_score);
+
 /* ---- diagnostics ---------------------------------------------------------------------------- */
+/* Back-pointer rows of the LAST beam search of this handle, HOST pointer [B,T,K] int32: entry = (parent slot << 28) | (appended
+ * token + 1), 0 for a dead slot - the whole history of every stream's beam, frame by frame. The parity tests compare it with
+ * the oracle's beams to find the frame at which a stream first diverges (and so verify the 64-bit sequence-hash dedupe against
+ * real token sequences).                                                                                                     */
+K2B_API int32_t k2b_debug_backpointers(k2b_handle* h, int32_t* out, int32_t B, int32_t T, int32_t K);
 /* Hardware self-tests of the tcgen05 / TMEM / bulk-TMA / cluster building blocks (HOST pointers).
  * k2b_selftest_umma: D[128,N] = A[128,K] * B[N,K]^T through tcgen05.mma; mode 0 = bf16 operands in
  * shared memory, 1 = split-bf16 x3 all in shared memory, 2 = x3 with the low part of A resident in
@@ -224,10 +285,11 @@ K2B_API int32_t k2b_selftest_dsmem_bw(k2b_handle* h, int32_t csize, int32_t nclu
 K2B_API int32_t k2b_selftest_cluster(k2b_handle* h, int32_t csize, int32_t nclusters, int32_t* bad,
                                      int32_t* ctas_done);
 
-/* Cycle totals (12 slots) of the phases of one frame step (build, sync, MMA issue, MMA wait, TMEM read-out,
- * reductions + DSMEM, cluster barrier, merge) summed over the last cluster-kernel launch, CTA 0. The first
- * call switches the collection on.                                                                    */
-K2B_API int32_t k2b_cluster_phase_cycles(k2b_handle* h, int64_t* out12);
+/* Cycle totals (out20: 20 int64 slots) of the phases of one frame step (0-7: build, MMA wait, TMEM read-out, reductions, exchange,
+ * exchange wait, merge, end barrier; 8-14: merge sub-steps; 15-18: the four K-quarters of the build) summed over the last
+ * cluster-kernel launch, CTA 0. The first call switches the collection on (the instrumented kernel instantiation then serves
+ * every launch); k2b_set_option(h, "cluster_timing", 0) switches it off again.                                           */
+K2B_API int32_t k2b_cluster_phase_cycles(k2b_handle* h, int64_t* out20);
 
 /* Diagnostic clock64 timeline of the large-vocabulary beam search (joiner_tc.cu). The first call allocates the buffer and
  * switches the collection on; later calls copy out [64][148][8] int64 stamps and re-arm. Persistent kernel: CTA 0 writes

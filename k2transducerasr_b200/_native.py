@@ -66,6 +66,20 @@ _SIGS = {
     "k2b_modified_beam_search_dev": (C.c_int32, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I]),
     "k2b_ctc_greedy": (C.c_int32, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I]),
     "k2b_ctc_greedy_dev": (C.c_int32, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I]),
+    "k2b_set_option": (C.c_int32, [_P, C.c_char_p, _I]),
+    "k2b_get_stat": (C.c_int32, [_P, C.c_char_p, C.POINTER(C.c_double)]),
+    "k2b_host_alloc": (C.c_int32, [C.POINTER(_P), C.c_int64]),
+    "k2b_host_free": (C.c_int32, [_P]),
+    "k2b_host_register": (C.c_int32, [_P, C.c_int64]),
+    "k2b_host_unregister": (C.c_int32, [_P]),
+    "k2b_beam_pool_create": (C.c_int32, [_P, _I, _I, _I]),
+    "k2b_beam_pool_reset": (C.c_int32, [_P, _I, _P]),
+    "k2b_modified_beam_search_online_chunk": (C.c_int32, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I]),
+    "k2b_modified_beam_search_online_chunk_dev": (C.c_int32, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I]),
+    "k2b_nccl_unique_id": (C.c_int32, [_P]),
+    "k2b_nccl_init": (C.c_int32, [_P, _P, _I, _I]),
+    "k2b_gather_results_nccl": (C.c_int32, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
+    "k2b_debug_backpointers": (C.c_int32, [_P, _P, _I, _I, _I]),
     "k2b_selftest_umma": (C.c_int32, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "k2b_state_pool_create": (C.c_int32, [_P, _P, _I, _I]),
     "k2b_state_pool_stacked_floats": (C.c_int64, [_P, _I]),
@@ -90,6 +104,7 @@ def header_symbols() -> list[str]:
 
 
 _lib = None
+_HOST_ALLOCS: dict = {}
 
 
 def lib() -> C.CDLL:
@@ -191,6 +206,14 @@ class Handle:
 
     def sync(self):
         self._check(self._lib.k2b_sync(self._h))
+
+    def set_option(self, name: str, value: int):
+        self._check(self._lib.k2b_set_option(self._h, name.encode(), int(value)))
+
+    def get_stat(self, name: str) -> float:
+        v = C.c_double(0.0)
+        self._check(self._lib.k2b_get_stat(self._h, name.encode(), C.byref(v)))
+        return float(v.value)
 
     def launch_count(self) -> int:
         return int(self._lib.k2b_launch_count(self._h))
@@ -294,6 +317,37 @@ class Handle:
         toks, tss = self._unpack(tokens, ts, n)
         return toks, tss, score
 
+    # -- streaming modified_beam_search (hypotheses carried between chunks in device slots) ---------------------
+    def beam_pool_create(self, max_streams: int, beam: int = 4, max_frames: int = 4096):
+        self._check(self._lib.k2b_beam_pool_create(self._h, int(max_streams), int(beam), int(max_frames)))
+
+    def beam_pool_reset(self, slot: int, hyp: Optional[Sequence[int]] = None):
+        v = None if hyp is None else np.ascontiguousarray(hyp, dtype=np.int64)
+        self._check(self._lib.k2b_beam_pool_reset(self._h, int(slot), _ptr(v)))
+
+    def modified_beam_search_online_chunk(self, enc: np.ndarray, slots: Sequence[int], cap: int = 512,
+                                          enc_is_raw: Optional[bool] = None):
+        """Returns (tokens, timestamps, score, hyp): per stream the whole best hypothesis since the slot's reset."""
+        enc, B, T, raw = self._frames(enc)
+        if enc_is_raw is not None:
+            raw = int(enc_is_raw)
+        sl = np.ascontiguousarray(slots, dtype=np.int32)
+        assert sl.size == B
+        tokens = np.zeros((B, cap), np.int64); ts = np.zeros((B, cap), np.int32); n = np.zeros(B, np.int32)
+        score = np.zeros(B, np.float32); hyp = np.zeros((B, self.cfg.context_size), np.int64)
+        self._check(self._lib.k2b_modified_beam_search_online_chunk(self._h, _ptr(enc), raw, B, T, _ptr(sl), _ptr(hyp), _ptr(tokens),
+                                                                    _ptr(ts), _ptr(n), _ptr(score), cap))
+        if (n > cap).any():
+            raise K2bError(K2B_ERR_INVALID, f"cap {cap} is too small for a hypothesis of {int(n.max())} symbols")
+        toks, tss = self._unpack(tokens, ts, n)
+        return toks, tss, score, hyp
+
+    def debug_backpointers(self, B: int, T: int, K: int) -> np.ndarray:
+        """[B,T,K] back-pointer history of the last beam search: entry = (parent slot << 28) | (token + 1)."""
+        out = np.zeros((B, T, K), np.int32)
+        self._check(self._lib.k2b_debug_backpointers(self._h, _ptr(out), B, T, K))
+        return out
+
     def ctc_greedy(self, logp: np.ndarray, blank: int = 0, frame_offset: Optional[Sequence[int]] = None,
                    prev: Optional[np.ndarray] = None, trailing_blank: Optional[np.ndarray] = None):
         logp = np.ascontiguousarray(logp, dtype=np.float32)
@@ -379,6 +433,28 @@ class Handle:
         bad, done = C.c_int32(-1), C.c_int32(-1)
         self._check(self._lib.k2b_selftest_cluster(self._h, csize, nclusters, C.byref(bad), C.byref(done)))
         return int(bad.value), int(done.value)
+
+    # -- page-locked host memory ---------------------------------------------------------------------------------
+    @staticmethod
+    def host_alloc(shape, dtype) -> np.ndarray:
+        """A numpy array over page-locked memory from k2b_host_alloc (freed with host_free(arr))."""
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape)) * dt.itemsize
+        p = _P()
+        st = lib().k2b_host_alloc(C.byref(p), max(n, 1))
+        if st != K2B_OK:
+            raise K2bError(st, "k2b_host_alloc failed")
+        buf = (C.c_char * max(n, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+        arr.flags.writeable = True
+        _HOST_ALLOCS[arr.ctypes.data] = p.value
+        return arr
+
+    @staticmethod
+    def host_free(arr: np.ndarray):
+        p = _HOST_ALLOCS.pop(arr.ctypes.data, None)
+        if p is not None:
+            lib().k2b_host_free(p)
 
     # -- raw pointer access for device-resident / pinned buffers (bench.py, dist.py) ---------------------------
     def call(self, name: str, *args):

@@ -44,9 +44,23 @@ def _digest() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """Idempotent and safe under torchrun: the ranks of one box serialise on a file lock, the first one compiles, the others find
+    the stamp up to date when they get the lock."""
+    import fcntl
     digest = _digest()
     if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
         return LIB
+    with open(PKG / ".build_lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
+                return LIB
+            return _build_locked(digest, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(digest: str, verbose: bool) -> Path:
     nvcc = _nvcc()
     objdir = PKG / "build"
     objdir.mkdir(exist_ok=True)
@@ -67,8 +81,10 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     (objdir / "ptxas.log").write_text("\n".join(log))
     if verbose:
         print("\n".join(log))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-Xlinker", "--exclude-libs,ALL", "-cudart", "static"]
+    tmp = LIB.with_suffix(".so.tmp")
+    cmd = [nvcc, "-shared", "-o", str(tmp), *map(str, objs), "-Xlinker", "--exclude-libs,ALL", "-cudart", "static", "-ldl"]
     subprocess.run(cmd, check=True)
+    os.replace(tmp, LIB)              # a process that already mapped the old file keeps it
     STAMP.write_text(digest)
     return LIB
 

@@ -26,6 +26,42 @@ __global__ void ctx_from_i64_kernel(const int64_t* __restrict__ y, int n, int bl
   }
 }
 
+// OnlineStream.Hyp arrives from the caller: ids outside the vocabulary must not become table addresses. Device-pointer callers get
+// the ids clamped to blank and the error reported by the next k2b_sync / host-pointer call (dev_status[2]).
+__global__ void check_hyp_kernel(int64_t* __restrict__ hyp, int B, int V, int blank, int allow_neg_tail, int* __restrict__ status) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int64_t c0 = hyp[2 * b], c1 = hyp[2 * b + 1];
+  const bool bad0 = c0 < -1 || c0 >= V, bad1 = c1 >= V || c1 < (allow_neg_tail ? -1 : 0);
+  if (bad0) hyp[2 * b] = blank;
+  if (bad1) hyp[2 * b + 1] = blank;
+  if (bad0 || bad1) atomicExch(status + 2, 1);
+}
+__global__ void fill_hyp_kernel(int64_t* __restrict__ hyp, int B, int c0, int c1) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) { hyp[2 * b] = c0; hyp[2 * b + 1] = c1; }
+}
+// Q6: frame of the batch's first emission = min over the streams of their first timestamp (T when nobody emits)
+__global__ void first_emission_kernel(const int32_t* __restrict__ ts, const int32_t* __restrict__ n, int B, int cap, int T, int* __restrict__ tstar) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B && n[b] > 0) atomicMin(tstar, ts[(size_t)b * cap]);
+}
+// streams that had not emitted when the batch first did are decoded again from frame tstar + 1 with the context {blank, blank}
+// (pass 2); every other stream keeps its pass-1 result
+__global__ void compat_select_kernel(int B, int cap, int tstar, int ts_off, const int64_t* __restrict__ tok2, const int32_t* __restrict__ ts2,
+                                     const int32_t* __restrict__ n2, int64_t* __restrict__ tok, int32_t* __restrict__ ts, int32_t* __restrict__ n) {
+  const int b = blockIdx.x;
+  const bool redo = n[b] == 0 || ts[(size_t)b * cap] > tstar;
+  __syncthreads();
+  if (!redo) return;
+  const int m = n2[b];
+  for (int i = threadIdx.x; i < m && i < cap; i += blockDim.x) {
+    tok[(size_t)b * cap + i] = tok2[(size_t)b * cap + i];
+    ts[(size_t)b * cap + i] = ts2[(size_t)b * cap + i] + ts_off;
+  }
+  if (threadIdx.x == 0) n[b] = m;
+}
+
 void free_buf(DevBuf& b) {
   if (b.p) cudaFree(b.p);
   b.p = nullptr;
@@ -38,6 +74,7 @@ void free_cluster_assets(k2b_handle* h) {
   if (h->bias_pad) cudaFree(h->bias_pad);
   if (h->dec_tab) cudaFree(h->dec_tab);
   h->wo_hi_img = nullptr; h->wo_lo = nullptr; h->bias_pad = nullptr; h->dec_tab = nullptr; h->dec_tab_state = 0;
+  h->dec_tab_bytes = 0; h->dec_tab_build_ms = 0.f;
   h->tc_ready = false;
   if (h->we_hi_img) cudaFree(h->we_hi_img);
   if (h->we_lo_img) cudaFree(h->we_lo_img);
@@ -140,7 +177,7 @@ int32_t beam_cluster_pipelined(k2b_handle* h, const float* enc_host, int B, int 
   // up to 10 chunks of at least 8 frames: measured on cfg2 (PCIe-bound, 196 MB in) 4 chunks 4.04 ms, 8 chunks 3.85 ms, 12 chunks
   // 3.81 ms per batch - the un-overlapped tail (last chunk's projection + search) shrinks, each extra launch costs ~30 us
   int nchunk = T / 8 < 10 ? (T / 8 > 0 ? T / 8 : 1) : 10;
-  if (const char* e = getenv("K2B_PIPE_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= 64) nchunk = v; }
+  if (h->opt_pipe_chunks >= 1) nchunk = h->opt_pipe_chunks;
   const int Tc = (T + nchunk - 1) / nchunk;
   if (h->copy_stream == nullptr) {
     K2B_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -206,7 +243,7 @@ int32_t beam_chunked_host(k2b_handle* h, const float* enc_host, int B, int T, in
   // each chunk is one persistent launch (~20 us of set-up); measured on cfg4 (131 MB in): 3 chunks 6.06 ms, 5 chunks 5.82 ms,
   // 8 chunks 5.64 ms, 12 chunks 5.67 ms per batch
   int nchunk = T / 30 < 8 ? (T / 30 > 0 ? T / 30 : 1) : 8;
-  if (const char* e = getenv("K2B_PIPE_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= 64) nchunk = v; }
+  if (h->opt_pipe_chunks >= 1) nchunk = h->opt_pipe_chunks;
   const int Tc = (T + nchunk - 1) / nchunk;
   if (h->copy_stream == nullptr) {
     K2B_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -346,7 +383,50 @@ int32_t k2b_create(const k2b_config* cfg, k2b_handle** out) {
   e = cudaMalloc(reinterpret_cast<void**>(&h->dev_status), 4 * sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(h->dev_status, 0, 4 * sizeof(int));
   if (e != cudaSuccess) { cudaStreamDestroy(h->own_stream); delete h; return cuda_fail(nullptr, e, "cudaMalloc(status)", __FILE__, __LINE__); }
+  // engine switches: the environment only seeds them (tools set it before creating the handle); k2b_set_option changes them later
+  auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e != nullptr ? atoi(e) : dflt; };
+  h->opt_pipe_chunks = env_int("K2B_PIPE_CHUNKS", 0);
+  h->opt_no_mega = env_int("K2B_NO_MEGA", 0);
+  h->opt_unfused_step = env_int("K2B_UNFUSED_STEP", 0);
+  h->opt_greedy_persistent = env_int("K2B_GREEDY_PERSISTENT", -1);
+  h->opt_pair = env_int("K2B_PAIR", 0);
+  h->prof_which = env_int("K2B_PROF_WHICH", 0);
   *out = h;
+  return K2B_OK;
+}
+
+int32_t k2b_set_option(k2b_handle* h, const char* name, int32_t value) {
+  K2B_TRY(enter(h));
+  if (name == nullptr) return fail(h, K2B_ERR_INVALID, "k2b_set_option: name is NULL");
+  const std::string n(name);
+  if (n == "pipe_chunks") { if (value < 0 || value > 64) return fail(h, K2B_ERR_INVALID, "pipe_chunks: 0 (auto) .. 64"); h->opt_pipe_chunks = value; }
+  else if (n == "no_mega") h->opt_no_mega = value;
+  else if (n == "unfused_step") h->opt_unfused_step = value;
+  else if (n == "greedy_persistent") h->opt_greedy_persistent = value;
+  else if (n == "pair") h->opt_pair = value;
+  else if (n == "prof_which") h->prof_which = value;
+  else if (n == "async_d2h") h->opt_async_d2h = value;
+  else if (n == "max_sym_per_frame") {
+    if (value < 1 || value > 16) return fail(h, K2B_ERR_INVALID, "max_sym_per_frame: 1 .. 16");
+    h->max_sym_per_frame = value;
+  } else if (n == "cluster_timing") {
+    if (value == 0 && h->cluster_timing != nullptr) {
+      K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+      cudaFree(h->cluster_timing);
+      h->cluster_timing = nullptr;
+    }
+  } else return fail(h, K2B_ERR_INVALID, "k2b_set_option: unknown option " + n);
+  return K2B_OK;
+}
+
+int32_t k2b_get_stat(k2b_handle* h, const char* name, double* value) {
+  K2B_TRY(enter(h));
+  if (name == nullptr || value == nullptr) return fail(h, K2B_ERR_INVALID, "k2b_get_stat: NULL argument");
+  const std::string n(name);
+  if (n == "decoder_table_bytes") *value = (double)h->dec_tab_bytes;
+  else if (n == "decoder_table_build_ms") *value = (double)h->dec_tab_build_ms;
+  else if (n == "decoder_table_state") *value = (double)h->dec_tab_state;
+  else return fail(h, K2B_ERR_INVALID, "k2b_get_stat: unknown statistic " + n);
   return K2B_OK;
 }
 
@@ -358,6 +438,8 @@ int32_t k2b_destroy(k2b_handle* h) {
   for (float** p : ws) { if (*p) cudaFree(*p); *p = nullptr; }
   free_cluster_assets(h);
   state_pool_free(h);
+  beam_pool_free(h);
+  nccl_free(h);
   if (h->lens_dev) cudaFree(h->lens_dev);
   if (h->cluster_timing) cudaFree(h->cluster_timing);
   if (h->timeline) cudaFree(h->timeline);
@@ -426,7 +508,7 @@ int32_t k2b_set_stream(k2b_handle* h, void* cuda_stream) {
 int32_t k2b_sync(k2b_handle* h) {
   K2B_TRY(enter(h));
   K2B_CUDA(h, cudaStreamSynchronize(h->stream));
-  return K2B_OK;
+  return cluster_status(h);          // device-pointer callers learn of kernel time-outs / rejected Hyp ids here
 }
 
 int64_t k2b_launch_count(const k2b_handle* h) { return h ? h->launches : 0; }
@@ -440,7 +522,6 @@ int32_t k2b_reset_launch_count(k2b_handle* h) {
 int32_t k2b_profile_enable(k2b_handle* h, int32_t on) {
   K2B_TRY(enter(h));
   h->profile_on = on != 0;
-  if (const char* w = getenv("K2B_PROF_WHICH")) h->prof_which = atoi(w);
   return K2B_OK;
 }
 
@@ -460,9 +541,11 @@ int32_t k2b_profile_read(k2b_handle* h, int64_t* n_launches, double* total_ms) {
   return K2B_OK;
 }
 
-// diagnostic: per-phase cycle totals of the last cluster-kernel launch (8 values); enables collection on first call
-K2B_API int32_t k2b_cluster_phase_cycles(k2b_handle* h, int64_t* out8) {
+// diagnostic: per-phase cycle totals of the last cluster-kernel launch (20 values); enables collection on first call,
+// k2b_set_option("cluster_timing", 0) switches it off again (production launches then use the uninstrumented kernel)
+K2B_API int32_t k2b_cluster_phase_cycles(k2b_handle* h, int64_t* out20) {
   K2B_TRY(enter(h));
+  if (out20 == nullptr) return fail(h, K2B_ERR_INVALID, "k2b_cluster_phase_cycles: out20 is NULL");
   if (h->cluster_timing == nullptr) {
     K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->cluster_timing), 20 * sizeof(long long)));
     K2B_CUDA(h, cudaMemset(h->cluster_timing, 0, 20 * sizeof(long long)));
@@ -470,7 +553,7 @@ K2B_API int32_t k2b_cluster_phase_cycles(k2b_handle* h, int64_t* out8) {
   K2B_CUDA(h, cudaStreamSynchronize(h->stream));
   long long v[20];
   K2B_CUDA(h, cudaMemcpy(v, h->cluster_timing, sizeof(v), cudaMemcpyDeviceToHost));
-  for (int i = 0; i < 20; ++i) out8[i] = v[i];
+  for (int i = 0; i < 20; ++i) out20[i] = v[i];
   K2B_CUDA(h, cudaMemset(h->cluster_timing, 0, sizeof(v)));
   return K2B_OK;
 }
@@ -619,7 +702,8 @@ int32_t k2b_unstack_states(k2b_handle* h, const int32_t* slots, int32_t B, const
 }
 
 // ---- ragged batches -----------------------------------------------------------------------------------
-// The per-stream frame counts set by k2b_set_encoder_out_lens are consumed by the next fused offline search call.
+// The per-stream frame counts set by k2b_set_encoder_out_lens are consumed by the next fused offline search call; an online chunk
+// call in between discards them (the online loops have no lengths: ref OnlineRecognizer.cs:85-219).
 namespace {
 struct LensGuard {
   k2b_handle* h;
@@ -633,6 +717,25 @@ int32_t check_lens(k2b_handle* h, int B, const char* who) {
   }
   return K2B_OK;
 }
+
+int32_t check_hyp_host(k2b_handle* h, const int64_t* hyp, int B, bool allow_neg_tail, const char* who) {
+  const int64_t V = h->cfg.vocab_size;
+  for (int b = 0; b < B; ++b) {
+    const int64_t c0 = hyp[2 * b], c1 = hyp[2 * b + 1];
+    if (c0 < -1 || c0 >= V || c1 >= V || c1 < (allow_neg_tail ? -1 : 0))
+      return fail(h, K2B_ERR_INVALID, std::string(who) + ": Hyp of stream " + std::to_string(b) + " holds a token id outside the vocabulary");
+  }
+  return K2B_OK;
+}
+
+// host-pointer fused calls end here: results are on their way to the caller's buffers; wait for them (and for the kernels' status
+// word) unless the caller asked for overlap (k2b_set_option("async_d2h", 1) with pinned buffers: k2b_sync completes the call)
+int32_t finish_host_call(k2b_handle* h) {
+  if (h->opt_async_d2h) return K2B_OK;
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  return cluster_status(h);
+}
+
 }  // namespace
 
 int32_t k2b_set_encoder_out_lens(k2b_handle* h, const int64_t* lens, int32_t B) {
@@ -661,10 +764,98 @@ int32_t k2b_set_encoder_out_lens(k2b_handle* h, const int64_t* lens, int32_t B) 
 // on the persistent beam kernel beyond that - and also for 1024 < V <= 2048 when the batch needs three or more waves of 16-CTA
 // clusters (about six of them, 32 streams each, are co-resident). Measured on cfg3 (V = 2000, 512 streams, chunks of 8 frames):
 // cluster kernel 185 us per chunk, persistent kernel 147 us (its merge warps step four streams at once, greedy_merge_warp).
-// K2B_GREEDY_PERSISTENT=0/1 overrides the choice (comparison runs, tests).
+// k2b_set_option("greedy_persistent", 0/1) overrides the choice (comparison runs, tests).
 static bool prefer_persistent_greedy(k2b_handle* h, int B) {
-  if (const char* e = getenv("K2B_GREEDY_PERSISTENT")) return atoi(e) != 0 && beam_greedy_usable(h);
+  if (h->opt_greedy_persistent >= 0) return h->opt_greedy_persistent != 0 && beam_greedy_usable(h);
   return h->cfg.vocab_size > 1024 && B > 384 && beam_greedy_usable(h);
+}
+
+// One pass of per-stream greedy search on the fast engines (beam 1 on the cluster kernel or on the persistent kernel) over frames
+// [t_begin, T) of a [B,T,.] batch. hyp_in (device, [B,2]) seeds the contexts (nullptr = {-1, blank}); extra_mask is the online
+// loop's literal 1 or -1. `frames_ready`: ws_encproj already holds this batch's frames in the engine's form (second pass of
+// BATCH_COMPAT). Timestamps are frame indices of the whole utterance on the cluster kernel and relative to t_begin on the
+// persistent kernel (*ts_rel tells).
+static int32_t greedy_fast_pass(k2b_handle* h, const float* enc, int enc_is_raw, int B, int T, int t_begin, int extra_mask,
+                                int64_t* hyp_inout, int64_t* tokens, int32_t* ts, int32_t* n_out, int cap, bool frames_ready,
+                                bool* ts_rel) {
+  const size_t J = h->cfg.joiner_dim;
+  *ts_rel = false;
+  if (cluster_path_supported(h, 1) && !prefer_persistent_greedy(h, B)) {
+    K2B_TRY(ensure_cluster_assets(h));
+    const size_t n = (size_t)B * T;
+    K2B_TRY(ensure(h, h->ws_encproj, sizeof(float) * n * J));
+    float* encE = static_cast<float*>(h->ws_encproj.p);
+    if (!frames_ready) {
+      if (enc_is_raw) {
+        if (h->cfg.encoder_dim <= 0 || h->enc_w == nullptr) return fail(h, K2B_ERR_STATE, "encoder_proj weights not loaded (E == 0)");
+        if (encproj_tc_supported(h)) {
+          K2B_TRY(encoder_proj_tc(h, enc, (int)n, encE, true));
+        } else {
+          GemmArgs g;
+          g.M = (int)n; g.N = (int)J; g.K = h->cfg.encoder_dim;
+          g.A = enc; g.W = h->enc_w; g.bias = h->enc_b; g.C = encE;
+          K2B_TRY(launch_gemm_simt(h, PRO_PLAIN, EPI_EXP2X, g));
+        }
+      } else {
+        K2B_TRY(exp2x_frames(h, enc, encE, n * J));
+      }
+    }
+    const size_t a4 = ((size_t)B * 4 + 255) & ~size_t(255);
+    K2B_TRY(ensure(h, h->ws_state, 4 * a4));
+    K2B_TRY(ensure(h, h->ws_bp, sizeof(int32_t) * (size_t)B * T));
+    char* p = static_cast<char*>(h->ws_state.p);
+    float* fin_lp = reinterpret_cast<float*>(p); p += a4;
+    int32_t* fin_len = reinterpret_cast<int32_t*>(p); p += a4;
+    int32_t* fin_nlive = reinterpret_cast<int32_t*>(p); p += a4;
+    float* score = reinterpret_cast<float*>(p);
+    int32_t* bp = static_cast<int32_t*>(h->ws_bp.p);
+    if (t_begin > 0) K2B_CUDA(h, cudaMemsetAsync(bp, 0, sizeof(int32_t) * (size_t)B * T, h->stream));   // rows before t_begin: "nothing emitted"
+    K2B_TRY(beam_cluster_dev(h, encE, B, T - t_begin, 1, bp, fin_lp, fin_len, fin_nlive, extra_mask, hyp_inout, hyp_inout, t_begin, T, 0,
+                             nullptr, nullptr, false));
+    return beam_backtrace_dev(h, B, 1, T, fin_lp, fin_len, fin_nlive, bp, tokens, ts, n_out, score, cap);
+  }
+  // large vocabulary: beam 1 on the persistent beam kernel
+  const float* frames = static_cast<const float*>(h->ws_encproj.p);
+  if (!frames_ready) K2B_TRY(frames_for_search(h, enc, enc_is_raw, B, T, &frames));
+  else if (!enc_is_raw) frames = enc;
+  K2B_TRY(ensure(h, h->ws_misc, sizeof(float) * (size_t)B));
+  *ts_rel = t_begin > 0;
+  return beam_dev(h, frames + (size_t)t_begin * J, B, T - t_begin, 1, tokens, ts, n_out, static_cast<float*>(h->ws_misc.p), cap, extra_mask,
+                  hyp_inout, true, 0, 0, false, t_begin > 0 ? (long long)T * (long long)J : 0);
+}
+
+// BATCH_COMPAT on the fast engines. The reference's batch loop (ref OfflineRecognizer.cs:189-303) re-runs the decoder for ALL
+// streams from their token-list tails whenever ANY stream emits (ref :246, :278-286); the lists are seeded with blanks (Q5), so
+// the only effect on a stream is that its context is {blank, blank} instead of {-1, blank} from the frame after the batch's
+// first emission (t*) until its own first emission (Q6) - from then on the tail of its list is what the single-stream loop
+// would use. Hence: pass 1 decodes every stream alone (PER_STREAM); t* = min of the first timestamps; streams that emit at t*
+// are done; the others emitted nothing up to t* and are decoded again over (t*, T) from {blank, blank} (pass 2).
+static int32_t greedy_compat_fast(k2b_handle* h, const float* enc, int enc_is_raw, int B, int T, int64_t* tokens, int32_t* ts,
+                                  int32_t* n_out, int cap) {
+  bool rel = false;
+  K2B_TRY(greedy_fast_pass(h, enc, enc_is_raw, B, T, 0, -1, nullptr, tokens, ts, n_out, cap, false, &rel));
+  int* tstar_dev = h->dev_status + 3;
+  int tstar = T;
+  K2B_CUDA(h, cudaMemcpyAsync(tstar_dev, &tstar, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  first_emission_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(ts, n_out, B, cap, T, tstar_dev);
+  K2B_LAUNCH_CHECK(h);
+  K2B_CUDA(h, cudaMemcpyAsync(&tstar, tstar_dev, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));      // the second pass starts at a data-dependent frame
+  if (tstar + 1 >= T) return K2B_OK;
+  const size_t tok_b = (sizeof(int64_t) * (size_t)B * cap + 255) & ~size_t(255), ts_b = (sizeof(int32_t) * (size_t)B * cap + 255) & ~size_t(255);
+  const size_t n_b = (sizeof(int32_t) * (size_t)B + 255) & ~size_t(255), hyp_b = (sizeof(int64_t) * 2 * (size_t)B + 255) & ~size_t(255);
+  K2B_TRY(ensure(h, h->ws_dec, tok_b + ts_b + n_b + hyp_b));
+  char* p = static_cast<char*>(h->ws_dec.p);
+  int64_t* tok2 = reinterpret_cast<int64_t*>(p); p += tok_b;
+  int32_t* ts2 = reinterpret_cast<int32_t*>(p); p += ts_b;
+  int32_t* n2 = reinterpret_cast<int32_t*>(p); p += n_b;
+  int64_t* hyp2 = reinterpret_cast<int64_t*>(p);
+  fill_hyp_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(hyp2, B, h->cfg.blank_id, h->cfg.blank_id);
+  K2B_LAUNCH_CHECK(h);
+  K2B_TRY(greedy_fast_pass(h, enc, enc_is_raw, B, T, tstar + 1, -1, hyp2, tok2, ts2, n2, cap, true, &rel));
+  compat_select_kernel<<<B, 64, 0, h->stream>>>(B, cap, tstar, rel ? tstar + 1 : 0, tok2, ts2, n2, tokens, ts, n_out);
+  K2B_LAUNCH_CHECK(h);
+  return K2B_OK;
 }
 
 // ---- fused search ---------------------------------------------------------------------------------
@@ -680,18 +871,18 @@ int32_t k2b_greedy_offline_dev(k2b_handle* h, const float* enc, int32_t enc_is_r
     return fail(h, K2B_ERR_UNSUPPORTED, "k2b_greedy_offline: BATCH_COMPAT decodes the padding like the reference (Q7); use PER_STREAM with lengths");
   if (mode == K2B_GREEDY_SINGLE && B != 1) return fail(h, K2B_ERR_INVALID, "k2b_greedy_offline: SINGLE mode needs B == 1");
   if (B == 0) return K2B_OK;
-  // greedy search == beam 1 with the same tie rule: SINGLE / PER_STREAM run on the persistent cluster kernel in the tcgen05
-  // precisions. BATCH_COMPAT (Q6) couples every stream of the batch at every frame and stays on the per-frame path, as does
-  // an utterance long enough to meet the 1000-symbol cap of the single-stream loop (ref OfflineRecognizer.cs:122).
-  const bool as_beam1 = h->cfg.precision != K2B_PREC_FP32 && mode != K2B_GREEDY_BATCH_COMPAT && T > 0 && T <= 1000;
-  if (as_beam1 && cluster_path_supported(h, 1) && !prefer_persistent_greedy(h, B))
-    return beam_cluster_path(h, enc, enc_is_raw, B, T, 1, tokens, ts, n_out, nullptr, cap);
+  // greedy search == beam 1 with the same tie rule: SINGLE / PER_STREAM run on the persistent kernels in the tcgen05 precisions,
+  // BATCH_COMPAT as two such passes (greedy_compat_fast). The per-frame path keeps: fp32 precision, an utterance long enough to
+  // meet the 1000-symbol cap of the single-stream loop (ref OfflineRecognizer.cs:122), more than one symbol per frame.
+  const bool fast = h->cfg.precision != K2B_PREC_FP32 && T > 0 && T <= 1000 && h->max_sym_per_frame == 1 &&
+                    (cluster_path_supported(h, 1) || beam_greedy_usable(h));
+  if (fast && mode == K2B_GREEDY_BATCH_COMPAT && B > 1) return greedy_compat_fast(h, enc, enc_is_raw, B, T, tokens, ts, n_out, cap);
+  if (fast) {
+    bool rel = false;
+    return greedy_fast_pass(h, enc, enc_is_raw, B, T, 0, -1, nullptr, tokens, ts, n_out, cap, false, &rel);
+  }
   const float* frames = nullptr;
   K2B_TRY(frames_for_search(h, enc, enc_is_raw, B, T, &frames));
-  if (as_beam1 && beam_greedy_usable(h)) {           // large vocabulary: beam 1 on the persistent beam kernel
-    K2B_TRY(ensure(h, h->ws_misc, sizeof(float) * (size_t)B));
-    return beam_dev(h, frames, B, T, 1, tokens, ts, n_out, static_cast<float*>(h->ws_misc.p), cap, -1, nullptr, true);
-  }
   return greedy_dev(h, frames, B, T, mode, false, nullptr, tokens, ts, n_out, cap);
 }
 
@@ -714,27 +905,27 @@ int32_t k2b_greedy_offline(k2b_handle* h, const float* enc, int32_t enc_is_raw, 
     K2B_CUDA(h, cudaMemcpyAsync(ts, o.ts, sizeof(int32_t) * (size_t)B * cap, cudaMemcpyDeviceToHost, h->stream));
   }
   K2B_CUDA(h, cudaMemcpyAsync(n_out, o.n, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
-  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (h->cfg.precision != K2B_PREC_FP32) K2B_TRY(cluster_status(h));
-  return K2B_OK;
+  return finish_host_call(h);
 }
 
 int32_t k2b_greedy_online_chunk_dev(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t Tc,
                                     int64_t* hyp_inout, int64_t* tokens, int32_t* ts, int32_t* n_out, int32_t cap) {
   K2B_TRY(enter(h));
   K2B_TRY(need_weights(h));
+  h->lens_active = false;              // lengths belong to offline searches; a pending setting must not freeze online streams
   K2B_TRY(check_search_args(h, enc, B, Tc, cap, tokens, ts, n_out, "k2b_greedy_online_chunk"));
   if (B > 0 && hyp_inout == nullptr) return fail(h, K2B_ERR_INVALID, "k2b_greedy_online_chunk: hyp_inout is NULL");
   if (B == 0) return K2B_OK;
-  const bool as_beam1 = h->cfg.precision != K2B_PREC_FP32 && Tc > 0;                  // online: Q6 is a no-op (ctx == list tail)
-  if (as_beam1 && cluster_path_supported(h, 1) && !prefer_persistent_greedy(h, B))
-    return beam_cluster_path(h, enc, enc_is_raw, B, Tc, 1, tokens, ts, n_out, nullptr, cap, 1, hyp_inout);
+  const bool as_beam1 = h->cfg.precision != K2B_PREC_FP32 && Tc > 0 &&                   // online: Q6 is a no-op (ctx == list tail)
+                        (cluster_path_supported(h, 1) || beam_greedy_usable(h));
+  check_hyp_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(hyp_inout, B, h->cfg.vocab_size, h->cfg.blank_id, as_beam1 ? 0 : 1, h->dev_status);
+  K2B_LAUNCH_CHECK(h);
+  if (as_beam1) {
+    bool rel = false;
+    return greedy_fast_pass(h, enc, enc_is_raw, B, Tc, 0, 1, hyp_inout, tokens, ts, n_out, cap, false, &rel);
+  }
   const float* frames = nullptr;
   K2B_TRY(frames_for_search(h, enc, enc_is_raw, B, Tc, &frames));
-  if (as_beam1 && beam_greedy_usable(h)) {
-    K2B_TRY(ensure(h, h->ws_misc, sizeof(float) * (size_t)B));
-    return beam_dev(h, frames, B, Tc, 1, tokens, ts, n_out, static_cast<float*>(h->ws_misc.p), cap, 1, hyp_inout, true);
-  }
   return greedy_dev(h, frames, B, Tc, K2B_GREEDY_BATCH_COMPAT, true, hyp_inout, tokens, ts, n_out, cap);
 }
 
@@ -745,6 +936,7 @@ int32_t k2b_greedy_online_chunk(k2b_handle* h, const float* enc, int32_t enc_is_
   K2B_TRY(check_search_args(h, enc, B, Tc, cap, tokens, ts, n_out, "k2b_greedy_online_chunk"));
   if (B > 0 && hyp_inout == nullptr) return fail(h, K2B_ERR_INVALID, "k2b_greedy_online_chunk: hyp_inout is NULL");
   if (B == 0) return K2B_OK;
+  K2B_TRY(check_hyp_host(h, hyp_inout, B, h->cfg.precision == K2B_PREC_FP32, "k2b_greedy_online_chunk"));
   const size_t width = enc_is_raw ? h->cfg.encoder_dim : h->cfg.joiner_dim;
   const size_t in_bytes = sizeof(float) * (size_t)B * Tc * width;
   K2B_TRY(ensure(h, h->ws_in, in_bytes > 0 ? in_bytes : 4));
@@ -759,9 +951,7 @@ int32_t k2b_greedy_online_chunk(k2b_handle* h, const float* enc, int32_t enc_is_
   }
   K2B_CUDA(h, cudaMemcpyAsync(n_out, o.n, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
   K2B_CUDA(h, cudaMemcpyAsync(hyp_inout, o.hyp, sizeof(int64_t) * 2 * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
-  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (h->cfg.precision != K2B_PREC_FP32) K2B_TRY(cluster_status(h));
-  return K2B_OK;
+  return finish_host_call(h);
 }
 
 int32_t k2b_modified_beam_search_dev(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t T, int32_t K,
@@ -816,8 +1006,114 @@ int32_t k2b_modified_beam_search(k2b_handle* h, const float* enc, int32_t enc_is
   }
   K2B_CUDA(h, cudaMemcpyAsync(n_out, o.n, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
   K2B_CUDA(h, cudaMemcpyAsync(score, o.score, sizeof(float) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+  return finish_host_call(h);
+}
+
+// ---- streaming modified_beam_search ---------------------------------------------------------------------------------
+int32_t k2b_beam_pool_create(k2b_handle* h, int32_t max_streams, int32_t K, int32_t max_frames) {
+  K2B_TRY(enter(h));
+  if (max_streams <= 0 || max_frames <= 0) return fail(h, K2B_ERR_INVALID, "k2b_beam_pool_create: max_streams and max_frames must be positive");
+  if (K < 1 || K > kMaxBeam || K > h->cfg.vocab_size) return fail(h, K2B_ERR_INVALID, "k2b_beam_pool_create: beam must be in 1..8 and <= vocab_size");
+  return beam_pool_create(h, max_streams, K, max_frames);
+}
+
+int32_t k2b_beam_pool_reset(k2b_handle* h, int32_t slot, const int64_t* hyp) {
+  K2B_TRY(enter(h));
+  return beam_pool_reset(h, slot, hyp);
+}
+
+int32_t k2b_modified_beam_search_online_chunk_dev(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t Tc,
+                                                  const int32_t* slots, int64_t* hyp_out, int64_t* tokens, int32_t* ts,
+                                                  int32_t* n_out, float* score, int32_t cap) {
+  K2B_TRY(enter(h));
+  K2B_TRY(need_weights(h));
+  h->lens_active = false;
+  if (B < 0 || Tc < 0) return fail(h, K2B_ERR_INVALID, "k2b_modified_beam_search_online_chunk: negative B or Tc");
+  if (B == 0) return K2B_OK;
+  if (slots == nullptr || tokens == nullptr || ts == nullptr || n_out == nullptr || score == nullptr || (Tc > 0 && enc == nullptr) || cap < 1)
+    return fail(h, K2B_ERR_INVALID, "k2b_modified_beam_search_online_chunk: NULL argument or cap < 1");
+  K2B_TRY(beam_pool_begin(h, slots, B, Tc));
+  const int K = beam_pool_K(h);
+  const int mask3 = 1;                   // the online loops do not emit the literal id 1 either (ref OnlineRecognizer.cs:181)
+  if (Tc > 0) {
+    const size_t NK = (size_t)B * K, J = h->cfg.joiner_dim;
+    K2B_TRY(ensure(h, h->ws_bp, sizeof(int32_t) * NK * Tc));
+    int32_t* bp = static_cast<int32_t*>(h->ws_bp.p);
+    if (h->cfg.precision != K2B_PREC_FP32 && cluster_path_supported(h, K)) {
+      K2B_TRY(ensure_cluster_assets(h));
+      const size_t n = (size_t)B * Tc;
+      K2B_TRY(ensure(h, h->ws_encproj, sizeof(float) * n * J));
+      float* encE = static_cast<float*>(h->ws_encproj.p);
+      if (enc_is_raw) {
+        if (h->cfg.encoder_dim <= 0 || h->enc_w == nullptr) return fail(h, K2B_ERR_STATE, "encoder_proj weights not loaded (E == 0)");
+        if (encproj_tc_supported(h)) {
+          K2B_TRY(encoder_proj_tc(h, enc, (int)n, encE, true));
+        } else {
+          GemmArgs g;
+          g.M = (int)n; g.N = (int)J; g.K = h->cfg.encoder_dim;
+          g.A = enc; g.W = h->enc_w; g.bias = h->enc_b; g.C = encE;
+          K2B_TRY(launch_gemm_simt(h, PRO_PLAIN, EPI_EXP2X, g));
+        }
+      } else {
+        K2B_TRY(exp2x_frames(h, enc, encE, n * J));
+      }
+      const size_t a4 = (NK * 4 + 255) & ~size_t(255), a8 = (NK * 8 + 255) & ~size_t(255), ab = ((size_t)B * 4 + 255) & ~size_t(255);
+      K2B_TRY(ensure(h, h->ws_state, 2 * a4 + ab + 2 * a8));
+      char* p = static_cast<char*>(h->ws_state.p);
+      BeamStateView v;
+      v.lp = reinterpret_cast<float*>(p); p += a4;
+      v.len = reinterpret_cast<int32_t*>(p); p += a4;
+      v.nlive = reinterpret_cast<int32_t*>(p); p += ab;
+      v.ctx = reinterpret_cast<int32_t*>(p); p += a8;
+      v.hash = reinterpret_cast<unsigned long long*>(p);
+      K2B_TRY(beam_pool_gather(h, B, v));
+      K2B_TRY(beam_cluster_dev(h, encE, B, Tc, K, bp, v.lp, v.len, v.nlive, mask3, nullptr, nullptr, 0, Tc, 1, v.ctx, v.hash, true));
+      K2B_TRY(beam_pool_scatter(h, B, Tc, v, bp));
+    } else {
+      const float* frames = nullptr;
+      K2B_TRY(frames_for_search(h, enc, enc_is_raw, B, Tc, &frames));
+      K2B_TRY(ensure(h, h->ws_state, 2 * beam_state_bytes(B, K)));
+      K2B_TRY(beam_pool_gather(h, B, beam_state_view(h, B, K, 0)));
+      K2B_TRY(beam_dev(h, frames, B, Tc, K, tokens, ts, n_out, score, cap, mask3, nullptr, false, 0, 0, true));
+      K2B_TRY(beam_pool_scatter(h, B, Tc, beam_state_view(h, B, K, Tc & 1), bp));
+    }
+  }
+  return beam_pool_backtrace(h, B, tokens, ts, n_out, score, hyp_out, cap);
+}
+
+int32_t k2b_modified_beam_search_online_chunk(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t Tc,
+                                              const int32_t* slots, int64_t* hyp_out, int64_t* tokens, int32_t* ts,
+                                              int32_t* n_out, float* score, int32_t cap) {
+  K2B_TRY(enter(h));
+  K2B_TRY(need_weights(h));
+  if (B < 0 || Tc < 0) return fail(h, K2B_ERR_INVALID, "k2b_modified_beam_search_online_chunk: negative B or Tc");
+  if (B == 0) return K2B_OK;
+  if (slots == nullptr || tokens == nullptr || ts == nullptr || n_out == nullptr || score == nullptr || (Tc > 0 && enc == nullptr) || cap < 1)
+    return fail(h, K2B_ERR_INVALID, "k2b_modified_beam_search_online_chunk: NULL argument or cap < 1");
+  const size_t width = enc_is_raw ? h->cfg.encoder_dim : h->cfg.joiner_dim;
+  const size_t in_bytes = sizeof(float) * (size_t)B * Tc * width;
+  K2B_TRY(ensure(h, h->ws_in, in_bytes > 0 ? in_bytes : 4));
+  OutStage o;
+  K2B_TRY(stage_out(h, B, cap, &o));
+  if (in_bytes) K2B_CUDA(h, cudaMemcpyAsync(h->ws_in.p, enc, in_bytes, cudaMemcpyHostToDevice, h->stream));
+  K2B_TRY(k2b_modified_beam_search_online_chunk_dev(h, static_cast<const float*>(h->ws_in.p), enc_is_raw, B, Tc, slots,
+                                                    hyp_out ? o.hyp : nullptr, o.tokens, o.ts, o.n, o.score, cap));
+  K2B_CUDA(h, cudaMemcpyAsync(tokens, o.tokens, sizeof(int64_t) * (size_t)B * cap, cudaMemcpyDeviceToHost, h->stream));
+  K2B_CUDA(h, cudaMemcpyAsync(ts, o.ts, sizeof(int32_t) * (size_t)B * cap, cudaMemcpyDeviceToHost, h->stream));
+  K2B_CUDA(h, cudaMemcpyAsync(n_out, o.n, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+  K2B_CUDA(h, cudaMemcpyAsync(score, o.score, sizeof(float) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+  if (hyp_out) K2B_CUDA(h, cudaMemcpyAsync(hyp_out, o.hyp, sizeof(int64_t) * 2 * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+  return finish_host_call(h);
+}
+
+// diagnostic / parity evidence: the back-pointer rows of the LAST beam search of this handle ([B,T,K] int32, entry =
+// (parent slot << 28) | (appended token + 1), 0 for a dead slot), i.e. the whole history of the beam
+int32_t k2b_debug_backpointers(k2b_handle* h, int32_t* out, int32_t B, int32_t T, int32_t K) {
+  K2B_TRY(enter(h));
+  const size_t bytes = sizeof(int32_t) * (size_t)B * T * K;
+  if (out == nullptr || B < 0 || T < 0 || K < 1 || bytes > h->ws_bp.bytes) return fail(h, K2B_ERR_INVALID, "k2b_debug_backpointers: no such history");
   K2B_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (h->cfg.precision != K2B_PREC_FP32) K2B_TRY(cluster_status(h));
+  K2B_CUDA(h, cudaMemcpy(out, h->ws_bp.p, bytes, cudaMemcpyDeviceToHost));
   return K2B_OK;
 }
 
@@ -855,8 +1151,30 @@ int32_t k2b_ctc_greedy(k2b_handle* h, const float* logp, int32_t B, int32_t T, i
   K2B_CUDA(h, cudaMemcpyAsync(n_out, o.n, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
   if (trailing_blank_inout) K2B_CUDA(h, cudaMemcpyAsync(trailing_blank_inout, o.aux_b, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
   if (prev_inout) K2B_CUDA(h, cudaMemcpyAsync(prev_inout, o.prev, sizeof(int64_t) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+  if (h->opt_async_d2h) return K2B_OK;
   K2B_CUDA(h, cudaStreamSynchronize(h->stream));
   return K2B_OK;
+}
+
+// ---- page-locked host memory ------------------------------------------------------------------------------------
+// A P/Invoke float[] is pageable: its copies are staged through the driver's bounce buffer and serialise with the host. Callers
+// that want the PCIe rate (and the async_d2h overlap) take their frame / result buffers from here, or register their own.
+int32_t k2b_host_alloc(void** out, int64_t bytes) {
+  if (out == nullptr || bytes <= 0) return K2B_ERR_INVALID;
+  *out = nullptr;
+  return cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable) == cudaSuccess ? K2B_OK : (cudaGetLastError(), K2B_ERR_CUDA);
+}
+int32_t k2b_host_free(void* p) {
+  if (p == nullptr) return K2B_OK;
+  return cudaFreeHost(p) == cudaSuccess ? K2B_OK : (cudaGetLastError(), K2B_ERR_CUDA);
+}
+int32_t k2b_host_register(void* p, int64_t bytes) {
+  if (p == nullptr || bytes <= 0) return K2B_ERR_INVALID;
+  return cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable) == cudaSuccess ? K2B_OK : (cudaGetLastError(), K2B_ERR_CUDA);
+}
+int32_t k2b_host_unregister(void* p) {
+  if (p == nullptr) return K2B_OK;
+  return cudaHostUnregister(p) == cudaSuccess ? K2B_OK : (cudaGetLastError(), K2B_ERR_CUDA);
 }
 
 }  // extern "C"

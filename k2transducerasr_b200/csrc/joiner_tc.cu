@@ -564,7 +564,7 @@ size_t beam_mega_sync_ints(const k2b_handle* h, int B, int T, int K) {
 
 // ---- the whole modified_beam_search time loop in one launch (memoised decoder, K in {2, 4, 8}) --------------------------------
 bool beam_mega_usable(const k2b_handle* h, int K) {
-  const bool off = getenv("K2B_NO_MEGA") != nullptr;       // read per call: tests compare the two engines in one process
+  const bool off = h->opt_no_mega != 0;                    // k2b_set_option("no_mega"): tests compare the two engines in one process
   return !off && (K == 1 || K == 2 || K == 4 || K == 8) && joiner_topk_usable(h, K) && h->dec_tab != nullptr;
 }
 

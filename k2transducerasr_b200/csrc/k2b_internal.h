@@ -33,7 +33,7 @@ struct ProfEvents {
 
 }  // namespace k2b
 
-namespace k2b { struct StatePool; }
+namespace k2b { struct StatePool; struct BeamPool; struct NcclState; }
 
 struct k2b_handle {
   k2b_config cfg{};
@@ -81,6 +81,8 @@ struct k2b_handle {
   float* bias_pad = nullptr;      // [CS*128] out_b, -inf beyond V
   float* dec_tab = nullptr;       // [(V+1)*V, J] exp(2*decoder(y0,y1)): the memoised stateless decoder
   int dec_tab_state = 0;          // 0 not tried, 1 built, -1 does not fit (decoder GEMM per frame instead)
+  size_t dec_tab_bytes = 0;       // what the memoised decoder occupies, and the device time its build took (k2b_get_stat)
+  float dec_tab_build_ms = 0.f;
 
   int cluster16_ok = -1;          // 16-CTA cluster launchable on this device? (-1 unknown; occupancy query, cached)
   bool enc_ready = false;         // encproj_tc.cu: pre-split, pre-swizzled encoder_proj weight images
@@ -106,6 +108,16 @@ struct k2b_handle {
   int lens_n = 0;
   bool lens_active = false;
   k2b::ProfEvents prof;
+  k2b::BeamPool* beam_pool = nullptr;     // streaming modified_beam_search: per-stream hypotheses carried between chunks (stream_beam.cu)
+  k2b::NcclState* nccl = nullptr;         // k2b_nccl_init / k2b_gather_results_nccl (nccl_gather.cu; libnccl is dlopen'ed)
+  int max_sym_per_frame = 1;              // k2b_set_option("max_sym_per_frame"): ref OfflineRecognizer.cs:19 fixes it to 1
+  // engine switches (k2b_set_option; the K2B_* environment variables only give their initial values at k2b_create)
+  int opt_pipe_chunks = 0;                // > 0: number of time chunks of the host-pointer beam search
+  int opt_no_mega = 0;                    // large-vocabulary beam search as per-frame launches instead of the persistent launch
+  int opt_unfused_step = 0;               // the three-launch frame step
+  int opt_greedy_persistent = -1;         // -1 auto, 0 cluster kernel, 1 persistent kernel (greedy, 1024 < V <= 2048)
+  int opt_pair = 0;                       // CTA-pair variant of the cluster kernel
+  int opt_async_d2h = 0;                  // host-pointer fused calls return without the final sync (pinned buffers; k2b_sync completes)
 };
 
 namespace k2b {
@@ -199,9 +211,15 @@ int32_t greedy_dev(k2b_handle* h, const float* enc, int B, int T, int mode, bool
                    int64_t* hyp_inout, int64_t* tokens, int32_t* ts, int32_t* n_out, int cap);
 // extra_mask / hyp_inout: greedy search as beam 1 (the literal-1 mask and OnlineStream.Hyp of the online loop); only the engines
 // built on beam_merge_stream implement them - beam_dev fails with K2B_ERR_UNSUPPORTED otherwise (beam_greedy_usable tells)
+// carry: the hypothesis state is already in the first state buffer (beam_state_ptrs(.., 0)); T frames are decoded from it, the final
+// state is left in buffer T & 1 and NO back-trace runs (streaming beam search: the caller owns history and state).
+// enc_stride: floats between the frames of consecutive streams when it is not Ttot * J.
 int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* tokens, int32_t* ts,
                  int32_t* n_out, float* score, int cap, int extra_mask = -1, int64_t* hyp_inout = nullptr, bool greedy = false,
-                 int t0 = 0, int Ttot = 0);
+                 int t0 = 0, int Ttot = 0, bool carry = false, long long enc_stride = 0);
+struct BeamStateView { int32_t* ctx; float* lp; int32_t* len; unsigned long long* hash; int32_t* nlive; };
+size_t beam_state_bytes(int B, int K);                                   // one of the two state buffers of beam_dev
+BeamStateView beam_state_view(k2b_handle* h, int B, int K, int which);   // inside ws_state (ensure 2 * beam_state_bytes first)
 // a search may be stepped in time chunks (enc = frame t0 of a [B,Ttot,J] array, T frames per call: the host-pointer entry point hides
 // the input copy behind the search that way) on the engines built on beam_merge_stream
 bool beam_chunkable(k2b_handle* h, int K);
@@ -221,6 +239,20 @@ int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, 
                          int32_t* fin_nlive, int extra_mask, const int64_t* hyp_in, int64_t* hyp_out, int t0 = 0, int Ttot = 0,
                          int resume = 0, int32_t* io_ctx = nullptr, unsigned long long* io_hash = nullptr, bool need_lp = true);
 int32_t cluster_status(k2b_handle* h);
+
+// ---- stream_beam.cu: hypotheses carried between the chunks of a stream -----------------------------------------
+int32_t beam_pool_create(k2b_handle* h, int max_streams, int K, int max_frames);
+void beam_pool_free(k2b_handle* h);
+int32_t beam_pool_reset(k2b_handle* h, int slot, const int64_t* hyp_host);
+// slots_host [B]; layout A (cluster kernel): separate arrays; layout B (beam_dev): a BeamStateView
+int32_t beam_pool_begin(k2b_handle* h, const int32_t* slots_host, int B, int Tc);
+int32_t beam_pool_gather(k2b_handle* h, int B, const BeamStateView& dst);
+int32_t beam_pool_scatter(k2b_handle* h, int B, int Tc, const BeamStateView& src, const int32_t* bp_chunk);
+int32_t beam_pool_backtrace(k2b_handle* h, int B, int64_t* tokens, int32_t* ts, int32_t* n_out, float* score, int64_t* hyp_out, int cap);
+int beam_pool_K(const k2b_handle* h);
+
+// ---- nccl_gather.cu ------------------------------------------------------------------------------------------
+void nccl_free(k2b_handle* h);
 
 // ---- encproj_tc.cu -----------------------------------------------------------------------------
 bool encproj_tc_supported(const k2b_handle* h);

@@ -41,10 +41,16 @@ __global__ void greedy_select_kernel(int B, int nt, const float* __restrict__ pv
                                      const int32_t* __restrict__ pnan, int32_t* __restrict__ ctx,
                                      int64_t* __restrict__ tokens, int32_t* __restrict__ ts, int32_t* __restrict__ n_out,
                                      int cap, int t, int blank, int unk, int extra_mask, int max_sym,
-                                     int32_t* __restrict__ flag, const int32_t* __restrict__ lens) {
+                                     int32_t* __restrict__ flag, const int32_t* __restrict__ lens, int sub, int32_t* __restrict__ spf) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   if (lens != nullptr && t >= lens[b]) return;      // ragged batch: this stream has ended
+  // max_sym_per_frame > 1 (ref OfflineRecognizer.cs:127-179): evaluation `sub` of frame t only concerns the streams that emitted
+  // on each of the `sub` evaluations before it
+  if (spf != nullptr) {
+    if (sub == 0) spf[b] = 0;
+    else if (spf[b] != sub) return;
+  }
   float bv = 0.f;
   int bi = -1, bn = 0;
   for (int i = 0; i < nt; ++i) {
@@ -68,6 +74,7 @@ __global__ void greedy_select_kernel(int B, int nt, const float* __restrict__ pv
     ctx[2 * b] = ctx[2 * b + 1];
     ctx[2 * b + 1] = y;
     *flag = 1;                       // Q6: somebody in the batch emitted
+    if (spf != nullptr) spf[b] = sub + 1;
   }
 }
 
@@ -104,7 +111,7 @@ __device__ __forceinline__ bool better(float v, int i, float ev, int ei) {
 // Branch-free throughout (predicated selects, REDUX max for the arg-best rounds): the lanes of a warp never diverge.
 
 __global__ void __launch_bounds__(128)
-beam_select_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk,
+beam_select_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk, int mask3,
                    const float* __restrict__ part_m, const float* __restrict__ part_s,
                    const float* __restrict__ part_tv, const int32_t* __restrict__ part_ti,
                    BeamState in, BeamState out, int32_t* __restrict__ bp, const int32_t* __restrict__ lens) {
@@ -253,7 +260,7 @@ beam_select_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk
     ln = in.len[prow];
     c0 = in.ctx[2 * prow];
     c1 = in.ctx[2 * prow + 1];
-    if (y != blank && y != unk) {      // ys unchanged for blank / unk
+    if (y != blank && y != unk && y != mask3) {      // ys unchanged for blank / unk (/ the literal 1 of the online loop)
       tok = y;
       hs = hash_push(hs, y);
       ln += 1;
@@ -400,6 +407,13 @@ size_t state_bytes(int B, int K) {
 
 }  // namespace
 
+size_t beam_state_bytes(int B, int K) { return state_bytes(B, K); }
+BeamStateView beam_state_view(k2b_handle* h, int B, int K, int which) {
+  char* p = static_cast<char*>(h->ws_state.p) + (size_t)which * state_bytes(B, K);
+  const BeamState s = carve_state(p, B, K);
+  return BeamStateView{s.ctx, s.lp, s.len, reinterpret_cast<unsigned long long*>(s.hash), s.nlive};
+}
+
 void prof_begin(k2b_handle* h) {
   if (!h->profile_on) return;
   ProfEvents& p = h->prof;
@@ -427,9 +441,13 @@ int32_t greedy_dev(k2b_handle* h, const float* enc, int B, int T, int mode, bool
   const int nt = tc ? joiner_tc_tiles(h) : num_vocab_tiles(V);
   K2B_TRY(ensure(h, h->ws_x, sizeof(float) * (size_t)B * J));
   K2B_TRY(ensure(h, h->ws_part, (size_t)B * nt * 12));
-  K2B_TRY(ensure(h, h->ws_state, align256((size_t)B * 8) + 256));
+  K2B_TRY(ensure(h, h->ws_state, align256((size_t)B * 8) + 256 + align256((size_t)B * 4)));
   int32_t* ctx = static_cast<int32_t*>(h->ws_state.p);
   int32_t* flag = reinterpret_cast<int32_t*>(static_cast<char*>(h->ws_state.p) + align256((size_t)B * 8));
+  // symbols per frame: only the single-stream loop of the reference has the notion (ref OfflineRecognizer.cs:19, :127-134); the
+  // batch and online loops evaluate every frame once by construction
+  const int nsub = (!online && mode != K2B_GREEDY_BATCH_COMPAT) ? h->max_sym_per_frame : 1;
+  int32_t* spf = nsub > 1 ? reinterpret_cast<int32_t*>(static_cast<char*>(h->ws_state.p) + align256((size_t)B * 8) + 256) : nullptr;
   float* pval = static_cast<float*>(h->ws_part.p);
   int32_t* pidx = reinterpret_cast<int32_t*>(pval + (size_t)B * nt);
   int32_t* pnan = pidx + (size_t)B * nt;
@@ -441,7 +459,8 @@ int32_t greedy_dev(k2b_handle* h, const float* enc, int B, int T, int mode, bool
 
   const int max_sym = (mode == K2B_GREEDY_SINGLE && !online) ? 1000 : 0x7fffffff;
   const int extra_mask = online ? 1 : -1;   // the literal `y != 1` of ref OnlineRecognizer.cs:181
-  for (int t = 0; t < T; ++t) {
+  for (int t = 0; t < T; ++t)
+  for (int sub = 0; sub < nsub; ++sub) {
     GemmArgs d;
     d.M = B; d.N = J; d.K = D;
     d.W = h->dec_w; d.bias = h->dec_b;
@@ -463,7 +482,7 @@ int32_t greedy_dev(k2b_handle* h, const float* enc, int B, int T, int mode, bool
 
     greedy_select_kernel<<<gb, tb, 0, h->stream>>>(B, nt, pval, pidx, pnan, ctx, tokens, ts, n_out, cap, t, c.blank_id,
                                                    c.unk_id, extra_mask, max_sym, flag,
-                                                   (!online && h->lens_active) ? h->lens_dev : nullptr);
+                                                   (!online && h->lens_active) ? h->lens_dev : nullptr, sub, spf);
     K2B_LAUNCH_CHECK(h);
   }
   if (online) {
@@ -534,7 +553,7 @@ bool beam_chunkable(k2b_handle* h, int K) {
   if (h->cfg.precision == K2B_PREC_FP32 || !joiner_tc_supported(h) || h->tab0 == nullptr || !joiner_topk_usable(h, K)) return false;
   bool have = false;
   if (ensure_dec_table(h, &have) != K2B_OK) return false;
-  return have && getenv("K2B_UNFUSED_STEP") == nullptr;
+  return have && h->opt_unfused_step == 0;
 }
 
 // greedy search as beam 1 on the persistent kernel: needs the tcgen05 precisions and the memoised decoder table
@@ -546,11 +565,13 @@ bool beam_greedy_usable(k2b_handle* h) {
 }
 
 int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* tokens, int32_t* ts, int32_t* n_out,
-                 float* score, int cap, int extra_mask, int64_t* hyp_inout, bool greedy, int t0, int Ttot) {
+                 float* score, int cap, int extra_mask, int64_t* hyp_inout, bool greedy, int t0, int Ttot, bool carry,
+                 long long enc_stride_in) {
   const k2b_config& c = h->cfg;
   if (Ttot <= 0) { Ttot = T; t0 = 0; }
-  const long long enc_stride = (long long)Ttot * c.joiner_dim;       // enc points at frame t0 of a [B,Ttot,J] array
-  const bool resume = t0 > 0, last = t0 + T >= Ttot;
+  if (carry && t0 != 0) return fail(h, K2B_ERR_INVALID, "beam_dev: a carried state starts at the first frame of its chunk");
+  const long long enc_stride = enc_stride_in > 0 ? enc_stride_in : (long long)Ttot * c.joiner_dim;   // enc points at frame t0 of a [B,Ttot,J] array
+  const bool resume = t0 > 0 || carry, last = !carry && t0 + T >= Ttot;
   const int J = c.joiner_dim, V = c.vocab_size, D = c.decoder_dim;
   const bool tc = c.precision != K2B_PREC_FP32 && joiner_tc_supported(h);   // per-frame tcgen05 joiner (256-column tiles)
   const int N = B * K;
@@ -584,11 +605,11 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
   int32_t* bp = static_cast<int32_t*>(h->ws_bp.p);
   float* x = static_cast<float*>(h->ws_x.p);
 
-  const bool greedy_ext = extra_mask >= 0 || hyp_inout != nullptr;
-  if (greedy_ext && K != 1) return fail(h, K2B_ERR_INVALID, "beam_dev: mask / Hyp are beam-1 (greedy) options");
-  static const bool unfused = getenv("K2B_UNFUSED_STEP") != nullptr;
+  const bool greedy_ext = hyp_inout != nullptr;
+  if (greedy_ext && K != 1) return fail(h, K2B_ERR_INVALID, "beam_dev: Hyp in / out is a beam-1 (greedy) option");
+  const bool unfused = h->opt_unfused_step != 0;
   const bool fused = tc && have_tab && ximg != nullptr && !unfused && joiner_topk_usable(h, K) && T > 0;
-  if (resume && !fused) return fail(h, K2B_ERR_UNSUPPORTED, "beam_dev: time chunks need the memoised decoder table");
+  if (t0 > 0 && !fused) return fail(h, K2B_ERR_UNSUPPORTED, "beam_dev: time chunks need the memoised decoder table");
   if (fused) {
     K2B_TRY(ensure_joiner_assets(h));
     const size_t nsync = beam_mega_sync_ints(h, B, T, K);
@@ -601,7 +622,7 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
       K2B_CUDA(h, cudaMemsetAsync(h->ws_sync.p, 0, nsync * sizeof(int), h->stream));
       K2B_TRY(joinin_table_tc(h, st[t0 & 1].ctx, N, enc, enc_stride, K, ximg));
     }
-  } else {
+  } else if (!carry) {
     beam_init_kernel<<<(N + 127) / 128, 128, 0, h->stream>>>(B, K, c.blank_id, st[0], st[1]);
     K2B_LAUNCH_CHECK(h);
     if (hyp_inout != nullptr) {
@@ -655,6 +676,7 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
     return last ? finish(cur) : K2B_OK;
   }
   if (greedy_ext) return fail(h, K2B_ERR_UNSUPPORTED, "beam_dev: greedy options need the memoised decoder table");
+  if (enc_stride_in > 0 && enc_stride_in != (long long)T * J) return fail(h, K2B_ERR_UNSUPPORTED, "beam_dev: strided frames need the fused path");
   for (int t = 0; t < T; ++t) {
     GemmArgs d;
     d.M = N; d.N = J; d.K = D;
@@ -683,14 +705,14 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
 
     if (h->prof_which == 2) prof_begin(h);
     K2B_CUDA(h, launch_pdl(beam_select_kernel, dim3((B + 3) / 4), dim3(128), 0, h->stream, B, K, V, nt, T, t, (int)c.blank_id,
-                            (int)c.unk_id, (const float*)part_m, (const float*)part_s, (const float*)part_tv,
+                            (int)c.unk_id, extra_mask, (const float*)part_m, (const float*)part_s, (const float*)part_tv,
                             (const int32_t*)part_ti, st[cur], st[cur ^ 1], bp,
                             (const int32_t*)(h->lens_active ? h->lens_dev : nullptr)));
     K2B_LAUNCH_CHECK(h);
     if (h->prof_which == 2) prof_end(h);
     cur ^= 1;
   }
-
+  if (carry) return K2B_OK;
   return beam_backtrace_dev(h, B, K, T, st[cur].lp, st[cur].len, st[cur].nlive, bp, tokens, ts, n_out, score, cap);
 }
 

@@ -779,10 +779,7 @@ static void (*cluster_kernel_for(int K, bool x3, bool timed, bool pair))(const C
   if (pair) return x3 ? cluster_kernel_kx<true, true>(K) : cluster_kernel_kx<false, true>(K);
   return x3 ? cluster_kernel_kx<true, false>(K) : cluster_kernel_kx<false, false>(K);
 }
-static bool cluster_pair_mode(int CS) {
-  const char* e = getenv("K2B_PAIR");
-  return CS % 2 == 0 && e != nullptr && e[0] == '1';
-}
+static bool cluster_pair_mode(const k2b_handle* h, int CS) { return CS % 2 == 0 && h->opt_pair != 0; }
 
 static size_t cluster_dyn_smem(int J, int CS, int K) {
   const int nkb = J / 64;
@@ -805,7 +802,7 @@ bool cluster_path_supported(const k2b_handle* h, int K) {
     k2b_handle* hm = const_cast<k2b_handle*>(h);
     if (hm->cluster16_ok < 0) {
       hm->cluster16_ok = 0;
-      auto kern = cluster_kernel_for(1, c.precision == K2B_PREC_BF16X3, false, cluster_pair_mode(CS));
+      auto kern = cluster_kernel_for(1, c.precision == K2B_PREC_BF16X3, false, cluster_pair_mode(h, CS));
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
           cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) == cudaSuccess) {
         cudaLaunchConfig_t cfg = {};
@@ -821,7 +818,14 @@ bool cluster_path_supported(const k2b_handle* h, int K) {
     }
     if (hm->cluster16_ok != 1) return false;
   }
-  return true;
+  // the kernel reads the memoised decoder table: when that does not fit beside what else lives on the device (another handle, the
+  // encoder's own session) the callers take the per-frame path, which needs none
+  k2b_handle* hm = const_cast<k2b_handle*>(h);
+  if (hm->weights_loaded && hm->dec_tab_state == 0) {
+    bool have = false;
+    if (ensure_dec_table(hm, &have) != K2B_OK) return false;
+  }
+  return hm->dec_tab_state > 0;
 }
 
 // The memoised stateless decoder: dec_tab[(y0+1)*V + y1] = exp(2*clamp(decoder(y0, y1))) for every context, J floats per row
@@ -846,20 +850,40 @@ int32_t ensure_dec_table(k2b_handle* h, bool* have) {
   }
   const int chunk = 1 << 18;
   int32_t* ctx = nullptr;
-  K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&ctx), sizeof(int32_t) * 2 * chunk));
-  for (long long first = 0; first < nctx; first += chunk) {
-    const int n = (int)((nctx - first) < chunk ? (nctx - first) : chunk);
-    enum_ctx_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(V, first, n, ctx);
-    K2B_LAUNCH_CHECK(h);
-    GemmArgs g;
-    g.M = n; g.N = J; g.K = D;
-    g.W = h->dec_w; g.bias = h->dec_b;
-    g.ctx = ctx; g.tab0 = h->tab0; g.tab1 = h->tab1; g.V = V; g.neg_wrap = c.neg_id_mode == K2B_NEGID_WRAP; g.blank = c.blank_id;
-    g.C = h->dec_tab + (size_t)first * J;
-    K2B_TRY(launch_gemm_simt(h, PRO_DEC, EPI_EXP2X, g));
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  auto build = [&]() -> int32_t {
+    K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&ctx), sizeof(int32_t) * 2 * chunk));
+    K2B_CUDA(h, cudaEventCreate(&ev0));
+    K2B_CUDA(h, cudaEventCreate(&ev1));
+    K2B_CUDA(h, cudaEventRecord(ev0, h->stream));
+    for (long long first = 0; first < nctx; first += chunk) {
+      const int n = (int)((nctx - first) < chunk ? (nctx - first) : chunk);
+      enum_ctx_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(V, first, n, ctx);
+      K2B_LAUNCH_CHECK(h);
+      GemmArgs g;
+      g.M = n; g.N = J; g.K = D;
+      g.W = h->dec_w; g.bias = h->dec_b;
+      g.ctx = ctx; g.tab0 = h->tab0; g.tab1 = h->tab1; g.V = V; g.neg_wrap = c.neg_id_mode == K2B_NEGID_WRAP; g.blank = c.blank_id;
+      g.C = h->dec_tab + (size_t)first * J;
+      K2B_TRY(launch_gemm_simt(h, PRO_DEC, EPI_EXP2X, g));
+    }
+    K2B_CUDA(h, cudaEventRecord(ev1, h->stream));
+    K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) h->dec_tab_build_ms = ms;
+    return K2B_OK;
+  };
+  const int32_t st = build();
+  if (ctx) cudaFree(ctx);
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+  if (st != K2B_OK) {                 // nothing half-built survives an error
+    cudaFree(h->dec_tab);
+    h->dec_tab = nullptr;
+    h->dec_tab_state = -1;
+    return st;
   }
-  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
-  cudaFree(ctx);
+  h->dec_tab_bytes = bytes;
   h->dec_tab_state = 1;
   *have = true;
   return K2B_OK;
@@ -872,14 +896,15 @@ int32_t ensure_cluster_assets(k2b_handle* h) {
   const k2b_config& c = h->cfg;
   const int V = c.vocab_size, J = c.joiner_dim, D = c.decoder_dim, CS = (V + 127) / 128;
   const size_t rows = (size_t)CS * 128;
-  K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->wo_hi_img), rows * J * 2));
-  K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->wo_lo), rows * J * 2));
-  K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->bias_pad), rows * sizeof(float)));
+  bool have = false;
+  K2B_TRY(ensure_dec_table(h, &have));      // first: without the table there is no cluster search and nothing else is allocated
+  if (!have) return fail(h, K2B_ERR_STATE, "cluster search: the memoised decoder table could not be allocated");
+  // (a retry after a failed allocation below re-uses what the earlier attempt obtained)
+  if (h->wo_hi_img == nullptr) K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->wo_hi_img), rows * J * 2));
+  if (h->wo_lo == nullptr) K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->wo_lo), rows * J * 2));
+  if (h->bias_pad == nullptr) K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->bias_pad), rows * sizeof(float)));
   pack_out_w_kernel<<<(unsigned)rows, 128, 0, h->stream>>>(h->out_w, h->out_b, V, J, CS, h->wo_hi_img, h->wo_lo, h->bias_pad);
   K2B_LAUNCH_CHECK(h);
-  bool have = false;
-  K2B_TRY(ensure_dec_table(h, &have));
-  if (!have) return fail(h, K2B_ERR_STATE, "cluster search: the memoised decoder table could not be allocated");
   h->tc_ready = true;
   return K2B_OK;
 }
@@ -909,7 +934,7 @@ int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, 
   a.lens = h->lens_active ? h->lens_dev : nullptr;
   a.bp = bp; a.fin_lp = fin_lp; a.fin_len = fin_len; a.fin_nlive = fin_nlive; a.status = status;
   const size_t dyn = cluster_dyn_smem(J, CS, K);
-  void (*kern)(const ClusterArgs) = cluster_kernel_for(K, a.x3 != 0, a.timing != nullptr, cluster_pair_mode(CS));
+  void (*kern)(const ClusterArgs) = cluster_kernel_for(K, a.x3 != 0, a.timing != nullptr, cluster_pair_mode(h, CS));
   if (CS > 8) K2B_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   K2B_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   cudaLaunchConfig_t cfg = {};
@@ -928,12 +953,16 @@ int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, 
   return K2B_OK;
 }
 
+// dev_status: [0] cluster / persistent search kernels: an mbarrier or counter wait timed out, [1] the same in the tcgen05 GEMMs,
+// [2] a caller-supplied Hyp held a token id outside the vocabulary (device-pointer calls), [3] scratch (first-emission frame)
 int32_t cluster_status(k2b_handle* h) {
   int st[4] = {0, 0, 0, 0};
   K2B_CUDA(h, cudaMemcpyAsync(st, h->dev_status, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
   K2B_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (st[0] != 0 || st[1] != 0) {
-    cudaMemsetAsync(h->dev_status, 0, sizeof(st), h->stream);
+  if (st[0] != 0 || st[1] != 0 || st[2] != 0) {
+    cudaMemsetAsync(h->dev_status, 0, 3 * sizeof(int), h->stream);
+    if (st[2] != 0 && st[0] == 0 && st[1] == 0)
+      return fail(h, K2B_ERR_INVALID, "a Hyp passed by device pointer held a token id outside the vocabulary (it was decoded as blank)");
     return fail(h, K2B_ERR_STATE, st[0] ? "cluster search kernel: an mbarrier wait timed out" : "encoder_proj tcgen05 kernel: an mbarrier wait timed out");
   }
   return K2B_OK;

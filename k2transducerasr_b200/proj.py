@@ -174,13 +174,51 @@ class OfflineProjOfB200ctc(_ProjBase):
         return None
 
 
+@dataclass
+class DeviceStates:
+    """One stream's encoder caches, resident in a slot of the library's device pool (k2b_state_pool_*): what takes the place of
+    the List<List<float[]>> of ref OnlineStream.cs:14 when the caches never leave the GPU."""
+    slot: int
+
+
+@dataclass
+class StackedStates:
+    """The batched caches of one encoder call (ref stack_states' return value), as ONE device buffer laid out as k2b_stack_states
+    documents (tensor i of all B streams at float offset B * off_i), plus the slots they came from."""
+    buffer: object            # torch tensor on the handle's device
+    slots: List[int]
+
+
+def zipformer2_state_layout(num_encoder_layers, encoder_dims, num_heads, query_head_dims, value_head_dims, left_context_len,
+                            cnn_module_kernels):
+    """Per-stream cache tensors of a streaming zipformer2 from its ONNX metadata (keys of ref Model/OnlineCustomMetadata.cs), in the
+    order of ref OnlineProjOfZipformer2.cs:63-111 (per layer: key, nonlin_attn, val1, val2, conv1, conv2; then embed_states and
+    processed_lens), with the "axisnum" of stack_states for each (ref :236-341). Returns (item_len, axis_len)."""
+    il, ax = [], []
+    for i, nl in enumerate(num_encoder_layers):
+        d = encoder_dims[i]
+        key, val = query_head_dims[i] * num_heads[i], value_head_dims[i] * num_heads[i]
+        left, pad = left_context_len[i], cnn_module_kernels[i] // 2
+        for _ in range(nl):
+            il += [left * key, left * (3 * d // 4), left * val, left * val, d * pad, d * pad]
+            ax += [key, left, val, val, d * pad, d * pad]
+    il += [128 * 3 * 19, 1]           # embed_states (ref :58-61), processed_lens
+    ax += [128 * 3 * 19, 1]
+    return il, ax
+
+
 class OnlineProjOfB200(_ProjBase):
     """IOnlineProj (ref IOnlineProj.cs:8-72) over libk2b200.so: stands in for OnlineProjOfZipformer /
     Zipformer2 / Lstm / Conformer, whose DecoderProj/JoinerProj bodies are identical.
-    Encoder caches are opaque here: stack_states / unstack_states regroup them per stream without
-    interpreting them (the encoder network is out of scope)."""
 
-    def __init__(self, dims: ModelDims, weights: dict, model_type: str = "zipformer2", chunk_frames: int = 8, **kw):
+    Encoder caches: with `state_layout` = (item_len, axis_len) the caches live in the library's device pool and
+    GetEncoderInitStates / stack_states / unstack_states are k2b_state_pool_put / k2b_stack_states / k2b_unstack_states (one launch
+    each, nothing crosses PCIe) - the O(B * cache) Array.Copy loops of ref OnlineProjOfZipformer2.cs:144-489 on the device. Without a
+    layout the caches are opaque host objects passed through (the encoder network itself is out of scope either way; `encoder_hook`
+    is where it would run: it receives the stacked device buffer and updates it in place)."""
+
+    def __init__(self, dims: ModelDims, weights: dict, model_type: str = "zipformer2", chunk_frames: int = 8,
+                 state_layout=None, max_streams: int = 512, encoder_hook=None, **kw):
         super().__init__(dims, weights, model_type, **kw)
         self.CustomMetadata = OnlineCustomMetadata(Model_type=model_type, Context_size=dims.context_size,
                                                    Vocab_size=dims.vocab_size, Joiner_dim=dims.joiner_dim,
@@ -189,15 +227,50 @@ class OnlineProjOfB200(_ProjBase):
         self.ShiftLength = chunk_frames        # ref OnlineModel.cs:49
         self.FeatureDim = self.FrameWidth
         self.SampleRate = 16000
+        self._layout = None
+        self._encoder_hook = encoder_hook
+        self._device = kw.get("device", 0)
+        if state_layout is not None:
+            item_len, axis_len = state_layout
+            self._layout = (np.asarray(item_len, np.int32), np.asarray(axis_len, np.int32))
+            self._native.state_pool_create(item_len, max_streams)
+            self._free_state_slots = list(range(max_streams - 1, -1, -1))
+            self._zeros = np.zeros(int(self._layout[0].sum()), np.float32)
 
     def GetEncoderInitStates(self, batchSize: int = 1):
-        return [[] for _ in range(batchSize)]
+        """ref OnlineProjOfZipformer2.cs:63-111: all-zero caches of one stream - here written into a fresh pool slot."""
+        if self._layout is None:
+            return [[] for _ in range(batchSize)]
+        if not self._free_state_slots:
+            raise Exception("OnlineProjOfB200: more concurrent streams than max_streams")
+        slot = self._free_state_slots.pop()
+        self._native.state_pool_put(slot, self._zeros)
+        return DeviceStates(slot)
+
+    def ReleaseStates(self, states):
+        if self._layout is not None and isinstance(states, DeviceStates):
+            self._free_state_slots.append(states.slot)
 
     def stack_states(self, stateList):
-        return stateList
+        """ref OnlineProjOfZipformer2.cs:144-362: per-stream caches -> batched tensors (batch on axis 1)."""
+        if self._layout is None:
+            return stateList
+        import torch
+        slots = [st.slot for st in stateList]
+        n = self._native.state_pool_stacked_floats(len(slots))
+        buf = torch.empty(n, dtype=torch.float32, device=f"cuda:{self._device}")
+        torch.cuda.current_stream(self._device).synchronize()       # the buffer is written on the handle's stream
+        self._native.stack_states_dev(slots, self._layout[1], buf.data_ptr())
+        return StackedStates(buf, slots)
 
     def unstack_states(self, encoder_out_states):
-        return encoder_out_states
+        """ref OnlineProjOfZipformer2.cs:363-489: the encoder's new batched caches -> back into every stream's slot."""
+        if self._layout is None:
+            return encoder_out_states
+        st = encoder_out_states
+        self._native.unstack_states_dev(st.slots, self._layout[1], st.buffer.data_ptr())
+        self._native.sync()
+        return [DeviceStates(s) for s in st.slots]
 
     def EncoderProj(self, modelInputs: List[OnlineInputEntity], batchSize: int, statesList=None) -> EncoderOutputEntity:
         """ref OnlineProjOfZipformer2.cs:491-618 reduced to its tail: [B,T',J] projected frames + caches."""
@@ -205,6 +278,9 @@ class OnlineProjOfB200(_ProjBase):
             x = _pad_batch(modelInputs, self.FrameWidth)
             if self._frames_are_raw:
                 x = self._native.encoder_proj(x)
+            if self._encoder_hook is not None and isinstance(statesList, StackedStates):
+                self._native.sync()
+                self._encoder_hook(statesList.buffer)            # the encoder network would consume / produce the caches here
             return EncoderOutputEntity(encoder_out=x.reshape(-1), encoder_out_lens=np.full(batchSize, x.shape[1], np.int64),
                                        encoder_out_states=statesList)
         except Exception as ex:
@@ -232,3 +308,6 @@ class OnlineProjOfB200ctc(OfflineProjOfB200ctc):
 
     def unstack_states(self, encoder_out_states):
         return encoder_out_states
+
+    def ReleaseStates(self, states):
+        pass

@@ -21,6 +21,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import _native
+from .text import decode_multi
 from .proj import (OfflineInputEntity, OnlineInputEntity, OfflineProjOfB200, OfflineProjOfB200ctc,
                    OnlineProjOfB200, OnlineProjOfB200ctc)
 
@@ -41,21 +42,10 @@ def _argmax_hi_rows(logits: np.ndarray) -> np.ndarray:
     return V - 1 - np.argmax(logits[:, ::-1], axis=1)
 
 
-def _decode_text(token_ids: Sequence[int], symbols: Optional[Sequence[str]]):
-    """DecodeMulti, reduced (ref OfflineRecognizer.cs:432-577): stop at id 2 offline is NOT replicated here;
-    skip <blk>, <sos/eos>, <unk>; sentencepiece U+2581 -> space; lower-case."""
-    toks, text = [], ""
-    if symbols is None:
-        return "", []
-    for t in token_ids:
-        if t < 0 or t >= len(symbols):
-            continue
-        s = symbols[t].split(" ")[0]
-        if s in ("<blk>", "<sos/eos>", "<unk>"):
-            continue
-        toks.append(s)
-        text += s
-    return text.replace("▁", " ").strip().lower(), toks
+def _decode_text(token_ids: Sequence[int], symbols: Optional[Sequence[str]], online: bool = False):
+    """DecodeMulti of one stream (ref OfflineRecognizer.cs:432-467, OnlineRecognizer.cs:321-351): text.py restates it in full -
+    stop at id 2, <0xNN> byte fallback, byte-level BPE, lower-casing."""
+    return decode_multi(token_ids, symbols, online=online)
 
 
 # ---- streams ------------------------------------------------------------------------------------------
@@ -102,6 +92,8 @@ class OnlineStream:
         self.FrameOffset = 0
         self.NumTrailingBlank = 0
         self._finished = False
+        self.BeamSlot: Optional[int] = None      # streaming modified_beam_search: this stream's slot in the device beam pool
+        self.NumProcessedFrames = 0              # encoder frames decoded since the stream began (or was last reset)
 
     def AcceptFrames(self, frames: np.ndarray):
         f = np.asarray(frames, np.float32).reshape(-1, self._width)
@@ -137,8 +129,11 @@ class OfflineRecognizer:
     ref :54-68). batch_mode: 'compat' restates the reference batch loop incl. Q5/Q6, 'per_stream' is ours."""
 
     def __init__(self, offlineProj, tokens: Optional[Sequence[str]] = None, decodingMethod: str = "greedy_search",
-                 fused: bool = True, maxActivePaths: int = 4, batch_mode: str = "compat"):
+                 fused: bool = True, maxActivePaths: int = 4, batch_mode: str = "compat", maxSymPerFrame: int = 1):
         self._offlineProj = offlineProj
+        self._max_sym_per_frame = maxSymPerFrame                         # ref :19 (fixed to 1 there)
+        if maxSymPerFrame != 1:
+            offlineProj.Native.set_option("max_sym_per_frame", maxSymPerFrame)
         self._tokens = list(tokens) if tokens is not None else None
         self._blank_id = offlineProj.Blank_id
         self._unk_id = offlineProj.Unk_id
@@ -190,8 +185,12 @@ class OfflineRecognizer:
             hypList = [-1, self._blank_id]
             decoder_out = proj.DecoderProj(np.array(hypList, np.int64), 1).decoder_out
             timestamp: List[int] = []
-            t, sym_per_utt = 0, 0
+            t, sym_per_utt, sym_per_frame = 0, 0, 0
             while t < TT and sym_per_utt < 1000:
+                if sym_per_frame >= self._max_sym_per_frame:             # ref :129-134
+                    sym_per_frame = 0
+                    t += 1
+                    continue
                 logits = proj.JoinerProj(frames[0, t], decoder_out).Logits
                 y = int(_argmax_hi_rows(logits)[0])
                 if y != self._blank_id and y != self._unk_id:
@@ -199,7 +198,10 @@ class OfflineRecognizer:
                     timestamp.append(t)
                     decoder_out = proj.DecoderProj(np.array(hypList[-ctx:], np.int64), 1).decoder_out
                     sym_per_utt += 1
-                t += 1                      # max_sym_per_frame == 1 (ref :19, :129-134)
+                    sym_per_frame += 1
+                else:                                                    # ref :174-178
+                    sym_per_frame = 0
+                    t += 1
             stream.Tokens = hypList
             stream.Timestamps.extend(timestamp)
         except Exception as ex:
@@ -315,20 +317,52 @@ class OfflineRecognizer:
 
 # ---- online ----------------------------------------------------------------------------------------------
 class OnlineRecognizer:
-    """ref OnlineRecognizer.cs:11-84."""
+    """ref OnlineRecognizer.cs:11-84. `decodingMethod`: greedy_search | greedy_search_ctc | modified_beam_search - the reference
+    accepts the last together with `maxActivePaths` and silently decodes greedily (ref :18-19, :46-57); here it selects the
+    streaming beam search of the library (hypotheses carried between chunks in device slots). `enableEndpoint` (accepted and
+    ignored by the reference, ref :19) switches the NumTrailingBlank-based endpoint rules on (IsEndpoint)."""
+
+    # endpoint rules [EXT: sherpa-onnx defaults], in encoder frames of 40 ms: trailing silence with nothing decoded, trailing
+    # silence after something was decoded, utterance length
+    RULE1_FRAMES, RULE2_FRAMES, RULE3_FRAMES = 60, 30, 500
 
     def __init__(self, onlineProj, tokens: Optional[Sequence[str]] = None, decodingMethod: str = "greedy_search",
-                 fused: bool = True, maxActivePaths: int = 4, enableEndpoint: int = 0):
+                 fused: bool = True, maxActivePaths: int = 4, enableEndpoint: int = 0, maxStreams: int = 512,
+                 maxFrames: int = 4096):
         self._onlineProj = onlineProj
         self._tokens = list(tokens) if tokens is not None else None
         self._fused = fused
+        self._beam = maxActivePaths
+        self._enableEndpoint = enableEndpoint
+        self._free_slots: List[int] = []
         if onlineProj.CustomMetadata.Model_type == "zipformer2ctc":      # ref :34-37
             decodingMethod = "greedy_search_ctc"
-        self._forwardBatch = (self.ForwardBatchGreedySearchCTC if decodingMethod == "greedy_search_ctc"
-                              else self.ForwardBatchGreedySearch)        # ref :46-57
+        if decodingMethod == "greedy_search_ctc":
+            self._forwardBatch = self.ForwardBatchGreedySearchCTC
+        elif decodingMethod == "modified_beam_search":
+            self._forwardBatch = self.ForwardBatchModifiedBeamSearch
+            onlineProj.Native.beam_pool_create(maxStreams, maxActivePaths, maxFrames)
+            self._free_slots = list(range(maxStreams - 1, -1, -1))
+            self._cap = maxFrames
+        else:
+            self._forwardBatch = self.ForwardBatchGreedySearch           # ref :46-57
+        self._decodingMethod = decodingMethod
 
     def CreateOnlineStream(self) -> OnlineStream:                        # ref :60-64
-        return OnlineStream(self._onlineProj)
+        s = OnlineStream(self._onlineProj)
+        if self._decodingMethod == "modified_beam_search":
+            if not self._free_slots:
+                raise Exception("OnlineRecognizer: more concurrent streams than maxStreams")
+            s.BeamSlot = self._free_slots.pop()
+            self._onlineProj.Native.beam_pool_reset(s.BeamSlot, s.Hyp)
+        return s
+
+    def ReleaseOnlineStream(self, stream: OnlineStream):
+        """Gives the stream's device slots (beam pool, encoder caches) back; the reference leaves this to the GC."""
+        if stream.BeamSlot is not None:
+            self._free_slots.append(stream.BeamSlot)
+            stream.BeamSlot = None
+        self._onlineProj.ReleaseStates(stream.States)
 
     def GetResult(self, stream: OnlineStream):                           # ref :66-74
         return self.GetResults([stream])[0]
@@ -337,9 +371,41 @@ class OnlineRecognizer:
         self._forwardBatch(streams)
         out = []
         for s in streams:
-            text, toks = _decode_text(s.Tokens, self._tokens)
+            text, toks = _decode_text(s.Tokens, self._tokens, online=True)
             out.append(OnlineRecognizerResultEntity(text=text, tokens=toks, timestamps=list(s.Timestamps)))
         return out
+
+    # -- endpointing on NumTrailingBlank (the field exists in the reference, OnlineStream.cs:16,55,
+    #    but nothing produces or consumes it on the transducer path) --------------------------------------------------------------
+    def IsEndpoint(self, stream: OnlineStream) -> bool:
+        if not self._enableEndpoint:
+            return False
+        decoded = len(stream.Tokens) > self._onlineProj.CustomMetadata.Context_size
+        if not decoded and stream.NumTrailingBlank >= self.RULE1_FRAMES:
+            return True
+        if decoded and stream.NumTrailingBlank >= self.RULE2_FRAMES:
+            return True
+        return stream.NumProcessedFrames >= self.RULE3_FRAMES
+
+    def Reset(self, stream: OnlineStream):
+        """After an endpoint: a new utterance on the same stream (encoder caches are kept, the search state starts over)."""
+        blank = self._onlineProj.Blank_id
+        stream.Hyp = np.array([blank, blank], np.int64)
+        stream.Tokens = [blank, blank]
+        stream.Timestamps = []
+        stream.NumTrailingBlank = 0
+        stream.NumProcessedFrames = 0
+        if stream.BeamSlot is not None:
+            self._onlineProj.Native.beam_pool_reset(stream.BeamSlot, stream.Hyp)
+
+    @staticmethod
+    def _count_trailing(stream: OnlineStream, n_frames: int, chunk_ts: Sequence[int]):
+        """NumTrailingBlank from one chunk's chunk-local timestamps (the rule of the CTC loop, ref OfflineRecognizer.cs:337-344)."""
+        stream.NumProcessedFrames += n_frames
+        if len(chunk_ts):
+            stream.NumTrailingBlank = n_frames - 1 - int(chunk_ts[-1])
+        else:
+            stream.NumTrailingBlank += n_frames
 
     def _collect(self, streams: List[OnlineStream]):
         """ref :97-120: streams without a full chunk are REMOVED from the caller's list."""
@@ -400,6 +466,7 @@ class OnlineRecognizer:
                 s.Hyp = np.asarray(hyp_out[m], np.int64).copy()          # ref :208
                 s.Timestamps.extend(tss[m])                              # chunk-local t (ref :184)
                 s.States = next_states[m] if next_states else s.States
+                self._count_trailing(s, frames.shape[1], tss[m])
         except Exception as ex:
             raise Exception("Online recognition failed") from ex        # ref :215-218
 
@@ -424,6 +491,36 @@ class OnlineRecognizer:
                 s.Tokens = list(s.Tokens) + toks[m]
                 s.Timestamps = list(s.Timestamps) + tss[m]
                 s.States = next_states[m] if next_states else s.States
+        except Exception as ex:
+            raise Exception("Online recognition failed") from ex
+
+    # -- streaming modified_beam_search (ours; what maxActivePaths was meant for) ------------------------------------------------
+    def ForwardBatchModifiedBeamSearch(self, streams: List[OnlineStream]):
+        if len(streams) == 0:
+            return
+        inputs, active = self._collect(streams)
+        if not inputs:
+            return
+        proj = self._onlineProj
+        B = len(inputs)
+        try:
+            states = proj.stack_states([s.States for s in active])
+            enc = proj.EncoderProj(inputs, B, states)
+            J = proj.CustomMetadata.Joiner_dim
+            frames = enc.encoder_out.reshape(B, -1, J)
+            slots = [s.BeamSlot for s in active]
+            toks, tss, score, hyp_out = proj.Native.modified_beam_search_online_chunk(frames, slots, cap=self._cap, enc_is_raw=False)
+            next_states = proj.unstack_states(enc.encoder_out_states)
+            blank = proj.Blank_id
+            for m, s in enumerate(active):
+                # the best hypothesis may change retroactively: Tokens / Timestamps are REPLACED, not appended to
+                s.Tokens = [blank, blank] + toks[m]                      # seed of ref OnlineStream.cs:45
+                s.Timestamps = list(tss[m])                              # frame index since the stream began
+                s.Hyp = np.asarray(hyp_out[m], np.int64).copy()
+                s.States = next_states[m] if next_states else s.States
+                s.NumProcessedFrames += frames.shape[1]
+                s.NumTrailingBlank = s.NumProcessedFrames - 1 - tss[m][-1] if tss[m] else s.NumProcessedFrames
+            self.LastScores = [float(x) for x in score]
         except Exception as ex:
             raise Exception("Online recognition failed") from ex
 

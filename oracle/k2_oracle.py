@@ -207,33 +207,50 @@ class StreamResult:
     score: float = 0.0             # mbs: un-normalised log-prob of the chosen hypothesis
     min_gap: float = float("inf")  # smallest decision margin met while decoding this stream
     hyp: Optional[List[int]] = None  # online: stream.Hyp after the call
+    frame_gap: List[float] = field(default_factory=list)   # decision margin of every decoded frame (greedy: top-2 logit gap;
+                                                           # mbs: smallest adjacent gap among the stream's top-(beam+1) scores)
+    history: Optional[List[List[tuple]]] = None   # mbs: per frame, the surviving hypotheses in insertion order as
+                                                  # (parent slot in the previous frame's list, appended token or -1)
+    final_gap: float = float("inf")               # mbs: margin of the final length-normalised pick
 
 
 # --------------------------------------------------------------------------------------------
 # A.1 offline single-stream greedy  (ref OfflineRecognizer.cs:93-187)
 # --------------------------------------------------------------------------------------------
-def greedy_search_single(m: Model, enc: np.ndarray, max_sym_per_utt: int = 1000) -> StreamResult:
-    """enc [T,J] projected frames. max_sym_per_frame == 1 (ref :19) => one joiner evaluation per
-    frame; emit unless y in {blank, unk} (ref :161); decoder refreshed on emission (ref :165-170);
-    Tokens start {-1, blank} (ref :115-117); timestamps = frame index (ref :164)."""
+def greedy_search_single(m: Model, enc: np.ndarray, max_sym_per_utt: int = 1000,
+                         max_sym_per_frame: int = 1) -> StreamResult:
+    """enc [T,J] projected frames. The loop of ref :127-179 verbatim: a frame is re-evaluated with the
+    refreshed decoder output until it yields blank / unk or `max_sym_per_frame` symbols were emitted on it
+    (the reference fixes max_sym_per_frame = 1, ref :19 => one joiner evaluation per frame); emit unless
+    y in {blank, unk} (ref :161); decoder refreshed on emission (ref :165-170); Tokens start {-1, blank}
+    (ref :115-117); timestamps = frame index (ref :164). frame_gap[t] = the smallest top-2 margin of the
+    evaluations made on frame t."""
     enc = np.asarray(enc, F32).reshape(-1, m.J)
     T = enc.shape[0]
     toks = [-1, m.blank_id]
     ts: List[int] = []
     d = decoder(m, np.array([[-1, m.blank_id]], np.int64))
-    t, n_sym, gap = 0, 0, float("inf")
+    t, n_sym, sym_per_frame = 0, 0, 0
+    fgap = [float("inf")] * T
     while t < T and n_sym < max_sym_per_utt:
+        if sym_per_frame >= max_sym_per_frame:      # ref :129-134
+            sym_per_frame = 0
+            t += 1
+            continue
         lg = joiner(m, enc[t:t + 1], d)
         y = int(argmax_hi(lg)[0])
-        gap = min(gap, float(top2_gap(lg)[0]))
+        fgap[t] = min(fgap[t], float(top2_gap(lg)[0]))
         if y != m.blank_id and y != m.unk_id:
             toks.append(y)
             ts.append(t)
             d = decoder(m, np.array([toks[-m.context_size:]], np.int64))
             n_sym += 1
-        # with max_sym_per_frame == 1 the frame index advances either way (ref :129-134, :174-178)
-        t += 1
-    return StreamResult(tokens=toks, timestamps=ts, appended=toks[2:], min_gap=gap)
+            sym_per_frame += 1
+        else:                                       # ref :174-178
+            sym_per_frame = 0
+            t += 1
+    return StreamResult(tokens=toks, timestamps=ts, appended=toks[2:], min_gap=min(fgap, default=float("inf")),
+                        frame_gap=fgap)
 
 
 # --------------------------------------------------------------------------------------------
@@ -255,10 +272,12 @@ def greedy_search_batch(m: Model, enc: np.ndarray, compat: bool = True) -> List[
         ts = [[] for _ in range(B)]
     n0 = len(toks[0]) if B else 0
     gap = np.full(B, np.inf, F32)
+    fgap = np.full((B, T), np.inf, F32)
     for t in range(T):
         lg = joiner(m, enc[:, t, :], d)
         y = argmax_hi(lg)
-        gap = np.minimum(gap, top2_gap(lg))
+        fgap[:, t] = top2_gap(lg)
+        gap = np.minimum(gap, fgap[:, t])
         emitted = False
         for b in range(B):
             if y[b] != blank and y[b] != m.unk_id:
@@ -272,8 +291,8 @@ def greedy_search_batch(m: Model, enc: np.ndarray, compat: bool = True) -> List[
         toks = [[] for _ in range(B)]
         ts = [[] for _ in range(B)]
         n0 = 0
-    return [StreamResult(tokens=toks[b], timestamps=ts[b], appended=toks[b][n0:], min_gap=float(gap[b]))
-            for b in range(B)]
+    return [StreamResult(tokens=toks[b], timestamps=ts[b], appended=toks[b][n0:], min_gap=float(gap[b]),
+                         frame_gap=[float(g) for g in fgap[b]]) for b in range(B)]
 
 
 # --------------------------------------------------------------------------------------------
@@ -292,10 +311,12 @@ def greedy_search_online_chunk(m: Model, enc: np.ndarray, hyps: Sequence[Sequenc
     ts: List[List[int]] = [[] for _ in range(B)]
     d = decoder(m, np.array([list(h) for h in hyps], np.int64).reshape(B, m.context_size))
     gap = np.full(B, np.inf, F32)
+    fgap = np.full((B, T), np.inf, F32)
     for t in range(T):
         lg = joiner(m, enc[:, t, :], d)
         y = argmax_hi(lg)
-        gap = np.minimum(gap, top2_gap(lg))
+        fgap[:, t] = top2_gap(lg)
+        gap = np.minimum(gap, fgap[:, t])
         emitted = False
         for b in range(B):
             if y[b] != m.blank_id and y[b] != m.unk_id and y[b] != 1:
@@ -305,7 +326,7 @@ def greedy_search_online_chunk(m: Model, enc: np.ndarray, hyps: Sequence[Sequenc
         if emitted:
             d = decoder(m, np.array([tk[-m.context_size:] for tk in toks], np.int64))
     return [StreamResult(tokens=toks[b], timestamps=ts[b], appended=toks[b][n0[b]:], min_gap=float(gap[b]),
-                         hyp=toks[b][-m.context_size:]) for b in range(B)]
+                         hyp=toks[b][-m.context_size:], frame_gap=[float(g) for g in fgap[b]]) for b in range(B)]
 
 
 # --------------------------------------------------------------------------------------------
@@ -338,9 +359,12 @@ def ctc_greedy_search(logp: np.ndarray, blank: int = 0, frame_offset: Optional[S
                 toks.append(y)
                 ts.append(t + off)
             prev_id = y
+        fg: List[float] = []
         if T and V > 1 and not nanrow.any():
-            gap = float(top2_gap(rows).min())
-        r = StreamResult(tokens=toks, timestamps=ts, appended=toks, num_trailing_blank=ntb, min_gap=gap)
+            g2 = top2_gap(rows)
+            gap = float(g2.min())
+            fg = [float(x) for x in g2]
+        r = StreamResult(tokens=toks, timestamps=ts, appended=toks, num_trailing_blank=ntb, min_gap=gap, frame_gap=fg)
         r.hyp = [prev_id]
         out.append(r)
     return out
@@ -370,7 +394,17 @@ class _Hyp:
     ts: List[int]
 
 
-def modified_beam_search(m: Model, enc: np.ndarray, beam: int = 4) -> List[StreamResult]:
+def mbs_seed(m: Model, B: int, hyp: Optional[Sequence[Sequence[int]]] = None) -> List[List[_Hyp]]:
+    """Initial beam of B streams: one hypothesis {ys = [-1]*(ctx-1) + [blank], lp = 0} (offline, the seed of
+    ref OfflineRecognizer.cs:105), or ys = stream.Hyp (online: {blank, blank}, ref OnlineStream.cs:44-45)."""
+    if hyp is None:
+        return [[_Hyp([-1] * (m.context_size - 1) + [m.blank_id], F32(0), [])] for _ in range(B)]
+    return [[_Hyp([int(x) for x in hyp[b]], F32(0), [])] for b in range(B)]
+
+
+def modified_beam_search(m: Model, enc: np.ndarray, beam: int = 4, init: Optional[List[List[_Hyp]]] = None,
+                         frame_offset: Optional[Sequence[int]] = None, extra_mask: Optional[int] = None,
+                         return_state: bool = False):
     """enc [B,T,J]. Per stream keep <= beam hypotheses, seeded {ys=[-1]*(ctx-1)+[blank], lp=0}.
     Per frame: decoder on every live hypothesis' last ctx tokens -> joiner with the stream's frame
     -> log_softmax -> + hyp.lp -> top-`beam` over the stream's flattened [n_hyps*V] scores ->
@@ -378,12 +412,19 @@ def modified_beam_search(m: Model, enc: np.ndarray, beam: int = 4) -> List[Strea
     hypothesis keeps its timestamps. Result: argmax lp/len(ys) (len counts the seeds), first
     maximum in insertion order.
     Stated choices nothing pins: top-k order is value-descending then flat-index-DEscending
-    (consistent with Q1: beam=1 equals greedy_search_single), temperature 1, no blank penalty."""
+    (consistent with Q1: beam=1 equals greedy_search_single), temperature 1, no blank penalty.
+    Streaming (the dead maxActivePaths of ref OnlineRecognizer.cs:19 brought to life): `init` = the beams a
+    previous chunk returned (return_state=True), `frame_offset[b]` = frames of stream b decoded before this
+    chunk (timestamps are utterance-absolute), `extra_mask` = a third non-emitting id (the literal 1 of
+    ref OnlineRecognizer.cs:181). Decoding an utterance chunk by chunk equals decoding it whole."""
     enc = np.asarray(enc, F32)
     B, T, _ = enc.shape
     V = m.V
-    hyps: List[List[_Hyp]] = [[_Hyp([-1] * (m.context_size - 1) + [m.blank_id], F32(0), [])] for _ in range(B)]
+    hyps: List[List[_Hyp]] = mbs_seed(m, B) if init is None else [[_Hyp(list(h.ys), F32(h.lp), list(h.ts)) for h in hs] for hs in init]
+    foff = [0] * B if frame_offset is None else [int(x) for x in frame_offset]
     gap = np.full(B, np.inf, np.float64)
+    fgap = np.full((B, T), np.inf, np.float64)
+    history: List[List[List[tuple]]] = [[] for _ in range(B)]
     for t in range(T):
         counts = [len(h) for h in hyps]
         ctx = np.array([h.ys[-m.context_size:] for hs in hyps for h in hs], np.int64)
@@ -408,16 +449,20 @@ def modified_beam_search(m: Model, enc: np.ndarray, beam: int = 4) -> List[Strea
             # of two colliding hypotheses is inserted first and so keeps its timestamps)
             head = flat[order[:min(k + 1, flat.size)]].astype(np.float64)
             if head.size > 1:
-                gap[b] = min(gap[b], float(np.min(head[:-1] - head[1:])))
+                fgap[b, t] = float(np.min(head[:-1] - head[1:]))
+                gap[b] = min(gap[b], fgap[b, t])
             new: List[_Hyp] = []
             index = {}
+            rec: List[tuple] = []
             for fi in top:
-                h = hyps[b][int(fi) // V]
+                par = int(fi) // V
+                h = hyps[b][par]
                 tok = int(fi) % V
                 ys, tss = h.ys, h.ts
-                if tok != m.blank_id and tok != m.unk_id:
+                emit = tok != m.blank_id and tok != m.unk_id and tok != extra_mask
+                if emit:
                     ys = ys + [tok]
-                    tss = tss + [t]
+                    tss = tss + [t + foff[b]]
                 key = tuple(ys)
                 if key in index:
                     o = new[index[key]]
@@ -425,7 +470,9 @@ def modified_beam_search(m: Model, enc: np.ndarray, beam: int = 4) -> List[Strea
                 else:
                     index[key] = len(new)
                     new.append(_Hyp(list(ys), F32(flat[fi]), list(tss)))
+                    rec.append((par, tok if emit else -1))
             hyps[b] = new
+            history[b].append(rec)
     out = []
     for b in range(B):
         norm = [F32(h.lp) / F32(len(h.ys)) for h in hyps[b]]
@@ -433,13 +480,16 @@ def modified_beam_search(m: Model, enc: np.ndarray, beam: int = 4) -> List[Strea
         for i in range(1, len(norm)):
             if norm[i] > norm[bi]:
                 bi = i
+        fin = float("inf")
         if len(norm) > 1:
             srt = sorted(float(x) for x in norm)
-            gap[b] = min(gap[b], srt[-1] - srt[-2])
+            fin = srt[-1] - srt[-2]
+            gap[b] = min(gap[b], fin)
         h = hyps[b][bi]
         out.append(StreamResult(tokens=h.ys, timestamps=h.ts, appended=h.ys[m.context_size:], score=float(h.lp),
-                                min_gap=float(gap[b])))
-    return out
+                                min_gap=float(gap[b]), hyp=h.ys[-m.context_size:], frame_gap=[float(g) for g in fgap[b]],
+                                history=history[b], final_gap=fin))
+    return (out, hyps) if return_state else out
 
 
 def ragged(search, m: Model, enc: np.ndarray, lens: Sequence[int], *args, **kw) -> List[StreamResult]:

@@ -1,13 +1,15 @@
-"""Shared checkers of the parity tests. The oracle (oracle/k2_oracle.py) is the reference side."""
+"""Shared checkers of the parity tests. The oracle (oracle/k2_oracle.py) is the reference side; the comparison rules live in
+oracle/parity.py (first divergent frame, near ties judged AT that frame, frames-identical percentage)."""
 from __future__ import annotations
 
 import numpy as np
 
 from k2transducerasr_b200 import synth
 from oracle import k2_oracle as O
+from oracle import parity as P
 
-NEAR_TIE = 1e-4      # BASELINE.json north_star: frames with a top-2 gap under 1e-4 are listed separately
-SCORE_TOL = 1e-3     # hypothesis log-probs: 1e-3 absolute in fp32
+NEAR_TIE = P.NEAR_TIE    # BASELINE.json north_star: frames with a top-2 gap under 1e-4 are listed separately
+SCORE_TOL = P.SCORE_TOL  # hypothesis log-probs: 1e-3 absolute in fp32
 
 SMALL = synth.ModelDims(vocab_size=53, joiner_dim=32, decoder_dim=32, encoder_dim=48)
 MID = synth.ModelDims(vocab_size=500, joiner_dim=512, decoder_dim=512, encoder_dim=256)
@@ -19,19 +21,28 @@ def model_and_weights(dims, blank_bias=0.0, seed=synth.WEIGHT_SEED, **kw):
                              context_size=dims.context_size, **kw), w
 
 
-def compare_streams(got_tokens, got_ts, want, what="", allow_frac=0.02):
-    """Token / timestamp sequences must be identical per stream; a stream may differ only if the oracle met a
-    near-tie decision (gap < NEAR_TIE) while decoding it. Returns the list of excused streams."""
-    assert len(got_tokens) == len(want)
-    excused = []
-    for b, r in enumerate(want):
-        n = len(r.appended)
-        want_ts = list(r.timestamps)[len(r.timestamps) - n:] if n else []
-        if list(got_tokens[b]) == list(r.appended) and list(got_ts[b]) == want_ts:
-            continue
-        assert r.min_gap < NEAR_TIE, (
-            f"{what}: stream {b} differs from the oracle without a near tie (min gap {r.min_gap:.3g}):\n"
-            f" got  {list(got_tokens[b])[:40]}\n want {list(r.appended)[:40]}")
-        excused.append(b)
-    assert len(excused) <= max(1, int(allow_frac * len(want))), f"{what}: too many near-tie streams: {excused}"
+def frames_of(want) -> int:
+    """Frames per stream of an oracle result list (the longest stream of a ragged batch)."""
+    T = max((len(r.frame_gap) for r in want), default=0)
+    if T == 0:
+        T = max((max(r.timestamps) + 1 for r in want if r.timestamps), default=1)
+    return max(T, 1)
+
+
+def parity_report(got_tokens, got_ts, want, scores=None, bp=None, coupled=False, T=None, t0=0) -> P.ParityReport:
+    return P.compare(got_tokens, got_ts, want, T if T is not None else frames_of(want), got_score=scores, bp=bp,
+                     coupled=coupled, t0=t0)
+
+
+def compare_streams(got_tokens, got_ts, want, what="", allow_frac=0.05, scores=None, bp=None, coupled=False, T=None,
+                    min_frames_pct=0.0, score_tol=SCORE_TOL):
+    """Token / timestamp sequences must be identical per stream. A stream may differ only if the oracle's decision margin AT ITS
+    FIRST DIVERGENT FRAME is a near tie (< NEAR_TIE) - located on the beam history when `bp` (k2b_debug_backpointers) is given,
+    on the output otherwise. At most allow_frac of the streams (but one at least) may be such near ties. Returns the excused
+    streams. `scores`: hypothesis log-probs of the identical streams must agree within SCORE_TOL."""
+    rep = parity_report(got_tokens, got_ts, want, scores=scores, bp=bp, coupled=coupled, T=T)
+    rep.assert_ok(what, min_frames_pct=min_frames_pct, score_tol=score_tol)
+    excused = sorted({b for b, _, _ in rep.near_tie_frames} | set(rep.cascade_streams))
+    assert len(excused) <= max(1, int(allow_frac * len(want))), \
+        f"{what}: too many near-tie streams: {rep.near_tie_frames[:10]} (+ cascades {rep.cascade_streams[:10]})"
     return excused

@@ -16,7 +16,7 @@ def test_library_builds_and_exports_header_symbols(built_lib):
     missing = [s for s in declared if not hasattr(lib, s)]
     assert not missing, f"declared in k2b200.h but not exported: {missing}"
     assert set(declared) == set(_native._SIGS), "ctypes binding and header disagree"
-    assert lib.k2b_abi_version() == 1
+    assert lib.k2b_abi_version() == 2
 
 
 def test_only_the_abi_is_exported(built_lib):

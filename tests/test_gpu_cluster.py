@@ -174,8 +174,8 @@ def test_cta_pair_variant_matches_oracle(setup, monkeypatch, prec):
     """K2B_PAIR=1: the CTAs 2i, 2i+1 of a cluster issue tcgen05.mma.cta_group::2 (M = 256, the B operand split between them, so
     each builds 16 of the 32 hypothesis rows). Opt-in (measured slower); must decode like the default kernel."""
     m, w, raw, enc = setup
-    monkeypatch.setenv("K2B_PAIR", "1")
     h = make(MID, w, prec)
+    h.set_option("pair", 1)
     if prec == "bf16x3":
         mo, want_enc = m, enc
     else:
@@ -360,9 +360,9 @@ def test_persistent_beam_kernel_large_vocab(built_lib, monkeypatch, beam):
     raw = synth.make_frames(B, T, dims.encoder_dim, 77 + beam)
     enc = O.encoder_proj(m, raw)
     t1, s1, sc1 = h.modified_beam_search(raw, beam, enc_is_raw=True)
-    monkeypatch.setenv("K2B_NO_MEGA", "1")
+    h.set_option("no_mega", 1)
     t0, s0, sc0 = h.modified_beam_search(raw, beam, enc_is_raw=True)
-    monkeypatch.delenv("K2B_NO_MEGA")
+    h.set_option("no_mega", 0)
     assert t1 == t0 and s1 == s0
     np.testing.assert_array_equal(np.asarray(sc1), np.asarray(sc0))
     want = O.modified_beam_search(m, enc[:12], beam)
@@ -373,7 +373,7 @@ def test_persistent_beam_kernel_large_vocab(built_lib, monkeypatch, beam):
     lens = np.array([(7 * b) % (T + 1) for b in range(B)], np.int64)
     h.set_encoder_out_lens(lens)
     t2, s2, _ = h.modified_beam_search(raw, beam, enc_is_raw=True)
-    monkeypatch.setenv("K2B_NO_MEGA", "1")
+    h.set_option("no_mega", 1)
     h.set_encoder_out_lens(lens)
     t3, s3, _ = h.modified_beam_search(raw, beam, enc_is_raw=True)
     assert t2 == t3 and s2 == s3
@@ -419,9 +419,9 @@ def test_persistent_greedy_large_vocab(built_lib, monkeypatch):
     t, s = h.greedy_offline(raw, _native.GREEDY_PER_STREAM, enc_is_raw=True)
     assert h.launch_count() - n0 <= 8, "the persistent kernel was not taken"
     compare_streams(t, s, O.greedy_search_batch(m, enc, compat=False), "persistent greedy per_stream V=5537", allow_frac=0.2)
-    monkeypatch.setenv("K2B_NO_MEGA", "1")            # the same search as one joiner + one merge launch per frame
+    h.set_option("no_mega", 1)            # the same search as one joiner + one merge launch per frame
     tp, sp = h.greedy_offline(raw, _native.GREEDY_PER_STREAM, enc_is_raw=True)
-    monkeypatch.delenv("K2B_NO_MEGA")
+    h.set_option("no_mega", 0)
     assert tp == t and sp == s
     t1, s1 = h.greedy_offline(raw[:1], _native.GREEDY_SINGLE, enc_is_raw=True)
     ws = O.greedy_search_single(m, enc[0])
@@ -446,14 +446,14 @@ def test_persistent_greedy_large_vocab(built_lib, monkeypatch):
     raw = synth.make_frames(B, 2 * Tc, dims.encoder_dim, 92)
     outs = []
     for force in ("0", "1"):
-        monkeypatch.setenv("K2B_GREEDY_PERSISTENT", force)
+        h.set_option("greedy_persistent", int(force))
         hyp = np.zeros((B, 2), np.int64)
         got = []
         for c in range(2):
             t, s, hyp = h.greedy_online_chunk(np.ascontiguousarray(raw[:, Tc * c:Tc * c + Tc]), hyp, enc_is_raw=True)
             got.append((t, s, hyp.tolist()))
         outs.append(got)
-    monkeypatch.delenv("K2B_GREEDY_PERSISTENT")
+    h.set_option("greedy_persistent", -1)
     same = sum(1 for b in range(B) if all(outs[0][c][0][b] == outs[1][c][0][b] and outs[0][c][1][b] == outs[1][c][1][b] for c in range(2)))
     assert same >= B - 2, f"persistent and cluster greedy disagree on {B - same} of {B} streams"      # near ties may differ
     h.close()
@@ -492,16 +492,16 @@ def test_time_chunked_host_call_large_vocab(built_lib, monkeypatch, beam):
     n0 = h.launch_count()
     t1, s1, sc1 = h.modified_beam_search(raw, beam, enc_is_raw=True)
     n_chunked = h.launch_count() - n0
-    monkeypatch.setenv("K2B_PIPE_CHUNKS", "1")
+    h.set_option("pipe_chunks", 1)
     n0 = h.launch_count()
     t2, s2, sc2 = h.modified_beam_search(raw, beam, enc_is_raw=True)
     n_one = h.launch_count() - n0
-    monkeypatch.delenv("K2B_PIPE_CHUNKS")
+    h.set_option("pipe_chunks", 0)
     assert t1 == t2 and s1 == s2 and sc1.tolist() == sc2.tolist()
     assert n_chunked > n_one, (n_chunked, n_one)
     lens = [T - (11 * b) % T for b in range(B)]
     t3, s3, _ = h.modified_beam_search(raw, beam, enc_is_raw=True, lens=lens)
-    monkeypatch.setenv("K2B_PIPE_CHUNKS", "1")
+    h.set_option("pipe_chunks", 1)
     t4, s4, _ = h.modified_beam_search(raw, beam, enc_is_raw=True, lens=lens)
     assert t3 == t4 and s3 == s4
     enc = O.encoder_proj(m, raw[:6])

@@ -383,9 +383,9 @@ def test_full_size_cfg4_properties(built_lib, monkeypatch):
     assert [tr[b] for b in range(cfg.streams) if lens[b] == T] == [t1[b] for b in range(cfg.streams) if lens[b] == T]
     full = synth.make_frames(cfg.streams, cfg.frames, cfg.dims.encoder_dim, cfg.seed + 1)
     tm, sm, scm = h.modified_beam_search(full, 4, enc_is_raw=True)
-    monkeypatch.setenv("K2B_NO_MEGA", "1")
+    h.set_option("no_mega", 1)
     tp, sp, scp = h.modified_beam_search(full, 4, enc_is_raw=True)
-    monkeypatch.delenv("K2B_NO_MEGA")
+    h.set_option("no_mega", 0)
     assert tm == tp and sm == sp and scm.tolist() == scp.tolist()
     assert sum(len(t) for t in tm) > cfg.streams * 10            # it decoded something
     h.close()
