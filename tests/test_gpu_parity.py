@@ -216,7 +216,8 @@ def test_beam_search_vs_oracle_mid(mid, beam):
     enc = O.encoder_proj(m, raw)
     want = O.modified_beam_search(m, enc, beam)
     t, s, sc = h.modified_beam_search(raw, beam)
-    ex = compare_streams(t, s, want, f"mbs beam={beam}")
+    bp = h.debug_backpointers(10, 40, beam)
+    ex = compare_streams(t, s, want, f"mbs beam={beam}", bp=bp, scores=sc, allow_frac=0.1)
     for b, r in enumerate(want):
         if b not in ex:
             assert abs(float(sc[b]) - r.score) < SCORE_TOL
@@ -324,7 +325,7 @@ def test_full_size_cfg2_properties(built_lib):
     assert all(all(3 <= tok < cfg.dims.vocab_size or tok == 1 for tok in t) for t in t1)
     enc = O.encoder_proj(m, raw[:6])
     want = O.modified_beam_search(m, enc, 4)
-    ex = compare_streams(t1[:6], s1[:6], want, "cfg2 spot", allow_frac=0.5)
+    ex = compare_streams(t1[:6], s1[:6], want, "cfg2 spot", allow_frac=0.15)
     for b in range(6):
         if b not in ex:
             assert abs(float(sc1[b]) - want[b].score) < SCORE_TOL
@@ -373,7 +374,7 @@ def test_full_size_cfg4_properties(built_lib, monkeypatch):
     assert all(all(3 <= tok < cfg.dims.vocab_size or tok == 1 for tok in t) for t in t1)
     enc = O.encoder_proj(m, raw[:4])
     want = O.modified_beam_search(m, enc, 4)
-    ex = compare_streams(t1[:4], s1[:4], want, "cfg4 spot", allow_frac=0.5)
+    ex = compare_streams(t1[:4], s1[:4], want, "cfg4 spot", allow_frac=0.15)
     for b in range(4):
         if b not in ex:
             assert abs(float(sc1[b]) - want[b].score) < SCORE_TOL
@@ -417,5 +418,5 @@ def test_full_size_cfg3_online_properties(built_lib):
         assert all(tok not in (0, 1, 2) for tok in t_all[b])    # ref :181: blank, unk and the literal 1 are never emitted
     enc = O.encoder_proj(m, raw[:6])
     res = O.greedy_search_online_chunk(m, enc, [[0, 0]] * 6, [[0, 0]] * 6)
-    compare_streams(t_all[:6], s_all[:6], res, "cfg3 spot", allow_frac=0.5)
+    compare_streams(t_all[:6], s_all[:6], res, "cfg3 spot", allow_frac=0.15)
     h.close()
