@@ -1,26 +1,32 @@
 #!/usr/bin/env python
 """bench.py - encoder frames/sec decoded by the transducer-search hot path (BASELINE.json metric).
 
-A "step" is one pass of the hot path over one batch of synthetic input of cfg2's shape
-(zipformer-large-en offline, modified_beam_search beam=4, 256 utterances x 250 frames, vocab 500, E=768):
-encoder_proj -> per frame {stateless decoder, fused joiner + log-softmax/top-k, hypothesis merge} -> best
-hypothesis per stream. One independent batch per GPU (weak scaling), no data-path collective; NCCL only
-gathers the per-stream results for reporting (inside the timed region).
+A "step" is one pass of the hot path over one batch of synthetic input of the named config's shape. Default workload = cfg2, the
+config BASELINE.json's metric is quoted on (zipformer-large-en offline, modified_beam_search beam=4, 256 utterances x 250 frames,
+vocab 500, E=768): encoder_proj -> per frame {stateless decoder, fused joiner + log-softmax/top-k, hypothesis merge} -> best
+hypothesis per stream. One independent batch per GPU (weak scaling), no data-path collective; with more than one rank every step
+ends with ONE all-gather of all ranks' results over NVLink (k2b_gather_results_nccl), inside the timed region of `value`.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg1|cfg2|cfg3|cfg4|cfg5]
     torchrun ... bench.py --gpus N ...      (one rank per GPU)
 
-`value`  : frames/s with the batch already resident in HBM (device-pointer entry point).
-`e2e`    : the same metric through the host-pointer C-ABI call a P/Invoke shim makes, from pinned host
-           memory, H2D and D2H copies inside the timed region.
-`roofline`: the joiner GEMM launch (dominant kernel): 2*N*J*V flop per launch over its CUDA-event duration,
-           against the measured bf16 tensor peak.
-`cpu_baseline` / --impl reference: the CPU oracle port (numpy/OpenBLAS, all host threads) on a bounded sample
-           of the same workload. The reference C#+ONNX Runtime binary cannot run in this image (no .NET).
+`value`   : frames/s with the batch already resident in HBM (device-pointer entry points).
+`e2e`     : the same metric through the host-pointer C-ABI call a P/Invoke shim makes, from page-locked host memory, H2D and D2H
+            copies inside the timed region. Beside it (extra keys, same unit): `e2e_pageable` (what a plain managed array costs),
+            `e2e_projected` (the reference seam's own payload, already projected [B,T,J] frames), `e2e_async` (results of batch i
+            leave while batch i+1 arrives: k2b_set_option("async_d2h")), and `h2d_ceiling` - the bare copy of the same input bytes
+            by every rank at once, i.e. what the box's PCIe / host memory allows whatever the library does.
+`roofline`: the dominant kernel, timed live with CUDA events on the launch stream (k2b_profile_*): tensor roofline for the joiner
+            kernels (cfg1-4: 2*N*J*V flop per hypothesis-frame), HBM roofline for CTC (cfg5: V*4 bytes per frame).
+`parity`  : the outputs of the LAST timed device-resident step against the CPU oracle on the same inputs (frames identical, near
+            ties located at the first divergent frame; oracle/parity.py). Rank 0, N = 1.
+`cpu_baseline` / --impl reference: the CPU oracle port (numpy/OpenBLAS, all host threads) on a bounded sample of the same workload
+            (the same oracle run feeds `parity`). The reference C#+ONNX Runtime binary cannot run in this image (no .NET).
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -37,9 +43,16 @@ sys.path.insert(0, str(ROOT))
 
 from k2transducerasr_b200 import synth  # noqa: E402
 
-CFG4_TRAFFIC = 342.3e6   # dram__bytes_read.sum + dram__bytes_write.sum of one whole-loop launch on cfg4 (337.1 MB + 5.2 MB)
-METRIC = "encoder frames/sec decoded (modified_beam_search beam=4, batch 256/GPU)"
 UNIT = "frames/s"
+METRICS = {
+    "cfg1": "encoder frames/sec decoded (greedy_search, single stream)",
+    "cfg2": "encoder frames/sec decoded (modified_beam_search beam=4, batch 256/GPU)",
+    "cfg3": "encoder frames/sec decoded (online greedy_search, 512 streams/GPU, chunks of 8 frames)",
+    "cfg4": "encoder frames/sec decoded (modified_beam_search beam=4, batch 256/GPU, vocab 5537)",
+    "cfg5": "encoder frames/sec decoded (CTC greedy, 128 streams/GPU)",
+}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (ncu --set full captures under profiles/)
+TRAFFIC = {"cfg2": 247.2e6, "cfg4": 342.3e6, "cfg5": None, "cfg1": None, "cfg3": None}
 
 
 def load_peaks():
@@ -127,30 +140,77 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on a bounded sample (the ONLY place bench.py executes oracle/)
 # ------------------------------------------------------------------------------------------------------------
-def cpu_oracle_step(model, raw_sample, beam):
+def all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is to use every host thread it can."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
+
+
+def oracle_model(cfg):
     from oracle import k2_oracle as O
-    enc = O.encoder_proj(model, raw_sample)
-    return O.modified_beam_search(model, enc, beam)
+    if cfg.mode == "ctc":
+        return None
+    return O.Model.from_dict(synth.make_weights(cfg.dims, blank_bias=cfg.blank_bias))
 
 
-def cpu_sample_setup(cfg, streams):
+def oracle_step(cfg, model, inp):
+    """One pass of the path on the CPU over inp = raw frames [n,T,E] (or log-probs [n,T,V] for CTC). Returns StreamResults."""
     from oracle import k2_oracle as O
-    w = synth.make_weights(cfg.dims, blank_bias=cfg.blank_bias)
-    model = O.Model.from_dict(w)
-    raw = synth.make_frames(streams, cfg.frames, cfg.dims.encoder_dim, cfg.seed)
-    return model, raw
+    if cfg.mode == "ctc":
+        return O.ctc_greedy_search(inp)
+    enc = O.encoder_proj(model, inp)
+    if cfg.mode == "mbs":
+        return O.modified_beam_search(model, enc, cfg.beam)
+    if cfg.mode == "greedy_single":
+        return [O.greedy_search_single(model, enc[0])]
+    n = enc.shape[0]                                   # online greedy: chunks of cfg.frames with Hyp / Tokens carried
+    hyps, toks = [[0, 0]] * n, [[0, 0]] * n
+    out = None
+    for c in range(cfg.chunks):
+        res = O.greedy_search_online_chunk(model, enc[:, c * cfg.frames:(c + 1) * cfg.frames], hyps, toks)
+        hyps, toks = [r.hyp for r in res], [r.tokens for r in res]
+        if out is None:
+            out = res
+        else:
+            for a, r in zip(out, res):
+                a.tokens, a.appended = r.tokens, a.appended + r.appended
+                a.timestamps = a.timestamps + [t + c * cfg.frames for t in r.timestamps]
+                a.frame_gap = a.frame_gap + r.frame_gap
+                a.min_gap = min(a.min_gap, r.min_gap)
+                a.hyp = r.hyp
+    return out
 
 
-def run_cpu_baseline(cfg, streams=32, repeats=1):
-    model, raw = cpu_sample_setup(cfg, streams)
-    cpu_oracle_step(model, raw[:2, :20], cfg.beam)          # warm BLAS
+def make_input(cfg, streams, seed):
+    T = cfg.frames * cfg.chunks
+    if cfg.mode == "ctc":
+        return synth.make_ctc_logp(streams, T, cfg.dims.vocab_size, seed, blank_bias=cfg.blank_bias)
+    return synth.make_frames(streams, T, cfg.dims.encoder_dim, seed)
+
+
+CPU_SAMPLE = {"cfg1": 1, "cfg2": 256, "cfg3": 512, "cfg4": 48, "cfg5": 128}     # streams: ~10-30 s of CPU work each
+
+
+def run_cpu_baseline(cfg, name, inp):
+    """Times the oracle on the first CPU_SAMPLE[name] streams of `inp` (the batch the last timed GPU step decoded) and returns
+    (cpu_baseline dict, oracle results) - the results feed the parity block."""
+    all_host_threads()
+    n = min(CPU_SAMPLE[name], inp.shape[0])
+    model = oracle_model(cfg)
+    T = cfg.frames * cfg.chunks
+    if cfg.mode != "greedy_online":
+        oracle_step(cfg, model, inp[:1, :min(T, 16)])          # warm BLAS
+    reps = 20 if name == "cfg1" else 1
     t0 = time.perf_counter()
-    for _ in range(repeats):
-        cpu_oracle_step(model, raw, cfg.beam)
-    dt = (time.perf_counter() - t0) / repeats
-    return {"value": streams * cfg.frames / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-            "sample": f"{streams} of {cfg.streams} streams x {cfg.frames} frames, beam {cfg.beam}, oracle/k2_oracle.py "
-                      f"(numpy/OpenBLAS fp32, {os.cpu_count()} threads), {dt:.2f} s"}
+    for _ in range(reps):
+        res = oracle_step(cfg, model, inp[:n])
+    dt = (time.perf_counter() - t0) / reps
+    return ({"value": n * T / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+             "sample": f"{n} of {inp.shape[0]} streams x {T} frames, oracle/k2_oracle.py (numpy/OpenBLAS fp32, "
+                       f"{os.cpu_count()} threads), {dt:.2f} s per pass"}, res)
 
 
 def run_reference_arm(args, cfg):
@@ -158,26 +218,29 @@ def run_reference_arm(args, cfg):
     not runnable here). Rank 0 only; other ranks exit 0 without work."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    all_host_threads()
     budget = 150.0
-    model, raw = cpu_sample_setup(cfg, 4)
+    model = oracle_model(cfg)
+    T = cfg.frames * cfg.chunks
+    probe = make_input(cfg, min(4, cfg.streams), cfg.seed)
     t0 = time.perf_counter()
-    cpu_oracle_step(model, raw, cfg.beam)
-    per_stream = (time.perf_counter() - t0) / 4
-    streams = int(max(2, min(cfg.streams, budget / max(1, args.steps + args.warmup) / max(per_stream * 0.5, 1e-3))))
-    model, raw = cpu_sample_setup(cfg, streams)
+    oracle_step(cfg, model, probe)
+    per_stream = (time.perf_counter() - t0) / probe.shape[0]
+    streams = int(max(1, min(cfg.streams, budget / max(1, args.steps + args.warmup) / max(per_stream * 0.5, 1e-4))))
+    inp = make_input(cfg, streams, cfg.seed)
     for _ in range(args.warmup):
-        cpu_oracle_step(model, raw, cfg.beam)
+        oracle_step(cfg, model, inp)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_oracle_step(model, raw, cfg.beam)
+        oracle_step(cfg, model, inp)
     dt = time.perf_counter() - t0
-    val = streams * cfg.frames * args.steps / dt
-    sample = (f"{streams} of {cfg.streams} streams x {cfg.frames} frames per step, beam {cfg.beam}; CPU oracle port "
-              f"(numpy/OpenBLAS fp32) - the C#+ONNX Runtime reference cannot run in this image (no .NET)")
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    val = streams * T * args.steps / dt
+    sample = (f"{streams} of {cfg.streams} streams x {T} frames per step, {cfg.mode}; CPU oracle port (numpy/OpenBLAS fp32, "
+              f"{os.cpu_count()} threads) - the C#+ONNX Runtime reference cannot run in this image (no .NET)")
+    line = {"impl": "reference", "metric": METRICS[args.workload], "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg.name, "streams_per_step": streams, "frames": cfg.frames, "beam": cfg.beam,
+            "config": {"workload": cfg.name, "streams_per_step": streams, "frames": T, "beam": cfg.beam,
                        "vocab": cfg.dims.vocab_size},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -188,11 +251,129 @@ def run_reference_arm(args, cfg):
 # ------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------
+class Work:
+    """One workload on one rank: device-resident step, host-pointer steps, sizes, roofline bookkeeping."""
+
+    def __init__(self, args, cfg, h, torch, dev, rank, B):
+        self.args, self.cfg, self.h, self.torch, self.dev, self.B = args, cfg, h, torch, dev, B
+        d = cfg.dims
+        self.T = cfg.frames * cfg.chunks
+        self.Tc = cfg.frames
+        self.K, self.V, self.J, self.E = cfg.beam, d.vocab_size, d.joiner_dim, d.encoder_dim
+        self.width = self.V if cfg.mode == "ctc" else self.E
+        self.nbuf = 2
+        # two distinct batches per rank, alternated; each is larger than the 126 MB L2 except cfg1 / cfg3-per-chunk (see config.l2)
+        self.np_in = [make_input(cfg, B, cfg.seed + 17 * rank + i) for i in range(self.nbuf)]
+        self.host_in = [torch.from_numpy(x).pin_memory() for x in self.np_in]
+        self.dev_in = [x.to(dev) for x in self.host_in]
+        self.cap = self.T if cfg.mode != "greedy_online" else self.Tc
+        C = cfg.chunks if cfg.mode == "greedy_online" else 1
+        z = lambda shape, dt, **kw: torch.zeros(shape, dtype=dt, **kw)
+        self.d_tok = z((C, B, self.cap), torch.int64, device=dev); self.d_ts = z((C, B, self.cap), torch.int32, device=dev)
+        self.d_n = z((C, B), torch.int32, device=dev); self.d_sc = z((B,), torch.float32, device=dev)
+        self.d_hyp = z((B, 2), torch.int64, device=dev)
+        self.p_out = [(z((C, B, self.cap), torch.int64).pin_memory(), z((C, B, self.cap), torch.int32).pin_memory(),
+                       z((C, B), torch.int32).pin_memory(), z((B,), torch.float32).pin_memory()) for _ in range(2)]
+        self.p_hyp = z((B, 2), torch.int64).pin_memory()
+        self.pg_in = None          # pageable copies, made on demand
+        self.proj_in = None
+        if cfg.mode == "greedy_online":
+            self.dev_chunks = [[x[:, c * self.Tc:(c + 1) * self.Tc].contiguous() for c in range(C)] for x in self.dev_in]
+            self.host_chunks = [[x[:, c * self.Tc:(c + 1) * self.Tc].contiguous().pin_memory() for c in range(C)] for x in self.host_in]
+
+    # -- sizes ------------------------------------------------------------------------------------------------
+    @property
+    def frames_per_step(self):
+        return self.B * self.T
+
+    @property
+    def h2d(self):
+        return self.B * self.T * self.width * 4 + (self.B * 16 * self.cfg.chunks if self.cfg.mode == "greedy_online" else 0)
+
+    @property
+    def d2h(self):
+        per = self.B * self.cap * 12 + self.B * 4
+        if self.cfg.mode == "mbs":
+            return per + self.B * 4
+        if self.cfg.mode == "greedy_online":
+            return (per + self.B * 16) * self.cfg.chunks
+        return per
+
+    # -- steps -----------------------------------------------------------------------------------------------
+    def step_dev(self, i):
+        h, m, x = self.h, self.cfg.mode, self.dev_in[i % self.nbuf]
+        B, T = self.B, self.T
+        if m == "mbs":
+            h.call("k2b_modified_beam_search_dev", x, 1, B, T, self.K, self.d_tok, self.d_ts, self.d_n, self.d_sc, self.cap)
+        elif m == "greedy_single":
+            h.call("k2b_greedy_offline_dev", x, 1, B, T, 0, self.d_tok, self.d_ts, self.d_n, self.cap)
+        elif m == "ctc":
+            h.call("k2b_ctc_greedy_dev", x, B, T, self.V, 0, None, None, self.d_tok, self.d_ts, self.d_n, None, self.cap)
+        else:
+            self.d_hyp.zero_()
+            for c, xc in enumerate(self.dev_chunks[i % self.nbuf]):
+                h.call("k2b_greedy_online_chunk_dev", xc, 1, B, self.Tc, self.d_hyp, self.d_tok[c], self.d_ts[c], self.d_n[c], self.cap)
+
+    def step_host(self, i, src=None, out=None, raw=1):
+        h, m = self.h, self.cfg.mode
+        x = (src or self.host_in)[i % self.nbuf]
+        tok, ts, n, sc = out or self.p_out[0]
+        B, T = self.B, self.T
+        if m == "mbs":
+            h.call("k2b_modified_beam_search", x, raw, B, T, self.K, tok, ts, n, sc, self.cap)
+        elif m == "greedy_single":
+            h.call("k2b_greedy_offline", x, raw, B, T, 0, tok, ts, n, self.cap)
+        elif m == "ctc":
+            h.call("k2b_ctc_greedy", x, B, T, self.V, 0, None, None, tok, ts, n, None, self.cap)
+        else:
+            self.p_hyp.zero_()
+            chunks = self.host_chunks[i % self.nbuf] if src is None else x
+            for c, xc in enumerate(chunks):
+                h.call("k2b_greedy_online_chunk", xc, raw, B, self.Tc, self.p_hyp, tok[c], ts[c], n[c], self.cap)
+
+    def results(self):
+        """(tokens, timestamps, scores) of the last device-resident step, as Python lists (timestamps utterance-absolute)."""
+        n = self.d_n.cpu().numpy(); tok = self.d_tok.cpu().numpy(); ts = self.d_ts.cpu().numpy()
+        toks, tss = [[] for _ in range(self.B)], [[] for _ in range(self.B)]
+        for c in range(tok.shape[0]):
+            for b in range(self.B):
+                k = int(n[c, b])
+                toks[b] += tok[c, b, :k].tolist()
+                tss[b] += (ts[c, b, :k] + c * self.Tc * (1 if self.cfg.mode == "greedy_online" else 0)).tolist()
+        return toks, tss, (self.d_sc.cpu().numpy() if self.cfg.mode == "mbs" else None)
+
+    # -- roofline of the dominant kernel --------------------------------------------------------------------------
+    def roofline(self, n_launch, tot_ms, ms_step, peaks, fused_loop):
+        cfg, B, T = self.cfg, self.B, self.T
+        avg_ms = tot_ms / max(n_launch, 1)
+        if cfg.mode == "ctc":
+            bytes_per_launch = float(B) * T * self.V * 4
+            gbs = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if n_launch else 0.0
+            return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                    "traffic": TRAFFIC.get(self.args.workload), "kernel": "ctc_greedy_kernel (argmax + collapse, one launch)",
+                    "avg_launch_us": avg_ms * 1e3, "launches_timed": n_launch, "bytes_per_launch": bytes_per_launch,
+                    "bytes_per_frame": self.V * 4, "peak_source": peaks["src"] + ", copy bandwidth"}
+        rows = B * (self.K if cfg.mode == "mbs" else 1)
+        frames_per_launch = (self.Tc if cfg.mode == "greedy_online" else T) if fused_loop else 1
+        flop = 2.0 * rows * self.J * self.V * frames_per_launch
+        tf = flop / (avg_ms * 1e-3) / 1e12 if n_launch else 0.0
+        kern = {"mbs": "cluster_beam_kernel" if self.V <= 1024 else "joiner_topk_kernel<MEGA>", "greedy_single": "cluster_beam_kernel<1>",
+                "greedy_online": "joiner_topk_kernel<1, MEGA> (one launch per 8-frame chunk)"}[cfg.mode]
+        return {"bound": "tensor", "achieved": tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["tf_sustained"],
+                "traffic": TRAFFIC.get(self.args.workload) if fused_loop else None,
+                "kernel": kern + ": whole time loop (tcgen05 joiner + log-softmax / top-k + merge)" if fused_loop else
+                          "joiner GEMM (+log-softmax / top-k epilogue), one launch per frame",
+                "avg_launch_us": avg_ms * 1e3, "launches_timed": n_launch, "flop_per_launch": flop,
+                "flop_per_hyp_frame": 2.0 * self.J * self.V, "peak_source": peaks["src"] + ", sustained bf16",
+                "frame_step_roofline_us": 2.0 * rows * self.J * self.V / (peaks["tf_sustained"] * 1e12) * 1e6,
+                "frame_step_us": ms_step * 1e3 / T,
+                "whole_step_frac": (2.0 * rows * self.J * self.V * T / (peaks["tf_sustained"] * 1e12)) / (ms_step * 1e-3)}
+
+
 def run_ours(args, cfg):
     import torch
     import torch.distributed as dist
     from k2transducerasr_b200 import _native, build
-    from k2transducerasr_b200 import dist as kd
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -207,39 +388,49 @@ def run_ours(args, cfg):
     build.build()
 
     d = cfg.dims
-    B, T, K, V, J, E = cfg.streams, cfg.frames, cfg.beam, d.vocab_size, d.joiner_dim, d.encoder_dim
+    B = cfg.streams if args.streams <= 0 else args.streams
+    if args.scaling == "strong":
+        B = max(1, B // world)
     prec = _native.PREC_NAMES[args.precision]
-    h = _native.Handle(vocab_size=V, joiner_dim=J, decoder_dim=d.decoder_dim, encoder_dim=E, device=local_rank,
-                       max_streams=B, max_frames=T, max_beam=K)
-    h.load_weights(synth.make_weights(d, blank_bias=cfg.blank_bias))
-    if prec != _native.PREC_FP32:
-        h.set_precision(prec)
+    h = _native.Handle(vocab_size=d.vocab_size, joiner_dim=d.joiner_dim, decoder_dim=d.decoder_dim, encoder_dim=d.encoder_dim,
+                       device=local_rank, max_streams=B, max_frames=cfg.frames * cfg.chunks, max_beam=cfg.beam)
+    t_load = time.perf_counter()
+    if cfg.mode != "ctc":
+        h.load_weights(synth.make_weights(d, blank_bias=cfg.blank_bias))
+        if prec != _native.PREC_FP32:
+            h.set_precision(prec)
     # a real (non-legacy) stream shared by torch's events and the library's launches: the legacy default stream has
     # handle 0, which k2b_set_stream reads as "use the handle's own stream" and torch events would then see nothing
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     h.set_stream(stream.cuda_stream)
+    wk = Work(args, cfg, h, torch, dev, rank, B)
+    T = wk.T
 
-    # two distinct batches per rank, alternated, each 196 MB > the 126 MB L2
-    nbuf = 2
-    host_in = [torch.from_numpy(synth.make_frames(B, T, E, cfg.seed + 17 * rank + i)).pin_memory() for i in range(nbuf)]
-    dev_in = [x.to(dev) for x in host_in]
-    cap = T
-    d_tok = torch.zeros((B, cap), dtype=torch.int64, device=dev)
-    d_ts = torch.zeros((B, cap), dtype=torch.int32, device=dev)
-    d_n = torch.zeros((B,), dtype=torch.int32, device=dev)
-    d_sc = torch.zeros((B,), dtype=torch.float32, device=dev)
-    p_tok = torch.zeros((B, cap), dtype=torch.int64).pin_memory()
-    p_ts = torch.zeros((B, cap), dtype=torch.int32).pin_memory()
-    p_n = torch.zeros((B,), dtype=torch.int32).pin_memory()
-    p_sc = torch.zeros((B,), dtype=torch.float32).pin_memory()
+    # all ranks' results in one all-gather per step (device buffers, NVLink), when there is more than one rank
+    gather = None
+    if world > 1 and cfg.mode in ("mbs", "ctc", "greedy_single"):
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            buf = (ctypes.c_char * 128)()
+            assert _native.lib().k2b_nccl_unique_id(buf) == 0, "libnccl could not be loaded"
+            uid.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        uid_host = uid.cpu().numpy().tobytes()
+        h.call("k2b_nccl_init", ctypes.c_char_p(uid_host), rank, world)
+        a_tok = torch.zeros((world, B, wk.cap), dtype=torch.int64, device=dev); a_ts = torch.zeros((world, B, wk.cap), dtype=torch.int32, device=dev)
+        a_n = torch.zeros((world, B), dtype=torch.int32, device=dev); a_sc = torch.zeros((world, B), dtype=torch.float32, device=dev)
+        with_score = cfg.mode == "mbs"
+
+        def gather():
+            h.call("k2b_gather_results_nccl", wk.d_tok, wk.d_ts, wk.d_n, wk.d_sc if with_score else None, B, wk.cap,
+                   a_tok, a_ts, a_n, a_sc if with_score else None)
 
     def step_dev(i):
-        h.call("k2b_modified_beam_search_dev", dev_in[i % nbuf], 1, B, T, K, d_tok, d_ts, d_n, d_sc, cap)
-
-    def step_host(i):
-        h.call("k2b_modified_beam_search", host_in[i % nbuf], 1, B, T, K, p_tok, p_ts, p_n, p_sc, cap)
+        wk.step_dev(i)
+        if gather is not None:
+            gather()
 
     def barrier():
         if world > 1:
@@ -261,87 +452,142 @@ def run_ours(args, cfg):
             ms = float(t.item())
         return ms
 
+    def timed_wall(fn, steps):
+        """For calls that synchronise on the host inside (pageable copies): wall clock between two device-wide syncs, max over ranks."""
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            fn(i)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
     try:
         dev_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
     except Exception:
         dev_uuid = None
     clk = ClockSampler(local_rank, dev_uuid)
     clk.__enter__()                      # sampled from warm-up to the end of the e2e region: all of it is under load
-    for i in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for i in range(warm):
         step_dev(i)
     torch.cuda.synchronize()
+    load_ms = (time.perf_counter() - t_load) * 1e3          # weights + derived images + memoised decoder table + first calls
 
     h.reset_launch_count()
     ms = timed(step_dev, args.steps)
     launches = h.launch_count()
-    value = world * B * T * args.steps / (ms * 1e-3)
-
-    # gather of results for reporting (NCCL over NVLink) - once, outside `value`'s kernel loop but shown to work
+    value = world * wk.frames_per_step * args.steps / (ms * 1e-3)
+    last_batch = (args.steps - 1) % wk.nbuf
+    got = wk.results() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    bp = None
+    if got is not None and cfg.mode == "mbs":
+        bp = h.debug_backpointers(B, T, cfg.beam)
     gathered = None
-    if world > 1:
-        n = d_n.cpu().numpy()
-        toks = [d_tok[b, :n[b]].cpu().tolist() for b in range(min(B, 8))]
-        tss = [d_ts[b, :n[b]].cpu().tolist() for b in range(min(B, 8))]
-        allt, _, _ = kd.gather_results(toks, tss, d_sc[:len(toks)].cpu().tolist(), len(toks) * world, cap, device=dev)
-        gathered = len(allt)
+    if gather is not None:
+        torch.cuda.synchronize()
+        ok = bool(torch.equal(a_n[rank], wk.d_n[0]) and torch.equal(a_tok[rank], wk.d_tok[0]))
+        gathered = {"streams": world * B, "own_shard_intact": ok, "bytes_per_rank": int(B * wk.cap * 12 + B * 8)}
 
-    # e2e through the host-pointer entry point (pinned host buffers; H2D + D2H inside the timed region)
-    for i in range(2):
-        step_host(i)
+    # ---- end to end through the host-pointer entry points ----------------------------------------------------------------------
+    frames = world * wk.frames_per_step
     e2e_steps = max(2, min(args.steps, 10))
-    ms_e2e = timed(step_host, e2e_steps)
-    e2e_value = world * B * T * e2e_steps / (ms_e2e * 1e-3)
-    h2d = B * T * E * 4
-    d2h = B * cap * 8 + B * cap * 4 + B * 4 + B * 4
+    for i in range(2):
+        wk.step_host(i)
+    ms_e2e = timed(wk.step_host, e2e_steps)
+    e2e = {"value": frames * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": wk.h2d, "d2h_bytes_per_step": wk.d2h,
+           "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps, "host_memory": "page-locked"}
+    extra = {}
+    if not args.quick:
+        # (a) the bare copy of the same input bytes, all ranks at once: the ceiling any e2e number lives under
+        def h2d_only(i):
+            src = wk.host_in[i % wk.nbuf]
+            wk.dev_in[i % wk.nbuf].copy_(src, non_blocking=True)
+        h2d_only(0)
+        ms_c = timed(h2d_only, e2e_steps)
+        gbs = wk.B * T * wk.width * 4 * e2e_steps / (ms_c * 1e-3) / 1e9
+        extra["h2d_ceiling"] = {"gb_per_s_per_rank": gbs, "gb_per_s_all_ranks": gbs * world, "ms_per_step": ms_c / e2e_steps,
+                                "frames_per_s": frames * e2e_steps / (ms_c * 1e-3),
+                                "what": "cudaMemcpyAsync of one step's input from page-locked memory, every rank at once"}
+        # (b) results of batch i leave while batch i+1 arrives (two result buffers in flight)
+        h.set_option("async_d2h", 1)
+        def step_async(i):
+            wk.step_host(i, out=wk.p_out[i % 2])
+        step_async(0); h.sync()
+        ms_a = timed(step_async, e2e_steps)
+        h.sync()
+        h.set_option("async_d2h", 0)
+        extra["e2e_async"] = {"value": frames * e2e_steps / (ms_a * 1e-3), "unit": UNIT, "ms_per_step": ms_a / e2e_steps,
+                              "what": "k2b_set_option(async_d2h): no host sync between consecutive batches, k2b_sync at the end"}
+        # (c) pageable input, as a plain managed array is
+        if cfg.mode != "greedy_online":
+            pg = [np.array(x, copy=True) for x in wk.np_in]
+            wk.step_host(0, src=pg)
+            ms_p = timed_wall(lambda i: wk.step_host(i, src=pg), max(2, e2e_steps // 2))
+            extra["e2e_pageable"] = {"value": frames * max(2, e2e_steps // 2) / (ms_p * 1e-3), "unit": UNIT,
+                                     "ms_per_step": ms_p / max(2, e2e_steps // 2), "host_memory": "pageable (wall clock)"}
+        # (d) the reference seam's payload: frames already projected by the encoder graph, [B,T,J] (ref OfflineProjOfTransducer.cs:83)
+        if cfg.mode == "mbs":
+            proj = [torch.from_numpy(h.encoder_proj(x)).pin_memory() for x in wk.np_in]
+            wk.step_host(0, src=proj, raw=0)
+            ms_j = timed(lambda i: wk.step_host(i, src=proj, raw=0), e2e_steps)
+            extra["e2e_projected"] = {"value": frames * e2e_steps / (ms_j * 1e-3), "unit": UNIT, "ms_per_step": ms_j / e2e_steps,
+                                      "h2d_bytes_per_step": wk.B * T * wk.J * 4,
+                                      "what": "enc_is_raw = 0: [B,T,J] projected frames in, as the reference's EncoderProj returns them"}
     clk.__exit__(None, None, None)
 
-    # dominant kernel: the joiner GEMM of every frame, bracketed with CUDA events on the launch stream
+    # ---- dominant kernel, bracketed with CUDA events on the launch stream ---------------------------------------------------
     h.profile_enable(True)
     prof_steps = max(1, min(args.steps, 3))
     for i in range(prof_steps):
-        step_dev(i)
+        wk.step_dev(i)
     torch.cuda.synchronize()
     n_l, tot_ms = h.profile_read()
     h.profile_enable(False)
     peaks = load_peaks()
-    fused_loop = prec != _native.PREC_FP32          # persistent cluster kernel: one launch runs all T frames
-    flops_per_launch = 2.0 * (B * K) * J * V * (T if fused_loop else 1)
-    avg_ms = tot_ms / max(n_l, 1)
-    achieved_tf = flops_per_launch / (avg_ms * 1e-3) / 1e12 if n_l else 0.0
-    # dram__bytes_read.sum + dram__bytes_write.sum of one cluster_beam_kernel launch on this workload, from the
-    # ncu --set full capture profiles/r01_cluster_beam_v8_full.ncu-rep (240.5 MB + 6.8 MB); none taken for the fp32 path
-    # cfg4 (persistent joiner_topk_kernel, whole time loop): profiles/r01_beam_mega_cfg4_T250_full.ncu-rep
-    traffic = {"cfg2": 247.2e6, "cfg4": CFG4_TRAFFIC}.get(args.workload) if fused_loop else None
-    kernel_name = ("cluster_beam_kernel: whole time loop (joiner tcgen05 GEMM + log-softmax/top-k + merge)" if args.workload == "cfg2"
-                   else "joiner_topk_kernel<MEGA>: whole time loop (persistent tcgen05 joiner with top-k epilogue + merge warps)")
-    roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved_tf / peaks["tf_sustained"], "traffic": traffic, "kernel": (kernel_name if fused_loop else "joiner GEMM (+log-softmax/top-k epilogue), one launch per frame"),
-                "avg_launch_us": avg_ms * 1e3, "launches_timed": n_l, "flop_per_launch": flops_per_launch,
-                "peak_source": peaks["src"] + ", sustained bf16",
-                "frame_step_roofline_us": 2.0 * (B * K) * J * V / (peaks["tf_sustained"] * 1e12) * 1e6,
-                "frame_step_us": ms * 1e3 / args.steps / T,
-                "whole_step_frac": (2.0 * (B * K) * J * V * T / (peaks["tf_sustained"] * 1e12)) / (ms * 1e-3 / args.steps)}
+    fused_loop = prec != _native.PREC_FP32 or cfg.mode == "ctc"
+    roofline = wk.roofline(n_l, tot_ms, ms / args.steps, peaks, fused_loop)
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = run_cpu_baseline(cfg, streams=cfg.streams, repeats=2)     # two full batches: ~10 s of CPU work
+    cpu, parity = None, None
+    if got is not None:
+        cpu, want = run_cpu_baseline(cfg, args.workload, wk.np_in[last_batch])
+        from oracle import parity as OP
+        n = len(want)
+        rep = OP.compare(got[0][:n], got[1][:n], want, T, got_score=None if got[2] is None else got[2][:n],
+                         bp=None if bp is None else bp[:n])
+        parity = rep.as_dict()
+        parity["checked"] = f"outputs of the last timed device-resident step, {n} of {B} streams x {T} frames, against oracle/k2_oracle.py"
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "bf16x3": "bf16x3", "bf16": "bf16"}[args.precision],
+        stats = {}
+        if cfg.mode != "ctc":
+            stats = {"load_ms": load_ms, "decoder_table_bytes": h.get_stat("decoder_table_bytes"),
+                     "decoder_table_build_ms": h.get_stat("decoder_table_build_ms")}
+        inb = wk.B * T * wk.width * 4
+        line = {"metric": METRICS[args.workload], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": args.scaling, "vs_baseline": None,
+                "dtype": "f32" if cfg.mode == "ctc" else {"fp32": "f32", "bf16x3": "bf16x3", "bf16": "bf16"}[args.precision],
                 "data": "synthetic",
-                "config": {"workload": cfg.name, "streams_per_gpu": B, "frames": T, "beam": K, "vocab": V, "joiner_dim": J,
-                           "encoder_dim": E, "precision": args.precision, "parallelism": f"dp{world} (independent batches)",
-                           "l2": f"inputs ({B * T * E * 4 / 1e6:.0f} MB/step, 2 alternating batches) larger than the 126 MB L2",
-                           "blank_bias": cfg.blank_bias, "regime": args.regime, "weights": "random-init, seed 7"},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
+                "config": {"workload": cfg.name, "streams_per_gpu": B, "frames": T, "beam": cfg.beam if cfg.mode == "mbs" else 1,
+                           "vocab": wk.V, "joiner_dim": wk.J, "encoder_dim": wk.E, "precision": args.precision,
+                           "parallelism": f"dp{world} (independent batches" + (", one all-gather of the results per step)" if gather else ")"),
+                           "l2": (f"inputs ({inb / 1e6:.0f} MB/step, 2 alternating batches) larger than the 126 MB L2" if inb > 126e6 else
+                                  f"inputs {inb / 1e6:.1f} MB/step, 2 alternating batches; weights + memoised decoder rows are L2 / HBM resident by design"),
+                           "blank_bias": cfg.blank_bias, "regime": args.regime, "weights": "random-init, seed 7", **stats},
+                "e2e": e2e, **extra,
                 "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if parity is not None:
+            line["parity"] = parity
         if gathered is not None:
-            line["gathered_streams"] = gathered
+            line["gathered"] = gathered
         print(json.dumps(line), flush=True)
     h.close()
     if world > 1:
@@ -354,16 +600,24 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default: the config's; cfg5: 128 = 1024 sharded over 8)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong: the config's batch is split over the ranks (cfg2: 256 streams -> 32 per GPU at 8 GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="skip the extra e2e legs (pageable / projected / async / copy ceiling)")
     ap.add_argument("--regime", default="speech", choices=["speech", "raw"],
                     help="speech: blank bias calibrated so that 70-80 %% of the frames are blank (default); raw: random-init joiner as is, "
                          "almost every frame emits (worst case for the decoder gather)")
     args = ap.parse_args()
+    import dataclasses
     cfg = synth.CONFIGS[args.workload]
+    if args.workload == "cfg5":
+        cfg = dataclasses.replace(cfg, streams=128)           # BASELINE.json: batch 1024 sharded over 8 GPUs = 128 per GPU
+    if args.workload in ("cfg1", "cfg3", "cfg5") and args.steps == 100 and "--steps" not in sys.argv:
+        args.steps = {"cfg1": 50, "cfg3": 20, "cfg5": 50}[args.workload]
     if args.regime == "raw":
-        import dataclasses
         cfg = dataclasses.replace(cfg, blank_bias=0.0)
     if args.impl == "reference":
         run_reference_arm(args, cfg)

@@ -68,6 +68,36 @@ namespace K2TransducerAsr.B200
         [DllImport(Lib)] public static extern int k2b_modified_beam_search_dev(IntPtr h, IntPtr enc, int enc_is_raw, int B, int T, int K,
             IntPtr tokens, IntPtr ts, IntPtr n_out, IntPtr score, int cap);
 
+        // round 2 of the ABI (K2B_ABI_VERSION 2)
+        [DllImport(Lib)] public static extern int k2b_set_option(IntPtr h, [MarshalAs(UnmanagedType.LPUTF8Str)] string name, int value);
+        [DllImport(Lib)] public static extern int k2b_get_stat(IntPtr h, [MarshalAs(UnmanagedType.LPUTF8Str)] string name, out double value);
+        // page-locked host buffers: a managed float[] is pageable (staged, synchronous copies); frames / results that should move
+        // at the PCIe rate live in memory from k2b_host_alloc (wrap it in a Span<float>) or in a pinned GCHandle registered here
+        [DllImport(Lib)] public static extern int k2b_host_alloc(out IntPtr p, long bytes);
+        [DllImport(Lib)] public static extern int k2b_host_free(IntPtr p);
+        [DllImport(Lib)] public static extern int k2b_host_register(IntPtr p, long bytes);
+        [DllImport(Lib)] public static extern int k2b_host_unregister(IntPtr p);
+        // pointer-typed overloads of the fused calls for such buffers
+        [DllImport(Lib, EntryPoint = "k2b_modified_beam_search")] public static extern int k2b_modified_beam_search_p(IntPtr h, IntPtr enc,
+            int enc_is_raw, int B, int T, int K, IntPtr tokens, IntPtr ts, IntPtr n_out, IntPtr score, int cap);
+        [DllImport(Lib, EntryPoint = "k2b_greedy_offline")] public static extern int k2b_greedy_offline_p(IntPtr h, IntPtr enc, int enc_is_raw,
+            int B, int T, int mode, IntPtr tokens, IntPtr ts, IntPtr n_out, int cap);
+        // streaming modified_beam_search: what decodingMethod / maxActivePaths of OnlineRecognizer (ref OnlineRecognizer.cs:18-19) select
+        [DllImport(Lib)] public static extern int k2b_beam_pool_create(IntPtr h, int max_streams, int K, int max_frames);
+        [DllImport(Lib)] public static extern int k2b_beam_pool_reset(IntPtr h, int slot, long[]? hyp);
+        [DllImport(Lib)] public static extern int k2b_modified_beam_search_online_chunk(IntPtr h, float[] enc, int enc_is_raw, int B, int Tc,
+            int[] slots, [Out] long[]? hyp_out, [Out] long[] tokens, [Out] int[] ts, [Out] int[] n_out, [Out] float[] score, int cap);
+        [DllImport(Lib)] public static extern int k2b_modified_beam_search_online_chunk_dev(IntPtr h, IntPtr enc, int enc_is_raw, int B, int Tc,
+            int[] slots, IntPtr hyp_out, IntPtr tokens, IntPtr ts, IntPtr n_out, IntPtr score, int cap);
+        [DllImport(Lib)] public static extern int k2b_ctc_greedy_dev(IntPtr h, IntPtr logp, int B, int T, int V, int blank, IntPtr frame_offset,
+            IntPtr prev_inout, IntPtr tokens, IntPtr ts, IntPtr n_out, IntPtr trailing_blank_inout, int cap);
+        // multi-GPU reporting: one all-gather of the ranks' results (libnccl is loaded on first use)
+        [DllImport(Lib)] public static extern int k2b_nccl_unique_id([Out] byte[] id128);
+        [DllImport(Lib)] public static extern int k2b_nccl_init(IntPtr h, byte[] id128, int rank, int nranks);
+        [DllImport(Lib)] public static extern int k2b_gather_results_nccl(IntPtr h, IntPtr tokens, IntPtr ts, IntPtr n, IntPtr score, int B, int cap,
+            IntPtr all_tokens, IntPtr all_ts, IntPtr all_n, IntPtr all_score);
+        [DllImport(Lib)] public static extern int k2b_debug_backpointers(IntPtr h, [Out] int[] outp, int B, int T, int K);
+
         internal static void Check(IntPtr h, int status, string what)
         {
             if (status == K2B_OK) return;

@@ -66,12 +66,4 @@ namespace K2TransducerAsr.B200
         }
         ~OfflineProjOfB200() { if (_h != IntPtr.Zero) NativeMethods.k2b_destroy(_h); }
     }
-
-    /// Weights extracted once from decoder.onnx / joiner.onnx initialisers (row-major fp32, layouts in k2b200.h).
-    internal class B200Weights
-    {
-        public int DecoderDim, EncoderDim;
-        public float[] Emb = null!, ConvW = null!, DecProjW = null!, DecProjB = null!, OutW = null!, OutB = null!;
-        public float[]? EncProjW, EncProjB;
-    }
 }

@@ -105,25 +105,38 @@ ctc_greedy_kernel(const float* __restrict__ logp, int B, int T, int V, int blank
   int carry = prev_inout != nullptr ? (int)prev_inout[b] : -1;
   int base = 0, last_nonblank = -1;
   const int32_t* yb = ybuf + (size_t)b * T;
-  for (int c0 = 0; c0 < T; c0 += 32) {
-    const int t = c0 + lane;
-    const bool in = t < T;
-    const int y = in ? __ldcg(yb + t) : blank;
-    int p = __shfl_up_sync(0xffffffffu, y, 1);
-    if (lane == 0) p = carry;
-    const bool emit = in && y != blank && y != p;
-    const unsigned em = __ballot_sync(0xffffffffu, emit);
-    const unsigned nb = __ballot_sync(0xffffffffu, in && y != blank);
-    if (emit) {
-      const int pos = base + __popc(em & ((1u << lane) - 1u));
-      if (pos < cap) {
-        tokens[(size_t)b * cap + pos] = y;
-        ts[(size_t)b * cap + pos] = t + off;
-      }
+  // The collapse is a serial tail behind the last segment of every stream: its loads (one L2 round trip each) are issued eight
+  // 32-frame groups at a time, so a 250-frame utterance pays ONE round trip instead of eight dependent ones.
+  for (int g0 = 0; g0 < T; g0 += 256) {
+    int ys[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int t = g0 + 32 * u + lane;
+      ys[u] = t < T ? __ldcg(yb + t) : blank;
     }
-    base += __popc(em);
-    if (nb) last_nonblank = c0 + 31 - __clz(nb);
-    carry = __shfl_sync(0xffffffffu, y, min(31, T - 1 - c0));
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c0 = g0 + 32 * u;
+      if (c0 >= T) break;                          // warp-uniform
+      const int t = c0 + lane;
+      const bool in = t < T;
+      const int y = ys[u];
+      int p = __shfl_up_sync(0xffffffffu, y, 1);
+      if (lane == 0) p = carry;
+      const bool emit = in && y != blank && y != p;
+      const unsigned em = __ballot_sync(0xffffffffu, emit);
+      const unsigned nb = __ballot_sync(0xffffffffu, in && y != blank);
+      if (emit) {
+        const int pos = base + __popc(em & ((1u << lane) - 1u));
+        if (pos < cap) {
+          tokens[(size_t)b * cap + pos] = y;
+          ts[(size_t)b * cap + pos] = t + off;
+        }
+      }
+      base += __popc(em);
+      if (nb) last_nonblank = c0 + 31 - __clz(nb);
+      carry = __shfl_sync(0xffffffffu, y, min(31, T - 1 - c0));
+    }
   }
   if (lane == 0) {
     n_out[b] = base;
@@ -156,8 +169,10 @@ int32_t ctc_greedy_dev(k2b_handle* h, const float* logp, int B, int T, int V, in
   const int nseg = (T + kSeg - 1) / kSeg;
   const long long nblk = (long long)B * nseg;
   if (nblk > 0x7fffffffLL) return fail(h, K2B_ERR_INVALID, "ctc_greedy: B*ceil(T/32) exceeds the grid limit");
+  prof_begin(h);
   ctc_greedy_kernel<<<(unsigned)nblk, kWarps * 32, 0, h->stream>>>(logp, B, T, V, blank, nseg, frame_offset, prev_inout,
                                                                   tokens, ts, n_out, trailing_inout, cap, ybuf, ticket);
+  prof_end(h);
   K2B_LAUNCH_CHECK(h);
   return K2B_OK;
 }

@@ -212,6 +212,8 @@ class StreamResult:
     history: Optional[List[List[tuple]]] = None   # mbs: per frame, the surviving hypotheses in insertion order as
                                                   # (parent slot in the previous frame's list, appended token or -1)
     final_gap: float = float("inf")               # mbs: margin of the final length-normalised pick
+    frame_scale: List[float] = field(default_factory=list)   # mbs: |best hypothesis score| of every frame - the float32 spacing
+                                                             # at that magnitude bounds what ANY fp32 implementation can resolve
 
 
 # --------------------------------------------------------------------------------------------
@@ -424,6 +426,7 @@ def modified_beam_search(m: Model, enc: np.ndarray, beam: int = 4, init: Optiona
     foff = [0] * B if frame_offset is None else [int(x) for x in frame_offset]
     gap = np.full(B, np.inf, np.float64)
     fgap = np.full((B, T), np.inf, np.float64)
+    fscale = np.zeros((B, T), np.float64)
     history: List[List[List[tuple]]] = [[] for _ in range(B)]
     for t in range(T):
         counts = [len(h) for h in hyps]
@@ -448,6 +451,7 @@ def modified_beam_search(m: Model, enc: np.ndarray, beam: int = 4, init: Optiona
             # decision margins: the beam boundary AND the order inside the beam (it decides which
             # of two colliding hypotheses is inserted first and so keeps its timestamps)
             head = flat[order[:min(k + 1, flat.size)]].astype(np.float64)
+            fscale[b, t] = abs(float(head[0])) if head.size else 0.0
             if head.size > 1:
                 fgap[b, t] = float(np.min(head[:-1] - head[1:]))
                 gap[b] = min(gap[b], fgap[b, t])
@@ -488,7 +492,7 @@ def modified_beam_search(m: Model, enc: np.ndarray, beam: int = 4, init: Optiona
         h = hyps[b][bi]
         out.append(StreamResult(tokens=h.ys, timestamps=h.ts, appended=h.ys[m.context_size:], score=float(h.lp),
                                 min_gap=float(gap[b]), hyp=h.ys[-m.context_size:], frame_gap=[float(g) for g in fgap[b]],
-                                history=history[b], final_gap=fin))
+                                history=history[b], final_gap=fin, frame_scale=[float(x) for x in fscale[b]]))
     return (out, hyps) if return_state else out
 
 

@@ -42,7 +42,10 @@ def compare_streams(got_tokens, got_ts, want, what="", allow_frac=0.05, scores=N
     streams. `scores`: hypothesis log-probs of the identical streams must agree within SCORE_TOL."""
     rep = parity_report(got_tokens, got_ts, want, scores=scores, bp=bp, coupled=coupled, T=T)
     rep.assert_ok(what, min_frames_pct=min_frames_pct, score_tol=score_tol)
-    excused = sorted({b for b, _, _ in rep.near_tie_frames} | set(rep.cascade_streams))
+    # assert_ok has established that every divergence sits on a near tie (or below fp32 resolution); what is bounded here is how
+    # many streams end up with a different OUTPUT because of one (a beam that differs at a tie and still yields the same result
+    # is reported, not counted)
+    excused = sorted(rep.output_differs)
     assert len(excused) <= max(1, int(allow_frac * len(want))), \
-        f"{what}: too many near-tie streams: {rep.near_tie_frames[:10]} (+ cascades {rep.cascade_streams[:10]})"
+        f"{what}: too many streams differ at near ties: {rep.near_tie_frames[:10]} {rep.resolution_ties[:10]} (+ cascades {rep.cascade_streams[:10]})"
     return excused
