@@ -10,7 +10,8 @@ ends with ONE all-gather of all ranks' results over NVLink (k2b_gather_results_n
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg1|cfg2|cfg3|cfg4|cfg5]
     torchrun ... bench.py --gpus N ...      (one rank per GPU)
 
-`value`   : frames/s with the batch already resident in HBM (device-pointer entry points).
+`value`   : frames/s with the batch already resident in HBM (device-pointer entry points), the D2H of every step's results included
+            (SURVEY.md section 8d's definition of the metric).
 `e2e`     : the same metric through the host-pointer C-ABI call a P/Invoke shim makes, from page-locked host memory, H2D and D2H
             copies inside the timed region. Beside it (extra keys, same unit): `e2e_pageable` (what a plain managed array costs),
             `e2e_projected` (the reference seam's own payload, already projected [B,T,J] frames), `e2e_async` (results of batch i
@@ -331,6 +332,13 @@ class Work:
             for c, xc in enumerate(chunks):
                 h.call("k2b_greedy_online_chunk", xc, raw, B, self.Tc, self.p_hyp, tok[c], ts[c], n[c], self.cap)
 
+    def results_to_host(self):
+        """Asynchronous D2H of the step's results into page-locked buffers, on the launch stream."""
+        tok, ts, n, sc = self.p_out[1]
+        tok.copy_(self.d_tok, non_blocking=True); ts.copy_(self.d_ts, non_blocking=True); n.copy_(self.d_n, non_blocking=True)
+        if self.cfg.mode == "mbs":
+            sc.copy_(self.d_sc, non_blocking=True)
+
     def results(self):
         """(tokens, timestamps, scores) of the last device-resident step, as Python lists (timestamps utterance-absolute)."""
         n = self.d_n.cpu().numpy(); tok = self.d_tok.cpu().numpy(); ts = self.d_ts.cpu().numpy()
@@ -431,6 +439,7 @@ def run_ours(args, cfg):
         wk.step_dev(i)
         if gather is not None:
             gather()
+        wk.results_to_host()          # frames resident on the device, the D2H of the results inside the timed call
 
     def barrier():
         if world > 1:

@@ -170,10 +170,11 @@ int32_t beam_cluster_path(k2b_handle* h, const float* enc, int enc_is_raw, int B
 // Host-pointer modified_beam_search with the input copy hidden behind the search: the batch is cut into time chunks;
 // chunk c+1 crosses PCIe (strided 2-D copy into a compact [B,Tc,E] staging buffer, on a copy stream) while chunk c is
 // projected and decoded (one cluster-kernel launch per chunk, hypothesis state carried through global memory).
-int32_t beam_cluster_pipelined(k2b_handle* h, const float* enc_host, int B, int T, int K, int64_t* tokens, int32_t* ts,
+int32_t beam_cluster_pipelined(k2b_handle* h, const float* enc_host, int enc_is_raw, int B, int T, int K, int64_t* tokens, int32_t* ts,
                                int32_t* n_out, float* score, int cap) {
   K2B_TRY(ensure_cluster_assets(h));
-  const int E = h->cfg.encoder_dim, J = h->cfg.joiner_dim;
+  const int J = h->cfg.joiner_dim;
+  const int E = enc_is_raw ? h->cfg.encoder_dim : J;      // width of what crosses PCIe: raw frames, or the seam's projected ones
   // up to 10 chunks of at least 8 frames: measured on cfg2 (PCIe-bound, 196 MB in) 4 chunks 4.04 ms, 8 chunks 3.85 ms, 12 chunks
   // 3.81 ms per batch - the un-overlapped tail (last chunk's projection + search) shrinks, each extra launch costs ~30 us
   int nchunk = T / 8 < 10 ? (T / 8 > 0 ? T / 8 : 1) : 10;
@@ -209,11 +210,12 @@ int32_t beam_cluster_pipelined(k2b_handle* h, const float* enc_host, int B, int 
     const int tc = (T - t0) < Tc ? (T - t0) : Tc, sb = c & 1;
     float* stage = reinterpret_cast<float*>(static_cast<char*>(h->ws_in.p) + (size_t)sb * buf_bytes);
     K2B_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_free[sb], 0));
-    K2B_CUDA(h, cudaMemcpy2DAsync(stage, sizeof(float) * (size_t)tc * E, enc_host + (size_t)t0 * E, sizeof(float) * (size_t)T * E,
-                                  sizeof(float) * (size_t)tc * E, (size_t)B, cudaMemcpyHostToDevice, h->copy_stream));
+    K2B_TRY(h2d_rows(h, stage, sizeof(float) * (size_t)tc * E, enc_host + (size_t)t0 * E, sizeof(float) * (size_t)T * E,
+                     sizeof(float) * (size_t)tc * E, (size_t)B, h->copy_stream));
     K2B_CUDA(h, cudaEventRecord(h->ev_ready[sb], h->copy_stream));
     K2B_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_ready[sb], 0));
-    K2B_TRY(encoder_proj_tc(h, stage, B * tc, encE, true, tc, T, t0));
+    if (enc_is_raw) K2B_TRY(encoder_proj_tc(h, stage, B * tc, encE, true, tc, T, t0));
+    else K2B_TRY(exp2x_frames_chunk(h, stage, encE, B, tc, T, t0));
     K2B_CUDA(h, cudaEventRecord(h->ev_free[sb], h->stream));
     K2B_TRY(beam_cluster_dev(h, encE, B, tc, K, bp, fin_lp, fin_len, fin_nlive, -1, nullptr, nullptr, t0, T, c > 0 ? 1 : 0, io_ctx, io_hash));
   }
@@ -237,9 +239,9 @@ static int32_t encoder_proj_chunk(k2b_handle* h, const float* stage, int B, int 
 
 // The same for the engines of beam_dev that can be stepped in time chunks (persistent beam kernel: large vocabularies): chunk c+1
 // crosses PCIe while chunk c is projected and searched; the hypothesis state stays in the workspaces between the chunks.
-int32_t beam_chunked_host(k2b_handle* h, const float* enc_host, int B, int T, int K, int64_t* tokens, int32_t* ts, int32_t* n_out,
-                          float* score, int cap) {
-  const int E = h->cfg.encoder_dim, J = h->cfg.joiner_dim;
+int32_t beam_chunked_host(k2b_handle* h, const float* enc_host, int enc_is_raw, int B, int T, int K, int64_t* tokens, int32_t* ts,
+                          int32_t* n_out, float* score, int cap) {
+  const int J = h->cfg.joiner_dim, E = enc_is_raw ? h->cfg.encoder_dim : J;
   // each chunk is one persistent launch (~20 us of set-up); measured on cfg4 (131 MB in): 3 chunks 6.06 ms, 5 chunks 5.82 ms,
   // 8 chunks 5.64 ms, 12 chunks 5.67 ms per batch
   int nchunk = T / 30 < 8 ? (T / 30 > 0 ? T / 30 : 1) : 8;
@@ -253,7 +255,7 @@ int32_t beam_chunked_host(k2b_handle* h, const float* enc_host, int B, int T, in
     }
   }
   const size_t buf_bytes = ((sizeof(float) * (size_t)B * Tc * E) + 255) & ~size_t(255);
-  K2B_TRY(ensure(h, h->ws_in, 2 * buf_bytes));
+  if (enc_is_raw) K2B_TRY(ensure(h, h->ws_in, 2 * buf_bytes));
   K2B_TRY(ensure(h, h->ws_encproj, sizeof(float) * (size_t)B * T * J));
   float* encP = static_cast<float*>(h->ws_encproj.p);
   K2B_CUDA(h, cudaEventRecord(h->ev_free[0], h->stream));
@@ -261,13 +263,22 @@ int32_t beam_chunked_host(k2b_handle* h, const float* enc_host, int B, int T, in
   int c = 0;
   for (int t0 = 0; t0 < T; t0 += Tc, ++c) {
     const int tc = (T - t0) < Tc ? (T - t0) : Tc, sb = c & 1;
-    float* stage = reinterpret_cast<float*>(static_cast<char*>(h->ws_in.p) + (size_t)sb * buf_bytes);
     K2B_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_free[sb], 0));
-    K2B_CUDA(h, cudaMemcpy2DAsync(stage, sizeof(float) * (size_t)tc * E, enc_host + (size_t)t0 * E, sizeof(float) * (size_t)T * E,
-                                  sizeof(float) * (size_t)tc * E, (size_t)B, cudaMemcpyHostToDevice, h->copy_stream));
-    K2B_CUDA(h, cudaEventRecord(h->ev_ready[sb], h->copy_stream));
-    K2B_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_ready[sb], 0));
-    K2B_TRY(encoder_proj_chunk(h, stage, B, tc, encP, T, t0));
+    if (enc_is_raw) {
+      float* stage = reinterpret_cast<float*>(static_cast<char*>(h->ws_in.p) + (size_t)sb * buf_bytes);
+      K2B_TRY(h2d_rows(h, stage, sizeof(float) * (size_t)tc * E, enc_host + (size_t)t0 * E, sizeof(float) * (size_t)T * E,
+                       sizeof(float) * (size_t)tc * E, (size_t)B, h->copy_stream));
+      K2B_CUDA(h, cudaEventRecord(h->ev_ready[sb], h->copy_stream));
+      K2B_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_ready[sb], 0));
+      K2B_TRY(encoder_proj_chunk(h, stage, B, tc, encP, T, t0));
+    } else {
+      // the seam's own payload, already projected: the chunk's columns go straight to their place in [B,T,J] (no staging buffer; the
+      // array as a whole is free once the work recorded in ev_free has finished)
+      K2B_TRY(h2d_rows(h, encP + (size_t)t0 * J, sizeof(float) * (size_t)T * J, enc_host + (size_t)t0 * J, sizeof(float) * (size_t)T * J,
+                       sizeof(float) * (size_t)tc * J, (size_t)B, h->copy_stream));
+      K2B_CUDA(h, cudaEventRecord(h->ev_ready[sb], h->copy_stream));
+      K2B_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_ready[sb], 0));
+    }
     K2B_CUDA(h, cudaEventRecord(h->ev_free[sb], h->stream));
     K2B_TRY(beam_dev(h, encP + (size_t)t0 * J, B, tc, K, tokens, ts, n_out, score, cap, -1, nullptr, false, t0, T));
   }
@@ -440,6 +451,7 @@ int32_t k2b_destroy(k2b_handle* h) {
   state_pool_free(h);
   beam_pool_free(h);
   nccl_free(h);
+  host_stage_free(h);
   if (h->lens_dev) cudaFree(h->lens_dev);
   if (h->cluster_timing) cudaFree(h->cluster_timing);
   if (h->timeline) cudaFree(h->timeline);
@@ -898,7 +910,7 @@ int32_t k2b_greedy_offline(k2b_handle* h, const float* enc, int32_t enc_is_raw, 
   K2B_TRY(ensure(h, h->ws_in, in_bytes > 0 ? in_bytes : 4));
   OutStage o;
   K2B_TRY(stage_out(h, B, cap > 0 ? cap : 1, &o));
-  if (in_bytes) K2B_CUDA(h, cudaMemcpyAsync(h->ws_in.p, enc, in_bytes, cudaMemcpyHostToDevice, h->stream));
+  if (in_bytes) K2B_TRY(h2d_rows(h, h->ws_in.p, in_bytes, enc, in_bytes, in_bytes, 1, h->stream));
   K2B_TRY(k2b_greedy_offline_dev(h, static_cast<const float*>(h->ws_in.p), enc_is_raw, B, T, mode, o.tokens, o.ts, o.n, cap));
   if (cap > 0) {
     K2B_CUDA(h, cudaMemcpyAsync(tokens, o.tokens, sizeof(int64_t) * (size_t)B * cap, cudaMemcpyDeviceToHost, h->stream));
@@ -942,7 +954,7 @@ int32_t k2b_greedy_online_chunk(k2b_handle* h, const float* enc, int32_t enc_is_
   K2B_TRY(ensure(h, h->ws_in, in_bytes > 0 ? in_bytes : 4));
   OutStage o;
   K2B_TRY(stage_out(h, B, cap > 0 ? cap : 1, &o));
-  if (in_bytes) K2B_CUDA(h, cudaMemcpyAsync(h->ws_in.p, enc, in_bytes, cudaMemcpyHostToDevice, h->stream));
+  if (in_bytes) K2B_TRY(h2d_rows(h, h->ws_in.p, in_bytes, enc, in_bytes, in_bytes, 1, h->stream));
   K2B_CUDA(h, cudaMemcpyAsync(o.hyp, hyp_inout, sizeof(int64_t) * 2 * (size_t)B, cudaMemcpyHostToDevice, h->stream));
   K2B_TRY(k2b_greedy_online_chunk_dev(h, static_cast<const float*>(h->ws_in.p), enc_is_raw, B, Tc, o.hyp, o.tokens, o.ts, o.n, cap));
   if (cap > 0) {
@@ -986,17 +998,17 @@ int32_t k2b_modified_beam_search(k2b_handle* h, const float* enc, int32_t enc_is
   OutStage o;
   K2B_TRY(stage_out(h, B, cap > 0 ? cap : 1, &o));
   if (K < 1 || K > kMaxBeam) return fail(h, K2B_ERR_INVALID, "k2b_modified_beam_search: beam must be in 1..8");
-  const bool pipelined = enc_is_raw && h->cfg.precision != K2B_PREC_FP32 && cluster_path_supported(h, K) && encproj_tc_supported(h) &&
-                         T >= 32 && !h->profile_on && K <= h->cfg.vocab_size;
-  const bool chunked = !pipelined && enc_is_raw && h->cfg.precision != K2B_PREC_FP32 && !cluster_path_supported(h, K) &&
-                       T >= 64 && !h->profile_on && K <= h->cfg.vocab_size && h->cfg.encoder_dim > 0 && beam_chunkable(h, K);
+  const bool pipelined = h->cfg.precision != K2B_PREC_FP32 && cluster_path_supported(h, K) && (!enc_is_raw || encproj_tc_supported(h)) &&
+                         T >= 32 && !h->profile_on && K <= h->cfg.vocab_size && h->cfg.joiner_dim % 4 == 0;
+  const bool chunked = !pipelined && h->cfg.precision != K2B_PREC_FP32 && !cluster_path_supported(h, K) &&
+                       T >= 64 && !h->profile_on && K <= h->cfg.vocab_size && (!enc_is_raw || h->cfg.encoder_dim > 0) && beam_chunkable(h, K);
   if (pipelined) {
-    K2B_TRY(beam_cluster_pipelined(h, enc, B, T, K, o.tokens, o.ts, o.n, o.score, cap));
+    K2B_TRY(beam_cluster_pipelined(h, enc, enc_is_raw, B, T, K, o.tokens, o.ts, o.n, o.score, cap));
   } else if (chunked) {
-    K2B_TRY(beam_chunked_host(h, enc, B, T, K, o.tokens, o.ts, o.n, o.score, cap));
+    K2B_TRY(beam_chunked_host(h, enc, enc_is_raw, B, T, K, o.tokens, o.ts, o.n, o.score, cap));
   } else {
     K2B_TRY(ensure(h, h->ws_in, in_bytes > 0 ? in_bytes : 4));
-    if (in_bytes) K2B_CUDA(h, cudaMemcpyAsync(h->ws_in.p, enc, in_bytes, cudaMemcpyHostToDevice, h->stream));
+    if (in_bytes) K2B_TRY(h2d_rows(h, h->ws_in.p, in_bytes, enc, in_bytes, in_bytes, 1, h->stream));
     K2B_TRY(k2b_modified_beam_search_dev(h, static_cast<const float*>(h->ws_in.p), enc_is_raw, B, T, K, o.tokens, o.ts, o.n,
                                          o.score, cap));
   }
@@ -1095,7 +1107,7 @@ int32_t k2b_modified_beam_search_online_chunk(k2b_handle* h, const float* enc, i
   K2B_TRY(ensure(h, h->ws_in, in_bytes > 0 ? in_bytes : 4));
   OutStage o;
   K2B_TRY(stage_out(h, B, cap, &o));
-  if (in_bytes) K2B_CUDA(h, cudaMemcpyAsync(h->ws_in.p, enc, in_bytes, cudaMemcpyHostToDevice, h->stream));
+  if (in_bytes) K2B_TRY(h2d_rows(h, h->ws_in.p, in_bytes, enc, in_bytes, in_bytes, 1, h->stream));
   K2B_TRY(k2b_modified_beam_search_online_chunk_dev(h, static_cast<const float*>(h->ws_in.p), enc_is_raw, B, Tc, slots,
                                                     hyp_out ? o.hyp : nullptr, o.tokens, o.ts, o.n, o.score, cap));
   K2B_CUDA(h, cudaMemcpyAsync(tokens, o.tokens, sizeof(int64_t) * (size_t)B * cap, cudaMemcpyDeviceToHost, h->stream));
@@ -1138,7 +1150,7 @@ int32_t k2b_ctc_greedy(k2b_handle* h, const float* logp, int32_t B, int32_t T, i
   K2B_TRY(ensure(h, h->ws_in, in_bytes > 0 ? in_bytes : 4));
   OutStage o;
   K2B_TRY(stage_out(h, B, cap > 0 ? cap : 1, &o));
-  if (in_bytes) K2B_CUDA(h, cudaMemcpyAsync(h->ws_in.p, logp, in_bytes, cudaMemcpyHostToDevice, h->stream));
+  if (in_bytes) K2B_TRY(h2d_rows(h, h->ws_in.p, in_bytes, logp, in_bytes, in_bytes, 1, h->stream));
   if (frame_offset) K2B_CUDA(h, cudaMemcpyAsync(o.aux_a, frame_offset, sizeof(int32_t) * (size_t)B, cudaMemcpyHostToDevice, h->stream));
   if (trailing_blank_inout) K2B_CUDA(h, cudaMemcpyAsync(o.aux_b, trailing_blank_inout, sizeof(int32_t) * (size_t)B, cudaMemcpyHostToDevice, h->stream));
   if (prev_inout) K2B_CUDA(h, cudaMemcpyAsync(o.prev, prev_inout, sizeof(int64_t) * (size_t)B, cudaMemcpyHostToDevice, h->stream));

@@ -33,7 +33,7 @@ struct ProfEvents {
 
 }  // namespace k2b
 
-namespace k2b { struct StatePool; struct BeamPool; struct NcclState; }
+namespace k2b { struct StatePool; struct BeamPool; struct NcclState; struct HostStage; }
 
 struct k2b_handle {
   k2b_config cfg{};
@@ -110,6 +110,7 @@ struct k2b_handle {
   k2b::ProfEvents prof;
   k2b::BeamPool* beam_pool = nullptr;     // streaming modified_beam_search: per-stream hypotheses carried between chunks (stream_beam.cu)
   k2b::NcclState* nccl = nullptr;         // k2b_nccl_init / k2b_gather_results_nccl (nccl_gather.cu; libnccl is dlopen'ed)
+  k2b::HostStage* host_stage = nullptr;   // page-locked bounce buffers + copy threads for pageable inputs (host_stage.cu)
   int max_sym_per_frame = 1;              // k2b_set_option("max_sym_per_frame"): ref OfflineRecognizer.cs:19 fixes it to 1
   // engine switches (k2b_set_option; the K2B_* environment variables only give their initial values at k2b_create)
   int opt_pipe_chunks = 0;                // > 0: number of time chunks of the host-pointer beam search
@@ -235,6 +236,7 @@ int32_t ensure_dec_table(k2b_handle* h, bool* have);
 int32_t joinin_table_tc(k2b_handle* h, const int32_t* ctx, int M, const float* enc, long long enc_stride, int rows_per_stream,
                         uint8_t* x_img);
 int32_t exp2x_frames(k2b_handle* h, const float* in, float* out, size_t n);
+int32_t exp2x_frames_chunk(k2b_handle* h, const float* in, float* out, int B, int tc, int T, int t0);   // [B,tc,J] -> rows t0.. of [B,T,J]
 int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, int32_t* bp, float* fin_lp, int32_t* fin_len,
                          int32_t* fin_nlive, int extra_mask, const int64_t* hyp_in, int64_t* hyp_out, int t0 = 0, int Ttot = 0,
                          int resume = 0, int32_t* io_ctx = nullptr, unsigned long long* io_hash = nullptr, bool need_lp = true);
@@ -250,6 +252,10 @@ int32_t beam_pool_gather(k2b_handle* h, int B, const BeamStateView& dst);
 int32_t beam_pool_scatter(k2b_handle* h, int B, int Tc, const BeamStateView& src, const int32_t* bp_chunk);
 int32_t beam_pool_backtrace(k2b_handle* h, int B, int64_t* tokens, int32_t* ts, int32_t* n_out, float* score, int64_t* hyp_out, int cap);
 int beam_pool_K(const k2b_handle* h);
+
+// ---- host_stage.cu: H2D of `rows` rows of `width` bytes; pageable sources are staged by the library's own copy threads ----------
+int32_t h2d_rows(k2b_handle* h, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows, cudaStream_t stream);
+void host_stage_free(k2b_handle* h);
 
 // ---- nccl_gather.cu ------------------------------------------------------------------------------------------
 void nccl_free(k2b_handle* h);

@@ -758,6 +758,19 @@ __global__ void exp2x_kernel(const float* __restrict__ in, float* __restrict__ o
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = expf(2.f * fminf(fmaxf(in[i], -21.f), 21.f));
 }
+// time chunk [t0, t0 + tc) of every stream: in [B,tc,J] compact -> out [B,T,J]
+__global__ void exp2x_chunk_kernel(const float4* __restrict__ in, float4* __restrict__ out, int B, int tc, int T, int t0, int J4) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * tc * J4) return;
+  const int j = (int)(i % J4);
+  const size_t bt = i / J4;
+  const int t = (int)(bt % tc), b = (int)(bt / tc);
+  const float4 x = __ldg(in + i);
+  float4 y;
+  y.x = expf(2.f * fminf(fmaxf(x.x, -21.f), 21.f)); y.y = expf(2.f * fminf(fmaxf(x.y, -21.f), 21.f));
+  y.z = expf(2.f * fminf(fmaxf(x.z, -21.f), 21.f)); y.w = expf(2.f * fminf(fmaxf(x.w, -21.f), 21.f));
+  out[((size_t)b * T + t0 + t) * J4 + j] = y;
+}
 
 }  // namespace
 
@@ -906,6 +919,15 @@ int32_t ensure_cluster_assets(k2b_handle* h) {
   pack_out_w_kernel<<<(unsigned)rows, 128, 0, h->stream>>>(h->out_w, h->out_b, V, J, CS, h->wo_hi_img, h->wo_lo, h->bias_pad);
   K2B_LAUNCH_CHECK(h);
   h->tc_ready = true;
+  return K2B_OK;
+}
+
+int32_t exp2x_frames_chunk(k2b_handle* h, const float* in, float* out, int B, int tc, int T, int t0) {
+  const int J4 = h->cfg.joiner_dim / 4;
+  const size_t n = (size_t)B * tc * J4;
+  exp2x_chunk_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out),
+                                                                         B, tc, T, t0, J4);
+  K2B_LAUNCH_CHECK(h);
   return K2B_OK;
 }
 

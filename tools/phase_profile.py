@@ -16,6 +16,7 @@ if __name__ == "__main__":
         h = _native.Handle(vocab_size=d.vocab_size, joiner_dim=d.joiner_dim, decoder_dim=d.decoder_dim, encoder_dim=d.encoder_dim,
                            precision=_native.PREC_NAMES[prec])
         h.load_weights(synth.make_weights(d, blank_bias=cfg.blank_bias))
+        h.set_option("pipe_chunks", 1)      # one kernel launch for the whole utterance (the host call would cut it into time chunks)
         raw = synth.make_frames(cfg.streams, cfg.frames, d.encoder_dim, cfg.seed)
         enc = h.encoder_proj(raw)           # projected frames in -> the host call is not time-chunked: one kernel launch
         h.modified_beam_search(enc, 4, enc_is_raw=False)
