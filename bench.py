@@ -150,11 +150,14 @@ def all_host_threads():
         pass
 
 
-def oracle_model(cfg):
+def oracle_model(cfg, precision="bf16x3"):
+    """fp32 oracle; for --precision bf16 (single-pass bf16 operands, a stated-tolerance mode) the oracle restated with bf16-rounded
+    GEMM operands, so that the parity block still compares like with like."""
     from oracle import k2_oracle as O
     if cfg.mode == "ctc":
         return None
-    return O.Model.from_dict(synth.make_weights(cfg.dims, blank_bias=cfg.blank_bias))
+    kw = {"prec_joiner": "bf16", "prec_enc": "bf16"} if precision == "bf16" else {}
+    return O.Model.from_dict(synth.make_weights(cfg.dims, blank_bias=cfg.blank_bias), **kw)
 
 
 def oracle_step(cfg, model, inp):
@@ -195,12 +198,12 @@ def make_input(cfg, streams, seed):
 CPU_SAMPLE = {"cfg1": 1, "cfg2": 256, "cfg3": 512, "cfg4": 48, "cfg5": 128}     # streams: ~10-30 s of CPU work each
 
 
-def run_cpu_baseline(cfg, name, inp):
+def run_cpu_baseline(cfg, name, inp, precision="bf16x3"):
     """Times the oracle on the first CPU_SAMPLE[name] streams of `inp` (the batch the last timed GPU step decoded) and returns
     (cpu_baseline dict, oracle results) - the results feed the parity block."""
     all_host_threads()
     n = min(CPU_SAMPLE[name], inp.shape[0])
-    model = oracle_model(cfg)
+    model = oracle_model(cfg, precision)
     T = cfg.frames * cfg.chunks
     if cfg.mode != "greedy_online":
         oracle_step(cfg, model, inp[:1, :min(T, 16)])          # warm BLAS
@@ -564,13 +567,14 @@ def run_ours(args, cfg):
 
     cpu, parity = None, None
     if got is not None:
-        cpu, want = run_cpu_baseline(cfg, args.workload, wk.np_in[last_batch])
+        cpu, want = run_cpu_baseline(cfg, args.workload, wk.np_in[last_batch], args.precision)
         from oracle import parity as OP
         n = len(want)
         rep = OP.compare(got[0][:n], got[1][:n], want, T, got_score=None if got[2] is None else got[2][:n],
                          bp=None if bp is None else bp[:n])
         parity = rep.as_dict()
-        parity["checked"] = f"outputs of the last timed device-resident step, {n} of {B} streams x {T} frames, against oracle/k2_oracle.py"
+        parity["checked"] = (f"outputs of the last timed device-resident step, {n} of {B} streams x {T} frames, against oracle/k2_oracle.py"
+                             + (" restated with bf16-rounded GEMM operands" if args.precision == "bf16" else ""))
 
     if rank == 0:
         stats = {}

@@ -211,6 +211,17 @@ K2B_API int32_t k2b_modified_beam_search_online_chunk_dev(k2b_handle* h, const f
                                                           const int32_t* slots, int64_t* hyp_out, int64_t* tokens, int32_t* ts,
                                                           int32_t* n_out, float* score, int32_t cap);
 
+/* Contextual biasing (hot words) of modified_beam_search - SURVEY.md section 8f rank 4; the reference only holds a dead N-best
+ * substitution stub (ref Utils/HotwordsHelper.cs:8-57, no caller). The hot words are compiled on the host into a dense automaton
+ * over token ids (k2transducerasr_b200/hotwords.py, csharp: the same tables): HOST pointers next [S,V] int32, delta [S,V] float,
+ * residual [S] float; state 0 is the root. When a hypothesis in state s is extended by token y (after the top-K selection, as
+ * icefall does), delta[s,y] is added to its log-prob and it moves to next[s,y]; a match that breaks gives its boost back through a
+ * negative delta; when the utterance ends in state s, residual[s] (the boost of a match still in progress) is subtracted before
+ * the hypotheses are compared. Served by the cluster kernel (V <= 1024, beams 2 / 4 / 8, incl. the time-chunked and streaming
+ * calls, where the state travels with the hypothesis) and by the per-frame merge (fp32 precision, or option "unfused_step");
+ * other engines answer K2B_ERR_UNSUPPORTED while a graph is set. Greedy search is never biased. n_states == 0 clears it.      */
+K2B_API int32_t k2b_set_context_graph(k2b_handle* h, const int32_t* next, const float* delta, const float* residual, int32_t n_states);
+
 /* replaces: ForwardGreedySearchCTC / ForwardBatchGreedySearchCTC (ref OfflineRecognizer.cs:305-430)
  * and the online variant (ref OnlineRecognizer.cs:220-319). logp [B,T,V]; V is an argument because
  * the reference takes it from tokens.txt (ref :325). frame_offset [B] or NULL (= 0) is added to

@@ -72,6 +72,7 @@ _SIGS = {
     "k2b_host_free": (C.c_int32, [_P]),
     "k2b_host_register": (C.c_int32, [_P, C.c_int64]),
     "k2b_host_unregister": (C.c_int32, [_P]),
+    "k2b_set_context_graph": (C.c_int32, [_P, _P, _P, _P, _I]),
     "k2b_beam_pool_create": (C.c_int32, [_P, _I, _I, _I]),
     "k2b_beam_pool_reset": (C.c_int32, [_P, _I, _P]),
     "k2b_modified_beam_search_online_chunk": (C.c_int32, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I]),
@@ -341,6 +342,17 @@ class Handle:
             raise K2bError(K2B_ERR_INVALID, f"cap {cap} is too small for a hypothesis of {int(n.max())} symbols")
         toks, tss = self._unpack(tokens, ts, n)
         return toks, tss, score, hyp
+
+    def set_context_graph(self, graph=None):
+        """graph: hotwords.ContextGraph (dense automaton over token ids) or None to clear."""
+        if graph is None:
+            self._check(self._lib.k2b_set_context_graph(self._h, None, None, None, 0))
+            return
+        nxt = np.ascontiguousarray(graph.next, dtype=np.int32)
+        dlt = np.ascontiguousarray(graph.delta, dtype=np.float32)
+        res = np.ascontiguousarray(graph.residual, dtype=np.float32)
+        assert nxt.shape == dlt.shape == (res.size, self.V)
+        self._check(self._lib.k2b_set_context_graph(self._h, _ptr(nxt), _ptr(dlt), _ptr(res), int(res.size)))
 
     def debug_backpointers(self, B: int, T: int, K: int) -> np.ndarray:
         """[B,T,K] back-pointer history of the last beam search: entry = (parent slot << 28) | (token + 1)."""

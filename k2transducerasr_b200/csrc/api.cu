@@ -164,7 +164,7 @@ int32_t beam_cluster_path(k2b_handle* h, const float* enc, int enc_is_raw, int B
   int32_t* bp = static_cast<int32_t*>(h->ws_bp.p);
   K2B_TRY(beam_cluster_dev(h, encE, B, T, K, bp, fin_lp, fin_len, fin_nlive, extra_mask, hyp_inout, hyp_inout, 0, 0, 0, nullptr, nullptr,
                            need_lp));
-  return beam_backtrace_dev(h, B, K, T, fin_lp, fin_len, fin_nlive, bp, tokens, ts, n_out, score, cap);
+  return beam_backtrace_dev(h, B, K, T, fin_lp, fin_len, fin_nlive, bp, tokens, ts, n_out, score, cap, K > 1 ? cluster_cst(h, B, K) : nullptr);
 }
 
 // Host-pointer modified_beam_search with the input copy hidden behind the search: the batch is cut into time chunks;
@@ -219,7 +219,7 @@ int32_t beam_cluster_pipelined(k2b_handle* h, const float* enc_host, int enc_is_
     K2B_CUDA(h, cudaEventRecord(h->ev_free[sb], h->stream));
     K2B_TRY(beam_cluster_dev(h, encE, B, tc, K, bp, fin_lp, fin_len, fin_nlive, -1, nullptr, nullptr, t0, T, c > 0 ? 1 : 0, io_ctx, io_hash));
   }
-  return beam_backtrace_dev(h, B, K, T, fin_lp, fin_len, fin_nlive, bp, tokens, ts, n_out, score, cap);
+  return beam_backtrace_dev(h, B, K, T, fin_lp, fin_len, fin_nlive, bp, tokens, ts, n_out, score, cap, K > 1 ? cluster_cst(h, B, K) : nullptr);
 }
 
 // projected frames of time chunk [t0, t0 + tc) of every stream, written into a [B,T,J] array (tcgen05 GEMM, or the CUDA-core one
@@ -458,6 +458,10 @@ int32_t k2b_destroy(k2b_handle* h) {
   if (h->dev_status) cudaFree(h->dev_status);
   for (int i = 0; i < 2; ++i) { if (h->ev_ready[i]) cudaEventDestroy(h->ev_ready[i]); if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]); }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->cg_next) cudaFree(h->cg_next);
+  if (h->cg_delta) cudaFree(h->cg_delta);
+  if (h->cg_resid) cudaFree(h->cg_resid);
+  free_buf(h->ws_cst);
   DevBuf* bufs[] = {&h->ws_in, &h->ws_encproj, &h->ws_x, &h->ws_ximg, &h->ws_dec, &h->ws_logits, &h->ws_part, &h->ws_state, &h->ws_bp,
                     &h->ws_out, &h->ws_misc, &h->ws_ctc, &h->ws_sync};
   for (DevBuf* b : bufs) free_buf(*b);
@@ -1021,6 +1025,29 @@ int32_t k2b_modified_beam_search(k2b_handle* h, const float* enc, int32_t enc_is
   return finish_host_call(h);
 }
 
+// ---- contextual biasing (hot words) -----------------------------------------------------------------------------------
+int32_t k2b_set_context_graph(k2b_handle* h, const int32_t* next, const float* delta, const float* residual, int32_t n_states) {
+  K2B_TRY(enter(h));
+  K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->cg_next) cudaFree(h->cg_next);
+  if (h->cg_delta) cudaFree(h->cg_delta);
+  if (h->cg_resid) cudaFree(h->cg_resid);
+  h->cg_next = nullptr; h->cg_delta = nullptr; h->cg_resid = nullptr; h->cg_states = 0;
+  if (n_states <= 0 || next == nullptr) return K2B_OK;                       // cleared
+  if (delta == nullptr || residual == nullptr) return fail(h, K2B_ERR_INVALID, "k2b_set_context_graph: delta / residual is NULL");
+  const size_t V = h->cfg.vocab_size, n = (size_t)n_states * V;
+  for (size_t i = 0; i < n; ++i)
+    if (next[i] < 0 || next[i] >= n_states) return fail(h, K2B_ERR_INVALID, "k2b_set_context_graph: a transition leaves the automaton");
+  K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->cg_next), n * sizeof(int32_t)));
+  K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->cg_delta), n * sizeof(float)));
+  K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->cg_resid), (size_t)n_states * sizeof(float)));
+  K2B_CUDA(h, cudaMemcpy(h->cg_next, next, n * sizeof(int32_t), cudaMemcpyHostToDevice));
+  K2B_CUDA(h, cudaMemcpy(h->cg_delta, delta, n * sizeof(float), cudaMemcpyHostToDevice));
+  K2B_CUDA(h, cudaMemcpy(h->cg_resid, residual, (size_t)n_states * sizeof(float), cudaMemcpyHostToDevice));
+  h->cg_states = n_states;
+  return K2B_OK;
+}
+
 // ---- streaming modified_beam_search ---------------------------------------------------------------------------------
 int32_t k2b_beam_pool_create(k2b_handle* h, int32_t max_streams, int32_t K, int32_t max_frames) {
   K2B_TRY(enter(h));
@@ -1078,6 +1105,7 @@ int32_t k2b_modified_beam_search_online_chunk_dev(k2b_handle* h, const float* en
       v.nlive = reinterpret_cast<int32_t*>(p); p += ab;
       v.ctx = reinterpret_cast<int32_t*>(p); p += a8;
       v.hash = reinterpret_cast<unsigned long long*>(p);
+      v.cst = K > 1 ? cluster_cst(h, B, K) : nullptr;
       K2B_TRY(beam_pool_gather(h, B, v));
       K2B_TRY(beam_cluster_dev(h, encE, B, Tc, K, bp, v.lp, v.len, v.nlive, mask3, nullptr, nullptr, 0, Tc, 1, v.ctx, v.hash, true));
       K2B_TRY(beam_pool_scatter(h, B, Tc, v, bp));

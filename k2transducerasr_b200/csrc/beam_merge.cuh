@@ -14,6 +14,7 @@ struct BeamState {
   int32_t* len;    // [N]
   uint64_t* hash;  // [N]
   int32_t* nlive;  // [B]
+  int32_t* cst = nullptr;   // [N] context-graph (hot word) state; only the per-frame fp32 merge and the cluster kernel bias
 };
 
 constexpr uint64_t kHashSeed = 0x9E3779B97F4A7C15ull;

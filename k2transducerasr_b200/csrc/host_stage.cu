@@ -95,7 +95,8 @@ static int32_t ensure_stage(k2b_handle* h) {
     K2B_CUDA(h, cudaEventCreateWithFlags(&s->done[i], cudaEventDisableTiming));
   }
   unsigned hw = std::thread::hardware_concurrency();
-  int n = hw >= 16 ? 6 : (hw >= 8 ? 4 : (hw >= 4 ? 2 : 0));     // copy threads (memory bound: more does not help)
+  int n = (int)(hw / 4);                                        // copy threads: a quarter of the host's (several ranks share it)
+  n = n > 8 ? 8 : (n < 2 ? (hw >= 4 ? 2 : 0) : n);
   s->start(n);
   return K2B_OK;
 }

@@ -110,6 +110,12 @@ struct k2b_handle {
   k2b::ProfEvents prof;
   k2b::BeamPool* beam_pool = nullptr;     // streaming modified_beam_search: per-stream hypotheses carried between chunks (stream_beam.cu)
   k2b::NcclState* nccl = nullptr;         // k2b_nccl_init / k2b_gather_results_nccl (nccl_gather.cu; libnccl is dlopen'ed)
+  // contextual biasing (hot words) of modified_beam_search: a dense automaton over token ids (k2b_set_context_graph)
+  int32_t* cg_next = nullptr;             // [S,V] next state
+  float* cg_delta = nullptr;              // [S,V] score added on that transition
+  float* cg_resid = nullptr;              // [S]   unearned partial boost revoked when the utterance ends in state s
+  int cg_states = 0;
+  k2b::DevBuf ws_cst;                     // cluster engine: automaton state per hypothesis [B*K], carried between time chunks
   k2b::HostStage* host_stage = nullptr;   // page-locked bounce buffers + copy threads for pageable inputs (host_stage.cu)
   int max_sym_per_frame = 1;              // k2b_set_option("max_sym_per_frame"): ref OfflineRecognizer.cs:19 fixes it to 1
   // engine switches (k2b_set_option; the K2B_* environment variables only give their initial values at k2b_create)
@@ -218,7 +224,7 @@ int32_t greedy_dev(k2b_handle* h, const float* enc, int B, int T, int mode, bool
 int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* tokens, int32_t* ts,
                  int32_t* n_out, float* score, int cap, int extra_mask = -1, int64_t* hyp_inout = nullptr, bool greedy = false,
                  int t0 = 0, int Ttot = 0, bool carry = false, long long enc_stride = 0);
-struct BeamStateView { int32_t* ctx; float* lp; int32_t* len; unsigned long long* hash; int32_t* nlive; };
+struct BeamStateView { int32_t* ctx; float* lp; int32_t* len; unsigned long long* hash; int32_t* nlive; int32_t* cst = nullptr; };
 size_t beam_state_bytes(int B, int K);                                   // one of the two state buffers of beam_dev
 BeamStateView beam_state_view(k2b_handle* h, int B, int K, int which);   // inside ws_state (ensure 2 * beam_state_bytes first)
 // a search may be stepped in time chunks (enc = frame t0 of a [B,Ttot,J] array, T frames per call: the host-pointer entry point hides
@@ -227,7 +233,9 @@ bool beam_chunkable(k2b_handle* h, int K);
 bool beam_greedy_usable(k2b_handle* h);
 
 int32_t beam_backtrace_dev(k2b_handle* h, int B, int K, int T, const float* lp, const int32_t* len, const int32_t* nlive,
-                           const int32_t* bp, int64_t* tokens, int32_t* ts, int32_t* n_out, float* score, int cap);
+                           const int32_t* bp, int64_t* tokens, int32_t* ts, int32_t* n_out, float* score, int cap,
+                           const int32_t* cst = nullptr);
+int32_t* cluster_cst(k2b_handle* h, int B, int K);      // the cluster engine's automaton-state array (null without a context graph)
 
 // ---- search_cluster.cu -------------------------------------------------------------------------
 bool cluster_path_supported(const k2b_handle* h, int K);

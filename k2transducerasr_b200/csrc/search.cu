@@ -98,6 +98,7 @@ __global__ void beam_init_kernel(int B, int K, int blank, BeamState s0, BeamStat
   s0.lp[n] = slot == 0 ? 0.f : -INFINITY;
   s0.len[n] = 2;
   s0.hash[n] = kHashSeed;
+  if (s0.cst != nullptr) { s0.cst[n] = 0; s1.cst[n] = 0; }
   if (slot == 0) s0.nlive[n / K] = 1;
 }
 
@@ -114,7 +115,8 @@ __global__ void __launch_bounds__(128)
 beam_select_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk, int mask3,
                    const float* __restrict__ part_m, const float* __restrict__ part_s,
                    const float* __restrict__ part_tv, const int32_t* __restrict__ part_ti,
-                   BeamState in, BeamState out, int32_t* __restrict__ bp, const int32_t* __restrict__ lens) {
+                   BeamState in, BeamState out, int32_t* __restrict__ bp, const int32_t* __restrict__ lens,
+                   const int32_t* __restrict__ cg_next, const float* __restrict__ cg_delta) {
   __shared__ float s_mx[4][kMaxBeam], s_ls[4][kMaxBeam], s_lp[4][kMaxBeam];
   constexpr int kNone = (int)0x80000000;
   const unsigned full = 0xffffffffu;
@@ -129,6 +131,7 @@ beam_select_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk
       const size_t o = (size_t)s * K + lane;
       out.ctx[2 * o] = in.ctx[2 * o]; out.ctx[2 * o + 1] = in.ctx[2 * o + 1];
       out.lp[o] = in.lp[o]; out.len[o] = in.len[o]; out.hash[o] = in.hash[o];
+      if (cg_next != nullptr) out.cst[o] = in.cst[o];
       bp[((size_t)s * T + t) * K + lane] = lane < nl ? (lane << 28) : 0;
     }
     if (lane == 0) out.nlive[s] = nl;
@@ -250,7 +253,7 @@ beam_select_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk
 
   // lane r < K: the r-th extension in rank order
   const bool cand = lane < K && my_f >= 0;
-  int par = 0, tok = -1, c0 = -1, c1 = blank, ln = 2;
+  int par = 0, tok = -1, c0 = -1, c1 = blank, ln = 2, cs = 0;
   uint64_t hs = kHashSeed;
   if (cand) {
     par = my_f / V;
@@ -260,12 +263,17 @@ beam_select_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk
     ln = in.len[prow];
     c0 = in.ctx[2 * prow];
     c1 = in.ctx[2 * prow + 1];
+    if (cg_next != nullptr) cs = in.cst[prow];
     if (y != blank && y != unk && y != mask3) {      // ys unchanged for blank / unk (/ the literal 1 of the online loop)
       tok = y;
       hs = hash_push(hs, y);
       ln += 1;
       c0 = c1;
       c1 = y;
+      if (cg_next != nullptr) {                      // hot words: the boost is applied AFTER the top-K selection, to the extended hypothesis
+        my_v += cg_delta[(size_t)cs * V + y];
+        cs = cg_next[(size_t)cs * V + y];
+      }
     }
   }
   // dedupe: first earlier lane holding the same token sequence
@@ -297,6 +305,7 @@ beam_select_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk
     out.lp[o] = lp;
     out.len[o] = ln;
     out.hash[o] = hs;
+    if (cg_next != nullptr) out.cst[o] = cs;
     bp[((size_t)s * T + t) * K + slot] = (par << 28) | (tok + 1);
   }
   if (lane >= nnew && lane < K) {      // dead slots keep a valid context for the next decoder GEMM
@@ -306,6 +315,7 @@ beam_select_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk
     out.lp[o] = -INFINITY;
     out.len[o] = 2;
     out.hash[o] = kHashSeed;
+    if (cg_next != nullptr) out.cst[o] = 0;
     bp[((size_t)s * T + t) * K + lane] = 0;
   }
   if (lane == 0) out.nlive[s] = nnew;
@@ -351,7 +361,8 @@ beam_step_kernel(int B, int K, int V, int nt, int T, int t, int blank, int unk, 
 // shared memory, write tokens / timestamps in forward order.
 __global__ void __launch_bounds__(32)
 beam_backtrace_kernel(int B, int K, int T, BeamState fin, const int32_t* __restrict__ bp, int64_t* __restrict__ tokens,
-                      int32_t* __restrict__ ts, int32_t* __restrict__ n_out, float* __restrict__ score, int cap) {
+                      int32_t* __restrict__ ts, int32_t* __restrict__ n_out, float* __restrict__ score, int cap,
+                      const float* __restrict__ cg_resid) {
   extern __shared__ int32_t sm[];
   int32_t* trel = sm;                 // [T*K]
   int32_t* rtok = sm + (size_t)T * K; // [T]
@@ -366,10 +377,12 @@ beam_backtrace_kernel(int B, int K, int T, BeamState fin, const int32_t* __restr
     int best = 0;
     float bn = -INFINITY;
     for (int q = 0; q < nl; ++q) {
-      const float norm = __fdiv_rn(fin.lp[(size_t)s * K + q], (float)fin.len[(size_t)s * K + q]);
+      // hot words: the boost of a match that did not complete is revoked before the hypotheses are compared
+      const float lpq = fin.lp[(size_t)s * K + q] - (cg_resid != nullptr ? cg_resid[fin.cst[(size_t)s * K + q]] : 0.f);
+      const float norm = __fdiv_rn(lpq, (float)fin.len[(size_t)s * K + q]);
       if (q == 0 || norm > bn) { bn = norm; best = q; }
     }
-    score[s] = fin.lp[(size_t)s * K + best];
+    score[s] = fin.lp[(size_t)s * K + best] - (cg_resid != nullptr ? cg_resid[fin.cst[(size_t)s * K + best]] : 0.f);
     int slot = best;
     for (int t = T - 1; t >= 0; --t) {
       const int e = trel[t * K + slot];
@@ -397,12 +410,13 @@ BeamState carve_state(char*& p, int B, int K) {
   s.len = reinterpret_cast<int32_t*>(p);  p += align256(N * sizeof(int32_t));
   s.hash = reinterpret_cast<uint64_t*>(p); p += align256(N * sizeof(uint64_t));
   s.nlive = reinterpret_cast<int32_t*>(p); p += align256((size_t)B * sizeof(int32_t));
+  s.cst = reinterpret_cast<int32_t*>(p);  p += align256(N * sizeof(int32_t));
   return s;
 }
 
 size_t state_bytes(int B, int K) {
   const size_t N = (size_t)B * K;
-  return align256(N * 8) + align256(N * 4) + align256(N * 4) + align256(N * 8) + align256((size_t)B * 4);
+  return align256(N * 8) + align256(N * 4) + align256(N * 4) + align256(N * 8) + align256((size_t)B * 4) + align256(N * 4);
 }
 
 }  // namespace
@@ -411,7 +425,7 @@ size_t beam_state_bytes(int B, int K) { return state_bytes(B, K); }
 BeamStateView beam_state_view(k2b_handle* h, int B, int K, int which) {
   char* p = static_cast<char*>(h->ws_state.p) + (size_t)which * state_bytes(B, K);
   const BeamState s = carve_state(p, B, K);
-  return BeamStateView{s.ctx, s.lp, s.len, reinterpret_cast<unsigned long long*>(s.hash), s.nlive};
+  return BeamStateView{s.ctx, s.lp, s.len, reinterpret_cast<unsigned long long*>(s.hash), s.nlive, s.cst};
 }
 
 void prof_begin(k2b_handle* h) {
@@ -610,6 +624,10 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
   const bool unfused = h->opt_unfused_step != 0;
   const bool fused = tc && have_tab && ximg != nullptr && !unfused && joiner_topk_usable(h, K) && T > 0;
   if (t0 > 0 && !fused) return fail(h, K2B_ERR_UNSUPPORTED, "beam_dev: time chunks need the memoised decoder table");
+  const bool biased = h->cg_next != nullptr && !greedy;
+  if (biased && fused)
+    return fail(h, K2B_ERR_UNSUPPORTED, "a context graph (hot words) is served by the cluster kernel (V <= 1024) and by the per-frame merge: "
+                                        "k2b_set_option(h, \"unfused_step\", 1) or fp32 precision for this vocabulary");
   if (fused) {
     K2B_TRY(ensure_joiner_assets(h));
     const size_t nsync = beam_mega_sync_ints(h, B, T, K);
@@ -707,26 +725,30 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
     K2B_CUDA(h, launch_pdl(beam_select_kernel, dim3((B + 3) / 4), dim3(128), 0, h->stream, B, K, V, nt, T, t, (int)c.blank_id,
                             (int)c.unk_id, extra_mask, (const float*)part_m, (const float*)part_s, (const float*)part_tv,
                             (const int32_t*)part_ti, st[cur], st[cur ^ 1], bp,
-                            (const int32_t*)(h->lens_active ? h->lens_dev : nullptr)));
+                            (const int32_t*)(h->lens_active ? h->lens_dev : nullptr),
+                            (const int32_t*)(biased ? h->cg_next : nullptr), (const float*)(biased ? h->cg_delta : nullptr)));
     K2B_LAUNCH_CHECK(h);
     if (h->prof_which == 2) prof_end(h);
     cur ^= 1;
   }
   if (carry) return K2B_OK;
-  return beam_backtrace_dev(h, B, K, T, st[cur].lp, st[cur].len, st[cur].nlive, bp, tokens, ts, n_out, score, cap);
+  return beam_backtrace_dev(h, B, K, T, st[cur].lp, st[cur].len, st[cur].nlive, bp, tokens, ts, n_out, score, cap,
+                            biased ? st[cur].cst : nullptr);
 }
 
 int32_t beam_backtrace_dev(k2b_handle* h, int B, int K, int T, const float* lp, const int32_t* len, const int32_t* nlive,
-                           const int32_t* bp, int64_t* tokens, int32_t* ts, int32_t* n_out, float* score, int cap) {
+                           const int32_t* bp, int64_t* tokens, int32_t* ts, int32_t* n_out, float* score, int cap, const int32_t* cst) {
   BeamState fin{};
   fin.lp = const_cast<float*>(lp);
   fin.len = const_cast<int32_t*>(len);
   fin.nlive = const_cast<int32_t*>(nlive);
+  fin.cst = const_cast<int32_t*>(cst);
   const size_t smem = sizeof(int32_t) * ((size_t)T * K + 2 * (size_t)T);
   if (smem > 200 * 1024) return fail(h, K2B_ERR_UNSUPPORTED, "modified_beam_search: T*K too large for the back-trace");
   if (smem > 48 * 1024)
     K2B_CUDA(h, cudaFuncSetAttribute(beam_backtrace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  beam_backtrace_kernel<<<B, 32, smem, h->stream>>>(B, K, T, fin, bp, tokens, ts, n_out, score, cap);
+  beam_backtrace_kernel<<<B, 32, smem, h->stream>>>(B, K, T, fin, bp, tokens, ts, n_out, score, cap,
+                                                    cst != nullptr ? h->cg_resid : nullptr);
   K2B_LAUNCH_CHECK(h);
   return K2B_OK;
 }

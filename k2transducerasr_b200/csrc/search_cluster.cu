@@ -42,6 +42,7 @@ struct HypState {
   int len[kNH];
   unsigned long long hash[kNH];
   int nlive[kNH];
+  int cst[kNH];             // context-graph (hot word) state of every hypothesis; all zero without a graph
 };
 
 struct ClusterArgs {
@@ -67,6 +68,11 @@ struct ClusterArgs {
   int* status;
   long long* timing;        // optional [8] cycle totals of the step phases (cluster 0, CTA 0, thread 0)
   const int32_t* lens;      // [B] frames to decode per stream (k2b_set_encoder_out_lens), or null = all T
+  // contextual biasing (hot words): dense automaton over token ids, or null. io_cst [B*K]: state per hypothesis, written at the end
+  // of every launch and read back when `resume` is set
+  const int32_t* cg_next;   // [S,V]
+  const float* cg_delta;    // [S,V]
+  int32_t* io_cst;
 };
 
 __device__ __forceinline__ bool better_c(float v, int i, float ev, int ei) { return v > ev || (v == ev && i > ei); }
@@ -120,7 +126,8 @@ template <int K>
 __device__ __forceinline__ void select_stream(int s, int V, int CS, const float* __restrict__ xb, const HypState& in,
                                               HypState& out, int blank, int unk, int extra_mask, int32_t* __restrict__ bp_row,
                                               int lane, const float* __restrict__ dec_tab, int J, bool do_prefetch,
-                                              uint32_t* __restrict__ scr, bool need_lp, long long* tp = nullptr) {
+                                              uint32_t* __restrict__ scr, bool need_lp, const int32_t* __restrict__ cg_next,
+                                              const float* __restrict__ cg_delta, long long* tp = nullptr) {
 #define K2B_SUB(i) do { if (tp != nullptr) { const long long now = clock64(); tp[i] += now - tp[19]; tp[19] = now; } } while (0)
   if (tp != nullptr) tp[19] = clock64();
   constexpr int XWP = xw_padded(K);
@@ -145,7 +152,7 @@ __device__ __forceinline__ void select_stream(int s, int V, int CS, const float*
   if (nl == 0) {                                   // warp-uniform
     if (lane < K) {
       const int o = s * K + lane;
-      out.ctx0[o] = -1; out.ctx1[o] = blank; out.lp[o] = -INFINITY; out.len[o] = 2; out.hash[o] = kHashSeedC;
+      out.ctx0[o] = -1; out.ctx1[o] = blank; out.lp[o] = -INFINITY; out.len[o] = 2; out.hash[o] = kHashSeedC; out.cst[o] = 0;
     }
     if (lane == 0) out.nlive[s] = 0;
     return;
@@ -233,16 +240,20 @@ __device__ __forceinline__ void select_stream(int s, int V, int CS, const float*
   K2B_SUB(10);
   // ---- lanes 0..K-1 hold the winners, best first -------------------------------------------------------------
   const bool cand = lane < K && my_f >= 0;
-  int par = 0, tok = -1, c0 = -1, c1 = blank, ln = 2;
+  int par = 0, tok = -1, c0 = -1, c1 = blank, ln = 2, cs = 0;
   uint64_t hs = kHashSeedC;
   if (cand) {
 #pragma unroll
     for (int hh = 1; hh < K; ++hh) par += (my_f >= hh * V) ? 1 : 0;
     const int y = my_f - par * V;
     const int prow = s * K + par;
-    hs = in.hash[prow]; ln = in.len[prow]; c0 = in.ctx0[prow]; c1 = in.ctx1[prow];
+    hs = in.hash[prow]; ln = in.len[prow]; c0 = in.ctx0[prow]; c1 = in.ctx1[prow]; cs = in.cst[prow];
     if (y != blank && y != unk && y != extra_mask) {
       tok = y; hs = hash_push_c(hs, y); ln += 1; c0 = c1; c1 = y;
+      if (cg_next != nullptr) {       // hot words: the boost goes to the extended hypothesis, after the top-K selection
+        my_v += __ldg(cg_delta + (size_t)cs * V + y);
+        cs = __ldg(cg_next + (size_t)cs * V + y);
+      }
       if (do_prefetch)    // pull the new context's decoder row towards L2 while the merge finishes (one TMA-unit op)
         l2_prefetch_bulk(dec_tab + ((size_t)(c0 + 1) * V + c1) * J, (uint32_t)(J * 4));
     }
@@ -287,12 +298,12 @@ __device__ __forceinline__ void select_stream(int s, int V, int CS, const float*
   if (is_root) {
     const int slot = __popc(roots & ((1u << lane) - 1u));
     const int o = s * K + slot;
-    out.ctx0[o] = c0; out.ctx1[o] = c1; out.lp[o] = lp; out.len[o] = ln; out.hash[o] = hs;
+    out.ctx0[o] = c0; out.ctx1[o] = c1; out.lp[o] = lp; out.len[o] = ln; out.hash[o] = hs; out.cst[o] = cs;
     if (bp_row != nullptr) bp_row[slot] = (par << 28) | (tok + 1);
   }
   if (lane >= nnew && lane < K) {
     const int o = s * K + lane;
-    out.ctx0[o] = -1; out.ctx1[o] = blank; out.lp[o] = -INFINITY; out.len[o] = 2; out.hash[o] = kHashSeedC;
+    out.ctx0[o] = -1; out.ctx1[o] = blank; out.lp[o] = -INFINITY; out.len[o] = 2; out.hash[o] = kHashSeedC; out.cst[o] = 0;
     if (bp_row != nullptr) bp_row[lane] = 0;
   }
   if (lane == 0) out.nlive[s] = nnew;
@@ -385,6 +396,7 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
       st[b].lp[n] = (h == 0) ? 0.f : -INFINITY;
       st[b].len[n] = 2; st[b].hash[n] = kHashSeedC;
       st[b].nlive[n] = 0;
+      st[b].cst[n] = 0;
     }
     if (n < S) {
       const int gs = cluster * S + n;
@@ -396,6 +408,7 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
         const size_t gi = (size_t)gs * K + h;
         st[0].ctx0[n] = a.io_ctx[2 * gi]; st[0].ctx1[n] = a.io_ctx[2 * gi + 1];
         st[0].lp[n] = a.fin_lp[gi]; st[0].len[n] = a.fin_len[gi]; st[0].hash[n] = a.io_hash[gi];
+        if (a.io_cst != nullptr) st[0].cst[n] = a.io_cst[gi];
       }
     }
   }
@@ -686,7 +699,7 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
             if (lane < K) {
               const int o = s * K + lane;
               st[cur ^ 1].ctx0[o] = st[cur].ctx0[o]; st[cur ^ 1].ctx1[o] = st[cur].ctx1[o]; st[cur ^ 1].lp[o] = st[cur].lp[o];
-              st[cur ^ 1].len[o] = st[cur].len[o]; st[cur ^ 1].hash[o] = st[cur].hash[o];
+              st[cur ^ 1].len[o] = st[cur].len[o]; st[cur ^ 1].hash[o] = st[cur].hash[o]; st[cur ^ 1].cst[o] = st[cur].cst[o];
               if (bp_row != nullptr) bp_row[lane] = lane < st[cur].nlive[s] ? (lane << 28) : 0;
             }
             if (lane == 0) st[cur ^ 1].nlive[s] = st[cur].nlive[s];
@@ -694,7 +707,7 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
             continue;
           }
           select_stream<K>(s, V, CS, xw, st[cur], st[cur ^ 1], a.blank, a.unk, a.extra_mask, bp_row, lane, a.dec_tab, J,
-                           (int)rank == (s % CS), sel_scr[warp], a.need_lp != 0, (TIMED && timed) ? tph : nullptr);
+                           (int)rank == (s % CS), sel_scr[warp], a.need_lp != 0, a.cg_next, a.cg_delta, (TIMED && timed) ? tph : nullptr);
         }
       }
       K2B_PHASE(6);
@@ -709,6 +722,7 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
       if (g < a.B) {
         a.fin_lp[(size_t)g * K + hslot] = st[cur].lp[tid];
         a.fin_len[(size_t)g * K + hslot] = st[cur].len[tid];
+        if (a.io_cst != nullptr) a.io_cst[(size_t)g * K + hslot] = st[cur].cst[tid];
         if (a.io_ctx != nullptr) {
           a.io_ctx[2 * ((size_t)g * K + hslot)] = st[cur].ctx0[tid];
           a.io_ctx[2 * ((size_t)g * K + hslot) + 1] = st[cur].ctx1[tid];
@@ -954,6 +968,12 @@ int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, 
   a.t0 = t0; a.Ttot = Ttot > 0 ? Ttot : T; a.resume = resume; a.io_ctx = io_ctx; a.io_hash = io_hash;
   a.timing = h->cluster_timing;
   a.lens = h->lens_active ? h->lens_dev : nullptr;
+  a.cg_next = nullptr; a.cg_delta = nullptr; a.io_cst = nullptr;
+  if (h->cg_next != nullptr && K > 1) {               // greedy search (beam 1) is never biased
+    a.cg_next = h->cg_next; a.cg_delta = h->cg_delta;
+    a.io_cst = cluster_cst(h, B, K);
+    if (a.io_cst == nullptr) return K2B_ERR_CUDA;
+  }
   a.bp = bp; a.fin_lp = fin_lp; a.fin_len = fin_len; a.fin_nlive = fin_nlive; a.status = status;
   const size_t dyn = cluster_dyn_smem(J, CS, K);
   void (*kern)(const ClusterArgs) = cluster_kernel_for(K, a.x3 != 0, a.timing != nullptr, cluster_pair_mode(h, CS));
@@ -977,6 +997,14 @@ int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, 
 
 // dev_status: [0] cluster / persistent search kernels: an mbarrier or counter wait timed out, [1] the same in the tcgen05 GEMMs,
 // [2] a caller-supplied Hyp held a token id outside the vocabulary (device-pointer calls), [3] scratch (first-emission frame)
+// automaton state per hypothesis of the cluster engine: lives on the handle so that it is carried from one time chunk's launch
+// to the next (resume) and is there for the back-trace
+int32_t* cluster_cst(k2b_handle* h, int B, int K) {
+  if (h->cg_next == nullptr) return nullptr;
+  if (ensure(h, h->ws_cst, sizeof(int32_t) * (size_t)B * K) != K2B_OK) return nullptr;
+  return static_cast<int32_t*>(h->ws_cst.p);
+}
+
 int32_t cluster_status(k2b_handle* h) {
   int st[4] = {0, 0, 0, 0};
   K2B_CUDA(h, cudaMemcpyAsync(st, h->dev_status, sizeof(st), cudaMemcpyDeviceToHost, h->stream));

@@ -21,6 +21,7 @@ struct BeamPool {
   int32_t* len = nullptr;              // [S][K]
   unsigned long long* hash = nullptr;  // [S][K]
   int32_t* nlive = nullptr;            // [S]
+  int32_t* cst = nullptr;              // [S][K] context-graph (hot word) state
   int32_t* nframes = nullptr;          // [S] frames decoded so far
   int32_t* hist = nullptr;             // [S][max_frames][K] back-pointer rows: (parent slot << 28) | (token + 1)
   int32_t* slots = nullptr;            // [max_streams] the slots of the call in flight
@@ -33,10 +34,11 @@ constexpr unsigned long long kSeedHash = 0x9E3779B97F4A7C15ull;
 
 __global__ void pool_reset_kernel(int K, int slot, int c0, int c1, int blank, int32_t* __restrict__ ctx, float* __restrict__ lp,
                                   int32_t* __restrict__ len, unsigned long long* __restrict__ hash, int32_t* __restrict__ nlive,
-                                  int32_t* __restrict__ nframes) {
+                                  int32_t* __restrict__ nframes, int32_t* __restrict__ cst) {
   const int k = threadIdx.x;
   if (k >= K) return;
   const size_t o = (size_t)slot * K + k;
+  cst[o] = 0;
   ctx[2 * o] = k == 0 ? c0 : -1;
   ctx[2 * o + 1] = k == 0 ? c1 : blank;
   lp[o] = k == 0 ? 0.f : -INFINITY;
@@ -47,11 +49,13 @@ __global__ void pool_reset_kernel(int K, int slot, int c0, int c1, int blank, in
 
 __global__ void pool_gather_kernel(int B, int K, const int32_t* __restrict__ slots, const int32_t* __restrict__ ctx,
                                    const float* __restrict__ lp, const int32_t* __restrict__ len,
-                                   const unsigned long long* __restrict__ hash, const int32_t* __restrict__ nlive, BeamStateView d) {
+                                   const unsigned long long* __restrict__ hash, const int32_t* __restrict__ nlive,
+                                   const int32_t* __restrict__ cst, BeamStateView d) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * K) return;
   const int b = i / K, k = i - b * K;
   const size_t o = (size_t)slots[b] * K + k;
+  if (d.cst != nullptr) d.cst[i] = cst[o];
   d.ctx[2 * i] = ctx[2 * o]; d.ctx[2 * i + 1] = ctx[2 * o + 1];
   d.lp[i] = lp[o]; d.len[i] = len[o]; d.hash[i] = hash[o];
   if (k == 0) d.nlive[b] = nlive[slots[b]];
@@ -61,7 +65,7 @@ __global__ void pool_gather_kernel(int B, int K, const int32_t* __restrict__ slo
 __global__ void pool_scatter_kernel(int B, int K, int Tc, int max_frames, const int32_t* __restrict__ slots, BeamStateView s,
                                     const int32_t* __restrict__ bp, int32_t* __restrict__ ctx, float* __restrict__ lp,
                                     int32_t* __restrict__ len, unsigned long long* __restrict__ hash, int32_t* __restrict__ nlive,
-                                    int32_t* __restrict__ nframes, int32_t* __restrict__ hist) {
+                                    int32_t* __restrict__ nframes, int32_t* __restrict__ hist, int32_t* __restrict__ cst) {
   const int b = blockIdx.x;
   const int slot = slots[b];
   const int f0 = nframes[slot];
@@ -71,6 +75,7 @@ __global__ void pool_scatter_kernel(int B, int K, int Tc, int max_frames, const 
     const size_t i = (size_t)b * K + threadIdx.x, o = (size_t)slot * K + threadIdx.x;
     ctx[2 * o] = s.ctx[2 * i]; ctx[2 * o + 1] = s.ctx[2 * i + 1];
     lp[o] = s.lp[i]; len[o] = s.len[i]; hash[o] = s.hash[i];
+    if (s.cst != nullptr) cst[o] = s.cst[i];
   }
   __syncthreads();
   if (threadIdx.x == 0) { nlive[slot] = s.nlive[b]; nframes[slot] = f0 + Tc; }
@@ -85,7 +90,7 @@ pool_backtrace_kernel(int B, int K, int max_frames, const int32_t* __restrict__ 
                       const int32_t* __restrict__ len, const int32_t* __restrict__ nlive, const int32_t* __restrict__ nframes,
                       const int32_t* __restrict__ ctx, const int32_t* __restrict__ hist, int64_t* __restrict__ tokens,
                       int32_t* __restrict__ ts, int32_t* __restrict__ n_out, float* __restrict__ score, int64_t* __restrict__ hyp_out,
-                      int cap) {
+                      int cap, const int32_t* __restrict__ cst, const float* __restrict__ cg_resid) {
   __shared__ int32_t tile[kTileFrames * kMaxBeam];
   const int b = blockIdx.x, lane = threadIdx.x;
   const int slot = slots[b];
@@ -95,9 +100,12 @@ pool_backtrace_kernel(int B, int K, int max_frames, const int32_t* __restrict__ 
   if (lane == 0) {
     float bn = -INFINITY;
     for (int q = 0; q < nl; ++q) {
+      // (the boost of a hot word still being matched stays in the score while the stream is alive: only a finished utterance
+      // revokes it - streaming results are "so far")
       const float norm = __fdiv_rn(lp[(size_t)slot * K + q], (float)len[(size_t)slot * K + q]);
       if (q == 0 || norm > bn) { bn = norm; best = q; }
     }
+    (void)cst; (void)cg_resid;
     score[b] = lp[(size_t)slot * K + best];
     if (hyp_out != nullptr) {             // OnlineStream.Hyp <- last ctx tokens of the best hypothesis (ref OnlineRecognizer.cs:208)
       hyp_out[2 * b] = ctx[2 * ((size_t)slot * K + best)];
@@ -135,7 +143,7 @@ pool_backtrace_kernel(int B, int K, int max_frames, const int32_t* __restrict__ 
 void beam_pool_free(k2b_handle* h) {
   BeamPool* p = h->beam_pool;
   if (p == nullptr) return;
-  void* bufs[] = {p->ctx, p->lp, p->len, p->hash, p->nlive, p->nframes, p->hist, p->slots};
+  void* bufs[] = {p->ctx, p->lp, p->len, p->hash, p->nlive, p->nframes, p->hist, p->slots, p->cst};
   for (void* b : bufs) if (b) cudaFree(b);
   delete p;
   h->beam_pool = nullptr;
@@ -154,6 +162,7 @@ int32_t beam_pool_create(k2b_handle* h, int max_streams, int K, int max_frames) 
   K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&p->lp), N * sizeof(float)));
   K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&p->len), N * sizeof(int32_t)));
   K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&p->hash), N * sizeof(unsigned long long)));
+  K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&p->cst), N * sizeof(int32_t)));
   K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&p->nlive), S * sizeof(int32_t)));
   K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&p->nframes), S * sizeof(int32_t)));
   K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&p->hist), N * (size_t)max_frames * sizeof(int32_t)));
@@ -174,7 +183,7 @@ int32_t beam_pool_reset(k2b_handle* h, int slot, const int64_t* hyp_host) {
       return fail(h, K2B_ERR_INVALID, "k2b_beam_pool_reset: Hyp holds a token id outside the vocabulary");
     c0 = (int)hyp_host[0]; c1 = (int)hyp_host[1];
   }
-  pool_reset_kernel<<<1, 32, 0, h->stream>>>(p->K, slot, c0, c1, h->cfg.blank_id, p->ctx, p->lp, p->len, p->hash, p->nlive, p->nframes);
+  pool_reset_kernel<<<1, 32, 0, h->stream>>>(p->K, slot, c0, c1, h->cfg.blank_id, p->ctx, p->lp, p->len, p->hash, p->nlive, p->nframes, p->cst);
   K2B_LAUNCH_CHECK(h);
   p->nframes_host[(size_t)slot] = 0;
   return K2B_OK;
@@ -201,7 +210,7 @@ int32_t beam_pool_begin(k2b_handle* h, const int32_t* slots_host, int B, int Tc)
 
 int32_t beam_pool_gather(k2b_handle* h, int B, const BeamStateView& dst) {
   BeamPool* p = h->beam_pool;
-  pool_gather_kernel<<<(B * p->K + 127) / 128, 128, 0, h->stream>>>(B, p->K, p->slots, p->ctx, p->lp, p->len, p->hash, p->nlive, dst);
+  pool_gather_kernel<<<(B * p->K + 127) / 128, 128, 0, h->stream>>>(B, p->K, p->slots, p->ctx, p->lp, p->len, p->hash, p->nlive, p->cst, dst);
   K2B_LAUNCH_CHECK(h);
   return K2B_OK;
 }
@@ -209,7 +218,7 @@ int32_t beam_pool_gather(k2b_handle* h, int B, const BeamStateView& dst) {
 int32_t beam_pool_scatter(k2b_handle* h, int B, int Tc, const BeamStateView& src, const int32_t* bp_chunk) {
   BeamPool* p = h->beam_pool;
   pool_scatter_kernel<<<B, 128, 0, h->stream>>>(B, p->K, Tc, p->max_frames, p->slots, src, bp_chunk, p->ctx, p->lp, p->len, p->hash,
-                                                p->nlive, p->nframes, p->hist);
+                                                p->nlive, p->nframes, p->hist, p->cst);
   K2B_LAUNCH_CHECK(h);
   for (int s : p->cur_slots) p->nframes_host[(size_t)s] += Tc;
   return K2B_OK;
@@ -218,7 +227,7 @@ int32_t beam_pool_scatter(k2b_handle* h, int B, int Tc, const BeamStateView& src
 int32_t beam_pool_backtrace(k2b_handle* h, int B, int64_t* tokens, int32_t* ts, int32_t* n_out, float* score, int64_t* hyp_out, int cap) {
   BeamPool* p = h->beam_pool;
   pool_backtrace_kernel<<<B, 32, 0, h->stream>>>(B, p->K, p->max_frames, p->slots, p->lp, p->len, p->nlive, p->nframes, p->ctx, p->hist,
-                                                 tokens, ts, n_out, score, hyp_out, cap);
+                                                 tokens, ts, n_out, score, hyp_out, cap, p->cst, h->cg_resid);
   K2B_LAUNCH_CHECK(h);
   return K2B_OK;
 }

@@ -394,6 +394,7 @@ class _Hyp:
     ys: List[int]
     lp: np.float32
     ts: List[int]
+    cs: int = 0          # context-graph (hot word) state
 
 
 def mbs_seed(m: Model, B: int, hyp: Optional[Sequence[Sequence[int]]] = None) -> List[List[_Hyp]]:
@@ -406,7 +407,7 @@ def mbs_seed(m: Model, B: int, hyp: Optional[Sequence[Sequence[int]]] = None) ->
 
 def modified_beam_search(m: Model, enc: np.ndarray, beam: int = 4, init: Optional[List[List[_Hyp]]] = None,
                          frame_offset: Optional[Sequence[int]] = None, extra_mask: Optional[int] = None,
-                         return_state: bool = False):
+                         return_state: bool = False, context_graph=None, finalize: bool = True):
     """enc [B,T,J]. Per stream keep <= beam hypotheses, seeded {ys=[-1]*(ctx-1)+[blank], lp=0}.
     Per frame: decoder on every live hypothesis' last ctx tokens -> joiner with the stream's frame
     -> log_softmax -> + hyp.lp -> top-`beam` over the stream's flattened [n_hyps*V] scores ->
@@ -418,11 +419,15 @@ def modified_beam_search(m: Model, enc: np.ndarray, beam: int = 4, init: Optiona
     Streaming (the dead maxActivePaths of ref OnlineRecognizer.cs:19 brought to life): `init` = the beams a
     previous chunk returned (return_state=True), `frame_offset[b]` = frames of stream b decoded before this
     chunk (timestamps are utterance-absolute), `extra_mask` = a third non-emitting id (the literal 1 of
-    ref OnlineRecognizer.cs:181). Decoding an utterance chunk by chunk equals decoding it whole."""
+    ref OnlineRecognizer.cs:181). Decoding an utterance chunk by chunk equals decoding it whole.
+    Hot words (`context_graph` = k2transducerasr_b200.hotwords.ContextGraph: dense next / delta / residual tables, semantics in
+    that module): the boost delta[state, token] is added to an EXTENDED hypothesis after the top-`beam` selection (icefall's order
+    [EXT]) and the hypothesis moves to next[state, token]; with `finalize` the residual of the final state is subtracted before the
+    hypotheses are compared (offline); streaming results "so far" keep it (finalize=False)."""
     enc = np.asarray(enc, F32)
     B, T, _ = enc.shape
     V = m.V
-    hyps: List[List[_Hyp]] = mbs_seed(m, B) if init is None else [[_Hyp(list(h.ys), F32(h.lp), list(h.ts)) for h in hs] for hs in init]
+    hyps: List[List[_Hyp]] = mbs_seed(m, B) if init is None else [[_Hyp(list(h.ys), F32(h.lp), list(h.ts), h.cs) for h in hs] for hs in init]
     foff = [0] * B if frame_offset is None else [int(x) for x in frame_offset]
     gap = np.full(B, np.inf, np.float64)
     fgap = np.full((B, T), np.inf, np.float64)
@@ -462,24 +467,29 @@ def modified_beam_search(m: Model, enc: np.ndarray, beam: int = 4, init: Optiona
                 par = int(fi) // V
                 h = hyps[b][par]
                 tok = int(fi) % V
-                ys, tss = h.ys, h.ts
+                ys, tss, cs = h.ys, h.ts, h.cs
                 emit = tok != m.blank_id and tok != m.unk_id and tok != extra_mask
+                new_lp = F32(flat[fi])
                 if emit:
                     ys = ys + [tok]
                     tss = tss + [t + foff[b]]
+                    if context_graph is not None:
+                        new_lp = F32(new_lp + F32(context_graph.delta[cs, tok]))
+                        cs = int(context_graph.next[cs, tok])
                 key = tuple(ys)
                 if key in index:
                     o = new[index[key]]
-                    o.lp = logaddexp32(o.lp, flat[fi])
+                    o.lp = logaddexp32(o.lp, new_lp)
                 else:
                     index[key] = len(new)
-                    new.append(_Hyp(list(ys), F32(flat[fi]), list(tss)))
+                    new.append(_Hyp(list(ys), new_lp, list(tss), cs))
                     rec.append((par, tok if emit else -1))
             hyps[b] = new
             history[b].append(rec)
     out = []
     for b in range(B):
-        norm = [F32(h.lp) / F32(len(h.ys)) for h in hyps[b]]
+        fin_lp = [F32(h.lp) - (F32(context_graph.residual[h.cs]) if (context_graph is not None and finalize) else F32(0)) for h in hyps[b]]
+        norm = [F32(v) / F32(len(h.ys)) for v, h in zip(fin_lp, hyps[b])]
         bi = 0
         for i in range(1, len(norm)):
             if norm[i] > norm[bi]:
@@ -490,7 +500,7 @@ def modified_beam_search(m: Model, enc: np.ndarray, beam: int = 4, init: Optiona
             fin = srt[-1] - srt[-2]
             gap[b] = min(gap[b], fin)
         h = hyps[b][bi]
-        out.append(StreamResult(tokens=h.ys, timestamps=h.ts, appended=h.ys[m.context_size:], score=float(h.lp),
+        out.append(StreamResult(tokens=h.ys, timestamps=h.ts, appended=h.ys[m.context_size:], score=float(fin_lp[bi]),
                                 min_gap=float(gap[b]), hyp=h.ys[-m.context_size:], frame_gap=[float(g) for g in fgap[b]],
                                 history=history[b], final_gap=fin, frame_scale=[float(x) for x in fscale[b]]))
     return (out, hyps) if return_state else out

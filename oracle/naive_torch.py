@@ -90,8 +90,24 @@ def greedy_single(m: TorchModel, enc: np.ndarray, max_sym_per_frame: int = 1, ex
     return toks, ts
 
 
-def beam_search(m: TorchModel, enc: np.ndarray, beam: int) -> Tuple[List[int], List[int], float]:
-    """Textbook modified_beam_search of ONE stream, enc [T,J]. Returns (emitted tokens, timestamps, log-prob)."""
+def beam_search(m: TorchModel, enc: np.ndarray, beam: int, hotwords=None, hot_score: float = 0.0) -> Tuple[List[int], List[int], float]:
+    """Textbook modified_beam_search of ONE stream, enc [T,J]. Returns (emitted tokens, timestamps, log-prob).
+    hotwords (token-id sequences) + hot_score: contextual biasing restated WITHOUT an automaton - a hypothesis' total boost is a
+    function of its token sequence (k2transducerasr_b200.hotwords.brute_force_boost plus the boost of the match in progress); an
+    extension adds the difference of the totals; the match in progress is revoked at the end."""
+    def boost(ys, final):
+        if not hotwords:
+            return 0.0
+        words = [tuple(int(x) for x in w) for w in hotwords if len(w)]
+        earned, hist = 0.0, ()
+        for y in ys[m.ctx:]:
+            hist = hist + (int(y),)
+            while hist and not any(w[:len(hist)] == hist for w in words):
+                hist = hist[1:]
+            if hist in words:
+                earned += len(hist) * hot_score
+                hist = ()
+        return earned + (0.0 if final else len(hist) * hot_score)
     enc_t = torch.from_numpy(np.ascontiguousarray(enc, dtype=np.float32))
     seed = tuple([-1] * (m.ctx - 1) + [m.blank_id])
     beams: Dict[tuple, Tuple[np.float32, List[int]]] = {seed: (np.float32(0.0), [])}      # insertion-ordered
@@ -106,6 +122,7 @@ def beam_search(m: TorchModel, enc: np.ndarray, beam: int) -> Tuple[List[int], L
             par, tok = divmod(i, m.V)
             ys, tss = keys[par], beams[keys[par]][1]
             if tok != m.blank_id and tok != m.unk_id:
+                v = float(np.float32(np.float32(v) + np.float32(boost(ys + (tok,), False) - boost(ys, False))))
                 ys, tss = ys + (tok,), tss + [t]
             if ys in new:
                 a, b = np.float32(new[ys][0]), np.float32(v)
@@ -114,12 +131,13 @@ def beam_search(m: TorchModel, enc: np.ndarray, beam: int) -> Tuple[List[int], L
             else:
                 new[ys] = (np.float32(v), tss)
         beams = new
-    best, best_norm = None, None
+    best, best_norm, best_lp = None, None, None
     for ys, (lpv, tss) in beams.items():
-        norm = np.float32(lpv) / np.float32(len(ys))
+        fin = np.float32(np.float32(lpv) - np.float32(boost(ys, False) - boost(ys, True)))     # revoke the match in progress
+        norm = fin / np.float32(len(ys))
         if best is None or norm > best_norm:
-            best, best_norm = ys, norm
-    return list(best[m.ctx:]), beams[best][1], float(beams[best][0])
+            best, best_norm, best_lp = ys, norm, fin
+    return list(best[m.ctx:]), beams[best][1], float(best_lp)
 
 
 def ctc_greedy(logp: np.ndarray, blank: int = 0) -> Tuple[List[int], List[int], int]:

@@ -444,6 +444,57 @@ def test_ctc_projs_through_the_recognizers(built_lib):
     reco.Dispose()
 
 
+# ---- f4: hot words in the merge step --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["cluster_bf16x3", "perframe_fp32", "large_vocab_unfused"])
+def test_hotword_biasing_in_the_merge(built_lib, case):
+    """k2b_set_context_graph: the boost of a dense hot-word automaton applied inside the beam search's merge step (cluster kernel and
+    per-frame merge), against the oracle's biased search - offline (finalised), through the time-chunked host call, and streaming
+    (state carried in the beam pool, not finalised); other engines answer UNSUPPORTED; clearing the graph restores the plain search."""
+    from k2transducerasr_b200.hotwords import ContextGraph
+    if case == "large_vocab_unfused":
+        dims, bias, prec = synth.ModelDims(2100, 64, 32, 64), 0.5, "bf16x3"
+    else:
+        dims, bias, prec = MID, 0.99, ("fp32" if case == "perframe_fp32" else "bf16x3")
+    m, w = model_and_weights(dims, blank_bias=bias)
+    B, T, K = 12, 40, 4
+    raw = synth.make_frames(B, T, dims.encoder_dim, 1234)
+    enc = O.encoder_proj(m, raw)
+    plain = O.modified_beam_search(m, enc, K)
+    seen = [t for r in plain for t in r.appended]
+    words = [seen[0:2], seen[2:5], seen[6:7], seen[9:12], [dims.vocab_size - 1, dims.vocab_size - 2]]
+    g = ContextGraph.build(words, dims.vocab_size, 2.0)
+    want = O.modified_beam_search(m, enc, K, context_graph=g)
+    assert any(a.appended != b.appended or abs(a.score - b.score) > 1.0 for a, b in zip(plain, want))
+    h = make(dims, w, prec)
+    h.set_context_graph(g)
+    if case == "large_vocab_unfused":
+        with pytest.raises(_native.K2bError) as e:
+            h.modified_beam_search(raw, K, enc_is_raw=True)
+        assert e.value.status == _native.K2B_ERR_UNSUPPORTED
+        h.set_option("unfused_step", 1)
+    t, s, sc = h.modified_beam_search(raw, K, enc_is_raw=True)                # T >= 32 raw frames: the time-chunked host call
+    bp = h.debug_backpointers(B, T, K)
+    compare_streams(t, s, want, f"hot words {case}", allow_frac=0.2, scores=sc, bp=bp, T=T)
+    t2, s2, sc2 = h.modified_beam_search(enc, K, enc_is_raw=False)            # projected frames
+    compare_streams(t2, s2, want, f"hot words {case} projected", allow_frac=0.2, scores=sc2, T=T)
+    if case != "large_vocab_unfused":
+        # streaming: the automaton state travels with the hypotheses; results "so far" keep the boost of a match in progress
+        h.beam_pool_create(B, K, 64)
+        for sl in range(B):
+            h.beam_pool_reset(sl, None)                                       # offline seed {-1, blank}: same search as above
+        for lo, hi in ((0, 8), (8, 9), (9, 40)):
+            ts_, ss_, scs_, _ = h.modified_beam_search_online_chunk(np.ascontiguousarray(raw[:, lo:hi]), list(range(B)), cap=64, enc_is_raw=True)
+        want_s = O.modified_beam_search(m, enc, K, context_graph=g, finalize=False, extra_mask=1)
+        compare_streams(ts_, ss_, want_s, f"hot words {case} streaming", allow_frac=0.2, scores=scs_, T=T)
+    # greedy search is not biased; clearing the graph restores the plain beam search
+    gt, gs = h.greedy_offline(enc, _native.GREEDY_PER_STREAM, enc_is_raw=False)
+    compare_streams(gt, gs, O.greedy_search_batch(m, enc, compat=False), f"hot words {case}: greedy untouched", allow_frac=0.2, T=T)
+    h.set_context_graph(None)
+    t3, s3, sc3 = h.modified_beam_search(raw, K, enc_is_raw=True)
+    compare_streams(t3, s3, plain, f"hot words {case} cleared", allow_frac=0.2, scores=sc3, T=T)
+    h.close()
+
+
 # ---- host memory, overlap, multi-GPU gather, diagnostics ---------------------------------------------------------------------
 def test_pinned_host_buffers_and_async_results(built_lib):
     """k2b_host_alloc'ed frame / result buffers and "async_d2h": two batches in flight on one handle, completed by k2b_sync,
