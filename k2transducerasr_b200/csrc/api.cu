@@ -71,9 +71,10 @@ void free_buf(DevBuf& b) {
 void free_cluster_assets(k2b_handle* h) {
   if (h->wo_hi_img) cudaFree(h->wo_hi_img);
   if (h->wo_lo) cudaFree(h->wo_lo);
+  if (h->wo_hi_rows) cudaFree(h->wo_hi_rows);
   if (h->bias_pad) cudaFree(h->bias_pad);
   if (h->dec_tab) cudaFree(h->dec_tab);
-  h->wo_hi_img = nullptr; h->wo_lo = nullptr; h->bias_pad = nullptr; h->dec_tab = nullptr; h->dec_tab_state = 0;
+  h->wo_hi_img = nullptr; h->wo_lo = nullptr; h->wo_hi_rows = nullptr; h->bias_pad = nullptr; h->dec_tab = nullptr; h->dec_tab_state = 0;
   h->dec_tab_bytes = 0; h->dec_tab_build_ms = 0.f;
   h->tc_ready = false;
   if (h->we_hi_img) cudaFree(h->we_hi_img);
@@ -415,6 +416,7 @@ int32_t k2b_set_option(k2b_handle* h, const char* name, int32_t value) {
   else if (n == "unfused_step") h->opt_unfused_step = value;
   else if (n == "greedy_persistent") h->opt_greedy_persistent = value;
   else if (n == "pair") h->opt_pair = value;
+  else if (n == "wh_tmem_kb") h->opt_wh_tmem = value;
   else if (n == "prof_which") h->prof_which = value;
   else if (n == "async_d2h") h->opt_async_d2h = value;
   else if (n == "max_sym_per_frame") {

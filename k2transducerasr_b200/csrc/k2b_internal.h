@@ -78,6 +78,7 @@ struct k2b_handle {
   bool tc_ready = false;
   uint8_t* wo_hi_img = nullptr;   // [CS][J/64][16 KB] bf16 hi of out_w in the swizzled shared-memory image
   uint32_t* wo_lo = nullptr;      // [CS*128][J/2] bf16 lo of out_w, packed pairs (TMEM source)
+  uint32_t* wo_hi_rows = nullptr; // [CS*128][J/2] bf16 hi of out_w, packed pairs (TMEM source of the k-blocks kept in tensor memory)
   float* bias_pad = nullptr;      // [CS*128] out_b, -inf beyond V
   float* dec_tab = nullptr;       // [(V+1)*V, J] exp(2*decoder(y0,y1)): the memoised stateless decoder
   int dec_tab_state = 0;          // 0 not tried, 1 built, -1 does not fit (decoder GEMM per frame instead)
@@ -124,6 +125,7 @@ struct k2b_handle {
   int opt_unfused_step = 0;               // the three-launch frame step
   int opt_greedy_persistent = -1;         // -1 auto, 0 cluster kernel, 1 persistent kernel (greedy, 1024 < V <= 2048)
   int opt_pair = 0;                       // CTA-pair variant of the cluster kernel
+  int opt_wh_tmem = -1;                   // cluster kernel: k-blocks of W_hi held in tensor memory (-1 = balanced choice)
   int opt_async_d2h = 0;                  // host-pointer fused calls return without the final sync (pinned buffers; k2b_sync completes)
 };
 

@@ -30,6 +30,9 @@ namespace {
 
 using namespace ptx;
 
+#ifndef K2B_CLUSTER_MAXREG
+#define K2B_CLUSTER_MAXREG 96     // 17 warps: up to 120 would fit the register file
+#endif
 constexpr int kNH = 32;          // hypothesis rows per cluster (UMMA N)
 constexpr int kWorkers = 16;     // warps 0..15: prologue / read-out / reductions / merge
 constexpr int kCAll = (kWorkers + 1) * 32;   // + warp 16, which only issues MMAs
@@ -50,6 +53,8 @@ struct ClusterArgs {
   const float* dec_tab;     // [(V+1)*V, J]  exp(2*clamp(decoder(y0,y1)))
   const uint8_t* wo_hi_img; // [CS][J/64][128 x 128 B swizzled]
   const uint32_t* wo_lo;    // [CS*128][J/2] packed bf16 pairs
+  const uint32_t* wo_hi_rows;  // [CS*128][J/2] packed bf16 pairs (source of the W_hi k-blocks kept in tensor memory)
+  int nt;                   // the first nt k-blocks (64 joiner columns each) of W_hi live in TMEM, the others in shared memory
   const float* bias;        // [CS*128], -inf beyond V
   int B, T, K, V, J, S, CS, blank, unk, x3;
   int extra_mask;           // third non-emitting id (the literal 1 of ref OnlineRecognizer.cs:181), or -1
@@ -122,7 +127,8 @@ constexpr int kKeyNone = (int)0x80000000;
 // without a record contribute the neutral element) and every candidate is scored in the lane that loaded it. K rounds of
 // two REDUX then pick the stream's top K over K*V (value, then flat index). The K winners meet in a small per-warp scratch
 // (broadcast loads instead of shuffles) for the dedupe by token sequence (hash, length, context) and the log-add.
-template <int K>
+// CG: a context graph (hot words) is set - the only instantiation that touches the automaton state of the hypotheses.
+template <int K, bool CG>
 __device__ __forceinline__ void select_stream(int s, int V, int CS, const float* __restrict__ xb, const HypState& in,
                                               HypState& out, int blank, int unk, int extra_mask, int32_t* __restrict__ bp_row,
                                               int lane, const float* __restrict__ dec_tab, int J, bool do_prefetch,
@@ -152,7 +158,8 @@ __device__ __forceinline__ void select_stream(int s, int V, int CS, const float*
   if (nl == 0) {                                   // warp-uniform
     if (lane < K) {
       const int o = s * K + lane;
-      out.ctx0[o] = -1; out.ctx1[o] = blank; out.lp[o] = -INFINITY; out.len[o] = 2; out.hash[o] = kHashSeedC; out.cst[o] = 0;
+      out.ctx0[o] = -1; out.ctx1[o] = blank; out.lp[o] = -INFINITY; out.len[o] = 2; out.hash[o] = kHashSeedC;
+      if (CG) out.cst[o] = 0;
     }
     if (lane == 0) out.nlive[s] = 0;
     return;
@@ -247,10 +254,11 @@ __device__ __forceinline__ void select_stream(int s, int V, int CS, const float*
     for (int hh = 1; hh < K; ++hh) par += (my_f >= hh * V) ? 1 : 0;
     const int y = my_f - par * V;
     const int prow = s * K + par;
-    hs = in.hash[prow]; ln = in.len[prow]; c0 = in.ctx0[prow]; c1 = in.ctx1[prow]; cs = in.cst[prow];
+    hs = in.hash[prow]; ln = in.len[prow]; c0 = in.ctx0[prow]; c1 = in.ctx1[prow];
+    if (CG) cs = in.cst[prow];
     if (y != blank && y != unk && y != extra_mask) {
       tok = y; hs = hash_push_c(hs, y); ln += 1; c0 = c1; c1 = y;
-      if (cg_next != nullptr) {       // hot words: the boost goes to the extended hypothesis, after the top-K selection
+      if (CG) {                       // hot words: the boost goes to the extended hypothesis, after the top-K selection
         my_v += __ldg(cg_delta + (size_t)cs * V + y);
         cs = __ldg(cg_next + (size_t)cs * V + y);
       }
@@ -298,12 +306,14 @@ __device__ __forceinline__ void select_stream(int s, int V, int CS, const float*
   if (is_root) {
     const int slot = __popc(roots & ((1u << lane) - 1u));
     const int o = s * K + slot;
-    out.ctx0[o] = c0; out.ctx1[o] = c1; out.lp[o] = lp; out.len[o] = ln; out.hash[o] = hs; out.cst[o] = cs;
+    out.ctx0[o] = c0; out.ctx1[o] = c1; out.lp[o] = lp; out.len[o] = ln; out.hash[o] = hs;
+    if (CG) out.cst[o] = cs;
     if (bp_row != nullptr) bp_row[slot] = (par << 28) | (tok + 1);
   }
   if (lane >= nnew && lane < K) {
     const int o = s * K + lane;
-    out.ctx0[o] = -1; out.ctx1[o] = blank; out.lp[o] = -INFINITY; out.len[o] = 2; out.hash[o] = kHashSeedC; out.cst[o] = 0;
+    out.ctx0[o] = -1; out.ctx1[o] = blank; out.lp[o] = -INFINITY; out.len[o] = 2; out.hash[o] = kHashSeedC;
+    if (CG) out.cst[o] = 0;
     if (bp_row != nullptr) bp_row[lane] = 0;
   }
   if (lane == 0) out.nlive[s] = nnew;
@@ -321,8 +331,14 @@ __device__ __forceinline__ void select_stream(int s, int V, int CS, const float*
 // the 32 hypothesis rows (one per worker warp): half the decoder-row traffic, half the tanh / split work, half the stores.
 // The even CTA's MMA warp issues for both (its bar_q mbarriers also count the peer's warps, arriving through DSMEM), the
 // commit is multicast to both CTAs' bar_mma; everything after the accumulator read-out is unchanged.
-template <int K, bool X3, bool TIMED, bool PAIR>
-__global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
+//
+// NTC >= 0 (J = 512 only, not PAIR): the first NTC of the 8 k-blocks of W_hi are held in TENSOR MEMORY (beside W_lo and the
+// accumulator) and their products are TS MMAs; the MMA issue loop is fully unrolled with every descriptor a compile-time offset
+// from two uniform registers (a run-time split costs ~65 cycles of dependent uniform arithmetic per k-block on the issue chain,
+// more than it saves). NTC < 0: any J, everything of W_hi in shared memory.
+template <int K, bool X3, bool TIMED, bool PAIR, int NTC>
+__global__ void __maxnreg__(K2B_CLUSTER_MAXREG) cluster_beam_kernel(const ClusterArgs a) {
+  static_assert(NTC < 0 || (!PAIR && NTC <= 8 && 64 + (X3 ? 256 : 0) + 32 * NTC <= 512), "W_hi k-blocks in tensor memory: no room");
   constexpr int XWP = xw_padded(K);
   constexpr int S = kNH / K;
   constexpr int kRowsCta = PAIR ? 16 : 32;            // hypothesis rows this CTA builds
@@ -341,10 +357,11 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
   const bool worker = warp_u < kWorkers;
   const uint32_t rank = cluster_ctarank();
   const int cluster = blockIdx.x / a.CS;
-  const int J = a.J, V = a.V, CS = a.CS, T = a.T;
+  const int J = NTC >= 0 ? 512 : a.J, V = a.V, CS = a.CS, T = a.T;
   const int nkb = J / 64;
-  uint8_t* w_hi = smem;
-  uint8_t* xop = w_hi + (size_t)nkb * 16384;                          // nkb tiles of 64 rows x 128 B
+  const int nt = NTC >= 0 ? NTC : 0;                                  // W_hi k-blocks [0, nt) are read from tensor memory
+  uint8_t* w_hi = smem;                                               // k-blocks [nt, nkb): tiles of 128 rows x 128 B
+  uint8_t* xop = w_hi + (size_t)(nkb - nt) * 16384;                   // nkb tiles of 64 rows x 128 B
   float* Lt = reinterpret_cast<float*>(xop);                          // aliases the operand between MMA and next build
   float* xch = reinterpret_cast<float*>(xop + xop_region_bytes(nkb, kXTile, kLtStride));  // [2][CS][NH][XWP]
 
@@ -361,16 +378,31 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = tmem_slot;
-  // TMEM columns: accumulator 64 | (PAIR: second accumulator 32 for the W_lo product, whose column order differs) | W_lo 256
+  // TMEM columns: accumulator 64 | (PAIR: second accumulator 32 for the W_lo product, whose column order differs) | W_lo J/2
+  // (X3 only) | the first nt k-blocks of W_hi, 32 columns each
   const uint32_t t_d = tbase, t_d2 = tbase + 64, t_wlo = PAIR ? tbase + 128 : tbase + 64;
+  const uint32_t t_whi = X3 ? t_wlo + (uint32_t)(J / 2) : t_wlo;
   const uint32_t prank = PAIR ? (rank & 1u) : 0u;
   const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
 
   // ---- one-time staging of this CTA's weight slice ------------------------------------------------------
   if (tid == 0) {
-    mbar_expect_tx(&bar_w, (uint32_t)(nkb * 16384));
-    for (int kb = 0; kb < nkb; ++kb)
-      tma_bulk_g2s(w_hi + (size_t)kb * 16384, a.wo_hi_img + ((size_t)rank * nkb + kb) * 16384, 16384, &bar_w);
+    mbar_expect_tx(&bar_w, (uint32_t)((nkb - nt) * 16384));
+    for (int kb = nt; kb < nkb; ++kb)
+      tma_bulk_g2s(w_hi + (size_t)(kb - nt) * 16384, a.wo_hi_img + ((size_t)rank * nkb + kb) * 16384, 16384, &bar_w);
+  }
+  if (nt > 0 && warp < 4) {
+    const uint32_t* src = a.wo_hi_rows + ((size_t)rank * 128 + tid) * (J / 2);
+    for (int c0 = 0; c0 < nt * 32; c0 += 32) {
+      uint32_t v[32];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + c0) + q);
+        v[4 * q] = u.x; v[4 * q + 1] = u.y; v[4 * q + 2] = u.z; v[4 * q + 3] = u.w;
+      }
+      tmem_st32(t_whi + lane_base + (uint32_t)c0, v);
+    }
+    tmem_st_wait();
   }
   if (X3 && warp < 4) {
     const uint32_t* src = a.wo_lo + ((size_t)rank * 128 + tid) * (J / 2);
@@ -440,25 +472,48 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
     if (!PAIR || prank == 0) {
       for (int t = 0; t < T; ++t) {
         uint32_t acc = 0;
-        for (int qd = 0; qd < 4; ++qd) {
-          if (PAIR) { if (!mbar_wait_cluster(&bar_q[qd], (uint32_t)(t & 1))) ok = false; }
-          else { if (!mbar_wait(&bar_q[qd], (uint32_t)(t & 1))) ok = false; }
-          tc_fence_after();
-          for (int kb = 2 * qd; kb < 2 * qd + 2 && kb < nkb; ++kb) {
+        if constexpr (NTC >= 0) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t dw = ((uint64_t)desc_hi << 32) | (uint64_t)(w_lo0 + (uint32_t)(kb * (16384 >> 4) + k * 2));
-              const uint64_t dx = ((uint64_t)desc_hi << 32) | (uint64_t)(x_lo0 + (uint32_t)(kb * (kXTile >> 4) + k * 2));
-              if (PAIR) {
-                // pair MMA: columns [0,16) Wh*xh(rows of CTA 0), [16,32) Wh*xl(CTA 0), [32,48) Wh*xh(CTA 1), [48,64) Wh*xl(CTA 1);
-                // the W_lo product (each CTA supplies its 16 hi rows) goes to its own 32 columns
-                umma2_ss_e(t_d, dw, dx, X3 ? idesc64 : idesc32, acc, el);
-                if (X3) umma2_ts_e(t_d2, t_wlo + (uint32_t)((kb * 4 + k) * 8), dx, idesc32, acc, el);
-              } else {
-                umma_ss_e(t_d, dw, dx, X3 ? idesc64 : idesc32, acc, el);
+          for (int qd = 0; qd < 4; ++qd) {
+            if (!mbar_wait(&bar_q[qd], (uint32_t)(t & 1))) ok = false;
+            tc_fence_after();
+#pragma unroll
+            for (int kb = 2 * qd; kb < 2 * qd + 2; ++kb) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t dx = ((uint64_t)desc_hi << 32) | (uint64_t)(x_lo0 + (uint32_t)(kb * (kXTile >> 4) + k * 2));
+                if (kb < NTC) {
+                  umma_ts_e(t_d, t_whi + (uint32_t)((kb * 4 + k) * 8), dx, X3 ? idesc64 : idesc32, acc, el);
+                } else {
+                  const uint64_t dw = ((uint64_t)desc_hi << 32) | (uint64_t)(w_lo0 + (uint32_t)((kb - NTC) * (16384 >> 4) + k * 2));
+                  umma_ss_e(t_d, dw, dx, X3 ? idesc64 : idesc32, acc, el);
+                }
                 if (X3) umma_ts_e(t_d, t_wlo + (uint32_t)((kb * 4 + k) * 8), dx, idesc32, 1, el);
+                acc = 1;
               }
-              acc = 1;
+            }
+          }
+        } else {
+          for (int qd = 0; qd < 4; ++qd) {
+            if (PAIR) { if (!mbar_wait_cluster(&bar_q[qd], (uint32_t)(t & 1))) ok = false; }
+            else { if (!mbar_wait(&bar_q[qd], (uint32_t)(t & 1))) ok = false; }
+            tc_fence_after();
+            for (int kb = 2 * qd; kb < 2 * qd + 2 && kb < nkb; ++kb) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t dw = ((uint64_t)desc_hi << 32) | (uint64_t)(w_lo0 + (uint32_t)(kb * (16384 >> 4) + k * 2));
+                const uint64_t dx = ((uint64_t)desc_hi << 32) | (uint64_t)(x_lo0 + (uint32_t)(kb * (kXTile >> 4) + k * 2));
+                if (PAIR) {
+                  // pair MMA: columns [0,16) Wh*xh(rows of CTA 0), [16,32) Wh*xl(CTA 0), [32,48) Wh*xh(CTA 1), [48,64) Wh*xl(CTA 1);
+                  // the W_lo product (each CTA supplies its 16 hi rows) goes to its own 32 columns
+                  umma2_ss_e(t_d, dw, dx, X3 ? idesc64 : idesc32, acc, el);
+                  if (X3) umma2_ts_e(t_d2, t_wlo + (uint32_t)((kb * 4 + k) * 8), dx, idesc32, acc, el);
+                } else {
+                  umma_ss_e(t_d, dw, dx, X3 ? idesc64 : idesc32, acc, el);
+                  if (X3) umma_ts_e(t_d, t_wlo + (uint32_t)((kb * 4 + k) * 8), dx, idesc32, 1, el);
+                }
+                acc = 1;
+              }
             }
           }
         }
@@ -699,15 +754,20 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
             if (lane < K) {
               const int o = s * K + lane;
               st[cur ^ 1].ctx0[o] = st[cur].ctx0[o]; st[cur ^ 1].ctx1[o] = st[cur].ctx1[o]; st[cur ^ 1].lp[o] = st[cur].lp[o];
-              st[cur ^ 1].len[o] = st[cur].len[o]; st[cur ^ 1].hash[o] = st[cur].hash[o]; st[cur ^ 1].cst[o] = st[cur].cst[o];
+              st[cur ^ 1].len[o] = st[cur].len[o]; st[cur ^ 1].hash[o] = st[cur].hash[o];
+              if (a.cg_next != nullptr) st[cur ^ 1].cst[o] = st[cur].cst[o];
               if (bp_row != nullptr) bp_row[lane] = lane < st[cur].nlive[s] ? (lane << 28) : 0;
             }
             if (lane == 0) st[cur ^ 1].nlive[s] = st[cur].nlive[s];
             __syncwarp();
             continue;
           }
-          select_stream<K>(s, V, CS, xw, st[cur], st[cur ^ 1], a.blank, a.unk, a.extra_mask, bp_row, lane, a.dec_tab, J,
-                           (int)rank == (s % CS), sel_scr[warp], a.need_lp != 0, a.cg_next, a.cg_delta, (TIMED && timed) ? tph : nullptr);
+          if (K > 1 && a.cg_next != nullptr)
+            select_stream<K, true>(s, V, CS, xw, st[cur], st[cur ^ 1], a.blank, a.unk, a.extra_mask, bp_row, lane, a.dec_tab, J,
+                                   (int)rank == (s % CS), sel_scr[warp], a.need_lp != 0, a.cg_next, a.cg_delta, nullptr);
+          else
+            select_stream<K, false>(s, V, CS, xw, st[cur], st[cur ^ 1], a.blank, a.unk, a.extra_mask, bp_row, lane, a.dec_tab, J,
+                                    (int)rank == (s % CS), sel_scr[warp], a.need_lp != 0, nullptr, nullptr, (TIMED && timed) ? tph : nullptr);
         }
       }
       K2B_PHASE(6);
@@ -746,7 +806,8 @@ __global__ void __maxnreg__(96) cluster_beam_kernel(const ClusterArgs a) {
 
 // ---- weight-load-time packing ----------------------------------------------------------------------------------
 __global__ void pack_out_w_kernel(const float* __restrict__ out_w, const float* __restrict__ out_b, int V, int J, int CS,
-                                  uint8_t* __restrict__ img, uint32_t* __restrict__ lo, float* __restrict__ bias) {
+                                  uint8_t* __restrict__ img, uint32_t* __restrict__ lo, uint32_t* __restrict__ hi_rows,
+                                  float* __restrict__ bias) {
   const int row = blockIdx.x;            // 0 .. CS*128-1
   const int c = row >> 7, r = row & 127, nkb = J / 64;
   if (threadIdx.x == 0) bias[row] = row < V ? out_b[row] : -INFINITY;
@@ -757,6 +818,7 @@ __global__ void pack_out_w_kernel(const float* __restrict__ out_w, const float* 
     const size_t off = ((size_t)c * nkb + (k >> 6)) * 16384 + ptx::sw128_offset(r, k & 63);
     *reinterpret_cast<uint32_t*>(img + off) = ptx::pack_bf16x2(h0, h1);
     lo[(size_t)row * (J / 2) + (k >> 1)] = ptx::pack_bf16x2(x0 - h0, x1 - h1);
+    hi_rows[(size_t)row * (J / 2) + (k >> 1)] = ptx::pack_bf16x2(h0, h1);
   }
 }
 
@@ -792,25 +854,44 @@ __global__ void exp2x_chunk_kernel(const float4* __restrict__ in, float4* __rest
 // `pair`: CTA-pair variant (even cluster sizes), opt-in with K2B_PAIR=1: measured on cfg2 it halves the prologue (quarters
 // 1053 + 742 + 368 + 325 cycles against 1169 + 1028 + 474 + 438) but a cta_group::2 MMA at N <= 64 costs ~70 cycles against
 // ~57 for the single-CTA form, so the step gets longer (1449 us per launch against 1383 us).
-template <bool X3, bool PAIR>
+template <bool X3, bool PAIR, int NTC>
 static void (*cluster_kernel_kx(int K))(const ClusterArgs) {
-  return K == 1 ? cluster_beam_kernel<1, X3, false, PAIR> : (K == 2 ? cluster_beam_kernel<2, X3, false, PAIR>
-       : (K == 4 ? cluster_beam_kernel<4, X3, false, PAIR> : cluster_beam_kernel<8, X3, false, PAIR>));
+  return K == 1 ? cluster_beam_kernel<1, X3, false, PAIR, NTC> : (K == 2 ? cluster_beam_kernel<2, X3, false, PAIR, NTC>
+       : (K == 4 ? cluster_beam_kernel<4, X3, false, PAIR, NTC> : cluster_beam_kernel<8, X3, false, PAIR, NTC>));
 }
-static void (*cluster_kernel_for(int K, bool x3, bool timed, bool pair))(const ClusterArgs) {
+// W_hi k-blocks in tensor memory (J = 512): as many as fit beside the accumulator and W_lo
+constexpr int kNtX3 = 6, kNtBf16 = 8;
+// `nt` > 0 selects the instantiation with that many W_hi k-blocks in tensor memory (cluster_plan only offers kNtX3 / kNtBf16)
+static void (*cluster_kernel_for(int K, bool x3, bool timed, bool pair, int nt))(const ClusterArgs) {
   if (timed && K == 4) {
-    if (pair) return x3 ? cluster_beam_kernel<4, true, true, true> : cluster_beam_kernel<4, false, true, true>;
-    return x3 ? cluster_beam_kernel<4, true, true, false> : cluster_beam_kernel<4, false, true, false>;
+    if (pair) return x3 ? cluster_beam_kernel<4, true, true, true, -1> : cluster_beam_kernel<4, false, true, true, -1>;
+    if (nt > 0) return x3 ? cluster_beam_kernel<4, true, true, false, kNtX3> : cluster_beam_kernel<4, false, true, false, kNtBf16>;
+    return x3 ? cluster_beam_kernel<4, true, true, false, -1> : cluster_beam_kernel<4, false, true, false, -1>;
   }
-  if (timed && K == 1 && x3 && !pair) return cluster_beam_kernel<1, true, true, false>;
-  if (pair) return x3 ? cluster_kernel_kx<true, true>(K) : cluster_kernel_kx<false, true>(K);
-  return x3 ? cluster_kernel_kx<true, false>(K) : cluster_kernel_kx<false, false>(K);
+  if (timed && K == 1 && x3 && !pair && nt == 0) return cluster_beam_kernel<1, true, true, false, -1>;
+  if (pair) return x3 ? cluster_kernel_kx<true, true, -1>(K) : cluster_kernel_kx<false, true, -1>(K);
+  if (nt > 0) return x3 ? cluster_kernel_kx<true, false, kNtX3>(K) : cluster_kernel_kx<false, false, kNtBf16>(K);
+  return x3 ? cluster_kernel_kx<true, false, -1>(K) : cluster_kernel_kx<false, false, -1>(K);
 }
 static bool cluster_pair_mode(const k2b_handle* h, int CS) { return CS % 2 == 0 && h->opt_pair != 0; }
 
-static size_t cluster_dyn_smem(int J, int CS, int K) {
+static size_t cluster_dyn_smem(int J, int CS, int K, int nt = 0) {
   const int nkb = J / 64;
-  return (size_t)nkb * 16384 + xop_region_bytes(nkb, 64 * 128, kLtStride) + 2ull * CS * kNH * xw_padded(K) * 4;
+  return (size_t)(nkb - nt) * 16384 + xop_region_bytes(nkb, 64 * 128, kLtStride) + 2ull * CS * kNH * xw_padded(K) * 4;
+}
+
+// Where the A operand lives. Measured on cfg2 (tools/time_cluster_variants.py, profiles/r02_cluster_placement.txt): every k-block
+// of W_hi that is read from tensor memory instead of shared memory (a TS MMA instead of an SS one) takes ~130 cycles off the 64-MMA
+// issue chain of a frame step, so at J = 512 as many as fit beside the accumulator and W_lo go there (6 of 8 with split-bf16 x3,
+// all 8 in single-pass bf16) - and the shared memory they free lets V up to 1024 with beam 8 fit.
+// k2b_set_option("wh_tmem_kb", 0) keeps everything in shared memory (comparison runs); other joiner widths always do.
+struct ClusterPlan { int nt; size_t dyn; };
+static ClusterPlan cluster_plan(const k2b_handle* h, int K, bool pair) {
+  const k2b_config& c = h->cfg;
+  const int J = c.joiner_dim, CS = (c.vocab_size + 127) / 128;
+  const bool x3 = c.precision == K2B_PREC_BF16X3;
+  int nt = (J == 512 && !pair && h->opt_wh_tmem != 0) ? (x3 ? kNtX3 : kNtBf16) : 0;
+  return ClusterPlan{nt, cluster_dyn_smem(J, CS, K, nt)};
 }
 
 // V <= 1024: portable clusters of up to 8 CTAs, beams 1/2/4/8. 1024 < V <= 2048: 16-CTA (non-portable) clusters, greedy
@@ -821,15 +902,16 @@ bool cluster_path_supported(const k2b_handle* h, int K) {
   if (c.vocab_size > 2048 || c.joiner_dim > 512 || c.joiner_dim % 64) return false;
   if (K != 1 && K != 2 && K != 4 && K != 8) return false;
   if (CS > 8 && K != 1) return false;
-  const size_t dyn = cluster_dyn_smem(c.joiner_dim, CS, K);
-  if (dyn + 8192 > 227 * 1024) return false;
+  const size_t dyn = cluster_plan(h, K, cluster_pair_mode(h, CS)).dyn;
+  if (dyn + 7424 > 227 * 1024) return false;
   const size_t tab = (size_t)(c.vocab_size + 1) * c.vocab_size * c.joiner_dim * sizeof(float);
   if (tab > ((size_t)16 << 30)) return false;
   if (CS > 8) {
     k2b_handle* hm = const_cast<k2b_handle*>(h);
     if (hm->cluster16_ok < 0) {
       hm->cluster16_ok = 0;
-      auto kern = cluster_kernel_for(1, c.precision == K2B_PREC_BF16X3, false, cluster_pair_mode(h, CS));
+      auto kern = cluster_kernel_for(1, c.precision == K2B_PREC_BF16X3, false, cluster_pair_mode(h, CS),
+                                     cluster_plan(h, 1, cluster_pair_mode(h, CS)).nt);
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
           cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) == cudaSuccess) {
         cudaLaunchConfig_t cfg = {};
@@ -929,8 +1011,9 @@ int32_t ensure_cluster_assets(k2b_handle* h) {
   // (a retry after a failed allocation below re-uses what the earlier attempt obtained)
   if (h->wo_hi_img == nullptr) K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->wo_hi_img), rows * J * 2));
   if (h->wo_lo == nullptr) K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->wo_lo), rows * J * 2));
+  if (h->wo_hi_rows == nullptr) K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->wo_hi_rows), rows * J * 2));
   if (h->bias_pad == nullptr) K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->bias_pad), rows * sizeof(float)));
-  pack_out_w_kernel<<<(unsigned)rows, 128, 0, h->stream>>>(h->out_w, h->out_b, V, J, CS, h->wo_hi_img, h->wo_lo, h->bias_pad);
+  pack_out_w_kernel<<<(unsigned)rows, 128, 0, h->stream>>>(h->out_w, h->out_b, V, J, CS, h->wo_hi_img, h->wo_lo, h->wo_hi_rows, h->bias_pad);
   K2B_LAUNCH_CHECK(h);
   h->tc_ready = true;
   return K2B_OK;
@@ -975,8 +1058,10 @@ int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, 
     if (a.io_cst == nullptr) return K2B_ERR_CUDA;
   }
   a.bp = bp; a.fin_lp = fin_lp; a.fin_len = fin_len; a.fin_nlive = fin_nlive; a.status = status;
-  const size_t dyn = cluster_dyn_smem(J, CS, K);
-  void (*kern)(const ClusterArgs) = cluster_kernel_for(K, a.x3 != 0, a.timing != nullptr, cluster_pair_mode(h, CS));
+  const ClusterPlan plan = cluster_plan(h, K, cluster_pair_mode(h, CS));
+  a.wo_hi_rows = h->wo_hi_rows; a.nt = plan.nt;
+  const size_t dyn = plan.dyn;
+  void (*kern)(const ClusterArgs) = cluster_kernel_for(K, a.x3 != 0, a.timing != nullptr, cluster_pair_mode(h, CS), plan.nt);
   if (CS > 8) K2B_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   K2B_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   cudaLaunchConfig_t cfg = {};
