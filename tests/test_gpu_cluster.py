@@ -192,6 +192,25 @@ def test_cta_pair_variant_matches_oracle(setup, monkeypatch, prec):
     h.close()
 
 
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+def test_w_hi_in_tensor_memory_is_bit_identical(setup, prec):
+    """J = 512: six (split-bf16 x3) / all eight (bf16) k-blocks of W_hi are read from tensor memory by TS MMAs in a fully unrolled
+    issue loop; k2b_set_option("wh_tmem_kb", 0) selects the general kernel (everything in shared memory, SS MMAs). Same products,
+    same accumulation order: tokens, timestamps and scores must be identical bit for bit, for every beam and for greedy."""
+    m, w, raw, enc = setup
+    h = make(MID, w, prec)
+    for beam in (4, 1, 2, 8):
+        h.set_option("wh_tmem_kb", -1)
+        t1, s1, sc1 = h.modified_beam_search(raw, beam)
+        g1, gs1 = h.greedy_offline(enc, _native.GREEDY_PER_STREAM, enc_is_raw=False)
+        h.set_option("wh_tmem_kb", 0)
+        t0, s0, sc0 = h.modified_beam_search(raw, beam)
+        g0, gs0 = h.greedy_offline(enc, _native.GREEDY_PER_STREAM, enc_is_raw=False)
+        assert t1 == t0 and s1 == s0 and np.array_equal(np.asarray(sc1), np.asarray(sc0)), f"{prec} beam {beam}"
+        assert g1 == g0 and gs1 == gs0
+    h.close()
+
+
 @pytest.mark.parametrize("prec", ["bf16x3", "fp32"])
 def test_ragged_lengths_freeze_streams(setup, prec):
     """k2b_set_encoder_out_lens (the seam's encoder_out_lens, which the reference never consumes): stream b is decoded over its
