@@ -52,8 +52,9 @@ METRICS = {
     "cfg4": "encoder frames/sec decoded (modified_beam_search beam=4, batch 256/GPU, vocab 5537)",
     "cfg5": "encoder frames/sec decoded (CTC greedy, 128 streams/GPU)",
 }
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (ncu --set full captures under profiles/)
-TRAFFIC = {"cfg2": 247.2e6, "cfg4": 342.3e6, "cfg5": None, "cfg1": None, "cfg3": None}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (ncu --set full captures under profiles/:
+# cfg2 r02_cluster_beam_wh_tmem_full.ncu-rep, cfg4 r01_beam_mega_cfg4_T250_full.ncu-rep)
+TRAFFIC = {"cfg2": 247.8e6, "cfg4": 342.3e6, "cfg5": None, "cfg1": None, "cfg3": None}
 
 
 def load_peaks():

@@ -37,6 +37,7 @@ constexpr int kNH = 32;          // hypothesis rows per cluster (UMMA N)
 constexpr int kWorkers = 16;     // warps 0..15: prologue / read-out / reductions / merge
 constexpr int kCAll = (kWorkers + 1) * 32;   // + warp 16, which only issues MMAs
 constexpr int kLtStride = 33;
+constexpr int kBpSteps = 32;     // back-pointer rows are collected in shared memory and written out every kBpSteps frames
 constexpr uint64_t kHashSeedC = 0x9E3779B97F4A7C15ull;
 
 struct HypState {
@@ -162,6 +163,7 @@ __device__ __forceinline__ void select_stream(int s, int V, int CS, const float*
       if (CG) out.cst[o] = 0;
     }
     if (lane == 0) out.nlive[s] = 0;
+    if (bp_row != nullptr && lane < K) bp_row[lane] = 0;
     return;
   }
   K2B_SUB(8);
@@ -351,6 +353,10 @@ __global__ void __maxnreg__(K2B_CLUSTER_MAXREG) cluster_beam_kernel(const Cluste
   __shared__ uint64_t xbar[2];                    // partials of frame t (buffer t & 1): 16 local warps + remote st.async bytes
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) uint32_t sel_scr[kWorkers][8 * K];   // per-warp winner exchange of the merge
+  // back-pointer rows of the last kBpSteps frames (CTA 0 of the cluster): a global store per winner inside the merge cost ~100
+  // cycles of every step (address arithmetic + the store on the merge warp's chain); every kBpSteps frames all worker warps write
+  // the block out in 512-byte runs instead
+  __shared__ int32_t bp_ring[kBpSteps][kNH];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);     // the compiler knows this one is warp-uniform
@@ -748,7 +754,7 @@ __global__ void __maxnreg__(K2B_CLUSTER_MAXREG) cluster_beam_kernel(const Cluste
         K2B_PHASE(5);
         for (int s = warp; s < S; s += kWorkers) {
           const int g = cluster * S + s;
-          int32_t* bp_row = (rank == 0 && g < a.B) ? a.bp + ((size_t)g * a.Ttot + a.t0 + t) * K : nullptr;
+          int32_t* bp_row = (rank == 0) ? &bp_ring[t & (kBpSteps - 1)][s * K] : nullptr;
           if (a.lens != nullptr && g < a.B && a.t0 + t >= a.lens[g]) {
             // past the end of this stream (ragged batch): the hypotheses stay as they are, the back-pointers are the identity
             if (lane < K) {
@@ -773,6 +779,15 @@ __global__ void __maxnreg__(K2B_CLUSTER_MAXREG) cluster_beam_kernel(const Cluste
       K2B_PHASE(6);
       named_bar_sync(1, kWorkers * 32);
       cur ^= 1;
+      if (rank == 0 && ((t & (kBpSteps - 1)) == kBpSteps - 1 || t == T - 1)) {
+        // bp [B, Ttot, K]: the (step, slot) entries of one stream are contiguous
+        const int t_first = t & ~(kBpSteps - 1), per = (t - t_first + 1) * K;
+        for (int i = tid; i < S * per; i += kWorkers * 32) {
+          const int s = i / per, rem = i - s * per, step = rem / K, k = rem - step * K;
+          const int g = cluster * S + s;
+          if (g < a.B) a.bp[((size_t)g * a.Ttot + a.t0 + t_first + step) * K + k] = bp_ring[step][s * K + k];
+        }
+      }
       K2B_PHASE(7);
     }
     if (timed) for (int i = 0; i < 20; ++i) a.timing[i] = tph[i];
@@ -903,7 +918,7 @@ bool cluster_path_supported(const k2b_handle* h, int K) {
   if (K != 1 && K != 2 && K != 4 && K != 8) return false;
   if (CS > 8 && K != 1) return false;
   const size_t dyn = cluster_plan(h, K, cluster_pair_mode(h, CS)).dyn;
-  if (dyn + 7424 > 227 * 1024) return false;
+  if (dyn + 12288 > 227 * 1024) return false;      // + the kernel's static shared memory (7 - 11.5 KB)
   const size_t tab = (size_t)(c.vocab_size + 1) * c.vocab_size * c.joiner_dim * sizeof(float);
   if (tab > ((size_t)16 << 30)) return false;
   if (CS > 8) {
