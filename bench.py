@@ -362,7 +362,7 @@ class Work:
             bytes_per_launch = float(B) * T * self.V * 4
             gbs = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if n_launch else 0.0
             return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                    "traffic": TRAFFIC.get(self.args.workload), "kernel": "ctc_greedy_kernel (argmax + collapse, one launch)",
+                    "traffic": TRAFFIC.get(self.args.workload), "kernel": "ctc_frames_kernel (per-frame argmax, persistent) + ctc_collapse_kernel (programmatic dependent launch)",
                     "avg_launch_us": avg_ms * 1e3, "launches_timed": n_launch, "bytes_per_launch": bytes_per_launch,
                     "bytes_per_frame": self.V * 4, "peak_source": peaks["src"] + ", copy bandwidth"}
         rows = B * (self.K if cfg.mode == "mbs" else 1)

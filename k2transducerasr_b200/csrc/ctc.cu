@@ -8,18 +8,23 @@
 // log_softmax is monotone per frame, so the argmax of log-probs needs no normalisation pass: the kernel
 // reads every fp32 score exactly once (V*4 algorithmic bytes per frame) with 128-bit streaming loads.
 //
-// Grid: PERSISTENT - as many CTAs as are co-resident (occupancy x SMs), eight warps each; frames are handed out eight at a time
-// (one per warp) from a global counter whose next value is fetched one round ahead. A grid of one CTA per (stream, 32-frame
-// segment) runs cfg5's 128-stream shard as 1024 CTAs = 1.15 waves of 888 resident CTAs: the second wave has 2 MB in flight instead
-// of 14 and takes as long as the first (61 us per launch, 64 % of the HBM peak); handing frames out dynamically removes that tail.
-// A warp reduces a whole frame: coalesced 128-bit streaming loads, eight in flight per lane; the fold costs 2.5 instructions per
-// score (three FMNMX per 16-byte group - they skip NaN like .NET's Max - one strict compare, and predicated copies of the winning
-// group), because at the ~10 instructions per score of an element-wise compare-and-select the schedulers, not the memory, set
-// the pace (ncu: issue slots 50 % busy at 60 % of the HBM peak). The per-frame ids go to a small scratch; every frame posts a
-// ticket for its stream with a release-atomic whose RESULT is only looked at one frame later (no round trip on the warp's
-// chain); the warp that learns it posted a stream's last ticket runs the order-dependent collapse for that stream with warp
-// ballots - no second launch, and the collapses are spread over the kernel instead of forming a tail.
+// Two forms (ctc_greedy_dev picks by input size):
+//  * frames + collapse (inputs of 12 MB and more): `ctc_frames_kernel`, a PERSISTENT grid - two CTAs of eight warps per SM, frames
+//    handed out eight at a time (one per warp) from a global counter whose next value is fetched one round ahead - in which a warp
+//    reduces a whole frame with ALL of its 128-bit streaming loads in flight at once (16 per lane at V = 2000: one memory round trip
+//    per frame) and posts nothing but the frame's id; `ctc_collapse_kernel` (one warp per stream: ballots for the order-dependent
+//    blank / repeat collapse) is chained to it by a programmatic dependent launch and is resident, waiting, when the last frame is
+//    reduced. cfg5's shard (128 streams = 256 MB): 46 us = 5.6 TB/s (torch.sum over the same bytes: 48 us); 1024 streams: 288 us =
+//    7.1 TB/s (a pure read runs above the copy figure MEASURED_PEAKS.json holds).
+//  * one kernel (small inputs, where a second launch costs more than it saves): `ctc_greedy_kernel`, the same hand-out with eight
+//    loads per lane and batch, every frame posting a ticket for its stream with a release-atomic whose RESULT is looked at one frame
+//    later; the warp that learns it posted a stream's last ticket runs the collapse. Round 2 measured what that costs at 256 MB
+//    (62 us): the release is a MEMBAR.ALL.GPU on every frame's chain, the loop state spills at 64 registers, a frame is two
+//    dependent round trips, and 4736 resident warps x 4 KB in flight make a frame - and therefore the tail - ~9 us long.
+// The fold costs 2.5 instructions per score (three FMNMX per 16-byte group - they skip NaN like .NET's Max - one strict compare, and
+// predicated copies of the winning group); a frame whose maximum is -inf or NaN-only is re-done by an exact slow path.
 #include "k2b_internal.h"
+#include "sm100_ptx.cuh"
 
 namespace k2b {
 
@@ -72,6 +77,7 @@ __device__ __noinline__ int frame_argmax_slow(const float* __restrict__ row, int
 // First index of the maximum of one frame (one warp). Strict '>' in index order keeps the first of equal maxima inside a lane,
 // `pick` across lanes. A frame whose maximum is -inf (or that holds nothing but NaN) is not decided by the fold (-inf > -inf is
 // false) and takes the exact slow path - log-probs of real models never do.
+template <int NB>      // 128-bit loads in flight per lane and batch
 __device__ __forceinline__ int frame_argmax(const float* __restrict__ row, int V, int lane) {
   // rows are only 4-byte aligned in general (V = 5537): scalar head up to the next 16-byte boundary
   const int head = min(V, (int)(((16u - (unsigned)((uintptr_t)row & 15u)) & 15u) >> 2));
@@ -87,19 +93,19 @@ __device__ __forceinline__ int frame_argmax(const float* __restrict__ row, int V
     bv = u_ ? m_ : bv; bq = u_ ? (qq) : bq; bx.x = u_ ? (v4_).x : bx.x; bx.y = u_ ? (v4_).y : bx.y; bx.z = u_ ? (v4_).z : bx.z; \
     bx.w = u_ ? (v4_).w : bx.w; } while (0)
   int qb = 0;                          // warp-uniform batch base: every batch is one round trip for the whole warp
-  for (; qb + 256 <= nvec; qb += 256) {   // 8 independent 128-bit loads in flight per lane
-    float4 x[8];
+  for (; qb + 32 * NB <= nvec; qb += 32 * NB) {   // NB independent 128-bit loads in flight per lane
+    float4 x[NB];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) x[u] = ld_stream(vp + qb + lane + 32 * u);
+    for (int u = 0; u < NB; ++u) x[u] = ld_stream(vp + qb + lane + 32 * u);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) K2B_FOLD(x[u], qb + lane + 32 * u);
+    for (int u = 0; u < NB; ++u) K2B_FOLD(x[u], qb + lane + 32 * u);
   }
-  if (qb < nvec) {                     // the rest of the row: up to 8 more loads, issued together as well
-    float4 x[8];
+  if (qb < nvec) {                     // the rest of the row: up to NB more loads, issued together as well
+    float4 x[NB];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) if (qb + lane + 32 * u < nvec) x[u] = ld_stream(vp + qb + lane + 32 * u);
+    for (int u = 0; u < NB; ++u) if (qb + lane + 32 * u < nvec) x[u] = ld_stream(vp + qb + lane + 32 * u);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) if (qb + lane + 32 * u < nvec) K2B_FOLD(x[u], qb + lane + 32 * u);
+    for (int u = 0; u < NB; ++u) if (qb + lane + 32 * u < nvec) K2B_FOLD(x[u], qb + lane + 32 * u);
   }
 #undef K2B_FOLD
   if (bq >= 0) {                       // the body beat the head: first position of bv inside its group
@@ -200,7 +206,7 @@ ctc_greedy_kernel(const float* __restrict__ logp, int B, int T, int V, int blank
       const long long f = base + warp + (long long)g * kWarps;
       if (f >= total) break;
       const int b = (int)(f / T);
-      const int y = frame_argmax(logp + (size_t)f * V, V, lane);
+      const int y = frame_argmax<8>(logp + (size_t)f * V, V, lane);
       retire();
       if (lane == 0) {
         ybuf[f] = y;
@@ -218,71 +224,47 @@ ctc_greedy_kernel(const float* __restrict__ logp, int B, int T, int V, int blank
   }
 }
 
-// Large inputs (four or more waves of CTAs): one CTA per (stream, 32-frame segment), the hardware's CTA scheduler deals the
-// work, a warp walks four frames on its own (no barrier, no ticket per frame), the last CTA of a stream collapses. Measured at 1024
-// streams x 250 frames x V = 2000 (2 GB): 313 us = 6.5 TB/s, against 365 us for the persistent kernel above, whose frame-by-frame
-// hand-out only pays when the grid is a wave or two (cfg5's 128-stream shard: 58-61 us against 61-65 us).
-constexpr int kSeg = 32;       // frames per CTA
-__global__ void __launch_bounds__(kWarps * 32)
-ctc_greedy_seg_kernel(const float* __restrict__ logp, int B, int T, int V, int blank, int nseg,
-                  const int32_t* __restrict__ frame_offset, int64_t* __restrict__ prev_inout,
-                  int64_t* __restrict__ tokens, int32_t* __restrict__ ts, int32_t* __restrict__ n_out,
-                  int32_t* __restrict__ trailing_inout, int cap, int32_t* __restrict__ ybuf,
-                  int32_t* __restrict__ ticket) {
-  const int b = blockIdx.x / nseg, seg = blockIdx.x - b * nseg;
+// ---- round 2, second session: the per-frame work and the order-dependent part as TWO kernels chained by a programmatic dependent
+// launch. What ncu showed on the one-kernel version at cfg5's shard (128 streams = 256 MB, 62 us): the release-atomic ticket of
+// every frame is a MEMBAR.ALL.GPU on the warp's chain (stall_membar 2.6 warps per issue cycle), the loop state spills (15 STL +
+// 18 LDL per frame at 64 registers), a frame is two dependent load round trips, and with 4736 resident warps x 4 KB in flight
+// (19 MB) the queueing delay makes a frame ~9 us long - which is also the length of the tail. Here a frame is ONE round trip (all
+// of its 128-bit loads - 16 per lane at V = 2000 - are issued before the first fold; two CTAs per SM, 128 registers, no spills),
+// the frame kernel posts nothing but the per-frame id (no ticket, no fence, no 64-bit division), and the collapse kernel (one warp
+// per stream) is launched with programmatic stream serialisation: it is resident and waiting when the last frame is reduced.
+__global__ void __launch_bounds__(kWarps * 32, 2)
+ctc_frames_kernel(const float* __restrict__ logp, long long total, int V, int32_t* __restrict__ ybuf, int32_t* __restrict__ sched) {
+  __shared__ int s_base[2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t_end = min(T, (seg + 1) * kSeg);
-
-  for (int t = seg * kSeg + warp; t < t_end; t += kWarps) {
-    const float* row = logp + ((size_t)b * T + t) * V;
-    // rows are only 4-byte aligned in general (V = 5537): scalar head up to the next 16-byte boundary
-    const int head = min(V, (int)(((16u - (unsigned)((uintptr_t)row & 15u)) & 15u) >> 2));
-    const int nvec = (V - head) >> 2;
-    const int tail0 = head + (nvec << 2);
-    Arg best{0.f, -1};
-    if (lane < head) take(best, __ldg(row + lane), lane);
-    const float4* vp = reinterpret_cast<const float4*>(row + head);
-    int q = lane;
-    for (; q + 96 < nvec; q += 128) {   // 4 independent 128-bit loads in flight per lane
-      const float4 x0 = ld_stream(vp + q), x1 = ld_stream(vp + q + 32), x2 = ld_stream(vp + q + 64),
-                   x3 = ld_stream(vp + q + 96);
-      int i = head + 4 * q;
-      take(best, x0.x, i); take(best, x0.y, i + 1); take(best, x0.z, i + 2); take(best, x0.w, i + 3);
-      i += 128;
-      take(best, x1.x, i); take(best, x1.y, i + 1); take(best, x1.z, i + 2); take(best, x1.w, i + 3);
-      i += 128;
-      take(best, x2.x, i); take(best, x2.y, i + 1); take(best, x2.z, i + 2); take(best, x2.w, i + 3);
-      i += 128;
-      take(best, x3.x, i); take(best, x3.y, i + 1); take(best, x3.z, i + 2); take(best, x3.w, i + 3);
+  ptx::griddep_launch_dependents();     // the collapse grid may take its SM slots as soon as they free up; it waits for this grid
+  if (threadIdx.x == 0) s_base[0] = atomicAdd(&sched[0], kWarps);
+  for (int round = 0;; ++round) {
+    __syncthreads();
+    const long long base = s_base[round & 1];
+    if (base >= total) break;                                                 // CTA-uniform
+    int next = 0;
+    if (threadIdx.x == 0) next = atomicAdd(&sched[0], kWarps);                // next round's frames: fetched behind this round's loads
+    const long long f = base + warp;
+    if (f < total) {
+      const int y = frame_argmax<16>(logp + (size_t)f * V, V, lane);
+      if (lane == 0) ybuf[f] = y;
     }
-    for (; q < nvec; q += 32) {
-      const float4 x = ld_stream(vp + q);
-      const int i = head + 4 * q;
-      take(best, x.x, i); take(best, x.y, i + 1); take(best, x.z, i + 2); take(best, x.w, i + 3);
-    }
-    if (tail0 + lane < V) take(best, __ldg(row + tail0 + lane), tail0 + lane);
-    // a lane's indices are not monotone across head/body/tail only in the sense head < body < tail: fine.
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
-      Arg o;
-      o.v = __shfl_xor_sync(0xffffffffu, best.v, s);
-      o.i = __shfl_xor_sync(0xffffffffu, best.i, s);
-      best = pick(best, o);
-    }
-    if (lane == 0) ybuf[(size_t)b * T + t] = best.i < 0 ? 0 : best.i;  // all-NaN frame -> index 0
+    if (threadIdx.x == 0) s_base[(round + 1) & 1] = next;
   }
+  // the last CTA to leave re-arms the frame counter (every CTA has made its final, failing, grab by then)
+  if (threadIdx.x == 0 && atomicAdd(&sched[1], 1) == (int)gridDim.x - 1) {
+    sched[0] = 0;
+    sched[1] = 0;
+  }
+}
 
-  // ---- ticket: the last CTA of this stream collapses ------------------------------------------
-  __shared__ int s_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&ticket[b], 1) == nseg - 1) ? 1 : 0;
-  __syncthreads();
-  if (!s_last || warp != 0) return;
-  __threadfence();
-
-  collapse_stream(b, T, blank, lane, frame_offset, prev_inout, tokens, ts, n_out, trailing_inout, cap, ybuf);
-  if (lane == 0) ticket[b] = 0;  // ready for the next launch
+__global__ void __launch_bounds__(kWarps * 32)
+ctc_collapse_kernel(int B, int T, int blank, const int32_t* __restrict__ frame_offset, int64_t* __restrict__ prev_inout,
+                    int64_t* __restrict__ tokens, int32_t* __restrict__ ts, int32_t* __restrict__ n_out,
+                    int32_t* __restrict__ trailing_inout, int cap, const int32_t* __restrict__ ybuf) {
+  const int b = blockIdx.x * kWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  ptx::griddep_wait();                  // every frame id of the frame kernel is written and visible
+  if (b < B) collapse_stream(b, T, blank, lane, frame_offset, prev_inout, tokens, ts, n_out, trailing_inout, cap, ybuf);
 }
 
 }  // namespace
@@ -307,24 +289,35 @@ int32_t ctc_greedy_dev(k2b_handle* h, const float* logp, int B, int T, int V, in
   int32_t* sched = static_cast<int32_t*>(h->ws_ctc.p);
   int32_t* ticket = reinterpret_cast<int32_t*>(static_cast<char*>(h->ws_ctc.p) + tick_off);
   int32_t* ybuf = reinterpret_cast<int32_t*>(static_cast<char*>(h->ws_ctc.p) + ybuf_off);
+  const long long rounds = ((long long)B * T + kWarps - 1) / kWarps;
+  const double bytes = (double)B * T * V * sizeof(float);
+  // small inputs (measured crossover between 8 and 16 MB, tools/run_ctc_shard.py): one kernel with tickets - a second launch costs
+  // more than the fences; everything else: frames + collapse as two kernels chained by a programmatic dependent launch
+  const bool one_kernel = h->opt_ctc_one_kernel >= 0 ? h->opt_ctc_one_kernel == 1 : bytes < 12e6;
+  if (!one_kernel) {
+    static int per_sm2 = 0;
+    if (per_sm2 == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, ctc_frames_kernel, kWarps * 32, 0) != cudaSuccess || per_sm2 < 1)) {
+      cudaGetLastError();
+      per_sm2 = 2;
+    }
+    const long long nblk2 = rounds < (long long)per_sm2 * h->sm_count ? rounds : (long long)per_sm2 * h->sm_count;
+    prof_begin(h);
+    ctc_frames_kernel<<<(unsigned)nblk2, kWarps * 32, 0, h->stream>>>(logp, (long long)B * T, V, ybuf, sched);
+    K2B_LAUNCH_CHECK(h);
+    K2B_CUDA(h, launch_pdl(ctc_collapse_kernel, dim3((unsigned)((B + kWarps - 1) / kWarps)), dim3(kWarps * 32), 0, h->stream, B, T, blank,
+                           frame_offset, prev_inout, tokens, ts, n_out, trailing_inout, cap, (const int32_t*)ybuf));
+    prof_end(h);
+    h->launches++;
+    return K2B_OK;
+  }
   static int per_sm = 0;
   if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctc_greedy_kernel, kWarps * 32, 0) != cudaSuccess || per_sm < 1)) {
     cudaGetLastError();
     per_sm = 4;
   }
-  const long long rounds = ((long long)B * T + kWarps - 1) / kWarps;
   const long long nblk = rounds < (long long)per_sm * h->sm_count ? rounds : (long long)per_sm * h->sm_count;
   const long long per_warp = (long long)B * T / (nblk * kWarps);
   const int G = per_warp >= 32 ? 4 : (per_warp >= 16 ? 2 : 1);
-  const int nseg = (T + kSeg - 1) / kSeg;
-  if ((long long)B * nseg >= 4LL * 6 * h->sm_count && (long long)B * nseg <= 0x7fffffffLL) {      // four waves of six CTAs per SM
-    prof_begin(h);
-    ctc_greedy_seg_kernel<<<(unsigned)(B * nseg), kWarps * 32, 0, h->stream>>>(logp, B, T, V, blank, nseg, frame_offset, prev_inout,
-                                                                              tokens, ts, n_out, trailing_inout, cap, ybuf, ticket);
-    prof_end(h);
-    K2B_LAUNCH_CHECK(h);
-    return K2B_OK;
-  }
   prof_begin(h);
   ctc_greedy_kernel<<<(unsigned)nblk, kWarps * 32, 0, h->stream>>>(logp, B, T, V, blank, frame_offset, prev_inout,
                                                                   tokens, ts, n_out, trailing_inout, cap, ybuf, ticket, sched, G);

@@ -125,6 +125,7 @@ struct k2b_handle {
   int opt_unfused_step = 0;               // the three-launch frame step
   int opt_greedy_persistent = -1;         // -1 auto, 0 cluster kernel, 1 persistent kernel (greedy, 1024 < V <= 2048)
   int opt_pair = 0;                       // CTA-pair variant of the cluster kernel
+  int opt_ctc_one_kernel = -1;            // CTC greedy: 1 = one kernel (tickets), 0 = frames + collapse kernels (PDL), -1 = by input size
   int opt_wh_tmem = -1;                   // cluster kernel: k-blocks of W_hi held in tensor memory (-1 = balanced choice)
   int opt_async_d2h = 0;                  // host-pointer fused calls return without the final sync (pinned buffers; k2b_sync completes)
 };

@@ -250,9 +250,11 @@ def test_golden_ctc(small):
     assert tb.tolist() == GOLD["ctc_trailing"].tolist()
 
 
-@pytest.mark.parametrize("B,T,V", [(1, 1, 1), (3, 33, 2), (5, 64, 37), (4, 100, 2000), (3, 70, 5537), (2, 250, 501)])
-def test_ctc_bit_exact_vs_oracle(small, B, T, V):
+@pytest.mark.parametrize("form", [1, 0])      # k2b_set_option("ctc_one_kernel"): tickets in one kernel / frames + collapse kernels
+@pytest.mark.parametrize("B,T,V", [(1, 1, 1), (3, 33, 2), (5, 64, 37), (4, 100, 2000), (3, 70, 5537), (2, 250, 501), (9, 40, 2051)])
+def test_ctc_bit_exact_vs_oracle(small, B, T, V, form):
     m, w, h = small
+    h.set_option("ctc_one_kernel", form)
     lp = synth.make_ctc_logp(B, T, V, 1000 + V, blank_bias=2.0 if V > 2 else 0.0)
     fo = np.arange(B, dtype=np.int32) * 3
     tb0 = np.arange(B, dtype=np.int32)
@@ -261,10 +263,13 @@ def test_ctc_bit_exact_vs_oracle(small, B, T, V):
     assert t == [r.appended for r in want]
     assert s == [r.timestamps for r in want]
     assert tb.tolist() == [r.num_trailing_blank for r in want]
+    h.set_option("ctc_one_kernel", -1)
 
 
-def test_ctc_ties_nan_and_chunk_carry(small):
+@pytest.mark.parametrize("form", [1, 0])
+def test_ctc_ties_nan_and_chunk_carry(small, form):
     m, w, h = small
+    h.set_option("ctc_one_kernel", form)
     lp = synth.make_ctc_logp(2, 40, 101, 5, blank_bias=1.0)
     lp[0, 3, :] = -2.0                                    # whole-frame tie -> index 0 (blank)
     lp[0, 4, 10:] = -9.0; lp[0, 4, :10] = -8.0; lp[0, 4, 6] = lp[0, 4, 9] = -1.0    # tie -> 6
@@ -279,6 +284,12 @@ def test_ctc_ties_nan_and_chunk_carry(small):
     assert [x + y for x, y in zip(a[0], b[0])] == [r.appended for r in want]
     assert [x + y for x, y in zip(a[1], b[1])] == [r.timestamps for r in want]
     assert b[2].tolist() == [r.num_trailing_blank for r in want]
+    lp[1, 7, :] = -np.inf                                 # a frame of -inf only: the fold cannot decide it, the exact path must
+    lp[0, 8, 3] = np.inf
+    want = O.ctc_greedy_search(lp)
+    t, s, _, _ = h.ctc_greedy(lp)
+    assert t == [r.appended for r in want] and s == [r.timestamps for r in want]
+    h.set_option("ctc_one_kernel", -1)
 
 
 # ---- the reference-interface mirror, fused and fine-grained, on the GPU ---------------------------------------
