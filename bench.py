@@ -196,7 +196,7 @@ def make_input(cfg, streams, seed):
     return synth.make_frames(streams, T, cfg.dims.encoder_dim, seed)
 
 
-CPU_SAMPLE = {"cfg1": 1, "cfg2": 256, "cfg3": 512, "cfg4": 48, "cfg5": 128}     # streams: ~10-30 s of CPU work each
+CPU_SAMPLE = {"cfg1": 1, "cfg2": 256, "cfg3": 512, "cfg4": 256, "cfg5": 128}     # streams: ~10-30 s of CPU work each
 
 
 def run_cpu_baseline(cfg, name, inp, precision="bf16x3"):
