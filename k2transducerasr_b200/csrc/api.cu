@@ -417,6 +417,7 @@ int32_t k2b_set_option(k2b_handle* h, const char* name, int32_t value) {
   else if (n == "greedy_persistent") h->opt_greedy_persistent = value;
   else if (n == "pair") h->opt_pair = value;
   else if (n == "wh_tmem_kb") h->opt_wh_tmem = value;
+  else if (n == "tagged_records") h->opt_tagged_records = value;
   else if (n == "ctc_one_kernel") h->opt_ctc_one_kernel = value;
   else if (n == "prof_which") h->prof_which = value;
   else if (n == "async_d2h") h->opt_async_d2h = value;

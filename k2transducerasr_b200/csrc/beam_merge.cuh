@@ -73,7 +73,11 @@ __device__ __forceinline__ void beam_merge_stream(
     const BeamState& in, const BeamState& out, int32_t* bp, const int32_t* lens,
     const float* dec_tab, const float* enc_next, long long enc_stride, int J, uint8_t* x_img, float4 pe0, float4 pe1, float* c_v,
     int* c_f,
-    int* s_ctx, long long* tl) {
+    int* s_ctx, long long* tl, uint32_t tag = 0u, int* abort_flag = nullptr, int* bad = nullptr) {
+  // tag != 0 (persistent kernel, nt <= 64, V < 65535): TAGGED records - every 16-byte vector of a record is (three data words, the
+  // epoch tag of its frame), the data words being max, sum-exp, KB values and the KB indices packed two 16-bit halves to a word;
+  // the joiner CTAs announce nothing, every lane polls its own records until all their vectors carry the expected tag (see
+  // greedy_merge_warp). A time-out / abort sets *bad (shared) and the records read as empty.
   constexpr int kNone = (int)0x80000000;
   // per-lane register batch: the records of tiles lane and lane + 32 (nt <= 64 without a tail pass), KB candidates each
   constexpr int kPairs = 2, kCands = kPairs * KB, RW = kBeamRecWords<KB>;
@@ -117,11 +121,53 @@ __device__ __forceinline__ void beam_merge_stream(
       for (int u = 0; u < kPairs; ++u) {
         const int i = lane + 32 * u;
         uint32_t w[RW];
+        if (tag == 0u) {
 #pragma unroll
-        for (int v = 0; v < RW / 4; ++v) {
-          uint4 q4 = make_uint4(0xff800000u, 0u, 0xff800000u, 0xff800000u);
-          if (i < nt) q4 = __ldcg(reinterpret_cast<const uint4*>(rrow + (size_t)i * RW) + v);
-          w[4 * v] = q4.x; w[4 * v + 1] = q4.y; w[4 * v + 2] = q4.z; w[4 * v + 3] = q4.w;
+          for (int v = 0; v < RW / 4; ++v) {
+            uint4 q4 = make_uint4(0xff800000u, 0u, 0xff800000u, 0xff800000u);
+            if (i < nt) q4 = __ldcg(reinterpret_cast<const uint4*>(rrow + (size_t)i * RW) + v);
+            w[4 * v] = q4.x; w[4 * v + 1] = q4.y; w[4 * v + 2] = q4.z; w[4 * v + 3] = q4.w;
+          }
+        } else {
+          // plain layout out of the tagged one: data word j sits in vector j / 3 at position j % 3
+          uint32_t d[3 * (RW / 4)];
+#pragma unroll
+          for (int j = 0; j < 3 * (RW / 4); ++j) d[j] = (j == 0) ? 0xff800000u : 0u;
+          if (i < nt) {
+            const uint4* rp = reinterpret_cast<const uint4*>(rrow + (size_t)i * RW);
+            const long long c0 = clock64();
+            int spins = 0;
+#pragma unroll 1
+            while (true) {
+              bool all = true;
+#pragma unroll
+              for (int v = 0; v < RW / 4; ++v) {
+                uint4 q4;
+                asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q4.x), "=r"(q4.y), "=r"(q4.z), "=r"(q4.w) : "l"(rp + v) : "memory");
+                d[3 * v] = q4.x; d[3 * v + 1] = q4.y; d[3 * v + 2] = q4.z;
+                all &= q4.w == tag;
+              }
+              if (all) break;
+              if (((++spins) & 63) == 0) {
+                int ab;
+                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(ab) : "l"(abort_flag) : "memory");
+                if (ab != 0 || clock64() - c0 > k2b::ptx::kWaitTimeoutCycles) {
+                  *bad = 1;
+#pragma unroll
+                  for (int j = 0; j < 3 * (RW / 4); ++j) d[j] = (j == 0) ? 0xff800000u : 0u;
+                  d[2 + KB] = 0xffffffffu;
+                  break;
+                }
+              }
+            }
+          }
+          w[0] = d[0]; w[1] = d[1];
+#pragma unroll
+          for (int j = 0; j < KB; ++j) {
+            w[2 + j] = d[2 + j];
+            const uint32_t h16 = (d[2 + KB + (j >> 1)] >> (16 * (j & 1))) & 0xffffu;
+            w[2 + KB + j] = h16 == 0xffffu ? 0xffffffffu : h16;
+          }
         }
         pm[u] = i < nt ? __uint_as_float(w[0]) : -INFINITY;
         ps[u] = i < nt ? __uint_as_float(w[1]) : 0.f;
@@ -363,16 +409,42 @@ struct GreedyOut {
   int64_t* hyp;      // [B,2] or null
   int cap;
 };
-__device__ __forceinline__ void greedy_merge_warp(int lane, int s, int V, int nt, int T, int t, int blank, int unk, int mask3,
+// `tag` != 0 (persistent kernel): the joiner CTAs do not announce their records through a counter - word 0 of a record is the
+// epoch tag of the frame it belongs to, written with the other three words by ONE 16-byte store, and every lane polls its own
+// records until the tag is the expected one: the producer needs no barrier and no gpu-scope release (a MEMBAR waiting for the
+// CTA's outstanding stores), the consumer no separate round trip for the counter. Returns false on a time-out / abort.
+__device__ __forceinline__ bool greedy_merge_warp(int lane, int s, int V, int nt, int T, int t, int blank, int unk, int mask3,
                                                   const float* part_rec, const BeamState& in, const BeamState& out, const GreedyOut& go,
                                                   const int32_t* lens, const float* dec_tab, const float* enc_next,
-                                                  long long enc_stride, int J, uint8_t* x_img) {
+                                                  long long enc_stride, int J, uint8_t* x_img, uint32_t tag = 0u,
+                                                  int* abort_flag = nullptr) {
   constexpr int kNone = (int)0x80000000, RW = kBeamRecWords<1>;
   const unsigned full = 0xffffffffu;
   const float* rrow = part_rec + (size_t)s * nt * RW;
   int bk = kNone, bf = -1;
+  bool good = true;
   for (int i = lane; i < nt; i += 32) {
-    const uint4 q = __ldcg(reinterpret_cast<const uint4*>(rrow + (size_t)i * RW));
+    uint4 q;
+    if (tag == 0u) {
+      q = __ldcg(reinterpret_cast<const uint4*>(rrow + (size_t)i * RW));
+    } else {
+      const uint4* rp = reinterpret_cast<const uint4*>(rrow + (size_t)i * RW);
+      asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(rp) : "memory");
+      if (q.x != tag) {
+        const long long c0 = clock64();
+        int spins = 0;
+#pragma unroll 1
+        while (true) {
+          asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(rp) : "memory");
+          if (q.x == tag) break;
+          if (((++spins) & 63) == 0) {
+            int ab;
+            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(ab) : "l"(abort_flag) : "memory");
+            if (ab != 0 || clock64() - c0 > ptx::kWaitTimeoutCycles) { good = false; break; }
+          }
+        }
+      }
+    }
     const float v = __uint_as_float(q.z);
     const int idx = (int)q.w;
     const bool okc = (idx >= 0) & (v == v);
@@ -380,6 +452,7 @@ __device__ __forceinline__ void greedy_merge_warp(int lane, int s, int V, int nt
     const bool better = (key > bk) | ((key == bk) & (f > bf));
     bk = better ? key : bk; bf = better ? f : bf;
   }
+  if (tag != 0u && !__all_sync(full, good)) return false;
   int c0 = __ldcg(in.ctx + 2 * s), c1 = __ldcg(in.ctx + 2 * s + 1), ln = __ldcg(in.len + s);
   const bool frozen = lens != nullptr && t >= __ldg(lens + s);
   const int wk = __reduce_max_sync(full, bk);
@@ -400,7 +473,7 @@ __device__ __forceinline__ void greedy_merge_warp(int lane, int s, int V, int nt
       if (go.hyp != nullptr) { go.hyp[2 * s] = c0; go.hyp[2 * s + 1] = c1; }
     }
   }
-  if (enc_next == nullptr) return;
+  if (enc_next == nullptr) return true;
   constexpr int kRowTile = 128, kImgTile = 128 * 128;
   const float* erow = enc_next + (size_t)s * enc_stride;
   const float* drow = dec_tab + ((size_t)(c0 + 1) * V + c1) * J;
@@ -423,6 +496,7 @@ __device__ __forceinline__ void greedy_merge_warp(int lane, int s, int V, int nt
         make_uint4(k2b::ptx::pack_bf16x2(x[0] - hi[0], x[1] - hi[1]), k2b::ptx::pack_bf16x2(x[2] - hi[2], x[3] - hi[3]),
                    k2b::ptx::pack_bf16x2(x[4] - hi[4], x[5] - hi[5]), k2b::ptx::pack_bf16x2(x[6] - hi[6], x[7] - hi[7]));
   }
+  return true;
 }
 
 }  // namespace k2b

@@ -78,6 +78,8 @@ struct JArgs {
   int* done;                 // [T][ntm]: column tiles of (frame, row tile) whose partials are written
   int* ready;                // [T+1][ntm]: streams of (frame, row tile) whose operand rows are written
   int* abort_flag;
+  uint32_t epoch0;           // MEGA, != 0: TAGGED records - those of frame t carry epoch0 + t + 1 (beam 1: in word 0; beams 4 / 8: in
+                             // the fourth word of every 16-byte vector, beam_merge.cuh) and no `done` counter is kept
   GreedyOut go;              // beam 1: where the merge warps leave tokens / timestamps / counts (/ Hyp)
 };
 
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float bias_t[BN];
   __shared__ float mg_v[MEGA ? KK * KK : 1];
-  __shared__ int mg_f[MEGA ? KK * KK : 1], mg_ctx[MEGA ? 2 * KK : 1];
+  __shared__ int mg_f[MEGA ? KK * KK : 1], mg_ctx[MEGA ? 2 * KK : 1], mg_bad;
   const int nframes = MEGA ? a.T : 1;
   const int spr = MEGA ? kJM / a.topk : 0;               // streams per row tile
 
@@ -133,6 +135,7 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
   const uint32_t x3 = (uint32_t)a.x3;
 
   if (tid == 0) {
+    mg_bad = 0;
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EW); }
     mbar_fence_init();
@@ -381,7 +384,9 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
         uint32_t w[RW];
 #pragma unroll
         for (int i = 0; i < RW; ++i) w[i] = 0u;
-        w[0] = __float_as_uint(mx);
+        const bool tagged = MEGA && a.epoch0 != 0u;
+        const uint32_t tagv = a.epoch0 + (uint32_t)t + 1u;
+        w[0] = (tagged && KK == 1) ? tagv : __float_as_uint(mx);       // beam 1: nobody reads max / sum
         w[1] = __float_as_uint(any ? sum : 0.f);
 #pragma unroll
         for (int i = 0; i < KK; ++i) {
@@ -389,13 +394,26 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
           w[2 + i] = __float_as_uint(has ? tv[i] : -INFINITY);
           w[2 + KK + i] = (uint32_t)(has ? col0 + (key[i] & 255) : -1);
         }
+        if (KK > 1 && tagged) {            // (three data words, tag) per vector; indices as 16-bit halves
+          uint32_t d[3 * (RW / 4)];
+#pragma unroll
+          for (int j = 0; j < 3 * (RW / 4); ++j) d[j] = 0u;
+          d[0] = w[0]; d[1] = w[1];
+#pragma unroll
+          for (int i = 0; i < KK; ++i) d[2 + i] = w[2 + i];
+#pragma unroll
+          for (int i = 0; i < KK; i += 2) d[2 + KK + (i >> 1)] = (w[2 + KK + i] & 0xffffu) | (w[2 + KK + i + 1] << 16);
+#pragma unroll
+          for (int v = 0; v < RW / 4; ++v) { w[4 * v] = d[3 * v]; w[4 * v + 1] = d[3 * v + 1]; w[4 * v + 2] = d[3 * v + 2]; w[4 * v + 3] = tagv; }
+        }
         uint4* dst = reinterpret_cast<uint4*>(a.part_rec + ((size_t)m * a.ntn + tile_n) * RW);
 #pragma unroll
         for (int v = 0; v < RW / 4; ++v) dst[v] = make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
       }
       if (dbg && it == 0) c_epi = clock64();
       if (tlm != nullptr && tid == 64 && t < 40 && tile == blockIdx.x) tlm[t * 16 + 12] = clock64();
-      if (MEGA) {                                         // publish: one more column tile of (frame, row tile) is reduced
+      if (MEGA && a.epoch0 == 0u) {                       // publish: one more column tile of (frame, row tile) is reduced
+                                                          // (tagged records announce themselves)
         named_bar_sync(3, EW * 32);                       // (CTA barrier, then one gpu-scope release: cumulative over the CTA's stores)
         if (etid == 0) red_release_gpu(a.done + (size_t)t * a.ntm + tile_m, 1);
         if (tlm != nullptr && tid == 64 && t < 40) tlm[t * 16 + (tile == blockIdx.x ? 2 : 5)] = clock64();
@@ -427,12 +445,19 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
         sin.nlive = odd ? a.st[1].nlive : a.st[0].nlive; sout.nlive = odd ? a.st[0].nlive : a.st[1].nlive;
         for (int s = blockIdx.x + mw * gridDim.x; s < a.B && ok; s += 4 * gridDim.x) {
           const int r = s / spr;
-          int good = 1;
-          if (lane == 0) good = wait_count(a.done + (size_t)t * a.ntm + r, a.ntn, a.abort_flag) ? 1 : 0;
-          good = __shfl_sync(0xffffffffu, good, 0);
-          if (!good) { ok = false; break; }
-          greedy_merge_warp(lane, s, a.V, a.ntn, a.Ttot, a.t0 + t, a.blank, a.unk, a.mask3, a.part_rec, sin, sout, a.go, a.lens, a.dec_tab,
-                            enc_next, a.enc_stride, a.J, a.x_img);
+          if (a.epoch0 == 0u) {                           // records announced by the row tile's counter
+            int good = 1;
+            if (lane == 0) good = wait_count(a.done + (size_t)t * a.ntm + r, a.ntn, a.abort_flag) ? 1 : 0;
+            good = __shfl_sync(0xffffffffu, good, 0);
+            if (!good) { ok = false; break; }
+          }
+          if (!greedy_merge_warp(lane, s, a.V, a.ntn, a.Ttot, a.t0 + t, a.blank, a.unk, a.mask3, a.part_rec, sin, sout, a.go, a.lens,
+                                 a.dec_tab, enc_next, a.enc_stride, a.J, a.x_img, a.epoch0 != 0u ? a.epoch0 + (uint32_t)t + 1u : 0u,
+                                 a.abort_flag)) {
+            if (lane == 0) atomicExch(a.abort_flag, 1);
+            ok = false;
+            break;
+          }
           if (t + 1 < a.T) {
             asm volatile("fence.proxy.async;" ::: "memory");
             __syncwarp();
@@ -447,13 +472,15 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
         const int r = s / spr;
         float4 pe0, pe1;
         beam_merge_prefetch(mtid, s, a.topk, a.J, enc_next, a.enc_stride, &pe0, &pe1);
-        int good = 1;
-        if (mtid == 0) good = wait_count(a.done + (size_t)t * a.ntm + r, a.ntn, a.abort_flag) ? 1 : 0;
-        if (mtid == 0) mg_ctx[0] = good;
-        named_bar_sync(2, 128);
-        good = mg_ctx[0];
-        named_bar_sync(2, 128);                           // mg_ctx is rewritten by the merge step
-        if (!good) { ok = false; break; }
+        if (a.epoch0 == 0u) {                             // counters (more than 64 column tiles, or indices beyond 16 bits)
+          int good = 1;
+          if (mtid == 0) good = wait_count(a.done + (size_t)t * a.ntm + r, a.ntn, a.abort_flag) ? 1 : 0;
+          if (mtid == 0) mg_ctx[0] = good;
+          named_bar_sync(2, 128);
+          good = mg_ctx[0];
+          named_bar_sync(2, 128);                         // mg_ctx is rewritten by the merge step
+          if (!good) { ok = false; break; }
+        }
         if (tlm != nullptr && mtid == 0 && t < 40) tlm[t * 16 + (s == blockIdx.x ? 6 : 8)] = clock64();
         const bool odd = ((a.t0 + t) & 1) != 0;
         BeamState sin, sout;
@@ -464,7 +491,12 @@ __global__ void __launch_bounds__(64 + EW * 32 + (MEGA ? 128 : 0), 1) joiner_top
         sin.nlive = odd ? a.st[1].nlive : a.st[0].nlive; sout.nlive = odd ? a.st[0].nlive : a.st[1].nlive;
         beam_merge_stream<KK>(mtid, 2, s, a.topk, a.V, a.ntn, a.Ttot, a.t0 + t, a.blank, a.unk, a.mask3, a.part_rec,
                               sin, sout, a.bp, a.lens, a.dec_tab, enc_next, a.enc_stride, a.J, a.x_img, pe0, pe1,
-                              mg_v, mg_f, mg_ctx, (tlm != nullptr && t < 40 && s == blockIdx.x) ? tlm + 640 + t * 8 : nullptr);
+                              mg_v, mg_f, mg_ctx, (tlm != nullptr && t < 40 && s == blockIdx.x) ? tlm + 640 + t * 8 : nullptr,
+                              a.epoch0 != 0u ? a.epoch0 + (uint32_t)t + 1u : 0u, a.abort_flag, &mg_bad);
+        if (a.epoch0 != 0u) {
+          named_bar_sync(2, 128);
+          if (mg_bad != 0) { if (mtid == 0) atomicExch(a.abort_flag, 1); ok = false; break; }
+        }
         if (t + 1 < a.T) {                                // publish: one more stream of (frame t + 1, row tile) has its operand rows
           asm volatile("fence.proxy.async;" ::: "memory");       // the rows are read through the async proxy (TMA)
           named_bar_sync(2, 128);
@@ -541,6 +573,7 @@ int joiner_topk_tiles(const k2b_handle* h, int M) {
 // x_img: the joiner operand as bf16 hi / lo tile images (joinin_table_tc / decoder_joinin_tc). Partial records per (row, 160-column
 // vocabulary tile): beam_partial_words(topk) floats each (beam_merge.cuh). The weight images must exist (ensure_joiner_assets).
 int32_t joiner_topk_tc(k2b_handle* h, const uint8_t* x_img, int M, int topk, int kk, float* part_rec) {
+  h->ll_clean_ptr = nullptr;             // untagged records: the persistent greedy kernel zeroes the buffer before its next use
   JArgs a = {};
   a.a_img = x_img; a.w_hi_img = h->wj_hi_img; a.w_lo_img = h->wj_lo_img; a.bias = h->out_b;
   const int bn = joiner_topk_width(h, M);
@@ -591,6 +624,22 @@ int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8
   if (kk == 1) {
     if (go == nullptr) return fail(h, K2B_ERR_INVALID, "beam_mega_tc: beam 1 writes its tokens itself and needs the output arrays");
     a.go = GreedyOut{go->tokens, go->ts, go->n, go->hyp, go->cap};
+  }
+  // Measured (tools/time_mega_tagged.py): greedy, cfg3's shape: 11.95 -> 11.2 us per frame with tagged records; beam 4, cfg4: 20.8 ->
+  // 22.8 us - there 128 merge threads poll three vectors of two records each while the joiner's weight stream already runs at the
+  // L2 -> SM limit, and the counters win. Hence: tagged for beam 1, counters for beams 4 / 8 (tagged_records = 2 forces tags).
+  if ((h->opt_tagged_records != 0 && kk == 1) || (h->opt_tagged_records == 2 && a.ntn <= 64 && h->cfg.vocab_size < 65535)) {
+    // tagged records: whatever another engine (or another layout) left in the partials buffer must not look like a tag
+    if (h->ll_clean_ptr != h->ws_part.p || h->ll_clean_bytes != h->ws_part.bytes || h->ll_clean_kk != kk) {
+      K2B_CUDA(h, cudaMemsetAsync(h->ws_part.p, 0, h->ws_part.bytes, h->stream));
+      h->ll_clean_ptr = h->ws_part.p; h->ll_clean_bytes = h->ws_part.bytes; h->ll_clean_kk = kk;
+      h->ll_epoch = 1;
+    }
+    a.epoch0 = h->ll_epoch;
+    h->ll_epoch += (uint32_t)T + 1u;
+    if (h->ll_epoch > 0xfff00000u) { h->ll_clean_ptr = nullptr; }       // long before the tags wrap: start again from a zeroed buffer
+  } else {
+    h->ll_clean_ptr = nullptr;           // records of another layout go into the same buffer
   }
   a.done = static_cast<int*>(h->ws_sync.p);
   a.ready = a.done + (size_t)T * a.ntm;

@@ -126,6 +126,14 @@ struct k2b_handle {
   int opt_greedy_persistent = -1;         // -1 auto, 0 cluster kernel, 1 persistent kernel (greedy, 1024 < V <= 2048)
   int opt_pair = 0;                       // CTA-pair variant of the cluster kernel
   int opt_ctc_one_kernel = -1;            // CTC greedy: 1 = one kernel (tickets), 0 = frames + collapse kernels (PDL), -1 = by input size
+  // persistent greedy kernel: records carry the frame's epoch tag instead of being announced by a counter (joiner_tc.cu); the tags
+  // of a launch are ll_epoch + 1 .. ll_epoch + T; ll_clean_ptr / _bytes: the partials buffer as it was last zeroed for tagged use
+  uint32_t ll_epoch = 1;
+  void* ll_clean_ptr = nullptr;
+  size_t ll_clean_bytes = 0;
+  int ll_clean_kk = 0;                    // ... and the record layout (beam bound of the instantiation) it was zeroed for
+  int opt_tagged_records = 1;             // persistent kernels: 0 = records announced through counters, 1 = epoch-tagged records for
+                                          // greedy search (default), 2 = for beam search as well (measured slower: joiner_tc.cu)
   int opt_wh_tmem = -1;                   // cluster kernel: k-blocks of W_hi held in tensor memory (-1 = balanced choice)
   int opt_async_d2h = 0;                  // host-pointer fused calls return without the final sync (pinned buffers; k2b_sync completes)
 };

@@ -455,6 +455,7 @@ int32_t greedy_dev(k2b_handle* h, const float* enc, int B, int T, int mode, bool
   const int nt = tc ? joiner_tc_tiles(h) : num_vocab_tiles(V);
   K2B_TRY(ensure(h, h->ws_x, sizeof(float) * (size_t)B * J));
   K2B_TRY(ensure(h, h->ws_part, (size_t)B * nt * 12));
+  h->ll_clean_ptr = nullptr;             // (the persistent greedy kernel's tagged records share this buffer)
   K2B_TRY(ensure(h, h->ws_state, align256((size_t)B * 8) + 256 + align256((size_t)B * 4)));
   int32_t* ctx = static_cast<int32_t*>(h->ws_state.p);
   int32_t* flag = reinterpret_cast<int32_t*>(static_cast<char*>(h->ws_state.p) + align256((size_t)B * 8));
@@ -694,6 +695,7 @@ int32_t beam_dev(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* 
     return last ? finish(cur) : K2B_OK;
   }
   if (greedy_ext) return fail(h, K2B_ERR_UNSUPPORTED, "beam_dev: greedy options need the memoised decoder table");
+  h->ll_clean_ptr = nullptr;             // (the persistent greedy kernel's tagged records share the partials buffer)
   if (enc_stride_in > 0 && enc_stride_in != (long long)T * J) return fail(h, K2B_ERR_UNSUPPORTED, "beam_dev: strided frames need the fused path");
   for (int t = 0; t < T; ++t) {
     GemmArgs d;
