@@ -676,7 +676,7 @@ __global__ void __maxnreg__(K2B_CLUSTER_MAXREG) cluster_beam_kernel(const Cluste
             v[r][j] = Lt[pos * kLtStride + n0 + r];
             const int kb = __float_as_int(v[r][j]);
             const int key = kb ^ ((kb >> 31) & 0x7fffffff);
-            pk[r][j] = pos < nvalid ? ((key & ~127) | pos) : kKeyNone;
+            pk[r][j] = (key & ~127) | pos;      // rows beyond V carry a -inf bias: their keys lose against every valid one
           }
           // sort the four unique keys of this lane once, best first: every round then pops the head
 #define K2B_CE(x, y) do { const int hi_ = max(pk[r][x], pk[r][y]), lo_ = min(pk[r][x], pk[r][y]); pk[r][x] = hi_; pk[r][y] = lo_; } while (0)
@@ -707,7 +707,7 @@ __global__ void __maxnreg__(K2B_CLUSTER_MAXREG) cluster_beam_kernel(const Cluste
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const float ex = ex2_approx(fmaf(v[r][j], 1.4426950408889634f, mneg));
-                  ls += (lane + 32 * j < nvalid) ? ex : 0.f;
+                  ls += ex;                      // (exp2(-inf) = 0 for the rows beyond V)
                 }
                 const unsigned tot = __reduce_add_sync(0xffffffffu, __float2uint_rn(ls * 16777216.f));
                 sum[r] = (wk == kKeyNone) ? 0.f : (float)tot * (1.f / 16777216.f);
@@ -721,7 +721,7 @@ __global__ void __maxnreg__(K2B_CLUSTER_MAXREG) cluster_beam_kernel(const Cluste
           if (lane == 0) *reinterpret_cast<float2*>(mine) = make_float2(m[r], sum[r]);
           if (lane < K) {
             const int pos = keep[r] & 127;
-            const bool has = keep[r] != kKeyNone;
+            const bool has = keep[r] != kKeyNone && pos < nvalid;      // a slice with fewer than K valid rows
             mine[2 + lane] = has ? Lt[pos * kLtStride + n0 + r] : -INFINITY;
             reinterpret_cast<int*>(mine)[2 + K + lane] = has ? (int)rank * 128 + pos : -1;
           }
