@@ -421,6 +421,9 @@ __device__ __forceinline__ bool greedy_merge_warp(int lane, int s, int V, int nt
   constexpr int kNone = (int)0x80000000, RW = kBeamRecWords<1>;
   const unsigned full = 0xffffffffu;
   const float* rrow = part_rec + (size_t)s * nt * RW;
+  // the stream's own state (written by this warp one frame ago): fetched BEFORE the wait for the records, not behind it
+  int c0 = __ldcg(in.ctx + 2 * s), c1 = __ldcg(in.ctx + 2 * s + 1), ln = __ldcg(in.len + s);
+  const bool frozen = lens != nullptr && t >= __ldg(lens + s);
   int bk = kNone, bf = -1;
   bool good = true;
   for (int i = lane; i < nt; i += 32) {
@@ -453,8 +456,6 @@ __device__ __forceinline__ bool greedy_merge_warp(int lane, int s, int V, int nt
     bk = better ? key : bk; bf = better ? f : bf;
   }
   if (tag != 0u && !__all_sync(full, good)) return false;
-  int c0 = __ldcg(in.ctx + 2 * s), c1 = __ldcg(in.ctx + 2 * s + 1), ln = __ldcg(in.len + s);
-  const bool frozen = lens != nullptr && t >= __ldg(lens + s);
   const int wk = __reduce_max_sync(full, bk);
   const int y = __reduce_max_sync(full, bk == wk ? bf : -1);
   const bool emit = !frozen && y >= 0 && y != blank && y != unk && y != mask3;
