@@ -109,6 +109,37 @@ __device__ __forceinline__ void beam_merge_stream(
       if (lane == 0) out.nlive[s] = nl;
     }
   } else {
+    if (tag != 0u) {
+      // tagged records: ONE warp polls (the last vector of the records of hypothesis 0, with a pause between rounds - 128 threads
+      // polling every vector of every record cost 10 % on cfg4, whose weight stream runs at the L2 -> SM limit); the records of
+      // the stream's other rows come from the same joiner CTAs a few cycles apart, and every load below still verifies its tags
+      if (warp == 0) {
+        const float* r0 = part_rec + (size_t)s * K * nt * RW;
+        const long long c0 = clock64();
+        int spins = 0;
+#pragma unroll 1
+        while (true) {
+          bool all = true;
+#pragma unroll
+          for (int u = 0; u < kPairs; ++u) {
+            const int i = lane + 32 * u;
+            if (i < nt) {
+              uint32_t tg;
+              asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(tg) : "l"(r0 + (size_t)i * RW + RW - 1) : "memory");
+              all &= tg == tag;
+            }
+          }
+          if (__all_sync(full, all)) break;
+          __nanosleep(20);
+          if (((++spins) & 15) == 0) {
+            int ab;
+            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(ab) : "l"(abort_flag) : "memory");
+            if (ab != 0 || clock64() - c0 > k2b::ptx::kWaitTimeoutCycles) { if (lane == 0) *bad = 1; break; }
+          }
+        }
+      }
+      k2b::ptx::named_bar_sync(bar_id, 128);
+    }
     // ---- A: per live hypothesis --------------------------------------------------------------------------------------------
 #pragma unroll 1
     for (int h = warp; h < K; h += 4) {        // the loads of row h are issued before the live count has arrived (dead rows are

@@ -625,10 +625,10 @@ int32_t beam_mega_tc(k2b_handle* h, const float* enc, int B, int T, int K, uint8
     if (go == nullptr) return fail(h, K2B_ERR_INVALID, "beam_mega_tc: beam 1 writes its tokens itself and needs the output arrays");
     a.go = GreedyOut{go->tokens, go->ts, go->n, go->hyp, go->cap};
   }
-  // Measured (tools/time_mega_tagged.py): greedy, cfg3's shape: 11.95 -> 11.2 us per frame with tagged records; beam 4, cfg4: 20.8 ->
-  // 22.8 us - there 128 merge threads poll three vectors of two records each while the joiner's weight stream already runs at the
-  // L2 -> SM limit, and the counters win. Hence: tagged for beam 1, counters for beams 4 / 8 (tagged_records = 2 forces tags).
-  if ((h->opt_tagged_records != 0 && kk == 1) || (h->opt_tagged_records == 2 && a.ntn <= 64 && h->cfg.vocab_size < 65535)) {
+  // Measured (tools/time_mega_tagged.py): greedy, cfg3's shape: 11.95 -> 11.0 us per frame with tagged records; beam 4, cfg4: 20.8 ->
+  // 22.8 us when all 128 merge threads poll every vector of their records (the joiner's weight stream already runs at the L2 -> SM
+  // limit), 20.8 -> 20.2 us when ONE warp polls one word per record with a pause between rounds (beam_merge_stream).
+  if (h->opt_tagged_records != 0 && (kk == 1 || (a.ntn <= 64 && h->cfg.vocab_size < 65535))) {
     // tagged records: whatever another engine (or another layout) left in the partials buffer must not look like a tag
     if (h->ll_clean_ptr != h->ws_part.p || h->ll_clean_bytes != h->ws_part.bytes || h->ll_clean_kk != kk) {
       K2B_CUDA(h, cudaMemsetAsync(h->ws_part.p, 0, h->ws_part.bytes, h->stream));

@@ -132,8 +132,7 @@ struct k2b_handle {
   void* ll_clean_ptr = nullptr;
   size_t ll_clean_bytes = 0;
   int ll_clean_kk = 0;                    // ... and the record layout (beam bound of the instantiation) it was zeroed for
-  int opt_tagged_records = 1;             // persistent kernels: 0 = records announced through counters, 1 = epoch-tagged records for
-                                          // greedy search (default), 2 = for beam search as well (measured slower: joiner_tc.cu)
+  int opt_tagged_records = 1;             // persistent kernels: 0 = records announced through counters, 1 = epoch-tagged records
   int opt_wh_tmem = -1;                   // cluster kernel: k-blocks of W_hi held in tensor memory (-1 = balanced choice)
   int opt_async_d2h = 0;                  // host-pointer fused calls return without the final sync (pinned buffers; k2b_sync completes)
 };
