@@ -369,11 +369,11 @@ class Work:
         frames_per_launch = (self.Tc if cfg.mode == "greedy_online" else T) if fused_loop else 1
         flop = 2.0 * rows * self.J * self.V * frames_per_launch
         tf = flop / (avg_ms * 1e-3) / 1e12 if n_launch else 0.0
-        kern = {"mbs": "cluster_beam_kernel" if self.V <= 1024 else "joiner_topk_kernel<MEGA>", "greedy_single": "cluster_beam_kernel<1>",
+        kern = {"mbs": "cluster_beam_kernel" if self.V <= 1024 else "joiner_topk_kernel<MEGA>", "greedy_single": "single_greedy_kernel (8-CTA cluster per stream, weights in registers, fp32 FMA)",
                 "greedy_online": "joiner_topk_kernel<1, MEGA> (one launch per 8-frame chunk)"}[cfg.mode]
         return {"bound": "tensor", "achieved": tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["tf_sustained"],
                 "traffic": TRAFFIC.get(self.args.workload) if fused_loop else None,
-                "kernel": kern + ": whole time loop (tcgen05 joiner + log-softmax / top-k + merge)" if fused_loop else
+                "kernel": (kern + ": whole time loop" + ("" if cfg.mode == "greedy_single" else " (tcgen05 joiner + log-softmax / top-k + merge)")) if fused_loop else
                           "joiner GEMM (+log-softmax / top-k epilogue), one launch per frame",
                 "avg_launch_us": avg_ms * 1e3, "launches_timed": n_launch, "flop_per_launch": flop,
                 "flop_per_hyp_frame": 2.0 * self.J * self.V, "peak_source": peaks["src"] + ", sustained bf16",

@@ -417,6 +417,7 @@ int32_t k2b_set_option(k2b_handle* h, const char* name, int32_t value) {
   else if (n == "greedy_persistent") h->opt_greedy_persistent = value;
   else if (n == "pair") h->opt_pair = value;
   else if (n == "wh_tmem_kb") h->opt_wh_tmem = value;
+  else if (n == "single_greedy") h->opt_single_greedy = value;
   else if (n == "tagged_records") h->opt_tagged_records = value;
   else if (n == "ctc_one_kernel") h->opt_ctc_one_kernel = value;
   else if (n == "prof_which") h->prof_which = value;
@@ -820,6 +821,9 @@ static int32_t greedy_fast_pass(k2b_handle* h, const float* enc, int enc_is_raw,
         K2B_TRY(exp2x_frames(h, enc, encE, n * J));
       }
     }
+    // a few streams: one 8-CTA cluster per stream, weights in registers, fp32 FMA - no back-pointers, no back-trace
+    if (single_greedy_usable(h, B, T - t_begin))
+      return single_greedy_dev(h, encE, B, T - t_begin, t_begin, T, extra_mask, hyp_inout, hyp_inout, tokens, ts, n_out, cap);
     const size_t a4 = ((size_t)B * 4 + 255) & ~size_t(255);
     K2B_TRY(ensure(h, h->ws_state, 4 * a4));
     K2B_TRY(ensure(h, h->ws_bp, sizeof(int32_t) * (size_t)B * T));

@@ -133,6 +133,7 @@ struct k2b_handle {
   size_t ll_clean_bytes = 0;
   int ll_clean_kk = 0;                    // ... and the record layout (beam bound of the instantiation) it was zeroed for
   int opt_tagged_records = 1;             // persistent kernels: 0 = records announced through counters, 1 = epoch-tagged records
+  int opt_single_greedy = 1;              // greedy search of up to 16 streams on the register-resident fp32 kernel (single_greedy.cu)
   int opt_wh_tmem = -1;                   // cluster kernel: k-blocks of W_hi held in tensor memory (-1 = balanced choice)
   int opt_async_d2h = 0;                  // host-pointer fused calls return without the final sync (pinned buffers; k2b_sync completes)
 };
@@ -246,6 +247,11 @@ int32_t beam_backtrace_dev(k2b_handle* h, int B, int K, int T, const float* lp, 
                            const int32_t* bp, int64_t* tokens, int32_t* ts, int32_t* n_out, float* score, int cap,
                            const int32_t* cst = nullptr);
 int32_t* cluster_cst(k2b_handle* h, int B, int K);      // the cluster engine's automaton-state array (null without a context graph)
+
+// ---- single_greedy.cu --------------------------------------------------------------------------
+bool single_greedy_usable(const k2b_handle* h, int B, int T);
+int32_t single_greedy_dev(k2b_handle* h, const float* encE, int B, int T, int t0, int Ttot, int extra_mask, const int64_t* hyp_in,
+                          int64_t* hyp_out, int64_t* tokens, int32_t* ts, int32_t* n_out, int cap);
 
 // ---- search_cluster.cu -------------------------------------------------------------------------
 bool cluster_path_supported(const k2b_handle* h, int K);

@@ -211,6 +211,56 @@ def test_w_hi_in_tensor_memory_is_bit_identical(setup, prec):
     h.close()
 
 
+def test_single_greedy_register_kernel(setup):
+    """Up to 16 streams of at least 16 frames (cfg1 is one stream): one 8-CTA cluster per stream, the joiner weight in registers,
+    fp32 FMA (single_greedy.cu). Against the oracle in SINGLE / PER_STREAM / BATCH_COMPAT mode (the latter: two passes, the second
+    from a data-dependent frame), with ragged lengths, as online chunks of 16 frames with Hyp carried and the literal-1 mask, with
+    an exact tie (larger index wins) - and the same calls with the kernel switched off must decode the same symbols."""
+    m, w, raw, enc = setup
+    h = make(MID, w, "bf16x3")
+    for B in (1, 3, 16):
+        e = np.ascontiguousarray(enc[:B])
+        h.greedy_offline(e, _native.GREEDY_PER_STREAM, enc_is_raw=False)      # (first call: the memoised decoder, the packed weights)
+        n0 = h.launch_count()
+        t, s = h.greedy_offline(e, _native.GREEDY_PER_STREAM, enc_is_raw=False)
+        n_on = h.launch_count() - n0
+        want = O.greedy_search_batch(m, e, compat=False)
+        compare_streams(t, s, want, f"single greedy per-stream B={B}", allow_frac=0.12, T=e.shape[1])
+        h.set_option("single_greedy", 0)
+        n0 = h.launch_count()
+        t0, s0 = h.greedy_offline(e, _native.GREEDY_PER_STREAM, enc_is_raw=False)
+        assert n_on < h.launch_count() - n0, "the register kernel needs no back-trace launch: it must have been the engine"
+        h.set_option("single_greedy", 1)
+        compare_streams(t0, s0, want, f"cluster greedy per-stream B={B}", allow_frac=0.12, T=e.shape[1])
+        tc, sc = h.greedy_offline(e, _native.GREEDY_BATCH_COMPAT, enc_is_raw=False)
+        compare_streams(tc, sc, O.greedy_search_batch(m, e, compat=True), f"single greedy batch-compat B={B}", allow_frac=0.12, T=e.shape[1])
+    t, s = h.greedy_offline(raw[:1], _native.GREEDY_SINGLE)              # raw frames: encoder_proj in front
+    compare_streams(t, s, [O.greedy_search_single(m, enc[0])], "single greedy SINGLE", allow_frac=1.0, T=enc.shape[1])
+    lens = [40, 17, 0, 33, 25]
+    t, s = h.greedy_offline(np.ascontiguousarray(enc[:5]), _native.GREEDY_PER_STREAM, enc_is_raw=False, lens=lens)
+    want = [O.greedy_search_single(m, enc[b, :lens[b]]) for b in range(5)]
+    compare_streams(t, s, want, "single greedy ragged", allow_frac=0.2, T=enc.shape[1])
+    hyp = np.zeros((4, 2), np.int64)
+    ohyp, otoks = [[0, 0]] * 4, [[0, 0] for _ in range(4)]
+    for c in range(2):                                                    # online chunks of 16 frames
+        ch = np.ascontiguousarray(enc[:4, 16 * c:16 * c + 16])
+        t, s, hyp = h.greedy_online_chunk(ch, hyp, enc_is_raw=False)
+        res = O.greedy_search_online_chunk(m, ch, ohyp, otoks)
+        if compare_streams(t, s, res, f"single greedy online chunk {c}", allow_frac=0.25):
+            break
+        ohyp, otoks = [r.hyp for r in res], [r.tokens for r in res]
+        assert hyp.tolist() == ohyp
+    h.close()
+    w2 = {k: (None if v is None else v.copy()) for k, v in w.items()}
+    w2["out_w"][:] = 0.0                                                  # logits == bias in every implementation: exact ties
+    w2["out_b"][:] = -3.0
+    w2["out_b"][[7, 130, 499]] = 2.5
+    h = make(MID, w2, "bf16x3")
+    t, s = h.greedy_offline(np.ascontiguousarray(enc[:2, :20]), _native.GREEDY_PER_STREAM, enc_is_raw=False)
+    assert t == [[499] * 20] * 2 and s == [list(range(20))] * 2
+    h.close()
+
+
 @pytest.mark.parametrize("prec", ["bf16x3", "fp32"])
 def test_ragged_lengths_freeze_streams(setup, prec):
     """k2b_set_encoder_out_lens (the seam's encoder_out_lens, which the reference never consumes): stream b is decoded over its
