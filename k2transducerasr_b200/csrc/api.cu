@@ -139,6 +139,55 @@ int32_t beam_cluster_path(k2b_handle* h, const float* enc, int enc_is_raw, int B
   const size_t n = (size_t)B * T, J = h->cfg.joiner_dim;
   K2B_TRY(ensure(h, h->ws_encproj, sizeof(float) * n * J));
   float* encE = static_cast<float*>(h->ws_encproj.p);
+  // Raw frames resident on the device, a batch that fills the cluster kernel's 128 SMs: the encoder_proj GEMM of the SECOND half
+  // of the frames runs on a side stream (on the SMs the search leaves free) under the search of the first half; the search is two
+  // launches with the hypothesis state carried through global memory, as in the host-pointer call. cfg2: 1.43 -> ~1.34 ms per batch.
+  const bool two = enc_is_raw && hyp_inout == nullptr && encproj_tc_supported(h) && h->cfg.encoder_dim > 0 && h->enc_w != nullptr &&
+                   (h->opt_dev_chunks < 0 ? (T >= 64 && (long long)B * K >= 512) : h->opt_dev_chunks == 2) && !h->profile_on;
+  if (two) {
+    const int tA = T / 2, tB = T - tA;
+    if (h->copy_stream == nullptr) {
+      // lowest priority: when the search's CTAs become ready, the SMs that projection tiles free go to them first
+      int lo = 0, hi = 0;
+      K2B_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      K2B_CUDA(h, cudaStreamCreateWithPriority(&h->copy_stream, cudaStreamNonBlocking, lo));
+      for (int i = 0; i < 2; ++i) {
+        K2B_CUDA(h, cudaEventCreateWithFlags(&h->ev_ready[i], cudaEventDisableTiming));
+        K2B_CUDA(h, cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
+      }
+    }
+    const size_t NK2 = (size_t)B * K;
+    const size_t a4 = (NK2 * 4 + 255) & ~size_t(255), a8 = (NK2 * 8 + 255) & ~size_t(255), ab = ((size_t)B * 4 + 255) & ~size_t(255);
+    K2B_TRY(ensure(h, h->ws_state, 2 * a4 + ab + a8 + a8 + ab));
+    K2B_TRY(ensure(h, h->ws_bp, sizeof(int32_t) * (size_t)B * T * K));
+    K2B_TRY(ensure_encproj_assets(h));      // (packs the weight images on the compute stream the first time)
+    char* q = static_cast<char*>(h->ws_state.p);
+    float* fin_lp = reinterpret_cast<float*>(q); q += a4;
+    int32_t* fin_len = reinterpret_cast<int32_t*>(q); q += a4;
+    int32_t* fin_nlive = reinterpret_cast<int32_t*>(q); q += ab;
+    int32_t* io_ctx = reinterpret_cast<int32_t*>(q); q += a8;
+    unsigned long long* io_hash = reinterpret_cast<unsigned long long*>(q); q += a8;
+    const bool need_lp2 = score != nullptr;
+    if (score == nullptr) score = reinterpret_cast<float*>(q);
+    int32_t* bp = static_cast<int32_t*>(h->ws_bp.p);
+    // the side stream starts behind the first half's projection (the caller's frames are ready, the workspaces free, and the two
+    // GEMMs do not compete)
+    K2B_TRY(encoder_proj_tc(h, enc, B * tA, encE, true, tA, T, 0, T));
+    K2B_CUDA(h, cudaEventRecord(h->ev_free[0], h->stream));
+    K2B_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_free[0], 0));
+    K2B_TRY(beam_cluster_dev(h, encE, B, tA, K, bp, fin_lp, fin_len, fin_nlive, extra_mask, nullptr, nullptr, 0, T, 0, io_ctx, io_hash, need_lp2));
+    {
+      cudaStream_t keep = h->stream;
+      h->stream = h->copy_stream;
+      const int32_t st = encoder_proj_tc(h, enc, B * tB, encE, true, tB, T, tA, T);
+      h->stream = keep;
+      K2B_TRY(st);
+    }
+    K2B_CUDA(h, cudaEventRecord(h->ev_ready[0], h->copy_stream));
+    K2B_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_ready[0], 0));
+    K2B_TRY(beam_cluster_dev(h, encE, B, tB, K, bp, fin_lp, fin_len, fin_nlive, extra_mask, nullptr, nullptr, tA, T, 1, io_ctx, io_hash, need_lp2));
+    return beam_backtrace_dev(h, B, K, T, fin_lp, fin_len, fin_nlive, bp, tokens, ts, n_out, score, cap, K > 1 ? cluster_cst(h, B, K) : nullptr);
+  }
   if (enc_is_raw) {
     if (h->cfg.encoder_dim <= 0 || h->enc_w == nullptr) return fail(h, K2B_ERR_STATE, "encoder_proj weights not loaded (E == 0)");
     if (encproj_tc_supported(h)) {
@@ -417,6 +466,7 @@ int32_t k2b_set_option(k2b_handle* h, const char* name, int32_t value) {
   else if (n == "greedy_persistent") h->opt_greedy_persistent = value;
   else if (n == "pair") h->opt_pair = value;
   else if (n == "wh_tmem_kb") h->opt_wh_tmem = value;
+  else if (n == "dev_chunks") h->opt_dev_chunks = value;
   else if (n == "single_greedy") h->opt_single_greedy = value;
   else if (n == "tagged_records") h->opt_tagged_records = value;
   else if (n == "ctc_one_kernel") h->opt_ctc_one_kernel = value;

@@ -43,6 +43,7 @@ struct EncArgs {
   // tile) partials: max / sum-exp / top-k (2, modified_beam_search) or the argmax fold with ties and NaN -> larger index (3).
   int epi, nvalid, topk;
   int rows_per_stream, out_T, out_t0;     // epi 0 with rows_per_stream > 0: row m = (b, tt) of a time chunk -> output row b*out_T + out_t0 + tt
+  int in_T;                               // > 0 (with rows_per_stream > 0): the INPUT is the whole [B,in_T,K] array too, row (b, out_t0 + tt)
   float* part_m; float* part_s; float* part_tv; int32_t* part_ti;     // epi 2: [M,nt], [M,nt], [M,nt,topk] x2
   float* part_val; int32_t* part_idx; int32_t* part_nan;              // epi 3: [M,nt] each
   // pro 1: stateless decoder as the A producer - A(m,k) = relu(tab0[row(y0(m))][k] + tab1[row(y1(m))][k]) (embedding gather +
@@ -187,6 +188,13 @@ __global__ void __launch_bounds__((2 + EW) * 32, 1) encproj_tc_kernel(const EncA
     const int half = lane >> 4, c4 = lane & 15;     // two rows per warp instruction, 16 float4 per 64-wide row
     constexpr int kRowsPerWarp = kEM / kProducers, kIters = kRowsPerWarp / 2;
     int r0[kIters], r1[kIters];          // pro 1: table rows of this thread's hypothesis rows
+    long long arow[kIters];              // pro 0: input row of tile row i (a time chunk may be read straight out of the whole array)
+#pragma unroll
+    for (int i = 0; i < kIters; ++i) {
+      const int m = tile_m * kEM + pw * kRowsPerWarp + 2 * i + half;
+      arow[i] = (a.in_T > 0 && a.rows_per_stream > 0)
+                    ? (long long)(m / a.rows_per_stream) * a.in_T + a.out_t0 + (m % a.rows_per_stream) : (long long)m;
+    }
     if (a.pro == 1) {
 #pragma unroll
       for (int i = 0; i < kIters; ++i) {
@@ -217,7 +225,7 @@ __global__ void __launch_bounds__((2 + EW) * 32, 1) encproj_tc_kernel(const EncA
       for (int i = 0; i < kIters; ++i) {
         const int r = pw * kRowsPerWarp + 2 * i + half;
         const int m = tile_m * kEM + r;
-        v[i] = (m < a.M) ? __ldg(reinterpret_cast<const float4*>(a.A + (size_t)m * a.K + (size_t)kb * kBKc) + c4)
+        v[i] = (m < a.M) ? __ldg(reinterpret_cast<const float4*>(a.A + (size_t)arow[i] * a.K + (size_t)kb * kBKc) + c4)
                          : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       }
@@ -497,10 +505,11 @@ static int32_t launch_tc(k2b_handle* h, EncArgs& a) {
 }
 
 // raw [n,E] -> out [n,J] = f(raw * We^T + be) on tcgen05; f = identity or exp(2*clamp(., +-21))
-int32_t encoder_proj_tc(k2b_handle* h, const float* raw, int n, float* out, bool exp2x, int rows_per_stream, int out_T, int out_t0) {
+int32_t encoder_proj_tc(k2b_handle* h, const float* raw, int n, float* out, bool exp2x, int rows_per_stream, int out_T, int out_t0,
+                        int in_T) {
   K2B_TRY(ensure_encproj_assets(h));
   EncArgs a = {};
-  a.rows_per_stream = rows_per_stream; a.out_T = out_T; a.out_t0 = out_t0;
+  a.rows_per_stream = rows_per_stream; a.out_T = out_T; a.out_t0 = out_t0; a.in_T = in_T;
   a.A = raw; a.w_hi_img = h->we_hi_img; a.w_lo_img = h->we_lo_img; a.bias = h->enc_b; a.C = out;
   a.M = n; a.N = h->cfg.joiner_dim; a.K = h->cfg.encoder_dim;
   a.exp2x = exp2x ? 1 : 0;

@@ -134,6 +134,7 @@ struct k2b_handle {
   int ll_clean_kk = 0;                    // ... and the record layout (beam bound of the instantiation) it was zeroed for
   int opt_tagged_records = 1;             // persistent kernels: 0 = records announced through counters, 1 = epoch-tagged records
   int opt_single_greedy = 1;              // greedy search of up to 16 streams on the register-resident fp32 kernel (single_greedy.cu)
+  int opt_dev_chunks = -1;                // device-pointer beam search on the cluster kernel: time chunks (-1 = two when it pays, 1 = one)
   int opt_wh_tmem = -1;                   // cluster kernel: k-blocks of W_hi held in tensor memory (-1 = balanced choice)
   int opt_async_d2h = 0;                  // host-pointer fused calls return without the final sync (pinned buffers; k2b_sync completes)
 };
@@ -286,8 +287,11 @@ void nccl_free(k2b_handle* h);
 
 // ---- encproj_tc.cu -----------------------------------------------------------------------------
 bool encproj_tc_supported(const k2b_handle* h);
+int32_t ensure_encproj_assets(k2b_handle* h);
+// rows_per_stream > 0: the n = B * rows_per_stream rows are time chunk [out_t0, out_t0 + rows_per_stream) of every stream and go to
+// rows b * out_T + out_t0 + tt of `out`; in_T > 0: `raw` is the whole [B,in_T,E] array as well (otherwise a compact [B,chunk,E] one)
 int32_t encoder_proj_tc(k2b_handle* h, const float* raw, int n, float* out, bool exp2x, int rows_per_stream = 0, int out_T = 0,
-                        int out_t0 = 0);
+                        int out_t0 = 0, int in_T = 0);
 int32_t state_pool_create(k2b_handle* h, const int32_t* item_len, int n_tensors, int max_streams);
 void state_pool_free(k2b_handle* h);
 int32_t state_pool_restack(k2b_handle* h, const int32_t* slots, int B, const int32_t* axis_len, float* stacked_dev, bool unstack);

@@ -555,6 +555,54 @@ def test_nccl_gather_single_rank(built_lib):
     h.close()
 
 
+def test_device_call_overlaps_the_second_half_projection(built_lib):
+    """k2b_modified_beam_search_dev on raw frames of a batch that fills the cluster kernel (B * K >= 512, T >= 64): the encoder_proj
+    GEMM of the second half of the frames runs on a side stream under the search of the first half, the search is two launches
+    with the state carried between them. Must equal the one-launch form (k2b_set_option("dev_chunks", 1)) bit for bit - also when
+    calls follow each other without a host synchronisation, with ragged lengths, and on an odd frame count."""
+    m, w = model_and_weights(MID, blank_bias=0.99)
+    h = make(MID, w)
+    B, K = 128, 4
+    for T, lens in ((64, None), (77, None), (64, "ragged")):
+        raws = [torch.from_numpy(synth.make_frames(B, T, MID.encoder_dim, 500 + i)).cuda() for i in range(2)]
+        outs = {}
+        for chunks in (1, 2):
+            h.set_option("dev_chunks", chunks)
+            res = []
+            for i in range(2):                       # two calls back to back on the handle's stream
+                tok = torch.zeros((B, T), dtype=torch.int64, device="cuda"); ts = torch.zeros((B, T), dtype=torch.int32, device="cuda")
+                n = torch.zeros(B, dtype=torch.int32, device="cuda"); sc = torch.zeros(B, dtype=torch.float32, device="cuda")
+                if lens is not None:
+                    h.set_encoder_out_lens([(7 * b + 3 * i) % (T + 1) for b in range(B)])
+                n0 = h.launch_count()
+                h.call("k2b_modified_beam_search_dev", raws[i], 1, B, T, K, tok, ts, n, sc, T)
+                res.append((tok, ts, n, sc, h.launch_count() - n0))
+            h.sync()
+            outs[chunks] = res
+        for i in range(2):
+            a, b = outs[1][i], outs[2][i]
+            assert i == 0 or b[4] > a[4], "two projections + two search launches (the first call also packs the weights)"
+            assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+            for s_ in range(B):
+                k = int(a[2][s_])
+                assert torch.equal(a[0][s_, :k], b[0][s_, :k]) and torch.equal(a[1][s_, :k], b[1][s_, :k])
+        assert int(outs[2][0][2].sum()) > 0
+    h.set_option("dev_chunks", -1)
+    # against the oracle (8 streams of the last batch)
+    T = 64
+    raw = synth.make_frames(B, T, MID.encoder_dim, 777)
+    d = torch.from_numpy(raw).cuda()
+    tok = torch.zeros((B, T), dtype=torch.int64, device="cuda"); ts = torch.zeros((B, T), dtype=torch.int32, device="cuda")
+    n = torch.zeros(B, dtype=torch.int32, device="cuda"); sc = torch.zeros(B, dtype=torch.float32, device="cuda")
+    h.call("k2b_modified_beam_search_dev", d, 1, B, T, K, tok, ts, n, sc, T)
+    h.sync()
+    want = O.modified_beam_search(m, O.encoder_proj(m, raw[:8]), K)
+    got_t = [tok[b, :int(n[b])].tolist() for b in range(8)]
+    got_s = [ts[b, :int(n[b])].tolist() for b in range(8)]
+    compare_streams(got_t, got_s, want, "device call, two chunks", allow_frac=0.25, scores=sc[:8].tolist(), T=T)
+    h.close()
+
+
 def test_backpointer_history_reconstructs_the_output(built_lib):
     """k2b_debug_backpointers: walking the history from the chosen hypothesis reproduces tokens / timestamps; no beam ever holds
     two hypotheses with the same token sequence (the hash dedupe checked against real sequences)."""
