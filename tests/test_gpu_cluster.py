@@ -475,6 +475,42 @@ def test_persistent_beam_kernel_shapes(built_lib, V, J, D, B, T, beam):
     h.close()
 
 
+def test_tagged_records_equal_counters_and_survive_engine_changes(built_lib):
+    """Persistent large-vocabulary kernel: the joiner CTAs hand their records to the merge warps by epoch tags (default) or through
+    release / acquire counters (k2b_set_option("tagged_records", 0)): identical results for beam 4 and for greedy. The partials
+    buffer is shared with every other engine and layout: calls are interleaved (beam 4 / greedy / the per-frame launches / the
+    fp32 path / beam 8) and every tagged call must still decode what the counter form decodes - a stale word that looked like a
+    tag would show here."""
+    dims = synth.ModelDims(2100, 128, 64, 64)
+    m, w = model_and_weights(dims, blank_bias=0.6)
+    h = make(dims, w, "bf16x3")
+    B, T = 37, 20
+    raw = synth.make_frames(B, T, dims.encoder_dim, 4242)
+    ref = {}
+    h.set_option("tagged_records", 0)
+    ref["b4"] = h.modified_beam_search(raw, 4, enc_is_raw=True)
+    ref["b8"] = h.modified_beam_search(raw, 8, enc_is_raw=True)
+    ref["g"] = h.greedy_offline(raw, _native.GREEDY_PER_STREAM, enc_is_raw=True)
+    h.set_option("tagged_records", 1)
+
+    def same(a, b):
+        return a[0] == b[0] and a[1] == b[1] and (len(a) < 3 or np.array_equal(np.asarray(a[2]), np.asarray(b[2])))
+
+    for rnd in range(3):
+        assert same(h.modified_beam_search(raw, 4, enc_is_raw=True), ref["b4"]), f"beam 4, round {rnd}"
+        assert same(h.greedy_offline(raw, _native.GREEDY_PER_STREAM, enc_is_raw=True), ref["g"]), f"greedy, round {rnd}"
+        h.set_option("no_mega", 1)                                  # per-frame launches write untagged records into the same buffer
+        assert same(h.modified_beam_search(raw, 4, enc_is_raw=True), ref["b4"])
+        h.set_option("no_mega", 0)
+        assert same(h.greedy_offline(raw, _native.GREEDY_PER_STREAM, enc_is_raw=True), ref["g"]), f"greedy after per-frame launches, round {rnd}"
+        h.set_precision("fp32")                                     # the CUDA-core path carves the buffer into four arrays
+        h.modified_beam_search(raw[:5], 4, enc_is_raw=True)
+        h.set_precision("bf16x3")
+        assert same(h.modified_beam_search(raw, 8, enc_is_raw=True), ref["b8"]), f"beam 8 after the fp32 path, round {rnd}"
+        assert same(h.greedy_offline(raw, _native.GREEDY_PER_STREAM, enc_is_raw=True), ref["g"])
+    h.close()
+
+
 def test_persistent_greedy_large_vocab(built_lib, monkeypatch):
     """Greedy search as beam 1 on the persistent beam kernel: V = 5537 (no cluster fits) offline PER_STREAM / SINGLE and online
     chunks against the oracle; V = 2000 online chunks forced onto it (K2B_GREEDY_PERSISTENT=1) against the 16-CTA cluster kernel."""
