@@ -397,9 +397,10 @@ __global__ void __maxnreg__(K2B_CLUSTER_MAXREG) cluster_beam_kernel(const Cluste
     for (int kb = nt; kb < nkb; ++kb)
       tma_bulk_g2s(w_hi + (size_t)(kb - nt) * 16384, a.wo_hi_img + ((size_t)rank * nkb + kb) * 16384, 16384, &bar_w);
   }
-  if (nt > 0 && warp < 4) {
-    const uint32_t* src = a.wo_hi_rows + ((size_t)rank * 128 + tid) * (J / 2);
-    for (int c0 = 0; c0 < nt * 32; c0 += 32) {
+  // (every worker warp takes part: a warp reaches the 32 TMEM lanes of its quarter, the four warps of a quarter share the columns)
+  if (nt > 0 && worker) {
+    const uint32_t* src = a.wo_hi_rows + ((size_t)rank * 128 + 32 * (warp & 3) + lane) * (J / 2);
+    for (int c0 = 32 * (warp >> 2); c0 < nt * 32; c0 += 32 * (kWorkers / 4)) {
       uint32_t v[32];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -410,9 +411,9 @@ __global__ void __maxnreg__(K2B_CLUSTER_MAXREG) cluster_beam_kernel(const Cluste
     }
     tmem_st_wait();
   }
-  if (X3 && warp < 4) {
-    const uint32_t* src = a.wo_lo + ((size_t)rank * 128 + tid) * (J / 2);
-    for (int c0 = 0; c0 < J / 2; c0 += 32) {
+  if (X3 && worker) {
+    const uint32_t* src = a.wo_lo + ((size_t)rank * 128 + 32 * (warp & 3) + lane) * (J / 2);
+    for (int c0 = 32 * (warp >> 2); c0 < J / 2; c0 += 32 * (kWorkers / 4)) {
       uint32_t v[32];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
