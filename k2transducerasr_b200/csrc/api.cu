@@ -217,6 +217,26 @@ int32_t beam_cluster_path(k2b_handle* h, const float* enc, int enc_is_raw, int B
   return beam_backtrace_dev(h, B, K, T, fin_lp, fin_len, fin_nlive, bp, tokens, ts, n_out, score, cap, K > 1 ? cluster_cst(h, B, K) : nullptr);
 }
 
+// Time chunks of a host-pointer call: short chunks at both ends, equal long ones between them. The first chunk's copy and the last
+// chunk's search are the two pieces nothing can hide (copy-bound: the tail; search-bound: the head), so both are kept at 8 frames;
+// the chunks in between are long so that the ~25 us of set-up per launch stays small against them.
+static std::vector<int> chunk_schedule(int T, int nchunk_fixed, int big) {
+  std::vector<int> v;
+  if (nchunk_fixed >= 1) {
+    const int Tc = (T + nchunk_fixed - 1) / nchunk_fixed;
+    for (int t0 = 0; t0 < T; t0 += Tc) v.push_back((T - t0) < Tc ? (T - t0) : Tc);
+    return v;
+  }
+  std::vector<int> tail;
+  int rest = T;
+  if (T >= 32) { v.push_back(8); tail.push_back(8); rest -= 16; }
+  if (T >= 128) { v.push_back(16); tail.insert(tail.begin(), 16); rest -= 32; }
+  const int nmid = (rest + big - 1) / big;
+  for (int i = 0; i < nmid; ++i) v.push_back(rest / nmid + (i < rest % nmid ? 1 : 0));
+  v.insert(v.end(), tail.begin(), tail.end());
+  return v;
+}
+
 // Host-pointer modified_beam_search with the input copy hidden behind the search: the batch is cut into time chunks;
 // chunk c+1 crosses PCIe (strided 2-D copy into a compact [B,Tc,E] staging buffer, on a copy stream) while chunk c is
 // projected and decoded (one cluster-kernel launch per chunk, hypothesis state carried through global memory).
@@ -225,11 +245,11 @@ int32_t beam_cluster_pipelined(k2b_handle* h, const float* enc_host, int enc_is_
   K2B_TRY(ensure_cluster_assets(h));
   const int J = h->cfg.joiner_dim;
   const int E = enc_is_raw ? h->cfg.encoder_dim : J;      // width of what crosses PCIe: raw frames, or the seam's projected ones
-  // up to 10 chunks of at least 8 frames: measured on cfg2 (PCIe-bound, 196 MB in) 4 chunks 4.04 ms, 8 chunks 3.85 ms, 12 chunks
-  // 3.81 ms per batch - the un-overlapped tail (last chunk's projection + search) shrinks, each extra launch costs ~30 us
-  int nchunk = T / 8 < 10 ? (T / 8 > 0 ? T / 8 : 1) : 10;
-  if (h->opt_pipe_chunks >= 1) nchunk = h->opt_pipe_chunks;
-  const int Tc = (T + nchunk - 1) / nchunk;
+  // measured on cfg2 (PCIe-bound, 196 MB in) with equal chunks: 4 chunks 4.04 ms, 8 chunks 3.85 ms, 12 chunks 3.81 ms per batch - the
+  // un-overlapped tail (last chunk's projection + search) shrinks, each extra launch costs ~30 us; hence the schedule above
+  const std::vector<int> sched = chunk_schedule(T, h->opt_pipe_chunks, 32);
+  int Tc = 1;
+  for (int x : sched) Tc = x > Tc ? x : Tc;
   if (h->copy_stream == nullptr) {
     K2B_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
@@ -255,9 +275,9 @@ int32_t beam_cluster_pipelined(k2b_handle* h, const float* enc_host, int enc_is_
   // the staging buffers may still be in use by earlier work on the compute stream
   K2B_CUDA(h, cudaEventRecord(h->ev_free[0], h->stream));
   K2B_CUDA(h, cudaEventRecord(h->ev_free[1], h->stream));
-  int c = 0;
-  for (int t0 = 0; t0 < T; t0 += Tc, ++c) {
-    const int tc = (T - t0) < Tc ? (T - t0) : Tc, sb = c & 1;
+  int c = 0, t0 = 0;
+  for (size_t ci = 0; ci < sched.size(); t0 += sched[ci], ++ci, ++c) {
+    const int tc = sched[ci], sb = c & 1;
     float* stage = reinterpret_cast<float*>(static_cast<char*>(h->ws_in.p) + (size_t)sb * buf_bytes);
     K2B_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_free[sb], 0));
     K2B_TRY(h2d_rows(h, stage, sizeof(float) * (size_t)tc * E, enc_host + (size_t)t0 * E, sizeof(float) * (size_t)T * E,
@@ -294,9 +314,9 @@ int32_t beam_chunked_host(k2b_handle* h, const float* enc_host, int enc_is_raw, 
   const int J = h->cfg.joiner_dim, E = enc_is_raw ? h->cfg.encoder_dim : J;
   // each chunk is one persistent launch (~20 us of set-up); measured on cfg4 (131 MB in): 3 chunks 6.06 ms, 5 chunks 5.82 ms,
   // 8 chunks 5.64 ms, 12 chunks 5.67 ms per batch
-  int nchunk = T / 30 < 8 ? (T / 30 > 0 ? T / 30 : 1) : 8;
-  if (h->opt_pipe_chunks >= 1) nchunk = h->opt_pipe_chunks;
-  const int Tc = (T + nchunk - 1) / nchunk;
+  const std::vector<int> sched = chunk_schedule(T, h->opt_pipe_chunks, 32);
+  int Tc = 1;
+  for (int x : sched) Tc = x > Tc ? x : Tc;
   if (h->copy_stream == nullptr) {
     K2B_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
@@ -310,9 +330,9 @@ int32_t beam_chunked_host(k2b_handle* h, const float* enc_host, int enc_is_raw, 
   float* encP = static_cast<float*>(h->ws_encproj.p);
   K2B_CUDA(h, cudaEventRecord(h->ev_free[0], h->stream));
   K2B_CUDA(h, cudaEventRecord(h->ev_free[1], h->stream));
-  int c = 0;
-  for (int t0 = 0; t0 < T; t0 += Tc, ++c) {
-    const int tc = (T - t0) < Tc ? (T - t0) : Tc, sb = c & 1;
+  int c = 0, t0 = 0;
+  for (size_t ci = 0; ci < sched.size(); t0 += sched[ci], ++ci, ++c) {
+    const int tc = sched[ci], sb = c & 1;
     K2B_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_free[sb], 0));
     if (enc_is_raw) {
       float* stage = reinterpret_cast<float*>(static_cast<char*>(h->ws_in.p) + (size_t)sb * buf_bytes);
