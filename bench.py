@@ -5,7 +5,8 @@ A "step" is one pass of the hot path over one batch of synthetic input of the na
 config BASELINE.json's metric is quoted on (zipformer-large-en offline, modified_beam_search beam=4, 256 utterances x 250 frames,
 vocab 500, E=768): encoder_proj -> per frame {stateless decoder, fused joiner + log-softmax/top-k, hypothesis merge} -> best
 hypothesis per stream. One independent batch per GPU (weak scaling), no data-path collective; with more than one rank every step
-ends with ONE all-gather of all ranks' results over NVLink (k2b_gather_results_nccl), inside the timed region of `value`.
+ends with ONE all-gather of all ranks' results over NVLink (k2b_gather_results_nccl, on a side stream under the next step's search;
+the timed region of `value` ends behind the last one).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg1|cfg2|cfg3|cfg4|cfg5]
     torchrun ... bench.py --gpus N ...      (one rank per GPU)
@@ -435,6 +436,10 @@ def run_ours(args, cfg):
         a_n = torch.zeros((world, B), dtype=torch.int32, device=dev); a_sc = torch.zeros((world, B), dtype=torch.float32, device=dev)
         with_score = cfg.mode == "mbs"
 
+        # the gather of batch i runs on a side stream under the search of batch i+1 (the library orders its next back-trace, the
+        # first kernel that overwrites these result buffers, behind it); the timed region ends behind the last gather (gather_join)
+        h.set_option("async_gather", 1)
+
         def gather():
             h.call("k2b_gather_results_nccl", wk.d_tok, wk.d_ts, wk.d_n, wk.d_sc if with_score else None, B, wk.cap,
                    a_tok, a_ts, a_n, a_sc if with_score else None)
@@ -456,6 +461,8 @@ def run_ours(args, cfg):
         e0.record(stream)
         for i in range(steps):
             fn(i)
+        if gather is not None:
+            h.call("k2b_gather_join")
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)

@@ -96,6 +96,7 @@ namespace K2TransducerAsr.B200
         [DllImport(Lib)] public static extern int k2b_nccl_init(IntPtr h, byte[] id128, int rank, int nranks);
         [DllImport(Lib)] public static extern int k2b_gather_results_nccl(IntPtr h, IntPtr tokens, IntPtr ts, IntPtr n, IntPtr score, int B, int cap,
             IntPtr all_tokens, IntPtr all_ts, IntPtr all_n, IntPtr all_score);
+        [DllImport(Lib)] public static extern int k2b_gather_join(IntPtr h);
         // contextual biasing (hot words): dense automaton over token ids, built on the host (hotwords.py shows the construction)
         [DllImport(Lib)] public static extern int k2b_set_context_graph(IntPtr h, int[]? next, float[]? delta, float[]? residual, int n_states);
         [DllImport(Lib)] public static extern int k2b_debug_backpointers(IntPtr h, [Out] int[] outp, int B, int T, int K);

@@ -112,6 +112,9 @@ K2B_API int32_t k2b_sync(k2b_handle* h);
  *   "async_d2h" 0/1            host-pointer fused calls return once their copies are enqueued (give them pinned buffers, see
  *                              k2b_host_alloc); k2b_sync() completes them. Lets batch i's results leave while batch i+1 arrives.
  *   "pipe_chunks" 0..64        time chunks of the host-pointer beam search (0 = automatic)
+ *   "async_gather" 0/1         k2b_gather_results_nccl on a side stream (see there)
+ *   "copy_threads" -1..64      host threads that stage PAGEABLE inputs into the library's page-locked bounce buffers (-1 = a quarter of
+ *                              the host's threads, 2..8; 0 = the calling thread copies). Page-locked inputs need none.
  *   "no_mega", "unfused_step", "greedy_persistent" (-1 auto / 0 / 1), "pair", "prof_which", "cluster_timing" (0 = off),
  *   "wh_tmem_kb" (-1 auto / 0), "single_greedy" (0 / 1), "dev_chunks" (-1 auto / 1 / 2), "tagged_records" (0 / 1), "ctc_one_kernel" (-1 by input size / 0 / 1):
  *                              comparison switches between engines that must give identical results.        */
@@ -260,11 +263,16 @@ K2B_API int32_t k2b_unstack_states(k2b_handle* h, const int32_t* slots, int32_t 
  * hands it to the other ranks by any means (bench.py: torch.distributed broadcast), every rank calls k2b_nccl_init once.
  * k2b_gather_results_nccl: DEVICE pointers; tokens / ts [B,cap], n / score [B] of this rank in, rank-major [nranks*B, ...] out;
  * enqueued on the handle's stream behind the search that produced the inputs, no host synchronisation. B and cap must be the same
- * on every rank. score / all_score may both be NULL.                                                                           */
+ * on every rank. score / all_score may both be NULL.
+ * With k2b_set_option("async_gather", 1) the gather runs on a side stream behind an event of the handle's stream, so the next
+ * batch's search starts without waiting for it: the library orders its own later writes to result buffers behind it (the cluster
+ * beam search only its back-trace, every other call as a whole); all_* are complete after k2b_gather_join (stream order, no host
+ * synchronisation) or k2b_sync.                                                                                                */
 K2B_API int32_t k2b_nccl_unique_id(void* id128);
 K2B_API int32_t k2b_nccl_init(k2b_handle* h, const void* id128, int32_t rank, int32_t nranks);
 K2B_API int32_t k2b_gather_results_nccl(k2b_handle* h, const int64_t* tokens, const int32_t* ts, const int32_t* n, const float* score,
                                         int32_t B, int32_t cap, int64_t* all_tokens, int32_t* all_ts, int32_t* all_n, float* all_score);
+K2B_API int32_t k2b_gather_join(k2b_handle* h);
 
 /* ---- diagnostics ---------------------------------------------------------------------------- */
 /* Back-pointer rows of the LAST beam search of this handle, HOST pointer [B,T,K] int32: entry = (parent slot << 28) | (appended

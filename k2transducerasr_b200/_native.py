@@ -80,6 +80,7 @@ _SIGS = {
     "k2b_nccl_unique_id": (C.c_int32, [_P]),
     "k2b_nccl_init": (C.c_int32, [_P, _P, _I, _I]),
     "k2b_gather_results_nccl": (C.c_int32, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
+    "k2b_gather_join": (C.c_int32, [_P]),
     "k2b_debug_backpointers": (C.c_int32, [_P, _P, _I, _I, _I]),
     "k2b_selftest_umma": (C.c_int32, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "k2b_state_pool_create": (C.c_int32, [_P, _P, _I, _I]),

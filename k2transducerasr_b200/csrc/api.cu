@@ -91,12 +91,14 @@ void free_cluster_assets(k2b_handle* h) {
   h->wd_ready = false;
 }
 
-int32_t enter(k2b_handle* h) {
+// join = false: the caller orders its stream behind an outstanding side-stream gather itself, in front of the first kernel that
+// writes caller-owned result buffers (the gather may still be reading them)
+int32_t enter(k2b_handle* h, bool join = true) {
   if (h == nullptr) return K2B_ERR_INVALID;
   if (h->poisoned) return K2B_ERR_STATE;
   cudaError_t e = cudaSetDevice(h->cfg.device);
   if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice", __FILE__, __LINE__);
-  return K2B_OK;
+  return join ? gather_join(h) : K2B_OK;
 }
 
 int32_t upload(k2b_handle* h, float** dst, const float* src, size_t n) {
@@ -186,6 +188,7 @@ int32_t beam_cluster_path(k2b_handle* h, const float* enc, int enc_is_raw, int B
     K2B_CUDA(h, cudaEventRecord(h->ev_ready[0], h->copy_stream));
     K2B_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_ready[0], 0));
     K2B_TRY(beam_cluster_dev(h, encE, B, tB, K, bp, fin_lp, fin_len, fin_nlive, extra_mask, nullptr, nullptr, tA, T, 1, io_ctx, io_hash, need_lp2));
+    K2B_TRY(gather_join(h));               // the back-trace is the first kernel that writes the caller's result buffers
     return beam_backtrace_dev(h, B, K, T, fin_lp, fin_len, fin_nlive, bp, tokens, ts, n_out, score, cap, K > 1 ? cluster_cst(h, B, K) : nullptr);
   }
   if (enc_is_raw) {
@@ -214,6 +217,7 @@ int32_t beam_cluster_path(k2b_handle* h, const float* enc, int enc_is_raw, int B
   int32_t* bp = static_cast<int32_t*>(h->ws_bp.p);
   K2B_TRY(beam_cluster_dev(h, encE, B, T, K, bp, fin_lp, fin_len, fin_nlive, extra_mask, hyp_inout, hyp_inout, 0, 0, 0, nullptr, nullptr,
                            need_lp));
+  K2B_TRY(gather_join(h));
   return beam_backtrace_dev(h, B, K, T, fin_lp, fin_len, fin_nlive, bp, tokens, ts, n_out, score, cap, K > 1 ? cluster_cst(h, B, K) : nullptr);
 }
 
@@ -492,6 +496,16 @@ int32_t k2b_set_option(k2b_handle* h, const char* name, int32_t value) {
   else if (n == "ctc_one_kernel") h->opt_ctc_one_kernel = value;
   else if (n == "prof_which") h->prof_which = value;
   else if (n == "async_d2h") h->opt_async_d2h = value;
+  else if (n == "async_gather") h->opt_async_gather = value;
+  else if (n == "copy_threads") {
+    if (value < -1 || value > 64) return fail(h, K2B_ERR_INVALID, "copy_threads: -1 (auto) .. 64");
+    if (value != h->opt_copy_threads) {                        // the pool is rebuilt with the new size by the next pageable copy
+      K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+      if (h->copy_stream != nullptr) K2B_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+      host_stage_free(h);
+    }
+    h->opt_copy_threads = value;
+  }
   else if (n == "max_sym_per_frame") {
     if (value < 1 || value > 16) return fail(h, K2B_ERR_INVALID, "max_sym_per_frame: 1 .. 16");
     h->max_sym_per_frame = value;
@@ -1050,7 +1064,7 @@ int32_t k2b_greedy_online_chunk(k2b_handle* h, const float* enc, int32_t enc_is_
 
 int32_t k2b_modified_beam_search_dev(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t T, int32_t K,
                                      int64_t* tokens, int32_t* ts, int32_t* n_out, float* score, int32_t cap) {
-  K2B_TRY(enter(h));
+  K2B_TRY(enter(h, false));
   K2B_TRY(need_weights(h));
   LensGuard lens_guard(h);
   K2B_TRY(check_search_args(h, enc, B, T, cap, tokens, ts, n_out, "k2b_modified_beam_search"));
@@ -1060,7 +1074,8 @@ int32_t k2b_modified_beam_search_dev(k2b_handle* h, const float* enc, int32_t en
   if (B > 0 && score == nullptr) return fail(h, K2B_ERR_INVALID, "k2b_modified_beam_search: score is NULL");
   if (B == 0) return K2B_OK;
   if (h->cfg.precision != K2B_PREC_FP32 && cluster_path_supported(h, K) && T > 0)
-    return beam_cluster_path(h, enc, enc_is_raw, B, T, K, tokens, ts, n_out, score, cap);
+    return beam_cluster_path(h, enc, enc_is_raw, B, T, K, tokens, ts, n_out, score, cap);   // joins in front of its back-trace
+  K2B_TRY(gather_join(h));
   const float* frames = nullptr;
   K2B_TRY(frames_for_search(h, enc, enc_is_raw, B, T, &frames));
   return beam_dev(h, frames, B, T, K, tokens, ts, n_out, score, cap);

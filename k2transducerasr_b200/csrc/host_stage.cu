@@ -97,6 +97,7 @@ static int32_t ensure_stage(k2b_handle* h) {
   unsigned hw = std::thread::hardware_concurrency();
   int n = (int)(hw / 4);                                        // copy threads: a quarter of the host's (several ranks share it)
   n = n > 8 ? 8 : (n < 2 ? (hw >= 4 ? 2 : 0) : n);
+  if (h->opt_copy_threads >= 0) n = h->opt_copy_threads;
   s->start(n);
   return K2B_OK;
 }

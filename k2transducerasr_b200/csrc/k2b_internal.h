@@ -120,6 +120,8 @@ struct k2b_handle {
   k2b::HostStage* host_stage = nullptr;   // page-locked bounce buffers + copy threads for pageable inputs (host_stage.cu)
   int max_sym_per_frame = 1;              // k2b_set_option("max_sym_per_frame"): ref OfflineRecognizer.cs:19 fixes it to 1
   // engine switches (k2b_set_option; the K2B_* environment variables only give their initial values at k2b_create)
+  int opt_async_gather = 0;               // 1: k2b_gather_results_nccl runs on a side stream (k2b_gather_join / k2b_sync order behind it)
+  int opt_copy_threads = -1;              // host threads staging pageable inputs (-1: a quarter of the host's, 2 .. 8)
   int opt_pipe_chunks = 0;                // > 0: number of time chunks of the host-pointer beam search
   int opt_no_mega = 0;                    // large-vocabulary beam search as per-frame launches instead of the persistent launch
   int opt_unfused_step = 0;               // the three-launch frame step
@@ -284,6 +286,7 @@ void host_stage_free(k2b_handle* h);
 
 // ---- nccl_gather.cu ------------------------------------------------------------------------------------------
 void nccl_free(k2b_handle* h);
+int32_t gather_join(k2b_handle* h);       // the handle's stream waits for an outstanding side-stream gather ("async_gather")
 
 // ---- encproj_tc.cu -----------------------------------------------------------------------------
 bool encproj_tc_supported(const k2b_handle* h);

@@ -69,13 +69,32 @@ constexpr int kNcclChar = 0;       // ncclInt8 / ncclChar: everything is gathere
 struct NcclState {
   nccl_comm_t comm = nullptr;
   int rank = 0, nranks = 1;
+  // "async_gather": the gather runs on its own stream so that the next batch's search does not wait for it
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_src = nullptr, ev_done = nullptr;
+  bool pending = false;                  // a gather on `side` that the handle's stream has not been ordered behind yet
 };
 
 void nccl_free(k2b_handle* h) {
   if (h->nccl == nullptr) return;
+  if (h->nccl->side != nullptr) {
+    cudaStreamSynchronize(h->nccl->side);
+    cudaEventDestroy(h->nccl->ev_src);
+    cudaEventDestroy(h->nccl->ev_done);
+    cudaStreamDestroy(h->nccl->side);
+  }
   if (h->nccl->comm != nullptr && api().destroy != nullptr) api().destroy(h->nccl->comm);
   delete h->nccl;
   h->nccl = nullptr;
+}
+
+// Orders the handle's stream behind an outstanding side-stream gather (no host synchronisation). Called by every entry point
+// before it may overwrite result buffers a gather could still be reading; the cluster beam search defers it to its back-trace.
+int32_t gather_join(k2b_handle* h) {
+  if (h->nccl == nullptr || !h->nccl->pending) return K2B_OK;
+  K2B_CUDA(h, cudaStreamWaitEvent(h->stream, h->nccl->ev_done, 0));
+  h->nccl->pending = false;
+  return K2B_OK;
 }
 
 }  // namespace k2b
@@ -115,7 +134,8 @@ int32_t k2b_nccl_init(k2b_handle* h, const void* id128, int32_t rank, int32_t nr
 
 // Every rank passes the DEVICE buffers one fused search call filled for its own B streams ([B,cap] tokens / ts, [B] n / score;
 // score may be NULL) and receives all ranks' results, rank-major, in DEVICE buffers of nranks times that size. Enqueued on the
-// handle's stream (ordered behind the search that produced the inputs); no host synchronisation.
+// handle's stream (ordered behind the search that produced the inputs), or with "async_gather" on a side stream behind an event
+// of the handle's stream; no host synchronisation.
 int32_t k2b_gather_results_nccl(k2b_handle* h, const int64_t* tokens, const int32_t* ts, const int32_t* n, const float* score,
                                 int32_t B, int32_t cap, int64_t* all_tokens, int32_t* all_ts, int32_t* all_n, float* all_score) {
   if (h == nullptr) return K2B_ERR_INVALID;
@@ -126,15 +146,42 @@ int32_t k2b_gather_results_nccl(k2b_handle* h, const int64_t* tokens, const int3
     return fail(h, K2B_ERR_INVALID, "k2b_gather_results_nccl: bad arguments");
   if (B == 0) return K2B_OK;
   NcclApi& a = api();
-  nccl_comm_t c = h->nccl->comm;
+  NcclState* st = h->nccl;
+  nccl_comm_t c = st->comm;
+  cudaStream_t on = h->stream;
+  if (h->opt_async_gather != 0) {
+    if (st->side == nullptr) {
+      int lo = 0, hi = 0;
+      K2B_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      K2B_CUDA(h, cudaStreamCreateWithPriority(&st->side, cudaStreamNonBlocking, hi));
+      K2B_CUDA(h, cudaEventCreateWithFlags(&st->ev_src, cudaEventDisableTiming));
+      K2B_CUDA(h, cudaEventCreateWithFlags(&st->ev_done, cudaEventDisableTiming));
+    }
+    K2B_CUDA(h, cudaEventRecord(st->ev_src, h->stream));              // behind the search that produced the inputs
+    K2B_CUDA(h, cudaStreamWaitEvent(st->side, st->ev_src, 0));
+    on = st->side;
+  } else {
+    K2B_TRY(gather_join(h));
+  }
   int rc = a.group_start();
-  if (rc == 0 && cap > 0) rc = a.all_gather(tokens, all_tokens, sizeof(int64_t) * (size_t)B * cap, kNcclChar, c, h->stream);
-  if (rc == 0 && cap > 0) rc = a.all_gather(ts, all_ts, sizeof(int32_t) * (size_t)B * cap, kNcclChar, c, h->stream);
-  if (rc == 0) rc = a.all_gather(n, all_n, sizeof(int32_t) * (size_t)B, kNcclChar, c, h->stream);
-  if (rc == 0 && score != nullptr) rc = a.all_gather(score, all_score, sizeof(float) * (size_t)B, kNcclChar, c, h->stream);
+  if (rc == 0 && cap > 0) rc = a.all_gather(tokens, all_tokens, sizeof(int64_t) * (size_t)B * cap, kNcclChar, c, on);
+  if (rc == 0 && cap > 0) rc = a.all_gather(ts, all_ts, sizeof(int32_t) * (size_t)B * cap, kNcclChar, c, on);
+  if (rc == 0) rc = a.all_gather(n, all_n, sizeof(int32_t) * (size_t)B, kNcclChar, c, on);
+  if (rc == 0 && score != nullptr) rc = a.all_gather(score, all_score, sizeof(float) * (size_t)B, kNcclChar, c, on);
   const int rc2 = a.group_end();
   if (rc != 0 || rc2 != 0) return fail(h, K2B_ERR_CUDA, "k2b_gather_results_nccl: " + nccl_msg(rc != 0 ? rc : rc2));
+  if (on == st->side) {
+    K2B_CUDA(h, cudaEventRecord(st->ev_done, st->side));
+    st->pending = true;
+  }
   return K2B_OK;
+}
+
+int32_t k2b_gather_join(k2b_handle* h) {
+  if (h == nullptr) return K2B_ERR_INVALID;
+  if (h->poisoned) return K2B_ERR_STATE;
+  K2B_CUDA(h, cudaSetDevice(h->cfg.device));
+  return gather_join(h);
 }
 
 }  // extern "C"

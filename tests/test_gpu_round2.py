@@ -526,6 +526,12 @@ def test_pinned_host_buffers_and_async_results(built_lib):
     t, s, sc = h.modified_beam_search(reg, K)
     assert t == ref[0][0]
     assert _native.lib().k2b_host_unregister(reg.ctypes.data) == 0
+    # pageable arrays are staged by the library's own copy threads: any pool size (0 = the calling thread copies) gives the same
+    for th in (0, 1, 3, -1):
+        h.set_option("copy_threads", th)
+        for i in range(2):
+            t, s, sc = h.modified_beam_search(raws[i], K)
+            assert t == ref[i][0] and s == ref[i][1]
     h.close()
 
 
@@ -552,6 +558,33 @@ def test_nccl_gather_single_rank(built_lib):
         k = int(n[b])
         assert torch.equal(atok[b, :k], tok[b, :k]) and torch.equal(ats[b, :k], ts[b, :k])
     assert int(n.sum()) > 0
+    # "async_gather": the gather of batch A runs on a side stream while batch B is searched INTO THE SAME result buffers; the
+    # library orders B's back-trace (cluster engine) / B's whole call (other engines) behind the gather, so all_* hold A's results
+    raw_b = torch.from_numpy(synth.make_frames(B, T, MID.encoder_dim, 6)).cuda()
+    h.set_option("async_gather", 1)
+    for prec in ("fp32", "bf16x3"):
+        h.set_precision(_native.PREC_NAMES[prec])
+        want = {}
+        for name, x in (("a", raw), ("b", raw_b)):
+            h.call("k2b_modified_beam_search_dev", x, 1, B, T, K, tok, ts, n, sc, T)
+            h.sync()
+            want[name] = (tok.clone(), ts.clone(), n.clone(), sc.clone())
+        for rep in range(3):
+            for o in (atok, ats, an, asc):
+                o.fill_(-1)
+            h.call("k2b_modified_beam_search_dev", raw, 1, B, T, K, tok, ts, n, sc, T)
+            h.call("k2b_gather_results_nccl", tok, ts, n, sc, B, T, atok, ats, an, asc)
+            h.call("k2b_modified_beam_search_dev", raw_b, 1, B, T, K, tok, ts, n, sc, T)
+            if rep == 0:
+                h.call("k2b_gather_join")
+            h.sync()
+            assert torch.equal(an, want["a"][2]) and torch.equal(asc, want["a"][3]), prec
+            assert torch.equal(n, want["b"][2]) and torch.equal(sc, want["b"][3]), prec
+            for b in range(B):
+                k = int(an[b])
+                assert torch.equal(atok[b, :k], want["a"][0][b, :k]) and torch.equal(ats[b, :k], want["a"][1][b, :k])
+                k = int(n[b])
+                assert torch.equal(tok[b, :k], want["b"][0][b, :k])
     h.close()
 
 
