@@ -420,6 +420,12 @@ def run_ours(args, cfg):
     h.set_stream(stream.cuda_stream)
     wk = Work(args, cfg, h, torch, dev, rank, B)
     T = wk.T
+    # the device-resident batches exist before the first timed call, which is what this option promises: the library may project
+    # batch i+1's frames on a side stream under batch i's search instead of ordering that behind the handle's stream
+    h.set_option("inputs_complete", args.inputs_complete)
+    for env, opt in (("K2B_DEV_CHUNK_SHIFT", "dev_chunk_shift"), ("K2B_DEV_CHUNKS", "dev_chunks")):     # experiments
+        if os.environ.get(env):
+            h.set_option(opt, int(os.environ[env]))
 
     # all ranks' results in one all-gather per step (device buffers, NVLink), when there is more than one rank
     gather = None
@@ -600,7 +606,9 @@ def run_ours(args, cfg):
                            "parallelism": f"dp{world} (independent batches" + (", one all-gather of the results per step)" if gather else ")"),
                            "l2": (f"inputs ({inb / 1e6:.0f} MB/step, 2 alternating batches) larger than the 126 MB L2" if inb > 126e6 else
                                   f"inputs {inb / 1e6:.1f} MB/step, 2 alternating batches; weights + memoised decoder rows are L2 / HBM resident by design"),
-                           "blank_bias": cfg.blank_bias, "regime": args.regime, "weights": "random-init, seed 7", **stats},
+                           "blank_bias": cfg.blank_bias, "regime": args.regime, "weights": "random-init, seed 7",
+                           "device_inputs": ("complete before the call (inputs_complete=1): batch i+1 is projected under batch i's search"
+                                             if args.inputs_complete else "ordered on the handle's stream"), **stats},
                 "e2e": e2e, **extra,
                 "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline}
         if cpu is not None:
@@ -627,6 +635,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="strong: the config's batch is split over the ranks (cfg2: 256 streams -> 32 per GPU at 8 GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inputs-complete", type=int, default=1, choices=[0, 1],
+                    help="k2b_set_option(inputs_complete): device-resident frames are complete at call time (default 1)")
     ap.add_argument("--quick", action="store_true", help="skip the extra e2e legs (pageable / projected / async / copy ceiling)")
     ap.add_argument("--regime", default="speech", choices=["speech", "raw"],
                     help="speech: blank bias calibrated so that 70-80 %% of the frames are blank (default); raw: random-init joiner as is, "

@@ -112,11 +112,17 @@ K2B_API int32_t k2b_sync(k2b_handle* h);
  *   "async_d2h" 0/1            host-pointer fused calls return once their copies are enqueued (give them pinned buffers, see
  *                              k2b_host_alloc); k2b_sync() completes them. Lets batch i's results leave while batch i+1 arrives.
  *   "pipe_chunks" 0..64        time chunks of the host-pointer beam search (0 = automatic)
+ *   "inputs_complete" 0/1      1: the caller promises that frames handed to the _dev entry points are complete in device memory when
+ *                              the call is made (an encoder that ran on another stream and was synchronised), not merely ordered on
+ *                              the handle's stream. The device-pointer beam search (which projects raw frames in time chunks on
+ *                              a side stream while one search launch polls per-chunk "projected" flags, "dev_chunks" 3) then does
+ *                              not order that side stream behind earlier work of the handle's stream: the next call's frames are
+ *                              projected under the current call's search.
  *   "async_gather" 0/1         k2b_gather_results_nccl on a side stream (see there)
  *   "copy_threads" -1..64      host threads that stage PAGEABLE inputs into the library's page-locked bounce buffers (-1 = a quarter of
  *                              the host's threads, 2..8; 0 = the calling thread copies). Page-locked inputs need none.
  *   "no_mega", "unfused_step", "greedy_persistent" (-1 auto / 0 / 1), "pair", "prof_which", "cluster_timing" (0 = off),
- *   "wh_tmem_kb" (-1 auto / 0), "single_greedy" (0 / 1), "dev_chunks" (-1 auto / 1 / 2), "tagged_records" (0 / 1), "ctc_one_kernel" (-1 by input size / 0 / 1):
+ *   "wh_tmem_kb" (-1 auto / 0), "single_greedy" (0 / 1), "dev_chunks" (-1 auto / 1 / 2 / 3), "dev_chunk_shift" (3..10), "tagged_records" (0 / 1), "ctc_one_kernel" (-1 by input size / 0 / 1):
  *                              comparison switches between engines that must give identical results.        */
 K2B_API int32_t k2b_set_option(k2b_handle* h, const char* name, int32_t value);
 /* "decoder_table_bytes", "decoder_table_build_ms", "decoder_table_state" (0 not built, 1 built, -1 does not fit).               */

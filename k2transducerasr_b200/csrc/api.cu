@@ -133,6 +133,84 @@ int32_t frames_for_search(k2b_handle* h, const float* enc_dev, int enc_is_raw, i
   return K2B_OK;
 }
 
+// Device-pointer search on raw frames with the encoder_proj GEMM hidden under the search, ONE cluster-kernel launch: the frames are
+// projected in time chunks of 32 on a low-priority side stream (on the SMs the cluster kernel leaves free); after each chunk a
+// one-thread kernel releases "chunk c is there" (an epoch in la_flags[c]); the running search polls the flag of a chunk in front of
+// that chunk's first frame load. Only the first chunk's GEMM is waited for with an event in front of the launch (it has the whole
+// GPU). The cluster kernel must leave SMs free while it polls, so this form is used only when its grid is at least 16 SMs smaller
+// than the device (cfg2: 128 of 148). Two projected-frame buffers are taken in turns; the side stream waits for the last search
+// that read the buffer it is about to fill.
+// With k2b_set_option("inputs_complete", 1) the caller promises that its frames are complete in memory at call time (an encoder
+// that ran on another stream and was synchronised): the side stream is then not ordered behind the handle's stream, so when calls
+// follow each other the next call's chunks are projected under the current search and its launch finds them ready.
+constexpr int kLaFlags = 1024;
+static bool flagged_search_possible(const k2b_handle* h, int B, int T, int K) {
+  return cluster_grid_ctas(h, B, K) + 16 <= h->sm_count && ((T + (1 << h->opt_la_shift) - 1) >> h->opt_la_shift) <= kLaFlags;
+}
+static int32_t beam_cluster_flagged(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* tokens, int32_t* ts, int32_t* n_out,
+                                    float* score, int cap, int extra_mask) {
+  const size_t J = h->cfg.joiner_dim;
+  if (h->la_stream == nullptr) {
+    int lo = 0, hi = 0;
+    K2B_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    K2B_CUDA(h, cudaStreamCreateWithPriority(&h->la_stream, cudaStreamNonBlocking, lo));
+    K2B_CUDA(h, cudaEventCreateWithFlags(&h->la_ev_a, cudaEventDisableTiming));
+    K2B_CUDA(h, cudaEventCreateWithFlags(&h->la_ev_b, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) K2B_CUDA(h, cudaEventCreateWithFlags(&h->la_ev_done[i], cudaEventDisableTiming));
+    K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->la_flags), sizeof(int) * kLaFlags));
+    K2B_CUDA(h, cudaMemset(h->la_flags, 0, sizeof(int) * kLaFlags));
+  }
+  const int X = (int)(h->la_turn++ & 1u);
+  DevBuf& buf = h->ws_encproj_la[X];
+  const size_t need = sizeof(float) * (size_t)B * T * J;
+  if (need > buf.bytes) {
+    K2B_CUDA(h, cudaStreamSynchronize(h->la_stream));
+    K2B_TRY(ensure(h, buf, need));
+    h->la_done_valid[X] = false;
+  }
+  const bool cold = !h->enc_ready;
+  K2B_TRY(ensure_encproj_assets(h));        // (packs the weight images on the compute stream the first time)
+  if (cold) K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+  const size_t NK = (size_t)B * K;
+  const size_t a4 = (NK * 4 + 255) & ~size_t(255), ab = ((size_t)B * 4 + 255) & ~size_t(255);
+  K2B_TRY(ensure(h, h->ws_state, 2 * a4 + 2 * ab));
+  K2B_TRY(ensure(h, h->ws_bp, sizeof(int32_t) * (size_t)B * T * K));
+  char* q = static_cast<char*>(h->ws_state.p);
+  float* fin_lp = reinterpret_cast<float*>(q); q += a4;
+  int32_t* fin_len = reinterpret_cast<int32_t*>(q); q += a4;
+  int32_t* fin_nlive = reinterpret_cast<int32_t*>(q); q += ab;
+  const bool need_lp = score != nullptr;
+  if (score == nullptr) score = reinterpret_cast<float*>(q);
+  int32_t* bp = static_cast<int32_t*>(h->ws_bp.p);
+  float* encE = static_cast<float*>(buf.p);
+  const int epoch = ++h->la_epoch;
+  if (h->opt_inputs_complete == 0) {        // the frames (and nothing else of this call) are ordered on the handle's stream
+    K2B_CUDA(h, cudaEventRecord(h->la_ev_b, h->stream));
+    K2B_CUDA(h, cudaStreamWaitEvent(h->la_stream, h->la_ev_b, 0));
+  }
+  if (h->la_done_valid[X]) K2B_CUDA(h, cudaStreamWaitEvent(h->la_stream, h->la_ev_done[X], 0));
+  const int kLaShift = h->opt_la_shift, L = 1 << kLaShift;
+  for (int c = 0, t0 = 0; t0 < T; t0 += L, ++c) {
+    const int tc = T - t0 < L ? T - t0 : L;
+    cudaStream_t keep = h->stream;
+    h->stream = h->la_stream;
+    int32_t st = encoder_proj_tc(h, enc, B * tc, encE, true, tc, T, t0, T);
+    if (st == K2B_OK) st = cluster_set_ready(h, h->la_flags + c, epoch);
+    h->stream = keep;
+    K2B_TRY(st);
+    if (c == 0) {
+      K2B_CUDA(h, cudaEventRecord(h->la_ev_a, h->la_stream));
+      K2B_CUDA(h, cudaStreamWaitEvent(h->stream, h->la_ev_a, 0));
+      K2B_TRY(beam_cluster_dev(h, encE, B, T, K, bp, fin_lp, fin_len, fin_nlive, extra_mask, nullptr, nullptr, 0, 0, 0, nullptr, nullptr,
+                               need_lp, h->la_flags, epoch, kLaShift));
+    }
+  }
+  K2B_CUDA(h, cudaEventRecord(h->la_ev_done[X], h->stream));
+  h->la_done_valid[X] = true;
+  K2B_TRY(gather_join(h));                 // the back-trace is the first kernel that writes the caller's result buffers
+  return beam_backtrace_dev(h, B, K, T, fin_lp, fin_len, fin_nlive, bp, tokens, ts, n_out, score, cap, K > 1 ? cluster_cst(h, B, K) : nullptr);
+}
+
 // modified_beam_search on the persistent cluster kernel (tcgen05 precisions): frames -> exp(2x) (fused into the
 // encoder_proj epilogue when the frames are raw), one launch for the whole time loop, then the back-trace.
 int32_t beam_cluster_path(k2b_handle* h, const float* enc, int enc_is_raw, int B, int T, int K, int64_t* tokens, int32_t* ts,
@@ -145,7 +223,12 @@ int32_t beam_cluster_path(k2b_handle* h, const float* enc, int enc_is_raw, int B
   // of the frames runs on a side stream (on the SMs the search leaves free) under the search of the first half; the search is two
   // launches with the hypothesis state carried through global memory, as in the host-pointer call. cfg2: 1.43 -> ~1.34 ms per batch.
   const bool two = enc_is_raw && hyp_inout == nullptr && encproj_tc_supported(h) && h->cfg.encoder_dim > 0 && h->enc_w != nullptr &&
-                   (h->opt_dev_chunks < 0 ? (T >= 64 && (long long)B * K >= 512) : h->opt_dev_chunks == 2) && !h->profile_on;
+                   (h->opt_dev_chunks < 0 ? (T >= 64 && (long long)B * K >= 512) : h->opt_dev_chunks >= 2) && !h->profile_on;
+  // measured on cfg2 (ms per batch, end of round 2): one launch behind the whole projection 1.395, two launches with events 1.365,
+  // one polling launch 1.314, and 1.253 when its projections may run ahead of the handle's stream ("inputs_complete"); chunks of
+  // 16 / 64 frames instead of 32: 1.67 / 1.35 (1.54 / 1.29 with "inputs_complete")
+  if (two && (h->opt_dev_chunks < 0 || h->opt_dev_chunks == 3) && flagged_search_possible(h, B, T, K))
+    return beam_cluster_flagged(h, enc, B, T, K, tokens, ts, n_out, score, cap, extra_mask);
   if (two) {
     const int tA = T / 2, tB = T - tA;
     if (h->copy_stream == nullptr) {
@@ -497,6 +580,8 @@ int32_t k2b_set_option(k2b_handle* h, const char* name, int32_t value) {
   else if (n == "prof_which") h->prof_which = value;
   else if (n == "async_d2h") h->opt_async_d2h = value;
   else if (n == "async_gather") h->opt_async_gather = value;
+  else if (n == "inputs_complete") h->opt_inputs_complete = value;
+  else if (n == "dev_chunk_shift") { if (value < 3 || value > 10) return fail(h, K2B_ERR_INVALID, "dev_chunk_shift: 3 .. 10"); h->opt_la_shift = value; }
   else if (n == "copy_threads") {
     if (value < -1 || value > 64) return fail(h, K2B_ERR_INVALID, "copy_threads: -1 (auto) .. 64");
     if (value != h->opt_copy_threads) {                        // the pool is rebuilt with the new size by the next pageable copy
@@ -547,6 +632,14 @@ int32_t k2b_destroy(k2b_handle* h) {
   if (h->dev_status) cudaFree(h->dev_status);
   for (int i = 0; i < 2; ++i) { if (h->ev_ready[i]) cudaEventDestroy(h->ev_ready[i]); if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]); }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->la_stream) {
+    cudaStreamSynchronize(h->la_stream);
+    cudaEventDestroy(h->la_ev_a); cudaEventDestroy(h->la_ev_b);
+    for (int i = 0; i < 2; ++i) cudaEventDestroy(h->la_ev_done[i]);
+    cudaStreamDestroy(h->la_stream);
+  }
+  free_buf(h->ws_encproj_la[0]); free_buf(h->ws_encproj_la[1]);
+  if (h->la_flags) cudaFree(h->la_flags);
   if (h->cg_next) cudaFree(h->cg_next);
   if (h->cg_delta) cudaFree(h->cg_delta);
   if (h->cg_resid) cudaFree(h->cg_resid);

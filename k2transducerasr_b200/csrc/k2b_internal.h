@@ -97,6 +97,15 @@ struct k2b_handle {
   uint8_t* wd_lo_img = nullptr;
   cudaStream_t copy_stream = nullptr;   // host-pointer calls: H2D of time chunk c+1 overlaps compute of chunk c
   cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  // "inputs_complete" look-ahead of the device-pointer beam search (api.cu::beam_cluster_lookahead): both encoder_proj GEMMs of a
+  // call run on a low-priority side stream, i.e. under the PREVIOUS call's search; two projected-frame buffers taken in turns
+  cudaStream_t la_stream = nullptr;
+  cudaEvent_t la_ev_a = nullptr, la_ev_b = nullptr, la_ev_done[2] = {nullptr, nullptr};
+  bool la_done_valid[2] = {false, false};
+  unsigned la_turn = 0;
+  k2b::DevBuf ws_encproj_la[2];
+  int* la_flags = nullptr;                // [kLaFlags] "time chunk c is projected" epochs, polled by the running cluster kernel
+  int la_epoch = 0;
   int* dev_status = nullptr;      // [4] error flags written by the tcgen05 kernels (mbarrier time-outs)
   long long* cluster_timing = nullptr;   // device [8]: per-phase cycle totals of the cluster kernel (diagnostic)
 
@@ -120,6 +129,8 @@ struct k2b_handle {
   k2b::HostStage* host_stage = nullptr;   // page-locked bounce buffers + copy threads for pageable inputs (host_stage.cu)
   int max_sym_per_frame = 1;              // k2b_set_option("max_sym_per_frame"): ref OfflineRecognizer.cs:19 fixes it to 1
   // engine switches (k2b_set_option; the K2B_* environment variables only give their initial values at k2b_create)
+  int opt_la_shift = 5;                   // log2 of the frames per time chunk of the flagged device-pointer search
+  int opt_inputs_complete = 0;            // 1: frames handed to _dev calls are complete in memory at call time (not merely stream-ordered)
   int opt_async_gather = 0;               // 1: k2b_gather_results_nccl runs on a side stream (k2b_gather_join / k2b_sync order behind it)
   int opt_copy_threads = -1;              // host threads staging pageable inputs (-1: a quarter of the host's, 2 .. 8)
   int opt_pipe_chunks = 0;                // > 0: number of time chunks of the host-pointer beam search
@@ -266,7 +277,10 @@ int32_t exp2x_frames(k2b_handle* h, const float* in, float* out, size_t n);
 int32_t exp2x_frames_chunk(k2b_handle* h, const float* in, float* out, int B, int tc, int T, int t0);   // [B,tc,J] -> rows t0.. of [B,T,J]
 int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, int32_t* bp, float* fin_lp, int32_t* fin_len,
                          int32_t* fin_nlive, int extra_mask, const int64_t* hyp_in, int64_t* hyp_out, int t0 = 0, int Ttot = 0,
-                         int resume = 0, int32_t* io_ctx = nullptr, unsigned long long* io_hash = nullptr, bool need_lp = true);
+                         int resume = 0, int32_t* io_ctx = nullptr, unsigned long long* io_hash = nullptr, bool need_lp = true,
+                         const int* ready = nullptr, int ready_epoch = 0, int ready_shift = 0);
+int cluster_grid_ctas(const k2b_handle* h, int B, int K);            // CTAs of one cluster-kernel launch (all resident at once or not)
+int32_t cluster_set_ready(k2b_handle* h, int* flag, int epoch);      // on h->stream: *flag = epoch, released at device scope
 int32_t cluster_status(k2b_handle* h);
 
 // ---- stream_beam.cu: hypotheses carried between the chunks of a stream -----------------------------------------

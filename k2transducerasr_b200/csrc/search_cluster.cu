@@ -79,7 +79,28 @@ struct ClusterArgs {
   const int32_t* cg_next;   // [S,V]
   const float* cg_delta;    // [S,V]
   int32_t* io_cst;
+  // frames that arrive while the kernel runs (the encoder_proj GEMMs of later time chunks are on a side stream): frames
+  // [c << ready_shift, (c + 1) << ready_shift) may be read once ready[c] has reached ready_epoch; null = all frames are there.
+  // The chunk of frames t0 and t0 + 1 must be complete before the launch. The MMA warp holds back the commit of step t until the
+  // chunk of frame t + 2 is there: the worker warps load frame t + 2 (one step ahead of its use) only behind that commit, so
+  // their code is the same with and without flags (a wait in the workers' own loop cost 80 us per 250-frame launch - the
+  // compiler split the loop -, whatever the kind of load).
+  const int* ready;
+  int ready_epoch, ready_shift;
 };
+
+// polled by the MMA warp (all lanes, one address), bounded like the mbarrier waits
+__device__ __forceinline__ bool wait_frames_ready(const int* flag, int epoch) {
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (;;) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v - epoch >= 0) return true;
+    if (clock64() - t0 > kWaitTimeoutCycles) return false;
+    __nanosleep(100);
+  }
+}
 
 __device__ __forceinline__ bool better_c(float v, int i, float ev, int ei) { return v > ev || (v == ev && i > ei); }
 
@@ -523,6 +544,9 @@ __global__ void __maxnreg__(K2B_CLUSTER_MAXREG) cluster_beam_kernel(const Cluste
               }
             }
           }
+        }
+        if (a.ready != nullptr && t + 2 < T && ((a.t0 + t + 2) & ((1 << a.ready_shift) - 1)) == 0) {
+          if (!wait_frames_ready(a.ready + ((a.t0 + t + 2) >> a.ready_shift), a.ready_epoch)) ok = false;
         }
         if (PAIR) umma2_commit_e(&bar_mma, (uint16_t)(3u << (rank & ~1u)), el);
         else umma_commit_e(&bar_mma, el);
@@ -1053,13 +1077,15 @@ int32_t exp2x_frames(k2b_handle* h, const float* in, float* out, size_t n) {
 // encE: [B,T,J] frames already mapped through exp(2x). Writes bp + final state; the caller runs the back-trace.
 int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, int32_t* bp, float* fin_lp, int32_t* fin_len,
                          int32_t* fin_nlive, int extra_mask, const int64_t* hyp_in, int64_t* hyp_out, int t0, int Ttot, int resume,
-                         int32_t* io_ctx, unsigned long long* io_hash, bool need_lp) {
+                         int32_t* io_ctx, unsigned long long* io_hash, bool need_lp, const int* ready, int ready_epoch,
+                         int ready_shift) {
   const k2b_config& c = h->cfg;
   const int V = c.vocab_size, J = c.joiner_dim, CS = (V + 127) / 128;
   const int S = kNH / K;
   const int nclusters = (B + S - 1) / S;
   int* status = h->dev_status;
   ClusterArgs a;
+  a.ready = ready; a.ready_epoch = ready_epoch; a.ready_shift = ready_shift;
   a.encE = encE; a.dec_tab = h->dec_tab; a.wo_hi_img = h->wo_hi_img; a.wo_lo = h->wo_lo; a.bias = h->bias_pad;
   a.B = B; a.T = T; a.K = K; a.V = V; a.J = J; a.S = S; a.CS = CS; a.blank = c.blank_id; a.unk = c.unk_id;
   a.x3 = c.precision == K2B_PREC_BF16X3 ? 1 : 0;
@@ -1093,6 +1119,23 @@ int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, 
   K2B_CUDA(h, cudaLaunchKernelEx(&cfg, kern, a));
   prof_end(h);
   h->launches++;
+  return K2B_OK;
+}
+
+int cluster_grid_ctas(const k2b_handle* h, int B, int K) {
+  const int CS = (h->cfg.vocab_size + 127) / 128, S = kNH / K;
+  return ((B + S - 1) / S) * CS;
+}
+
+namespace {
+__global__ void set_ready_kernel(int* flag, int epoch) {
+  if (threadIdx.x == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+}
+}  // namespace
+
+int32_t cluster_set_ready(k2b_handle* h, int* flag, int epoch) {
+  set_ready_kernel<<<1, 32, 0, h->stream>>>(flag, epoch);
+  K2B_LAUNCH_CHECK(h);
   return K2B_OK;
 }
 

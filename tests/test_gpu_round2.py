@@ -535,6 +535,55 @@ def test_pinned_host_buffers_and_async_results(built_lib):
     h.close()
 
 
+def test_search_polling_for_frames_projected_on_a_side_stream(built_lib):
+    """Device-pointer beam search on raw frames, dev_chunks = 3 (the default for a batch that fills the cluster kernel): the frames
+    are projected in time chunks of 32 on a side stream while ONE cluster-kernel launch searches them, polling a per-chunk flag in
+    front of each chunk's first frame. With "inputs_complete" the side stream is not ordered behind the handle's stream (the next
+    call's chunks are projected under the current search, two projected-frame buffers in turns). Calls that follow each other
+    without a host synchronisation - different inputs, an odd frame count, ragged lengths, another engine and a host-pointer call
+    in between, a batch that grows - must equal the plain one-launch form bit for bit."""
+    m, w = model_and_weights(MID, blank_bias=0.99)
+    h = make(MID, w)
+    K = 4
+
+    def run(raws, T, lens=None):
+        res = []
+        for x in raws:
+            B = x.shape[0]
+            tok = torch.zeros((B, T), dtype=torch.int64, device="cuda"); ts = torch.zeros((B, T), dtype=torch.int32, device="cuda")
+            n = torch.zeros(B, dtype=torch.int32, device="cuda"); sc = torch.zeros(B, dtype=torch.float32, device="cuda")
+            if lens is not None:
+                h.set_encoder_out_lens(lens[:B])
+            h.call("k2b_modified_beam_search_dev", x, 1, B, T, K, tok, ts, n, sc, T)
+            res.append((tok, ts, n, sc))
+        h.sync()
+        return res
+
+    for T, ragged in ((64, False), (77, False), (64, True)):
+        raws = [torch.from_numpy(synth.make_frames(128, T, MID.encoder_dim, 900 + i)).cuda() for i in range(5)]
+        raws.append(torch.from_numpy(synth.make_frames(160, T, MID.encoder_dim, 990)).cuda())      # the buffers grow
+        lens = np.random.default_rng(T).integers(T // 2, T + 1, size=160).astype(np.int64) if ragged else None
+        torch.cuda.synchronize()
+        h.set_option("inputs_complete", 0); h.set_option("dev_chunks", 1)
+        want = run(raws, T, lens)
+        for complete in (0, 1):
+            h.set_option("dev_chunks", 3 if complete else -1); h.set_option("inputs_complete", complete)
+            n0 = h.launch_count()
+            got = run(raws, T, lens)
+            # per call: one GEMM + one flag kernel per 32-frame chunk, ONE search launch, the back-trace
+            assert h.launch_count() - n0 == len(raws) * (2 * ((T + 31) // 32) + 2), (h.launch_count() - n0, T)
+            # another engine and a host-pointer call between such calls
+            g1 = run(raws[:1], T, lens)
+            h.greedy_offline(synth.make_frames(4, 24, MID.encoder_dim, 1), 1)
+            h.modified_beam_search(synth.make_frames(24, 40, MID.encoder_dim, 2), K)
+            g2 = run(raws[1:3], T, lens)
+            for a, b in zip(want + want[:3], got + g1 + g2):
+                for x, y in zip(a, b):
+                    assert torch.equal(x, y), (T, ragged, complete)
+    h.set_option("inputs_complete", 0)
+    h.close()
+
+
 def test_nccl_gather_single_rank(built_lib):
     """k2b_nccl_unique_id / k2b_nccl_init / k2b_gather_results_nccl with one rank: the gather is the identity (the N-rank case runs
     in bench.py under torchrun; here the dlopen'ed libnccl, the communicator and the stream ordering are exercised)."""
