@@ -198,13 +198,14 @@ static int32_t beam_cluster_flagged(k2b_handle* h, const float* enc, int B, int 
     if (st == K2B_OK) st = cluster_set_ready(h, h->la_flags + c, epoch);
     h->stream = keep;
     K2B_TRY(st);
-    if (c == 0) {
-      K2B_CUDA(h, cudaEventRecord(h->la_ev_a, h->la_stream));
-      K2B_CUDA(h, cudaStreamWaitEvent(h->stream, h->la_ev_a, 0));
-      K2B_TRY(beam_cluster_dev(h, encE, B, T, K, bp, fin_lp, fin_len, fin_nlive, extra_mask, nullptr, nullptr, 0, 0, 0, nullptr, nullptr,
-                               need_lp, h->la_flags, epoch, kLaShift));
-    }
+    if (c == 0) K2B_CUDA(h, cudaEventRecord(h->la_ev_a, h->la_stream));
   }
+  // the search is enqueued behind ALL the projections in host order (on the device it only waits for the first chunk): tools
+  // that run one kernel at a time in launch order (ncu, CUDA_LAUNCH_BLOCKING) then find every flag set instead of a search that
+  // polls for a kernel which cannot start
+  K2B_CUDA(h, cudaStreamWaitEvent(h->stream, h->la_ev_a, 0));
+  K2B_TRY(beam_cluster_dev(h, encE, B, T, K, bp, fin_lp, fin_len, fin_nlive, extra_mask, nullptr, nullptr, 0, 0, 0, nullptr, nullptr,
+                           need_lp, h->la_flags, epoch, kLaShift));
   K2B_CUDA(h, cudaEventRecord(h->la_ev_done[X], h->stream));
   h->la_done_valid[X] = true;
   K2B_TRY(gather_join(h));                 // the back-trace is the first kernel that writes the caller's result buffers
