@@ -54,8 +54,8 @@ METRICS = {
     "cfg5": "encoder frames/sec decoded (CTC greedy, 128 streams/GPU)",
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (ncu --set full captures under profiles/:
-# cfg2 r02_cluster_beam_wh_tmem_full.ncu-rep, cfg4 r01_beam_mega_cfg4_T250_full.ncu-rep)
-TRAFFIC = {"cfg2": 247.8e6, "cfg4": 342.3e6, "cfg5": None, "cfg1": None, "cfg3": None}
+# cfg2 r02_cluster_beam_final_full.ncu-rep (240.49 MB read + 4.51 MB written), cfg4 r01_beam_mega_cfg4_T250_full.ncu-rep)
+TRAFFIC = {"cfg2": 245.0e6, "cfg4": 342.3e6, "cfg5": None, "cfg1": None, "cfg3": None}
 
 
 def load_peaks():
