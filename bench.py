@@ -12,7 +12,8 @@ the timed region of `value` ends behind the last one).
     torchrun ... bench.py --gpus N ...      (one rank per GPU)
 
 `value`   : frames/s with the batch already resident in HBM (device-pointer entry points), the D2H of every step's results included
-            (SURVEY.md section 8d's definition of the metric).
+            (SURVEY.md section 8d's definition of the metric): one copy per step on a copy stream, under the next step's search,
+            two result buffers written in turns; the timed region ends behind the last copy.
 `e2e`     : the same metric through the host-pointer C-ABI call a P/Invoke shim makes, from page-locked host memory, H2D and D2H
             copies inside the timed region. Beside it (extra keys, same unit): `e2e_pageable` (what a plain managed array costs),
             `e2e_projected` (the reference seam's own payload, already projected [B,T,J] frames), `e2e_async` (results of batch i
@@ -275,8 +276,21 @@ class Work:
         self.cap = self.T if cfg.mode != "greedy_online" else self.Tc
         C = cfg.chunks if cfg.mode == "greedy_online" else 1
         z = lambda shape, dt, **kw: torch.zeros(shape, dtype=dt, **kw)
-        self.d_tok = z((C, B, self.cap), torch.int64, device=dev); self.d_ts = z((C, B, self.cap), torch.int32, device=dev)
-        self.d_n = z((C, B), torch.int32, device=dev); self.d_sc = z((B,), torch.float32, device=dev)
+        # device-resident results: (tokens, ts, n, score) of a step are views of ONE buffer, so that they leave in one copy; two such
+        # buffers are written in turns, so that the copy of step i (on a copy stream) runs under the search of step i+1
+        n_tok, n_ts, n_n = C * B * self.cap * 8, C * B * self.cap * 4, C * B * 4
+        self.pack_bytes = n_tok + n_ts + n_n + B * 4
+        self.d_pack = [z((self.pack_bytes,), torch.uint8, device=dev) for _ in range(2)]
+        self.p_pack = z((self.pack_bytes,), torch.uint8).pin_memory()
+
+        def views(buf):
+            return (buf[:n_tok].view(torch.int64).view(C, B, self.cap), buf[n_tok:n_tok + n_ts].view(torch.int32).view(C, B, self.cap),
+                    buf[n_tok + n_ts:n_tok + n_ts + n_n].view(torch.int32).view(C, B), buf[n_tok + n_ts + n_n:].view(torch.float32))
+        self.d_views = [views(b) for b in self.d_pack]
+        self.last = 0                                         # the buffer the last step wrote
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ev_written = [torch.cuda.Event() for _ in range(2)]
+        self.ev_copied = [None, None]
         self.d_hyp = z((B, 2), torch.int64, device=dev)
         self.p_out = [(z((C, B, self.cap), torch.int64).pin_memory(), z((C, B, self.cap), torch.int32).pin_memory(),
                        z((C, B), torch.int32).pin_memory(), z((B,), torch.float32).pin_memory()) for _ in range(2)]
@@ -286,6 +300,11 @@ class Work:
         if cfg.mode == "greedy_online":
             self.dev_chunks = [[x[:, c * self.Tc:(c + 1) * self.Tc].contiguous() for c in range(C)] for x in self.dev_in]
             self.host_chunks = [[x[:, c * self.Tc:(c + 1) * self.Tc].contiguous().pin_memory() for c in range(C)] for x in self.host_in]
+
+    d_tok = property(lambda self: self.d_views[self.last][0])
+    d_ts = property(lambda self: self.d_views[self.last][1])
+    d_n = property(lambda self: self.d_views[self.last][2])
+    d_sc = property(lambda self: self.d_views[self.last][3])
 
     # -- sizes ------------------------------------------------------------------------------------------------
     @property
@@ -309,6 +328,9 @@ class Work:
     def step_dev(self, i):
         h, m, x = self.h, self.cfg.mode, self.dev_in[i % self.nbuf]
         B, T = self.B, self.T
+        self.last = i & 1
+        if self.ev_copied[self.last] is not None:             # the copy of step i-2 has read this buffer (long ago)
+            self.torch.cuda.current_stream().wait_event(self.ev_copied[self.last])
         if m == "mbs":
             h.call("k2b_modified_beam_search_dev", x, 1, B, T, self.K, self.d_tok, self.d_ts, self.d_n, self.d_sc, self.cap)
         elif m == "greedy_single":
@@ -338,11 +360,19 @@ class Work:
                 h.call("k2b_greedy_online_chunk", xc, raw, B, self.Tc, self.p_hyp, tok[c], ts[c], n[c], self.cap)
 
     def results_to_host(self):
-        """Asynchronous D2H of the step's results into page-locked buffers, on the launch stream."""
-        tok, ts, n, sc = self.p_out[1]
-        tok.copy_(self.d_tok, non_blocking=True); ts.copy_(self.d_ts, non_blocking=True); n.copy_(self.d_n, non_blocking=True)
-        if self.cfg.mode == "mbs":
-            sc.copy_(self.d_sc, non_blocking=True)
+        """Asynchronous D2H of the step's results (one copy) into page-locked memory, on a copy stream behind the step."""
+        torch, k = self.torch, self.last
+        self.ev_written[k].record(torch.cuda.current_stream())
+        self.copy_stream.wait_event(self.ev_written[k])
+        with torch.cuda.stream(self.copy_stream):
+            self.p_pack.copy_(self.d_pack[k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self.ev_copied[k] = ev
+
+    def join_copies(self):
+        """Orders the launch stream behind the outstanding result copies (the timed region ends behind them)."""
+        self.torch.cuda.current_stream().wait_stream(self.copy_stream)
 
     def results(self):
         """(tokens, timestamps, scores) of the last device-resident step, as Python lists (timestamps utterance-absolute)."""
@@ -469,6 +499,7 @@ def run_ours(args, cfg):
             fn(i)
         if gather is not None:
             h.call("k2b_gather_join")
+        wk.join_copies()
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
