@@ -144,22 +144,25 @@ int32_t frames_for_search(k2b_handle* h, const float* enc_dev, int enc_is_raw, i
 // that ran on another stream and was synchronised): the side stream is then not ordered behind the handle's stream, so when calls
 // follow each other the next call's chunks are projected under the current search and its launch finds them ready.
 constexpr int kLaFlags = 1024;
+static int32_t lookahead_init(k2b_handle* h) {
+  int lo = 0, hi = 0;
+  K2B_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  K2B_CUDA(h, cudaStreamCreateWithPriority(&h->la_stream, cudaStreamNonBlocking, lo));
+  K2B_CUDA(h, cudaEventCreateWithFlags(&h->la_ev_a, cudaEventDisableTiming));
+  K2B_CUDA(h, cudaEventCreateWithFlags(&h->la_ev_b, cudaEventDisableTiming));
+  for (int i = 0; i < 2; ++i) K2B_CUDA(h, cudaEventCreateWithFlags(&h->la_ev_done[i], cudaEventDisableTiming));
+  K2B_CUDA(h, cudaEventCreateWithFlags(&h->la_ev_mark, cudaEventDisableTiming));
+  K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->la_flags), sizeof(int) * kLaFlags));
+  K2B_CUDA(h, cudaMemset(h->la_flags, 0, sizeof(int) * kLaFlags));
+  return K2B_OK;
+}
 static bool flagged_search_possible(const k2b_handle* h, int B, int T, int K) {
   return cluster_grid_ctas(h, B, K) + 16 <= h->sm_count && ((T + (1 << h->opt_la_shift) - 1) >> h->opt_la_shift) <= kLaFlags;
 }
 static int32_t beam_cluster_flagged(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* tokens, int32_t* ts, int32_t* n_out,
                                     float* score, int cap, int extra_mask) {
   const size_t J = h->cfg.joiner_dim;
-  if (h->la_stream == nullptr) {
-    int lo = 0, hi = 0;
-    K2B_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    K2B_CUDA(h, cudaStreamCreateWithPriority(&h->la_stream, cudaStreamNonBlocking, lo));
-    K2B_CUDA(h, cudaEventCreateWithFlags(&h->la_ev_a, cudaEventDisableTiming));
-    K2B_CUDA(h, cudaEventCreateWithFlags(&h->la_ev_b, cudaEventDisableTiming));
-    for (int i = 0; i < 2; ++i) K2B_CUDA(h, cudaEventCreateWithFlags(&h->la_ev_done[i], cudaEventDisableTiming));
-    K2B_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->la_flags), sizeof(int) * kLaFlags));
-    K2B_CUDA(h, cudaMemset(h->la_flags, 0, sizeof(int) * kLaFlags));
-  }
+  if (h->la_stream == nullptr) K2B_TRY(lookahead_init(h));
   const int X = (int)(h->la_turn++ & 1u);
   DevBuf& buf = h->ws_encproj_la[X];
   const size_t need = sizeof(float) * (size_t)B * T * J;
@@ -187,6 +190,8 @@ static int32_t beam_cluster_flagged(k2b_handle* h, const float* enc, int B, int 
   if (h->opt_inputs_complete == 0) {        // the frames (and nothing else of this call) are ordered on the handle's stream
     K2B_CUDA(h, cudaEventRecord(h->la_ev_b, h->stream));
     K2B_CUDA(h, cudaStreamWaitEvent(h->la_stream, h->la_ev_b, 0));
+  } else if (h->la_mark_valid) {            // not before the previous call's search has been launched (see la_ev_mark)
+    K2B_CUDA(h, cudaStreamWaitEvent(h->la_stream, h->la_ev_mark, 0));
   }
   if (h->la_done_valid[X]) K2B_CUDA(h, cudaStreamWaitEvent(h->la_stream, h->la_ev_done[X], 0));
   const int kLaShift = h->opt_la_shift, L = 1 << kLaShift;
@@ -204,6 +209,8 @@ static int32_t beam_cluster_flagged(k2b_handle* h, const float* enc, int B, int 
   // that run one kernel at a time in launch order (ncu, CUDA_LAUNCH_BLOCKING) then find every flag set instead of a search that
   // polls for a kernel which cannot start
   K2B_CUDA(h, cudaStreamWaitEvent(h->stream, h->la_ev_a, 0));
+  K2B_CUDA(h, cudaEventRecord(h->la_ev_mark, h->stream));
+  h->la_mark_valid = true;
   K2B_TRY(beam_cluster_dev(h, encE, B, T, K, bp, fin_lp, fin_len, fin_nlive, extra_mask, nullptr, nullptr, 0, 0, 0, nullptr, nullptr,
                            need_lp, h->la_flags, epoch, kLaShift));
   K2B_CUDA(h, cudaEventRecord(h->la_ev_done[X], h->stream));
@@ -637,6 +644,7 @@ int32_t k2b_destroy(k2b_handle* h) {
     cudaStreamSynchronize(h->la_stream);
     cudaEventDestroy(h->la_ev_a); cudaEventDestroy(h->la_ev_b);
     for (int i = 0; i < 2; ++i) cudaEventDestroy(h->la_ev_done[i]);
+    cudaEventDestroy(h->la_ev_mark);
     cudaStreamDestroy(h->la_stream);
   }
   free_buf(h->ws_encproj_la[0]); free_buf(h->ws_encproj_la[1]);
@@ -909,6 +917,14 @@ struct LensGuard {
   explicit LensGuard(k2b_handle* hh) : h(hh) {}
   ~LensGuard() { if (h != nullptr) h->lens_active = false; }
 };
+// Host-pointer wrappers stage their input with a copy on the handle's stream and then run the device-pointer code: whatever the
+// caller promised about ITS device buffers ("inputs_complete"), the staged frames are only ordered on the handle's stream.
+struct StagedInputGuard {
+  k2b_handle* h;
+  int keep;
+  explicit StagedInputGuard(k2b_handle* hh) : h(hh), keep(hh->opt_inputs_complete) { h->opt_inputs_complete = 0; }
+  ~StagedInputGuard() { h->opt_inputs_complete = keep; }
+};
 int32_t check_lens(k2b_handle* h, int B, const char* who) {
   if (h->lens_active && h->lens_n != B) {
     return fail(h, K2B_ERR_INVALID, std::string(who) + ": k2b_set_encoder_out_lens was given " + std::to_string(h->lens_n) +
@@ -1018,6 +1034,47 @@ static int32_t greedy_fast_pass(k2b_handle* h, const float* enc, int enc_is_raw,
   }
   // large vocabulary: beam 1 on the persistent beam kernel
   const float* frames = static_cast<const float*>(h->ws_encproj.p);
+  // "inputs_complete" (online chunks that follow each other, 128 < B <= 4 * (SMs - 20) so that the merges still are one wave): the
+  // raw frames are projected on the low-priority side stream, which is not ordered behind the handle's stream, into one of two
+  // buffers taken in turns, and the persistent kernel leaves 20 SMs free - so the projection of chunk c+1 runs under the search
+  // of chunk c (cfg3: 19 of the 114 us per chunk)
+  const int cap_sms = h->sm_count - 20;
+  const bool ahead = !frames_ready && enc_is_raw && h->opt_inputs_complete != 0 && t_begin == 0 && encproj_tc_supported(h) &&
+                     h->cfg.encoder_dim > 0 && h->enc_w != nullptr && B > 128 && B <= 4 * cap_sms && !h->profile_on;
+  if (ahead) {
+    if (h->la_stream == nullptr) K2B_TRY(lookahead_init(h));
+    const int X = (int)(h->la_turn++ & 1u);
+    DevBuf& buf = h->ws_encproj_la[X];
+    const size_t need = sizeof(float) * (size_t)B * T * J;
+    if (need > buf.bytes) {
+      K2B_CUDA(h, cudaStreamSynchronize(h->la_stream));
+      K2B_TRY(ensure(h, buf, need));
+      h->la_done_valid[X] = false;
+    }
+    const bool cold = !h->enc_ready;
+    K2B_TRY(ensure_encproj_assets(h));
+    if (cold) K2B_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->la_done_valid[X]) K2B_CUDA(h, cudaStreamWaitEvent(h->la_stream, h->la_ev_done[X], 0));
+    if (h->la_mark_valid) K2B_CUDA(h, cudaStreamWaitEvent(h->la_stream, h->la_ev_mark, 0));
+    cudaStream_t keep = h->stream;
+    h->stream = h->la_stream;
+    const int32_t st = encoder_proj_tc(h, enc, B * T, static_cast<float*>(buf.p), false);
+    h->stream = keep;
+    K2B_TRY(st);
+    K2B_CUDA(h, cudaEventRecord(h->la_ev_a, h->la_stream));
+    K2B_CUDA(h, cudaStreamWaitEvent(h->stream, h->la_ev_a, 0));
+    K2B_TRY(ensure(h, h->ws_misc, sizeof(float) * (size_t)B));
+    h->mega_grid_cap = cap_sms;
+    h->la_mark_arm = true;
+    const int32_t sb = beam_dev(h, static_cast<const float*>(buf.p), B, T, 1, tokens, ts, n_out, static_cast<float*>(h->ws_misc.p), cap,
+                                extra_mask, hyp_inout, true, 0, 0, false, 0);
+    h->mega_grid_cap = 0;
+    h->la_mark_arm = false;
+    K2B_TRY(sb);
+    K2B_CUDA(h, cudaEventRecord(h->la_ev_done[X], h->stream));
+    h->la_done_valid[X] = true;
+    return K2B_OK;
+  }
   if (!frames_ready) K2B_TRY(frames_for_search(h, enc, enc_is_raw, B, T, &frames));
   else if (!enc_is_raw) frames = enc;
   K2B_TRY(ensure(h, h->ws_misc, sizeof(float) * (size_t)B));
@@ -1091,6 +1148,7 @@ int32_t k2b_greedy_offline_dev(k2b_handle* h, const float* enc, int32_t enc_is_r
 int32_t k2b_greedy_offline(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t T, int32_t mode,
                            int64_t* tokens, int32_t* ts, int32_t* n_out, int32_t cap) {
   K2B_TRY(enter(h));
+  StagedInputGuard staged_guard(h);
   LensGuard lens_guard(h);
   K2B_TRY(need_weights(h));
   K2B_TRY(check_search_args(h, enc, B, T, cap, tokens, ts, n_out, "k2b_greedy_offline"));
@@ -1134,6 +1192,7 @@ int32_t k2b_greedy_online_chunk_dev(k2b_handle* h, const float* enc, int32_t enc
 int32_t k2b_greedy_online_chunk(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t Tc,
                                 int64_t* hyp_inout, int64_t* tokens, int32_t* ts, int32_t* n_out, int32_t cap) {
   K2B_TRY(enter(h));
+  StagedInputGuard staged_guard(h);
   K2B_TRY(need_weights(h));
   K2B_TRY(check_search_args(h, enc, B, Tc, cap, tokens, ts, n_out, "k2b_greedy_online_chunk"));
   if (B > 0 && hyp_inout == nullptr) return fail(h, K2B_ERR_INVALID, "k2b_greedy_online_chunk: hyp_inout is NULL");
@@ -1178,6 +1237,7 @@ int32_t k2b_modified_beam_search_dev(k2b_handle* h, const float* enc, int32_t en
 int32_t k2b_modified_beam_search(k2b_handle* h, const float* enc, int32_t enc_is_raw, int32_t B, int32_t T, int32_t K,
                                  int64_t* tokens, int32_t* ts, int32_t* n_out, float* score, int32_t cap) {
   K2B_TRY(enter(h));
+  StagedInputGuard staged_guard(h);
   LensGuard lens_guard(h);
   K2B_TRY(need_weights(h));
   K2B_TRY(check_search_args(h, enc, B, T, cap, tokens, ts, n_out, "k2b_modified_beam_search"));
@@ -1312,6 +1372,7 @@ int32_t k2b_modified_beam_search_online_chunk(k2b_handle* h, const float* enc, i
                                               const int32_t* slots, int64_t* hyp_out, int64_t* tokens, int32_t* ts,
                                               int32_t* n_out, float* score, int32_t cap) {
   K2B_TRY(enter(h));
+  StagedInputGuard staged_guard(h);
   K2B_TRY(need_weights(h));
   if (B < 0 || Tc < 0) return fail(h, K2B_ERR_INVALID, "k2b_modified_beam_search_online_chunk: negative B or Tc");
   if (B == 0) return K2B_OK;

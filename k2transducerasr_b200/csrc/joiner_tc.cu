@@ -523,7 +523,9 @@ int32_t launch_bn(k2b_handle* h, const JArgs& a) {
   const int tiles = a.ntm * a.ntn;
   // MEGA: CTAs beyond the tile count still merge their share of the streams
   const int want = MEGA && a.B > tiles ? a.B : tiles;
-  const int grid = want < h->sm_count ? want : h->sm_count;
+  // (a caller that projects the next chunk's frames on a side stream meanwhile leaves SMs free: mega_grid_cap)
+  const int sms = MEGA && h->mega_grid_cap > 0 && h->mega_grid_cap >= tiles && h->mega_grid_cap < h->sm_count ? h->mega_grid_cap : h->sm_count;
+  const int grid = want < sms ? want : sms;
   if (MEGA) {
     // every CTA waits for counters other CTAs publish: all of them must be resident at once (cooperative launch checks that)
     cudaLaunchConfig_t cfg = {};
@@ -532,6 +534,10 @@ int32_t launch_bn(k2b_handle* h, const JArgs& a) {
     at[0].id = cudaLaunchAttributeCooperative;
     at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
+    if (h->la_mark_arm) {
+      K2B_CUDA(h, cudaEventRecord(h->la_ev_mark, h->stream));
+      h->la_mark_valid = true;
+    }
     const cudaError_t e = cudaLaunchKernelEx(&cfg, joiner_topk_kernel<KK, MEGA, kEpiWarps, BN>, a);
     if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) {
       cudaGetLastError();                 // not all CTAs can be resident (SMs taken by another context): per-frame launches instead

@@ -104,6 +104,12 @@ struct k2b_handle {
   bool la_done_valid[2] = {false, false};
   unsigned la_turn = 0;
   k2b::DevBuf ws_encproj_la[2];
+  // recorded on the handle's stream right in front of the search kernel of a look-ahead call: the NEXT call's side-stream work waits
+  // for it, so that its low-priority CTAs do not take the SMs in the gap before that search is launched (they would have to
+  // drain first: up to one GEMM tile, ~20 us, per launch)
+  cudaEvent_t la_ev_mark = nullptr;
+  bool la_mark_valid = false, la_mark_arm = false;
+  int mega_grid_cap = 0;                  // > 0: the persistent beam kernel of the current call takes at most this many SMs
   int* la_flags = nullptr;                // [kLaFlags] "time chunk c is projected" epochs, polled by the running cluster kernel
   int la_epoch = 0;
   int* dev_status = nullptr;      // [4] error flags written by the tcgen05 kernels (mbarrier time-outs)

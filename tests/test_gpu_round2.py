@@ -87,6 +87,43 @@ def test_parity_full_cfg3_online_512_streams_32_chunks(built_lib):
     h.close()
 
 
+def test_online_chunks_projected_ahead_on_a_side_stream(built_lib):
+    """cfg3 shape through the device-pointer entry with "inputs_complete": the encoder_proj of chunk c+1 runs on a side stream
+    under the persistent search of chunk c (which leaves 20 SMs free), projected frames in two buffers taken in turns. Chunks
+    enqueued back to back without a host synchronisation must give what the stream-ordered form gives, bit for bit - also with the
+    host-pointer entry (whose staged input is NOT complete at call time) in between."""
+    cfg, m, w, raw = cfg_setup("cfg3")
+    h = make(cfg.dims, w)
+    B, Tc, C = cfg.streams, cfg.frames, 10
+    chunks = [torch.from_numpy(np.ascontiguousarray(raw[:, Tc * c:Tc * c + Tc])).cuda() for c in range(C)]
+    outs = {}
+    for complete in (0, 1):
+        h.set_option("inputs_complete", complete)
+        hyp = torch.zeros((B, 2), dtype=torch.int64, device="cuda")
+        tok = torch.zeros((C, B, Tc), dtype=torch.int64, device="cuda"); ts = torch.zeros((C, B, Tc), dtype=torch.int32, device="cuda")
+        n = torch.zeros((C, B), dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        for c in range(C):
+            if c == 5:        # a host-pointer chunk in the middle (same frames, host Hyp round trip)
+                hh = hyp.cpu().numpy()
+                t5, s5, hh = h.greedy_online_chunk(np.ascontiguousarray(raw[:, Tc * c:Tc * c + Tc]), hh, enc_is_raw=True)
+                hyp.copy_(torch.from_numpy(hh))
+                for b in range(B):
+                    n[c, b] = len(t5[b])
+                    if t5[b]:
+                        tok[c, b, :len(t5[b])] = torch.tensor(t5[b]); ts[c, b, :len(t5[b])] = torch.tensor(s5[b], dtype=torch.int32)
+                continue
+            h.call("k2b_greedy_online_chunk_dev", chunks[c], 1, B, Tc, hyp, tok[c], ts[c], n[c], Tc)
+        h.sync()
+        outs[complete] = (tok, ts, n, hyp)
+    h.set_option("inputs_complete", 0)
+    a, b = outs[0], outs[1]
+    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]) and int(a[2].sum()) > 0
+    mask = torch.arange(Tc, device="cuda")[None, None, :] < a[2][:, :, None]
+    assert torch.equal(a[0][mask], b[0][mask]) and torch.equal(a[1][mask], b[1][mask])
+    h.close()
+
+
 def test_parity_full_cfg1_single_stream(built_lib):
     """cfg1: one utterance of 250 frames, offline single-stream greedy (the reference's own CPU-runnable case)."""
     cfg, m, w, raw = cfg_setup("cfg1")
