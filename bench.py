@@ -453,7 +453,7 @@ def run_ours(args, cfg):
     # the device-resident batches exist before the first timed call, which is what this option promises: the library may project
     # batch i+1's frames on a side stream under batch i's search instead of ordering that behind the handle's stream
     h.set_option("inputs_complete", args.inputs_complete)
-    for env, opt in (("K2B_DEV_CHUNK_SHIFT", "dev_chunk_shift"), ("K2B_DEV_CHUNKS", "dev_chunks")):     # experiments
+    for env, opt in (("K2B_DEV_CHUNK_FRAMES", "dev_chunk_frames"), ("K2B_DEV_CHUNKS", "dev_chunks")):     # experiments
         if os.environ.get(env):
             h.set_option(opt, int(os.environ[env]))
 

@@ -122,7 +122,7 @@ K2B_API int32_t k2b_sync(k2b_handle* h);
  *   "copy_threads" -1..64      host threads that stage PAGEABLE inputs into the library's page-locked bounce buffers (-1 = a quarter of
  *                              the host's threads, 2..8; 0 = the calling thread copies). Page-locked inputs need none.
  *   "no_mega", "unfused_step", "greedy_persistent" (-1 auto / 0 / 1), "pair", "prof_which", "cluster_timing" (0 = off),
- *   "wh_tmem_kb" (-1 auto / 0), "single_greedy" (0 / 1), "dev_chunks" (-1 auto / 1 / 2 / 3), "dev_chunk_shift" (3..10), "tagged_records" (0 / 1), "ctc_one_kernel" (-1 by input size / 0 / 1):
+ *   "wh_tmem_kb" (-1 auto / 0), "single_greedy" (0 / 1), "dev_chunks" (-1 auto / 1 / 2 / 3), "dev_chunk_frames" (0 auto / 2..4096), "tagged_records" (0 / 1), "ctc_one_kernel" (-1 by input size / 0 / 1):
  *                              comparison switches between engines that must give identical results.        */
 K2B_API int32_t k2b_set_option(k2b_handle* h, const char* name, int32_t value);
 /* "decoder_table_bytes", "decoder_table_build_ms", "decoder_table_state" (0 not built, 1 built, -1 does not fit).               */

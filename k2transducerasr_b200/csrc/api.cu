@@ -156,8 +156,26 @@ static int32_t lookahead_init(k2b_handle* h) {
   K2B_CUDA(h, cudaMemset(h->la_flags, 0, sizeof(int) * kLaFlags));
   return K2B_OK;
 }
+// Frames per time chunk: the chunk's GEMM runs on the F SMs the search leaves free, in waves of F tiles of 128 rows x 256 columns,
+// so a chunk should be a whole number of waves (cfg2: 25 frames = 100 tiles = 5 waves of 20; 32 frames would be 6.4 -> 7 waves)
+static int chunk_frames(const k2b_handle* h, int B, int T, int K) {
+  if (h->opt_la_frames > 0) return h->opt_la_frames;
+  const int F = h->sm_count - cluster_grid_ctas(h, B, K), ntn = (h->cfg.joiner_dim + 255) / 256;
+  int best = 32;
+  double best_cost = 1e30;
+  for (int L = 16; L <= 48; ++L) {
+    const int tiles = (int)(((long long)B * L + 127) / 128) * ntn, waves = (tiles + F - 1) / F;
+    const int rem = T % L, rem_tiles = (int)(((long long)B * rem + 127) / 128) * ntn;
+    const int nfull = T / L;
+    const double cost = ((double)nfull * (waves + 0.3) + (rem ? (rem_tiles + F - 1) / F + 0.3 : 0.0)) / T;   // waves per frame
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = L; }
+  }
+  return best;
+}
 static bool flagged_search_possible(const k2b_handle* h, int B, int T, int K) {
-  return cluster_grid_ctas(h, B, K) + 16 <= h->sm_count && ((T + (1 << h->opt_la_shift) - 1) >> h->opt_la_shift) <= kLaFlags;
+  if (cluster_grid_ctas(h, B, K) + 16 > h->sm_count) return false;
+  const int L = chunk_frames(h, B, T, K);
+  return (T + L - 1) / L <= kLaFlags;
 }
 static int32_t beam_cluster_flagged(k2b_handle* h, const float* enc, int B, int T, int K, int64_t* tokens, int32_t* ts, int32_t* n_out,
                                     float* score, int cap, int extra_mask) {
@@ -194,7 +212,7 @@ static int32_t beam_cluster_flagged(k2b_handle* h, const float* enc, int B, int 
     K2B_CUDA(h, cudaStreamWaitEvent(h->la_stream, h->la_ev_mark, 0));
   }
   if (h->la_done_valid[X]) K2B_CUDA(h, cudaStreamWaitEvent(h->la_stream, h->la_ev_done[X], 0));
-  const int kLaShift = h->opt_la_shift, L = 1 << kLaShift;
+  const int L = chunk_frames(h, B, T, K);
   for (int c = 0, t0 = 0; t0 < T; t0 += L, ++c) {
     const int tc = T - t0 < L ? T - t0 : L;
     cudaStream_t keep = h->stream;
@@ -212,7 +230,7 @@ static int32_t beam_cluster_flagged(k2b_handle* h, const float* enc, int B, int 
   K2B_CUDA(h, cudaEventRecord(h->la_ev_mark, h->stream));
   h->la_mark_valid = true;
   K2B_TRY(beam_cluster_dev(h, encE, B, T, K, bp, fin_lp, fin_len, fin_nlive, extra_mask, nullptr, nullptr, 0, 0, 0, nullptr, nullptr,
-                           need_lp, h->la_flags, epoch, kLaShift));
+                           need_lp, h->la_flags, epoch, L));
   K2B_CUDA(h, cudaEventRecord(h->la_ev_done[X], h->stream));
   h->la_done_valid[X] = true;
   K2B_TRY(gather_join(h));                 // the back-trace is the first kernel that writes the caller's result buffers
@@ -589,7 +607,7 @@ int32_t k2b_set_option(k2b_handle* h, const char* name, int32_t value) {
   else if (n == "async_d2h") h->opt_async_d2h = value;
   else if (n == "async_gather") h->opt_async_gather = value;
   else if (n == "inputs_complete") h->opt_inputs_complete = value;
-  else if (n == "dev_chunk_shift") { if (value < 3 || value > 10) return fail(h, K2B_ERR_INVALID, "dev_chunk_shift: 3 .. 10"); h->opt_la_shift = value; }
+  else if (n == "dev_chunk_frames") { if (value < 0 || value > 4096 || value == 1) return fail(h, K2B_ERR_INVALID, "dev_chunk_frames: 0 (auto), 2 .. 4096"); h->opt_la_frames = value; }
   else if (n == "copy_threads") {
     if (value < -1 || value > 64) return fail(h, K2B_ERR_INVALID, "copy_threads: -1 (auto) .. 64");
     if (value != h->opt_copy_threads) {                        // the pool is rebuilt with the new size by the next pageable copy

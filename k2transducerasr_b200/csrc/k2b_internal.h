@@ -135,7 +135,7 @@ struct k2b_handle {
   k2b::HostStage* host_stage = nullptr;   // page-locked bounce buffers + copy threads for pageable inputs (host_stage.cu)
   int max_sym_per_frame = 1;              // k2b_set_option("max_sym_per_frame"): ref OfflineRecognizer.cs:19 fixes it to 1
   // engine switches (k2b_set_option; the K2B_* environment variables only give their initial values at k2b_create)
-  int opt_la_shift = 5;                   // log2 of the frames per time chunk of the flagged device-pointer search
+  int opt_la_frames = 0;                  // frames per time chunk of the polling device-pointer search (0 = chosen per call)
   int opt_inputs_complete = 0;            // 1: frames handed to _dev calls are complete in memory at call time (not merely stream-ordered)
   int opt_async_gather = 0;               // 1: k2b_gather_results_nccl runs on a side stream (k2b_gather_join / k2b_sync order behind it)
   int opt_copy_threads = -1;              // host threads staging pageable inputs (-1: a quarter of the host's, 2 .. 8)
@@ -284,7 +284,7 @@ int32_t exp2x_frames_chunk(k2b_handle* h, const float* in, float* out, int B, in
 int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, int32_t* bp, float* fin_lp, int32_t* fin_len,
                          int32_t* fin_nlive, int extra_mask, const int64_t* hyp_in, int64_t* hyp_out, int t0 = 0, int Ttot = 0,
                          int resume = 0, int32_t* io_ctx = nullptr, unsigned long long* io_hash = nullptr, bool need_lp = true,
-                         const int* ready = nullptr, int ready_epoch = 0, int ready_shift = 0);
+                         const int* ready = nullptr, int ready_epoch = 0, int ready_len = 0);
 int cluster_grid_ctas(const k2b_handle* h, int B, int K);            // CTAs of one cluster-kernel launch (all resident at once or not)
 int32_t cluster_set_ready(k2b_handle* h, int* flag, int epoch);      // on h->stream: *flag = epoch, released at device scope
 int32_t cluster_status(k2b_handle* h);

@@ -80,13 +80,13 @@ struct ClusterArgs {
   const float* cg_delta;    // [S,V]
   int32_t* io_cst;
   // frames that arrive while the kernel runs (the encoder_proj GEMMs of later time chunks are on a side stream): frames
-  // [c << ready_shift, (c + 1) << ready_shift) may be read once ready[c] has reached ready_epoch; null = all frames are there.
+  // [c * ready_len, (c + 1) * ready_len) may be read once ready[c] has reached ready_epoch; null = all frames are there.
   // The chunk of frames t0 and t0 + 1 must be complete before the launch. The MMA warp holds back the commit of step t until the
   // chunk of frame t + 2 is there: the worker warps load frame t + 2 (one step ahead of its use) only behind that commit, so
   // their code is the same with and without flags (a wait in the workers' own loop cost 80 us per 250-frame launch - the
   // compiler split the loop -, whatever the kind of load).
   const int* ready;
-  int ready_epoch, ready_shift;
+  int ready_epoch, ready_len;
 };
 
 // polled by the MMA warp (all lanes, one address), bounded like the mbarrier waits
@@ -498,6 +498,8 @@ __global__ void __maxnreg__(K2B_CLUSTER_MAXREG) cluster_beam_kernel(const Cluste
     const uint32_t x_lo0 = ((smem_u32(xop) & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t el = elect_one();
     if (!PAIR || prank == 0) {
+      // local index of the first frame of the next time chunk (a.t0 + that is a multiple of ready_len), or never
+      int next_ready = a.ready != nullptr ? a.ready_len - a.t0 % a.ready_len : 0x7fffffff;
       for (int t = 0; t < T; ++t) {
         uint32_t acc = 0;
         if constexpr (NTC >= 0) {
@@ -545,8 +547,9 @@ __global__ void __maxnreg__(K2B_CLUSTER_MAXREG) cluster_beam_kernel(const Cluste
             }
           }
         }
-        if (a.ready != nullptr && t + 2 < T && ((a.t0 + t + 2) & ((1 << a.ready_shift) - 1)) == 0) {
-          if (!wait_frames_ready(a.ready + ((a.t0 + t + 2) >> a.ready_shift), a.ready_epoch)) ok = false;
+        if (t + 2 == next_ready) {          // frame t + 2 is the first of a time chunk that may still be on its way
+          if (next_ready < T && !wait_frames_ready(a.ready + (a.t0 + next_ready) / a.ready_len, a.ready_epoch)) ok = false;
+          next_ready += a.ready_len;
         }
         if (PAIR) umma2_commit_e(&bar_mma, (uint16_t)(3u << (rank & ~1u)), el);
         else umma_commit_e(&bar_mma, el);
@@ -1078,14 +1081,14 @@ int32_t exp2x_frames(k2b_handle* h, const float* in, float* out, size_t n) {
 int32_t beam_cluster_dev(k2b_handle* h, const float* encE, int B, int T, int K, int32_t* bp, float* fin_lp, int32_t* fin_len,
                          int32_t* fin_nlive, int extra_mask, const int64_t* hyp_in, int64_t* hyp_out, int t0, int Ttot, int resume,
                          int32_t* io_ctx, unsigned long long* io_hash, bool need_lp, const int* ready, int ready_epoch,
-                         int ready_shift) {
+                         int ready_len) {
   const k2b_config& c = h->cfg;
   const int V = c.vocab_size, J = c.joiner_dim, CS = (V + 127) / 128;
   const int S = kNH / K;
   const int nclusters = (B + S - 1) / S;
   int* status = h->dev_status;
   ClusterArgs a;
-  a.ready = ready; a.ready_epoch = ready_epoch; a.ready_shift = ready_shift;
+  a.ready = ready; a.ready_epoch = ready_epoch; a.ready_len = ready_len > 0 ? ready_len : 1;
   a.encE = encE; a.dec_tab = h->dec_tab; a.wo_hi_img = h->wo_hi_img; a.wo_lo = h->wo_lo; a.bias = h->bias_pad;
   a.B = B; a.T = T; a.K = K; a.V = V; a.J = J; a.S = S; a.CS = CS; a.blank = c.blank_id; a.unk = c.unk_id;
   a.x3 = c.precision == K2B_PREC_BF16X3 ? 1 : 0;

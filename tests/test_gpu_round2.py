@@ -603,12 +603,13 @@ def test_search_polling_for_frames_projected_on_a_side_stream(built_lib):
         torch.cuda.synchronize()
         h.set_option("inputs_complete", 0); h.set_option("dev_chunks", 1)
         want = run(raws, T, lens)
-        for complete in (0, 1):
+        for complete, L in ((0, 32), (1, 32), (1, 7), (0, 0), (1, 0)):          # L = 0: chosen by the library (whole GEMM waves)
             h.set_option("dev_chunks", 3 if complete else -1); h.set_option("inputs_complete", complete)
+            h.set_option("dev_chunk_frames", L)
             n0 = h.launch_count()
             got = run(raws, T, lens)
-            # per call: one GEMM + one flag kernel per 32-frame chunk, ONE search launch, the back-trace
-            assert h.launch_count() - n0 == len(raws) * (2 * ((T + 31) // 32) + 2), (h.launch_count() - n0, T)
+            # per call: one GEMM + one flag kernel per chunk of L frames, ONE search launch, the back-trace
+            assert L == 0 or h.launch_count() - n0 == len(raws) * (2 * ((T + L - 1) // L) + 2), (h.launch_count() - n0, T, L)
             # another engine and a host-pointer call between such calls
             g1 = run(raws[:1], T, lens)
             h.greedy_offline(synth.make_frames(4, 24, MID.encoder_dim, 1), 1)
@@ -616,7 +617,8 @@ def test_search_polling_for_frames_projected_on_a_side_stream(built_lib):
             g2 = run(raws[1:3], T, lens)
             for a, b in zip(want + want[:3], got + g1 + g2):
                 for x, y in zip(a, b):
-                    assert torch.equal(x, y), (T, ragged, complete)
+                    assert torch.equal(x, y), (T, ragged, complete, L)
+        h.set_option("dev_chunk_frames", 0)
     h.set_option("inputs_complete", 0)
     h.close()
 
