@@ -12,8 +12,9 @@ the timed region of `value` ends behind the last one).
     torchrun ... bench.py --gpus N ...      (one rank per GPU)
 
 `value`   : frames/s with the batch already resident in HBM (device-pointer entry points), the D2H of every step's results included
-            (SURVEY.md section 8d's definition of the metric): one copy per step on a copy stream, under the next step's search,
-            two result buffers written in turns; the timed region ends behind the last copy.
+            (SURVEY.md section 8d's definition of the metric): one copy per step - on a copy stream under the next step's search when
+            there is one rank (two result buffers written in turns; the timed region ends behind the last copy), on the launch
+            stream when there are several.
 `e2e`     : the same metric through the host-pointer C-ABI call a P/Invoke shim makes, from page-locked host memory, H2D and D2H
             copies inside the timed region. Beside it (extra keys, same unit): `e2e_pageable` (what a plain managed array costs),
             `e2e_projected` (the reference seam's own payload, already projected [B,T,J] frames), `e2e_async` (results of batch i
@@ -288,6 +289,7 @@ class Work:
                     buf[n_tok + n_ts:n_tok + n_ts + n_n].view(torch.int32).view(C, B), buf[n_tok + n_ts + n_n:].view(torch.float32))
         self.d_views = [views(b) for b in self.d_pack]
         self.last = 0                                         # the buffer the last step wrote
+        self.multi_rank = int(os.environ.get("WORLD_SIZE", "1")) > 1
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.ev_written = [torch.cuda.Event() for _ in range(2)]
         self.ev_copied = [None, None]
@@ -362,6 +364,11 @@ class Work:
     def results_to_host(self):
         """Asynchronous D2H of the step's results (one copy) into page-locked memory, on a copy stream behind the step."""
         torch, k = self.torch, self.last
+        # with more than one rank the copy stays on the launch stream: beside the side-stream all-gather of the same buffers a
+        # copy-stream D2H made the step SLOWER (two GPUs: 1.281 against 1.237 ms, eight: 1.52 against 1.27 ms per step)
+        if self.multi_rank or os.environ.get("K2B_BENCH_COPY_ON_LAUNCH_STREAM"):
+            self.p_pack.copy_(self.d_pack[k], non_blocking=True)
+            return
         self.ev_written[k].record(torch.cuda.current_stream())
         self.copy_stream.wait_event(self.ev_written[k])
         with torch.cuda.stream(self.copy_stream):
